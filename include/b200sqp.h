@@ -1,0 +1,195 @@
+/*
+ * b200sqp.h -- C ABI of libb200sqp.so: the batched, device-resident Levenberg-Marquardt / SQP inner loop for
+ * control_box_rst's hypergraph-structured direct-transcription OCPs on NVIDIA B200 (sm_100a).
+ *
+ * The reference (rst-tu-dortmund/control_box_rst) has no C ABI: its plugin boundary is the C++ class
+ * corbo::NlpSolverInterface (src/optimization/include/corbo-optimization/solver/nlp_solver_interface.h:67-118).
+ * The entry points below are what a corbo::NlpSolverInterface subclass binds to (see
+ * control_box_rst_b200/adapter/solver_b200_lm.{h,cpp} and INTEGRATION.md); each one names the reference interface it
+ * replaces.  Plain pointers and sizes only; no C++/torch types.  All functions return 0 on success or a negative
+ * b200sqp_error; they never throw.  Host buffers are owned by the caller, device buffers by the library.  A handle owns
+ * one CUDA stream and is not thread-safe.
+ */
+#ifndef B200SQP_H_
+#define B200SQP_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define B200SQP_MAX_NX 16
+#define B200SQP_MAX_NU 8
+#define B200SQP_MAX_DYN_PARAMS 8
+
+typedef enum {
+    B200SQP_OK                = 0,
+    B200SQP_ERR_INVALID       = -1, /* bad argument / null pointer / inconsistent descriptor */
+    B200SQP_ERR_UNSUPPORTED   = -2, /* structure outside the closed functor registry -> corbo::SolverStatus::Error, no CPU fallback */
+    B200SQP_ERR_CUDA          = -3, /* CUDA runtime failure (b200sqp_last_error() has the text) */
+    B200SQP_ERR_NO_DEVICE     = -4, /* no sm_100 class device visible */
+    B200SQP_ERR_NOT_LSQ       = -5  /* problem is not in least-squares form (levenberg_marquardt_sparse.cpp:50-54) */
+} b200sqp_error;
+
+/* corbo::SolverStatus (src/optimization/include/corbo-optimization/types.h:30) */
+typedef enum { B200SQP_STATUS_CONVERGED = 0, B200SQP_STATUS_EARLY_TERMINATED = 1, B200SQP_STATUS_INFEASIBLE = 2, B200SQP_STATUS_ERROR = 3 } b200sqp_status;
+
+/* System dynamics registry: corbo::SystemDynamicsInterface::dynamics (src/systems/include/corbo-systems/system_dynamics_interface.h:121).
+ * 0..5 restate models of src/systems/include/corbo-systems/benchmark/nonlinear_benchmark_systems.h and linear_benchmark_systems.h;
+ * UNICYCLE and QUADROTOR do not exist in the reference and are defined by this project on both sides. */
+typedef enum {
+    B200SQP_DYN_VAN_DER_POL      = 0, /* nonlinear_benchmark_systems.h:52-60, params[0] = a */
+    B200SQP_DYN_DUFFING          = 1, /* nonlinear_benchmark_systems.h DuffingOscillator */
+    B200SQP_DYN_SIMPLE_PENDULUM  = 2, /* nonlinear_benchmark_systems.h SimplePendulum, params = m,l,g,rho */
+    B200SQP_DYN_CART_POLE        = 3, /* nonlinear_benchmark_systems.h:337-352, params = mc,mp,l,g */
+    B200SQP_DYN_DOUBLE_INTEGRATOR = 4, /* linear_benchmark_systems.h DoubleIntegratorDiscreteTime's continuous twin: x'' = u */
+    B200SQP_DYN_UNICYCLE         = 5, /* new: x' = v cos(th), y' = v sin(th), th' = w */
+    B200SQP_DYN_QUADROTOR        = 6  /* new: 12-state rigid-body quadrotor, params = m,g,Ixx,Iyy,Izz */
+} b200sqp_dynamics;
+
+/* Discretization grids (vertex sets + edge factories), src/optimal_control/.../discretization_grids/ */
+typedef enum {
+    B200SQP_GRID_FD_UNIFORM           = 0, /* FiniteDifferencesGrid: fixed x0, single fixed dt (finite_differences_grid.cpp:38-154) */
+    B200SQP_GRID_FD_NONUNIFORM_VARDT  = 1, /* NonUniformFiniteDifferencesVariableGrid: one free dt per interval (non_uniform_finite_differences_variable_grid.cpp:60) */
+    B200SQP_GRID_MULTIPLE_SHOOTING    = 2  /* MultipleShootingGrid, one control per interval (multiple_shooting_grid.cpp:38-197) */
+} b200sqp_grid;
+
+/* FiniteDifferencesCollocationInterface (src/numerics/include/corbo-numerics/finite_differences_collocation.h:119-241) */
+typedef enum { B200SQP_COLL_FORWARD = 0, B200SQP_COLL_BACKWARD = 1, B200SQP_COLL_MIDPOINT = 2, B200SQP_COLL_CRANK_NICOLSON = 3 } b200sqp_collocation;
+
+/* NumericalIntegratorExplicitInterface (src/numerics/include/corbo-numerics/explicit_integrators.h) */
+typedef enum { B200SQP_INT_EULER = 0, B200SQP_INT_RK4 = 1 } b200sqp_integrator;
+
+/* Stage cost registry (src/optimal_control/src/functions/) */
+typedef enum {
+    B200SQP_COST_NONE           = 0,
+    B200SQP_COST_QUADRATIC_LSQ  = 1, /* QuadraticFormCost(Q,R,integral=false,lsq=true), diagonal Q/R (quadratic_cost.cpp:100-184) */
+    B200SQP_COST_MINIMUM_TIME_LSQ = 2 /* MinimumTime(lsq=true) (minimum_time.h:49-78) */
+} b200sqp_stage_cost;
+
+/*
+ * One OCP structure shared by all instances of a batch.  It carries exactly what the hypergraph walk of a
+ * StructuredOptimalControlProblem yields (SURVEY.md section 8b "discovery gap"): grid kind and size, functor ids and their
+ * parameters, bounds, fixed masks.  Per-instance data (x0, references, the parameter vector) is set separately.
+ */
+typedef struct b200sqp_ocp {
+    int32_t grid;         /* b200sqp_grid */
+    int32_t dynamics;     /* b200sqp_dynamics */
+    int32_t collocation;  /* b200sqp_collocation (FD grids) */
+    int32_t integrator;   /* b200sqp_integrator (shooting grids) */
+    int32_t n_grid;       /* N: number of grid points (N-1 intervals), >= 2 */
+    int32_t nx, nu;       /* must match the dynamics id */
+    int32_t stage_cost;   /* b200sqp_stage_cost */
+    int32_t final_cost;   /* 0 none, 1 QuadraticFinalStateCost(Qf, lsq=true) diagonal (final_state_cost.cpp:73-90) */
+    int32_t zero_x_ref;   /* ReferenceTrajectoryInterface::isZero() of xref (quadratic_cost.cpp:107) */
+    int32_t zero_u_ref;   /* must be 1 with lsq control cost (the reference's non-zero-uref lsq branch returns a scalar, quadratic_cost.cpp:161) */
+    int32_t xf_fixed[B200SQP_MAX_NX]; /* FullDiscretizationGridBase::setXfFixed */
+    double dt_ref;        /* grid dt (fixed) or initial dt (variable grids) */
+    double dt_lb, dt_ub;  /* NonUniformFiniteDifferencesVariableGrid::setDtBounds; ignored for fixed-dt grids */
+    double dyn_params[B200SQP_MAX_DYN_PARAMS];
+    double q_diag[B200SQP_MAX_NX];  /* diagonal of Q  (stage state cost)   */
+    double r_diag[B200SQP_MAX_NU];  /* diagonal of R  (stage control cost) */
+    double qf_diag[B200SQP_MAX_NX]; /* diagonal of Qf (final state cost)   */
+    double x_lb[B200SQP_MAX_NX], x_ub[B200SQP_MAX_NX]; /* |bound| >= 2e30 (CORBO_INF_DBL, core/types.h:53) means unbounded */
+    double u_lb[B200SQP_MAX_NU], u_ub[B200SQP_MAX_NU];
+} b200sqp_ocp;
+
+/* LevenbergMarquardtSparse parameters (levenberg_marquardt_sparse.h:85-90,112-124); defaults 10 / 2,2,2 / 1,1,1 / 500,500,500 */
+typedef struct b200sqp_lm_options {
+    int32_t iterations;
+    double weight_eq, weight_ineq, weight_bounds;                      /* setPenaltyWeights */
+    double adapt_factor_eq, adapt_factor_ineq, adapt_factor_bounds;    /* setWeightAdapation */
+    double adapt_max_eq, adapt_max_ineq, adapt_max_bounds;
+} b200sqp_lm_options;
+
+/* Dimensions the reference reports through OptimizationProblemInterface (levenberg_marquardt_sparse.cpp:56-71) */
+typedef struct b200sqp_dims {
+    int32_t n_params;    /* getParameterDimension() */
+    int32_t m_lsq;       /* getLsqObjectiveDimension() */
+    int32_t m_eq;        /* getEqualityDimension() */
+    int32_t m_ineq;      /* getInequalityDimension() */
+    int32_t m_bounds;    /* finiteCombinedBoundsDimension() */
+    int32_t nnz_jacobian;      /* computeSparseJacobian*NNZ() summed (structural, explicit zeros included) */
+    int32_t nnz_hessian_upper; /* structural nnz of triu(J^T J) */
+    int32_t n_blocks, block_dim; /* block-tridiagonal view used on the device */
+    int64_t algorithmic_bytes_per_iteration; /* s*[2*(nnzJ+nnzH+nnzL+2m+2n)+4n], s=8 */
+} b200sqp_dims;
+
+typedef struct b200sqp_solver* b200sqp_handle;
+
+/* ---- lifetime ------------------------------------------------------------------------------------------------------ */
+/* NlpSolverInterface::initialize + the new_structure branch of LevenbergMarquardtSparse::solve (levenberg_marquardt_sparse.cpp:48-80):
+ * derives dimensions and index maps, allocates all device state for `batch` instances on CUDA device `device`. */
+int b200sqp_create(const b200sqp_ocp* ocp, int32_t batch, int32_t device, b200sqp_handle* out);
+/* NlpSolverInterface::clear + destruction */
+int b200sqp_destroy(b200sqp_handle h);
+const char* b200sqp_last_error(void);
+/* 1 if the library was built with the CUDA kernels and a usable device is present, else 0 (never a CPU fallback) */
+int b200sqp_device_available(void);
+
+/* ---- structure / indexing (bit-exact with the reference) --------------------------------------------------------------- */
+/* Host-only, needs no GPU: usable on a handle-less descriptor. */
+int b200sqp_dims_of(const b200sqp_ocp* ocp, b200sqp_dims* out);
+/* VertexSetInterface::computeVertexIndices (vertex_set.cpp:405-418) over FullDiscretizationGridBase::computeActiveVertices
+ * (full_discretization_grid_base.cpp:514-527): for every grid point k, the parameter index of x_k[0] / u_k[0] / dt_k, or -1 if fixed. */
+int b200sqp_vertex_indices(const b200sqp_ocp* ocp, int32_t* x_idx /*[N]*/, int32_t* u_idx /*[N-1]*/, int32_t* dt_idx /*[N-1]*/);
+/* OptimizationEdgeSet::computeEdgeIndices (edge_set.cpp:31-42,101-166): row offset inside its category of the state-cost,
+ * control-cost and dynamics edge of every interval; final-cost edge index in final_cost_idx (or -1). */
+int b200sqp_edge_indices(const b200sqp_ocp* ocp, int32_t* state_cost_idx /*[N-1]*/, int32_t* control_cost_idx /*[N-1]*/,
+                         int32_t* dt_cost_idx /*[2*(N-1)]*/, int32_t* dynamics_idx /*[N-1]*/, int32_t* final_cost_idx /*[1]*/);
+/* CSC pattern of computeCombinedSparseJacobian (hyper_graph_optimization_problem_edge_based.cpp:1480-1753), rows lsq->eq->ineq->bounds */
+int b200sqp_jacobian_pattern(const b200sqp_ocp* ocp, int32_t* col_ptr /*[n+1]*/, int32_t* row_idx /*[nnzJ]*/);
+
+/* ---- per-instance data ------------------------------------------------------------------------------------------------- */
+/* x0: [batch*nx] measured start states (FullDiscretizationGridBase::update :101); xref: [batch*nx] static state reference or NULL
+ * (then zero / xf = 0).  Host pointers. */
+int b200sqp_set_problem_data(b200sqp_handle h, const double* x0, const double* xref);
+/* FullDiscretizationGridBase::initializeSequences (full_discretization_grid_base.cpp:134-179): linear x0 -> xref interpolation,
+ * u = 0, dt = dt_ref, on the device. */
+int b200sqp_initialize_trajectories(b200sqp_handle h);
+/* Parameter vectors in the reference's own order (param index = vertex_idx + free component), [batch*n_params], host pointers. */
+int b200sqp_set_params(b200sqp_handle h, const double* params);
+int b200sqp_get_params(b200sqp_handle h, double* params);
+/* FullDiscretizationGridBase::getFirstControlInput: u_0 of every instance, [batch*nu] */
+int b200sqp_get_first_controls(b200sqp_handle h, double* u0);
+
+/* ---- the hot path ------------------------------------------------------------------------------------------------------ */
+/* LevenbergMarquardtSparse::solve (levenberg_marquardt_sparse.cpp:44-220) for all instances, entirely on the device:
+ * opts->iterations outer passes each; new_run=1 resets the penalty weights, 0 adapts them (:83-86).
+ * status [batch] (b200sqp_status) and chi2 [batch] (*obj_value) are host pointers and may be NULL. */
+int b200sqp_solve(b200sqp_handle h, const b200sqp_lm_options* opts, int32_t new_run, int32_t* status, double* chi2);
+/* Same, but nothing crosses PCIe: results stay in HBM (b200sqp_get_* fetches them).  Asynchronous on the handle's stream. */
+int b200sqp_solve_async(b200sqp_handle h, const b200sqp_lm_options* opts, int32_t new_run);
+int b200sqp_synchronize(b200sqp_handle h);
+/* One call a controller makes per MPC step for a whole batch: H2D of x0 [batch*nx] (+xref), trajectory initialisation when
+ * `cold_start`, solve, D2H of the optimised parameter vectors [batch*n_params], chi2 and status.  Host pointers (pinned or not). */
+int b200sqp_step(b200sqp_handle h, const b200sqp_lm_options* opts, int32_t cold_start, const double* x0, const double* xref,
+                 double* params_out, double* chi2_out, int32_t* status_out);
+
+/* LevenbergMarquardtSparse::computeValues (:222-246) and ...EdgeBased::computeCombinedSparseJacobian (:1480-1753) at the current
+ * parameters, penalty weights applied: values [batch*m], jac_values [batch*nnzJ] in the CSC order of b200sqp_jacobian_pattern.
+ * Like the reference, evaluating the Jacobian perturbs the parameters in place (+d,-2d,+d; edge_interface.cpp:78-85). */
+int b200sqp_evaluate(b200sqp_handle h, double weight_eq, double weight_ineq, double weight_bounds, double* values, double* jac_values);
+
+/* Per-instance LM bookkeeping of the last solve: [batch] each, host pointers, any may be NULL.
+ * inner_passes = number of factorisations, rejects = rejected trial steps, relinearizations = Jacobian evaluations. */
+int b200sqp_get_statistics(b200sqp_handle h, int32_t* inner_passes, int32_t* rejects, int32_t* relinearizations, double* mu, double* rho);
+/* per-iteration chi2 trace of the last solve, [batch*(iterations+1)] (row = instance); entry 0 is the initial chi2 */
+int b200sqp_get_chi2_trace(b200sqp_handle h, double* trace, int32_t iterations);
+
+/* ---- measurement / multi-GPU plumbing ---------------------------------------------------------------------------------- */
+/* device time of the last solve (CUDA events on the handle's stream), milliseconds */
+int b200sqp_last_solve_ms(b200sqp_handle h, float* ms);
+/* number of kernel launches issued by this handle so far */
+int b200sqp_launch_count(b200sqp_handle h, int64_t* launches);
+/* raw device pointers for zero-copy interop (torch / NCCL all-gather of the stop-test residuals): chi2 [batch] doubles,
+ * status [batch] int32, x0 [batch*nx] doubles.  Valid until destroy. */
+int b200sqp_device_pointers(b200sqp_handle h, void** chi2, void** status, void** x0);
+/* make the handle launch on an external stream (e.g. torch's current stream); pass NULL to restore its own */
+int b200sqp_set_stream(b200sqp_handle h, void* cuda_stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B200SQP_H_ */

@@ -1,0 +1,183 @@
+"""TEST INFRASTRUCTURE ONLY -- ctypes bindings of the two CPU checkers.
+
+  * `Oracle`     oracle/libsqp_oracle.so   plain-C++ restatement of the reference algorithm (oracle/sqp_oracle.cpp)
+  * `Reference`  oracle/_ref/libcorbo_ref.so  the unmodified reference compiled from /root/reference (oracle/ref_driver.cpp)
+
+Both expose the same calls with the same argument meaning, prefixed `sqp_oracle_` / `corbo_ref_`.  Only tests/,
+__graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may import this module; the product
+(control_box_rst_b200/) never does.
+"""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+from control_box_rst_b200 import _abi as abi
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ORACLE_SO = os.path.join(HERE, "libsqp_oracle.so")
+REF_SO = os.path.join(HERE, "_ref", "libcorbo_ref.so")
+
+EV_JACOBIAN, EV_INCREMENT, EV_RESTORE, EV_DISCARD = 0, 1, 2, 3
+
+_dp = C.POINTER(C.c_double)
+_ip = C.POINTER(C.c_int32)
+
+
+def _d(a):
+    return None if a is None else a.ctypes.data_as(_dp)
+
+
+def _i(a):
+    return None if a is None else a.ctypes.data_as(_ip)
+
+
+def build_oracle():
+    subprocess.run(["make", "-s", "-C", HERE, "oracle"], check=True)
+
+
+def build_reference(reference_root="/root/reference"):
+    """Compile the unmodified reference where it lies (only possible where /root/reference exists)."""
+    if not os.path.isdir(reference_root):
+        return False
+    subprocess.run(["make", "-s", "-j8", "-C", HERE, "ref", "REF=" + reference_root], check=True)
+    return True
+
+
+class _Checker:
+    prefix = ""
+    path = ""
+
+    def __init__(self):
+        if not os.path.exists(self.path):
+            raise FileNotFoundError(self.path)
+        self.lib = C.CDLL(self.path)
+        p = self.prefix
+        self._dims = getattr(self.lib, p + "dims")
+        self._vertex_indices = getattr(self.lib, p + "vertex_indices")
+        self._edge_table = getattr(self.lib, p + "edge_table")
+        self._initial_params = getattr(self.lib, p + "initial_params")
+        self._evaluate = getattr(self.lib, p + "evaluate")
+        self._trace = getattr(self.lib, p + "trace")
+        self._solve_batch = getattr(self.lib, p + "solve_batch")
+        for f in (self._dims, self._vertex_indices, self._edge_table, self._initial_params, self._evaluate, self._trace, self._solve_batch):
+            f.restype = C.c_int
+
+    @classmethod
+    def available(cls):
+        return os.path.exists(cls.path)
+
+    def dims(self, ocp):
+        out = abi.Dims()
+        rc = self._dims(C.byref(ocp), C.byref(out))
+        if rc != 0:
+            raise RuntimeError(f"{self.prefix}dims failed: {rc}")
+        return out
+
+    def vertex_indices(self, ocp):
+        N = ocp.n_grid
+        x_idx = np.full(N, -2, np.int32)
+        u_idx = np.full(N - 1, -2, np.int32)
+        dt_idx = np.full(N - 1, -2, np.int32)
+        rc = self._vertex_indices(C.byref(ocp), _i(x_idx), _i(u_idx), _i(dt_idx))
+        if rc != 0:
+            raise RuntimeError(f"{self.prefix}vertex_indices failed: {rc}")
+        return x_idx, u_idx, dt_idx
+
+    def edge_table(self, ocp, category, max_edges=4096):
+        """rows: [dim, edge_idx, n_vertices, vertex_idx0..3] in creation order for category 0 lsq / 1 eq / 2 ineq"""
+        table = np.zeros((max_edges, 7), np.int32)
+        cnt = self._edge_table(C.byref(ocp), C.c_int(category), _i(table), C.c_int(max_edges))
+        if cnt < 0:
+            raise RuntimeError(f"{self.prefix}edge_table failed: {cnt}")
+        return table[:cnt].copy()
+
+    def initial_params(self, ocp, x0, xref=None):
+        n = self.dims(ocp).n_params
+        x0 = np.ascontiguousarray(x0, np.float64)
+        xref = None if xref is None else np.ascontiguousarray(xref, np.float64)
+        p = np.zeros(n)
+        rc = self._initial_params(C.byref(ocp), _d(x0), _d(xref), _d(p))
+        if rc != 0:
+            raise RuntimeError(f"{self.prefix}initial_params failed: {rc}")
+        return p
+
+    def evaluate(self, ocp, x0, xref=None, params=None, weights=(2.0, 2.0, 2.0), jacobian=True):
+        """-> values [m], J dense [m,n], stored-entry pattern [m,n] (bool), parameters after the in-place FD sweep [n]"""
+        dm = self.dims(ocp)
+        n, m = dm.n_params, dm.m
+        x0 = np.ascontiguousarray(x0, np.float64)
+        xref = None if xref is None else np.ascontiguousarray(xref, np.float64)
+        params = None if params is None else np.ascontiguousarray(params, np.float64)
+        values = np.zeros(m)
+        jac = np.zeros((m, n)) if jacobian else None
+        pat = np.zeros((m, n), np.uint8) if jacobian else None
+        after = np.zeros(n) if jacobian else None
+        rc = self._evaluate(C.byref(ocp), _d(x0), _d(xref), _d(params), C.c_double(weights[0]), C.c_double(weights[1]), C.c_double(weights[2]),
+                            _d(values), _d(jac), None if pat is None else pat.ctypes.data_as(C.POINTER(C.c_uint8)), _d(after))
+        if rc != 0:
+            raise RuntimeError(f"{self.prefix}evaluate failed: {rc}")
+        return values, jac, None if pat is None else pat.astype(bool), after
+
+    def trace(self, ocp, opts, x0, xref=None, params=None, max_events=4096):
+        """One instance with the event log: -> dict(params, chi2, status, events=[(type, chi2, vec)])"""
+        n = self.dims(ocp).n_params
+        x0 = np.ascontiguousarray(x0, np.float64)
+        xref = None if xref is None else np.ascontiguousarray(xref, np.float64)
+        params = None if params is None else np.ascontiguousarray(params, np.float64)
+        out = np.zeros(n)
+        chi2 = C.c_double(0)
+        status = C.c_int32(0)
+        ev_type = np.zeros(max_events, np.int32)
+        ev_chi2 = np.zeros(max_events)
+        ev_vec = np.zeros((max_events, n))
+        n_ev = C.c_int32(0)
+        rc = self._trace(C.byref(ocp), C.byref(opts), _d(x0), _d(xref), _d(params), _d(out), C.byref(chi2), C.byref(status), C.c_int(max_events),
+                         _i(ev_type), _d(ev_chi2), _d(ev_vec), C.byref(n_ev))
+        if rc != 0:
+            raise RuntimeError(f"{self.prefix}trace failed: {rc}")
+        k = min(n_ev.value, max_events)
+        return dict(params=out, chi2=chi2.value, status=status.value, n_events=n_ev.value,
+                    events=[(int(ev_type[i]), float(ev_chi2[i]), ev_vec[i].copy()) for i in range(k)])
+
+    def solve_batch(self, ocp, opts, x0, xref=None, params=None, threads=1):
+        """-> params [B,n], chi2 [B], status [B], seconds (wall, sum solve, sum prepare)"""
+        x0 = np.ascontiguousarray(x0, np.float64)
+        B = x0.shape[0]
+        n = self.dims(ocp).n_params
+        xref = None if xref is None else np.ascontiguousarray(xref, np.float64)
+        params = None if params is None else np.ascontiguousarray(params, np.float64)
+        out = np.zeros((B, n))
+        chi2 = np.zeros(B)
+        status = np.zeros(B, np.int32)
+        secs = np.zeros(3)
+        rc = self._solve_batch(C.byref(ocp), C.byref(opts), C.c_int(B), _d(x0), _d(xref), _d(params), _d(out), _d(chi2), _i(status),
+                               C.c_int(threads), _d(secs))
+        if rc != 0:
+            raise RuntimeError(f"{self.prefix}solve_batch failed: {rc}")
+        return out, chi2, status, secs
+
+
+class Oracle(_Checker):
+    prefix = "sqp_oracle_"
+    path = ORACLE_SO
+
+
+class Reference(_Checker):
+    prefix = "corbo_ref_"
+    path = REF_SO
+
+    def closed_loop(self, ocp, opts, x0, steps):
+        x0 = np.ascontiguousarray(x0, np.float64)
+        u = np.zeros((steps, ocp.nu))
+        x = np.zeros((steps + 1, ocp.nx))
+        f = self.lib.corbo_ref_closed_loop
+        f.restype = C.c_int
+        rc = f(C.byref(ocp), C.byref(opts), _d(x0), C.c_int(steps), _d(u), _d(x))
+        if rc != 0:
+            raise RuntimeError(f"corbo_ref_closed_loop failed: {rc}")
+        return u, x
+
+    def hardware_threads(self):
+        return int(self.lib.corbo_ref_hardware_threads())

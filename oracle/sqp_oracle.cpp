@@ -1,0 +1,1073 @@
+// TEST INFRASTRUCTURE ONLY -- not part of the shipped product, never linked into libb200sqp.so.
+//
+// CPU oracle: a plain-C++ restatement (no Eigen, no reference code) of the hot path of rst-tu-dortmund/control_box_rst that
+// BASELINE.json's north_star names -- the Levenberg-Marquardt / SQP inner loop on the hypergraph-structured OCP.  It keeps the
+// reference's object model (vertices, edges, per-edge central-difference Jacobians scattered into one combined Jacobian, the
+// LM loop with all its quirks) so that it can be read side by side with the reference; every function cites the file:line it
+// follows (paths relative to /root/reference/src).
+//
+// PARITY PINNING: this oracle is pinned against the UNMODIFIED reference compiled from /root/reference
+// (oracle/_ref/libcorbo_ref.so, built by oracle/Makefile) in tests/test_oracle_vs_reference.py, and against the committed
+// golden vectors tests/golden/*.npz that tests/golden/make_golden.py generated from that same compiled reference.
+//
+// Compiled with -ffp-contract=off and the same expression order as the reference so that the central-difference Jacobians carry
+// the same rounding noise (SURVEY.md "FD-noise parity").
+#include "sqp_oracle.h"
+
+#include <algorithm>
+#include <atomic>
+#include <chrono>
+#include <cmath>
+#include <cstring>
+#include <functional>
+#include <memory>
+#include <thread>
+#include <vector>
+
+namespace {
+
+constexpr double CORBO_INF = 2e30;  // core/include/corbo-core/types.h:53
+
+// ---------------------------------------------------------------------------------------------------------------------------
+// Hypergraph: vertices  (optimization/include/corbo-optimization/hyper_graph/vector_vertex.h:51-446, scalar_vertex.h:50-198)
+// ---------------------------------------------------------------------------------------------------------------------------
+struct Vertex
+{
+    std::vector<double> val, lb, ub;
+    std::vector<char> fixed;  // per component (PartiallyFixedVectorVertex); VectorVertex::setFixed sets all
+    int idx = -1;             // VertexInterface::getVertexIdx
+    std::vector<double> backup;
+
+    int dim() const { return (int)val.size(); }
+    int dimUnfixed() const
+    {
+        int c = 0;
+        for (char f : fixed) c += f ? 0 : 1;
+        return c;
+    }
+    bool isFixed() const { return dimUnfixed() == 0; }
+    bool finiteLb(int i) const { return lb[i] > -CORBO_INF; }  // vector_vertex.h:174-178
+    bool finiteUb(int i) const { return ub[i] < CORBO_INF; }   // vector_vertex.h:180-184
+};
+
+// Edges (optimization/include/corbo-optimization/hyper_graph/edge_interface.h, generic_edge.h:294-498)
+struct Edge
+{
+    int dim = 0;
+    int idx = -1;  // EdgeInterface::getEdgeIdx: row offset inside its category
+    std::vector<Vertex*> v;
+    std::function<void(double*)> values;  // BaseEdge::computeValues
+};
+
+struct Graph
+{
+    std::vector<std::unique_ptr<Vertex>> storage;
+    std::vector<Vertex*> active;  // VertexSetInterface::getActiveVertices
+    std::vector<Edge> lsq, eq, ineq;
+    // grid bookkeeping for index queries
+    std::vector<Vertex*> xs, us, dts;  // per grid point / interval
+    int n = 0, m_lsq = 0, m_eq = 0, m_ineq = 0, m_b = 0;
+
+    Vertex* add(int dim)
+    {
+        storage.emplace_back(new Vertex);
+        Vertex* p = storage.back().get();
+        p->val.assign(dim, 0.0);
+        p->lb.assign(dim, -CORBO_INF);
+        p->ub.assign(dim, CORBO_INF);
+        p->fixed.assign(dim, 0);
+        return p;
+    }
+};
+
+// VertexSetInterface::computeVertexIndices (optimization/src/hyper_graph/vertex_set.cpp:405-418)
+void computeVertexIndices(Graph& g)
+{
+    int idx = 0;
+    for (Vertex* v : g.active)
+    {
+        v->idx = idx;
+        idx += v->dimUnfixed();
+    }
+    g.n = idx;
+}
+
+// OptimizationEdgeSet::computeEdgeIndices (optimization/src/hyper_graph/edge_set.cpp:31-42,101-166): prefix sums per category
+void computeEdgeIndices(Graph& g)
+{
+    int i = 0;
+    for (Edge& e : g.lsq)
+    {
+        e.idx = i;
+        i += e.dim;
+    }
+    g.m_lsq = i;
+    i       = 0;
+    for (Edge& e : g.eq)
+    {
+        e.idx = i;
+        i += e.dim;
+    }
+    g.m_eq = i;
+    i      = 0;
+    for (Edge& e : g.ineq)
+    {
+        e.idx = i;
+        i += e.dim;
+    }
+    g.m_ineq = i;
+    // BaseHyperGraphOptimizationProblem::finiteCombinedBoundsDimension (hyper_graph_optimization_problem_base.cpp:249-261)
+    int mb = 0;
+    for (Vertex* v : g.active)
+        for (int c = 0; c < v->dim(); ++c)
+            if (!v->fixed[c] && (v->finiteLb(c) || v->finiteUb(c))) ++mb;
+    g.m_b = mb;
+}
+
+// ---------------------------------------------------------------------------------------------------------------------------
+// System dynamics  (systems/include/corbo-systems/benchmark/*.h; unicycle/quadrotor: oracle/ref_models.h)
+// ---------------------------------------------------------------------------------------------------------------------------
+using Dyn = std::function<void(const double* x, const double* u, double* f)>;
+
+Dyn makeDynamics(const b200sqp_ocp& d)
+{
+    const double* p = d.dyn_params;
+    switch (d.dynamics)
+    {
+        case B200SQP_DYN_VAN_DER_POL:  // nonlinear_benchmark_systems.h:52-60
+        {
+            const double a = p[0];
+            return [a](const double* x, const double* u, double* f) {
+                f[0] = x[1];
+                f[1] = -a * (x[0] * x[0] - 1) * x[1] - x[0] + u[0];
+            };
+        }
+        case B200SQP_DYN_DUFFING:  // nonlinear_benchmark_systems.h:108-117
+        {
+            const double damping = p[0], alpha = p[1], beta = p[2];
+            return [=](const double* x, const double* u, double* f) {
+                f[0] = x[1];
+                f[1] = -damping * x[1] - alpha * x[0] - beta * x[0] * x[0] * x[0] + u[0];
+            };
+        }
+        case B200SQP_DYN_SIMPLE_PENDULUM:  // nonlinear_benchmark_systems.h:207-216
+        {
+            const double m = p[0], l = p[1], g = p[2], rho = p[3];
+            return [=](const double* x, const double* u, double* f) {
+                f[0] = x[1];
+                f[1] = u[0] - rho / (m * l * l) * x[1] - g / l * std::sin(x[0]);
+            };
+        }
+        case B200SQP_DYN_CART_POLE:  // nonlinear_benchmark_systems.h:337-352 (mc, mp, l, g private defaults :390-394)
+        {
+            const double mc = 1.0, mp = 0.3, l = 0.5, g = 9.81;
+            return [=](const double* x, const double* u, double* f) {
+                double sin_phi_phidot_sq = std::sin(x[1]) * x[3] * x[3];
+                double denum             = mc + mp * (1 - std::pow(std::cos(x[1]), 2));
+                f[0]                     = x[2];
+                f[1]                     = x[3];
+                f[2]                     = (l * mp * sin_phi_phidot_sq + u[0] + mp * g * std::cos(x[1]) * std::sin(x[1])) / denum;
+                f[3] = -(l * mp * std::cos(x[1]) * sin_phi_phidot_sq + u[0] * std::cos(x[1]) + (mp + mc) * g * std::sin(x[1])) / (l * denum);
+            };
+        }
+        case B200SQP_DYN_DOUBLE_INTEGRATOR:  // linear_benchmark_systems.h:71-82 (SerialIntegratorSystem, dimension 2)
+        {
+            const double T = p[0];
+            return [T](const double* x, const double* u, double* f) {
+                f[0] = x[1];
+                f[1] = u[0] / T;
+            };
+        }
+        case B200SQP_DYN_UNICYCLE:  // oracle/ref_models.h Unicycle
+            return [](const double* x, const double* u, double* f) {
+                f[0] = u[0] * std::cos(x[2]);
+                f[1] = u[0] * std::sin(x[2]);
+                f[2] = u[1];
+            };
+        case B200SQP_DYN_QUADROTOR:  // oracle/ref_models.h Quadrotor
+        {
+            const double m = p[0], g = p[1], ixx = p[2], iyy = p[3], izz = p[4];
+            return [=](const double* x, const double* u, double* f) {
+                const double sphi = std::sin(x[3]), cphi = std::cos(x[3]);
+                const double sth = std::sin(x[4]), cth = std::cos(x[4]);
+                const double spsi = std::sin(x[5]), cpsi = std::cos(x[5]);
+                const double pp = x[9], q = x[10], r = x[11];
+                const double tm = u[0] / m;
+                f[0]            = x[6];
+                f[1]            = x[7];
+                f[2]            = x[8];
+                const double qr = q * sphi + r * cphi;
+                f[3]            = pp + qr * (sth / cth);
+                f[4]            = q * cphi - r * sphi;
+                f[5]            = qr / cth;
+                f[6]            = (cphi * sth * cpsi + sphi * spsi) * tm;
+                f[7]            = (cphi * sth * spsi - sphi * cpsi) * tm;
+                f[8]            = cphi * cth * tm - g;
+                f[9]            = (u[1] + (iyy - izz) * q * r) / ixx;
+                f[10]           = (u[2] + (izz - ixx) * pp * r) / iyy;
+                f[11]           = (u[3] + (ixx - iyy) * pp * q) / izz;
+            };
+        }
+    }
+    return {};
+}
+
+// FiniteDifferencesCollocationInterface::computeEqualityConstraint (numerics/include/corbo-numerics/finite_differences_collocation.h)
+void collocation(int kind, const Dyn& f, int nx, const double* x1, const double* u1, const double* x2, double dt, double* e)
+{
+    double f1[B200SQP_MAX_NX], xm[B200SQP_MAX_NX];
+    switch (kind)
+    {
+        case B200SQP_COLL_FORWARD:  // :119-136   e = f(x1,u1); e -= (x2-x1)/dt
+            f(x1, u1, e);
+            for (int i = 0; i < nx; ++i) e[i] -= (x2[i] - x1[i]) / dt;
+            break;
+        case B200SQP_COLL_BACKWARD:  // :153-170
+            f(x2, u1, e);
+            for (int i = 0; i < nx; ++i) e[i] -= (x2[i] - x1[i]) / dt;
+            break;
+        case B200SQP_COLL_MIDPOINT:  // :187-204
+            for (int i = 0; i < nx; ++i) xm[i] = 0.5 * (x1[i] + x2[i]);
+            f(xm, u1, e);
+            for (int i = 0; i < nx; ++i) e[i] -= (x2[i] - x1[i]) / dt;
+            break;
+        default:  // Crank-Nicolson :221-240   e = (x2-x1)/dt - 0.5*(f(x1,u1)+f(x2,u1))
+            f(x1, u1, f1);
+            f(x2, u1, e);
+            for (int i = 0; i < nx; ++i) e[i] = (x2[i] - x1[i]) / dt - 0.5 * (f1[i] + e[i]);
+            break;
+    }
+}
+
+// NumericalIntegratorExplicitInterface::computeEqualityConstraint = solveIVP - x2 (numerics/include/corbo-numerics/integrator_interface.h:217-222)
+void shooting(int kind, const Dyn& f, int nx, const double* x1, const double* u1, const double* x2, double dt, double* e)
+{
+    double k1[B200SQP_MAX_NX], k2[B200SQP_MAX_NX], k3[B200SQP_MAX_NX], k4[B200SQP_MAX_NX], xt[B200SQP_MAX_NX];
+    if (kind == B200SQP_INT_EULER)
+    {
+        // IntegratorExplicitEuler::solveIVP (explicit_integrators.h): x2 = x1 + dt * f(x1,u1), evaluated as f *= dt; f += x1
+        f(x1, u1, k1);
+        for (int i = 0; i < nx; ++i) e[i] = (x1[i] + dt * k1[i]) - x2[i];
+        return;
+    }
+    // IntegratorExplicitRungeKutta4::solveIVP (explicit_integrators.h:280-295)
+    f(x1, u1, k1);
+    for (int i = 0; i < nx; ++i) k1[i] *= dt;
+    for (int i = 0; i < nx; ++i) xt[i] = x1[i] + k1[i] / 2.0;
+    f(xt, u1, k2);
+    for (int i = 0; i < nx; ++i) k2[i] *= dt;
+    for (int i = 0; i < nx; ++i) xt[i] = x1[i] + k2[i] / 2.0;
+    f(xt, u1, k3);
+    for (int i = 0; i < nx; ++i) k3[i] *= dt;
+    for (int i = 0; i < nx; ++i) xt[i] = x1[i] + k3[i];
+    f(xt, u1, k4);
+    for (int i = 0; i < nx; ++i) k4[i] *= dt;
+    for (int i = 0; i < nx; ++i) e[i] = (x1[i] + (k1[i] + 2.0 * k2[i] + 2.0 * k3[i] + k4[i]) / 6.0) - x2[i];
+}
+
+// ---------------------------------------------------------------------------------------------------------------------------
+// Grids = vertex sets + edge factories
+// ---------------------------------------------------------------------------------------------------------------------------
+struct BuildInput
+{
+    const b200sqp_ocp* d;
+    const double* x0;
+    const double* xref;  // static reference (may be null -> zeros)
+};
+
+// NlpFunctions::getNonIntegralStageFunctionEdges (optimal_control/src/functions/nlp_functions.cpp:70-132) for the supported stage
+// costs: state term, control term, dt term (created TWICE, :91-107), in that order.
+void addStageCostEdges(Graph& g, const b200sqp_ocp& d, int k, Vertex* xk, Vertex* uk, Vertex* dtk, const std::vector<double>& xref, bool single_dt)
+{
+    const int nx = d.nx, nu = d.nu;
+    if (d.stage_cost == B200SQP_COST_QUADRATIC_LSQ)
+    {
+        // QuadraticFormCost::computeNonIntegralStateTerm, lsq + diagonal branch (optimal_control/src/functions/quadratic_cost.cpp:105-123)
+        std::vector<double> qs(nx), rs(nu);
+        for (int i = 0; i < nx; ++i) qs[i] = std::sqrt(d.q_diag[i]);  // setWeightQ: cwiseSqrt (:62)
+        for (int i = 0; i < nu; ++i) rs[i] = std::sqrt(d.r_diag[i]);
+        bool zero_ref = true;
+        for (double r : xref) zero_ref = zero_ref && (r == 0.0);  // StaticReference::isZero (core/reference_trajectory.h:123)
+        Edge ex;
+        ex.dim = nx;
+        ex.v   = {xk};
+        if (zero_ref)
+            ex.values = [xk, qs, nx](double* out) {
+                for (int i = 0; i < nx; ++i) out[i] = qs[i] * xk->val[i];
+            };
+        else
+            ex.values = [xk, qs, nx, xref](double* out) {
+                for (int i = 0; i < nx; ++i) out[i] = qs[i] * (xk->val[i] - xref[i]);
+            };
+        g.lsq.push_back(ex);
+        // computeNonIntegralControlTerm, lsq + zero uref + diagonal (:146-154)
+        Edge eu;
+        eu.dim    = nu;
+        eu.v      = {uk};
+        eu.values = [uk, rs, nu](double* out) {
+            for (int i = 0; i < nu; ++i) out[i] = rs[i] * uk->val[i];
+        };
+        g.lsq.push_back(eu);
+    }
+    else if (d.stage_cost == B200SQP_COST_MINIMUM_TIME_LSQ)
+    {
+        // MinimumTime (optimal_control/include/corbo-optimal-control/functions/minimum_time.h:49-78): dt-term dimension 1 if k==0 or
+        // !single_dt; weight sqrt(n-1) in lsq form; the dt edge is pushed twice by nlp_functions.cpp:91-107
+        if (k == 0 || !single_dt)
+        {
+            const double w = std::sqrt((double)(d.n_grid - 1));
+            for (int rep = 0; rep < 2; ++rep)
+            {
+                Edge et;
+                et.dim    = 1;
+                et.v      = {dtk};
+                et.values = [dtk, w](double* out) { out[0] = w * dtk->val[0]; };
+                g.lsq.push_back(et);
+            }
+        }
+    }
+}
+
+// QuadraticFinalStateCost::computeNonIntegralStateTerm, lsq + diagonal (optimal_control/src/functions/final_state_cost.cpp:73-90)
+void addFinalCostEdge(Graph& g, const b200sqp_ocp& d, Vertex* xf, const std::vector<double>& xref)
+{
+    if (d.final_cost != 1) return;
+    const int nx = d.nx;
+    std::vector<double> qs(nx);
+    for (int i = 0; i < nx; ++i) qs[i] = std::sqrt(d.qf_diag[i]);
+    bool zero_ref = true;
+    for (double r : xref) zero_ref = zero_ref && (r == 0.0);
+    Edge e;
+    e.dim = nx;
+    e.v   = {xf};
+    if (zero_ref)
+        e.values = [xf, qs, nx](double* out) {
+            for (int i = 0; i < nx; ++i) out[i] = qs[i] * xf->val[i];
+        };
+    else
+        e.values = [xf, qs, nx, xref](double* out) {
+            for (int i = 0; i < nx; ++i) out[i] = qs[i] * (xf->val[i] - xref[i]);
+        };
+    g.lsq.push_back(e);
+}
+
+// FullDiscretizationGridBase::initializeSequences (full_discretization_grid_base.cpp:134-179) -- same code in
+// NonUniformFullDiscretizationGridBase (non_uniform_full_discretization_grid_base.cpp:146-190) and ShootingGridBase
+// (shooting_grid_base.cpp:141-200): linear x0 -> xf interpolation, controls = uref (zero), first state fixed;
+// then createEdges of the three grids (finite_differences_grid.cpp:38-154, non_uniform_finite_differences_variable_grid.cpp:60-172,
+// multiple_shooting_grid.cpp:38-197), which share one per-interval pattern for the supported stage functions:
+//    [state cost(x_k), control cost(u_k), dt cost(dt_k) x2]  ->  lsq edges;  dynamics(x_k,u_k,x_{k+1},dt_k) -> equality edge;
+// final-state cost on xf if xf is not fully fixed.
+std::unique_ptr<Graph> buildGraph(const BuildInput& in)
+{
+    const b200sqp_ocp& d = *in.d;
+    const int nx = d.nx, nu = d.nu, N = d.n_grid;
+    if (N < 2 || nx < 1 || nx > B200SQP_MAX_NX || nu < 1 || nu > B200SQP_MAX_NU) return nullptr;
+    Dyn f = makeDynamics(d);
+    if (!f) return nullptr;
+    std::unique_ptr<Graph> gp(new Graph);
+    Graph& g = *gp;
+
+    std::vector<double> xref(nx, 0.0);
+    if (in.xref)
+        for (int i = 0; i < nx; ++i) xref[i] = in.xref[i];
+    const std::vector<double>& xf_goal = xref;  // xref.getReferenceCached(n-1) of a static reference
+
+    const bool var_dt    = d.grid == B200SQP_GRID_FD_NONUNIFORM_VARDT;
+    const bool single_dt = !var_dt;  // hasSingleDt(): FullDiscretizationGridBase true; NonUniform... false
+    const int intervals  = N - 1;
+
+    // direction / step of the linear initialisation
+    std::vector<double> dir(nx);
+    double dist = 0;
+    for (int i = 0; i < nx; ++i)
+    {
+        dir[i] = xf_goal[i] - in.x0[i];
+        dist += dir[i] * dir[i];
+    }
+    dist = std::sqrt(dist);
+    if (dist != 0)
+        for (int i = 0; i < nx; ++i) dir[i] /= dist;
+    const double step = dist / intervals;
+
+    Vertex* dt_single = nullptr;
+    if (!var_dt)
+    {
+        dt_single          = g.add(1);  // _dt.set(_dt_ref, _dt_lb, _dt_ub, isDtFixedIntended()=true)
+        dt_single->val[0]  = d.dt_ref;
+        dt_single->lb[0]   = 0;
+        dt_single->fixed[0] = 1;
+    }
+    for (int k = 0; k < intervals; ++k)
+    {
+        Vertex* x = g.add(nx);
+        for (int i = 0; i < nx; ++i)
+        {
+            x->val[i] = in.x0[i] + (double)k * step * dir[i];
+            x->lb[i]  = d.x_lb[i];
+            x->ub[i]  = d.x_ub[i];
+        }
+        Vertex* u = g.add(nu);
+        for (int i = 0; i < nu; ++i)
+        {
+            u->val[i] = 0.0;  // uref.getReferenceCached(k), ZeroReference
+            u->lb[i]  = d.u_lb[i];
+            u->ub[i]  = d.u_ub[i];
+        }
+        g.xs.push_back(x);
+        g.us.push_back(u);
+        if (var_dt)
+        {
+            Vertex* t = g.add(1);  // _dt_seq.emplace_back(_dt_ref, _dt_lb, _dt_ub, false)
+            t->val[0] = d.dt_ref;
+            t->lb[0]  = d.dt_lb;
+            t->ub[0]  = d.dt_ub;
+            g.dts.push_back(t);
+        }
+        else
+            g.dts.push_back(dt_single);
+    }
+    Vertex* xf = g.add(nx);
+    for (int i = 0; i < nx; ++i)
+    {
+        xf->val[i]   = xf_goal[i];
+        xf->lb[i]    = d.x_lb[i];
+        xf->ub[i]    = d.x_ub[i];
+        xf->fixed[i] = d.xf_fixed[i] ? 1 : 0;
+    }
+    g.xs.push_back(xf);
+    for (int i = 0; i < nx; ++i) g.xs[0]->fixed[i] = 1;  // _x_seq.front().setFixed(true)
+
+    // computeActiveVertices: full_discretization_grid_base.cpp:514-527 / non_uniform_...:454-467 / shooting_grid_base.cpp:583-598
+    for (int k = 0; k < intervals; ++k)
+    {
+        if (!g.xs[k]->isFixed()) g.active.push_back(g.xs[k]);
+        if (!g.us[k]->isFixed()) g.active.push_back(g.us[k]);
+        if (var_dt && !g.dts[k]->isFixed()) g.active.push_back(g.dts[k]);
+    }
+    if (!xf->isFixed()) g.active.push_back(xf);
+    computeVertexIndices(g);
+
+    // createEdges
+    const int coll = d.collocation, integ = d.integrator, gridkind = d.grid;
+    for (int k = 0; k < intervals; ++k)
+    {
+        Vertex *xk = g.xs[k], *uk = g.us[k], *xn = g.xs[k + 1], *dtk = g.dts[k];
+        addStageCostEdges(g, d, k, xk, uk, dtk, xref, single_dt);
+        Edge e;
+        e.dim = nx;
+        e.v   = {xk, uk, xn, dtk};  // FDCollocationEdge / MSVariableDynamicsOnlyEdge vertex order (x1,u1,x2,dt)
+        if (gridkind == B200SQP_GRID_MULTIPLE_SHOOTING)
+            e.values = [=](double* out) { shooting(integ, f, nx, xk->val.data(), uk->val.data(), xn->val.data(), dtk->val[0], out); };
+        else
+            e.values = [=](double* out) { collocation(coll, f, nx, xk->val.data(), uk->val.data(), xn->val.data(), dtk->val[0], out); };
+        g.eq.push_back(e);
+    }
+    if (!xf->isFixed()) addFinalCostEdge(g, d, xf, xref);
+    computeEdgeIndices(g);
+    return gp;
+}
+
+// ---------------------------------------------------------------------------------------------------------------------------
+// Problem-level evaluation  (optimization/src/hyper_graph/hyper_graph_optimization_problem_base.cpp, ..._edge_based.cpp)
+// ---------------------------------------------------------------------------------------------------------------------------
+int valDim(const Graph& g) { return g.m_lsq + g.m_eq + g.m_ineq + g.m_b; }
+
+// LevenbergMarquardtSparse::computeValues (optimization/src/solver/levenberg_marquardt_sparse.cpp:222-246) over
+// computeValuesLsqObjective/Equality/ActiveInequality (..._base.cpp:106-125,162-200,278-289) and
+// computeDistanceFiniteCombinedBounds (..._base.cpp:291-315)
+void computeValues(Graph& g, double w_eq, double w_ineq, double w_b, double* r)
+{
+    for (Edge& e : g.lsq) e.values(r + e.idx);
+    double* req = r + g.m_lsq;
+    for (Edge& e : g.eq) e.values(req + e.idx);
+    for (int i = 0; i < g.m_eq; ++i) req[i] *= w_eq;
+    double* rin = req + g.m_eq;
+    for (Edge& e : g.ineq) e.values(rin + e.idx);
+    for (int i = 0; i < g.m_ineq; ++i)
+    {
+        if (rin[i] < 0)
+            rin[i] = 0;
+        else
+            rin[i] *= w_ineq;
+    }
+    double* rb = rin + g.m_ineq;
+    int idx    = 0;
+    for (Vertex* v : g.active)
+        for (int c = 0; c < v->dim(); ++c)
+        {
+            if (v->fixed[c]) continue;
+            if (v->finiteLb(c) || v->finiteUb(c))
+            {
+                if (v->val[c] < v->lb[c])
+                    rb[idx] = v->lb[c] - v->val[c];
+                else if (v->val[c] > v->ub[c])
+                    rb[idx] = v->val[c] - v->ub[c];
+                else
+                    rb[idx] = 0;
+                ++idx;
+            }
+        }
+    for (int i = 0; i < g.m_b; ++i) rb[i] *= w_b;
+}
+
+// One stored entry of the combined Jacobian
+struct JEntry
+{
+    int row, col;
+    double val;
+};
+
+// BaseEdge::computeJacobian (optimization/src/hyper_graph/edge_interface.cpp:55-96): central differences, delta = 1e-9, performed IN
+// PLACE on the vertex (+delta, -2 delta, +delta) so the vertex value drifts by rounding exactly as in the reference.
+void edgeJacobian(Edge& e, int vtx, std::vector<double>& block /*dim x unfixed, col-major*/)
+{
+    constexpr double delta     = 1e-9;
+    constexpr double neg2delta = -2 * delta;
+    constexpr double scalar    = 1.0 / (2 * delta);
+    Vertex* v                  = e.v[vtx];
+    std::vector<double> v1(e.dim), v2(e.dim);
+    int col = 0;
+    for (int i = 0; i < v->dim(); ++i)
+    {
+        if (v->fixed[i]) continue;
+        v->val[i] += delta;
+        e.values(v2.data());
+        v->val[i] += neg2delta;
+        e.values(v1.data());
+        for (int j = 0; j < e.dim; ++j) block[(size_t)col * e.dim + j] = scalar * (v2[j] - v1[j]);
+        v->val[i] += delta;
+        ++col;
+    }
+}
+
+// HyperGraphOptimizationProblemEdgeBased::computeCombinedSparseJacobian
+// (optimization/src/hyper_graph/hyper_graph_optimization_problem_edge_based.cpp:1480-1753): lsq edges, equality edges (x w_eq),
+// inequality edges (x w_ineq when the row's value > 0, explicit 0.0 otherwise), bound rows (-w / +w / 0.0).  Entries are
+// produced in the reference's visiting order; explicit zeros are kept.
+void combinedJacobian(Graph& g, double w_eq, double w_ineq, double w_b, const double* values, std::vector<JEntry>& J)
+{
+    J.clear();
+    const int eq_start = g.m_lsq, ineq_start = eq_start + g.m_eq, b_start = ineq_start + g.m_ineq;
+    std::vector<double> block;
+    auto scatter = [&](Edge& e, int row0, double w, const std::vector<char>* active) {
+        for (int vi = 0; vi < (int)e.v.size(); ++vi)
+        {
+            Vertex* v = e.v[vi];
+            int nunf  = v->dimUnfixed();
+            if (nunf == 0) continue;
+            block.assign((size_t)e.dim * nunf, 0.0);
+            edgeJacobian(e, vi, block);
+            int free = 0;
+            for (int i = 0; i < v->dim(); ++i)
+            {
+                if (v->fixed[i]) continue;
+                for (int j = 0; j < e.dim; ++j)
+                {
+                    double val = block[(size_t)free * e.dim + j];
+                    if (active)
+                        val = (*active)[j] ? val * w : 0.0;  // :1602-1610
+                    else
+                        val = val * w;  // :1552
+                    J.push_back({row0 + e.idx + j, v->idx + free, val});
+                }
+                ++free;
+            }
+        }
+    };
+    for (Edge& e : g.lsq)
+    {
+        // lsq rows are stored unweighted (:1519)
+        for (int vi = 0; vi < (int)e.v.size(); ++vi)
+        {
+            Vertex* v = e.v[vi];
+            int nunf  = v->dimUnfixed();
+            if (nunf == 0) continue;
+            block.assign((size_t)e.dim * nunf, 0.0);
+            edgeJacobian(e, vi, block);
+            int free = 0;
+            for (int i = 0; i < v->dim(); ++i)
+            {
+                if (v->fixed[i]) continue;
+                for (int j = 0; j < e.dim; ++j) J.push_back({e.idx + j, v->idx + free, block[(size_t)free * e.dim + j]});
+                ++free;
+            }
+        }
+    }
+    for (Edge& e : g.eq) scatter(e, eq_start, w_eq, nullptr);
+    for (Edge& e : g.ineq)
+    {
+        std::vector<char> active(e.dim);
+        for (int j = 0; j < e.dim; ++j) active[j] = values[ineq_start + e.idx + j] > 0.0;
+        scatter(e, ineq_start, w_ineq, &active);
+    }
+    int row = b_start;
+    for (Vertex* v : g.active)
+    {
+        int free = 0;
+        for (int i = 0; i < v->dim(); ++i)
+        {
+            if (v->fixed[i]) continue;
+            if (v->finiteLb(i) || v->finiteUb(i))
+            {
+                double val = 0.0;
+                if (v->val[i] < v->lb[i])
+                    val = -w_b;
+                else if (v->val[i] > v->ub[i])
+                    val = w_b;
+                J.push_back({row, v->idx + free, val});
+                ++row;
+            }
+            ++free;
+        }
+    }
+}
+
+// parameter access in the reference's order: VertexSetInterface::applyIncrementNonFixed (vertex_set.cpp:357-367),
+// get/setParameterVector, backup stack (vertex_set.cpp:431-464)
+void getParams(Graph& g, double* p)
+{
+    for (Vertex* v : g.active)
+    {
+        int f = 0;
+        for (int i = 0; i < v->dim(); ++i)
+            if (!v->fixed[i]) p[v->idx + f++] = v->val[i];
+    }
+}
+void setParams(Graph& g, const double* p)
+{
+    for (Vertex* v : g.active)
+    {
+        int f = 0;
+        for (int i = 0; i < v->dim(); ++i)
+            if (!v->fixed[i]) v->val[i] = p[v->idx + f++];
+    }
+}
+void applyIncrement(Graph& g, const double* inc)
+{
+    for (Vertex* v : g.active)
+    {
+        int f = 0;
+        for (int i = 0; i < v->dim(); ++i)
+            if (!v->fixed[i]) v->val[i] += inc[v->idx + f++];
+    }
+}
+void backupParams(Graph& g)
+{
+    for (Vertex* v : g.active) v->backup = v->val;
+}
+void restoreParams(Graph& g)
+{
+    for (Vertex* v : g.active) v->val = v->backup;
+}
+
+// ---------------------------------------------------------------------------------------------------------------------------
+// Normal equations + banded Cholesky (stands in for Eigen's sparse product and SimplicialLLT; same mathematics, different
+// summation order -> agreement to rounding, which the tests state)
+// ---------------------------------------------------------------------------------------------------------------------------
+struct Normal
+{
+    int n = 0, bw = 0;          // half bandwidth
+    std::vector<double> H;      // lower band storage: H[(i)*(bw+1) + (i-j)] for j<=i, i-j<=bw
+    std::vector<double> g;      // rhs = J^T (-r)
+    std::vector<double> L;      // factor, same layout
+    double& h(int i, int j) { return H[(size_t)i * (bw + 1) + (i - j)]; }
+    double& l(int i, int j) { return L[(size_t)i * (bw + 1) + (i - j)]; }
+};
+
+void buildNormal(const std::vector<JEntry>& J, const double* r, int m, int n, Normal& N)
+{
+    // rows of J as sparse lists
+    std::vector<std::vector<std::pair<int, double>>> rows(m);
+    for (const JEntry& e : J) rows[e.row].push_back({e.col, e.val});
+    int bw = 0;
+    for (auto& row : rows)
+    {
+        int lo = n, hi = -1;
+        for (auto& c : row)
+        {
+            lo = std::min(lo, c.first);
+            hi = std::max(hi, c.first);
+        }
+        if (hi >= 0) bw = std::max(bw, hi - lo);
+    }
+    N.n  = n;
+    N.bw = bw;
+    N.H.assign((size_t)n * (bw + 1), 0.0);
+    N.g.assign(n, 0.0);
+    for (int i = 0; i < m; ++i)
+    {
+        auto& row = rows[i];
+        for (auto& a : row)
+        {
+            N.g[a.first] += a.second * -r[i];
+            for (auto& b : row)
+                if (b.first <= a.first) N.h(a.first, b.first) += a.second * b.second;
+        }
+    }
+}
+
+bool bandCholeskySolve(Normal& N, std::vector<double>& x)
+{
+    const int n = N.n, bw = N.bw;
+    N.L = N.H;
+    bool ok = true;
+    for (int j = 0; j < n; ++j)
+    {
+        double d = N.l(j, j);
+        for (int k = std::max(0, j - bw); k < j; ++k) d -= N.l(j, k) * N.l(j, k);
+        if (!(d > 0)) ok = false;
+        d          = std::sqrt(d);
+        N.l(j, j)  = d;
+        for (int i = j + 1; i <= std::min(n - 1, j + bw); ++i)
+        {
+            double s = N.l(i, j);
+            for (int k = std::max(0, i - bw); k < j; ++k) s -= N.l(i, k) * N.l(j, k);
+            N.l(i, j) = s / d;
+        }
+    }
+    x = N.g;
+    for (int i = 0; i < n; ++i)
+    {
+        double s = x[i];
+        for (int k = std::max(0, i - bw); k < i; ++k) s -= N.l(i, k) * x[k];
+        x[i] = s / N.l(i, i);
+    }
+    for (int i = n - 1; i >= 0; --i)
+    {
+        double s = x[i];
+        for (int k = i + 1; k <= std::min(n - 1, i + bw); ++k) s -= N.l(k, i) * x[k];
+        x[i] = s / N.l(i, i);
+    }
+    return ok;
+}
+
+// ---------------------------------------------------------------------------------------------------------------------------
+// LevenbergMarquardtSparse::solve  (optimization/src/solver/levenberg_marquardt_sparse.cpp:44-220), quirks included:
+// damping is added to the Hessian diagonal on every inner pass and never removed (:135-138,208); all `iterations` outer passes
+// always run (:129); `stop` is overwritten by ||values|| <= eps3 (:216); the last outer pass does not re-linearise (:178).
+// ---------------------------------------------------------------------------------------------------------------------------
+enum { EV_JACOBIAN = 0, EV_INCREMENT = 1, EV_RESTORE = 2, EV_DISCARD = 3 };
+struct Event
+{
+    int type;
+    double chi2;
+    std::vector<double> vec;
+};
+
+struct Weights
+{
+    double eq, ineq, b;
+};
+
+int lmSolve(Graph& g, const b200sqp_lm_options& o, bool new_run, Weights& w, double* obj_value, std::vector<Event>* log)
+{
+    if (obj_value) *obj_value = -1;
+    const int n = g.n, m = valDim(g);
+    // resetWeights / adaptWeights (:83-86,:264-287)
+    if (new_run)
+        w = {o.weight_eq, o.weight_ineq, o.weight_bounds};
+    else
+    {
+        w.eq *= o.adapt_factor_eq;
+        if (w.eq > o.adapt_max_eq) w.eq = o.adapt_max_eq;
+        w.ineq *= o.adapt_factor_ineq;
+        if (w.ineq > o.adapt_max_ineq) w.ineq = o.adapt_max_ineq;
+        w.b *= o.adapt_factor_bounds;
+        if (w.b > o.adapt_max_bounds) w.b = o.adapt_max_bounds;
+    }
+    std::vector<double> values(m), delta(n), params(n);
+    std::vector<JEntry> J;
+    Normal N;
+    auto sqnorm = [](const std::vector<double>& v) {
+        double s = 0;
+        for (double x : v) s += x * x;
+        return s;
+    };
+    auto linearize = [&]() {
+        if (log)
+        {
+            getParams(g, params.data());
+            log->push_back({EV_JACOBIAN, sqnorm(values), params});
+        }
+        combinedJacobian(g, w.eq, w.ineq, w.b, values.data(), J);
+        buildNormal(J, values.data(), m, n, N);
+    };
+    auto rhsInfNorm = [&]() {
+        double s = 0;
+        for (double x : N.g) s = std::max(s, std::fabs(x));
+        return s;
+    };
+
+    computeValues(g, w.eq, w.ineq, w.b, values.data());
+    linearize();
+
+    constexpr double eps1 = 1e-5, eps2 = 1e-5, eps3 = 1e-5, eps4 = 0;
+    unsigned int v = 2;
+    const double tau = 1e-5;
+    constexpr double goodStepUpperScale = 2. / 3., goodStepLowerScale = 1. / 3.;
+
+    bool stop = rhsInfNorm() <= eps1;
+    double maxdiag = -HUGE_VAL;
+    for (int i = 0; i < n; ++i) maxdiag = std::max(maxdiag, N.h(i, i));
+    double mu = tau * maxdiag;
+    if (mu < 0) mu = 0;
+    double rho      = 0;
+    double chi2_old = sqnorm(values);
+    if (obj_value) *obj_value = chi2_old;
+
+    for (int k = 0; k < o.iterations; ++k)
+    {
+        do
+        {
+            for (int i = 0; i < n; ++i) N.h(i, i) += mu;
+            bandCholeskySolve(N, delta);
+            double dn = std::sqrt(sqnorm(delta));
+            if (dn <= eps2)
+            {
+                stop = true;
+            }
+            else
+            {
+                backupParams(g);
+                if (log) log->push_back({EV_INCREMENT, 0.0, delta});
+                applyIncrement(g, delta.data());
+                computeValues(g, w.eq, w.ineq, w.b, values.data());
+                double chi2_new = sqnorm(values);
+                double denom    = 0;
+                for (int i = 0; i < n; ++i) denom += delta[i] * (mu * delta[i] + N.g[i]);
+                rho = (chi2_old - chi2_new) / denom;
+                if (rho > 0 && !std::isnan(chi2_new) && !std::isinf(chi2_new))
+                {
+                    stop = (std::sqrt(chi2_old) - std::sqrt(chi2_new) < eps4 * std::sqrt(chi2_old));
+                    if (log) log->push_back({EV_DISCARD, 0.0, {}});
+                    if (!stop && k < o.iterations - 1)
+                    {
+                        linearize();
+                        stop               = stop || (rhsInfNorm() <= eps1);
+                        double alpha       = std::min(goodStepUpperScale, 1 - std::pow((2 * rho - 1), 3));
+                        double scaleFactor = std::max(goodStepLowerScale, alpha);
+                        mu *= scaleFactor;
+                        v = 2;
+                    }
+                    chi2_old = chi2_new;
+                    if (obj_value) *obj_value = chi2_old;
+                }
+                else
+                {
+                    if (log) log->push_back({EV_RESTORE, 0.0, {}});
+                    restoreParams(g);
+                    mu = mu * v;
+                    v  = 2 * v;
+                }
+            }
+        } while (rho <= 0 && !stop);
+        stop = (std::sqrt(sqnorm(values)) <= eps3);
+    }
+    return (stop || rho <= 0) ? B200SQP_STATUS_CONVERGED : B200SQP_STATUS_EARLY_TERMINATED;
+}
+
+void fillDims(Graph& g, b200sqp_dims* out)
+{
+    std::memset(out, 0, sizeof(*out));
+    out->n_params = g.n;
+    out->m_lsq    = g.m_lsq;
+    out->m_eq     = g.m_eq;
+    out->m_ineq   = g.m_ineq;
+    out->m_bounds = g.m_b;
+    const int m   = valDim(g);
+    std::vector<double> backup(g.n), values(m, 1.0);
+    getParams(g, backup.data());
+    std::vector<JEntry> J;
+    combinedJacobian(g, 1.0, 1.0, 1.0, values.data(), J);
+    setParams(g, backup.data());
+    out->nnz_jacobian = (int)J.size();
+    // structural nnz of the upper triangle of J^T J
+    std::vector<std::vector<int>> rows(m);
+    for (auto& e : J) rows[e.row].push_back(e.col);
+    std::vector<std::vector<char>> mark;  // band-limited marker to stay small
+    int bw = 0;
+    for (auto& r : rows)
+        if (!r.empty()) bw = std::max(bw, *std::max_element(r.begin(), r.end()) - *std::min_element(r.begin(), r.end()));
+    std::vector<char> band((size_t)g.n * (bw + 1), 0);
+    for (auto& r : rows)
+        for (int a : r)
+            for (int b : r)
+                if (b <= a) band[(size_t)a * (bw + 1) + (a - b)] = 1;
+    int nnz = 0;
+    for (char c : band) nnz += c;
+    out->nnz_hessian_upper = nnz;
+    const int64_t s        = 8;
+    out->algorithmic_bytes_per_iteration =
+        s * (2 * ((int64_t)out->nnz_jacobian + 2 * (int64_t)nnz + 2 * (int64_t)m + 2 * (int64_t)g.n) + 4 * (int64_t)g.n);
+}
+
+}  // namespace
+
+extern "C" {
+
+int sqp_oracle_dims(const b200sqp_ocp* d, b200sqp_dims* out)
+{
+    std::vector<double> x0(d->nx, 0.25);
+    auto g = buildGraph({d, x0.data(), nullptr});
+    if (!g) return -1;
+    fillDims(*g, out);
+    return 0;
+}
+
+int sqp_oracle_vertex_indices(const b200sqp_ocp* d, int32_t* x_idx, int32_t* u_idx, int32_t* dt_idx)
+{
+    std::vector<double> x0(d->nx, 0.25);
+    auto g = buildGraph({d, x0.data(), nullptr});
+    if (!g) return -1;
+    auto idx = [](Vertex* v) { return v->dimUnfixed() > 0 ? v->idx : -1; };
+    for (int k = 0; k < d->n_grid - 1; ++k)
+    {
+        x_idx[k]  = idx(g->xs[k]);
+        u_idx[k]  = idx(g->us[k]);
+        dt_idx[k] = idx(g->dts[k]);
+    }
+    x_idx[d->n_grid - 1] = idx(g->xs[d->n_grid - 1]);
+    return 0;
+}
+
+int sqp_oracle_edge_table(const b200sqp_ocp* d, int category, int32_t* table, int max_edges)
+{
+    std::vector<double> x0(d->nx, 0.25);
+    auto g = buildGraph({d, x0.data(), nullptr});
+    if (!g) return -1;
+    std::vector<Edge>& list = category == 0 ? g->lsq : (category == 1 ? g->eq : g->ineq);
+    int cnt                 = 0;
+    for (Edge& e : list)
+    {
+        if (cnt >= max_edges) break;
+        int32_t* row = table + 7 * cnt;
+        row[0]       = e.dim;
+        row[1]       = e.idx;
+        row[2]       = (int)e.v.size();
+        for (int v = 0; v < 4; ++v) row[3 + v] = (v < (int)e.v.size() && e.v[v]->dimUnfixed() > 0) ? e.v[v]->idx : -1;
+        ++cnt;
+    }
+    return cnt;
+}
+
+int sqp_oracle_initial_params(const b200sqp_ocp* d, const double* x0, const double* xref, double* params)
+{
+    auto g = buildGraph({d, x0, xref});
+    if (!g) return -1;
+    getParams(*g, params);
+    return 0;
+}
+
+int sqp_oracle_evaluate(const b200sqp_ocp* d, const double* x0, const double* xref, const double* params, double w_eq, double w_ineq, double w_b,
+                        double* values, double* jac_dense, uint8_t* jac_pattern, double* params_after)
+{
+    auto g = buildGraph({d, x0, xref});
+    if (!g) return -1;
+    if (params) setParams(*g, params);
+    const int n = g->n, m = valDim(*g);
+    std::vector<double> v(m);
+    computeValues(*g, w_eq, w_ineq, w_b, v.data());
+    if (values) std::memcpy(values, v.data(), sizeof(double) * m);
+    if (jac_dense || jac_pattern || params_after)
+    {
+        std::vector<JEntry> J;
+        combinedJacobian(*g, w_eq, w_ineq, w_b, v.data(), J);
+        if (jac_dense) std::memset(jac_dense, 0, sizeof(double) * m * n);
+        if (jac_pattern) std::memset(jac_pattern, 0, (size_t)m * n);
+        for (auto& e : J)
+        {
+            if (jac_dense) jac_dense[(size_t)e.row * n + e.col] = e.val;
+            if (jac_pattern) jac_pattern[(size_t)e.row * n + e.col] = 1;
+        }
+        if (params_after) getParams(*g, params_after);
+    }
+    return 0;
+}
+
+int sqp_oracle_trace(const b200sqp_ocp* d, const b200sqp_lm_options* o, const double* x0, const double* xref, const double* params_in,
+                     double* params_out, double* chi2_out, int32_t* status_out, int max_events, int32_t* ev_type, double* ev_chi2, double* ev_vec,
+                     int32_t* n_events)
+{
+    auto g = buildGraph({d, x0, xref});
+    if (!g) return -1;
+    if (params_in) setParams(*g, params_in);
+    const int n = g->n;
+    std::vector<Event> log;
+    Weights w{0, 0, 0};
+    double obj = -1;
+    int st     = lmSolve(*g, *o, true, w, &obj, &log);
+    if (params_out) getParams(*g, params_out);
+    if (chi2_out) *chi2_out = obj;
+    if (status_out) *status_out = st;
+    int cnt = 0;
+    for (auto& e : log)
+    {
+        if (cnt >= max_events) break;
+        ev_type[cnt] = e.type;
+        ev_chi2[cnt] = e.chi2;
+        if (ev_vec)
+        {
+            std::memset(ev_vec + (size_t)cnt * n, 0, sizeof(double) * n);
+            if ((int)e.vec.size() == n) std::memcpy(ev_vec + (size_t)cnt * n, e.vec.data(), sizeof(double) * n);
+        }
+        ++cnt;
+    }
+    if (n_events) *n_events = (int)log.size();
+    return 0;
+}
+
+int sqp_oracle_solve_batch(const b200sqp_ocp* d, const b200sqp_lm_options* o, int batch, const double* x0, const double* xref,
+                           const double* params_in, double* params_out, double* chi2, int32_t* status, int threads, double* seconds)
+{
+    if (threads < 1) threads = 1;
+    b200sqp_dims dims;
+    if (sqp_oracle_dims(d, &dims) != 0) return -1;
+    const int n = dims.n_params;
+    std::atomic<int> failures(0);
+    std::vector<double> t_solve(threads, 0.0), t_prep(threads, 0.0);
+    auto t_begin = std::chrono::steady_clock::now();
+    auto worker  = [&](int tid) {
+        const int lo = (int)((int64_t)batch * tid / threads), hi = (int)((int64_t)batch * (tid + 1) / threads);
+        for (int i = lo; i < hi; ++i)
+        {
+            auto t0 = std::chrono::steady_clock::now();
+            auto g  = buildGraph({d, x0 + (size_t)i * d->nx, xref ? xref + (size_t)i * d->nx : nullptr});
+            if (!g)
+            {
+                ++failures;
+                continue;
+            }
+            if (params_in) setParams(*g, params_in + (size_t)i * n);
+            auto t1 = std::chrono::steady_clock::now();
+            Weights w{0, 0, 0};
+            double obj = -1;
+            int st     = lmSolve(*g, *o, true, w, &obj, nullptr);
+            auto t2    = std::chrono::steady_clock::now();
+            t_prep[tid] += std::chrono::duration<double>(t1 - t0).count();
+            t_solve[tid] += std::chrono::duration<double>(t2 - t1).count();
+            if (params_out) getParams(*g, params_out + (size_t)i * n);
+            if (chi2) chi2[i] = obj;
+            if (status) status[i] = st;
+        }
+    };
+    std::vector<std::thread> pool;
+    for (int t = 1; t < threads; ++t) pool.emplace_back(worker, t);
+    worker(0);
+    for (auto& th : pool) th.join();
+    auto t_end = std::chrono::steady_clock::now();
+    if (seconds)
+    {
+        seconds[0] = std::chrono::duration<double>(t_end - t_begin).count();
+        seconds[1] = 0;
+        seconds[2] = 0;
+        for (int t = 0; t < threads; ++t)
+        {
+            seconds[1] += t_solve[t];
+            seconds[2] += t_prep[t];
+        }
+    }
+    return failures.load() == 0 ? 0 : -1;
+}
+
+}  // extern "C"

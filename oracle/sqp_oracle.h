@@ -1,0 +1,26 @@
+/* TEST INFRASTRUCTURE ONLY -- CPU restatement (oracle) of the reference's LM/SQP hot path.  See sqp_oracle.cpp. */
+#ifndef SQP_ORACLE_H_
+#define SQP_ORACLE_H_
+
+#include "../include/b200sqp.h"
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+int sqp_oracle_dims(const b200sqp_ocp* d, b200sqp_dims* out);
+int sqp_oracle_vertex_indices(const b200sqp_ocp* d, int32_t* x_idx, int32_t* u_idx, int32_t* dt_idx);
+int sqp_oracle_edge_table(const b200sqp_ocp* d, int category, int32_t* table, int max_edges);
+int sqp_oracle_initial_params(const b200sqp_ocp* d, const double* x0, const double* xref, double* params);
+int sqp_oracle_evaluate(const b200sqp_ocp* d, const double* x0, const double* xref, const double* params, double w_eq, double w_ineq, double w_b,
+                        double* values, double* jac_dense, uint8_t* jac_pattern, double* params_after);
+int sqp_oracle_trace(const b200sqp_ocp* d, const b200sqp_lm_options* o, const double* x0, const double* xref, const double* params_in,
+                     double* params_out, double* chi2_out, int32_t* status_out, int max_events, int32_t* ev_type, double* ev_chi2, double* ev_vec,
+                     int32_t* n_events);
+int sqp_oracle_solve_batch(const b200sqp_ocp* d, const b200sqp_lm_options* o, int batch, const double* x0, const double* xref,
+                           const double* params_in, double* params_out, double* chi2, int32_t* status, int threads, double* seconds);
+
+#ifdef __cplusplus
+}
+#endif
+#endif
