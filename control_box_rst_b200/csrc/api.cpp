@@ -1,0 +1,581 @@
+// C ABI of libb200sqp.so (include/b200sqp.h).  Host-side plumbing only: handle lifetime, device buffers, H2D/D2H copies, weight
+// reset/adaptation, kernel dispatch through the launch table.  There is no CPU implementation of the hot path in this library:
+// without a usable CUDA device every compute entry point fails with B200SQP_ERR_NO_DEVICE.
+#include <cuda_runtime.h>
+
+#include <cmath>
+#include <cstring>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "../../include/b200sqp.h"
+#include "launch.h"
+#include "lm_device_types.h"
+#include "structure.h"
+
+using namespace b200sqp;
+
+namespace {
+
+thread_local std::string g_last_error;
+
+int fail(int code, const std::string& msg)
+{
+    g_last_error = msg;
+    return code;
+}
+
+#define CUDA_TRY(expr)                                                                                         \
+    do                                                                                                         \
+    {                                                                                                          \
+        cudaError_t _e = (expr);                                                                               \
+        if (_e != cudaSuccess) return fail(B200SQP_ERR_CUDA, std::string(#expr) + ": " + cudaGetErrorString(_e)); \
+    } while (0)
+
+}  // namespace
+
+namespace b200sqp {
+
+const KernelSet* findKernels(int dynamics, int defect, int vt)
+{
+    const KernelSet* (*tables[])(int*) = {kernelTableOscillators, kernelTableCartPole, kernelTableUnicycle, kernelTableQuadrotor};
+    for (auto t : tables)
+    {
+        int count            = 0;
+        const KernelSet* set = t(&count);
+        for (int i = 0; i < count; ++i)
+            if (set[i].dynamics == dynamics && set[i].defect == defect && set[i].vt == vt) return &set[i];
+    }
+    return nullptr;
+}
+
+}  // namespace b200sqp
+
+struct b200sqp_solver
+{
+    Structure s;
+    const KernelSet* kernels = nullptr;
+    int B = 0, S = 0, device = 0;
+    int max_iterations = 0;
+    DeviceOcp P{};
+    DeviceState st{};
+    cudaStream_t own_stream = nullptr, stream = nullptr;
+    cudaEvent_t ev_begin = nullptr, ev_end = nullptr;
+    bool timed = false;
+    int64_t launches = 0;
+    bool weights_initialised = false;
+    // staging
+    double* d_params = nullptr;   // [B][n]
+    double* d_x0_host_order = nullptr, *d_xref_host_order = nullptr;  // [B][nx]
+    double* d_u0 = nullptr;       // [B][nu]
+    int* d_ref_of_internal = nullptr, *d_internal_of_ref = nullptr, *d_value_rows = nullptr, *d_jac_pos = nullptr;
+    double* d_values = nullptr, *d_jac = nullptr, *d_eval_out = nullptr;
+    std::vector<void*> allocations;
+
+    template <class T>
+    cudaError_t alloc(T** p, size_t count)
+    {
+        cudaError_t e = cudaMalloc((void**)p, sizeof(T) * (count ? count : 1));
+        if (e == cudaSuccess)
+        {
+            allocations.push_back(*p);
+            e = cudaMemsetAsync(*p, 0, sizeof(T) * (count ? count : 1), stream);
+        }
+        return e;
+    }
+};
+
+namespace {
+
+void fillDeviceOcp(const Structure& s, int B, int S, DeviceOcp& P)
+{
+    std::memset(&P, 0, sizeof(P));
+    const b200sqp_ocp& o = s.ocp;
+    P.K                  = s.K;
+    P.B                  = B;
+    P.S                  = S;
+    P.stage_cost         = o.stage_cost;
+    P.final_cost         = (o.final_cost == 1 && !s.xfFullyFixed()) ? 1 : 0;
+    P.tcost_every_interval = s.vt;  // MinimumTime: a dt term on every interval iff !single_dt (minimum_time.h:49)
+    for (int i = 0; i < s.nx; ++i)
+    {
+        P.xf_fixed[i]  = o.xf_fixed[i] ? 1 : 0;
+        P.x_lb[i]      = o.x_lb[i];
+        P.x_ub[i]      = o.x_ub[i];
+        P.x_bounded[i] = (o.x_lb[i] > -kCorboInf || o.x_ub[i] < kCorboInf) ? 1 : 0;
+        P.q_sqrt[i]    = std::sqrt(o.q_diag[i]);   // QuadraticFormCost::setWeightQ -> cwiseSqrt (quadratic_cost.cpp:62)
+        P.qf_sqrt[i]   = std::sqrt(o.qf_diag[i]);  // QuadraticFinalStateCost::setWeightQf (final_state_cost.cpp:66)
+    }
+    for (int i = 0; i < s.nu; ++i)
+    {
+        P.u_lb[i]      = o.u_lb[i];
+        P.u_ub[i]      = o.u_ub[i];
+        P.u_bounded[i] = (o.u_lb[i] > -kCorboInf || o.u_ub[i] < kCorboInf) ? 1 : 0;
+        P.r_sqrt[i]    = std::sqrt(o.r_diag[i]);
+    }
+    P.dt_bounded = (s.vt && (o.dt_lb > -kCorboInf || o.dt_ub < kCorboInf)) ? 1 : 0;
+    P.dt_ref     = o.dt_ref;
+    P.dt_lb      = o.dt_lb;
+    P.dt_ub      = o.dt_ub;
+    P.tcost_w    = std::sqrt((double)(o.n_grid - 1));  // MinimumTime::update, lsq form (minimum_time.h:56-66)
+    for (int i = 0; i < B200SQP_MAX_DYN_PARAMS; ++i) P.dyn.p[i] = o.dyn_params[i];
+}
+
+int checkHandle(b200sqp_handle h)
+{
+    if (!h) return fail(B200SQP_ERR_INVALID, "null handle");
+    cudaError_t e = cudaSetDevice(h->device);
+    if (e != cudaSuccess) return fail(B200SQP_ERR_CUDA, std::string("cudaSetDevice: ") + cudaGetErrorString(e));
+    return B200SQP_OK;
+}
+
+// resetWeights / adaptWeights (levenberg_marquardt_sparse.cpp:83-86, 264-287)
+void updateWeights(b200sqp_handle h, const b200sqp_lm_options& o, bool new_run)
+{
+    if (new_run || !h->weights_initialised)
+    {
+        h->st.w_eq   = o.weight_eq;
+        h->st.w_ineq = o.weight_ineq;
+        h->st.w_b    = o.weight_bounds;
+    }
+    else
+    {
+        h->st.w_eq *= o.adapt_factor_eq;
+        if (h->st.w_eq > o.adapt_max_eq) h->st.w_eq = o.adapt_max_eq;
+        h->st.w_ineq *= o.adapt_factor_ineq;
+        if (h->st.w_ineq > o.adapt_max_ineq) h->st.w_ineq = o.adapt_max_ineq;
+        h->st.w_b *= o.adapt_factor_bounds;
+        if (h->st.w_b > o.adapt_max_bounds) h->st.w_b = o.adapt_max_bounds;
+    }
+    h->weights_initialised = true;
+}
+
+int ensureTrace(b200sqp_handle h, int iterations)
+{
+    if (iterations <= h->max_iterations && h->st.trace) return B200SQP_OK;
+    double* t = nullptr;
+    CUDA_TRY(h->alloc(&t, (size_t)(iterations + 1) * h->S));
+    h->st.trace       = t;
+    h->max_iterations = iterations;
+    return B200SQP_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+const char* b200sqp_last_error(void) { return g_last_error.c_str(); }
+
+int b200sqp_device_available(void)
+{
+    int count = 0;
+    if (cudaGetDeviceCount(&count) != cudaSuccess || count == 0)
+    {
+        cudaGetLastError();
+        return 0;
+    }
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, 0) != cudaSuccess) return 0;
+    return prop.major >= 10 ? 1 : 0;
+}
+
+int b200sqp_dims_of(const b200sqp_ocp* ocp, b200sqp_dims* out)
+{
+    if (!ocp || !out) return fail(B200SQP_ERR_INVALID, "null argument");
+    Structure s;
+    std::string err;
+    int rc = buildStructure(*ocp, s, err);
+    if (rc != B200SQP_OK) return fail(rc, err);
+    *out = s.dims;
+    return B200SQP_OK;
+}
+
+int b200sqp_vertex_indices(const b200sqp_ocp* ocp, int32_t* x_idx, int32_t* u_idx, int32_t* dt_idx)
+{
+    if (!ocp) return fail(B200SQP_ERR_INVALID, "null argument");
+    Structure s;
+    std::string err;
+    int rc = buildStructure(*ocp, s, err);
+    if (rc != B200SQP_OK) return fail(rc, err);
+    if (x_idx) std::memcpy(x_idx, s.x_idx.data(), sizeof(int32_t) * s.x_idx.size());
+    if (u_idx) std::memcpy(u_idx, s.u_idx.data(), sizeof(int32_t) * s.u_idx.size());
+    if (dt_idx) std::memcpy(dt_idx, s.dt_idx.data(), sizeof(int32_t) * s.dt_idx.size());
+    return B200SQP_OK;
+}
+
+int b200sqp_edge_indices(const b200sqp_ocp* ocp, int32_t* state_cost_idx, int32_t* control_cost_idx, int32_t* dt_cost_idx, int32_t* dynamics_idx,
+                         int32_t* final_cost_idx)
+{
+    if (!ocp) return fail(B200SQP_ERR_INVALID, "null argument");
+    Structure s;
+    std::string err;
+    int rc = buildStructure(*ocp, s, err);
+    if (rc != B200SQP_OK) return fail(rc, err);
+    if (state_cost_idx) std::memcpy(state_cost_idx, s.state_cost_idx.data(), sizeof(int32_t) * s.state_cost_idx.size());
+    if (control_cost_idx) std::memcpy(control_cost_idx, s.control_cost_idx.data(), sizeof(int32_t) * s.control_cost_idx.size());
+    if (dt_cost_idx) std::memcpy(dt_cost_idx, s.dt_cost_idx.data(), sizeof(int32_t) * s.dt_cost_idx.size());
+    if (dynamics_idx) std::memcpy(dynamics_idx, s.dynamics_idx.data(), sizeof(int32_t) * s.dynamics_idx.size());
+    if (final_cost_idx) *final_cost_idx = s.final_cost_idx;
+    return B200SQP_OK;
+}
+
+int b200sqp_jacobian_pattern(const b200sqp_ocp* ocp, int32_t* col_ptr, int32_t* row_idx)
+{
+    if (!ocp) return fail(B200SQP_ERR_INVALID, "null argument");
+    Structure s;
+    std::string err;
+    int rc = buildStructure(*ocp, s, err);
+    if (rc != B200SQP_OK) return fail(rc, err);
+    if (col_ptr) std::memcpy(col_ptr, s.col_ptr.data(), sizeof(int32_t) * s.col_ptr.size());
+    if (row_idx) std::memcpy(row_idx, s.row_idx.data(), sizeof(int32_t) * s.row_idx.size());
+    return B200SQP_OK;
+}
+
+int b200sqp_create(const b200sqp_ocp* ocp, int32_t batch, int32_t device, b200sqp_handle* out)
+{
+    if (!ocp || !out || batch < 1) return fail(B200SQP_ERR_INVALID, "null argument or batch < 1");
+    *out = nullptr;
+    Structure s;
+    std::string err;
+    int rc = buildStructure(*ocp, s, err);
+    if (rc != B200SQP_OK) return fail(rc, err);
+    const KernelSet* ks = findKernels(ocp->dynamics, s.defect, s.vt);
+    if (!ks) return fail(B200SQP_ERR_UNSUPPORTED, "no device kernel for this (dynamics, defect, grid) combination; no CPU fallback");
+    int count = 0;
+    if (cudaGetDeviceCount(&count) != cudaSuccess || count == 0)
+    {
+        cudaGetLastError();
+        return fail(B200SQP_ERR_NO_DEVICE, "no CUDA device visible: the LM hot path only exists as sm_100a kernels");
+    }
+    if (device < 0 || device >= count) return fail(B200SQP_ERR_INVALID, "device index out of range");
+    CUDA_TRY(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    CUDA_TRY(cudaGetDeviceProperties(&prop, device));
+    if (prop.major < 10) return fail(B200SQP_ERR_NO_DEVICE, "device is not sm_100 class (kernels are compiled for sm_100a only)");
+
+    b200sqp_solver* h = new b200sqp_solver;
+    h->s       = s;
+    h->kernels = ks;
+    h->B       = batch;
+    h->S       = (batch + 31) / 32 * 32;
+    h->device  = device;
+    cudaError_t e = cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking);
+    if (e == cudaSuccess) e = cudaEventCreate(&h->ev_begin);
+    if (e == cudaSuccess) e = cudaEventCreate(&h->ev_end);
+    h->stream = h->own_stream;
+    fillDeviceOcp(s, h->B, h->S, h->P);
+
+    const size_t S = h->S, K = s.K, nb = s.nb, nx = s.nx;
+    const size_t nd = nb * (nb + 1) / 2, ne = nb * nx, n = s.dims.n_params;
+    DeviceState& st = h->st;
+    auto A = [&](auto** p, size_t cnt) {
+        if (e == cudaSuccess) e = h->alloc(p, cnt);
+    };
+    A(&st.z[0], K * nb * S);
+    A(&st.z[1], K * nb * S);
+    A(&st.x0, nx * S);
+    A(&st.xref, nx * S);
+    A(&st.D, K * nd * S);
+    A(&st.E, K * ne * S);
+    A(&st.g, K * nb * S);
+    A(&st.dl, K * nb * S);
+    A(&st.L, K * nd * S);
+    A(&st.W, K * ne * S);
+    A(&st.chi2, S);
+    A(&st.mu, S);
+    A(&st.rho, S);
+    A(&st.status, S);
+    A(&st.cur, S);
+    A(&st.n_factor, S);
+    A(&st.n_reject, S);
+    A(&st.n_linearize, S);
+    A(&h->d_params, (size_t)h->B * n);
+    A(&h->d_x0_host_order, (size_t)h->B * nx);
+    A(&h->d_xref_host_order, (size_t)h->B * nx);
+    A(&h->d_u0, (size_t)h->B * s.nu);
+    A(&h->d_ref_of_internal, s.ref_of_internal.size());
+    A(&h->d_internal_of_ref, s.internal_of_ref.size());
+    A(&h->d_value_rows, s.value_rows.size());
+    A(&h->d_jac_pos, s.jac_pos.size());
+    st.trace = nullptr;
+    if (e == cudaSuccess)
+        e = cudaMemcpyAsync(h->d_ref_of_internal, s.ref_of_internal.data(), sizeof(int) * s.ref_of_internal.size(), cudaMemcpyHostToDevice, h->stream);
+    if (e == cudaSuccess)
+        e = cudaMemcpyAsync(h->d_internal_of_ref, s.internal_of_ref.data(), sizeof(int) * s.internal_of_ref.size(), cudaMemcpyHostToDevice, h->stream);
+    if (e == cudaSuccess)
+        e = cudaMemcpyAsync(h->d_value_rows, s.value_rows.data(), sizeof(int) * s.value_rows.size(), cudaMemcpyHostToDevice, h->stream);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(h->d_jac_pos, s.jac_pos.data(), sizeof(int) * s.jac_pos.size(), cudaMemcpyHostToDevice, h->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
+    if (e != cudaSuccess)
+    {
+        std::string msg = std::string("device allocation failed: ") + cudaGetErrorString(e);
+        b200sqp_destroy(h);
+        return fail(B200SQP_ERR_CUDA, msg);
+    }
+    st.w_eq = st.w_ineq = st.w_b = 2.0;
+    *out = h;
+    return B200SQP_OK;
+}
+
+int b200sqp_destroy(b200sqp_handle h)
+{
+    if (!h) return B200SQP_OK;
+    cudaSetDevice(h->device);
+    if (h->own_stream) cudaStreamSynchronize(h->own_stream);
+    for (void* p : h->allocations) cudaFree(p);
+    if (h->ev_begin) cudaEventDestroy(h->ev_begin);
+    if (h->ev_end) cudaEventDestroy(h->ev_end);
+    if (h->own_stream) cudaStreamDestroy(h->own_stream);
+    delete h;
+    return B200SQP_OK;
+}
+
+int b200sqp_get_dims(b200sqp_handle h, b200sqp_dims* out)
+{
+    if (!h || !out) return fail(B200SQP_ERR_INVALID, "null argument");
+    *out = h->s.dims;
+    return B200SQP_OK;
+}
+
+int b200sqp_set_problem_data(b200sqp_handle h, const double* x0, const double* xref)
+{
+    int rc = checkHandle(h);
+    if (rc) return rc;
+    if (!x0) return fail(B200SQP_ERR_INVALID, "x0 is null");
+    const size_t bytes = sizeof(double) * (size_t)h->B * h->s.nx;
+    CUDA_TRY(cudaMemcpyAsync(h->d_x0_host_order, x0, bytes, cudaMemcpyHostToDevice, h->stream));
+    launchTransposeIn(h->d_x0_host_order, h->s.nx, h->st.x0, h->B, h->S, h->stream);
+    if (xref)
+    {
+        CUDA_TRY(cudaMemcpyAsync(h->d_xref_host_order, xref, bytes, cudaMemcpyHostToDevice, h->stream));
+        launchTransposeIn(h->d_xref_host_order, h->s.nx, h->st.xref, h->B, h->S, h->stream);
+        h->launches += 1;
+    }
+    else
+        CUDA_TRY(cudaMemsetAsync(h->st.xref, 0, sizeof(double) * (size_t)h->S * h->s.nx, h->stream));
+    h->launches += 1;
+    // fixed goal components follow the reference: _xf.values()[i] = xref[i] (full_discretization_grid_base.cpp:102-106)
+    const int nb = h->s.nb, xo = h->s.nu + h->s.vt;
+    for (int i = 0; i < h->s.nx; ++i)
+        if (h->s.xfFixed(i))
+            for (int b = 0; b < 2; ++b)
+                CUDA_TRY(cudaMemcpyAsync(h->st.z[b] + ((size_t)(h->s.K - 1) * nb + xo + i) * h->S, h->st.xref + (size_t)i * h->S,
+                                         sizeof(double) * h->S, cudaMemcpyDeviceToDevice, h->stream));
+    CUDA_TRY(cudaGetLastError());
+    return B200SQP_OK;
+}
+
+int b200sqp_initialize_trajectories(b200sqp_handle h)
+{
+    int rc = checkHandle(h);
+    if (rc) return rc;
+    launchInitTrajectories(h->st.x0, h->st.xref, h->st.z[0], h->st.cur, h->s.K, h->s.nx, h->s.nu, h->s.vt, h->s.ocp.dt_ref, nullptr, h->B, h->S,
+                           h->stream);
+    h->launches += 1;
+    CUDA_TRY(cudaGetLastError());
+    return B200SQP_OK;
+}
+
+int b200sqp_set_params(b200sqp_handle h, const double* params)
+{
+    int rc = checkHandle(h);
+    if (rc) return rc;
+    if (!params) return fail(B200SQP_ERR_INVALID, "params is null");
+    const int n = h->s.dims.n_params;
+    CUDA_TRY(cudaMemcpyAsync(h->d_params, params, sizeof(double) * (size_t)h->B * n, cudaMemcpyHostToDevice, h->stream));
+    launchPack(h->d_params, n, h->d_ref_of_internal, h->s.K * h->s.nb, nullptr, h->st.z[0], h->st.cur, h->st.z[1], h->B, h->S, h->stream);
+    h->launches += 1;
+    CUDA_TRY(cudaGetLastError());
+    return B200SQP_OK;
+}
+
+int b200sqp_get_params(b200sqp_handle h, double* params)
+{
+    int rc = checkHandle(h);
+    if (rc) return rc;
+    if (!params) return fail(B200SQP_ERR_INVALID, "params is null");
+    const int n = h->s.dims.n_params;
+    launchUnpack(h->st.z[0], h->st.z[1], h->st.cur, h->d_internal_of_ref, n, h->d_params, h->B, h->S, h->stream);
+    h->launches += 1;
+    CUDA_TRY(cudaGetLastError());
+    CUDA_TRY(cudaMemcpyAsync(params, h->d_params, sizeof(double) * (size_t)h->B * n, cudaMemcpyDeviceToHost, h->stream));
+    CUDA_TRY(cudaStreamSynchronize(h->stream));
+    return B200SQP_OK;
+}
+
+int b200sqp_get_first_controls(b200sqp_handle h, double* u0)
+{
+    int rc = checkHandle(h);
+    if (rc) return rc;
+    if (!u0) return fail(B200SQP_ERR_INVALID, "u0 is null");
+    launchFirstControls(h->st.z[0], h->st.z[1], h->st.cur, h->s.nu, h->d_u0, h->B, h->S, h->stream);
+    h->launches += 1;
+    CUDA_TRY(cudaGetLastError());
+    CUDA_TRY(cudaMemcpyAsync(u0, h->d_u0, sizeof(double) * (size_t)h->B * h->s.nu, cudaMemcpyDeviceToHost, h->stream));
+    CUDA_TRY(cudaStreamSynchronize(h->stream));
+    return B200SQP_OK;
+}
+
+int b200sqp_solve_async(b200sqp_handle h, const b200sqp_lm_options* opts, int32_t new_run)
+{
+    int rc = checkHandle(h);
+    if (rc) return rc;
+    if (!opts || opts->iterations < 0) return fail(B200SQP_ERR_INVALID, "bad options");
+    rc = ensureTrace(h, opts->iterations);
+    if (rc) return rc;
+    updateWeights(h, *opts, new_run != 0);
+    CUDA_TRY(cudaEventRecord(h->ev_begin, h->stream));
+    h->kernels->solve(h->P, h->st, opts->iterations, h->stream);
+    h->launches += 1;
+    CUDA_TRY(cudaGetLastError());
+    CUDA_TRY(cudaEventRecord(h->ev_end, h->stream));
+    h->timed = true;
+    return B200SQP_OK;
+}
+
+int b200sqp_synchronize(b200sqp_handle h)
+{
+    int rc = checkHandle(h);
+    if (rc) return rc;
+    CUDA_TRY(cudaStreamSynchronize(h->stream));
+    return B200SQP_OK;
+}
+
+int b200sqp_solve(b200sqp_handle h, const b200sqp_lm_options* opts, int32_t new_run, int32_t* status, double* chi2)
+{
+    int rc = b200sqp_solve_async(h, opts, new_run);
+    if (rc) return rc;
+    if (status) CUDA_TRY(cudaMemcpyAsync(status, h->st.status, sizeof(int32_t) * h->B, cudaMemcpyDeviceToHost, h->stream));
+    if (chi2) CUDA_TRY(cudaMemcpyAsync(chi2, h->st.chi2, sizeof(double) * h->B, cudaMemcpyDeviceToHost, h->stream));
+    CUDA_TRY(cudaStreamSynchronize(h->stream));
+    return B200SQP_OK;
+}
+
+int b200sqp_step(b200sqp_handle h, const b200sqp_lm_options* opts, int32_t cold_start, const double* x0, const double* xref, double* params_out,
+                 double* chi2_out, int32_t* status_out)
+{
+    int rc = b200sqp_set_problem_data(h, x0, xref);
+    if (rc) return rc;
+    if (cold_start)
+    {
+        rc = b200sqp_initialize_trajectories(h);
+        if (rc) return rc;
+    }
+    rc = b200sqp_solve_async(h, opts, 1);
+    if (rc) return rc;
+    if (params_out)
+    {
+        const int n = h->s.dims.n_params;
+        launchUnpack(h->st.z[0], h->st.z[1], h->st.cur, h->d_internal_of_ref, n, h->d_params, h->B, h->S, h->stream);
+        h->launches += 1;
+        CUDA_TRY(cudaGetLastError());
+        CUDA_TRY(cudaMemcpyAsync(params_out, h->d_params, sizeof(double) * (size_t)h->B * n, cudaMemcpyDeviceToHost, h->stream));
+    }
+    if (status_out) CUDA_TRY(cudaMemcpyAsync(status_out, h->st.status, sizeof(int32_t) * h->B, cudaMemcpyDeviceToHost, h->stream));
+    if (chi2_out) CUDA_TRY(cudaMemcpyAsync(chi2_out, h->st.chi2, sizeof(double) * h->B, cudaMemcpyDeviceToHost, h->stream));
+    CUDA_TRY(cudaStreamSynchronize(h->stream));
+    return B200SQP_OK;
+}
+
+int b200sqp_evaluate(b200sqp_handle h, double weight_eq, double weight_ineq, double weight_bounds, double* values, double* jac_values)
+{
+    int rc = checkHandle(h);
+    if (rc) return rc;
+    const b200sqp_dims& d = h->s.dims;
+    const size_t m = (size_t)d.m_lsq + d.m_eq + d.m_ineq + d.m_bounds, nnz = d.nnz_jacobian;
+    if (!h->d_values)
+    {
+        CUDA_TRY(h->alloc(&h->d_values, m * h->S));
+        CUDA_TRY(h->alloc(&h->d_jac, nnz * h->S));
+        CUDA_TRY(h->alloc(&h->d_eval_out, (size_t)h->B * (m > nnz ? m : nnz)));
+    }
+    CUDA_TRY(cudaMemsetAsync(h->d_values, 0, sizeof(double) * m * h->S, h->stream));
+    CUDA_TRY(cudaMemsetAsync(h->d_jac, 0, sizeof(double) * nnz * h->S, h->stream));
+    DeviceState st = h->st;
+    st.w_eq        = weight_eq;
+    st.w_ineq      = weight_ineq;
+    st.w_b         = weight_bounds;
+    h->kernels->evaluate(h->P, st, h->d_values, jac_values ? h->d_jac : nullptr, h->d_value_rows, h->d_jac_pos, h->s.values_per_interval,
+                         h->s.jac_per_interval, h->stream);
+    h->launches += 1;
+    CUDA_TRY(cudaGetLastError());
+    if (values)
+    {
+        launchTransposeOut(h->d_values, (int)m, h->d_eval_out, h->B, h->S, h->stream);
+        h->launches += 1;
+        CUDA_TRY(cudaMemcpyAsync(values, h->d_eval_out, sizeof(double) * (size_t)h->B * m, cudaMemcpyDeviceToHost, h->stream));
+        CUDA_TRY(cudaStreamSynchronize(h->stream));
+    }
+    if (jac_values)
+    {
+        launchTransposeOut(h->d_jac, (int)nnz, h->d_eval_out, h->B, h->S, h->stream);
+        h->launches += 1;
+        CUDA_TRY(cudaMemcpyAsync(jac_values, h->d_eval_out, sizeof(double) * (size_t)h->B * nnz, cudaMemcpyDeviceToHost, h->stream));
+        CUDA_TRY(cudaStreamSynchronize(h->stream));
+    }
+    CUDA_TRY(cudaStreamSynchronize(h->stream));
+    return B200SQP_OK;
+}
+
+int b200sqp_get_statistics(b200sqp_handle h, int32_t* inner_passes, int32_t* rejects, int32_t* relinearizations, double* mu, double* rho)
+{
+    int rc = checkHandle(h);
+    if (rc) return rc;
+    const size_t bi = sizeof(int32_t) * h->B, bd = sizeof(double) * h->B;
+    if (inner_passes) CUDA_TRY(cudaMemcpyAsync(inner_passes, h->st.n_factor, bi, cudaMemcpyDeviceToHost, h->stream));
+    if (rejects) CUDA_TRY(cudaMemcpyAsync(rejects, h->st.n_reject, bi, cudaMemcpyDeviceToHost, h->stream));
+    if (relinearizations) CUDA_TRY(cudaMemcpyAsync(relinearizations, h->st.n_linearize, bi, cudaMemcpyDeviceToHost, h->stream));
+    if (mu) CUDA_TRY(cudaMemcpyAsync(mu, h->st.mu, bd, cudaMemcpyDeviceToHost, h->stream));
+    if (rho) CUDA_TRY(cudaMemcpyAsync(rho, h->st.rho, bd, cudaMemcpyDeviceToHost, h->stream));
+    CUDA_TRY(cudaStreamSynchronize(h->stream));
+    return B200SQP_OK;
+}
+
+int b200sqp_get_chi2_trace(b200sqp_handle h, double* trace, int32_t iterations)
+{
+    int rc = checkHandle(h);
+    if (rc) return rc;
+    if (!trace || !h->st.trace || iterations > h->max_iterations) return fail(B200SQP_ERR_INVALID, "no trace of that length recorded");
+    std::vector<double> tmp((size_t)(iterations + 1) * h->S);
+    CUDA_TRY(cudaMemcpyAsync(tmp.data(), h->st.trace, sizeof(double) * tmp.size(), cudaMemcpyDeviceToHost, h->stream));
+    CUDA_TRY(cudaStreamSynchronize(h->stream));
+    for (int i = 0; i < h->B; ++i)
+        for (int k = 0; k <= iterations; ++k) trace[(size_t)i * (iterations + 1) + k] = tmp[(size_t)k * h->S + i];
+    return B200SQP_OK;
+}
+
+int b200sqp_last_solve_ms(b200sqp_handle h, float* ms)
+{
+    int rc = checkHandle(h);
+    if (rc) return rc;
+    if (!ms || !h->timed) return fail(B200SQP_ERR_INVALID, "no solve recorded");
+    CUDA_TRY(cudaEventSynchronize(h->ev_end));
+    CUDA_TRY(cudaEventElapsedTime(ms, h->ev_begin, h->ev_end));
+    return B200SQP_OK;
+}
+
+int b200sqp_launch_count(b200sqp_handle h, int64_t* launches)
+{
+    if (!h || !launches) return fail(B200SQP_ERR_INVALID, "null argument");
+    *launches = h->launches;
+    return B200SQP_OK;
+}
+
+int b200sqp_device_pointers(b200sqp_handle h, void** chi2, void** status, void** x0)
+{
+    if (!h) return fail(B200SQP_ERR_INVALID, "null handle");
+    if (chi2) *chi2 = h->st.chi2;
+    if (status) *status = h->st.status;
+    if (x0) *x0 = h->d_x0_host_order;
+    return B200SQP_OK;
+}
+
+int b200sqp_set_stream(b200sqp_handle h, void* cuda_stream)
+{
+    if (!h) return fail(B200SQP_ERR_INVALID, "null handle");
+    h->stream = cuda_stream ? (cudaStream_t)cuda_stream : h->own_stream;
+    return B200SQP_OK;
+}
+
+}  // extern "C"

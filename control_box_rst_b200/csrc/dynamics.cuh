@@ -1,0 +1,193 @@
+// Device functors of the closed system-dynamics registry (include/b200sqp.h: b200sqp_dynamics) and of the defect constraints
+// built on them.
+//
+// The whole translation unit is compiled with --fmad=false: the reference evaluates these expressions with g++ on x86-64 without
+// FMA contraction, and its central-difference Jacobians (delta = 1e-9) amplify every last-bit difference by 5e8
+// (SURVEY.md "FD-noise parity").  Expression order below therefore follows the reference sources term by term; fused
+// multiply-adds are only used where this project's own linear algebra asks for them explicitly via fma().
+//
+// Reference: corbo::SystemDynamicsInterface::dynamics, src/systems/include/corbo-systems/system_dynamics_interface.h:121
+#pragma once
+
+#include "../../include/b200sqp.h"
+#include "dynamics_ids.h"
+#include "lm_device_types.h"
+
+namespace b200sqp {
+
+// VanDerPolOscillator::dynamics -- src/systems/include/corbo-systems/benchmark/nonlinear_benchmark_systems.h:52-60
+struct VanDerPol
+{
+    static constexpr int NX = 2, NU = 1, ID = B200SQP_DYN_VAN_DER_POL;
+    __device__ __forceinline__ static void f(const DynParams& c, const double* x, const double* u, double* out)
+    {
+        out[0] = x[1];
+        out[1] = -c.p[0] * (x[0] * x[0] - 1) * x[1] - x[0] + u[0];
+    }
+};
+
+// DuffingOscillator::dynamics -- nonlinear_benchmark_systems.h:108-117; p = damping, spring_alpha, spring_beta
+struct Duffing
+{
+    static constexpr int NX = 2, NU = 1, ID = B200SQP_DYN_DUFFING;
+    __device__ __forceinline__ static void f(const DynParams& c, const double* x, const double* u, double* out)
+    {
+        out[0] = x[1];
+        out[1] = -c.p[0] * x[1] - c.p[1] * x[0] - c.p[2] * x[0] * x[0] * x[0] + u[0];
+    }
+};
+
+// SimplePendulum::dynamics -- nonlinear_benchmark_systems.h:207-216; p = m, l, g, rho
+struct SimplePendulum
+{
+    static constexpr int NX = 2, NU = 1, ID = B200SQP_DYN_SIMPLE_PENDULUM;
+    __device__ __forceinline__ static void f(const DynParams& c, const double* x, const double* u, double* out)
+    {
+        out[0] = x[1];
+        out[1] = u[0] - c.p[3] / (c.p[0] * c.p[1] * c.p[1]) * x[1] - c.p[2] / c.p[1] * sin(x[0]);
+    }
+};
+
+// CartPole::dynamics -- nonlinear_benchmark_systems.h:337-352; the reference keeps mc, mp, l, g as private constants (:390-394)
+struct CartPole
+{
+    static constexpr int NX = 4, NU = 1, ID = B200SQP_DYN_CART_POLE;
+    __device__ __forceinline__ static void f(const DynParams&, const double* x, const double* u, double* out)
+    {
+        const double mc = 1.0, mp = 0.3, l = 0.5, g = 9.81;
+        const double s = sin(x[1]), co = cos(x[1]);
+        double sin_phi_phidot_sq = s * x[3] * x[3];
+        double denum             = mc + mp * (1 - co * co);  // std::pow(cos, 2) == cos*cos in IEEE arithmetic
+        out[0]                   = x[2];
+        out[1]                   = x[3];
+        out[2]                   = (l * mp * sin_phi_phidot_sq + u[0] + mp * g * co * s) / denum;
+        out[3]                   = -(l * mp * co * sin_phi_phidot_sq + u[0] * co + (mp + mc) * g * s) / (l * denum);
+    }
+};
+
+// SerialIntegratorSystem(dimension 2)::dynamics -- linear_benchmark_systems.h:71-82; p = time constant
+struct DoubleIntegrator
+{
+    static constexpr int NX = 2, NU = 1, ID = B200SQP_DYN_DOUBLE_INTEGRATOR;
+    __device__ __forceinline__ static void f(const DynParams& c, const double* x, const double* u, double* out)
+    {
+        out[0] = x[1];
+        out[1] = u[0] / c.p[0];
+    }
+};
+
+// New model (absent from the reference; same equations as oracle/ref_models.h Unicycle)
+struct Unicycle
+{
+    static constexpr int NX = 3, NU = 2, ID = B200SQP_DYN_UNICYCLE;
+    __device__ __forceinline__ static void f(const DynParams&, const double* x, const double* u, double* out)
+    {
+        out[0] = u[0] * cos(x[2]);
+        out[1] = u[0] * sin(x[2]);
+        out[2] = u[1];
+    }
+};
+
+// New model (absent from the reference; same equations as oracle/ref_models.h Quadrotor); p = m, g, Ixx, Iyy, Izz
+struct Quadrotor
+{
+    static constexpr int NX = 12, NU = 4, ID = B200SQP_DYN_QUADROTOR;
+    __device__ __forceinline__ static void f(const DynParams& c, const double* x, const double* u, double* out)
+    {
+        const double sphi = sin(x[3]), cphi = cos(x[3]);
+        const double sth = sin(x[4]), cth = cos(x[4]);
+        const double spsi = sin(x[5]), cpsi = cos(x[5]);
+        const double p = x[9], q = x[10], r = x[11];
+        const double tm = u[0] / c.p[0];
+        out[0]          = x[6];
+        out[1]          = x[7];
+        out[2]          = x[8];
+        const double qr = q * sphi + r * cphi;
+        out[3]          = p + qr * (sth / cth);
+        out[4]          = q * cphi - r * sphi;
+        out[5]          = qr / cth;
+        out[6]          = (cphi * sth * cpsi + sphi * spsi) * tm;
+        out[7]          = (cphi * sth * spsi - sphi * cpsi) * tm;
+        out[8]          = cphi * cth * tm - c.p[1];
+        out[9]          = (u[1] + (c.p[3] - c.p[4]) * q * r) / c.p[2];
+        out[10]         = (u[2] + (c.p[4] - c.p[2]) * p * r) / c.p[3];
+        out[11]         = (u[3] + (c.p[2] - c.p[3]) * p * q) / c.p[4];
+    }
+};
+
+// ---------------------------------------------------------------------------------------------------------------------------
+// Defect of one interval, e(x1, u1, x2, dt): FDCollocationEdge::computeValues
+// (src/optimal_control/include/corbo-optimal-control/structured_ocp/edges/finite_differences_collocation_edges.h:71-80) over
+// FiniteDifferencesCollocationInterface::computeEqualityConstraint (src/numerics/include/corbo-numerics/finite_differences_collocation.h)
+// and MSVariableDynamicsOnlyEdge::computeValues (.../edges/multiple_shooting_edges.h:125-134) over
+// NumericalIntegratorExplicitInterface::computeEqualityConstraint (src/numerics/include/corbo-numerics/integrator_interface.h:217-222).
+// DEFECT ids: 0..3 = b200sqp_collocation, 4 = explicit Euler shooting, 5 = RK4 shooting.
+// ---------------------------------------------------------------------------------------------------------------------------
+
+template <class M, int DEFECT>
+__device__ __forceinline__ void defect(const DynParams& c, const double* x1, const double* u1, const double* x2, double dt, double* e)
+{
+    constexpr int NX = M::NX;
+    if (DEFECT == DEFECT_FORWARD)  // finite_differences_collocation.h:119-136
+    {
+        M::f(c, x1, u1, e);
+#pragma unroll
+        for (int i = 0; i < NX; ++i) e[i] -= (x2[i] - x1[i]) / dt;
+    }
+    else if (DEFECT == DEFECT_BACKWARD)  // :153-170
+    {
+        M::f(c, x2, u1, e);
+#pragma unroll
+        for (int i = 0; i < NX; ++i) e[i] -= (x2[i] - x1[i]) / dt;
+    }
+    else if (DEFECT == DEFECT_MIDPOINT)  // :187-204
+    {
+        double xm[NX];
+#pragma unroll
+        for (int i = 0; i < NX; ++i) xm[i] = 0.5 * (x1[i] + x2[i]);
+        M::f(c, xm, u1, e);
+#pragma unroll
+        for (int i = 0; i < NX; ++i) e[i] -= (x2[i] - x1[i]) / dt;
+    }
+    else if (DEFECT == DEFECT_CRANK_NICOLSON)  // :221-240
+    {
+        double f1[NX], f2[NX];
+        M::f(c, x1, u1, f1);
+        M::f(c, x2, u1, f2);
+#pragma unroll
+        for (int i = 0; i < NX; ++i) e[i] = (x2[i] - x1[i]) / dt - 0.5 * (f1[i] + f2[i]);
+    }
+    else if (DEFECT == DEFECT_EULER)  // explicit_integrators.h:66-72, then "- x2"
+    {
+        double k1[NX];
+        M::f(c, x1, u1, k1);
+#pragma unroll
+        for (int i = 0; i < NX; ++i) e[i] = (k1[i] * dt + x1[i]) - x2[i];
+    }
+    else  // RK4: explicit_integrators.h:280-295, then "- x2"
+    {
+        double k1[NX], k2[NX], k3[NX], k4[NX], xt[NX];
+        M::f(c, x1, u1, k1);
+#pragma unroll
+        for (int i = 0; i < NX; ++i) k1[i] *= dt;
+#pragma unroll
+        for (int i = 0; i < NX; ++i) xt[i] = x1[i] + k1[i] / 2.0;
+        M::f(c, xt, u1, k2);
+#pragma unroll
+        for (int i = 0; i < NX; ++i) k2[i] *= dt;
+#pragma unroll
+        for (int i = 0; i < NX; ++i) xt[i] = x1[i] + k2[i] / 2.0;
+        M::f(c, xt, u1, k3);
+#pragma unroll
+        for (int i = 0; i < NX; ++i) k3[i] *= dt;
+#pragma unroll
+        for (int i = 0; i < NX; ++i) xt[i] = x1[i] + k3[i];
+        M::f(c, xt, u1, k4);
+#pragma unroll
+        for (int i = 0; i < NX; ++i) k4[i] *= dt;
+#pragma unroll
+        for (int i = 0; i < NX; ++i) e[i] = (x1[i] + (k1[i] + 2.0 * k2[i] + 2.0 * k3[i] + k4[i]) / 6.0) - x2[i];
+    }
+}
+
+}  // namespace b200sqp

@@ -1,0 +1,43 @@
+// Host-visible launch table: the C ABI (api.cpp) never sees a kernel template, only these function pointers.
+#pragma once
+
+#include <cuda_runtime.h>
+
+namespace b200sqp {
+
+struct DeviceOcp;
+struct DeviceState;
+
+struct KernelSet
+{
+    int dynamics, defect, vt, nx, nu;
+    void (*solve)(const DeviceOcp&, const DeviceState&, int iterations, cudaStream_t);
+    void (*evaluate)(const DeviceOcp&, const DeviceState&, double* values, double* jac, const int* value_rows, const int* jac_pos, int v_count,
+                     int j_count, cudaStream_t);
+};
+
+// closed registry (kernels_*.cu); nullptr = combination not compiled in -> B200SQP_ERR_UNSUPPORTED, never a CPU fallback
+const KernelSet* findKernels(int dynamics, int defect, int vt);
+
+// one table per translation unit so that the heavy templates compile in parallel
+const KernelSet* kernelTableOscillators(int* count);
+const KernelSet* kernelTableCartPole(int* count);
+const KernelSet* kernelTableUnicycle(int* count);
+const KernelSet* kernelTableQuadrotor(int* count);
+
+// layout helpers (util_kernels.cu); all arrays device pointers
+// params [B][n] (reference order)  <->  z [K*NB][S] (block order, instance-minor); pinned slots (ref index -1) are filled from `pinned`
+void launchPack(const double* params, int n, const int* ref_of_internal, int slots, const double* pinned_values /*[slots] or null*/, double* z,
+                const int* cur_or_null, double* z_alt, int B, int S, cudaStream_t);
+void launchUnpack(const double* z0, const double* z1, const int* cur, const int* internal_of_ref, int n, double* params, int B, int S, cudaStream_t);
+// x0/xref: [B][nx] -> [nx][S]
+void launchTransposeIn(const double* src, int dim, double* dst, int B, int S, cudaStream_t);
+// [rows][S] -> [B][rows]
+void launchTransposeOut(const double* src, int rows, double* dst, int B, int S, cudaStream_t);
+// FullDiscretizationGridBase::initializeSequences (full_discretization_grid_base.cpp:134-179) on the device
+void launchInitTrajectories(const double* x0 /*[nx][S]*/, const double* xref /*[nx][S]*/, double* z, int* cur, int K, int nx, int nu, int vt,
+                            double dt_ref, const int* xf_fixed_dev, int B, int S, cudaStream_t);
+// u_0 of every instance -> [B][nu]
+void launchFirstControls(const double* z0, const double* z1, const int* cur, int nu, double* u0, int B, int S, cudaStream_t);
+
+}  // namespace b200sqp

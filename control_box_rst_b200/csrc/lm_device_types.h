@@ -1,0 +1,57 @@
+// Plain structs shared by host (api.cpp) and device code: the per-structure constants and the per-handle device arrays.
+#pragma once
+
+#include "../../include/b200sqp.h"
+
+namespace b200sqp {
+
+struct DynParams
+{
+    double p[B200SQP_MAX_DYN_PARAMS];
+};
+
+struct DeviceOcp
+{
+    int K;       // intervals
+    int B;       // instances
+    int S;       // instance stride of all instance-minor arrays (B rounded up to a multiple of 32)
+    int stage_cost, final_cost, tcost_every_interval;
+    int xf_fixed[B200SQP_MAX_NX];
+    int x_bounded[B200SQP_MAX_NX], u_bounded[B200SQP_MAX_NU], dt_bounded;
+    DynParams dyn;
+    double dt_ref, dt_lb, dt_ub, tcost_w;
+    double q_sqrt[B200SQP_MAX_NX], r_sqrt[B200SQP_MAX_NU], qf_sqrt[B200SQP_MAX_NX];
+    double x_lb[B200SQP_MAX_NX], x_ub[B200SQP_MAX_NX], u_lb[B200SQP_MAX_NU], u_ub[B200SQP_MAX_NU];
+};
+
+struct Weights
+{
+    double eq, ineq, b;
+};
+
+// per-handle device arrays (all instance-minor unless noted)
+struct DeviceState
+{
+    double* z[2];     // [K*NB][S] two parameter buffers: current and trial (roles swap per instance on accept)
+    double* x0;       // [NX][S]
+    double* xref;     // [NX][S]
+    double* D;        // [K*ND][S] diagonal blocks of J^T J (packed lower)
+    double* E;        // [K*NB*NX][S] sub-diagonal coupling blocks
+    double* g;        // [K*NB][S]  J^T(-r)
+    double* dl;       // [K*NB][S]  step
+    double* L;        // [K*ND][S]  factor, diagonal blocks (reciprocal diagonal stored)
+    double* W;        // [K*NB*NX][S] factor, sub-diagonal blocks
+    // per instance results / LM state, [S]
+    double* chi2;
+    double* mu;
+    double* rho;
+    int* status;
+    int* cur;         // which of z[0]/z[1] holds the current parameters
+    int* n_factor;
+    int* n_reject;
+    int* n_linearize;
+    double* trace;    // [(max_iterations+1)][S] chi2 after every outer iteration
+    double w_eq, w_ineq, w_b;  // current penalty weights (host-managed: reset / adapted per solve)
+};
+
+}  // namespace b200sqp

@@ -1,0 +1,99 @@
+// Host-side structure of one OCP: dimensions, the reference's vertex/edge indexing, the CSC pattern of the combined Jacobian
+// and the device-side block layout.  No CUDA in here: these functions back the handle-less part of the C ABI
+// (b200sqp_dims_of / _vertex_indices / _edge_indices / _jacobian_pattern) and run on machines without a GPU.
+//
+// Indexing rules restated from the reference (paths relative to /root/reference/src):
+//   vertex index = prefix sum of unfixed dimensions over the active vertices       optimization/src/hyper_graph/vertex_set.cpp:405-418
+//   active order = [x_k?, u_k, dt_k?] per interval, then xf                         optimal_control/src/structured_ocp/discretization_grids/
+//                                                                                   full_discretization_grid_base.cpp:514-527,
+//                                                                                   non_uniform_full_discretization_grid_base.cpp:454-467,
+//                                                                                   shooting_grid_base.cpp:583-598
+//   edge index   = prefix sum of edge dimensions per category in creation order     optimization/src/hyper_graph/edge_set.cpp:31-42,101-166
+//   creation order per interval: state cost, control cost, dt cost (twice), dynamics  optimal_control/src/functions/nlp_functions.cpp:70-132,
+//                                                                                   .../finite_differences_grid.cpp:38-154
+//   Jacobian rows: lsq | equalities | inequalities | bounds                         optimization/src/hyper_graph/
+//                                                                                   hyper_graph_optimization_problem_edge_based.cpp:1491-1493
+#pragma once
+
+#include <cstdint>
+#include <string>
+#include <vector>
+
+#include "../../include/b200sqp.h"
+
+namespace b200sqp {
+
+constexpr double kCorboInf = 2e30;  // CORBO_INF_DBL, core/include/corbo-core/types.h:53
+
+struct Structure
+{
+    b200sqp_ocp ocp;
+    int K = 0;         // intervals = N-1
+    int nx = 0, nu = 0;
+    int vt = 0;        // 1: one free dt per interval (non-uniform grid)
+    int nb = 0;        // device block dimension nu + vt + nx, block k = [u_k, dt_k, x_{k+1}]
+    int defect = 0;    // DEFECT_* id (dynamics.cuh)
+    b200sqp_dims dims{};
+
+    // reference indexing
+    std::vector<int32_t> x_idx, u_idx, dt_idx;                 // [N], [K], [K]; -1 = fixed
+    std::vector<int32_t> state_cost_idx, control_cost_idx;     // [K] lsq row offsets, -1 = absent
+    std::vector<int32_t> dt_cost_idx;                          // [2K]
+    std::vector<int32_t> dynamics_idx;                         // [K] equality row offsets
+    int32_t final_cost_idx = -1;
+    std::vector<int32_t> bound_row;                            // [n] row offset inside the bounds block or -1
+    std::vector<int32_t> col_ptr, row_idx;                     // CSC pattern of the combined Jacobian
+
+    // device layout <-> reference parameter order
+    std::vector<int32_t> ref_of_internal;                      // [K*nb] reference parameter index of internal slot, -1 = fixed component
+    std::vector<int32_t> internal_of_ref;                      // [n]
+
+    // per-interval scatter tables for b200sqp_evaluate (values rows and CSC positions), see lm_device.cuh
+    std::vector<int32_t> value_rows;                           // [K * values_per_interval]
+    std::vector<int32_t> jac_pos;                              // [K * jac_per_interval]
+    int values_per_interval = 0, jac_per_interval = 0;
+
+    bool xfFixed(int i) const { return ocp.xf_fixed[i] != 0; }
+    bool xfFullyFixed() const
+    {
+        for (int i = 0; i < nx; ++i)
+            if (!xfFixed(i)) return false;
+        return true;
+    }
+};
+
+// Validates the descriptor against the closed registry and fills everything above.  Returns B200SQP_OK or an error code and
+// leaves a message in `err`.
+int buildStructure(const b200sqp_ocp& ocp, Structure& s, std::string& err);
+
+// layout of the per-interval tables (shared by structure.cpp and the materialising kernel)
+struct EvalLayout
+{
+    int nx, nu, vt;
+    // values rows per interval: [x0 cost nx | control cost nu | dt cost 2 | cost on x_{k+1} nx | defect nx | bounds u nu | bound dt 1 |
+    //                            bounds x_{k+1} nx]
+    int v_x0c() const { return 0; }
+    int v_uc() const { return nx; }
+    int v_tc() const { return nx + nu; }
+    int v_xs() const { return nx + nu + 2; }
+    int v_e() const { return 2 * nx + nu + 2; }
+    int v_ub() const { return 3 * nx + nu + 2; }
+    int v_tb() const { return 3 * nx + 2 * nu + 2; }
+    int v_xb() const { return 3 * nx + 2 * nu + 3; }
+    int v_count() const { return 4 * nx + 2 * nu + 3; }
+    // Jacobian positions per interval: [uc diag nu | tc 2 | xs diag nx | A nx*nx (col-major) | Bu nx*nu | Bt nx | C nx*nx |
+    //                                   bounds u nu | bound dt 1 | bounds x_{k+1} nx]
+    int j_uc() const { return 0; }
+    int j_tc() const { return nu; }
+    int j_xs() const { return nu + 2; }
+    int j_A() const { return nu + 2 + nx; }
+    int j_Bu() const { return j_A() + nx * nx; }
+    int j_Bt() const { return j_Bu() + nx * nu; }
+    int j_C() const { return j_Bt() + nx; }
+    int j_ub() const { return j_C() + nx * nx; }
+    int j_tb() const { return j_ub() + nu; }
+    int j_xb() const { return j_tb() + 1; }
+    int j_count() const { return j_xb() + nx; }
+};
+
+}  // namespace b200sqp

@@ -1,0 +1,128 @@
+// Layout kernels around the solver: host-order <-> instance-minor conversions, trajectory initialisation, first-control gather.
+// All are one-thread-per-instance (writes/reads of the instance-minor side coalesce; the host-order side is a short strided walk
+// through L1/L2) -- they move a few MB per solve and are not on the roofline-relevant path.
+#include "launch.h"
+
+namespace b200sqp {
+
+namespace {
+
+__global__ void packKernel(const double* __restrict__ params, int n, const int* __restrict__ ref_of_internal, int slots,
+                           const double* __restrict__ pinned, double* __restrict__ z, const int* __restrict__ cur, double* __restrict__ z_alt, int B,
+                           int S)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= B) return;
+    double* dst = (cur && cur[i]) ? z_alt : z;
+    for (int s = 0; s < slots; ++s)
+    {
+        const int r = ref_of_internal[s];
+        double v;
+        if (r >= 0)
+            v = params[(size_t)i * n + r];
+        else
+            v = pinned ? pinned[(size_t)s * S + i] : dst[(size_t)s * S + i];
+        dst[(size_t)s * S + i] = v;
+    }
+}
+
+__global__ void unpackKernel(const double* __restrict__ z0, const double* __restrict__ z1, const int* __restrict__ cur,
+                             const int* __restrict__ internal_of_ref, int n, double* __restrict__ params, int B, int S)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= B) return;
+    const double* src = cur[i] ? z1 : z0;
+    for (int r = 0; r < n; ++r) params[(size_t)i * n + r] = src[(size_t)internal_of_ref[r] * S + i];
+}
+
+__global__ void transposeInKernel(const double* __restrict__ src, int dim, double* __restrict__ dst, int B, int S)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= B) return;
+    for (int j = 0; j < dim; ++j) dst[(size_t)j * S + i] = src[(size_t)i * dim + j];
+}
+
+__global__ void transposeOutKernel(const double* __restrict__ src, int rows, double* __restrict__ dst, int B, int S)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= B) return;
+    for (int j = 0; j < rows; ++j) dst[(size_t)i * rows + j] = src[(size_t)j * S + i];
+}
+
+// FullDiscretizationGridBase::initializeSequences (optimal_control/src/structured_ocp/discretization_grids/
+// full_discretization_grid_base.cpp:134-179; same code in non_uniform_full_discretization_grid_base.cpp:146-190 and
+// shooting_grid_base.cpp:141-200): dir = (xf - x0)/||xf - x0||, step = ||xf - x0||/(N-1), x_k = x0 + k*step*dir, u_k = uref = 0,
+// dt_k = dt_ref, xf = xref.
+__global__ void initTrajectoriesKernel(const double* __restrict__ x0, const double* __restrict__ xref, double* __restrict__ z, int* __restrict__ cur,
+                                       int K, int nx, int nu, int vt, double dt_ref, int B, int S)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= B) return;
+    const int nb = nu + vt + nx;
+    double dist  = 0.0;
+    for (int j = 0; j < nx; ++j)
+    {
+        const double d = xref[(size_t)j * S + i] - x0[(size_t)j * S + i];
+        dist += d * d;
+    }
+    dist              = sqrt(dist);
+    const double step = dist / K;
+    for (int k = 0; k < K; ++k)
+    {
+        double* zk = z + (size_t)k * nb * S + i;
+        for (int j = 0; j < nu; ++j) zk[(size_t)j * S] = 0.0;
+        if (vt) zk[(size_t)nu * S] = dt_ref;
+        for (int j = 0; j < nx; ++j)
+        {
+            const double a = x0[(size_t)j * S + i], b = xref[(size_t)j * S + i];
+            double dir     = b - a;
+            if (dist != 0) dir /= dist;
+            // block k holds x_{k+1}; the last block holds xf = xref
+            zk[(size_t)(nu + vt + j) * S] = (k + 1 < K) ? a + (double)(k + 1) * step * dir : b;
+        }
+    }
+    cur[i] = 0;
+}
+
+__global__ void firstControlsKernel(const double* __restrict__ z0, const double* __restrict__ z1, const int* __restrict__ cur, int nu,
+                                    double* __restrict__ u0, int B, int S)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= B) return;
+    const double* src = cur[i] ? z1 : z0;
+    for (int j = 0; j < nu; ++j) u0[(size_t)i * nu + j] = src[(size_t)j * S + i];
+}
+
+inline int blocksFor(int B) { return (B + 127) / 128; }
+
+}  // namespace
+
+void launchPack(const double* params, int n, const int* ref_of_internal, int slots, const double* pinned, double* z, const int* cur, double* z_alt,
+                int B, int S, cudaStream_t st)
+{
+    packKernel<<<blocksFor(B), 128, 0, st>>>(params, n, ref_of_internal, slots, pinned, z, cur, z_alt, B, S);
+}
+void launchUnpack(const double* z0, const double* z1, const int* cur, const int* internal_of_ref, int n, double* params, int B, int S,
+                  cudaStream_t st)
+{
+    unpackKernel<<<blocksFor(B), 128, 0, st>>>(z0, z1, cur, internal_of_ref, n, params, B, S);
+}
+void launchTransposeIn(const double* src, int dim, double* dst, int B, int S, cudaStream_t st)
+{
+    transposeInKernel<<<blocksFor(B), 128, 0, st>>>(src, dim, dst, B, S);
+}
+void launchTransposeOut(const double* src, int rows, double* dst, int B, int S, cudaStream_t st)
+{
+    transposeOutKernel<<<blocksFor(B), 128, 0, st>>>(src, rows, dst, B, S);
+}
+void launchInitTrajectories(const double* x0, const double* xref, double* z, int* cur, int K, int nx, int nu, int vt, double dt_ref,
+                            const int* /*xf_fixed_dev*/, int B, int S, cudaStream_t st)
+{
+    initTrajectoriesKernel<<<blocksFor(B), 128, 0, st>>>(x0, xref, z, cur, K, nx, nu, vt, dt_ref, B, S);
+}
+void launchFirstControls(const double* z0, const double* z1, const int* cur, int nu, double* u0, int B, int S, cudaStream_t st)
+{
+    firstControlsKernel<<<blocksFor(B), 128, 0, st>>>(z0, z1, cur, nu, u0, B, S);
+}
+
+}  // namespace b200sqp

@@ -1,0 +1,249 @@
+"""Python host side over the C ABI of libb200sqp.so (include/b200sqp.h).
+
+`BatchedLevenbergMarquardt` mirrors the reference's solver interface for this path -- corbo::LevenbergMarquardtSparse
+(src/optimization/include/corbo-optimization/solver/levenberg_marquardt_sparse.h:68-163) behind corbo::NlpSolverInterface
+(solver/nlp_solver_interface.h:67-118) -- with the same method names, argument meaning and error behaviour, but for a whole batch
+of independent instances of one OCP structure.  All computation happens in the CUDA library; there is no Python/numpy/CPU fallback:
+if the library or a B200-class device is missing, construction raises.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+from . import _abi as abi
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libb200sqp.so")
+
+_dp = C.POINTER(C.c_double)
+_ip = C.POINTER(C.c_int32)
+
+# every symbol include/b200sqp.h declares (tests check the library exports all of them)
+ABI_SYMBOLS = [
+    "b200sqp_create", "b200sqp_destroy", "b200sqp_last_error", "b200sqp_device_available", "b200sqp_dims_of", "b200sqp_get_dims",
+    "b200sqp_vertex_indices", "b200sqp_edge_indices", "b200sqp_jacobian_pattern", "b200sqp_set_problem_data",
+    "b200sqp_initialize_trajectories", "b200sqp_set_params", "b200sqp_get_params", "b200sqp_get_first_controls", "b200sqp_solve",
+    "b200sqp_solve_async", "b200sqp_synchronize", "b200sqp_step", "b200sqp_evaluate", "b200sqp_get_statistics", "b200sqp_get_chi2_trace",
+    "b200sqp_last_solve_ms", "b200sqp_launch_count", "b200sqp_device_pointers", "b200sqp_set_stream",
+]
+
+
+class B200SqpError(RuntimeError):
+    def __init__(self, code, message):
+        super().__init__(f"b200sqp error {code}: {message}")
+        self.code = code
+
+
+_lib = None
+
+
+def load_library():
+    """dlopen libb200sqp.so (built in-tree by __graft_entry__.build / csrc/Makefile).  Fails loudly if it is missing."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise FileNotFoundError(f"{LIB_PATH} not built: run `python -c 'import __graft_entry__ as g; g.build()'` (needs nvcc); "
+                                    "there is no CPU fallback for the LM hot path")
+        lib = C.CDLL(LIB_PATH)
+        lib.b200sqp_last_error.restype = C.c_char_p
+        for name in ABI_SYMBOLS:
+            if name != "b200sqp_last_error":
+                getattr(lib, name).restype = C.c_int
+        _lib = lib
+    return _lib
+
+
+def _check(rc):
+    if rc != 0:
+        raise B200SqpError(rc, load_library().b200sqp_last_error().decode())
+
+
+def _d(a):
+    return None if a is None else a.ctypes.data_as(_dp)
+
+
+def _i(a):
+    return None if a is None else a.ctypes.data_as(_ip)
+
+
+def device_available():
+    return bool(load_library().b200sqp_device_available())
+
+
+# ---- handle-less structure queries (run without a GPU) -----------------------------------------------------------------------
+def dims_of(ocp):
+    out = abi.Dims()
+    _check(load_library().b200sqp_dims_of(C.byref(ocp), C.byref(out)))
+    return out
+
+
+def vertex_indices(ocp):
+    N = ocp.n_grid
+    x_idx, u_idx, dt_idx = np.full(N, -2, np.int32), np.full(N - 1, -2, np.int32), np.full(N - 1, -2, np.int32)
+    _check(load_library().b200sqp_vertex_indices(C.byref(ocp), _i(x_idx), _i(u_idx), _i(dt_idx)))
+    return x_idx, u_idx, dt_idx
+
+
+def edge_indices(ocp):
+    K = ocp.n_grid - 1
+    sc, cc, tc, dy = np.full(K, -2, np.int32), np.full(K, -2, np.int32), np.full(2 * K, -2, np.int32), np.full(K, -2, np.int32)
+    fc = C.c_int32(-2)
+    _check(load_library().b200sqp_edge_indices(C.byref(ocp), _i(sc), _i(cc), _i(tc), _i(dy), C.byref(fc)))
+    return dict(state_cost=sc, control_cost=cc, dt_cost=tc.reshape(K, 2), dynamics=dy, final_cost=fc.value)
+
+
+def jacobian_pattern(ocp):
+    d = dims_of(ocp)
+    col_ptr, row_idx = np.zeros(d.n_params + 1, np.int32), np.zeros(d.nnz_jacobian, np.int32)
+    _check(load_library().b200sqp_jacobian_pattern(C.byref(ocp), _i(col_ptr), _i(row_idx)))
+    return col_ptr, row_idx
+
+
+class BatchedLevenbergMarquardt:
+    """LevenbergMarquardtSparse for `batch` instances of one OCP structure, resident on one B200.
+
+    Method names follow the reference class: setIterations / setPenaltyWeights / setWeightAdapation / solve / clear.
+    """
+
+    def __init__(self, ocp, batch, device=0):
+        self._lib = load_library()
+        self.ocp = ocp
+        self.batch = int(batch)
+        self.device = int(device)
+        self._h = C.c_void_p()
+        # LevenbergMarquardtSparse defaults (levenberg_marquardt_sparse.h:112-124)
+        self._opts = abi.LmOptions.defaults()
+        _check(self._lib.b200sqp_create(C.byref(ocp), C.c_int32(self.batch), C.c_int32(self.device), C.byref(self._h)))
+        self.dims = abi.Dims()
+        _check(self._lib.b200sqp_get_dims(self._h, C.byref(self.dims)))
+
+    # -- NlpSolverInterface ---------------------------------------------------------------------------------------------------
+    def isLsqSolver(self):
+        return True
+
+    def setIterations(self, iterations):
+        self._opts.iterations = int(iterations)
+
+    def setPenaltyWeights(self, weight_eq, weight_ineq, weight_bounds):
+        self._opts.weight_eq, self._opts.weight_ineq, self._opts.weight_bounds = weight_eq, weight_ineq, weight_bounds
+
+    def setWeightAdapation(self, factor_eq, factor_ineq, factor_bounds, max_eq, max_ineq, max_bounds):
+        o = self._opts
+        o.adapt_factor_eq, o.adapt_factor_ineq, o.adapt_factor_bounds = factor_eq, factor_ineq, factor_bounds
+        o.adapt_max_eq, o.adapt_max_ineq, o.adapt_max_bounds = max_eq, max_ineq, max_bounds
+
+    def solve(self, new_run=True, fetch=True):
+        """LevenbergMarquardtSparse::solve for every instance.  -> (status [B] int32, chi2 [B]) or None when fetch=False
+        (results stay in HBM; use synchronize()/status()/get_params())."""
+        if not fetch:
+            _check(self._lib.b200sqp_solve_async(self._h, C.byref(self._opts), C.c_int32(1 if new_run else 0)))
+            return None
+        status = np.zeros(self.batch, np.int32)
+        chi2 = np.zeros(self.batch)
+        _check(self._lib.b200sqp_solve(self._h, C.byref(self._opts), C.c_int32(1 if new_run else 0), _i(status), _d(chi2)))
+        return status, chi2
+
+    def clear(self):
+        if self._h:
+            self._lib.b200sqp_destroy(self._h)
+            self._h = C.c_void_p()
+
+    close = clear
+
+    def __del__(self):
+        try:
+            self.clear()
+        except Exception:
+            pass
+
+    # -- problem data -------------------------------------------------------------------------------------------------------
+    def set_problem_data(self, x0, xref=None):
+        x0 = np.ascontiguousarray(x0, np.float64)
+        assert x0.shape == (self.batch, self.ocp.nx), x0.shape
+        if xref is not None:
+            xref = np.ascontiguousarray(xref, np.float64)
+            assert xref.shape == x0.shape
+        _check(self._lib.b200sqp_set_problem_data(self._h, _d(x0), _d(xref)))
+
+    def initialize_trajectories(self):
+        _check(self._lib.b200sqp_initialize_trajectories(self._h))
+
+    def set_params(self, params):
+        params = np.ascontiguousarray(params, np.float64)
+        assert params.shape == (self.batch, self.dims.n_params), params.shape
+        _check(self._lib.b200sqp_set_params(self._h, _d(params)))
+
+    def get_params(self):
+        out = np.zeros((self.batch, self.dims.n_params))
+        _check(self._lib.b200sqp_get_params(self._h, _d(out)))
+        return out
+
+    def get_first_controls(self):
+        out = np.zeros((self.batch, self.ocp.nu))
+        _check(self._lib.b200sqp_get_first_controls(self._h, _d(out)))
+        return out
+
+    def step(self, x0, xref=None, cold_start=True, out=None):
+        """One batched MPC step through host buffers: H2D x0 (+xref), [initialise], solve, D2H parameters, chi2, status."""
+        x0 = np.ascontiguousarray(x0, np.float64)
+        xref = None if xref is None else np.ascontiguousarray(xref, np.float64)
+        if out is None:
+            out = (np.zeros((self.batch, self.dims.n_params)), np.zeros(self.batch), np.zeros(self.batch, np.int32))
+        params, chi2, status = out
+        _check(self._lib.b200sqp_step(self._h, C.byref(self._opts), C.c_int32(1 if cold_start else 0), _d(x0), _d(xref), _d(params), _d(chi2),
+                                      _i(status)))
+        return params, chi2, status
+
+    def step_raw(self, x0_ptr, xref_ptr, params_ptr, chi2_ptr, status_ptr, cold_start=True):
+        """b200sqp_step on raw host addresses (e.g. pinned torch tensors' data_ptr())."""
+        _check(self._lib.b200sqp_step(self._h, C.byref(self._opts), C.c_int32(1 if cold_start else 0), C.c_void_p(x0_ptr), C.c_void_p(xref_ptr),
+                                      C.c_void_p(params_ptr), C.c_void_p(chi2_ptr), C.c_void_p(status_ptr)))
+
+    # -- evaluation surface (computeValues + computeCombinedSparseJacobian) ------------------------------------------------------------
+    def evaluate(self, weights=(2.0, 2.0, 2.0), jacobian=True):
+        """-> values [B, m], J values [B, nnzJ] in the CSC order of jacobian_pattern(ocp).  Perturbs the parameters like the reference."""
+        m, nnz = self.dims.m, self.dims.nnz_jacobian
+        values = np.zeros((self.batch, m))
+        jac = np.zeros((self.batch, nnz)) if jacobian else None
+        _check(self._lib.b200sqp_evaluate(self._h, C.c_double(weights[0]), C.c_double(weights[1]), C.c_double(weights[2]), _d(values), _d(jac)))
+        return values, jac
+
+    # -- bookkeeping ----------------------------------------------------------------------------------------------------------
+    def synchronize(self):
+        _check(self._lib.b200sqp_synchronize(self._h))
+
+    def statistics(self):
+        B = self.batch
+        f, r, l = np.zeros(B, np.int32), np.zeros(B, np.int32), np.zeros(B, np.int32)
+        mu, rho = np.zeros(B), np.zeros(B)
+        _check(self._lib.b200sqp_get_statistics(self._h, _i(f), _i(r), _i(l), _d(mu), _d(rho)))
+        return dict(inner_passes=f, rejects=r, relinearizations=l, mu=mu, rho=rho)
+
+    def chi2_trace(self):
+        it = self._opts.iterations
+        out = np.zeros((self.batch, it + 1))
+        _check(self._lib.b200sqp_get_chi2_trace(self._h, _d(out), C.c_int32(it)))
+        return out
+
+    def last_solve_ms(self):
+        ms = C.c_float(0)
+        _check(self._lib.b200sqp_last_solve_ms(self._h, C.byref(ms)))
+        return ms.value
+
+    def launch_count(self):
+        n = C.c_int64(0)
+        _check(self._lib.b200sqp_launch_count(self._h, C.byref(n)))
+        return n.value
+
+    def device_pointers(self):
+        chi2, status, x0 = C.c_void_p(), C.c_void_p(), C.c_void_p()
+        _check(self._lib.b200sqp_device_pointers(self._h, C.byref(chi2), C.byref(status), C.byref(x0)))
+        return dict(chi2=chi2.value, status=status.value, x0=x0.value)
+
+    def set_stream(self, cuda_stream):
+        _check(self._lib.b200sqp_set_stream(self._h, C.c_void_p(cuda_stream)))
+
+    @property
+    def options(self):
+        return self._opts

@@ -131,6 +131,7 @@ int b200sqp_device_available(void);
 /* ---- structure / indexing (bit-exact with the reference) --------------------------------------------------------------- */
 /* Host-only, needs no GPU: usable on a handle-less descriptor. */
 int b200sqp_dims_of(const b200sqp_ocp* ocp, b200sqp_dims* out);
+int b200sqp_get_dims(b200sqp_handle h, b200sqp_dims* out);
 /* VertexSetInterface::computeVertexIndices (vertex_set.cpp:405-418) over FullDiscretizationGridBase::computeActiveVertices
  * (full_discretization_grid_base.cpp:514-527): for every grid point k, the parameter index of x_k[0] / u_k[0] / dt_k, or -1 if fixed. */
 int b200sqp_vertex_indices(const b200sqp_ocp* ocp, int32_t* x_idx /*[N]*/, int32_t* u_idx /*[N-1]*/, int32_t* dt_idx /*[N-1]*/);
