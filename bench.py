@@ -1,0 +1,310 @@
+#!/usr/bin/env python
+"""bench.py -- SQP(LM) iterations per second on a batched OCP, on N B200s of one node, next to the reference's CPU path.
+
+    python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path
+    python bench.py --impl reference --gpus N --steps K ...  # the reference's own CPU solver on the host cores
+
+One "step" = one cold batched solve of the workload: trajectory initialisation + `iterations` Levenberg-Marquardt outer
+iterations for every instance (LevenbergMarquardtSparse always runs all of them).  metric = instances x iterations / time.
+  value      device-resident: x0 already in HBM, nothing crosses PCIe inside the timed region (CUDA events, max over ranks)
+  e2e        the same through b200sqp_step with pinned HOST buffers: H2D of x0/xref, solve, D2H of trajectories+chi2+status
+  roofline   the LM kernel alone against the measured HBM copy bandwidth with SURVEY.md section 8d's algorithmic bytes
+  cpu_baseline  the reference (oracle/_ref, kind "reference") or the oracle port timed on this box's host cores (rank 0, N=1)
+Instances shard over ranks with no data-path collective; one all-gather of the per-instance chi2 per step is the stop-test
+exchange.
+"""
+import argparse
+import ctypes
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+
+from control_box_rst_b200 import _abi as abi  # noqa: E402
+from control_box_rst_b200 import problems  # noqa: E402
+
+METRIC = "sqp_lm_iterations_per_second"
+UNIT = "iters/s"
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--config", type=int, default=1, help="BASELINE.json configs[] index of the OCP (1 = Van der Pol N=50)")
+    ap.add_argument("--batch", type=int, default=4096, help="instances per GPU (north_star target batch; weak scaling)")
+    ap.add_argument("--cpu-sample", type=int, default=4096, help="instances of the same workload timed on the host cores")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    return ap.parse_args()
+
+
+def workload_name(cfg, ocp, batch, iterations):
+    names = {0: "van_der_pol_fd_n20", 1: "van_der_pol_fd_n50", 2: "unicycle_time_optimal_n50", 3: "cart_pole_shooting_n100", 4: "quadrotor_fd_n60"}
+    return f"{names[cfg]}_batch{batch}_per_gpu_fp64_{iterations}_lm_iterations_cold_start"
+
+
+# ---------------------------------------------------------------------------------------------------------------------------
+# clocks during the timed region (B200_PROFILING.md)
+# ---------------------------------------------------------------------------------------------------------------------------
+class ClockSampler:
+    QUERY = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.gpu_index = gpu_index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.QUERY}", "--format=csv,noheader,nounits", "-lms", "100",
+                                          "-i", str(self.gpu_index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, smax, reasons = [], None, set()
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1]))
+                smax = float(f[2])
+            except ValueError:
+                continue
+            for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": smax, "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ---------------------------------------------------------------------------------------------------------------------------
+# the reference's own CPU implementation of the path, all host threads (oracle/_ref when it exists, else the oracle port)
+# ---------------------------------------------------------------------------------------------------------------------------
+def cpu_checker():
+    from oracle import bindings
+
+    if bindings.Reference.available():
+        return bindings.Reference(), "reference"
+    if not bindings.Oracle.available():
+        bindings.build_oracle()
+    return bindings.Oracle(), "port"
+
+
+def run_cpu(ocp, opts, sample, seed):
+    checker, kind = cpu_checker()
+    cores = os.cpu_count() or 1
+    x0, xref = problems.instance_data(ocp, sample, seed=seed)
+    t0 = time.perf_counter()
+    checker.solve_batch(ocp, opts, x0, xref, threads=cores)
+    dt = time.perf_counter() - t0
+    return sample * opts.iterations / dt, dt, kind, cores
+
+
+def main_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    ocp, kw, _ = problems.config(args.config)
+    opts = abi.LmOptions.defaults(iterations=kw["iterations"], weights=kw["weights"])
+    sample = min(args.cpu_sample, 2048)
+    for _ in range(max(0, min(args.warmup, 1))):
+        run_cpu(ocp, opts, 64, seed=99)
+    times, kind, cores = [], "port", 1
+    for s in range(args.steps):
+        v, dt, kind, cores = run_cpu(ocp, opts, sample, seed=1234 + args.config)
+        times.append(dt)
+    total = sum(times)
+    value = sample * opts.iterations * args.steps / total
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": 1e3 * total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+        "data": "synthetic",
+        "config": {"workload": workload_name(args.config, ocp, args.batch, opts.iterations),
+                   "note": "reference CPU path (LevenbergMarquardtSparse through its hypergraph problem), fresh solver objects per instance"},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": kind,
+                         "sample": f"{sample} instances of the workload per step, {args.steps} steps, std::thread static partition"},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+    return 0
+
+
+class _CudaArray:
+    """Zero-copy view of a raw device pointer for torch.as_tensor (CUDA array interface v2)."""
+
+    def __init__(self, ptr, shape, typestr):
+        self.__cuda_array_interface__ = {"shape": shape, "typestr": typestr, "data": (int(ptr), False), "version": 2}
+
+
+def main_b200(args):
+    import torch
+    import torch.distributed as dist
+
+    from control_box_rst_b200 import solver
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device -- the hot path only exists as sm_100a kernels (no CPU fallback)")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    n_gpus = world
+
+    ocp, kw, _ = problems.config(args.config)
+    B = args.batch
+    lm = solver.BatchedLevenbergMarquardt(ocp, B, device=local_rank)
+    lm.setIterations(kw["iterations"])
+    lm.setPenaltyWeights(*kw["weights"])
+    iterations = kw["iterations"]
+    # a dedicated (non-default) torch stream: the library launches on it, torch's events, the L2 flush and NCCL are ordered on it
+    stream = torch.cuda.Stream(device=local_rank)
+    torch.cuda.set_stream(stream)
+    lm.set_stream(stream.cuda_stream)
+
+    # every rank solves its own contiguous shard of the global instance list
+    x0, xref = problems.instance_data(ocp, B, seed=1234 + args.config, offset=rank * B)
+    lm.set_problem_data(x0, xref)
+    ptrs = lm.device_pointers()
+    chi2_local = torch.as_tensor(_CudaArray(ptrs["chi2"], (B,), "<f8"), device=f"cuda:{local_rank}")
+    chi2_all = torch.empty(B * world, dtype=torch.float64, device=f"cuda:{local_rank}") if world > 1 else None
+    flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=f"cuda:{local_rank}")  # > 126 MB L2
+
+    def device_step():
+        lm.initialize_trajectories()
+        lm.solve(new_run=True, fetch=False)
+        if world > 1:  # the single stop-test exchange: all-gather of the per-instance chi2
+            dist.all_gather_into_tensor(chi2_all, chi2_local)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps):
+        total_ms, kernel_ms = 0.0, 0.0
+        for _ in range(steps):
+            flush.zero_()  # evict L2 between timed iterations (outside the timed region)
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(stream)
+            fn()
+            e1.record(stream)
+            e1.synchronize()
+            total_ms += e0.elapsed_time(e1)
+            kernel_ms += lm.last_solve_ms()
+        return total_ms, kernel_ms
+
+    # ---- device-resident value ---------------------------------------------------------------------------------------------
+    for _ in range(max(args.warmup, 3)):
+        device_step()
+    barrier()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    launches0 = lm.launch_count()
+    wall0 = time.perf_counter()
+    total_ms, kernel_ms = timed(device_step, args.steps)
+    barrier()
+    wall = time.perf_counter() - wall0
+    launches = lm.launch_count() - launches0
+    clocks = sampler.stop() if rank == 0 else None
+    t = torch.tensor([total_ms, kernel_ms], dtype=torch.float64, device=f"cuda:{local_rank}")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    total_ms, kernel_ms = float(t[0]), float(t[1])
+    value = B * world * iterations * args.steps / (total_ms * 1e-3)
+
+    # ---- end to end through the C ABI with host buffers -----------------------------------------------------------------------
+    n = lm.dims.n_params
+    h_x0 = torch.from_numpy(x0).pin_memory()
+    h_xref = torch.from_numpy(xref).pin_memory()
+    h_params = torch.empty((B, n), dtype=torch.float64).pin_memory()
+    h_chi2 = torch.empty(B, dtype=torch.float64).pin_memory()
+    h_status = torch.empty(B, dtype=torch.int32).pin_memory()
+
+    def e2e_step():
+        lm.step_raw(h_x0.data_ptr(), h_xref.data_ptr(), h_params.data_ptr(), h_chi2.data_ptr(), h_status.data_ptr(), cold_start=True)
+        if world > 1:
+            dist.all_gather_into_tensor(chi2_all, chi2_local)
+
+    for _ in range(2):
+        e2e_step()
+    barrier()
+    e2e_ms, _ = timed(e2e_step, args.steps)
+    barrier()
+    t = torch.tensor([e2e_ms], dtype=torch.float64, device=f"cuda:{local_rank}")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_ms = float(t[0])
+    e2e_value = B * world * iterations * args.steps / (e2e_ms * 1e-3)
+    h2d = 2 * B * ocp.nx * 8
+    d2h = B * n * 8 + B * 8 + B * 4
+    stats = lm.statistics()
+
+    if rank == 0:
+        peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+        if os.path.exists(peaks_path):
+            peak, peak_src = float(json.load(open(peaks_path))["hbm_gbs"]), "MEASURED_PEAKS.json hbm_gbs (measured)"
+        else:
+            peak, peak_src = 6650.0, "B200_PROFILING.md fallback"
+        alg_bytes = lm.dims.algorithmic_bytes_per_iteration * B * iterations  # per launch of the LM kernel
+        achieved = alg_bytes / (kernel_ms / args.steps * 1e-3) / 1e9
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": n_gpus, "steps": args.steps, "warmup": max(args.warmup, 3),
+            "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+            "data": "synthetic",
+            "config": {"workload": workload_name(args.config, ocp, B, iterations), "instances_total": B * world, "n_grid": ocp.n_grid,
+                       "n_params": n, "parallelism": f"instance-sharded x{world}, one chi2 all-gather per step" if world > 1 else "single GPU",
+                       "timing": "CUDA events per step on the launch stream, L2 flushed (256 MiB memset) between steps, max over ranks",
+                       "wall_s_timed_region_incl_flush": wall},
+            "clocks": clocks,
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "ms_per_step": e2e_ms / args.steps},
+            "gpu_launches": int(launches),
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+                         "kernel": "lmSolve", "kernel_ms": kernel_ms / args.steps, "algorithmic_bytes_per_launch": alg_bytes,
+                         "peak_source": peak_src},
+            "lm": {"inner_passes_per_instance": float(stats["inner_passes"].mean()), "rejects_per_instance": float(stats["rejects"].mean()),
+                   "relinearizations_per_instance": float(stats["relinearizations"].mean())},
+        }
+        if n_gpus == 1 and not args.no_cpu_baseline:
+            opts = abi.LmOptions.defaults(iterations=iterations, weights=kw["weights"])
+            v, dt, kind, cores = run_cpu(ocp, opts, args.cpu_sample, seed=1234 + args.config)
+            line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": cores, "kind": kind,
+                                    "sample": f"{args.cpu_sample} instances of the same workload, {dt:.2f} s wall on {cores} threads"}
+        print(json.dumps(line))
+    lm.clear()
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    a = parse_args()
+    sys.exit(main_reference(a) if a.impl == "reference" else main_b200(a))

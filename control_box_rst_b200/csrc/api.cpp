@@ -39,7 +39,8 @@ namespace b200sqp {
 
 const KernelSet* findKernels(int dynamics, int defect, int vt)
 {
-    const KernelSet* (*tables[])(int*) = {kernelTableOscillators, kernelTableCartPole, kernelTableUnicycle, kernelTableQuadrotor};
+    const KernelSet* (*tables[])(int*) = {kernelTableVdpCn,       kernelTableVdpFd,    kernelTableVdpMs,   kernelTableOscillators,
+                                          kernelTableCartPole,    kernelTableUnicycle, kernelTableQuadrotor};
     for (auto t : tables)
     {
         int count            = 0;
@@ -65,6 +66,7 @@ struct b200sqp_solver
     bool timed = false;
     int64_t launches = 0;
     bool weights_initialised = false;
+    int threads_per_instance = 0;  // 0 = heuristic (launchSolve)
     // staging
     double* d_params = nullptr;   // [B][n]
     double* d_x0_host_order = nullptr, *d_xref_host_order = nullptr;  // [B][nx]
@@ -426,7 +428,7 @@ int b200sqp_solve_async(b200sqp_handle h, const b200sqp_lm_options* opts, int32_
     if (rc) return rc;
     updateWeights(h, *opts, new_run != 0);
     CUDA_TRY(cudaEventRecord(h->ev_begin, h->stream));
-    h->kernels->solve(h->P, h->st, opts->iterations, h->stream);
+    h->kernels->solve(h->P, h->st, opts->iterations, h->threads_per_instance, h->stream);
     h->launches += 1;
     CUDA_TRY(cudaGetLastError());
     CUDA_TRY(cudaEventRecord(h->ev_end, h->stream));
@@ -568,6 +570,13 @@ int b200sqp_device_pointers(b200sqp_handle h, void** chi2, void** status, void**
     if (chi2) *chi2 = h->st.chi2;
     if (status) *status = h->st.status;
     if (x0) *x0 = h->d_x0_host_order;
+    return B200SQP_OK;
+}
+
+int b200sqp_set_threads_per_instance(b200sqp_handle h, int32_t threads)
+{
+    if (!h || threads < 0 || threads > 8) return fail(B200SQP_ERR_INVALID, "threads per instance must be 0 (auto), 1, 2, 4 or 8");
+    h->threads_per_instance = threads;
     return B200SQP_OK;
 }
 

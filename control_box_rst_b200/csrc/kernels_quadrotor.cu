@@ -6,7 +6,7 @@ namespace b200sqp {
 const KernelSet* kernelTableQuadrotor(int* count)
 {
     static const KernelSet table[] = {
-        B200SQP_KERNEL_ENTRY(Quadrotor, DEFECT_CRANK_NICOLSON, 0),
+        B200SQP_KERNEL_ENTRY(Quadrotor, DEFECT_CRANK_NICOLSON, 0, 1),
     };
     *count = (int)(sizeof(table) / sizeof(table[0]));
     return table;

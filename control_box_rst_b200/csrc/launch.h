@@ -11,7 +11,7 @@ struct DeviceState;
 struct KernelSet
 {
     int dynamics, defect, vt, nx, nu;
-    void (*solve)(const DeviceOcp&, const DeviceState&, int iterations, cudaStream_t);
+    void (*solve)(const DeviceOcp&, const DeviceState&, int iterations, int threads_per_instance /*0 = auto*/, cudaStream_t);
     void (*evaluate)(const DeviceOcp&, const DeviceState&, double* values, double* jac, const int* value_rows, const int* jac_pos, int v_count,
                      int j_count, cudaStream_t);
 };
@@ -20,6 +20,9 @@ struct KernelSet
 const KernelSet* findKernels(int dynamics, int defect, int vt);
 
 // one table per translation unit so that the heavy templates compile in parallel
+const KernelSet* kernelTableVdpCn(int* count);
+const KernelSet* kernelTableVdpFd(int* count);
+const KernelSet* kernelTableVdpMs(int* count);
 const KernelSet* kernelTableOscillators(int* count);
 const KernelSet* kernelTableCartPole(int* count);
 const KernelSet* kernelTableUnicycle(int* count);

@@ -10,106 +10,215 @@
 
 namespace b200sqp {
 
-// LevenbergMarquardtSparse::solve (optimization/src/solver/levenberg_marquardt_sparse.cpp:44-220) for one instance.
-// Mirrored quirks: damping accumulates on the Hessian diagonal across inner passes and is never removed (:135-138,:208) ->
-// mu_acc; all `iterations` outer passes run (:129); `stop` is overwritten by ||values|| <= eps3 where `values` is whatever
-// computeValues produced last, i.e. possibly a rejected trial point (:216); the last outer pass never re-linearises (:178);
-// `v` is an unsigned int (:108).
-template <class M, int DEFECT, int VT>
-__global__ void __launch_bounds__(32) lmSolveKernel(const __grid_constant__ DeviceOcp P, const __grid_constant__ DeviceState st, int iterations)
+// LevenbergMarquardtSparse::solve (optimization/src/solver/levenberg_marquardt_sparse.cpp:44-220) for 32 instances per thread block.
+//
+// Thread layout: blockDim = 32*T; thread (g = tid & 31, p = tid >> 5) is cooperating thread p of the block's instance g, i.e. warp p
+// holds "lane p" of all 32 instances, so every global access of a warp is 32 consecutive doubles.  The T threads of an instance
+// split the horizon into T contiguous chunks for the two embarrassingly parallel phases (linearisation with the FD Jacobians,
+// trial-point evaluation); the block-tridiagonal factorisation is a sequential recursion and runs on thread p = 0 (warp 0) while
+// the other warps wait at the barrier without consuming issue slots.  Phases are separated by block barriers; the per-instance LM
+// state machine lives in the registers of thread p = 0 and is broadcast through shared memory.
+//
+// Mirrored quirks of the reference loop: damping accumulates on the Hessian diagonal across inner passes and is never removed
+// (:135-138,:208) -> mu_acc; all `iterations` outer passes run (:129); `stop` is overwritten by ||values|| <= eps3 where `values`
+// is whatever computeValues produced last, i.e. possibly a rejected trial point (:216); the last outer pass never re-linearises
+// (:178); `v` is an unsigned int (:108); the `stop || ||g||inf <= eps1` update after a re-linearisation (:193) is dead code
+// because rho > 0 leaves the inner loop and :216 overwrites `stop`, so ||g||inf is only evaluated for the initial test (:115).
+template <class M, int DEFECT, int VT, int T>
+__global__ void __launch_bounds__(32 * T) lmSolveKernel(const __grid_constant__ DeviceOcp P, const __grid_constant__ DeviceState st, int iterations)
 {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= P.B) return;
+    using Dm = Dim<M, VT>;
+    constexpr int NX = Dm::NX, XO = Dm::XO, NB = Dm::NB;
+    const int g      = threadIdx.x & 31;
+    const int p      = threadIdx.x >> 5;
+    const int i      = blockIdx.x * 32 + g;
+    const bool valid = i < P.B;
+    const int K      = P.K;
+    const int ka     = (int)((long long)p * K / T);
+    const int kb     = (int)((long long)(p + 1) * K / T);
+    const int S      = P.S;
+
+    __shared__ double s_red[3][T][32];
+    __shared__ double s_muacc[32], s_mu[32];
+    __shared__ int s_cur[32], s_flags[32];
+    enum { F_ACTIVE = 1, F_LIN = 2, F_SMALL = 4 };
+
     const Weights w{st.w_eq, st.w_ineq, st.w_b};
-    const double* x0p   = st.x0 + i;
-    const double* xrefp = st.xref + i;
-    double* D  = st.D + i;
-    double* E  = st.E + i;
-    double* g  = st.g + i;
-    double* dl = st.dl + i;
-    double* L  = st.L + i;
-    double* W  = st.W + i;
-    int cur    = st.cur[i];
+    const int ii        = valid ? i : 0;
+    const double* x0p   = st.x0 + ii;
+    const double* xrefp = st.xref + ii;
+    double* D  = st.D + ii;
+    double* E  = st.E + ii;
+    double* gg = st.g + ii;
+    double* dl = st.dl + ii;
+    double* L  = st.L + ii;
+    double* W  = st.W + ii;
 
     constexpr double eps1 = 1e-5, eps2 = 1e-5, eps3 = 1e-5, eps4 = 0;
     constexpr double tau                = 1e-5;
     constexpr double goodStepUpperScale = 2. / 3., goodStepLowerScale = 1. / 3.;
 
-    int n_factor = 0, n_reject = 0, n_lin = 0;
-
-    double chi2_old, ginf, maxdiag;
-    {
-        NormalEquationSink<M, VT> sink(P, D, E, g);
-        linearizeSweep<M, DEFECT, VT>(P, w, st.z[cur] + i, x0p, xrefp, sink);
-        chi2_old = sink.chi2;
-        ginf     = sink.ginf;
-        maxdiag  = sink.maxdiag;
-        ++n_lin;
-    }
+    // LM state of instance g (meaningful in thread p == 0 only)
+    int cur = 0, k_outer = 0, n_factor = 0, n_reject = 0, n_lin = 0;
     unsigned int v = 2;
-    bool stop      = ginf <= eps1;
-    double mu      = tau * maxdiag;
-    if (mu < 0) mu = 0;
-    double mu_acc      = 0.0;  // what has been added to the Hessian diagonal since the last re-linearisation
-    double rho         = 0;
-    double last_values = chi2_old;  // squaredNorm of the reference's `_values` member
-    if (st.trace) st.trace[i] = chi2_old;
+    bool stop = false, active = false;
+    double mu = 0, mu_acc = 0, rho = 0, chi2_old = 0, last_values = 0, dn2 = 0, dq = 0;
 
-    for (int k = 0; k < iterations; ++k)
+    if (p == 0)
     {
-        do
+        cur        = valid ? st.cur[i] : 0;
+        s_cur[g]   = cur;
+        s_flags[g] = valid ? (F_ACTIVE | F_LIN) : 0;
+    }
+    __syncthreads();
+
+    // One linearisation phase for the instances flagged F_LIN; executed by the whole block because it contains barriers.
+    auto linearizePhase = [&](bool first) {
+        const bool do_lin = valid && (s_flags[g] & F_LIN);
+        double* z         = st.z[s_cur[g]] + ii;
+        double xn_last[NX];
+        if (do_lin && kb < K)
         {
-            mu_acc += mu;
-            double dn2, dq;
-            factorSolve<M, VT>(P, D, E, g, L, W, dl, mu_acc, mu, dn2, dq);
-            ++n_factor;
-            if (sqrt(dn2) <= eps2)
+            const double* zp = z + (size_t)(kb - 1) * NB * S;
+#pragma unroll
+            for (int j = 0; j < NX; ++j) xn_last[j] = zp[(size_t)(XO + j) * S];
+        }
+        if (T > 1) __syncthreads();  // boundary states are read before any neighbour writes its perturbed copy back
+        NormalEquationSink<M, VT> sink(P, D, E, gg, ka, kb);
+        if (do_lin) linearizeSweep<M, DEFECT, VT>(P, w, z, x0p, xrefp, ka, kb, xn_last, sink);
+        if (T > 1)
+        {
+            __syncthreads();  // all blocks stored; now the chunk-start contributions can be added to the neighbour's last block
+            if (do_lin) sink.addBoundary();
+        }
+        if (first)
+        {
+            s_red[0][p][g] = sink.chi2;
+            s_red[1][p][g] = sink.ginf;
+            s_red[2][p][g] = sink.maxdiag;
+        }
+        __syncthreads();
+    };
+
+    linearizePhase(true);
+    if (p == 0 && valid)
+    {
+        double ginf = 0.0, maxdiag = -CUDART_INF;
+        chi2_old = 0.0;
+#pragma unroll
+        for (int q = 0; q < T; ++q)
+        {
+            chi2_old += s_red[0][q][g];
+            ginf    = fmax(ginf, s_red[1][q][g]);
+            maxdiag = fmax(maxdiag, s_red[2][q][g]);
+        }
+        ++n_lin;
+        stop = ginf <= eps1;
+        mu   = tau * maxdiag;
+        if (mu < 0) mu = 0;
+        last_values = chi2_old;
+        active      = iterations > 0;
+        if (st.trace) st.trace[i] = chi2_old;
+    }
+
+    while (true)
+    {
+        // ---- F: (H + sum(mu) I) delta = g on thread p == 0 of every instance still iterating
+        if (p == 0)
+        {
+            int flags = 0;
+            if (active)
             {
-                stop = true;
+                mu_acc += mu;
+                factorSolve<M, VT>(P, D, E, gg, L, W, dl, mu_acc, mu, dn2, dq);
+                ++n_factor;
+                flags = F_ACTIVE | ((sqrt(dn2) <= eps2) ? F_SMALL : 0);
             }
-            else
+            s_flags[g] = flags;
+        }
+        __syncthreads();
+        // ---- T: trial point and its chi2, all T threads
+        {
+            const int flags     = s_flags[g];
+            const bool do_trial = valid && (flags & F_ACTIVE) && !(flags & F_SMALL);
+            double part         = 0.0;
+            if (do_trial) part = trialChi2<M, DEFECT, VT>(P, w, st.z[s_cur[g]] + ii, dl, st.z[s_cur[g] ^ 1] + ii, x0p, xrefp, ka, kb);
+            s_red[0][p][g] = part;
+        }
+        __syncthreads();
+        // ---- C: gain ratio, accept / reject, damping update (thread p == 0)
+        bool any_lin = false;
+        if (p == 0)
+        {
+            int flags = 0;
+            if (active)
             {
-                const double chi2_new = trialChi2<M, DEFECT, VT>(P, w, st.z[cur] + i, dl, st.z[cur ^ 1] + i, x0p, xrefp);
-                last_values           = chi2_new;
-                rho                   = (chi2_old - chi2_new) / dq;
-                if (rho > 0 && !isnan(chi2_new) && !isinf(chi2_new))
+                if (s_flags[g] & F_SMALL)
                 {
-                    stop = (sqrt(chi2_old) - sqrt(chi2_new) < eps4 * sqrt(chi2_old));
-                    cur ^= 1;  // accept: the trial buffer becomes the current one (discardBackupParameters)
-                    if (!stop && k < iterations - 1)
-                    {
-                        NormalEquationSink<M, VT> sink(P, D, E, g);
-                        linearizeSweep<M, DEFECT, VT>(P, w, st.z[cur] + i, x0p, xrefp, sink);
-                        ++n_lin;
-                        mu_acc             = 0.0;
-                        stop               = stop || (sink.ginf <= eps1);
-                        const double c     = 2 * rho - 1;
-                        double alpha       = fmin(goodStepUpperScale, 1 - c * c * c);
-                        double scaleFactor = fmax(goodStepLowerScale, alpha);
-                        mu *= scaleFactor;
-                        v = 2;
-                    }
-                    chi2_old = chi2_new;
+                    stop = true;
                 }
                 else
                 {
-                    ++n_reject;  // restoreBackupParameters: the current buffer was never touched
-                    mu = mu * v;
-                    v  = 2 * v;
+                    double chi2_new = 0.0;
+#pragma unroll
+                    for (int q = 0; q < T; ++q) chi2_new += s_red[0][q][g];
+                    last_values = chi2_new;
+                    rho         = (chi2_old - chi2_new) / dq;
+                    if (rho > 0 && !isnan(chi2_new) && !isinf(chi2_new))
+                    {
+                        stop = (sqrt(chi2_old) - sqrt(chi2_new) < eps4 * sqrt(chi2_old));
+                        cur ^= 1;  // accept: the trial buffer becomes the current one (discardBackupParameters)
+                        if (!stop && k_outer < iterations - 1)
+                        {
+                            flags |= F_LIN;
+                            ++n_lin;
+                            mu_acc             = 0.0;
+                            const double c     = 2 * rho - 1;
+                            double alpha       = fmin(goodStepUpperScale, 1 - c * c * c);
+                            double scaleFactor = fmax(goodStepLowerScale, alpha);
+                            mu *= scaleFactor;
+                            v = 2;
+                        }
+                        chi2_old = chi2_new;
+                    }
+                    else
+                    {
+                        ++n_reject;  // restoreBackupParameters: the current buffer was never touched
+                        mu = mu * v;
+                        v  = 2 * v;
+                    }
                 }
+                if (!(rho <= 0 && !stop))
+                {
+                    // end of outer iteration k_outer (:216)
+                    stop = (sqrt(last_values) <= eps3);
+                    ++k_outer;
+                    if (st.trace) st.trace[(size_t)k_outer * S + i] = chi2_old;
+                    active = k_outer < iterations;
+                }
+                if (active) flags |= F_ACTIVE;
             }
-        } while (rho <= 0 && !stop);
-        stop = (sqrt(last_values) <= eps3);
-        if (st.trace) st.trace[(size_t)(k + 1) * P.S + i] = chi2_old;
+            s_cur[g]   = cur;
+            s_flags[g] = flags;
+            any_lin    = (flags & F_LIN) != 0;
+        }
+        const int any_active = __syncthreads_or(p == 0 && active);
+        if (!any_active) break;
+        // ---- L: re-linearise the accepted points
+        if (__syncthreads_or(any_lin)) linearizePhase(false);
     }
-    st.cur[i]         = cur;
-    st.chi2[i]        = chi2_old;
-    st.mu[i]          = mu;
-    st.rho[i]         = rho;
-    st.status[i]      = (stop || rho <= 0) ? B200SQP_STATUS_CONVERGED : B200SQP_STATUS_EARLY_TERMINATED;
-    st.n_factor[i]    = n_factor;
-    st.n_reject[i]    = n_reject;
-    st.n_linearize[i] = n_lin;
+
+    if (p == 0 && valid)
+    {
+        st.cur[i]         = cur;
+        st.chi2[i]        = chi2_old;
+        st.mu[i]          = mu;
+        st.rho[i]         = rho;
+        st.status[i]      = (stop || rho <= 0) ? B200SQP_STATUS_CONVERGED : B200SQP_STATUS_EARLY_TERMINATED;
+        st.n_factor[i]    = n_factor;
+        st.n_reject[i]    = n_reject;
+        st.n_linearize[i] = n_lin;
+    }
 }
 
 // LevenbergMarquardtSparse::computeValues + computeCombinedSparseJacobian, materialised (b200sqp_evaluate)
@@ -121,14 +230,31 @@ __global__ void __launch_bounds__(32) evaluateKernel(const __grid_constant__ Dev
     if (i >= P.B) return;
     const Weights w{st.w_eq, st.w_ineq, st.w_b};
     MaterializeSink<M, VT> sink{P, values ? values + i : nullptr, jac ? jac + i : nullptr, value_rows, jac_pos, v_count, j_count};
-    linearizeSweep<M, DEFECT, VT>(P, w, st.z[st.cur[i]] + i, st.x0 + i, st.xref + i, sink);
+    linearizeSweep<M, DEFECT, VT>(P, w, st.z[st.cur[i]] + i, st.x0 + i, st.xref + i, 0, P.K, nullptr, sink);
 }
 
-template <class M, int DEFECT, int VT>
-void launchSolve(const DeviceOcp& P, const DeviceState& st, int iterations, cudaStream_t stream)
+// Cooperating threads per instance: small batches are latency bound (one warp per SM would leave the machine idle), so the
+// horizon is split T ways; once a batch alone fills the SMs with warps T = 1 is the most work-efficient mapping.
+// MAXT bounds the variants that get compiled for a (model, defect, grid) combination.
+template <class M, int DEFECT, int VT, int MAXT>
+void launchSolve(const DeviceOcp& P, const DeviceState& st, int iterations, int threads_per_instance, cudaStream_t stream)
 {
     const int blocks = (P.B + 31) / 32;
-    lmSolveKernel<M, DEFECT, VT><<<blocks, 32, 0, stream>>>(P, st, iterations);
+    int T            = threads_per_instance;
+    if (T <= 0)
+    {
+        // heuristic: aim for >= 8 warps per SM across 148 SMs, keep >= 3 intervals per thread
+        T = 1;
+        while (T < 8 && blocks * T < 148 * 8 && P.K / (2 * T) >= 3) T *= 2;
+    }
+    if (T > MAXT) T = MAXT;
+    if constexpr (MAXT >= 8)
+        if (T >= 8) return (void)lmSolveKernel<M, DEFECT, VT, 8><<<blocks, 256, 0, stream>>>(P, st, iterations);
+    if constexpr (MAXT >= 4)
+        if (T >= 4) return (void)lmSolveKernel<M, DEFECT, VT, 4><<<blocks, 128, 0, stream>>>(P, st, iterations);
+    if constexpr (MAXT >= 2)
+        if (T >= 2) return (void)lmSolveKernel<M, DEFECT, VT, 2><<<blocks, 64, 0, stream>>>(P, st, iterations);
+    lmSolveKernel<M, DEFECT, VT, 1><<<blocks, 32, 0, stream>>>(P, st, iterations);
 }
 
 template <class M, int DEFECT, int VT>
@@ -139,7 +265,7 @@ void launchEvaluate(const DeviceOcp& P, const DeviceState& st, double* values, d
     evaluateKernel<M, DEFECT, VT><<<blocks, 32, 0, stream>>>(P, st, values, jac, value_rows, jac_pos, v_count, j_count);
 }
 
-#define B200SQP_KERNEL_ENTRY(MODEL, DEFECT, VT) \
-    KernelSet { MODEL::ID, DEFECT, VT, MODEL::NX, MODEL::NU, &launchSolve<MODEL, DEFECT, VT>, &launchEvaluate<MODEL, DEFECT, VT> }
+#define B200SQP_KERNEL_ENTRY(MODEL, DEFECT, VT, MAXT) \
+    KernelSet { MODEL::ID, DEFECT, VT, MODEL::NX, MODEL::NU, &launchSolve<MODEL, DEFECT, VT, MAXT>, &launchEvaluate<MODEL, DEFECT, VT> }
 
 }  // namespace b200sqp

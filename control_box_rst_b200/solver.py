@@ -25,7 +25,7 @@ ABI_SYMBOLS = [
     "b200sqp_vertex_indices", "b200sqp_edge_indices", "b200sqp_jacobian_pattern", "b200sqp_set_problem_data",
     "b200sqp_initialize_trajectories", "b200sqp_set_params", "b200sqp_get_params", "b200sqp_get_first_controls", "b200sqp_solve",
     "b200sqp_solve_async", "b200sqp_synchronize", "b200sqp_step", "b200sqp_evaluate", "b200sqp_get_statistics", "b200sqp_get_chi2_trace",
-    "b200sqp_last_solve_ms", "b200sqp_launch_count", "b200sqp_device_pointers", "b200sqp_set_stream",
+    "b200sqp_last_solve_ms", "b200sqp_launch_count", "b200sqp_device_pointers", "b200sqp_set_stream", "b200sqp_set_threads_per_instance",
 ]
 
 
@@ -240,6 +240,10 @@ class BatchedLevenbergMarquardt:
         chi2, status, x0 = C.c_void_p(), C.c_void_p(), C.c_void_p()
         _check(self._lib.b200sqp_device_pointers(self._h, C.byref(chi2), C.byref(status), C.byref(x0)))
         return dict(chi2=chi2.value, status=status.value, x0=x0.value)
+
+    def set_threads_per_instance(self, threads):
+        """cooperating threads per instance (1, 2, 4, 8; 0 = pick from the batch size)"""
+        _check(self._lib.b200sqp_set_threads_per_instance(self._h, C.c_int32(threads)))
 
     def set_stream(self, cuda_stream):
         _check(self._lib.b200sqp_set_stream(self._h, C.c_void_p(cuda_stream)))

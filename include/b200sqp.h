@@ -187,6 +187,8 @@ int b200sqp_launch_count(b200sqp_handle h, int64_t* launches);
 /* raw device pointers for zero-copy interop (torch / NCCL all-gather of the stop-test residuals): chi2 [batch] doubles,
  * status [batch] int32, x0 [batch*nx] doubles.  Valid until destroy. */
 int b200sqp_device_pointers(b200sqp_handle h, void** chi2, void** status, void** x0);
+/* tuning knob: cooperating threads per instance in the LM kernel (1, 2, 4, 8; 0 = choose from the batch size) */
+int b200sqp_set_threads_per_instance(b200sqp_handle h, int32_t threads);
 /* make the handle launch on an external stream (e.g. torch's current stream); pass NULL to restore its own */
 int b200sqp_set_stream(b200sqp_handle h, void* cuda_stream);
 
