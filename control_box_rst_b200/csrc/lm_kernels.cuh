@@ -38,10 +38,16 @@ __global__ void __launch_bounds__(32 * T) lmSolveKernel(const __grid_constant__ 
     const int kb     = (int)((long long)(p + 1) * K / T);
     const int S      = P.S;
 
+    using BS = BlockSolver<M, VT>;
+    constexpr int NXX = Dm::NXX, ND = Dm::ND;
+    constexpr bool TWISTED = T >= 2;  // two threads of an instance eliminate from both ends of the horizon
     __shared__ double s_red[3][T][32];
     __shared__ double s_muacc[32], s_mu[32];
+    __shared__ double s_xc[TWISTED ? NXX + 2 * NX : 1][32];  // chain B -> A: Schur contribution; chain A -> B: x-part of delta_m
+    __shared__ double s_dn[2][2][32];                        // partial ||delta||^2 and delta^T(mu delta + g) of the two chains
     __shared__ int s_cur[32], s_flags[32];
-    enum { F_ACTIVE = 1, F_LIN = 2, F_SMALL = 4 };
+    enum { F_ACTIVE = 1, F_LIN = 2 };
+    const int m_mid = TWISTED ? K / 2 : K - 1;  // middle block of the twisted elimination
 
     const Weights w{st.w_eq, st.w_ineq, st.w_b};
     const int ii        = valid ? i : 0;
@@ -62,7 +68,7 @@ __global__ void __launch_bounds__(32 * T) lmSolveKernel(const __grid_constant__ 
     int cur = 0, k_outer = 0, n_factor = 0, n_reject = 0, n_lin = 0;
     unsigned int v = 2;
     bool stop = false, active = false;
-    double mu = 0, mu_acc = 0, rho = 0, chi2_old = 0, last_values = 0, dn2 = 0, dq = 0;
+    double mu = 0, mu_acc = 0, rho = 0, chi2_old = 0, last_values = 0, dq = 0;
 
     if (p == 0)
     {
@@ -119,28 +125,81 @@ __global__ void __launch_bounds__(32 * T) lmSolveKernel(const __grid_constant__ 
         last_values = chi2_old;
         active      = iterations > 0;
         if (st.trace) st.trace[i] = chi2_old;
+        mu_acc      = mu;
+        s_muacc[g]  = mu_acc;
+        s_mu[g]     = mu;
+        s_flags[g]  = active ? F_ACTIVE : 0;
     }
+    else if (p == 0)
+        s_flags[g] = 0;
+    __syncthreads();
 
     while (true)
     {
-        // ---- F: (H + sum(mu) I) delta = g on thread p == 0 of every instance still iterating
-        if (p == 0)
+        // ---- F: (H + sum(mu) I) delta = g.  Chain A = thread p == 0, chain B = thread p == 1 (twisted elimination).
         {
-            int flags = 0;
-            if (active)
+            const bool inst_active = valid && (s_flags[g] & F_ACTIVE);
+            const double mua = s_muacc[g], mucur = s_mu[g];
+            double Lp[ND], yp[NX], carry[NX], dx[NX];
+            double pdn2 = 0.0, pdq = 0.0;
+            if (p == 0 && inst_active)
             {
-                mu_acc += mu;
-                factorSolve<M, VT>(P, D, E, gg, L, W, dl, mu_acc, mu, dn2, dq);
+                BS::chainAEliminate(P, D, E, gg, L, W, dl, mua, 0, TWISTED ? m_mid : K, Lp, yp, nullptr, nullptr);
                 ++n_factor;
-                flags = F_ACTIVE | ((sqrt(dn2) <= eps2) ? F_SMALL : 0);
             }
-            s_flags[g] = flags;
+            if (TWISTED)
+            {
+                if (p == 1 && inst_active)
+                {
+                    double cxx[NXX], cgx[NX];
+                    BS::chainBEliminate(P, D, E, gg, L, W, dl, mua, m_mid + 1, cxx, cgx);
+#pragma unroll
+                    for (int q = 0; q < NXX; ++q) s_xc[q][g] = cxx[q];
+#pragma unroll
+                    for (int q = 0; q < NX; ++q) s_xc[NXX + q][g] = cgx[q];
+                }
+                __syncthreads();
+                if (p == 0 && inst_active)
+                {
+                    double cxx[NXX], cgx[NX];
+#pragma unroll
+                    for (int q = 0; q < NXX; ++q) cxx[q] = s_xc[q][g];
+#pragma unroll
+                    for (int q = 0; q < NX; ++q) cgx[q] = s_xc[NXX + q][g];
+                    BS::chainAEliminate(P, D, E, gg, L, W, dl, mua, m_mid, m_mid + 1, Lp, yp, cxx, cgx);
+#pragma unroll
+                    for (int q = 0; q < NX; ++q) carry[q] = 0.0;
+                    BS::chainABacksub(P, gg, L, W, dl, mucur, m_mid, m_mid, carry, dx, pdn2, pdq);
+#pragma unroll
+                    for (int q = 0; q < NX; ++q) s_xc[NXX + NX + q][g] = dx[q];
+                }
+                __syncthreads();
+                if (p == 0 && inst_active) BS::chainABacksub(P, gg, L, W, dl, mucur, m_mid - 1, 0, carry, nullptr, pdn2, pdq);
+                if (p == 1 && inst_active)
+                {
+#pragma unroll
+                    for (int q = 0; q < NX; ++q) dx[q] = s_xc[NXX + NX + q][g];
+                    BS::chainBSubst(P, gg, L, W, dl, mucur, m_mid + 1, dx, pdn2, pdq);
+                }
+            }
+            else if (p == 0 && inst_active)
+            {
+#pragma unroll
+                for (int q = 0; q < NX; ++q) carry[q] = 0.0;
+                BS::chainABacksub(P, gg, L, W, dl, mucur, K - 1, 0, carry, nullptr, pdn2, pdq);
+            }
+            if (p < 2)
+            {
+                s_dn[0][p][g] = pdn2;
+                s_dn[1][p][g] = pdq;
+            }
         }
         __syncthreads();
         // ---- T: trial point and its chi2, all T threads
+        const double dn2_tot = s_dn[0][0][g] + (TWISTED ? s_dn[0][1][g] : 0.0);
+        const bool step_small = sqrt(dn2_tot) <= eps2;
         {
-            const int flags     = s_flags[g];
-            const bool do_trial = valid && (flags & F_ACTIVE) && !(flags & F_SMALL);
+            const bool do_trial = valid && (s_flags[g] & F_ACTIVE) && !step_small;
             double part         = 0.0;
             if (do_trial) part = trialChi2<M, DEFECT, VT>(P, w, st.z[s_cur[g]] + ii, dl, st.z[s_cur[g] ^ 1] + ii, x0p, xrefp, ka, kb);
             s_red[0][p][g] = part;
@@ -153,7 +212,8 @@ __global__ void __launch_bounds__(32 * T) lmSolveKernel(const __grid_constant__ 
             int flags = 0;
             if (active)
             {
-                if (s_flags[g] & F_SMALL)
+                dq = s_dn[1][0][g] + (TWISTED ? s_dn[1][1][g] : 0.0);
+                if (step_small)
                 {
                     stop = true;
                 }
@@ -196,7 +256,13 @@ __global__ void __launch_bounds__(32 * T) lmSolveKernel(const __grid_constant__ 
                     if (st.trace) st.trace[(size_t)k_outer * S + i] = chi2_old;
                     active = k_outer < iterations;
                 }
-                if (active) flags |= F_ACTIVE;
+                if (active)
+                {
+                    flags |= F_ACTIVE;
+                    mu_acc += mu;  // what the next factorisation adds to the diagonal (:135-138)
+                    s_muacc[g] = mu_acc;
+                    s_mu[g]    = mu;
+                }
             }
             s_cur[g]   = cur;
             s_flags[g] = flags;
@@ -243,9 +309,10 @@ void launchSolve(const DeviceOcp& P, const DeviceState& st, int iterations, int 
     int T            = threads_per_instance;
     if (T <= 0)
     {
-        // heuristic: aim for >= 8 warps per SM across 148 SMs, keep >= 3 intervals per thread
+        // measured on B200 (profiles/): the widest split wins at every batch size from 1k to 64k instances as long as every
+        // thread keeps >= 3 intervals; the two-sided elimination alone is worth T = 2
         T = 1;
-        while (T < 8 && blocks * T < 148 * 8 && P.K / (2 * T) >= 3) T *= 2;
+        while (T < 8 && P.K / (2 * T) >= 3) T *= 2;
     }
     if (T > MAXT) T = MAXT;
     if constexpr (MAXT >= 8)
