@@ -159,9 +159,40 @@ class _Checker:
         return out, chi2, status, secs
 
 
+def _known_answer(lib, fn_name, case_id, stage=0):
+    f = getattr(lib, fn_name)
+    f.restype = C.c_int
+    x, exp = np.zeros(3), np.zeros(3)
+    tol, n = C.c_double(0), C.c_int32(0)
+    rc = f(C.c_int(case_id), C.c_int(stage), _d(x), _d(exp), C.byref(tol), C.byref(n))
+    if rc != 0:
+        raise RuntimeError(f"{fn_name}({case_id}) failed: {rc}")
+    return x[:n.value], exp[:n.value], tol.value
+
+
+KNOWN_ANSWER_CASES = [(0, 0), (1, 0), (2, 0), (3, 0), (4, 0), (5, 0), (6, 0), (7, 0), (7, 1)]
+
+
 class Oracle(_Checker):
     prefix = "sqp_oracle_"
     path = ORACLE_SO
+
+    def solve_sequence(self, ocp, opts, x0, xref=None, n_solves=2):
+        """warm-started solves of one instance, new_run only on the first -> (params [n], chi2 [n_solves])"""
+        n = self.dims(ocp).n_params
+        x0 = np.ascontiguousarray(x0, np.float64)
+        xref = None if xref is None else np.ascontiguousarray(xref, np.float64)
+        p, chi2 = np.zeros(n), np.zeros(n_solves)
+        f = self.lib.sqp_oracle_solve_sequence
+        f.restype = C.c_int
+        rc = f(C.byref(ocp), C.byref(opts), _d(x0), _d(xref), C.c_int(n_solves), _d(p), _d(chi2))
+        if rc != 0:
+            raise RuntimeError(f"sqp_oracle_solve_sequence failed: {rc}")
+        return p, chi2
+
+    def known_answer(self, case_id, stage=0):
+        """reference's own LM known-answer tests restated: -> (x, expected, tol)"""
+        return _known_answer(self.lib, "sqp_oracle_known_answer", case_id, stage)
 
 
 class Reference(_Checker):
@@ -178,6 +209,9 @@ class Reference(_Checker):
         if rc != 0:
             raise RuntimeError(f"corbo_ref_closed_loop failed: {rc}")
         return u, x
+
+    def known_answer(self, case_id, stage=0):
+        return _known_answer(self.lib, "corbo_ref_known_answer", case_id, stage)
 
     def hardware_threads(self):
         return int(self.lib.corbo_ref_hardware_threads())

@@ -22,6 +22,7 @@
 #include <corbo-optimal-control/structured_ocp/discretization_grids/non_uniform_finite_differences_variable_grid.h>
 #include <corbo-optimal-control/structured_ocp/structured_optimal_control_problem.h>
 #include <corbo-optimization/hyper_graph/hyper_graph_optimization_problem_edge_based.h>
+#include <corbo-optimization/simple_optimization_problem.h>
 #include <corbo-optimization/solver/levenberg_marquardt_sparse.h>
 #include <corbo-systems/benchmark/linear_benchmark_systems.h>
 #include <corbo-systems/benchmark/nonlinear_benchmark_systems.h>
@@ -604,6 +605,119 @@ int corbo_ref_closed_loop(const b200sqp_ocp* d, const b200sqp_lm_options* o, con
         x = xn;
         std::memcpy(x_closed + (size_t)(s + 1) * d->nx, x.data(), sizeof(double) * d->nx);
     }
+    return 0;
+}
+
+// The reference's known-answer solver tests (optimization/test/test_levenberg_marquardt_sparse.cpp:72-296, excluded from its build)
+// run against the compiled reference: SimpleOptimizationProblemWithCallbacks + LevenbergMarquardtSparse, 100 iterations.
+int corbo_ref_known_answer(int case_id, int stage, double* x_out, double* expected, double* tol, int32_t* n_out)
+{
+    SimpleOptimizationProblemWithCallbacks optim;
+    LevenbergMarquardtSparse solver;
+    solver.setIterations(100);
+    auto shifted = [](const Eigen::VectorXd& x, Eigen::Ref<Eigen::VectorXd> values) { values[0] = x[0] - 2; };
+    int n        = 1;
+    double exp3[3] = {0, 0, 0};
+    switch (case_id)
+    {
+        case 0:
+            optim.resizeParameterVector(1);
+            optim.setX(Eigen::VectorXd::Ones(1));
+            optim.setObjectiveFunction(shifted, 1, true);
+            exp3[0] = 2, *tol = 1e-6;
+            break;
+        case 1:
+            n = 3;
+            optim.resizeParameterVector(3);
+            optim.setX(Eigen::VectorXd::Ones(3));
+            optim.setObjectiveFunction(
+                [](const Eigen::VectorXd& x, Eigen::Ref<Eigen::VectorXd> values) {
+                    values[0] = x[0] - 5;
+                    values[1] = x[1] + 3;
+                    values[2] = x[2];
+                },
+                3, true);
+            exp3[0] = 5, exp3[1] = -3, exp3[2] = 0, *tol = 1e-6;
+            break;
+        case 2:
+            n = 2;
+            optim.resizeParameterVector(2);
+            optim.setX(Eigen::VectorXd::Ones(2));
+            optim.setObjectiveFunction(
+                [](const Eigen::VectorXd& x, Eigen::Ref<Eigen::VectorXd> values) {
+                    values[0] = std::sqrt(100) * (x[1] - x[0] * x[0]);
+                    values[1] = 1 - x[0];
+                },
+                2, true);
+            exp3[0] = 1, exp3[1] = 1, *tol = 1e-3;
+            break;
+        case 3:
+            optim.resizeParameterVector(1);
+            optim.setX(Eigen::VectorXd::Ones(1));
+            optim.setObjectiveFunction(shifted, 1, true);
+            optim.setEqualityConstraint([](const Eigen::VectorXd& x, Eigen::Ref<Eigen::VectorXd> values) { values[0] = x[0] - 3; }, 1);
+            solver.setPenaltyWeights(100, 100, 100);
+            exp3[0] = 3, *tol = 1e-4;
+            break;
+        case 4:
+            optim.resizeParameterVector(1);
+            optim.setX(Eigen::VectorXd::Ones(1));
+            optim.setObjectiveFunction(shifted, 1, true);
+            optim.setInequalityConstraint([](const Eigen::VectorXd& x, Eigen::Ref<Eigen::VectorXd> values) { values[0] = -x[0] + 3; }, 1);
+            solver.setPenaltyWeights(100, 100, 100);
+            exp3[0] = 3, *tol = 1e-4;
+            break;
+        case 5:
+        case 6:
+        {
+            optim.resizeParameterVector(1);
+            optim.setX(Eigen::VectorXd::Ones(1));
+            Eigen::VectorXd b(1);
+            b[0] = case_id == 5 ? 5 : -1;
+            if (case_id == 5)
+                optim.setLowerBounds(b);
+            else
+                optim.setUpperBounds(b);
+            optim.setObjectiveFunction(shifted, 1, true);
+            solver.setPenaltyWeights(100, 100, 100);
+            exp3[0] = b[0], *tol = 1e-3;
+            break;
+        }
+        case 7:
+            n = 2;
+            optim.resizeParameterVector(2);
+            optim.setLowerBound(0, 2);
+            optim.setUpperBound(0, 50);
+            optim.setLowerBound(1, -50);
+            optim.setUpperBound(1, 50);
+            optim.setObjectiveFunction(
+                [](const Eigen::VectorXd& x, Eigen::Ref<Eigen::VectorXd> values) {
+                    values[0] = std::sqrt(0.01) * x[0];
+                    values[1] = x[1];
+                },
+                2, true);
+            optim.setInequalityConstraint(
+                [](const Eigen::VectorXd& x, Eigen::Ref<Eigen::VectorXd> values) { values[0] = x[1] - 10.0 * x[0] + 10.0; }, 1);
+            optim.setParameterValue(0, stage == 0 ? -5 : -1);
+            optim.setParameterValue(1, 0);
+            if (stage == 1)
+            {
+                solver.setPenaltyWeights(1, 10, 10);
+                solver.setIterations(5000);
+            }
+            exp3[0] = 2, exp3[1] = 0, *tol = 1e-2;
+            break;
+        default:
+            return -1;
+    }
+    if (!solver.initialize(&optim)) return -2;
+    solver.solve(optim, true, true, nullptr);
+    for (int i = 0; i < n; ++i)
+    {
+        x_out[i]    = optim.getX()[i];
+        expected[i] = exp3[i];
+    }
+    *n_out = n;
     return 0;
 }
 

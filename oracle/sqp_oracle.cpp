@@ -902,6 +902,91 @@ void fillDims(Graph& g, b200sqp_dims* out)
         s * (2 * ((int64_t)out->nnz_jacobian + 2 * (int64_t)nnz + 2 * (int64_t)m + 2 * (int64_t)g.n) + 4 * (int64_t)g.n);
 }
 
+
+// ---------------------------------------------------------------------------------------------------------------------------
+// The reference's own known-answer tests for the solver (optimization/test/test_levenberg_marquardt_sparse.cpp:72-371; the
+// file is excluded from the reference's build, optimization/CMakeLists.txt:99-101, but is the only place that pins optima of
+// LevenbergMarquardtSparse): restated on a one-vertex hypergraph.  case ids follow the order of the TEST_F blocks.
+// Returns the optimised parameters; `expected`/`tol` are the EXPECT_NEAR targets of the reference test.
+// ---------------------------------------------------------------------------------------------------------------------------
+struct KnownAnswer
+{
+    int n;
+    double x0[3], lb[3], ub[3];
+    std::function<void(const double*, double*)> obj, eq, ineq;
+    int obj_dim, eq_dim, ineq_dim;
+    double w[3];
+    int iterations;
+    double expected[3], tol;
+};
+
+bool knownAnswerCase(int id, int stage, KnownAnswer& c)
+{
+    c = KnownAnswer();
+    for (int i = 0; i < 3; ++i)
+    {
+        c.lb[i] = -CORBO_INF;
+        c.ub[i] = CORBO_INF;
+        c.x0[i] = 1.0;
+        c.w[i]  = 2.0;
+    }
+    c.iterations = 100;  // fixture SetUp (:60)
+    auto shifted = [](const double* x, double* v) { v[0] = x[0] - 2; };
+    switch (id)
+    {
+        case 0:  // solve_unconstr_1 (:72-88)
+            c.n = 1, c.obj = shifted, c.obj_dim = 1, c.expected[0] = 2.0, c.tol = 1e-6;
+            return true;
+        case 1:  // solve_unconstr_2 (:90-113)
+            c.n   = 3;
+            c.obj = [](const double* x, double* v) {
+                v[0] = x[0] - 5;
+                v[1] = x[1] + 3;
+                v[2] = x[2];
+            };
+            c.obj_dim = 3, c.expected[0] = 5, c.expected[1] = -3, c.expected[2] = 0, c.tol = 1e-6;
+            return true;
+        case 2:  // solve_rosenbrock_unconstr (:115-137)
+            c.n   = 2;
+            c.obj = [](const double* x, double* v) {
+                v[0] = std::sqrt(100) * (x[1] - x[0] * x[0]);
+                v[1] = 1 - x[0];
+            };
+            c.obj_dim = 2, c.expected[0] = 1, c.expected[1] = 1, c.tol = 1e-3;
+            return true;
+        case 3:  // solve_eqconstr_1 (:139-163)
+            c.n = 1, c.obj = shifted, c.obj_dim = 1;
+            c.eq     = [](const double* x, double* v) { v[0] = x[0] - 3; };
+            c.eq_dim = 1, c.w[0] = c.w[1] = c.w[2] = 100, c.expected[0] = 3.0, c.tol = 1e-4;
+            return true;
+        case 4:  // solve_ineqconstr_1 (:165-189)
+            c.n = 1, c.obj = shifted, c.obj_dim = 1;
+            c.ineq     = [](const double* x, double* v) { v[0] = -x[0] + 3; };
+            c.ineq_dim = 1, c.w[0] = c.w[1] = c.w[2] = 100, c.expected[0] = 3.0, c.tol = 1e-4;
+            return true;
+        case 5:  // solve_lower_bounds (:191-215)
+            c.n = 1, c.obj = shifted, c.obj_dim = 1, c.lb[0] = 5, c.w[0] = c.w[1] = c.w[2] = 100, c.expected[0] = 5.0, c.tol = 1e-3;
+            return true;
+        case 6:  // solve_upper_bounds (:217-241)
+            c.n = 1, c.obj = shifted, c.obj_dim = 1, c.ub[0] = -1, c.w[0] = c.w[1] = c.w[2] = 100, c.expected[0] = -1.0, c.tol = 1e-3;
+            return true;
+        case 7:  // solve_betts_fun_constr (:243-296); stage 0: x = (-5, 0), default weights; stage 1: x = (-1, 0), weights 1/10/10, 5000 its
+            c.n = 2, c.lb[0] = 2, c.ub[0] = 50, c.lb[1] = -50, c.ub[1] = 50;
+            c.obj = [](const double* x, double* v) {
+                v[0] = std::sqrt(0.01) * x[0];
+                v[1] = x[1];
+            };
+            c.obj_dim  = 2;
+            c.ineq     = [](const double* x, double* v) { v[0] = x[1] - 10.0 * x[0] + 10.0; };
+            c.ineq_dim = 1;
+            c.x0[0] = stage == 0 ? -5 : -1, c.x0[1] = 0;  // the test calls setParameterValue(0, .) twice: x[1] keeps its initial 0
+            if (stage == 1) c.w[0] = 1, c.w[1] = 10, c.w[2] = 10, c.iterations = 5000;
+            c.expected[0] = 2, c.expected[1] = 0, c.tol = 1e-2;
+            return true;
+    }
+    return false;
+}
+
 }  // namespace
 
 extern "C" {
@@ -1068,6 +1153,63 @@ int sqp_oracle_solve_batch(const b200sqp_ocp* d, const b200sqp_lm_options* o, in
         }
     }
     return failures.load() == 0 ? 0 : -1;
+}
+
+int sqp_oracle_known_answer(int case_id, int stage, double* x_out, double* expected, double* tol, int32_t* n_out)
+{
+    KnownAnswer c;
+    if (!knownAnswerCase(case_id, stage, c)) return -1;
+    Graph g;
+    Vertex* v = g.add(c.n);
+    for (int i = 0; i < c.n; ++i)
+    {
+        v->val[i] = c.x0[i];
+        v->lb[i]  = c.lb[i];
+        v->ub[i]  = c.ub[i];
+    }
+    g.active.push_back(v);
+    computeVertexIndices(g);
+    auto mk = [&](std::function<void(const double*, double*)> f, int dim) {
+        Edge e;
+        e.dim    = dim;
+        e.v      = {v};
+        e.values = [v, f](double* out) { f(v->val.data(), out); };
+        return e;
+    };
+    if (c.obj_dim) g.lsq.push_back(mk(c.obj, c.obj_dim));
+    if (c.eq_dim) g.eq.push_back(mk(c.eq, c.eq_dim));
+    if (c.ineq_dim) g.ineq.push_back(mk(c.ineq, c.ineq_dim));
+    computeEdgeIndices(g);
+    b200sqp_lm_options o = {c.iterations, c.w[0], c.w[1], c.w[2], 1, 1, 1, 500, 500, 500};
+    Weights w{0, 0, 0};
+    lmSolve(g, o, true, w, nullptr, nullptr);
+    for (int i = 0; i < c.n; ++i)
+    {
+        x_out[i]    = v->val[i];
+        expected[i] = c.expected[i];
+    }
+    *tol   = c.tol;
+    *n_out = c.n;
+    return 0;
+}
+
+// A warm-started sequence of solves on one instance, as PredictiveController::step drives it (controllers/src/
+// predictive_controller.cpp:60-68: `_ocp->compute(..., new_run = (i == 0))` for i < num_ocp_iterations): the first solve resets
+// the penalty weights, the following ones adapt them (levenberg_marquardt_sparse.cpp:83-86).
+int sqp_oracle_solve_sequence(const b200sqp_ocp* d, const b200sqp_lm_options* o, const double* x0, const double* xref, int n_solves,
+                              double* params_out, double* chi2_out)
+{
+    auto g = buildGraph({d, x0, xref});
+    if (!g) return -1;
+    Weights w{0, 0, 0};
+    for (int s = 0; s < n_solves; ++s)
+    {
+        double obj = -1;
+        lmSolve(*g, *o, s == 0, w, &obj, nullptr);
+        if (chi2_out) chi2_out[s] = obj;
+    }
+    if (params_out) getParams(*g, params_out);
+    return 0;
 }
 
 }  // extern "C"

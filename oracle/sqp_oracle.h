@@ -20,6 +20,10 @@ int sqp_oracle_trace(const b200sqp_ocp* d, const b200sqp_lm_options* o, const do
 int sqp_oracle_solve_batch(const b200sqp_ocp* d, const b200sqp_lm_options* o, int batch, const double* x0, const double* xref,
                            const double* params_in, double* params_out, double* chi2, int32_t* status, int threads, double* seconds);
 
+int sqp_oracle_solve_sequence(const b200sqp_ocp* d, const b200sqp_lm_options* o, const double* x0, const double* xref, int n_solves,
+                              double* params_out, double* chi2_out);
+int sqp_oracle_known_answer(int case_id, int stage, double* x_out, double* expected, double* tol, int32_t* n_out);
+
 #ifdef __cplusplus
 }
 #endif

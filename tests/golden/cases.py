@@ -1,0 +1,36 @@
+"""Shared case table for the golden fixtures (tests/golden/*.npz) -- used by make_golden.py (generation from the compiled
+reference) and by the tests that replay them."""
+import numpy as np
+
+from control_box_rst_b200 import _abi as abi
+from control_box_rst_b200 import problems
+
+# name -> (ocp builder, LM weights, instances in the fixture)
+CASES = {
+    "vdp20_cn": (lambda: problems.van_der_pol(20), (2.0, 2.0, 2.0), 8),
+    "vdp50_cn": (lambda: problems.van_der_pol(50), (2.0, 2.0, 2.0), 16),
+    "vdp50_cn_nofinal": (lambda: problems.van_der_pol(50, final_cost=False), (2.0, 2.0, 2.0), 4),
+    "vdp30_forward": (lambda: problems.van_der_pol(30, collocation=abi.COLL_FORWARD), (2.0, 2.0, 2.0), 4),
+    "vdp30_backward": (lambda: problems.van_der_pol(30, collocation=abi.COLL_BACKWARD), (2.0, 2.0, 2.0), 4),
+    "vdp30_midpoint": (lambda: problems.van_der_pol(30, collocation=abi.COLL_MIDPOINT), (2.0, 2.0, 2.0), 4),
+    "vdp2_minimal": (lambda: problems.van_der_pol(2), (2.0, 2.0, 2.0), 4),  # smallest legal grid: one interval
+    "unicycle30_timeopt": (lambda: problems.unicycle_time_optimal(30), (2.0, 2.0, 2.0), 4),
+    "cartpole40_rk4": (lambda: problems.cart_pole_shooting(40), (10.0, 10.0, 10.0), 4),
+    "quadrotor12_cn": (lambda: problems.quadrotor(12), (2.0, 2.0, 2.0), 2),
+}
+
+EVAL_WEIGHTS = (2.0, 3.0, 5.0)
+
+
+def perturbed_params(ocp, p_init, seed=3):
+    """Initial guess pushed off the linear interpolation so that bounds are violated and every Jacobian block is exercised."""
+    rng = np.random.default_rng(seed)
+    p = p_init + rng.uniform(-0.3, 0.3, p_init.shape)
+    return p
+
+
+def dense_to_csc_values(J, col_ptr, row_idx):
+    out = np.zeros(len(row_idx))
+    for c in range(len(col_ptr) - 1):
+        out[col_ptr[c]:col_ptr[c + 1]] = J[row_idx[col_ptr[c]:col_ptr[c + 1]], c]
+    return out

@@ -1,0 +1,73 @@
+"""Generates tests/golden/*.npz from the UNMODIFIED reference compiled out of /root/reference (oracle/_ref/libcorbo_ref.so).
+
+Run where /root/reference exists:   python tests/golden/make_golden.py
+Every array in the fixtures is an output of the reference's own classes (StructuredOptimalControlProblem, the discretization grids,
+HyperGraphOptimizationProblemEdgeBased, LevenbergMarquardtSparse); nothing is computed by this repository's oracle or kernels.
+"""
+import os
+import sys
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, HERE)
+
+from control_box_rst_b200 import _abi as abi  # noqa: E402
+from control_box_rst_b200 import problems  # noqa: E402
+from oracle import bindings  # noqa: E402
+import cases  # noqa: E402
+
+
+def main():
+    bindings.build_reference()
+    ref = bindings.Reference()
+    for name, (make, weights, B) in cases.CASES.items():
+        ocp = make()
+        d = ref.dims(ocp)
+        x_idx, u_idx, dt_idx = ref.vertex_indices(ocp)
+        x0, xref = problems.instance_data(ocp, B, seed=21)
+        p_init = np.stack([ref.initial_params(ocp, x0[i], xref[i]) for i in range(B)])
+        p_eval = cases.perturbed_params(ocp, p_init)
+        if ocp.grid == abi.GRID_FD_NONUNIFORM_VARDT:
+            p_eval[:, dt_idx] = np.abs(p_eval[:, dt_idx]) + 0.05
+        # Jacobian-level fixture for instance 0
+        values, J, pattern, after = ref.evaluate(ocp, x0[0], xref[0], p_eval[0], cases.EVAL_WEIGHTS)
+        rows, cols = np.nonzero(pattern.T)  # column-major order = CSC
+        col_idx, row_idx = rows.astype(np.int32), cols.astype(np.int32)
+        col_ptr = np.zeros(d.n_params + 1, np.int32)
+        np.add.at(col_ptr, col_idx + 1, 1)
+        col_ptr = np.cumsum(col_ptr).astype(np.int32)
+        jac_values = cases.dense_to_csc_values(J, col_ptr, row_idx)
+        # solver-level fixture
+        opts = abi.LmOptions.defaults(iterations=10, weights=weights)
+        p_final, chi2, status, _ = ref.solve_batch(ocp, opts, x0, xref, threads=4)
+        tr = ref.trace(ocp, opts, x0[0], xref[0])
+        np.savez_compressed(
+            os.path.join(HERE, name + ".npz"),
+            dims=np.array([d.n_params, d.m_lsq, d.m_eq, d.m_ineq, d.m_bounds, d.nnz_jacobian, d.nnz_hessian_upper,
+                           d.algorithmic_bytes_per_iteration], np.int64),
+            x_idx=x_idx, u_idx=u_idx, dt_idx=dt_idx,
+            edges_lsq=ref.edge_table(ocp, 0), edges_eq=ref.edge_table(ocp, 1),
+            col_ptr=col_ptr, row_idx=row_idx,
+            x0=x0, xref=xref, p_init=p_init, p_eval=p_eval[0], values=values, jac_values=jac_values, p_after=after,
+            p_final=p_final, chi2=chi2, status=status,
+            trace_types=np.array([e[0] for e in tr["events"]], np.int32),
+            trace_chi2=np.array([e[1] for e in tr["events"]]),
+        )
+        print(f"{name}: n={d.n_params} m={d.m} nnzJ={d.nnz_jacobian} chi2[0]={chi2[0]:.6g} events={tr['n_events']}")
+    ka = []
+    for cid, stage in bindings.KNOWN_ANSWER_CASES:
+        x, exp, tol = ref.known_answer(cid, stage)
+        ka.append(np.concatenate([[cid, stage, len(x), tol], np.pad(x, (0, 3 - len(x))), np.pad(exp, (0, 3 - len(exp)))]))
+    np.savez_compressed(os.path.join(HERE, "lm_known_answers.npz"), table=np.array(ka))
+    # closed-loop plumbing (configs[0]): 15 MPC steps of the reference's own controller loop
+    ocp = problems.van_der_pol(20)
+    u, x = ref.closed_loop(ocp, abi.LmOptions.defaults(), np.array([1.0, 0.5]), 15)
+    np.savez_compressed(os.path.join(HERE, "vdp20_closed_loop.npz"), u=u, x=x)
+    print("closed loop u[:3] =", u[:3, 0])
+
+
+if __name__ == "__main__":
+    main()

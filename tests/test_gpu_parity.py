@@ -111,3 +111,190 @@ def test_solve_matches_oracle(oracle, name, make, weights, B, tol95, tolmax, tol
     np.testing.assert_allclose(chi2, chi2_o, rtol=tolchi2)
     assert (status == status_o).mean() >= 0.95
     lm.clear()
+
+
+# ---------------------------------------------------------------------------------------------------------------------------
+# against the golden vectors generated from the compiled reference itself
+# ---------------------------------------------------------------------------------------------------------------------------
+import os  # noqa: E402
+import sys  # noqa: E402
+
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden"))
+import cases  # noqa: E402
+
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+POLYNOMIAL = {"vdp20_cn", "vdp50_cn", "vdp50_cn_nofinal", "vdp30_forward", "vdp30_backward", "vdp30_midpoint", "vdp2_minimal"}
+GOLD_TOL = {"unicycle30_timeopt": (1e-3, 1e-4), "cartpole40_rk4": (5e-3, 1e-3), "quadrotor12_cn": (1e-3, 1e-4)}  # (trajectory, chi2)
+
+
+@pytest.mark.parametrize("name", list(cases.CASES))
+def test_matches_reference_golden(name):
+    make, weights, B = cases.CASES[name]
+    ocp = make()
+    gold = np.load(os.path.join(GOLDEN, name + ".npz"))
+    x0, xref = gold["x0"], gold["xref"]
+    lm = solver.BatchedLevenbergMarquardt(ocp, B)
+    lm.set_problem_data(x0, xref)
+    lm.initialize_trajectories()
+    np.testing.assert_allclose(lm.get_params(), gold["p_init"], rtol=0, atol=1e-14)
+    p = gold["p_init"].copy()
+    p[0] = gold["p_eval"]
+    lm.set_params(p)
+    values, jac = lm.evaluate(cases.EVAL_WEIGHTS)
+    after = lm.get_params()
+    if name in POLYNOMIAL:
+        assert np.array_equal(values[0], gold["values"])
+        assert np.array_equal(jac[0], gold["jac_values"])
+        assert np.array_equal(after[0], gold["p_after"])
+    else:
+        np.testing.assert_allclose(values[0], gold["values"], rtol=1e-13, atol=1e-13)
+        np.testing.assert_allclose(jac[0], gold["jac_values"], rtol=0, atol=2e-6 * max(1.0, np.abs(gold["jac_values"]).max()))
+    lm.setIterations(10)
+    lm.setPenaltyWeights(*weights)
+    lm.initialize_trajectories()
+    status, chi2 = lm.solve(new_run=True)
+    traj_tol, chi2_tol = GOLD_TOL.get(name, (1e-6, 1e-8))
+    err = _traj_err(lm.get_params(), gold["p_final"])
+    assert err.max() <= traj_tol, err
+    np.testing.assert_allclose(chi2, gold["chi2"], rtol=chi2_tol)
+    assert np.array_equal(status, gold["status"])
+    # per-iteration chi2 of instance 0 against the reference's event trace (values at every Jacobian evaluation)
+    trace = lm.chi2_trace()[0]
+    ref_chi2 = gold["trace_chi2"][gold["trace_types"] == 0]
+    np.testing.assert_allclose(trace[:len(ref_chi2)], ref_chi2, rtol=max(chi2_tol, 1e-7))
+    lm.clear()
+
+
+def test_closed_loop_matches_reference_controller():
+    """configs[0] plumbing: 15 warm-started MPC steps (structure kept, x0 replaced, weights reset each step) against the
+    reference's own StructuredOptimalControlProblem::compute loop; plant = one RK4 step of the same dynamics."""
+    gold = np.load(os.path.join(GOLDEN, "vdp20_closed_loop.npz"))
+    ocp = problems.van_der_pol(20)
+    lm = solver.BatchedLevenbergMarquardt(ocp, 1)
+    lm.setIterations(10)
+
+    def f(x, u):
+        return np.array([x[1], -1.0 * (x[0] * x[0] - 1) * x[1] - x[0] + u[0]])
+
+    x = np.array([1.0, 0.5])
+    dt = ocp.dt_ref
+    for s in range(15):
+        lm.step(x[None, :], None, cold_start=(s == 0))
+        u = lm.get_first_controls()[0]
+        np.testing.assert_allclose(u, gold["u"][s], rtol=0, atol=2e-6)
+        k1 = f(x, u) * dt
+        k2 = f(x + k1 / 2.0, u) * dt
+        k3 = f(x + k2 / 2.0, u) * dt
+        k4 = f(x + k3, u) * dt
+        x = x + (k1 + 2.0 * k2 + 2.0 * k3 + k4) / 6.0
+        np.testing.assert_allclose(x, gold["x"][s + 1], rtol=0, atol=2e-6)
+    lm.clear()
+
+
+def test_partially_fixed_goal_state(oracle):
+    """PartiallyFixedVectorVertex xf (setXfFixed): fixed components are no parameters, take their value from the reference and
+    never move; parameter order and results match the oracle."""
+    ocp = problems.van_der_pol(25)
+    ocp.xf_fixed[1] = 1
+    B = 16
+    x0, _ = problems.instance_data(ocp, B, seed=9)
+    xref = np.tile(np.array([0.3, -0.2]), (B, 1))
+    lm = solver.BatchedLevenbergMarquardt(ocp, B)
+    assert lm.dims.n_params == 24 * 3 - 1
+    lm.setIterations(8)
+    lm.set_problem_data(x0, xref)
+    lm.initialize_trajectories()
+    status, chi2 = lm.solve()
+    p_o, chi2_o, status_o, _ = oracle.solve_batch(ocp, abi.LmOptions.defaults(iterations=8), x0, xref, threads=4)
+    assert _traj_err(lm.get_params(), p_o).max() <= 1e-6
+    np.testing.assert_allclose(chi2, chi2_o, rtol=1e-7)
+    lm.clear()
+
+
+def test_weight_adaptation_over_warm_started_solves(oracle):
+    """new_run = false multiplies the penalty weights by the adaptation factors up to their maxima
+    (levenberg_marquardt_sparse.cpp:83-86, 270-287)."""
+    ocp = problems.van_der_pol(20)
+    B = 4
+    x0, xref = problems.instance_data(ocp, B, seed=13)
+    lm = solver.BatchedLevenbergMarquardt(ocp, B)
+    lm.setIterations(3)
+    lm.setPenaltyWeights(2.0, 2.0, 2.0)
+    lm.setWeightAdapation(2.0, 2.0, 3.0, 10.0, 10.0, 10.0)
+    lm.set_problem_data(x0, xref)
+    lm.initialize_trajectories()
+    opts = abi.LmOptions.defaults(iterations=3, weights=(2.0, 2.0, 2.0), factors=(2.0, 2.0, 3.0), maxima=(10.0, 10.0, 10.0))
+    chi2_seq = []
+    for s in range(4):
+        _, chi2 = lm.solve(new_run=(s == 0))
+        chi2_seq.append(chi2)
+    p = lm.get_params()
+    for i in range(B):
+        p_o, chi2_o = oracle.solve_sequence(ocp, opts, x0[i], xref[i], n_solves=4)
+        np.testing.assert_allclose([c[i] for c in chi2_seq], chi2_o, rtol=1e-7)
+        np.testing.assert_allclose(p[i], p_o, rtol=0, atol=1e-6)
+    lm.clear()
+
+
+def test_full_size_properties():
+    """BASELINE.json configs[1] at the north-star batch (4096 x Van der Pol N=50), size-independent properties:
+    determinism (bit-identical reruns), batch independence (an instance's result does not depend on its neighbours),
+    monotone accepted chi2, first-order optimality of the penalty problem, agreement of the thread mappings within the FD-noise
+    floor."""
+    ocp, kw, _ = problems.config(1)
+    B = 4096
+    x0, xref = problems.instance_data(ocp, B, seed=1235)
+    lm = solver.BatchedLevenbergMarquardt(ocp, B)
+    lm.setIterations(10)
+    lm.set_problem_data(x0, xref)
+
+    def run(T):
+        lm.set_threads_per_instance(T)
+        lm.initialize_trajectories()
+        status, chi2 = lm.solve()
+        return lm.get_params(), chi2, status, lm.chi2_trace()
+
+    p8, c8, s8, tr8 = run(8)
+    p8b, c8b, s8b, _ = run(8)
+    assert np.array_equal(p8, p8b) and np.array_equal(c8, c8b) and np.array_equal(s8, s8b)
+    assert np.all(np.diff(tr8, axis=1) <= 0)  # chi2 only changes on accepted steps, which decrease it
+    assert np.all((s8 == abi.STATUS_CONVERGED) | (s8 == abi.STATUS_EARLY_TERMINATED)) and np.all(np.isfinite(p8))
+    p1, c1, _, _ = run(1)
+    err = _traj_err(p8, p1)
+    assert (err <= 1e-6).mean() >= 0.99 and err.max() <= 1e-4
+    np.testing.assert_allclose(c8, c1, rtol=1e-6)
+    # batch independence: the first 96 instances alone
+    small = solver.BatchedLevenbergMarquardt(ocp, 96)
+    small.setIterations(10)
+    small.set_threads_per_instance(8)
+    small.set_problem_data(x0[:96], xref[:96])
+    small.initialize_trajectories()
+    small.solve()
+    assert np.array_equal(small.get_params(), p8[:96])
+    small.clear()
+    # stationarity of the converged points: the LM gradient J^T r is small (evaluate re-linearises at the solution)
+    lm.set_threads_per_instance(8)
+    values, jac = lm.evaluate((2.0, 2.0, 2.0))
+    col_ptr, row_idx = solver.jacobian_pattern(ocp)
+    grad = np.zeros((B, lm.dims.n_params))
+    for c in range(lm.dims.n_params):
+        sl = slice(col_ptr[c], col_ptr[c + 1])
+        grad[:, c] = np.einsum("bi,bi->b", jac[:, sl], values[:, row_idx[sl]])
+    assert np.percentile(np.abs(grad).max(axis=1), 95) <= 1e-3
+    lm.clear()
+
+
+def test_ragged_batch_sizes(oracle):
+    """batches that do not fill a warp / a block, including a single instance"""
+    ocp = problems.van_der_pol(10)
+    for B in (1, 5, 33):
+        x0, xref = problems.instance_data(ocp, B, seed=B)
+        lm = solver.BatchedLevenbergMarquardt(ocp, B)
+        lm.setIterations(5)
+        lm.set_problem_data(x0, xref)
+        lm.initialize_trajectories()
+        status, chi2 = lm.solve()
+        p_o, chi2_o, _, _ = oracle.solve_batch(ocp, abi.LmOptions.defaults(iterations=5), x0, xref, threads=2)
+        assert _traj_err(lm.get_params(), p_o).max() <= 1e-6
+        np.testing.assert_allclose(chi2, chi2_o, rtol=1e-8)
+        lm.clear()

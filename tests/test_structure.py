@@ -1,0 +1,100 @@
+"""Bit-exact hypergraph indexing: dimensions, vertex indices, edge indices and the CSC pattern of the combined Jacobian from the
+C ABI (host-only part, no GPU) against the golden fixtures generated from the compiled reference, and against the oracle."""
+import os
+import sys
+
+import numpy as np
+import pytest
+
+from control_box_rst_b200 import _abi as abi
+from control_box_rst_b200 import problems, solver
+
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden"))
+import cases  # noqa: E402
+
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+@pytest.mark.parametrize("name", list(cases.CASES))
+def test_dims_and_indices_match_reference_golden(name):
+    ocp = cases.CASES[name][0]()
+    gold = np.load(os.path.join(GOLDEN, name + ".npz"))
+    d = solver.dims_of(ocp)
+    got = np.array([d.n_params, d.m_lsq, d.m_eq, d.m_ineq, d.m_bounds, d.nnz_jacobian, d.nnz_hessian_upper, d.algorithmic_bytes_per_iteration])
+    assert np.array_equal(got, gold["dims"]), (got, gold["dims"])
+    x_idx, u_idx, dt_idx = solver.vertex_indices(ocp)
+    assert np.array_equal(x_idx, gold["x_idx"]) and np.array_equal(u_idx, gold["u_idx"]) and np.array_equal(dt_idx, gold["dt_idx"])
+    col_ptr, row_idx = solver.jacobian_pattern(ocp)
+    assert np.array_equal(col_ptr, gold["col_ptr"]) and np.array_equal(row_idx, gold["row_idx"])
+    assert col_ptr.dtype == np.int32 and x_idx.dtype == np.int32
+
+
+@pytest.mark.parametrize("name", list(cases.CASES))
+def test_edge_indices_match_reference_golden(name):
+    ocp = cases.CASES[name][0]()
+    gold = np.load(os.path.join(GOLDEN, name + ".npz"))
+    e = solver.edge_indices(ocp)
+    # reference edge tables: rows [dim, edge_idx, n_vertices, vertex_idx0..3] in creation order
+    lsq, eq = gold["edges_lsq"], gold["edges_eq"]
+    assert np.array_equal(eq[:, 1], e["dynamics"])
+    assert np.all(eq[:, 0] == ocp.nx)
+    mine = []
+    K = ocp.n_grid - 1
+    for k in range(K):
+        if e["state_cost"][k] >= 0:
+            mine.append(e["state_cost"][k])
+        if e["control_cost"][k] >= 0:
+            mine.append(e["control_cost"][k])
+        for r in range(2):
+            if e["dt_cost"][k, r] >= 0:
+                mine.append(e["dt_cost"][k, r])
+    if e["final_cost"] >= 0:
+        mine.append(e["final_cost"])
+    assert np.array_equal(np.array(mine), lsq[:, 1])
+
+
+def test_structure_matches_oracle_on_sweep(oracle):
+    """every grid kind x a sweep of horizon lengths, fixed-goal masks and bound patterns"""
+    inf = abi.CORBO_INF_DBL
+    variants = []
+    for n in (2, 3, 7, 20):
+        variants.append(problems.van_der_pol(n))
+        o = problems.van_der_pol(n)
+        o.xf_fixed[0] = 1
+        variants.append(o)
+        o = problems.van_der_pol(n)
+        o.xf_fixed[0] = o.xf_fixed[1] = 1
+        variants.append(o)
+        o = problems.van_der_pol(n)
+        o.x_lb[1], o.x_ub[0] = -3.0, 4.0
+        o.u_lb[0], o.u_ub[0] = -inf, inf
+        variants.append(o)
+        variants.append(problems.unicycle_time_optimal(max(n, 3)))
+        variants.append(problems.cart_pole_shooting(max(n, 3)))
+    o = problems.unicycle_time_optimal(9)
+    o.xf_fixed[1] = 0
+    variants.append(o)
+    for ocp in variants:
+        d, od = solver.dims_of(ocp), oracle.dims(ocp)
+        for f in ("n_params", "m_lsq", "m_eq", "m_ineq", "m_bounds", "nnz_jacobian", "nnz_hessian_upper", "algorithmic_bytes_per_iteration"):
+            assert getattr(d, f) == getattr(od, f), f
+        for a, b in zip(solver.vertex_indices(ocp), oracle.vertex_indices(ocp)):
+            assert np.array_equal(a, b)
+        x0 = np.full(ocp.nx, 0.25)
+        _, _, pattern, _ = oracle.evaluate(ocp, x0)
+        col_ptr, row_idx = solver.jacobian_pattern(ocp)
+        mine = np.zeros_like(pattern)
+        for c in range(d.n_params):
+            mine[row_idx[col_ptr[c]:col_ptr[c + 1]], c] = True
+        assert np.array_equal(mine, pattern)
+
+
+def test_survey_numbers():
+    """VdP N=20 -> n=57, eq=38, bounds=19, nnzJ=300; N=50 -> n=147, nnzJ=780, nnzH(upper)=582, 49 984 B."""
+    d20, d50 = solver.dims_of(problems.van_der_pol(20)), solver.dims_of(problems.van_der_pol(50))
+    assert (d20.n_params, d20.m_eq, d20.m_bounds, d20.nnz_jacobian) == (57, 38, 19, 300)
+    assert (d50.n_params, d50.nnz_jacobian, d50.nnz_hessian_upper, d50.algorithmic_bytes_per_iteration) == (147, 780, 582, 49984)
+    dc = solver.dims_of(problems.cart_pole_shooting(100))
+    assert (dc.n_params, dc.m_lsq, dc.m_eq, dc.m_bounds) == (495, 499, 396, 99)
+    du = solver.dims_of(problems.unicycle_time_optimal(30))
+    assert du.m_lsq == 58  # the dt-cost edge is created twice per interval (nlp_functions.cpp:91-107)
