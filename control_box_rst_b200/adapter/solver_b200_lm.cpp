@@ -1,0 +1,431 @@
+// corbo::SolverB200Lm: hypergraph walk -> b200sqp_ocp descriptor -> libb200sqp.so.  See solver_b200_lm.h.
+#include "solver_b200_lm.h"
+
+#include <corbo-core/console.h>
+#include <corbo-numerics/explicit_integrators.h>
+#include <corbo-optimal-control/functions/final_state_cost.h>
+#include <corbo-optimal-control/functions/minimum_time.h>
+#include <corbo-optimal-control/functions/quadratic_cost.h>
+#include <corbo-optimal-control/structured_ocp/edges/finite_differences_collocation_edges.h>
+#include <corbo-optimal-control/structured_ocp/edges/multiple_shooting_edges.h>
+#include <corbo-optimization/hyper_graph/hyper_graph_optimization_problem_base.h>
+#include <corbo-systems/benchmark/linear_benchmark_systems.h>
+#include <corbo-systems/benchmark/nonlinear_benchmark_systems.h>
+
+#include <cmath>
+#include <cstring>
+
+namespace corbo {
+
+SolverB200Lm::SolverB200Lm()
+{
+    // LevenbergMarquardtSparse defaults (levenberg_marquardt_sparse.h:112-124)
+    _opts = {10, 2, 2, 2, 1, 1, 1, 500, 500, 500};
+    std::memset(&_ocp, 0, sizeof(_ocp));
+    std::memset(&_dims, 0, sizeof(_dims));
+}
+
+SolverB200Lm::~SolverB200Lm() { clear(); }
+
+void SolverB200Lm::setPenaltyWeights(double weight_eq, double weight_ineq, double weight_bounds)
+{
+    _opts.weight_eq     = weight_eq;
+    _opts.weight_ineq   = weight_ineq;
+    _opts.weight_bounds = weight_bounds;
+}
+
+void SolverB200Lm::setWeightAdapation(double factor_eq, double factor_ineq, double factor_bounds, double max_eq, double max_ineq, double max_bounds)
+{
+    _opts.adapt_factor_eq     = factor_eq;
+    _opts.adapt_factor_ineq   = factor_ineq;
+    _opts.adapt_factor_bounds = factor_bounds;
+    _opts.adapt_max_eq        = max_eq;
+    _opts.adapt_max_ineq      = max_ineq;
+    _opts.adapt_max_bounds    = max_bounds;
+}
+
+SolverStatus SolverB200Lm::fail(const std::string& msg)
+{
+    _error = msg;
+    PRINT_ERROR("SolverB200Lm: " << msg);
+    return SolverStatus::Error;
+}
+
+bool SolverB200Lm::initialize(OptimizationProblemInterface* problem)
+{
+    // same contract as LevenbergMarquardtSparse::initialize (levenberg_marquardt_sparse.cpp:32-41)
+    if (problem && !problem->isLeastSquaresProblem())
+    {
+        PRINT_ERROR("SolverB200Lm(): cannot handle non-least-squares objectives or LS objectives in non-LS form.");
+        return false;
+    }
+    if (!b200sqp_device_available())
+    {
+        PRINT_ERROR("SolverB200Lm(): no sm_100 class CUDA device visible; this solver has no CPU path.");
+        return false;
+    }
+    return true;
+}
+
+void SolverB200Lm::clear()
+{
+    if (_handle) b200sqp_destroy(_handle);
+    _handle = nullptr;
+    _batch  = 0;
+}
+
+double SolverB200Lm::lastSolveMilliseconds() const
+{
+    float ms = 0;
+    if (_handle && b200sqp_last_solve_ms(_handle, &ms) == 0) return ms;
+    return -1;
+}
+
+// Walk the hypergraph (BaseHyperGraphOptimizationProblem::getGraph, hyper_graph_optimization_problem_base.h:89) and the functor
+// objects into the flat descriptor of include/b200sqp.h.
+bool SolverB200Lm::describe(OptimizationProblemInterface& problem, b200sqp_ocp& d, std::vector<double>& x0, std::vector<double>& xref)
+{
+    auto* hg = dynamic_cast<BaseHyperGraphOptimizationProblem*>(&problem);
+    if (!hg || !hg->getGraph().hasEdgeSet())
+    {
+        _error = "problem is not a hypergraph optimization problem";
+        return false;
+    }
+    OptimizationEdgeSet* edges = hg->getGraph().getEdgeSetRaw();
+    if (!edges->getInequalityEdgesRef().empty() || !edges->getMixedEdgesRef().empty() || !edges->getObjectiveEdgesRef().empty())
+    {
+        _error = "inequality / mixed / non-lsq objective edges are outside the device registry";
+        return false;
+    }
+    std::vector<BaseEdge::Ptr>& eq = edges->getEqualityEdgesRef();
+    if (eq.empty() || !_dynamics)
+    {
+        _error = "no dynamics edges, or setSystemDynamics() was not called";
+        return false;
+    }
+    std::memset(&d, 0, sizeof(d));
+    const int K = (int)eq.size();
+    d.n_grid    = K + 1;
+    d.nx        = _dynamics->getStateDimension();
+    d.nu        = _dynamics->getInputDimension();
+    if (d.nx > B200SQP_MAX_NX || d.nu > B200SQP_MAX_NU)
+    {
+        _error = "state/input dimension exceeds the device limits";
+        return false;
+    }
+
+    // ---- dynamics registry
+    if (auto* s = dynamic_cast<VanDerPolOscillator*>(_dynamics.get()))
+    {
+        d.dynamics      = B200SQP_DYN_VAN_DER_POL;
+        d.dyn_params[0] = s->getDampingCoefficient();
+    }
+    else if (dynamic_cast<CartPole*>(_dynamics.get()))
+        d.dynamics = B200SQP_DYN_CART_POLE;  // parameters are private constants in the reference
+    else if (auto* s = dynamic_cast<SerialIntegratorSystem*>(_dynamics.get()))
+    {
+        if (s->getDimension() != 2)
+        {
+            _error = "SerialIntegratorSystem: only dimension 2 is in the device registry";
+            return false;
+        }
+        d.dynamics      = B200SQP_DYN_DOUBLE_INTEGRATOR;
+        d.dyn_params[0] = s->getTimeConstant();
+    }
+    else
+    {
+        _error = "system dynamics type is not in the device registry (Duffing/SimplePendulum expose no parameter getters)";
+        return false;
+    }
+
+    // ---- grid kind from the equality edges: every edge must be a dynamics edge over (x_k, u_k, x_{k+1}, dt_k)
+    bool fd = true, ms = true;
+    for (BaseEdge::Ptr& e : eq)
+    {
+        fd = fd && dynamic_cast<FDCollocationEdge*>(e.get()) != nullptr;
+        ms = ms && dynamic_cast<MSVariableDynamicsOnlyEdge*>(e.get()) != nullptr;
+        if (e->getNumVertices() != 4 || e->getDimension() != d.nx)
+        {
+            _error = "unexpected equality edge shape";
+            return false;
+        }
+    }
+    if (!fd && !ms)
+    {
+        _error = "equality edges are neither FDCollocationEdge nor MSVariableDynamicsOnlyEdge";
+        return false;
+    }
+    const VertexInterface* dt0 = eq.front()->getVertexRaw(3);
+    bool single_dt             = true;
+    for (BaseEdge::Ptr& e : eq) single_dt = single_dt && e->getVertexRaw(3) == dt0;
+    if (single_dt && !dt0->isFixed())
+    {
+        _error = "a single free dt (arrow-structured Hessian) is not supported yet";
+        return false;
+    }
+    if (ms)
+        d.grid = B200SQP_GRID_MULTIPLE_SHOOTING;
+    else
+        d.grid = single_dt ? B200SQP_GRID_FD_UNIFORM : B200SQP_GRID_FD_NONUNIFORM_VARDT;
+    d.dt_ref = dt0->getData()[0];
+    d.dt_lb  = dt0->getLowerBounds()[0];
+    d.dt_ub  = dt0->getUpperBounds()[0];
+    if (ms)
+    {
+        if (dynamic_cast<IntegratorExplicitRungeKutta4*>(_integrator.get()))
+            d.integrator = B200SQP_INT_RK4;
+        else if (dynamic_cast<IntegratorExplicitEuler*>(_integrator.get()))
+            d.integrator = B200SQP_INT_EULER;
+        else
+        {
+            _error = "setIntegrator(): Euler or RK4 expected";
+            return false;
+        }
+    }
+    else
+    {
+        // grids default to Crank-Nicolson (full_discretization_grid_base.h:138)
+        const FiniteDifferencesCollocationInterface* c = _collocation.get();
+        if (!c || dynamic_cast<const CrankNicolsonDiffCollocation*>(c))
+            d.collocation = B200SQP_COLL_CRANK_NICOLSON;
+        else if (dynamic_cast<const ForwardDiffCollocation*>(c))
+            d.collocation = B200SQP_COLL_FORWARD;
+        else if (dynamic_cast<const BackwardDiffCollocation*>(c))
+            d.collocation = B200SQP_COLL_BACKWARD;
+        else if (dynamic_cast<const MidpointDiffCollocation*>(c))
+            d.collocation = B200SQP_COLL_MIDPOINT;
+        else
+        {
+            _error = "collocation type is not in the device registry";
+            return false;
+        }
+    }
+
+    // ---- vertices: x0 (must be fixed), bounds, fixed goal mask
+    const VertexInterface* x_first = eq.front()->getVertexRaw(0);
+    const VertexInterface* u_first = eq.front()->getVertexRaw(1);
+    const VertexInterface* x_last  = eq.back()->getVertexRaw(2);
+    if (!x_first->isFixed())
+    {
+        _error = "the first state vertex is expected to be fixed";
+        return false;
+    }
+    x0.assign(x_first->getData(), x_first->getData() + d.nx);
+    for (int i = 0; i < d.nx; ++i)
+    {
+        d.x_lb[i]     = x_last->getLowerBounds()[i];
+        d.x_ub[i]     = x_last->getUpperBounds()[i];
+        d.xf_fixed[i] = x_last->isFixedComponent(i) ? 1 : 0;
+    }
+    for (int i = 0; i < d.nu; ++i)
+    {
+        d.u_lb[i] = u_first->getLowerBounds()[i];
+        d.u_ub[i] = u_first->getUpperBounds()[i];
+    }
+
+    // ---- reference: static state reference (also the value of fixed goal components)
+    xref.assign(d.nx, 0.0);
+    if (_xref)
+    {
+        if (!_xref->isStatic())
+        {
+            _error = "only static state references are supported";
+            return false;
+        }
+        const ReferenceTrajectoryInterface::OutputVector& r = _xref->getReferenceCached(0);
+        for (int i = 0; i < d.nx; ++i) xref[i] = r[i];
+    }
+    else
+        for (int i = 0; i < d.nx; ++i)
+            if (d.xf_fixed[i]) xref[i] = x_last->getData()[i];
+    d.zero_u_ref = 1;
+    d.zero_x_ref = 1;
+    for (double v : xref) d.zero_x_ref = d.zero_x_ref && v == 0.0;
+
+    // ---- costs
+    d.stage_cost = B200SQP_COST_NONE;
+    if (_stage_cost)
+    {
+        if (auto* q = dynamic_cast<QuadraticFormCost*>(_stage_cost.get()))
+        {
+            if (!q->isLsqFormNonIntegralStateTerm(0) || q->hasIntegralTerms(0))
+            {
+                _error = "QuadraticFormCost must be non-integral and in lsq form";
+                return false;
+            }
+            const Eigen::MatrixXd& Q = q->getWeightQ();
+            const Eigen::MatrixXd& R = q->getWeightR();
+            if (Q.rows() != d.nx || R.rows() != d.nu || !Q.isDiagonal(1e-10) || !R.isDiagonal(1e-10))
+            {
+                _error = "QuadraticFormCost: diagonal Q (nx) and R (nu) expected";
+                return false;
+            }
+            d.stage_cost = B200SQP_COST_QUADRATIC_LSQ;
+            for (int i = 0; i < d.nx; ++i) d.q_diag[i] = Q(i, i);
+            for (int i = 0; i < d.nu; ++i) d.r_diag[i] = R(i, i);
+        }
+        else if (auto* t = dynamic_cast<MinimumTime*>(_stage_cost.get()))
+        {
+            if (!t->isLsqFormNonIntegralDtTerm(0))
+            {
+                _error = "MinimumTime must be in lsq form";
+                return false;
+            }
+            d.stage_cost = B200SQP_COST_MINIMUM_TIME_LSQ;
+        }
+        else
+        {
+            _error = "stage cost type is not in the device registry";
+            return false;
+        }
+    }
+    d.final_cost = 0;
+    if (_final_cost)
+    {
+        auto* qf = dynamic_cast<QuadraticFinalStateCost*>(_final_cost.get());
+        if (!qf || !qf->isLsqFormNonIntegralStateTerm(0) || !qf->getWeightQf().isDiagonal(1e-10) || qf->getWeightQf().rows() != d.nx)
+        {
+            _error = "final cost must be a diagonal QuadraticFinalStateCost in lsq form";
+            return false;
+        }
+        d.final_cost = 1;
+        for (int i = 0; i < d.nx; ++i) d.qf_diag[i] = qf->getWeightQf()(i, i);
+    }
+    return true;
+}
+
+bool SolverB200Lm::upload(OptimizationProblemInterface& problem, int batch)
+{
+    std::vector<double> x0, xref;
+    b200sqp_ocp d;
+    if (!describe(problem, d, x0, xref)) return false;
+    b200sqp_dims dims;
+    if (b200sqp_dims_of(&d, &dims) != 0)
+    {
+        _error = std::string("descriptor rejected: ") + b200sqp_last_error();
+        return false;
+    }
+    // the reference's own numbers (levenberg_marquardt_sparse.cpp:56-71) must agree with the device structure, index for index
+    if (dims.n_params != problem.getParameterDimension() || dims.m_lsq != problem.getLsqObjectiveDimension() ||
+        dims.m_eq != problem.getEqualityDimension() || dims.m_ineq != problem.getInequalityDimension() ||
+        dims.m_bounds != problem.finiteCombinedBoundsDimension())
+    {
+        _error = "device structure does not match the hypergraph's dimensions";
+        return false;
+    }
+    if (_handle && (std::memcmp(&d, &_ocp, sizeof(d)) != 0 || batch != _batch)) clear();
+    _fresh = false;
+    if (!_handle)
+    {
+        _fresh = true;
+        if (b200sqp_create(&d, batch, _device, &_handle) != 0)
+        {
+            _error  = std::string("b200sqp_create: ") + b200sqp_last_error();
+            _handle = nullptr;
+            return false;
+        }
+        _ocp   = d;
+        _dims  = dims;
+        _batch = batch;
+    }
+    return true;
+}
+
+// Guard of SURVEY.md section 8b: the device residual vector at the current parameters must equal the reference's computeValues.
+bool SolverB200Lm::selfCheck(OptimizationProblemInterface& problem)
+{
+    const int m = _dims.m_lsq + _dims.m_eq + _dims.m_ineq + _dims.m_bounds;
+    std::vector<double> dev((size_t)m * _batch);
+    if (b200sqp_evaluate(_handle, 1.0, 1.0, 1.0, dev.data(), nullptr) != 0)
+    {
+        _error = std::string("b200sqp_evaluate: ") + b200sqp_last_error();
+        return false;
+    }
+    Eigen::VectorXd host(m);
+    if (_dims.m_lsq > 0) problem.computeValuesLsqObjective(host.segment(0, _dims.m_lsq));
+    if (_dims.m_eq > 0) problem.computeValuesEquality(host.segment(_dims.m_lsq, _dims.m_eq));
+    if (_dims.m_bounds > 0) problem.computeDistanceFiniteCombinedBounds(host.segment(_dims.m_lsq + _dims.m_eq, _dims.m_bounds));
+    double worst = 0;
+    for (int i = 0; i < m; ++i) worst = std::max(worst, std::abs(host[i] - dev[i]) / std::max(1.0, std::abs(host[i])));
+    if (!(worst <= 1e-9))
+    {
+        _error = "device residuals differ from the reference's computeValues (structure mis-extracted?)";
+        return false;
+    }
+    // b200sqp_evaluate perturbs the parameters like a Jacobian evaluation would; restore the caller's point
+    return true;
+}
+
+SolverStatus SolverB200Lm::solve(OptimizationProblemInterface& problem, bool new_structure, bool new_run, double* obj_value)
+{
+    if (obj_value) *obj_value = -1;  // levenberg_marquardt_sparse.cpp:46
+    if (!problem.isLeastSquaresProblem())
+        return fail("cannot handle non-least-squares objectives or LS objectives in non-LS form.");  // :50-54
+    std::vector<OptimizationProblemInterface*> one{&problem};
+    std::vector<SolverStatus> st;
+    std::vector<double> obj;
+    (void)new_structure;  // the descriptor comparison in upload() decides whether device state must be rebuilt
+    if (!solveBatch(one, new_run, &st, &obj)) return SolverStatus::Error;
+    if (obj_value) *obj_value = obj[0];
+    return st[0];
+}
+
+bool SolverB200Lm::solveBatch(const std::vector<OptimizationProblemInterface*>& problems, bool new_run, std::vector<SolverStatus>* statuses,
+                              std::vector<double>* obj_values)
+{
+    const int B = (int)problems.size();
+    if (B == 0) return true;
+    if (!upload(*problems[0], B))
+    {
+        fail(_error);
+        return false;
+    }
+    const int n = _dims.n_params, nx = _ocp.nx;
+    std::vector<double> x0((size_t)B * nx), xref((size_t)B * nx), params((size_t)B * n);
+    for (int i = 0; i < B; ++i)
+    {
+        std::vector<double> x0i, xrefi;
+        b200sqp_ocp di;
+        if (!describe(*problems[i], di, x0i, xrefi) || std::memcmp(&di, &_ocp, sizeof(di)) != 0)
+        {
+            fail("problems of one batch must share one structure: " + _error);
+            return false;
+        }
+        std::copy(x0i.begin(), x0i.end(), x0.begin() + (size_t)i * nx);
+        std::copy(xrefi.begin(), xrefi.end(), xref.begin() + (size_t)i * nx);
+        Eigen::Map<Eigen::VectorXd> p(params.data() + (size_t)i * n, n);
+        problems[i]->getParameterVector(p);
+    }
+    if (b200sqp_set_problem_data(_handle, x0.data(), xref.data()) != 0 || b200sqp_set_params(_handle, params.data()) != 0)
+    {
+        fail(std::string("upload failed: ") + b200sqp_last_error());
+        return false;
+    }
+    if (_fresh)
+    {
+        // new structure on the device: run the guard once, then restore the unperturbed parameters
+        if (!selfCheck(*problems[0]) || b200sqp_set_params(_handle, params.data()) != 0)
+        {
+            fail(_error);
+            return false;
+        }
+    }
+    std::vector<int32_t> status(B);
+    std::vector<double> chi2(B);
+    if (b200sqp_solve(_handle, &_opts, new_run ? 1 : 0, status.data(), chi2.data()) != 0 || b200sqp_get_params(_handle, params.data()) != 0)
+    {
+        fail(std::string("solve failed: ") + b200sqp_last_error());
+        return false;
+    }
+    for (int i = 0; i < B; ++i)
+        problems[i]->setParameterVector(Eigen::Map<const Eigen::VectorXd>(params.data() + (size_t)i * n, n));
+    if (statuses)
+    {
+        statuses->resize(B);
+        for (int i = 0; i < B; ++i) (*statuses)[i] = status[i] == B200SQP_STATUS_CONVERGED ? SolverStatus::Converged : SolverStatus::EarlyTerminated;
+    }
+    if (obj_values) obj_values->assign(chi2.begin(), chi2.end());
+    return true;
+}
+
+}  // namespace corbo

@@ -1,0 +1,97 @@
+// corbo::SolverB200Lm -- the reference-side plugin of this project: a corbo::NlpSolverInterface
+// (src/optimization/include/corbo-optimization/solver/nlp_solver_interface.h:67-118) that keeps the interface and parameters of
+// corbo::LevenbergMarquardtSparse (solver/levenberg_marquardt_sparse.h:68-163) and runs the whole LM/SQP inner loop on a B200
+// through the C ABI of libb200sqp.so (include/b200sqp.h).  It drops in under
+// StructuredOptimalControlProblem::initialize/compute/reset (src/optimal_control/src/structured_ocp/
+// structured_optimal_control_problem.cpp:61,134,204) and PredictiveController::step (src/controllers/src/predictive_controller.cpp:66)
+// without touching reference sources.
+//
+// Discovery gap: a solver only receives OptimizationProblemInterface&.  The hypergraph walk yields the grid
+// kind and size, dimensions, bounds, fixed masks, x0 and the parameter vector; the functors behind the edges are private in the
+// reference, so the objects the user handed to the OCP are handed to this solver as well (setSystemDynamics, setCollocation /
+// setIntegrator, setStageCost, setFinalStageCost, setStateReference).  Anything outside the closed registry makes solve() return
+// SolverStatus::Error -- there is no CPU fallback.  After every structure upload the device residual vector is compared with the
+// reference's own computeValues on the host to catch a mis-extraction.
+#ifndef CONTROL_BOX_RST_B200_ADAPTER_SOLVER_B200_LM_H_
+#define CONTROL_BOX_RST_B200_ADAPTER_SOLVER_B200_LM_H_
+
+#include <corbo-core/reference_trajectory.h>
+#include <corbo-numerics/finite_differences_collocation.h>
+#include <corbo-numerics/integrator_interface.h>
+#include <corbo-optimal-control/functions/stage_functions.h>
+#include <corbo-optimization/solver/nlp_solver_interface.h>
+#include <corbo-systems/system_dynamics_interface.h>
+
+#include <memory>
+#include <string>
+#include <vector>
+
+#include "../../include/b200sqp.h"
+
+namespace corbo {
+
+class SolverB200Lm : public NlpSolverInterface
+{
+ public:
+    using Ptr = std::shared_ptr<SolverB200Lm>;
+
+    SolverB200Lm();
+    ~SolverB200Lm() override;
+
+    // ---- NlpSolverInterface ----------------------------------------------------------------------------------------------
+    NlpSolverInterface::Ptr getInstance() const override { return std::make_shared<SolverB200Lm>(); }
+    bool isLsqSolver() const override { return true; }
+    bool initialize(OptimizationProblemInterface* problem = nullptr) override;
+    SolverStatus solve(OptimizationProblemInterface& problem, bool new_structure = true, bool new_run = true, double* obj_value = nullptr) override;
+    void clear() override;
+
+    // ---- LevenbergMarquardtSparse parameters (levenberg_marquardt_sparse.h:85-90) -------------------------------------------------
+    void setIterations(int iterations) { _opts.iterations = iterations; }
+    void setPenaltyWeights(double weight_eq, double weight_ineq, double weight_bounds);
+    void setWeightAdapation(double factor_eq, double factor_ineq, double factor_bounds, double max_eq, double max_ineq, double max_bounds);
+
+    // ---- the objects behind the edges (same shared_ptrs the user gave to StructuredOptimalControlProblem / the grid) -----------
+    void setSystemDynamics(SystemDynamicsInterface::Ptr dynamics) { _dynamics = dynamics; }
+    void setCollocation(FiniteDifferencesCollocationInterface::Ptr collocation) { _collocation = collocation; }
+    void setIntegrator(NumericalIntegratorExplicitInterface::Ptr integrator) { _integrator = integrator; }
+    void setStageCost(StageCost::Ptr stage_cost) { _stage_cost = stage_cost; }
+    void setFinalStageCost(FinalStageCost::Ptr final_cost) { _final_cost = final_cost; }
+    void setStateReference(ReferenceTrajectoryInterface::Ptr xref) { _xref = xref; }
+    void setDevice(int device) { _device = device; }
+
+    // ---- batch front-end: B OCP objects of identical structure, one device call (SURVEY.md section 7 "hard parts") ------------------
+    // problems[i] hold the initial parameters before and the optimised ones after the call; statuses/obj_values may be null.
+    bool solveBatch(const std::vector<OptimizationProblemInterface*>& problems, bool new_run, std::vector<SolverStatus>* statuses,
+                    std::vector<double>* obj_values);
+
+    const std::string& lastError() const { return _error; }
+    double lastSolveMilliseconds() const;
+
+ private:
+    bool describe(OptimizationProblemInterface& problem, b200sqp_ocp& ocp, std::vector<double>& x0, std::vector<double>& xref);
+    bool upload(OptimizationProblemInterface& problem, int batch);
+    bool selfCheck(OptimizationProblemInterface& problem);
+    SolverStatus fail(const std::string& msg);
+
+    b200sqp_lm_options _opts;
+    b200sqp_handle _handle = nullptr;
+    b200sqp_ocp _ocp;
+    b200sqp_dims _dims;
+    int _batch  = 0;
+    bool _fresh = false;  // device state was (re)built by the last upload()
+    int _device = 0;
+    std::string _error;
+
+    SystemDynamicsInterface::Ptr _dynamics;
+    FiniteDifferencesCollocationInterface::Ptr _collocation;
+    NumericalIntegratorExplicitInterface::Ptr _integrator;
+    StageCost::Ptr _stage_cost;
+    FinalStageCost::Ptr _final_cost;
+    ReferenceTrajectoryInterface::Ptr _xref;
+};
+
+FACTORY_REGISTER_NLP_SOLVER(SolverB200Lm)
+
+}  // namespace corbo
+
+#endif  // CONTROL_BOX_RST_B200_ADAPTER_SOLVER_B200_LM_H_
