@@ -359,11 +359,14 @@ int b200sqp_set_problem_data(b200sqp_handle h, const double* x0, const double* x
     h->launches += 1;
     // fixed goal components follow the reference: _xf.values()[i] = xref[i] (full_discretization_grid_base.cpp:102-106)
     const int nb = h->s.nb, xo = h->s.nu + h->s.vt;
+    unsigned mask = 0;
     for (int i = 0; i < h->s.nx; ++i)
-        if (h->s.xfFixed(i))
-            for (int b = 0; b < 2; ++b)
-                CUDA_TRY(cudaMemcpyAsync(h->st.z[b] + ((size_t)(h->s.K - 1) * nb + xo + i) * h->S, h->st.xref + (size_t)i * h->S,
-                                         sizeof(double) * h->S, cudaMemcpyDeviceToDevice, h->stream));
+        if (h->s.xfFixed(i)) mask |= 1u << i;
+    if (mask)
+    {
+        launchFillPinned(h->st.xref, h->st.z[0], h->st.z[1], (h->s.K - 1) * nb + xo, h->s.K * nb, h->s.nx, mask, h->B, h->stream);
+        h->launches += 1;
+    }
     CUDA_TRY(cudaGetLastError());
     return B200SQP_OK;
 }
@@ -398,7 +401,7 @@ int b200sqp_get_params(b200sqp_handle h, double* params)
     if (rc) return rc;
     if (!params) return fail(B200SQP_ERR_INVALID, "params is null");
     const int n = h->s.dims.n_params;
-    launchUnpack(h->st.z[0], h->st.z[1], h->st.cur, h->d_internal_of_ref, n, h->d_params, h->B, h->S, h->stream);
+    launchUnpack(h->st.z[0], h->st.z[1], h->st.cur, h->d_internal_of_ref, n, h->s.K * h->s.nb, h->d_params, h->B, h->S, h->stream);
     h->launches += 1;
     CUDA_TRY(cudaGetLastError());
     CUDA_TRY(cudaMemcpyAsync(params, h->d_params, sizeof(double) * (size_t)h->B * n, cudaMemcpyDeviceToHost, h->stream));
@@ -411,7 +414,7 @@ int b200sqp_get_first_controls(b200sqp_handle h, double* u0)
     int rc = checkHandle(h);
     if (rc) return rc;
     if (!u0) return fail(B200SQP_ERR_INVALID, "u0 is null");
-    launchFirstControls(h->st.z[0], h->st.z[1], h->st.cur, h->s.nu, h->d_u0, h->B, h->S, h->stream);
+    launchFirstControls(h->st.z[0], h->st.z[1], h->st.cur, h->s.nu, h->s.K * h->s.nb, h->d_u0, h->B, h->S, h->stream);
     h->launches += 1;
     CUDA_TRY(cudaGetLastError());
     CUDA_TRY(cudaMemcpyAsync(u0, h->d_u0, sizeof(double) * (size_t)h->B * h->s.nu, cudaMemcpyDeviceToHost, h->stream));
@@ -469,7 +472,7 @@ int b200sqp_step(b200sqp_handle h, const b200sqp_lm_options* opts, int32_t cold_
     if (params_out)
     {
         const int n = h->s.dims.n_params;
-        launchUnpack(h->st.z[0], h->st.z[1], h->st.cur, h->d_internal_of_ref, n, h->d_params, h->B, h->S, h->stream);
+        launchUnpack(h->st.z[0], h->st.z[1], h->st.cur, h->d_internal_of_ref, n, h->s.K * h->s.nb, h->d_params, h->B, h->S, h->stream);
         h->launches += 1;
         CUDA_TRY(cudaGetLastError());
         CUDA_TRY(cudaMemcpyAsync(params_out, h->d_params, sizeof(double) * (size_t)h->B * n, cudaMemcpyDeviceToHost, h->stream));

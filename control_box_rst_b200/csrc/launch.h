@@ -29,11 +29,14 @@ const KernelSet* kernelTableUnicycle(int* count);
 const KernelSet* kernelTableQuadrotor(int* count);
 
 // layout helpers (util_kernels.cu); all arrays device pointers
-// params [B][n] (reference order)  <->  z [K*NB][S] (block order, instance-minor); pinned slots (ref index -1) are filled from `pinned`
+// params [B][n] (reference order)  <->  z (block order, tiled instance-minor [tile][K*NB][32]); pinned slots (ref index -1) are left alone
 void launchPack(const double* params, int n, const int* ref_of_internal, int slots, const double* pinned_values /*[slots] or null*/, double* z,
                 const int* cur_or_null, double* z_alt, int B, int S, cudaStream_t);
-void launchUnpack(const double* z0, const double* z1, const int* cur, const int* internal_of_ref, int n, double* params, int B, int S, cudaStream_t);
-// x0/xref: [B][nx] -> [nx][S]
+void launchUnpack(const double* z0, const double* z1, const int* cur, const int* internal_of_ref, int n, int slots, double* params, int B, int S,
+                  cudaStream_t);
+// fixed goal components <- xref
+void launchFillPinned(const double* xref, double* z0, double* z1, int slot0, int slots, int nx, unsigned mask, int B, cudaStream_t);
+// x0/xref: [B][nx] -> tiled [tile][nx][32]
 void launchTransposeIn(const double* src, int dim, double* dst, int B, int S, cudaStream_t);
 // [rows][S] -> [B][rows]
 void launchTransposeOut(const double* src, int rows, double* dst, int B, int S, cudaStream_t);
@@ -41,6 +44,6 @@ void launchTransposeOut(const double* src, int rows, double* dst, int B, int S, 
 void launchInitTrajectories(const double* x0 /*[nx][S]*/, const double* xref /*[nx][S]*/, double* z, int* cur, int K, int nx, int nu, int vt,
                             double dt_ref, const int* xf_fixed_dev, int B, int S, cudaStream_t);
 // u_0 of every instance -> [B][nu]
-void launchFirstControls(const double* z0, const double* z1, const int* cur, int nu, double* u0, int B, int S, cudaStream_t);
+void launchFirstControls(const double* z0, const double* z1, const int* cur, int nu, int slots, double* u0, int B, int S, cudaStream_t);
 
 }  // namespace b200sqp

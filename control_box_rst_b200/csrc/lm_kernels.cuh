@@ -28,7 +28,7 @@ template <class M, int DEFECT, int VT, int T>
 __global__ void __launch_bounds__(32 * T) lmSolveKernel(const __grid_constant__ DeviceOcp P, const __grid_constant__ DeviceState st, int iterations)
 {
     using Dm = Dim<M, VT>;
-    constexpr int NX = Dm::NX, XO = Dm::XO, NB = Dm::NB;
+    constexpr int NX = Dm::NX, XO = Dm::XO, NB = Dm::NB, ND = Dm::ND;
     const int g      = threadIdx.x & 31;
     const int p      = threadIdx.x >> 5;
     const int i      = blockIdx.x * 32 + g;
@@ -39,7 +39,7 @@ __global__ void __launch_bounds__(32 * T) lmSolveKernel(const __grid_constant__ 
     const int S      = P.S;
 
     using BS = BlockSolver<M, VT>;
-    constexpr int NXX = Dm::NXX, ND = Dm::ND;
+    constexpr int NXX = Dm::NXX;
     constexpr bool TWISTED = T >= 2;  // two threads of an instance eliminate from both ends of the horizon
     __shared__ double s_red[3][T][32];
     __shared__ double s_muacc[32], s_mu[32];
@@ -50,15 +50,18 @@ __global__ void __launch_bounds__(32 * T) lmSolveKernel(const __grid_constant__ 
     const int m_mid = TWISTED ? K / 2 : K - 1;  // middle block of the twisted elimination
 
     const Weights w{st.w_eq, st.w_ineq, st.w_b};
-    const int ii        = valid ? i : 0;
-    const double* x0p   = st.x0 + ii;
-    const double* xrefp = st.xref + ii;
-    double* D  = st.D + ii;
-    double* E  = st.E + ii;
-    double* gg = st.g + ii;
-    double* dl = st.dl + ii;
-    double* L  = st.L + ii;
-    double* W  = st.W + ii;
+    // tiled arrays: this block's tile, this thread's lane (lm_device.cuh TILE)
+    constexpr int NE_   = Dm::NE;
+    const size_t tile   = blockIdx.x;
+    const double* x0p   = st.x0 + tile * ((size_t)NX * TILE) + g;
+    const double* xrefp = st.xref + tile * ((size_t)NX * TILE) + g;
+    double* D  = st.D + tile * ((size_t)K * ND * TILE) + g;
+    double* E  = st.E + tile * ((size_t)K * NE_ * TILE) + g;
+    double* gg = st.g + tile * ((size_t)K * NB * TILE) + g;
+    double* dl = st.dl + tile * ((size_t)K * NB * TILE) + g;
+    double* L  = st.L + tile * ((size_t)K * ND * TILE) + g;
+    double* W  = st.W + tile * ((size_t)K * NE_ * TILE) + g;
+    const size_t zoff = tile * ((size_t)K * NB * TILE) + g;
 
     constexpr double eps1 = 1e-5, eps2 = 1e-5, eps3 = 1e-5, eps4 = 0;
     constexpr double tau                = 1e-5;
@@ -81,13 +84,13 @@ __global__ void __launch_bounds__(32 * T) lmSolveKernel(const __grid_constant__ 
     // One linearisation phase for the instances flagged F_LIN; executed by the whole block because it contains barriers.
     auto linearizePhase = [&](bool first) {
         const bool do_lin = valid && (s_flags[g] & F_LIN);
-        double* z         = st.z[s_cur[g]] + ii;
+        double* z         = st.z[s_cur[g]] + zoff;
         double xn_last[NX];
         if (do_lin && kb < K)
         {
-            const double* zp = z + (size_t)(kb - 1) * NB * S;
+            const double* zp = z + (size_t)(kb - 1) * NB * TILE;
 #pragma unroll
-            for (int j = 0; j < NX; ++j) xn_last[j] = zp[(size_t)(XO + j) * S];
+            for (int j = 0; j < NX; ++j) xn_last[j] = zp[(size_t)(XO + j) * TILE];
         }
         if (T > 1) __syncthreads();  // boundary states are read before any neighbour writes its perturbed copy back
         NormalEquationSink<M, VT> sink(P, D, E, gg, ka, kb);
@@ -201,7 +204,7 @@ __global__ void __launch_bounds__(32 * T) lmSolveKernel(const __grid_constant__ 
         {
             const bool do_trial = valid && (s_flags[g] & F_ACTIVE) && !step_small;
             double part         = 0.0;
-            if (do_trial) part = trialChi2<M, DEFECT, VT>(P, w, st.z[s_cur[g]] + ii, dl, st.z[s_cur[g] ^ 1] + ii, x0p, xrefp, ka, kb);
+            if (do_trial) part = trialChi2<M, DEFECT, VT>(P, w, st.z[s_cur[g]] + zoff, dl, st.z[s_cur[g] ^ 1] + zoff, x0p, xrefp, ka, kb);
             s_red[0][p][g] = part;
         }
         __syncthreads();
@@ -296,7 +299,10 @@ __global__ void __launch_bounds__(32) evaluateKernel(const __grid_constant__ Dev
     if (i >= P.B) return;
     const Weights w{st.w_eq, st.w_ineq, st.w_b};
     MaterializeSink<M, VT> sink{P, values ? values + i : nullptr, jac ? jac + i : nullptr, value_rows, jac_pos, v_count, j_count};
-    linearizeSweep<M, DEFECT, VT>(P, w, st.z[st.cur[i]] + i, st.x0 + i, st.xref + i, 0, P.K, nullptr, sink);
+    using Dm          = Dim<M, VT>;
+    const size_t tile = i >> 5, lane = i & 31;
+    linearizeSweep<M, DEFECT, VT>(P, w, st.z[st.cur[i]] + tile * ((size_t)P.K * Dm::NB * TILE) + lane, st.x0 + tile * ((size_t)Dm::NX * TILE) + lane,
+                                  st.xref + tile * ((size_t)Dm::NX * TILE) + lane, 0, P.K, nullptr, sink);
 }
 
 // Cooperating threads per instance: small batches are latency bound (one warp per SM would leave the machine idle), so the

@@ -7,6 +7,9 @@ namespace b200sqp {
 
 namespace {
 
+// tiled instance-minor addressing (lm_device.cuh TILE): element `slot` of instance i in an array with `nslots` slots per instance
+__device__ __forceinline__ size_t tiled(int i, int slot, int nslots) { return ((size_t)(i >> 5) * nslots + slot) * 32 + (i & 31); }
+
 __global__ void packKernel(const double* __restrict__ params, int n, const int* __restrict__ ref_of_internal, int slots,
                            const double* __restrict__ pinned, double* __restrict__ z, const int* __restrict__ cur, double* __restrict__ z_alt, int B,
                            int S)
@@ -17,29 +20,24 @@ __global__ void packKernel(const double* __restrict__ params, int n, const int* 
     for (int s = 0; s < slots; ++s)
     {
         const int r = ref_of_internal[s];
-        double v;
-        if (r >= 0)
-            v = params[(size_t)i * n + r];
-        else
-            v = pinned ? pinned[(size_t)s * S + i] : dst[(size_t)s * S + i];
-        dst[(size_t)s * S + i] = v;
+        if (r >= 0) dst[tiled(i, s, slots)] = params[(size_t)i * n + r];  // pinned slots (fixed goal components) are left alone
     }
 }
 
 __global__ void unpackKernel(const double* __restrict__ z0, const double* __restrict__ z1, const int* __restrict__ cur,
-                             const int* __restrict__ internal_of_ref, int n, double* __restrict__ params, int B, int S)
+                             const int* __restrict__ internal_of_ref, int n, int slots, double* __restrict__ params, int B, int S)
 {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= B) return;
     const double* src = cur[i] ? z1 : z0;
-    for (int r = 0; r < n; ++r) params[(size_t)i * n + r] = src[(size_t)internal_of_ref[r] * S + i];
+    for (int r = 0; r < n; ++r) params[(size_t)i * n + r] = src[tiled(i, internal_of_ref[r], slots)];
 }
 
 __global__ void transposeInKernel(const double* __restrict__ src, int dim, double* __restrict__ dst, int B, int S)
 {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= B) return;
-    for (int j = 0; j < dim; ++j) dst[(size_t)j * S + i] = src[(size_t)i * dim + j];
+    for (int j = 0; j < dim; ++j) dst[tiled(i, j, dim)] = src[(size_t)i * dim + j];
 }
 
 __global__ void transposeOutKernel(const double* __restrict__ src, int rows, double* __restrict__ dst, int B, int S)
@@ -58,39 +56,53 @@ __global__ void initTrajectoriesKernel(const double* __restrict__ x0, const doub
 {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= B) return;
-    const int nb = nu + vt + nx;
+    const int nb = nu + vt + nx, slots = K * nb;
     double dist  = 0.0;
     for (int j = 0; j < nx; ++j)
     {
-        const double d = xref[(size_t)j * S + i] - x0[(size_t)j * S + i];
+        const double d = xref[tiled(i, j, nx)] - x0[tiled(i, j, nx)];
         dist += d * d;
     }
     dist              = sqrt(dist);
     const double step = dist / K;
     for (int k = 0; k < K; ++k)
     {
-        double* zk = z + (size_t)k * nb * S + i;
-        for (int j = 0; j < nu; ++j) zk[(size_t)j * S] = 0.0;
-        if (vt) zk[(size_t)nu * S] = dt_ref;
+        for (int j = 0; j < nu; ++j) z[tiled(i, k * nb + j, slots)] = 0.0;
+        if (vt) z[tiled(i, k * nb + nu, slots)] = dt_ref;
         for (int j = 0; j < nx; ++j)
         {
-            const double a = x0[(size_t)j * S + i], b = xref[(size_t)j * S + i];
+            const double a = x0[tiled(i, j, nx)], b = xref[tiled(i, j, nx)];
             double dir     = b - a;
             if (dist != 0) dir /= dist;
             // block k holds x_{k+1}; the last block holds xf = xref
-            zk[(size_t)(nu + vt + j) * S] = (k + 1 < K) ? a + (double)(k + 1) * step * dir : b;
+            z[tiled(i, k * nb + nu + vt + j, slots)] = (k + 1 < K) ? a + (double)(k + 1) * step * dir : b;
         }
     }
     cur[i] = 0;
 }
 
-__global__ void firstControlsKernel(const double* __restrict__ z0, const double* __restrict__ z1, const int* __restrict__ cur, int nu,
+__global__ void firstControlsKernel(const double* __restrict__ z0, const double* __restrict__ z1, const int* __restrict__ cur, int nu, int slots,
                                     double* __restrict__ u0, int B, int S)
 {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= B) return;
     const double* src = cur[i] ? z1 : z0;
-    for (int j = 0; j < nu; ++j) u0[(size_t)i * nu + j] = src[(size_t)j * S + i];
+    for (int j = 0; j < nu; ++j) u0[(size_t)i * nu + j] = src[tiled(i, j, slots)];
+}
+
+// fixed goal components take their value from the reference: _xf.values()[i] = xref[i] (full_discretization_grid_base.cpp:102-106)
+__global__ void fillPinnedKernel(const double* __restrict__ xref, double* __restrict__ z0, double* __restrict__ z1, int slot0, int slots, int nx,
+                                 unsigned mask, int B)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= B) return;
+    for (int j = 0; j < nx; ++j)
+        if (mask & (1u << j))
+        {
+            const double v               = xref[tiled(i, j, nx)];
+            z0[tiled(i, slot0 + j, slots)] = v;
+            z1[tiled(i, slot0 + j, slots)] = v;
+        }
 }
 
 inline int blocksFor(int B) { return (B + 127) / 128; }
@@ -102,10 +114,14 @@ void launchPack(const double* params, int n, const int* ref_of_internal, int slo
 {
     packKernel<<<blocksFor(B), 128, 0, st>>>(params, n, ref_of_internal, slots, pinned, z, cur, z_alt, B, S);
 }
-void launchUnpack(const double* z0, const double* z1, const int* cur, const int* internal_of_ref, int n, double* params, int B, int S,
+void launchUnpack(const double* z0, const double* z1, const int* cur, const int* internal_of_ref, int n, int slots, double* params, int B, int S,
                   cudaStream_t st)
 {
-    unpackKernel<<<blocksFor(B), 128, 0, st>>>(z0, z1, cur, internal_of_ref, n, params, B, S);
+    unpackKernel<<<blocksFor(B), 128, 0, st>>>(z0, z1, cur, internal_of_ref, n, slots, params, B, S);
+}
+void launchFillPinned(const double* xref, double* z0, double* z1, int slot0, int slots, int nx, unsigned mask, int B, cudaStream_t st)
+{
+    fillPinnedKernel<<<blocksFor(B), 128, 0, st>>>(xref, z0, z1, slot0, slots, nx, mask, B);
 }
 void launchTransposeIn(const double* src, int dim, double* dst, int B, int S, cudaStream_t st)
 {
@@ -120,9 +136,9 @@ void launchInitTrajectories(const double* x0, const double* xref, double* z, int
 {
     initTrajectoriesKernel<<<blocksFor(B), 128, 0, st>>>(x0, xref, z, cur, K, nx, nu, vt, dt_ref, B, S);
 }
-void launchFirstControls(const double* z0, const double* z1, const int* cur, int nu, double* u0, int B, int S, cudaStream_t st)
+void launchFirstControls(const double* z0, const double* z1, const int* cur, int nu, int slots, double* u0, int B, int S, cudaStream_t st)
 {
-    firstControlsKernel<<<blocksFor(B), 128, 0, st>>>(z0, z1, cur, nu, u0, B, S);
+    firstControlsKernel<<<blocksFor(B), 128, 0, st>>>(z0, z1, cur, nu, slots, u0, B, S);
 }
 
 }  // namespace b200sqp
