@@ -73,6 +73,8 @@ struct b200sqp_solver
     double* d_u0 = nullptr;       // [B][nu]
     int* d_ref_of_internal = nullptr, *d_internal_of_ref = nullptr, *d_value_rows = nullptr, *d_jac_pos = nullptr;
     double* d_values = nullptr, *d_jac = nullptr, *d_eval_out = nullptr;
+    long long* d_phase_cycles = nullptr;
+    int phase_blocks = 0;
     std::vector<void*> allocations;
 
     template <class T>
@@ -578,8 +580,38 @@ int b200sqp_device_pointers(b200sqp_handle h, void** chi2, void** status, void**
 
 int b200sqp_set_threads_per_instance(b200sqp_handle h, int32_t threads)
 {
-    if (!h || threads < 0 || threads > 8) return fail(B200SQP_ERR_INVALID, "threads per instance must be 0 (auto), 1, 2, 4 or 8");
+    if (!h || threads < 0 || threads > 32) return fail(B200SQP_ERR_INVALID, "threads per instance must be 0 (auto), 1, 2, 4 or 8");
     h->threads_per_instance = threads;
+    return B200SQP_OK;
+}
+
+int b200sqp_set_phase_profile(b200sqp_handle h, int32_t enable)
+{
+    int rc = checkHandle(h);
+    if (rc) return rc;
+    if (enable && !h->d_phase_cycles)
+    {
+        h->phase_blocks = (h->B + 31) / 32;
+        CUDA_TRY(h->alloc(&h->d_phase_cycles, (size_t)h->phase_blocks * 4));
+    }
+    h->st.phase_cycles = enable ? h->d_phase_cycles : nullptr;
+    return B200SQP_OK;
+}
+
+int b200sqp_get_phase_cycles(b200sqp_handle h, double* mean_cycles)
+{
+    int rc = checkHandle(h);
+    if (rc) return rc;
+    if (!mean_cycles || !h->st.phase_cycles) return fail(B200SQP_ERR_INVALID, "phase profile is off");
+    std::vector<long long> tmp((size_t)h->phase_blocks * 4);
+    CUDA_TRY(cudaMemcpyAsync(tmp.data(), h->d_phase_cycles, sizeof(long long) * tmp.size(), cudaMemcpyDeviceToHost, h->stream));
+    CUDA_TRY(cudaStreamSynchronize(h->stream));
+    for (int q = 0; q < 4; ++q)
+    {
+        double s = 0.0;
+        for (int b = 0; b < h->phase_blocks; ++b) s += (double)tmp[(size_t)b * 4 + q];
+        mean_cycles[q] = s / h->phase_blocks;
+    }
     return B200SQP_OK;
 }
 

@@ -124,21 +124,55 @@ struct Quadrotor
 // DEFECT ids: 0..3 = b200sqp_collocation, 4 = explicit Euler shooting, 5 = RK4 shooting.
 // ---------------------------------------------------------------------------------------------------------------------------
 
+// x / dt for many x and one dt, correctly rounded like the reference's IEEE division but without a divide per call.
+// With z = RN(1/dt) (one IEEE division per distinct dt):  q = RN(x z);  r = x - q dt (exact in one fma);  x/dt = RN(q + r z).
+// This three-operation sequence returns RN(x/dt) for every x unless dt's significand is all ones (Brisebarre, Muller, Raina,
+// "Accelerating correctly rounded floating-point division when the divisor is known in advance", IEEE TC 53(8), 2004, Alg. 1 /
+// Markstein's theorem), barring over/underflow of the intermediates: dt with an all-ones significand or an extreme exponent
+// takes the plain division.  x = +-inf gives NaN instead of +-inf; both make chi2 non-finite, which the LM loop rejects
+// identically (levenberg_marquardt_sparse.cpp:171).  Profile that motivated it: the divide in the Crank-Nicolson defect was
+// 27 % of all executed instructions of the LM kernel (profiles/r1c_*).  tests/test_division_by_step.py checks the sequence
+// against exact rational arithmetic on hard-to-round cases.
+struct StepSize
+{
+    double dt, rcp;
+    bool fast;
+    __device__ __forceinline__ explicit StepSize(double t) : dt(t)
+    {
+        rcp                          = 1.0 / t;
+        const unsigned long long b   = (unsigned long long)__double_as_longlong(t);
+        const unsigned long long man = b & 0xFFFFFFFFFFFFFull;
+        const unsigned ex            = (unsigned)(b >> 52) & 0x7FFu;
+        fast                         = man != 0xFFFFFFFFFFFFFull && ex > 523u && ex < 1523u;  // 2^-500 < |dt| < 2^500
+    }
+    __device__ __forceinline__ double div(double x) const
+    {
+        if (fast)
+        {
+            const double q = x * rcp;
+            const double r = fma(-q, dt, x);
+            return fma(r, rcp, q);
+        }
+        return x / dt;
+    }
+};
+
 template <class M, int DEFECT>
-__device__ __forceinline__ void defect(const DynParams& c, const double* x1, const double* u1, const double* x2, double dt, double* e)
+__device__ __forceinline__ void defect(const DynParams& c, const double* x1, const double* u1, const double* x2, const StepSize& h, double* e)
 {
     constexpr int NX = M::NX;
+    const double dt  = h.dt;
     if (DEFECT == DEFECT_FORWARD)  // finite_differences_collocation.h:119-136
     {
         M::f(c, x1, u1, e);
 #pragma unroll
-        for (int i = 0; i < NX; ++i) e[i] -= (x2[i] - x1[i]) / dt;
+        for (int i = 0; i < NX; ++i) e[i] -= h.div(x2[i] - x1[i]);
     }
     else if (DEFECT == DEFECT_BACKWARD)  // :153-170
     {
         M::f(c, x2, u1, e);
 #pragma unroll
-        for (int i = 0; i < NX; ++i) e[i] -= (x2[i] - x1[i]) / dt;
+        for (int i = 0; i < NX; ++i) e[i] -= h.div(x2[i] - x1[i]);
     }
     else if (DEFECT == DEFECT_MIDPOINT)  // :187-204
     {
@@ -147,7 +181,7 @@ __device__ __forceinline__ void defect(const DynParams& c, const double* x1, con
         for (int i = 0; i < NX; ++i) xm[i] = 0.5 * (x1[i] + x2[i]);
         M::f(c, xm, u1, e);
 #pragma unroll
-        for (int i = 0; i < NX; ++i) e[i] -= (x2[i] - x1[i]) / dt;
+        for (int i = 0; i < NX; ++i) e[i] -= h.div(x2[i] - x1[i]);
     }
     else if (DEFECT == DEFECT_CRANK_NICOLSON)  // :221-240
     {
@@ -155,7 +189,7 @@ __device__ __forceinline__ void defect(const DynParams& c, const double* x1, con
         M::f(c, x1, u1, f1);
         M::f(c, x2, u1, f2);
 #pragma unroll
-        for (int i = 0; i < NX; ++i) e[i] = (x2[i] - x1[i]) / dt - 0.5 * (f1[i] + f2[i]);
+        for (int i = 0; i < NX; ++i) e[i] = h.div(x2[i] - x1[i]) - 0.5 * (f1[i] + f2[i]);
     }
     else if (DEFECT == DEFECT_EULER)  // explicit_integrators.h:66-72, then "- x2"
     {

@@ -51,6 +51,7 @@ struct DeviceState
     int* n_reject;
     int* n_linearize;
     double* trace;    // [(max_iterations+1)][S] chi2 after every outer iteration
+    long long* phase_cycles;  // [blocks][4] clock64() per phase (linearise, factor+solve, trial, control) or null (profiling off)
     double w_eq, w_ineq, w_b;  // current penalty weights (host-managed: reset / adapted per solve)
 };
 

@@ -73,6 +73,20 @@ __global__ void __launch_bounds__(32 * T) lmSolveKernel(const __grid_constant__ 
     bool stop = false, active = false;
     double mu = 0, mu_acc = 0, rho = 0, chi2_old = 0, last_values = 0, dq = 0;
 
+    // optional phase profile (b200sqp_set_phase_profile): thread 0 of the block accumulates clock64() deltas per phase
+    long long prof_acc[4] = {0, 0, 0, 0};
+    long long prof_last   = 0;
+    const bool prof       = st.phase_cycles != nullptr && threadIdx.x == 0;
+    if (prof) prof_last = clock64();
+    auto tick = [&](int phase) {
+        if (prof)
+        {
+            const long long now = clock64();
+            prof_acc[phase] += now - prof_last;
+            prof_last = now;
+        }
+    };
+
     if (p == 0)
     {
         cur        = valid ? st.cur[i] : 0;
@@ -110,6 +124,7 @@ __global__ void __launch_bounds__(32 * T) lmSolveKernel(const __grid_constant__ 
     };
 
     linearizePhase(true);
+    tick(0);
     if (p == 0 && valid)
     {
         double ginf = 0.0, maxdiag = -CUDART_INF;
@@ -198,6 +213,7 @@ __global__ void __launch_bounds__(32 * T) lmSolveKernel(const __grid_constant__ 
             }
         }
         __syncthreads();
+        tick(1);
         // ---- T: trial point and its chi2, all T threads
         const double dn2_tot = s_dn[0][0][g] + (TWISTED ? s_dn[0][1][g] : 0.0);
         const bool step_small = sqrt(dn2_tot) <= eps2;
@@ -208,6 +224,7 @@ __global__ void __launch_bounds__(32 * T) lmSolveKernel(const __grid_constant__ 
             s_red[0][p][g] = part;
         }
         __syncthreads();
+        tick(2);
         // ---- C: gain ratio, accept / reject, damping update (thread p == 0)
         bool any_lin = false;
         if (p == 0)
@@ -272,9 +289,16 @@ __global__ void __launch_bounds__(32 * T) lmSolveKernel(const __grid_constant__ 
             any_lin    = (flags & F_LIN) != 0;
         }
         const int any_active = __syncthreads_or(p == 0 && active);
+        tick(3);
         if (!any_active) break;
         // ---- L: re-linearise the accepted points
         if (__syncthreads_or(any_lin)) linearizePhase(false);
+        tick(0);
+    }
+    if (prof)
+    {
+#pragma unroll
+        for (int q = 0; q < 4; ++q) st.phase_cycles[(size_t)blockIdx.x * 4 + q] = prof_acc[q];
     }
 
     if (p == 0 && valid)
@@ -321,6 +345,10 @@ void launchSolve(const DeviceOcp& P, const DeviceState& st, int iterations, int 
         while (T < 8 && P.K / (2 * T) >= 3) T *= 2;
     }
     if (T > MAXT) T = MAXT;
+    if constexpr (MAXT >= 24)
+        if (T >= 24) return (void)lmSolveKernel<M, DEFECT, VT, 24><<<blocks, 768, 0, stream>>>(P, st, iterations);
+    if constexpr (MAXT >= 16)
+        if (T >= 16) return (void)lmSolveKernel<M, DEFECT, VT, 16><<<blocks, 512, 0, stream>>>(P, st, iterations);
     if constexpr (MAXT >= 8)
         if (T >= 8) return (void)lmSolveKernel<M, DEFECT, VT, 8><<<blocks, 256, 0, stream>>>(P, st, iterations);
     if constexpr (MAXT >= 4)

@@ -26,6 +26,7 @@ ABI_SYMBOLS = [
     "b200sqp_initialize_trajectories", "b200sqp_set_params", "b200sqp_get_params", "b200sqp_get_first_controls", "b200sqp_solve",
     "b200sqp_solve_async", "b200sqp_synchronize", "b200sqp_step", "b200sqp_evaluate", "b200sqp_get_statistics", "b200sqp_get_chi2_trace",
     "b200sqp_last_solve_ms", "b200sqp_launch_count", "b200sqp_device_pointers", "b200sqp_set_stream", "b200sqp_set_threads_per_instance",
+    "b200sqp_set_phase_profile", "b200sqp_get_phase_cycles",
 ]
 
 
@@ -244,6 +245,16 @@ class BatchedLevenbergMarquardt:
     def set_threads_per_instance(self, threads):
         """cooperating threads per instance (1, 2, 4, 8; 0 = pick from the batch size)"""
         _check(self._lib.b200sqp_set_threads_per_instance(self._h, C.c_int32(threads)))
+
+    def set_phase_profile(self, enable=True):
+        """measurement aid: per-phase clock64() accounting inside the LM kernel (see phase_cycles)"""
+        _check(self._lib.b200sqp_set_phase_profile(self._h, C.c_int32(1 if enable else 0)))
+
+    def phase_cycles(self):
+        """mean SM cycles per thread block of the last solve: dict(linearize, factor_solve, trial, control)"""
+        out = np.zeros(4)
+        _check(self._lib.b200sqp_get_phase_cycles(self._h, _d(out)))
+        return dict(zip(("linearize", "factor_solve", "trial", "control"), out.tolist()))
 
     def set_stream(self, cuda_stream):
         _check(self._lib.b200sqp_set_stream(self._h, C.c_void_p(cuda_stream)))

@@ -189,6 +189,11 @@ int b200sqp_launch_count(b200sqp_handle h, int64_t* launches);
 int b200sqp_device_pointers(b200sqp_handle h, void** chi2, void** status, void** x0);
 /* tuning knob: cooperating threads per instance in the LM kernel (1, 2, 4, 8; 0 = choose from the batch size) */
 int b200sqp_set_threads_per_instance(b200sqp_handle h, int32_t threads);
+/* measurement aid: when enabled, thread 0 of every thread block of the LM kernel accumulates clock64() per phase; get returns the
+ * mean over thread blocks of the last solve, mean_cycles[4] = {linearise (a3/a4/a13), factor+solve (a14), trial values (a2/a12),
+ * LM control (a1)} in SM clock cycles.  Off by default (the kernel then only tests one pointer). */
+int b200sqp_set_phase_profile(b200sqp_handle h, int32_t enable);
+int b200sqp_get_phase_cycles(b200sqp_handle h, double* mean_cycles /*[4]*/);
 /* make the handle launch on an external stream (e.g. torch's current stream); pass NULL to restore its own */
 int b200sqp_set_stream(b200sqp_handle h, void* cuda_stream);
 

@@ -1,6 +1,8 @@
 """Ad-hoc timing probe (not a test, not the bench): device time of one batched solve for a few batch sizes / thread mappings.
 usage: python tests/quick_timing.py [B ...] [--T 1,2,4,8,0]"""
+import os
 import sys
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np
 from control_box_rst_b200 import problems, solver
 
@@ -33,6 +35,12 @@ for B in Bs:
             lm.synchronize()
             ts.append(lm.last_solve_ms())
         st = lm.statistics()
+        lm.set_phase_profile(True)
+        lm.initialize_trajectories()
+        lm.solve(new_run=True, fetch=False)
+        lm.synchronize()
+        pc = lm.phase_cycles()
+        lm.set_phase_profile(False)
         p = lm.get_params()
         if ref is None:
             ref = p
@@ -41,5 +49,5 @@ for B in Bs:
         print(f"cfg{cfg} B={B} T={T} ms={t:.3f} iters/s={B*10/t*1e3:.3e} "
               f"roofline_frac={B*10/t*1e3*d.algorithmic_bytes_per_iteration/6.45e12:.4f} inner/inst={st['inner_passes'].mean():.2f} "
               f"rejects/inst={st['rejects'].mean():.2f} lin/inst={st['relinearizations'].mean():.2f} "
-              f"maxdiff_vs_first_T={np.abs(p-ref).max():.2e}", flush=True)
+              f"maxdiff_vs_first_T={np.abs(p-ref).max():.2e} phase_kcycles={ {k: round(v/1e3,1) for k,v in pc.items()} }", flush=True)
     lm.clear()
