@@ -38,8 +38,8 @@ UNIT = "iters/s"
 def parse_args():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
-    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--config", type=int, default=1, help="BASELINE.json configs[] index of the OCP (1 = Van der Pol N=50)")
     ap.add_argument("--batch", type=int, default=4096, help="instances per GPU (north_star target batch; weak scaling)")
@@ -57,15 +57,43 @@ def workload_name(cfg, ocp, batch, iterations):
 # clocks during the timed region (B200_PROFILING.md)
 # ---------------------------------------------------------------------------------------------------------------------------
 class ClockSampler:
+    """SM clock and throttle reasons sampled DURING the timed region: NVML in a thread every few ms (the timed region of this
+    bench is tens of ms, too short for `nvidia-smi -lms`), with the profiling recipe's nvidia-smi query as fallback."""
     QUERY = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
-    def __init__(self, gpu_index):
+    def __init__(self, gpu_index, period_s=0.002):
         self.gpu_index = gpu_index
+        self.period_s = period_s
+        self.samples = []   # (sm_mhz, reasons bitmask, power_w)
+        self.smax = None
+        self.thread = None
+        self.stop_flag = threading.Event()
+        self.nvml = None
         self.proc = None
         self.lines = []
 
     def start(self):
+        try:
+            import pynvml
+
+            pynvml.nvmlInit()
+            self.nvml = pynvml
+            # NVML indexes physical devices: honour CUDA_VISIBLE_DEVICES when it is a plain index list
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+            idx = self.gpu_index
+            if vis:
+                try:
+                    idx = int(vis.split(",")[self.gpu_index])
+                except (ValueError, IndexError):
+                    idx = self.gpu_index
+            self.handle = pynvml.nvmlDeviceGetHandleByIndex(idx)
+            self.smax = float(pynvml.nvmlDeviceGetMaxClockInfo(self.handle, pynvml.NVML_CLOCK_SM))
+            self.thread = threading.Thread(target=self._poll, daemon=True)
+            self.thread.start()
+            return
+        except Exception:
+            self.nvml = None
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.QUERY}", "--format=csv,noheader,nounits", "-lms", "100",
                                           "-i", str(self.gpu_index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
@@ -74,11 +102,36 @@ class ClockSampler:
         except Exception:
             self.proc = None
 
+    def _poll(self):
+        n = self.nvml
+        while not self.stop_flag.is_set():
+            try:
+                mhz = float(n.nvmlDeviceGetClockInfo(self.handle, n.NVML_CLOCK_SM))
+                reasons = int(n.nvmlDeviceGetCurrentClocksEventReasons(self.handle)) if hasattr(n, "nvmlDeviceGetCurrentClocksEventReasons") \
+                    else int(n.nvmlDeviceGetCurrentClocksThrottleReasons(self.handle))
+                power = n.nvmlDeviceGetPowerUsage(self.handle) / 1000.0
+                self.samples.append((mhz, reasons, power))
+            except Exception:
+                pass
+            time.sleep(self.period_s)
+
     def _read(self):
         for line in self.proc.stdout:
             self.lines.append(line.strip())
 
     def stop(self):
+        if self.nvml is not None:
+            self.stop_flag.set()
+            self.thread.join(timeout=1)
+            n = self.nvml
+            names = {"hw_slowdown": getattr(n, "nvmlClocksThrottleReasonHwSlowdown", 0x8),
+                     "hw_thermal_slowdown": getattr(n, "nvmlClocksThrottleReasonHwThermalSlowdown", 0x40),
+                     "sw_thermal_slowdown": getattr(n, "nvmlClocksThrottleReasonSwThermalSlowdown", 0x20),
+                     "sw_power_cap": getattr(n, "nvmlClocksThrottleReasonSwPowerCap", 0x4)}
+            reasons = sorted(k for k, bit in names.items() if any(r & bit for _, r, _ in self.samples))
+            sm = [m for m, _, _ in self.samples]
+            return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": self.smax, "reasons": reasons, "samples": len(sm),
+                    "power_w_max": max((p for _, _, p in self.samples), default=None), "source": "nvml, sampled during the timed region"}
         if not self.proc:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         self.proc.terminate()
@@ -99,7 +152,8 @@ class ClockSampler:
             for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
                 if val.lower().startswith("active"):
                     reasons.add(name)
-        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": smax, "reasons": sorted(reasons), "samples": len(sm)}
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": smax, "reasons": sorted(reasons), "samples": len(sm),
+                "source": "nvidia-smi -lms 100"}
 
 
 # ---------------------------------------------------------------------------------------------------------------------------
@@ -275,6 +329,16 @@ def main_b200(args):
         else:
             peak, peak_src = 6650.0, "B200_PROFILING.md fallback"
         alg_bytes = lm.dims.algorithmic_bytes_per_iteration * B * iterations  # per launch of the LM kernel
+        # DRAM traffic of one launch from the committed `ncu --set full` capture of the same workload (profiles/traffic.json)
+        traffic, traffic_src = None, None
+        try:
+            t_all = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
+            key = f"{workload_name(args.config, ocp, B, iterations).split('_per_gpu')[0]}"
+            if key in t_all:
+                traffic = t_all[key]["dram_bytes_read"] + t_all[key]["dram_bytes_write"]
+                traffic_src = t_all[key]["source"]
+        except (OSError, ValueError, KeyError):
+            pass
         achieved = alg_bytes / (kernel_ms / args.steps * 1e-3) / 1e9
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": n_gpus, "steps": args.steps, "warmup": max(args.warmup, 3),
@@ -287,7 +351,7 @@ def main_b200(args):
             "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "ms_per_step": e2e_ms / args.steps},
             "gpu_launches": int(launches),
-            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "traffic_source": traffic_src,
                          "kernel": "lmSolve", "kernel_ms": kernel_ms / args.steps, "algorithmic_bytes_per_launch": alg_bytes,
                          "peak_source": peak_src},
             "lm": {"inner_passes_per_instance": float(stats["inner_passes"].mean()), "rejects_per_instance": float(stats["rejects"].mean()),

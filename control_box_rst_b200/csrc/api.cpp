@@ -39,8 +39,12 @@ namespace b200sqp {
 
 const KernelSet* findKernels(int dynamics, int defect, int vt)
 {
+#ifdef B200SQP_DEV_VDP_CN_ONLY  // development build (make dev): only the benchmark kernels, seconds instead of minutes to compile
+    const KernelSet* (*tables[])(int*) = {kernelTableVdpCn};
+#else
     const KernelSet* (*tables[])(int*) = {kernelTableVdpCn,       kernelTableVdpFd,    kernelTableVdpMs,   kernelTableOscillators,
                                           kernelTableCartPole,    kernelTableUnicycle, kernelTableQuadrotor};
+#endif
     for (auto t : tables)
     {
         int count            = 0;
@@ -286,6 +290,9 @@ int b200sqp_create(const b200sqp_ocp* ocp, int32_t batch, int32_t device, b200sq
     A(&st.dl, K * nb * S);
     A(&st.L, K * nd * S);
     A(&st.W, K * ne * S);
+    st.red_blocks = ks->max_threads > 1 ? ks->max_threads - 1 : 1;
+    A(&st.Y, ks->max_threads > 1 ? K * ne * S : 1);
+    A(&st.red, ks->max_threads > 1 ? (size_t)st.red_blocks * (2 * nd + 2 * ne + 2 * nb) * S : 1);
     A(&st.chi2, S);
     A(&st.mu, S);
     A(&st.rho, S);
@@ -580,7 +587,7 @@ int b200sqp_device_pointers(b200sqp_handle h, void** chi2, void** status, void**
 
 int b200sqp_set_threads_per_instance(b200sqp_handle h, int32_t threads)
 {
-    if (!h || threads < 0 || threads > 32) return fail(B200SQP_ERR_INVALID, "threads per instance must be 0 (auto), 1, 2, 4 or 8");
+    if (!h || threads < 0 || threads > 8) return fail(B200SQP_ERR_INVALID, "threads per instance must be 0 (auto), 1, 2, 4 or 8");
     h->threads_per_instance = threads;
     return B200SQP_OK;
 }

@@ -6,7 +6,7 @@ namespace b200sqp {
 const KernelSet* kernelTableVdpCn(int* count)
 {
     static const KernelSet table[] = {
-        B200SQP_KERNEL_ENTRY(VanDerPol, DEFECT_CRANK_NICOLSON, 0, 24),
+        B200SQP_KERNEL_ENTRY(VanDerPol, DEFECT_CRANK_NICOLSON, 0, 8),
     };
     *count = (int)(sizeof(table) / sizeof(table[0]));
     return table;

@@ -11,6 +11,7 @@ struct DeviceState;
 struct KernelSet
 {
     int dynamics, defect, vt, nx, nu;
+    int max_threads;  // widest cooperating-thread variant compiled for this combination
     void (*solve)(const DeviceOcp&, const DeviceState&, int iterations, int threads_per_instance /*0 = auto*/, cudaStream_t);
     void (*evaluate)(const DeviceOcp&, const DeviceState&, double* values, double* jac, const int* value_rows, const int* jac_pos, int v_count,
                      int j_count, cudaStream_t);

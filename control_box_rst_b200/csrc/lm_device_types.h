@@ -41,6 +41,9 @@ struct DeviceState
     double* dl;       // [K*NB][S]  step
     double* L;        // [K*ND][S]  factor, diagonal blocks (reciprocal diagonal stored)
     double* W;        // [K*NB*NX][S] factor, sub-diagonal blocks
+    double* Y;        // [K*NB*NX][S] factor, spike blocks of the partitioned factorisation (coupling to the separator above a chunk)
+    double* red;      // [red_blocks*(2 ND + 2 NB*NX + 2 NB)][S] reduced separator system of the partitioned factorisation: D,E,g,L,W,dl
+    int red_blocks;   // separators per instance = widest cooperating-thread variant - 1 (>= 1)
     // per instance results / LM state, [S]
     double* chi2;
     double* mu;

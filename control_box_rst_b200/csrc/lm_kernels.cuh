@@ -24,6 +24,15 @@ namespace b200sqp {
 // is whatever computeValues produced last, i.e. possibly a rejected trial point (:216); the last outer pass never re-linearises
 // (:178); `v` is an unsigned int (:108); the `stop || ||g||inf <= eps1` update after a re-linearisation (:193) is dead code
 // because rho > 0 leaves the inner loop and :216 overwrites `stop`, so ||g||inf is only evaluated for the initial test (:115).
+struct TrueTag
+{
+    static constexpr bool value = true;
+};
+struct FalseTag
+{
+    static constexpr bool value = false;
+};
+
 template <class M, int DEFECT, int VT, int T>
 __global__ void __launch_bounds__(32 * T) lmSolveKernel(const __grid_constant__ DeviceOcp P, const __grid_constant__ DeviceState st, int iterations)
 {
@@ -44,10 +53,10 @@ __global__ void __launch_bounds__(32 * T) lmSolveKernel(const __grid_constant__ 
     __shared__ double s_red[3][T][32];
     __shared__ double s_muacc[32], s_mu[32];
     __shared__ double s_xc[TWISTED ? NXX + 2 * NX : 1][32];  // chain B -> A: Schur contribution; chain A -> B: x-part of delta_m
-    __shared__ double s_dn[2][2][32];                        // partial ||delta||^2 and delta^T(mu delta + g) of the two chains
+    __shared__ double s_dn[2][T][32];                        // partial ||delta||^2 and delta^T(mu delta + g) per cooperating thread
     __shared__ int s_cur[32], s_flags[32];
     enum { F_ACTIVE = 1, F_LIN = 2 };
-    const int m_mid = TWISTED ? K / 2 : K - 1;  // middle block of the twisted elimination
+    const bool use_part = TWISTED && K >= 2 * T;  // partitioned factorisation: every chunk has a separator and >= 1 interior block
 
     const Weights w{st.w_eq, st.w_ineq, st.w_b};
     // tiled arrays: this block's tile, this thread's lane (lm_device.cuh TILE)
@@ -61,6 +70,14 @@ __global__ void __launch_bounds__(32 * T) lmSolveKernel(const __grid_constant__ 
     double* dl = st.dl + tile * ((size_t)K * NB * TILE) + g;
     double* L  = st.L + tile * ((size_t)K * ND * TILE) + g;
     double* W  = st.W + tile * ((size_t)K * NE_ * TILE) + g;
+    double* Yf = st.Y + tile * ((size_t)K * NE_ * TILE) + g;  // spike factors of the partitioned factorisation
+    // reduced (separator) system of the partitioned factorisation: st.red_blocks (= max cooperating threads - 1) blocks per instance
+    double* Dr  = st.red + tile * ((size_t)st.red_blocks * (2 * ND + 2 * NE_ + 2 * NB) * TILE) + g;
+    double* Er  = Dr + (size_t)st.red_blocks * ND * TILE;
+    double* gr  = Er + (size_t)st.red_blocks * NE_ * TILE;
+    double* Lr  = gr + (size_t)st.red_blocks * NB * TILE;
+    double* Wr  = Lr + (size_t)st.red_blocks * ND * TILE;
+    double* dlr = Wr + (size_t)st.red_blocks * NE_ * TILE;
     const size_t zoff = tile * ((size_t)K * NB * TILE) + g;
 
     constexpr double eps1 = 1e-5, eps2 = 1e-5, eps3 = 1e-5, eps4 = 0;
@@ -154,23 +171,26 @@ __global__ void __launch_bounds__(32 * T) lmSolveKernel(const __grid_constant__ 
 
     while (true)
     {
-        // ---- F: (H + sum(mu) I) delta = g.  Chain A = thread p == 0, chain B = thread p == 1 (twisted elimination).
+        // ---- F: (H + sum(mu) I) delta = g.
+        //      K >= 2T: partitioned -- every thread eliminates the interior of its chunk, the T-1 separators form a reduced
+        //      block-tridiagonal system for the twisted chains, every thread back-substitutes (BlockSolver::part*).
+        //      otherwise: twisted chains over the whole horizon (chain A = thread 0, chain B = thread 1), or one chain for T = 1.
         {
             const bool inst_active = valid && (s_flags[g] & F_ACTIVE);
             const double mua = s_muacc[g], mucur = s_mu[g];
-            double Lp[ND], yp[NX], carry[NX], dx[NX];
             double pdn2 = 0.0, pdq = 0.0;
-            if (p == 0 && inst_active)
-            {
-                BS::chainAEliminate(P, D, E, gg, L, W, dl, mua, 0, TWISTED ? m_mid : K, Lp, yp, nullptr, nullptr);
-                ++n_factor;
-            }
-            if (TWISTED)
-            {
+            if (p == 0 && inst_active) ++n_factor;
+            // twisted solve of a block-tridiagonal system with Kb blocks; ACC: account ||delta||^2 and delta^T(mu delta + g)
+            auto twistedSolve = [&](auto acc_tag, const double* Dq, const double* Eq, const double* gq, double* Lq, double* Wq, double* dlq, int Kb,
+                                    double mu_add) {
+                constexpr bool ACC = decltype(acc_tag)::value;
+                const int mid      = Kb / 2;
+                double Lp[ND], yp[NX], carry[NX], dx[NX];
+                if (p == 0 && inst_active) BS::chainAEliminate(P, Dq, Eq, gq, Lq, Wq, dlq, mu_add, 0, mid, Lp, yp, nullptr, nullptr);
                 if (p == 1 && inst_active)
                 {
                     double cxx[NXX], cgx[NX];
-                    BS::chainBEliminate(P, D, E, gg, L, W, dl, mua, m_mid + 1, cxx, cgx);
+                    BS::chainBEliminate(P, Dq, Eq, gq, Lq, Wq, dlq, mu_add, mid + 1, Kb, cxx, cgx);
 #pragma unroll
                     for (int q = 0; q < NXX; ++q) s_xc[q][g] = cxx[q];
 #pragma unroll
@@ -184,38 +204,56 @@ __global__ void __launch_bounds__(32 * T) lmSolveKernel(const __grid_constant__ 
                     for (int q = 0; q < NXX; ++q) cxx[q] = s_xc[q][g];
 #pragma unroll
                     for (int q = 0; q < NX; ++q) cgx[q] = s_xc[NXX + q][g];
-                    BS::chainAEliminate(P, D, E, gg, L, W, dl, mua, m_mid, m_mid + 1, Lp, yp, cxx, cgx);
+                    BS::chainAEliminate(P, Dq, Eq, gq, Lq, Wq, dlq, mu_add, mid, mid + 1, Lp, yp, cxx, cgx);
 #pragma unroll
                     for (int q = 0; q < NX; ++q) carry[q] = 0.0;
-                    BS::chainABacksub(P, gg, L, W, dl, mucur, m_mid, m_mid, carry, dx, pdn2, pdq);
+                    BS::template chainABacksub<ACC>(P, gq, Lq, Wq, dlq, mucur, mid, mid, carry, dx, pdn2, pdq);
 #pragma unroll
                     for (int q = 0; q < NX; ++q) s_xc[NXX + NX + q][g] = dx[q];
                 }
                 __syncthreads();
-                if (p == 0 && inst_active) BS::chainABacksub(P, gg, L, W, dl, mucur, m_mid - 1, 0, carry, nullptr, pdn2, pdq);
+                if (p == 0 && inst_active) BS::template chainABacksub<ACC>(P, gq, Lq, Wq, dlq, mucur, mid - 1, 0, carry, nullptr, pdn2, pdq);
                 if (p == 1 && inst_active)
                 {
 #pragma unroll
                     for (int q = 0; q < NX; ++q) dx[q] = s_xc[NXX + NX + q][g];
-                    BS::chainBSubst(P, gg, L, W, dl, mucur, m_mid + 1, dx, pdn2, pdq);
+                    BS::template chainBSubst<ACC>(P, gq, Lq, Wq, dlq, mucur, mid + 1, Kb, dx, pdn2, pdq);
                 }
+            };
+            if constexpr (TWISTED)
+            {
+                if (use_part)
+                {
+                    const bool has_up = p > 0, has_low = p < T - 1;
+                    double cxx[NXX], cgx[NX];
+                    if (inst_active) BS::partEliminate(D, E, gg, L, W, Yf, dl, Dr, Er, gr, mua, ka, kb, has_up, has_low, p, cxx, cgx);
+                    __syncthreads();
+                    if (inst_active && has_up) BS::partAddToUpper(Dr, gr, p - 1, cxx, cgx);
+                    __syncthreads();
+                    twistedSolve(FalseTag{}, Dr, Er, gr, Lr, Wr, dlr, T - 1, 0.0);
+                    __syncthreads();
+                    if (inst_active) BS::partBacksub(gg, L, W, Yf, dl, dlr, mucur, ka, kb, has_up, has_low, p, pdn2, pdq);
+                }
+                else
+                    twistedSolve(TrueTag{}, D, E, gg, L, W, dl, K, mua);
             }
             else if (p == 0 && inst_active)
             {
+                double Lp[ND], yp[NX], carry[NX];
+                BS::chainAEliminate(P, D, E, gg, L, W, dl, mua, 0, K, Lp, yp, nullptr, nullptr);
 #pragma unroll
                 for (int q = 0; q < NX; ++q) carry[q] = 0.0;
                 BS::chainABacksub(P, gg, L, W, dl, mucur, K - 1, 0, carry, nullptr, pdn2, pdq);
             }
-            if (p < 2)
-            {
-                s_dn[0][p][g] = pdn2;
-                s_dn[1][p][g] = pdq;
-            }
+            s_dn[0][p][g] = pdn2;
+            s_dn[1][p][g] = pdq;
         }
         __syncthreads();
         tick(1);
         // ---- T: trial point and its chi2, all T threads
-        const double dn2_tot = s_dn[0][0][g] + (TWISTED ? s_dn[0][1][g] : 0.0);
+        double dn2_tot = 0.0;
+#pragma unroll
+        for (int q = 0; q < T; ++q) dn2_tot += s_dn[0][q][g];
         const bool step_small = sqrt(dn2_tot) <= eps2;
         {
             const bool do_trial = valid && (s_flags[g] & F_ACTIVE) && !step_small;
@@ -232,7 +270,9 @@ __global__ void __launch_bounds__(32 * T) lmSolveKernel(const __grid_constant__ 
             int flags = 0;
             if (active)
             {
-                dq = s_dn[1][0][g] + (TWISTED ? s_dn[1][1][g] : 0.0);
+                dq = 0.0;
+#pragma unroll
+                for (int q = 0; q < T; ++q) dq += s_dn[1][q][g];
                 if (step_small)
                 {
                     stop = true;
@@ -345,10 +385,6 @@ void launchSolve(const DeviceOcp& P, const DeviceState& st, int iterations, int 
         while (T < 8 && P.K / (2 * T) >= 3) T *= 2;
     }
     if (T > MAXT) T = MAXT;
-    if constexpr (MAXT >= 24)
-        if (T >= 24) return (void)lmSolveKernel<M, DEFECT, VT, 24><<<blocks, 768, 0, stream>>>(P, st, iterations);
-    if constexpr (MAXT >= 16)
-        if (T >= 16) return (void)lmSolveKernel<M, DEFECT, VT, 16><<<blocks, 512, 0, stream>>>(P, st, iterations);
     if constexpr (MAXT >= 8)
         if (T >= 8) return (void)lmSolveKernel<M, DEFECT, VT, 8><<<blocks, 256, 0, stream>>>(P, st, iterations);
     if constexpr (MAXT >= 4)
@@ -367,6 +403,6 @@ void launchEvaluate(const DeviceOcp& P, const DeviceState& st, double* values, d
 }
 
 #define B200SQP_KERNEL_ENTRY(MODEL, DEFECT, VT, MAXT) \
-    KernelSet { MODEL::ID, DEFECT, VT, MODEL::NX, MODEL::NU, &launchSolve<MODEL, DEFECT, VT, MAXT>, &launchEvaluate<MODEL, DEFECT, VT> }
+    KernelSet { MODEL::ID, DEFECT, VT, MODEL::NX, MODEL::NU, MAXT, &launchSolve<MODEL, DEFECT, VT, MAXT>, &launchEvaluate<MODEL, DEFECT, VT> }
 
 }  // namespace b200sqp

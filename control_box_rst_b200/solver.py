@@ -14,7 +14,7 @@ import numpy as np
 from . import _abi as abi
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libb200sqp.so")
+LIB_PATH = os.environ.get("B200SQP_LIB") or os.path.join(_HERE, "libb200sqp.so")  # B200SQP_LIB: development builds only
 
 _dp = C.POINTER(C.c_double)
 _ip = C.POINTER(C.c_int32)
