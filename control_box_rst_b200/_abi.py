@@ -49,6 +49,11 @@ COST_NONE = 0
 COST_QUADRATIC_LSQ = 1
 COST_MINIMUM_TIME_LSQ = 2
 
+# b200sqp_final_constraint
+FINAL_CONSTRAINT_NONE = 0
+FINAL_CONSTRAINT_EQUALITY = 1
+FINAL_CONSTRAINT_BALL = 2
+
 # b200sqp_status == corbo::SolverStatus
 STATUS_CONVERGED = 0
 STATUS_EARLY_TERMINATED = 1
@@ -89,6 +94,10 @@ class Ocp(C.Structure):
         ("x_ub", C.c_double * MAX_NX),
         ("u_lb", C.c_double * MAX_NU),
         ("u_ub", C.c_double * MAX_NU),
+        ("final_constraint", C.c_int32),
+        ("term_xref", C.c_double * MAX_NX),
+        ("term_s_diag", C.c_double * MAX_NX),
+        ("term_gamma", C.c_double),
     ]
 
 

@@ -3,6 +3,7 @@
 
 #include <corbo-core/console.h>
 #include <corbo-numerics/explicit_integrators.h>
+#include <corbo-optimal-control/functions/final_state_constraints.h>
 #include <corbo-optimal-control/functions/final_state_cost.h>
 #include <corbo-optimal-control/functions/minimum_time.h>
 #include <corbo-optimal-control/functions/quadratic_cost.h>
@@ -92,12 +93,38 @@ bool SolverB200Lm::describe(OptimizationProblemInterface& problem, b200sqp_ocp& 
         return false;
     }
     OptimizationEdgeSet* edges = hg->getGraph().getEdgeSetRaw();
-    if (!edges->getInequalityEdgesRef().empty() || !edges->getMixedEdgesRef().empty() || !edges->getObjectiveEdgesRef().empty())
+    if (!edges->getMixedEdgesRef().empty() || !edges->getObjectiveEdgesRef().empty())
     {
-        _error = "inequality / mixed / non-lsq objective edges are outside the device registry";
+        _error = "mixed / non-lsq objective edges are outside the device registry";
         return false;
     }
-    std::vector<BaseEdge::Ptr>& eq = edges->getEqualityEdgesRef();
+    // final-stage constraint (functions/final_state_constraints.h): one extra equality edge (TerminalEqualityConstraint) or the
+    // only inequality edge (TerminalBall, diagonal S), a unary edge on xf created after all interval edges
+    // (finite_differences_grid.cpp:131-144)
+    auto* term_eq   = dynamic_cast<TerminalEqualityConstraint*>(_final_constraint.get());
+    auto* term_ball = dynamic_cast<TerminalBall*>(_final_constraint.get());
+    if (_final_constraint && !term_eq && !term_ball)
+    {
+        _error = "final-stage constraint type is not in the device registry";
+        return false;
+    }
+    std::vector<BaseEdge::Ptr> eq = edges->getEqualityEdgesRef();  // copy of the pointer list: the final-stage edge is split off below
+    std::vector<BaseEdge::Ptr>& ineq = edges->getInequalityEdgesRef();
+    bool has_term_eq = false, has_term_ball = false;
+    if (term_eq && !eq.empty() && eq.back()->getNumVertices() == 1)
+    {
+        has_term_eq = true;
+        eq.pop_back();
+    }
+    if (!ineq.empty())
+    {
+        if (!(term_ball && ineq.size() == 1 && ineq.front()->getNumVertices() == 1 && ineq.front()->getDimension() == 1))
+        {
+            _error = "inequality edges other than one TerminalBall edge are outside the device registry";
+            return false;
+        }
+        has_term_ball = true;
+    }
     if (eq.empty() || !_dynamics)
     {
         _error = "no dynamics edges, or setSystemDynamics() was not called";
@@ -291,6 +318,29 @@ bool SolverB200Lm::describe(OptimizationProblemInterface& problem, b200sqp_ocp& 
         d.final_cost = 1;
         for (int i = 0; i < d.nx; ++i) d.qf_diag[i] = qf->getWeightQf()(i, i);
     }
+    d.final_constraint = B200SQP_FINAL_CONSTRAINT_NONE;
+    if (has_term_eq)
+    {
+        if (term_eq->getXRef().size() != d.nx)
+        {
+            _error = "TerminalEqualityConstraint: xref dimension does not match the state dimension";
+            return false;
+        }
+        d.final_constraint = B200SQP_FINAL_CONSTRAINT_EQUALITY;
+        for (int i = 0; i < d.nx; ++i) d.term_xref[i] = term_eq->getXRef()[i];
+    }
+    else if (has_term_ball)
+    {
+        const Eigen::MatrixXd& S = term_ball->getWeightS();
+        if (S.rows() != d.nx || !S.isDiagonal(1e-10))  // TerminalBall::setWeightS switches to its diagonal mode by the same test
+        {
+            _error = "TerminalBall: only a diagonal weight S is in the device registry";
+            return false;
+        }
+        d.final_constraint = B200SQP_FINAL_CONSTRAINT_BALL;
+        for (int i = 0; i < d.nx; ++i) d.term_s_diag[i] = S(i, i);
+        d.term_gamma = term_ball->getGamma();
+    }
     return true;
 }
 
@@ -344,7 +394,9 @@ bool SolverB200Lm::selfCheck(OptimizationProblemInterface& problem)
     Eigen::VectorXd host(m);
     if (_dims.m_lsq > 0) problem.computeValuesLsqObjective(host.segment(0, _dims.m_lsq));
     if (_dims.m_eq > 0) problem.computeValuesEquality(host.segment(_dims.m_lsq, _dims.m_eq));
-    if (_dims.m_bounds > 0) problem.computeDistanceFiniteCombinedBounds(host.segment(_dims.m_lsq + _dims.m_eq, _dims.m_bounds));
+    if (_dims.m_ineq > 0) problem.computeValuesActiveInequality(host.segment(_dims.m_lsq + _dims.m_eq, _dims.m_ineq), 1.0);
+    if (_dims.m_bounds > 0)
+        problem.computeDistanceFiniteCombinedBounds(host.segment(_dims.m_lsq + _dims.m_eq + _dims.m_ineq, _dims.m_bounds));
     double worst = 0;
     for (int i = 0; i < m; ++i) worst = std::max(worst, std::abs(host[i] - dev[i]) / std::max(1.0, std::abs(host[i])));
     if (!(worst <= 1e-9))

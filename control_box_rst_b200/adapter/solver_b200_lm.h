@@ -9,7 +9,7 @@
 // Discovery gap: a solver only receives OptimizationProblemInterface&.  The hypergraph walk yields the grid
 // kind and size, dimensions, bounds, fixed masks, x0 and the parameter vector; the functors behind the edges are private in the
 // reference, so the objects the user handed to the OCP are handed to this solver as well (setSystemDynamics, setCollocation /
-// setIntegrator, setStageCost, setFinalStageCost, setStateReference).  Anything outside the closed registry makes solve() return
+// setIntegrator, setStageCost, setFinalStageCost, setFinalStageConstraint, setStateReference).  Anything outside the closed registry makes solve() return
 // SolverStatus::Error -- there is no CPU fallback.  After every structure upload the device residual vector is compared with the
 // reference's own computeValues on the host to catch a mis-extraction.
 #ifndef CONTROL_BOX_RST_B200_ADAPTER_SOLVER_B200_LM_H_
@@ -56,6 +56,7 @@ class SolverB200Lm : public NlpSolverInterface
     void setIntegrator(NumericalIntegratorExplicitInterface::Ptr integrator) { _integrator = integrator; }
     void setStageCost(StageCost::Ptr stage_cost) { _stage_cost = stage_cost; }
     void setFinalStageCost(FinalStageCost::Ptr final_cost) { _final_cost = final_cost; }
+    void setFinalStageConstraint(FinalStageConstraint::Ptr final_constraint) { _final_constraint = final_constraint; }
     void setStateReference(ReferenceTrajectoryInterface::Ptr xref) { _xref = xref; }
     void setDevice(int device) { _device = device; }
 
@@ -87,6 +88,7 @@ class SolverB200Lm : public NlpSolverInterface
     NumericalIntegratorExplicitInterface::Ptr _integrator;
     StageCost::Ptr _stage_cost;
     FinalStageCost::Ptr _final_cost;
+    FinalStageConstraint::Ptr _final_constraint;
     ReferenceTrajectoryInterface::Ptr _xref;
 };
 

@@ -122,6 +122,13 @@ void fillDeviceOcp(const Structure& s, int B, int S, DeviceOcp& P)
         P.u_bounded[i] = (o.u_lb[i] > -kCorboInf || o.u_ub[i] < kCorboInf) ? 1 : 0;
         P.r_sqrt[i]    = std::sqrt(o.r_diag[i]);
     }
+    P.final_constraint = s.xfFullyFixed() ? 0 : o.final_constraint;
+    for (int i = 0; i < s.nx; ++i)
+    {
+        P.term_xref[i] = o.term_xref[i];
+        P.term_s[i]    = o.term_s_diag[i];
+    }
+    P.term_gamma = o.term_gamma;
     P.dt_bounded = (s.vt && (o.dt_lb > -kCorboInf || o.dt_ub < kCorboInf)) ? 1 : 0;
     P.dt_ref     = o.dt_ref;
     P.dt_lb      = o.dt_lb;
@@ -225,6 +232,18 @@ int b200sqp_edge_indices(const b200sqp_ocp* ocp, int32_t* state_cost_idx, int32_
     if (dt_cost_idx) std::memcpy(dt_cost_idx, s.dt_cost_idx.data(), sizeof(int32_t) * s.dt_cost_idx.size());
     if (dynamics_idx) std::memcpy(dynamics_idx, s.dynamics_idx.data(), sizeof(int32_t) * s.dynamics_idx.size());
     if (final_cost_idx) *final_cost_idx = s.final_cost_idx;
+    return B200SQP_OK;
+}
+
+int b200sqp_final_constraint_indices(const b200sqp_ocp* ocp, int32_t* eq_idx, int32_t* ineq_idx)
+{
+    if (!ocp) return fail(B200SQP_ERR_INVALID, "null argument");
+    Structure s;
+    std::string err;
+    int rc = buildStructure(*ocp, s, err);
+    if (rc != B200SQP_OK) return fail(rc, err);
+    if (eq_idx) *eq_idx = s.final_eq_idx;
+    if (ineq_idx) *ineq_idx = s.final_ineq_idx;
     return B200SQP_OK;
 }
 

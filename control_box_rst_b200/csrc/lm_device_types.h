@@ -18,6 +18,8 @@ struct DeviceOcp
     int stage_cost, final_cost, tcost_every_interval;
     int xf_fixed[B200SQP_MAX_NX];
     int x_bounded[B200SQP_MAX_NX], u_bounded[B200SQP_MAX_NU], dt_bounded;
+    int final_constraint;  // b200sqp_final_constraint (0 if xf is fully fixed: the reference then creates no final-stage edge)
+    double term_xref[B200SQP_MAX_NX], term_s[B200SQP_MAX_NX], term_gamma;
     DynParams dyn;
     double dt_ref, dt_lb, dt_ub, tcost_w;
     double q_sqrt[B200SQP_MAX_NX], r_sqrt[B200SQP_MAX_NU], qf_sqrt[B200SQP_MAX_NX];

@@ -98,6 +98,11 @@ int buildStructure(const b200sqp_ocp& ocp, Structure& s, std::string& err)
         err = "unknown stage cost id";
         return B200SQP_ERR_UNSUPPORTED;
     }
+    if (ocp.final_constraint < B200SQP_FINAL_CONSTRAINT_NONE || ocp.final_constraint > B200SQP_FINAL_CONSTRAINT_BALL)
+    {
+        err = "unknown final-stage constraint id";
+        return B200SQP_ERR_UNSUPPORTED;
+    }
     if (ocp.stage_cost == B200SQP_COST_QUADRATIC_LSQ && !ocp.zero_u_ref)
     {
         // quadratic_cost.cpp:161,163: the lsq branch with a non-zero control reference returns a scalar into a vector -> not a
@@ -206,6 +211,19 @@ int buildStructure(const b200sqp_ocp& ocp, Structure& s, std::string& err)
         s.final_cost_idx = lsq;
         lsq += nx;
     }
+    // final-stage constraint edge on xf, created after all interval edges and only if xf is not fully fixed
+    // (finite_differences_grid.cpp:131-144; same in the non-uniform and shooting grids)
+    int ineq = 0;
+    if (xf_free > 0 && ocp.final_constraint == B200SQP_FINAL_CONSTRAINT_EQUALITY)
+    {
+        s.final_eq_idx = eq;
+        eq += nx;  // TerminalEqualityConstraint::getNonIntegralStateTermDimension = xref.size()
+    }
+    else if (xf_free > 0 && ocp.final_constraint == B200SQP_FINAL_CONSTRAINT_BALL)
+    {
+        s.final_ineq_idx = ineq;
+        ineq += 1;
+    }
 
     // ---- bounds rows: active vertices in order, unfixed components with a finite bound -----------------------------------------
     s.bound_row.assign(n, -1);
@@ -228,7 +246,7 @@ int buildStructure(const b200sqp_ocp& ocp, Structure& s, std::string& err)
     if (xf_free > 0) boundsOf(s.x_idx[K], nx, ocp.x_lb, ocp.x_ub, ocp.xf_fixed);
 
     // ---- combined Jacobian pattern -------------------------------------------------------------------------------------------
-    const int eq_start = lsq, ineq_start = lsq + eq, b_start = ineq_start;
+    const int eq_start = lsq, ineq_start = lsq + eq, b_start = ineq_start + ineq;
     std::vector<std::pair<int, int>> entries;  // (col, row)
     auto block = [&](int row0, int rows, int col0, int cols) {
         if (col0 < 0) return;
@@ -248,6 +266,8 @@ int buildStructure(const b200sqp_ocp& ocp, Structure& s, std::string& err)
         block(row0, nx, s.dt_idx[k], 1);
     }
     if (s.final_cost_idx >= 0) block(s.final_cost_idx, nx, s.x_idx[K], xf_free);
+    if (s.final_eq_idx >= 0) block(eq_start + s.final_eq_idx, nx, s.x_idx[K], xf_free);
+    if (s.final_ineq_idx >= 0) block(ineq_start + s.final_ineq_idx, 1, s.x_idx[K], xf_free);
     for (int c = 0; c < n; ++c)
         if (s.bound_row[c] >= 0) entries.push_back({c, b_start + s.bound_row[c]});
     std::sort(entries.begin(), entries.end());
@@ -261,7 +281,7 @@ int buildStructure(const b200sqp_ocp& ocp, Structure& s, std::string& err)
     for (int c = 0; c < n; ++c) s.col_ptr[c + 1] += s.col_ptr[c];
 
     // structural nnz of triu(J^T J): two columns couple iff they share a row
-    const int m = lsq + eq + mb;
+    const int m = lsq + eq + ineq + mb;
     int nnzH = 0;
     {
         std::vector<std::vector<int>> rows(m);
@@ -281,7 +301,7 @@ int buildStructure(const b200sqp_ocp& ocp, Structure& s, std::string& err)
     d.n_params          = n;
     d.m_lsq             = lsq;
     d.m_eq              = eq;
-    d.m_ineq            = 0;
+    d.m_ineq            = ineq;
     d.m_bounds          = mb;
     d.nnz_jacobian      = (int32_t)entries.size();
     d.nnz_hessian_upper = nnzH;
@@ -362,6 +382,20 @@ int buildStructure(const b200sqp_ocp& ocp, Structure& s, std::string& err)
         for (int c = 0; c < nu; ++c)
             for (int r = 0; r < nx; ++r) jp[L.j_Bu() + c * nx + r] = at(ucol[c], erow + r);
         for (int r = 0; r < nx; ++r) jp[L.j_Bt() + r] = at(tcol, erow + r);
+        if (k == K - 1)
+        {
+            if (s.final_eq_idx >= 0)
+            {
+                for (int r = 0; r < nx; ++r) vr[L.v_teq() + r] = eq_start + s.final_eq_idx + r;
+                for (int c = 0; c < nx; ++c)
+                    for (int r = 0; r < nx; ++r) jp[L.j_teq() + c * nx + r] = at(ncol[c], eq_start + s.final_eq_idx + r);
+            }
+            if (s.final_ineq_idx >= 0)
+            {
+                vr[L.v_tin()] = ineq_start + s.final_ineq_idx;
+                for (int c = 0; c < nx; ++c) jp[L.j_tin() + c] = at(ncol[c], ineq_start + s.final_ineq_idx);
+            }
+        }
     }
     return B200SQP_OK;
 }

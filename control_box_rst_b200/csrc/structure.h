@@ -41,6 +41,7 @@ struct Structure
     std::vector<int32_t> dt_cost_idx;                          // [2K]
     std::vector<int32_t> dynamics_idx;                         // [K] equality row offsets
     int32_t final_cost_idx = -1;
+    int32_t final_eq_idx = -1, final_ineq_idx = -1;            // final-stage constraint edge: row offset inside its category
     std::vector<int32_t> bound_row;                            // [n] row offset inside the bounds block or -1
     std::vector<int32_t> col_ptr, row_idx;                     // CSC pattern of the combined Jacobian
 
@@ -71,7 +72,7 @@ struct EvalLayout
 {
     int nx, nu, vt;
     // values rows per interval: [x0 cost nx | control cost nu | dt cost 2 | cost on x_{k+1} nx | defect nx | bounds u nu | bound dt 1 |
-    //                            bounds x_{k+1} nx]
+    //                            bounds x_{k+1} nx | final-stage equality nx | final-stage inequality 1]
     int v_x0c() const { return 0; }
     int v_uc() const { return nx; }
     int v_tc() const { return nx + nu; }
@@ -80,9 +81,11 @@ struct EvalLayout
     int v_ub() const { return 3 * nx + nu + 2; }
     int v_tb() const { return 3 * nx + 2 * nu + 2; }
     int v_xb() const { return 3 * nx + 2 * nu + 3; }
-    int v_count() const { return 4 * nx + 2 * nu + 3; }
+    int v_teq() const { return 4 * nx + 2 * nu + 3; }  // final-stage equality rows (last interval only)
+    int v_tin() const { return 5 * nx + 2 * nu + 3; }  // final-stage inequality row
+    int v_count() const { return 5 * nx + 2 * nu + 4; }
     // Jacobian positions per interval: [uc diag nu | tc 2 | xs diag nx | A nx*nx (col-major) | Bu nx*nu | Bt nx | C nx*nx |
-    //                                   bounds u nu | bound dt 1 | bounds x_{k+1} nx]
+    //                                   bounds u nu | bound dt 1 | bounds x_{k+1} nx | final-stage equality nx*nx | final-stage inequality nx]
     int j_uc() const { return 0; }
     int j_tc() const { return nu; }
     int j_xs() const { return nu + 2; }
@@ -93,7 +96,9 @@ struct EvalLayout
     int j_ub() const { return j_C() + nx * nx; }
     int j_tb() const { return j_ub() + nu; }
     int j_xb() const { return j_tb() + 1; }
-    int j_count() const { return j_xb() + nx; }
+    int j_teq() const { return j_xb() + nx; }        // nx*nx (col-major), final-stage equality block
+    int j_tin() const { return j_teq() + nx * nx; }  // nx, final-stage inequality row
+    int j_count() const { return j_tin() + nx; }
 };
 
 }  // namespace b200sqp

@@ -17,7 +17,7 @@ def _fill(arr, values, default=0.0):
 
 def make_ocp(*, grid, dynamics, n_grid, dt, collocation=abi.COLL_CRANK_NICOLSON, integrator=abi.INT_RK4, stage_cost=abi.COST_QUADRATIC_LSQ,
              q=(), r=(), qf=None, x_lb=None, x_ub=None, u_lb=None, u_ub=None, xf_fixed=None, dt_lb=0.0, dt_ub=abi.CORBO_INF_DBL,
-             dyn_params=()):
+             dyn_params=(), terminal_equality=None, terminal_ball=None):
     nx, nu = abi.DYN_DIMS[dynamics]
     d = abi.Ocp()
     d.grid, d.dynamics, d.collocation, d.integrator = grid, dynamics, collocation, integrator
@@ -36,13 +36,21 @@ def make_ocp(*, grid, dynamics, n_grid, dt, collocation=abi.COLL_CRANK_NICOLSON,
     _fill(d.x_ub, list(x_ub) if x_ub is not None else [inf] * nx, inf)
     _fill(d.u_lb, list(u_lb) if u_lb is not None else [-inf] * nu, -inf)
     _fill(d.u_ub, list(u_ub) if u_ub is not None else [inf] * nu, inf)
+    # final-stage constraint: TerminalEqualityConstraint(xref) or TerminalBall(diag S, gamma)
+    if terminal_equality is not None:
+        d.final_constraint = abi.FINAL_CONSTRAINT_EQUALITY
+        _fill(d.term_xref, list(terminal_equality))
+    elif terminal_ball is not None:
+        d.final_constraint = abi.FINAL_CONSTRAINT_BALL
+        _fill(d.term_s_diag, list(terminal_ball[0]))
+        d.term_gamma = float(terminal_ball[1])
     return d
 
 
-def van_der_pol(n_grid=50, dt=0.1, final_cost=True, collocation=abi.COLL_CRANK_NICOLSON, a=1.0):
+def van_der_pol(n_grid=50, dt=0.1, final_cost=True, collocation=abi.COLL_CRANK_NICOLSON, a=1.0, **kw):
     """configs[0] (N=20) / configs[1] (N=50): VdP, FiniteDifferencesGrid, CN collocation, Q=I, R=0.1, |u|<=1."""
     return make_ocp(grid=abi.GRID_FD_UNIFORM, dynamics=abi.DYN_VAN_DER_POL, n_grid=n_grid, dt=dt, collocation=collocation,
-                    q=(1.0, 1.0), r=(0.1,), qf=(1.0, 1.0) if final_cost else None, u_lb=(-1.0,), u_ub=(1.0,), dyn_params=(a,))
+                    q=(1.0, 1.0), r=(0.1,), qf=(1.0, 1.0) if final_cost else None, u_lb=(-1.0,), u_ub=(1.0,), dyn_params=(a,), **kw)
 
 
 def unicycle_time_optimal(n_grid=50, dt=0.1):
@@ -51,18 +59,18 @@ def unicycle_time_optimal(n_grid=50, dt=0.1):
                     stage_cost=abi.COST_MINIMUM_TIME_LSQ, u_lb=(-1.0, -1.0), u_ub=(1.0, 1.0), xf_fixed=(1, 1, 1), dt_lb=0.0, dt_ub=1.0)
 
 
-def cart_pole_shooting(n_grid=100, dt=0.02):
+def cart_pole_shooting(n_grid=100, dt=0.02, **kw):
     """configs[3]: CartPole defaults, MultipleShootingGrid, RK4, Q=I4, R=0.01, Qf=10 I4, |u|<=20 (weights 10 set on the solver)."""
     return make_ocp(grid=abi.GRID_MULTIPLE_SHOOTING, dynamics=abi.DYN_CART_POLE, n_grid=n_grid, dt=dt, integrator=abi.INT_RK4,
-                    q=(1.0,) * 4, r=(0.01,), qf=(10.0,) * 4, u_lb=(-20.0,), u_ub=(20.0,), dyn_params=(1.0, 0.3, 0.5, 9.81))
+                    q=(1.0,) * 4, r=(0.01,), qf=(10.0,) * 4, u_lb=(-20.0,), u_ub=(20.0,), dyn_params=(1.0, 0.3, 0.5, 9.81), **kw)
 
 
-def quadrotor(n_grid=60, dt=0.05):
+def quadrotor(n_grid=60, dt=0.05, **kw):
     """configs[4]: 12-state quadrotor, FiniteDifferencesGrid, quadratic lsq cost, thrust/torque bounds."""
     m, g = 1.0, 9.81
     return make_ocp(grid=abi.GRID_FD_UNIFORM, dynamics=abi.DYN_QUADROTOR, n_grid=n_grid, dt=dt,
                     q=(1.0,) * 12, r=(0.1,) * 4, qf=(1.0,) * 12, u_lb=(0.0, -1.0, -1.0, -1.0), u_ub=(2.0 * m * g, 1.0, 1.0, 1.0),
-                    dyn_params=(m, g, 0.01, 0.01, 0.02))
+                    dyn_params=(m, g, 0.01, 0.01, 0.02), **kw)
 
 
 def config(index):

@@ -26,7 +26,7 @@ ABI_SYMBOLS = [
     "b200sqp_initialize_trajectories", "b200sqp_set_params", "b200sqp_get_params", "b200sqp_get_first_controls", "b200sqp_solve",
     "b200sqp_solve_async", "b200sqp_synchronize", "b200sqp_step", "b200sqp_evaluate", "b200sqp_get_statistics", "b200sqp_get_chi2_trace",
     "b200sqp_last_solve_ms", "b200sqp_launch_count", "b200sqp_device_pointers", "b200sqp_set_stream", "b200sqp_set_threads_per_instance",
-    "b200sqp_set_phase_profile", "b200sqp_get_phase_cycles",
+    "b200sqp_set_phase_profile", "b200sqp_get_phase_cycles", "b200sqp_final_constraint_indices",
 ]
 
 
@@ -92,6 +92,12 @@ def edge_indices(ocp):
     fc = C.c_int32(-2)
     _check(load_library().b200sqp_edge_indices(C.byref(ocp), _i(sc), _i(cc), _i(tc), _i(dy), C.byref(fc)))
     return dict(state_cost=sc, control_cost=cc, dt_cost=tc.reshape(K, 2), dynamics=dy, final_cost=fc.value)
+
+
+def final_constraint_indices(ocp):
+    eq, ineq = C.c_int32(-2), C.c_int32(-2)
+    _check(load_library().b200sqp_final_constraint_indices(C.byref(ocp), C.byref(eq), C.byref(ineq)))
+    return eq.value, ineq.value
 
 
 def jacobian_pattern(ocp):

@@ -68,6 +68,14 @@ typedef enum {
     B200SQP_COST_MINIMUM_TIME_LSQ = 2 /* MinimumTime(lsq=true) (minimum_time.h:49-78) */
 } b200sqp_stage_cost;
 
+/* Final-stage constraints (src/optimal_control/include/corbo-optimal-control/functions/final_state_constraints.h) */
+typedef enum {
+    B200SQP_FINAL_CONSTRAINT_NONE     = 0,
+    B200SQP_FINAL_CONSTRAINT_EQUALITY = 1, /* TerminalEqualityConstraint: nx equality rows */
+    B200SQP_FINAL_CONSTRAINT_BALL     = 2  /* TerminalBall, diagonal S: one inequality row (active-set rule of
+                                              hyper_graph_optimization_problem_base.cpp:278-289, ..._edge_based.cpp:1565-1616) */
+} b200sqp_final_constraint;
+
 /*
  * One OCP structure shared by all instances of a batch.  It carries exactly what the hypergraph walk of a
  * StructuredOptimalControlProblem yields (SURVEY.md section 8b "discovery gap"): grid kind and size, functor ids and their
@@ -93,6 +101,12 @@ typedef struct b200sqp_ocp {
     double qf_diag[B200SQP_MAX_NX]; /* diagonal of Qf (final state cost)   */
     double x_lb[B200SQP_MAX_NX], x_ub[B200SQP_MAX_NX]; /* |bound| >= 2e30 (CORBO_INF_DBL, core/types.h:53) means unbounded */
     double u_lb[B200SQP_MAX_NU], u_ub[B200SQP_MAX_NU];
+    /* Final-stage constraint on the (not fully fixed) final state, one edge added after all interval edges
+     * (finite_differences_grid.cpp:131-144, nlp_functions.cpp:204-218): */
+    int32_t final_constraint;            /* b200sqp_final_constraint */
+    double term_xref[B200SQP_MAX_NX];    /* TerminalEqualityConstraint::setXRef (final_state_constraints.h:167-232): rows x_N - term_xref */
+    double term_s_diag[B200SQP_MAX_NX];  /* TerminalBall::setWeightS, diagonal S (final_state_constraints.h:38-107) */
+    double term_gamma;                   /* TerminalBall::setGamma: one inequality row (x_N - xref)^T S (x_N - xref) - gamma <= 0 */
 } b200sqp_ocp;
 
 /* LevenbergMarquardtSparse parameters (levenberg_marquardt_sparse.h:85-90,112-124); defaults 10 / 2,2,2 / 1,1,1 / 500,500,500 */
@@ -139,6 +153,8 @@ int b200sqp_vertex_indices(const b200sqp_ocp* ocp, int32_t* x_idx /*[N]*/, int32
  * control-cost and dynamics edge of every interval; final-cost edge index in final_cost_idx (or -1). */
 int b200sqp_edge_indices(const b200sqp_ocp* ocp, int32_t* state_cost_idx /*[N-1]*/, int32_t* control_cost_idx /*[N-1]*/,
                          int32_t* dt_cost_idx /*[2*(N-1)]*/, int32_t* dynamics_idx /*[N-1]*/, int32_t* final_cost_idx /*[1]*/);
+/* row offset of the final-stage constraint edge inside the equality (eq_idx) or inequality (ineq_idx) category, -1 if absent */
+int b200sqp_final_constraint_indices(const b200sqp_ocp* ocp, int32_t* eq_idx /*[1]*/, int32_t* ineq_idx /*[1]*/);
 /* CSC pattern of computeCombinedSparseJacobian (hyper_graph_optimization_problem_edge_based.cpp:1480-1753), rows lsq->eq->ineq->bounds */
 int b200sqp_jacobian_pattern(const b200sqp_ocp* ocp, int32_t* col_ptr /*[n+1]*/, int32_t* row_idx /*[nnzJ]*/);
 

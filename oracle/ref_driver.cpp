@@ -14,6 +14,7 @@
 #include <corbo-core/time.h>
 #include <corbo-numerics/explicit_integrators.h>
 #include <corbo-numerics/finite_differences_collocation.h>
+#include <corbo-optimal-control/functions/final_state_constraints.h>
 #include <corbo-optimal-control/functions/final_state_cost.h>
 #include <corbo-optimal-control/functions/minimum_time.h>
 #include <corbo-optimal-control/functions/quadratic_cost.h>
@@ -252,6 +253,19 @@ bool buildOcp(const b200sqp_ocp& d, const b200sqp_lm_options& o, RefOcp& r)
         Eigen::MatrixXd Qf = Eigen::MatrixXd::Zero(d.nx, d.nx);
         for (int i = 0; i < d.nx; ++i) Qf(i, i) = d.qf_diag[i];
         r.ocp->setFinalStageCost(std::make_shared<QuadraticFinalStateCost>(Qf, true));
+    }
+
+    if (d.final_constraint == B200SQP_FINAL_CONSTRAINT_EQUALITY)
+    {
+        Eigen::VectorXd tx(d.nx);
+        for (int i = 0; i < d.nx; ++i) tx[i] = d.term_xref[i];
+        r.ocp->setFinalStageConstraint(std::make_shared<TerminalEqualityConstraint>(tx));
+    }
+    else if (d.final_constraint == B200SQP_FINAL_CONSTRAINT_BALL)
+    {
+        Eigen::MatrixXd S = Eigen::MatrixXd::Zero(d.nx, d.nx);
+        for (int i = 0; i < d.nx; ++i) S(i, i) = d.term_s_diag[i];
+        r.ocp->setFinalStageConstraint(std::make_shared<TerminalBall>(S, d.term_gamma));
     }
 
     Eigen::VectorXd xlb(d.nx), xub(d.nx), ulb(d.nu), uub(d.nu);

@@ -351,6 +351,80 @@ void addFinalCostEdge(Graph& g, const b200sqp_ocp& d, Vertex* xf, const std::vec
     g.lsq.push_back(e);
 }
 
+// Eigen 3.3.7 evaluates `a.transpose() * D * b` (a 1 x n by n x 1 product) as a vectorised reduction of the coefficient products:
+// SSE2 packets of two doubles, two packet accumulators, then the horizontal add and a scalar tail
+// (extern/eigen3/Eigen/src/Core/Redux.h, redux_impl<Func, Derived, LinearVectorizedTraversal, NoUnrolling>).
+double eigenReduxSum(const std::vector<double>& t)
+{
+    const int n = (int)t.size();
+    const int aligned = (n / 2) * 2, aligned2 = (n / 4) * 4;
+    if (aligned == 0) return t[0];
+    double p0a = t[0], p0b = t[1];
+    if (aligned > 2)
+    {
+        double p1a = t[2], p1b = t[3];
+        for (int i = 4; i < aligned2; i += 4)
+        {
+            p0a += t[i];
+            p0b += t[i + 1];
+            p1a += t[i + 2];
+            p1b += t[i + 3];
+        }
+        p0a += p1a;
+        p0b += p1b;
+        if (aligned > aligned2)
+        {
+            p0a += t[aligned2];
+            p0b += t[aligned2 + 1];
+        }
+    }
+    double res = p0a + p0b;
+    for (int i = aligned; i < n; ++i) res += t[i];
+    return res;
+}
+
+// Final-stage constraint edge on xf: UnaryVectorVertexEdge over FinalStageConstraint::computeNonIntegralStateTerm
+// (optimal_control/src/functions/nlp_functions.cpp:204-218), added as an equality or inequality edge after all interval edges
+// (finite_differences_grid.cpp:131-144).
+//   TerminalEqualityConstraint: cost = x_k - _xref                      (functions/final_state_constraints.h:187-192)
+//   TerminalBall, diagonal S:   cost[0] = xd^T S_diag xd - gamma,  xd = x_k - xref(k) unless the reference is zero
+//                                                                        (src/functions/final_state_constraints.cpp:60-80)
+void addFinalConstraintEdge(Graph& g, const b200sqp_ocp& d, Vertex* xf, const std::vector<double>& xref)
+{
+    const int nx = d.nx;
+    if (d.final_constraint == B200SQP_FINAL_CONSTRAINT_EQUALITY)
+    {
+        std::vector<double> tx(d.term_xref, d.term_xref + nx);
+        Edge e;
+        e.dim    = nx;
+        e.v      = {xf};
+        e.values = [xf, tx, nx](double* out) {
+            for (int i = 0; i < nx; ++i) out[i] = xf->val[i] - tx[i];
+        };
+        g.eq.push_back(e);
+    }
+    else if (d.final_constraint == B200SQP_FINAL_CONSTRAINT_BALL)
+    {
+        std::vector<double> sd(d.term_s_diag, d.term_s_diag + nx);
+        const double gamma = d.term_gamma;
+        bool zero_ref      = true;
+        for (double r : xref) zero_ref = zero_ref && (r == 0.0);
+        Edge e;
+        e.dim    = 1;
+        e.v      = {xf};
+        e.values = [xf, sd, gamma, nx, xref, zero_ref](double* out) {
+            std::vector<double> t(nx);
+            for (int i = 0; i < nx; ++i)
+            {
+                const double xd = zero_ref ? xf->val[i] : xf->val[i] - xref[i];
+                t[i]            = (xd * sd[i]) * xd;
+            }
+            out[0] = eigenReduxSum(t) - gamma;
+        };
+        g.ineq.push_back(e);
+    }
+}
+
 // FullDiscretizationGridBase::initializeSequences (full_discretization_grid_base.cpp:134-179) -- same code in
 // NonUniformFullDiscretizationGridBase (non_uniform_full_discretization_grid_base.cpp:146-190) and ShootingGridBase
 // (shooting_grid_base.cpp:141-200): linear x0 -> xf interpolation, controls = uref (zero), first state fixed;
@@ -464,6 +538,7 @@ std::unique_ptr<Graph> buildGraph(const BuildInput& in)
         g.eq.push_back(e);
     }
     if (!xf->isFixed()) addFinalCostEdge(g, d, xf, xref);
+    if (!xf->isFixed()) addFinalConstraintEdge(g, d, xf, xref);
     computeEdgeIndices(g);
     return gp;
 }

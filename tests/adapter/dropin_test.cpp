@@ -7,6 +7,7 @@
 #include <corbo-controllers/predictive_controller.h>
 #include <corbo-core/reference_trajectory.h>
 #include <corbo-numerics/explicit_integrators.h>
+#include <corbo-optimal-control/functions/final_state_constraints.h>
 #include <corbo-optimal-control/functions/final_state_cost.h>
 #include <corbo-optimal-control/functions/quadratic_cost.h>
 #include <corbo-optimal-control/structured_ocp/discretization_grids/finite_differences_grid.h>
@@ -32,7 +33,7 @@ struct Loop
     std::shared_ptr<FiniteDifferencesGrid> grid;
 };
 
-static Loop makeLoop(NlpSolverInterface::Ptr solver, int n)
+static Loop makeLoop(NlpSolverInterface::Ptr solver, int n, FinalStageConstraint::Ptr final_constraint = {})
 {
     Loop l;
     l.dynamics = std::make_shared<VanDerPolOscillator>();
@@ -47,6 +48,7 @@ static Loop makeLoop(NlpSolverInterface::Ptr solver, int n)
     auto final_cost = std::make_shared<QuadraticFinalStateCost>(Q, true);
     l.ocp->setStageCost(stage_cost);
     l.ocp->setFinalStageCost(final_cost);
+    if (final_constraint) l.ocp->setFinalStageConstraint(final_constraint);
     Eigen::VectorXd xlb = Eigen::VectorXd::Constant(2, -CORBO_INF_DBL), xub = Eigen::VectorXd::Constant(2, CORBO_INF_DBL);
     Eigen::VectorXd ulb = Eigen::VectorXd::Constant(1, -1.0), uub = Eigen::VectorXd::Constant(1, 1.0);
     l.ocp->setBounds(xlb, xub, ulb, uub);
@@ -56,6 +58,7 @@ static Loop makeLoop(NlpSolverInterface::Ptr solver, int n)
         b200->setSystemDynamics(l.dynamics);
         b200->setStageCost(stage_cost);
         b200->setFinalStageCost(final_cost);
+        if (final_constraint) b200->setFinalStageConstraint(final_constraint);
     }
     l.controller = std::make_shared<PredictiveController>();
     l.controller->setOptimalControlProblem(l.ocp);
@@ -168,6 +171,45 @@ int main()
     {
         std::printf("FAIL: batched trajectories differ\n");
         ++failures;
+    }
+
+    // ---- 3b. final-stage constraints: TerminalBall (the inequality edge with its active-set rows) and TerminalEqualityConstraint ----
+    for (int variant = 0; variant < 2; ++variant)
+    {
+        FinalStageConstraint::Ptr fc;
+        if (variant == 0)
+        {
+            Eigen::MatrixXd S = Eigen::MatrixXd::Zero(2, 2);
+            S(0, 0) = 2.0;
+            S(1, 1) = 0.5;
+            fc = std::make_shared<TerminalBall>(S, 0.01);
+        }
+        else
+        {
+            Eigen::VectorXd tx(2);
+            tx << 0.1, -0.05;
+            fc = std::make_shared<TerminalEqualityConstraint>(tx);
+        }
+        Loop lr = makeLoop(std::make_shared<LevenbergMarquardtSparse>(), 30, fc);
+        Loop lb = makeLoop(std::make_shared<SolverB200Lm>(), 30, fc);
+        lr.ocp->initialize();
+        lb.ocp->initialize();
+        Eigen::VectorXd x0(2);
+        x0 << 1.5, -0.7;
+        bool ok_r = lr.ocp->compute(x0, xref, uref, nullptr, Time(0), true);
+        bool ok_b = lb.ocp->compute(x0, xref, uref, nullptr, Time(0), true);
+        Eigen::VectorXd pr(lr.problem->getParameterDimension()), pb(lb.problem->getParameterDimension());
+        lr.problem->getParameterVector(pr);
+        lb.problem->getParameterVector(pb);
+        double diff = pr.size() == pb.size() ? (pr - pb).cwiseAbs().maxCoeff() / std::max(1.0, pr.cwiseAbs().maxCoeff()) : 1e30;
+        std::printf("final-stage constraint %s: ineq dim %d, eq dim %d, max relative trajectory difference vs reference = %.3e\n",
+                    variant == 0 ? "TerminalBall" : "TerminalEqualityConstraint", lb.problem->getInequalityDimension(),
+                    lb.problem->getEqualityDimension(), diff);
+        if (!ok_r || !ok_b || !(diff <= 1e-5))
+        {
+            std::printf("FAIL: final-stage constraint variant %d (ok_ref=%d ok_b200=%d)\n", variant, (int)ok_r, (int)ok_b);
+            ++failures;
+        }
     }
 
     // ---- 4. error behaviour: structures outside the registry -> SolverStatus::Error, never a CPU fallback ---------------------------

@@ -17,6 +17,14 @@ CASES = {
     "unicycle30_timeopt": (lambda: problems.unicycle_time_optimal(30), (2.0, 2.0, 2.0), 4),
     "cartpole40_rk4": (lambda: problems.cart_pole_shooting(40), (10.0, 10.0, 10.0), 4),
     "quadrotor12_cn": (lambda: problems.quadrotor(12), (2.0, 2.0, 2.0), 2),
+    # final-stage constraints (functions/final_state_constraints.h): TerminalEqualityConstraint -> equality edge on xf,
+    # TerminalBall -> the path's only inequality edge (active-set rows); nx = 2, 4, 12 exercise Eigen's reduction order
+    "vdp30_terminal_eq": (lambda: problems.van_der_pol(30, terminal_equality=(0.1, -0.05)), (2.0, 2.0, 2.0), 4),
+    "vdp30_terminal_ball": (lambda: problems.van_der_pol(30, terminal_ball=((2.0, 0.5), 0.01)), (2.0, 3.0, 2.0), 4),
+    "vdp20_terminal_ball_xf_partly_fixed": (lambda: problems.van_der_pol(20, terminal_ball=((1.0, 1.0), 0.04), xf_fixed=(1, 0)),
+                                            (2.0, 2.0, 2.0), 4),
+    "cartpole20_terminal_ball": (lambda: problems.cart_pole_shooting(20, terminal_ball=((1.0, 2.0, 0.5, 0.25), 0.05)), (10.0, 10.0, 10.0), 4),
+    "quadrotor8_terminal_ball": (lambda: problems.quadrotor(8, terminal_ball=(tuple(0.5 + 0.1 * i for i in range(12)), 0.02)), (2.0, 2.0, 2.0), 2),
 }
 
 EVAL_WEIGHTS = (2.0, 3.0, 5.0)

@@ -42,6 +42,11 @@ CASES = [
     ("unicycle30_timeopt", lambda: problems.unicycle_time_optimal(30), False),
     ("cartpole40_rk4", lambda: problems.cart_pole_shooting(40), False),
     ("quadrotor12", lambda: problems.quadrotor(12), False),
+    # final-stage constraints: equality edge / the inequality edge with its active-set rows (final_state_constraints.h)
+    ("vdp30_terminal_eq", lambda: problems.van_der_pol(30, terminal_equality=(0.1, -0.05)), True),
+    ("vdp30_terminal_ball", lambda: problems.van_der_pol(30, terminal_ball=((2.0, 0.5), 0.01)), True),
+    ("vdp20_terminal_ball_xf_partly_fixed", lambda: problems.van_der_pol(20, terminal_ball=((1.0, 1.0), 0.04), xf_fixed=(1, 0)), True),
+    ("cartpole20_terminal_ball", lambda: problems.cart_pole_shooting(20, terminal_ball=((1.0, 2.0, 0.5, 0.25), 0.05)), False),
 ]
 
 
@@ -90,7 +95,9 @@ def _traj_err(p, p_ref):
     ("vdp50", lambda: problems.van_der_pol(50), (2.0, 2.0, 2.0), 256, 1e-6, 1e-4, 1e-6),
     ("unicycle30", lambda: problems.unicycle_time_optimal(30), (2.0, 2.0, 2.0), 32, 2e-5, 1e-3, 1e-6),
     ("cartpole40", lambda: problems.cart_pole_shooting(40), (10.0, 10.0, 10.0), 32, 5e-4, 5e-3, 1e-4),
-], ids=["vdp20", "vdp50", "unicycle30", "cartpole40"])
+    ("vdp30_terminal_eq", lambda: problems.van_der_pol(30, terminal_equality=(0.1, -0.05)), (2.0, 2.0, 2.0), 64, 1e-6, 1e-4, 1e-6),
+    ("vdp30_terminal_ball", lambda: problems.van_der_pol(30, terminal_ball=((2.0, 0.5), 0.01)), (2.0, 3.0, 2.0), 64, 1e-6, 1e-4, 1e-6),
+], ids=["vdp20", "vdp50", "unicycle30", "cartpole40", "vdp30_terminal_eq", "vdp30_terminal_ball"])
 def test_solve_matches_oracle(oracle, name, make, weights, B, tol95, tolmax, tolchi2, threads):
     ocp = make()
     x0, xref = problems.instance_data(ocp, B, seed=11)
@@ -123,8 +130,10 @@ sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "gol
 import cases  # noqa: E402
 
 GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
-POLYNOMIAL = {"vdp20_cn", "vdp50_cn", "vdp50_cn_nofinal", "vdp30_forward", "vdp30_backward", "vdp30_midpoint", "vdp2_minimal"}
-GOLD_TOL = {"unicycle30_timeopt": (1e-3, 1e-4), "cartpole40_rk4": (5e-3, 1e-3), "quadrotor12_cn": (1e-3, 1e-4)}  # (trajectory, chi2)
+POLYNOMIAL = {"vdp20_cn", "vdp50_cn", "vdp50_cn_nofinal", "vdp30_forward", "vdp30_backward", "vdp30_midpoint", "vdp2_minimal",
+              "vdp30_terminal_eq", "vdp30_terminal_ball", "vdp20_terminal_ball_xf_partly_fixed"}
+GOLD_TOL = {"unicycle30_timeopt": (1e-3, 1e-4), "cartpole40_rk4": (5e-3, 1e-3), "quadrotor12_cn": (1e-3, 1e-4),
+            "cartpole20_terminal_ball": (5e-3, 1e-3), "quadrotor8_terminal_ball": (1e-3, 1e-4)}  # (trajectory, chi2)
 
 
 @pytest.mark.parametrize("name", list(cases.CASES))

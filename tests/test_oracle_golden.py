@@ -15,9 +15,11 @@ import cases  # noqa: E402
 
 GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 # models whose edge functions only use + - * / : the oracle reproduces the reference bit for bit
-POLYNOMIAL = {"vdp20_cn", "vdp50_cn", "vdp50_cn_nofinal", "vdp30_forward", "vdp30_backward", "vdp30_midpoint", "vdp2_minimal"}
+POLYNOMIAL = {"vdp20_cn", "vdp50_cn", "vdp50_cn_nofinal", "vdp30_forward", "vdp30_backward", "vdp30_midpoint", "vdp2_minimal",
+              "vdp30_terminal_eq", "vdp30_terminal_ball", "vdp20_terminal_ball_xf_partly_fixed"}
 # FD-noise floor of the reference algorithm per case: trajectory tolerance for 10 LM iterations
-TRAJ_TOL = {"unicycle30_timeopt": 1e-3, "cartpole40_rk4": 5e-3, "quadrotor12_cn": 1e-3}
+TRAJ_TOL = {"unicycle30_timeopt": 1e-3, "cartpole40_rk4": 5e-3, "quadrotor12_cn": 1e-3, "cartpole20_terminal_ball": 5e-3,
+            "quadrotor8_terminal_ball": 1e-3}
 
 
 @pytest.mark.parametrize("name", list(cases.CASES))
@@ -31,6 +33,8 @@ def test_indices_and_dims(oracle, name):
         assert np.array_equal(a, gold[key])
     assert np.array_equal(oracle.edge_table(ocp, 0), gold["edges_lsq"])
     assert np.array_equal(oracle.edge_table(ocp, 1), gold["edges_eq"])
+    if "edges_ineq" in gold:
+        assert np.array_equal(oracle.edge_table(ocp, 2), gold["edges_ineq"])
 
 
 @pytest.mark.parametrize("name", list(cases.CASES))

@@ -36,10 +36,22 @@ def test_edge_indices_match_reference_golden(name):
     e = solver.edge_indices(ocp)
     # reference edge tables: rows [dim, edge_idx, n_vertices, vertex_idx0..3] in creation order
     lsq, eq = gold["edges_lsq"], gold["edges_eq"]
+    # final-stage constraint edge: last equality edge (TerminalEqualityConstraint) or the only inequality edge (TerminalBall)
+    feq, fineq = solver.final_constraint_indices(ocp)
+    K = ocp.n_grid - 1
+    if ocp.final_constraint == abi.FINAL_CONSTRAINT_EQUALITY:
+        assert len(eq) == K + 1 and eq[-1, 1] == feq and eq[-1, 0] == ocp.nx and eq[-1, 2] == 1
+        eq = eq[:-1]
+    else:
+        assert feq == -1
+    if "edges_ineq" in gold and len(gold["edges_ineq"]):
+        assert ocp.final_constraint == abi.FINAL_CONSTRAINT_BALL and gold["edges_ineq"].shape[0] == 1
+        assert gold["edges_ineq"][0, 1] == fineq and gold["edges_ineq"][0, 0] == 1
+    else:
+        assert fineq == -1
     assert np.array_equal(eq[:, 1], e["dynamics"])
     assert np.all(eq[:, 0] == ocp.nx)
     mine = []
-    K = ocp.n_grid - 1
     for k in range(K):
         if e["state_cost"][k] >= 0:
             mine.append(e["state_cost"][k])
@@ -74,6 +86,13 @@ def test_structure_matches_oracle_on_sweep(oracle):
     o = problems.unicycle_time_optimal(9)
     o.xf_fixed[1] = 0
     variants.append(o)
+    # final-stage constraints, incl. on a partially / fully fixed goal (fully fixed: the reference creates no final-stage edge)
+    for n in (2, 5, 20):
+        variants.append(problems.van_der_pol(n, terminal_equality=(0.1, -0.2)))
+        variants.append(problems.van_der_pol(n, terminal_ball=((1.0, 2.0), 0.1)))
+        variants.append(problems.van_der_pol(n, terminal_ball=((1.0, 2.0), 0.1), xf_fixed=(0, 1)))
+        variants.append(problems.van_der_pol(n, terminal_equality=(0.1, -0.2), xf_fixed=(1, 1)))
+        variants.append(problems.cart_pole_shooting(max(n, 3), terminal_ball=((1.0,) * 4, 0.5)))
     for ocp in variants:
         d, od = solver.dims_of(ocp), oracle.dims(ocp)
         for f in ("n_params", "m_lsq", "m_eq", "m_ineq", "m_bounds", "nnz_jacobian", "nnz_hessian_upper", "algorithmic_bytes_per_iteration"):
