@@ -45,6 +45,9 @@ def parse_args():
     ap.add_argument("--batch", type=int, default=4096, help="instances per GPU (north_star target batch; weak scaling)")
     ap.add_argument("--cpu-sample", type=int, default=4096, help="instances of the same workload timed on the host cores")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--collective", default="p2p", choices=["p2p", "nccl"],
+                    help="stop-test exchange at N>1: chi2 stored into every rank's gather buffer by the LM kernel itself over NVLink peer "
+                         "memory (p2p, default) or a separate NCCL all-gather after the solve (nccl)")
     return ap.parse_args()
 
 
@@ -250,12 +253,28 @@ def main_b200(args):
     chi2_local = torch.as_tensor(_CudaArray(ptrs["chi2"], (B,), "<f8"), device=f"cuda:{local_rank}")
     chi2_all = torch.empty(B * world, dtype=torch.float64, device=f"cuda:{local_rank}") if world > 1 else None
     flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=f"cuda:{local_rank}")  # > 126 MB L2
+    rendezvous = torch.zeros(1, dtype=torch.float32, device=f"cuda:{local_rank}")
+
+    # the single stop-test exchange.  p2p: NCCL/torch.distributed only carries the 64-byte IPC handles at
+    # set-up; per step the LM kernel's epilogue stores chi2 into every rank's gather buffer and b200sqp_peer_wait (stream-ordered,
+    # bounded) returns when all ranks' values have arrived.  nccl: one all_gather_into_tensor after the solve.
+    use_p2p = world > 1 and args.collective == "p2p"
+    if use_p2p:
+        handles = [None] * world
+        dist.all_gather_object(handles, lm.peer_export(world, rank))
+        lm.peer_attach(handles)
+        dist.barrier()
+
+    def exchange():
+        if use_p2p:
+            lm.peer_wait()
+        elif world > 1:
+            dist.all_gather_into_tensor(chi2_all, chi2_local)
 
     def device_step():
         lm.initialize_trajectories()
         lm.solve(new_run=True, fetch=False)
-        if world > 1:  # the single stop-test exchange: all-gather of the per-instance chi2
-            dist.all_gather_into_tensor(chi2_all, chi2_local)
+        exchange()
 
     def barrier():
         if world > 1:
@@ -266,6 +285,10 @@ def main_b200(args):
         total_ms, kernel_ms = 0.0, 0.0
         for _ in range(steps):
             flush.zero_()  # evict L2 between timed iterations (outside the timed region)
+            if world > 1:
+                # device-side rendezvous, also outside the timed region: all ranks enter the step together, so a step's time is
+                # its own work + exchange and not the other rank's leftover flush (the per-step analogue of the bracket barrier)
+                dist.all_reduce(rendezvous)
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record(stream)
             fn()
@@ -279,6 +302,14 @@ def main_b200(args):
     for _ in range(max(args.warmup, 3)):
         device_step()
     barrier()
+    if use_p2p:
+        # the fused gather must deliver exactly what an NCCL all-gather of the same solve delivers
+        gathered = torch.as_tensor(_CudaArray(lm.peer_gathered_ptr(), (B * world,), "<f8"), device=f"cuda:{local_rank}").clone()
+        dist.all_gather_into_tensor(chi2_all, chi2_local)
+        torch.cuda.synchronize()
+        if not torch.equal(gathered, chi2_all):
+            raise SystemExit("bench.py: peer-memory gather differs from the NCCL all-gather of the same solve")
+        barrier()
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
@@ -305,8 +336,7 @@ def main_b200(args):
 
     def e2e_step():
         lm.step_raw(h_x0.data_ptr(), h_xref.data_ptr(), h_params.data_ptr(), h_chi2.data_ptr(), h_status.data_ptr(), cold_start=True)
-        if world > 1:
-            dist.all_gather_into_tensor(chi2_all, chi2_local)
+        exchange()
 
     for _ in range(2):
         e2e_step()
@@ -345,8 +375,10 @@ def main_b200(args):
             "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
             "data": "synthetic",
             "config": {"workload": workload_name(args.config, ocp, B, iterations), "instances_total": B * world, "n_grid": ocp.n_grid,
-                       "n_params": n, "parallelism": f"instance-sharded x{world}, one chi2 all-gather per step" if world > 1 else "single GPU",
-                       "timing": "CUDA events per step on the launch stream, L2 flushed (256 MiB memset) between steps, max over ranks",
+                       "n_params": n, "parallelism": (f"instance-sharded x{world}, stop-test gather of chi2 fused into the LM kernel over NVLink peer memory"
+                                       if use_p2p else f"instance-sharded x{world}, one NCCL chi2 all-gather per step") if world > 1 else "single GPU",
+                       "timing": "CUDA events per step on the launch stream, L2 flushed (256 MiB memset) between steps"
+                                 + (", ranks rendezvous on the device before each timed step" if world > 1 else "") + ", max over ranks",
                        "wall_s_timed_region_incl_flush": wall},
             "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "ms_per_step": e2e_ms / args.steps},
@@ -363,6 +395,11 @@ def main_b200(args):
             line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": cores, "kind": kind,
                                     "sample": f"{args.cpu_sample} instances of the same workload, {dt:.2f} s wall on {cores} threads"}
         print(json.dumps(line))
+    if use_p2p:
+        if lm.peer_timed_out():
+            raise SystemExit("bench.py: a peer never arrived in b200sqp_peer_wait (2 s bound)")
+        barrier()  # nobody unmaps while a peer may still store
+        lm.peer_detach()
     lm.clear()
     if world > 1:
         dist.destroy_process_group()

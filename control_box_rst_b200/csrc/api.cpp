@@ -77,6 +77,12 @@ struct b200sqp_solver
     double* d_u0 = nullptr;       // [B][nu]
     int* d_ref_of_internal = nullptr, *d_internal_of_ref = nullptr, *d_value_rows = nullptr, *d_jac_pos = nullptr;
     double* d_values = nullptr, *d_jac = nullptr, *d_eval_out = nullptr;
+    // fused peer gather
+    int peer_world = 0, peer_rank = 0;
+    bool peer_attached = false;
+    void* peer_local = nullptr;              // own buffer: [2*world*B] doubles, then [world] arrival counters, then 1 int timeout flag
+    void* peer_mapped[MAX_PEERS] = {};       // cudaIpcOpenMemHandle results (null for own rank)
+    unsigned long long peer_solves = 0;      // solves launched since attach
     long long* d_phase_cycles = nullptr;
     int phase_blocks = 0;
     std::vector<void*> allocations;
@@ -353,6 +359,7 @@ int b200sqp_destroy(b200sqp_handle h)
     if (!h) return B200SQP_OK;
     cudaSetDevice(h->device);
     if (h->own_stream) cudaStreamSynchronize(h->own_stream);
+    b200sqp_peer_detach(h);
     for (void* p : h->allocations) cudaFree(p);
     if (h->ev_begin) cudaEventDestroy(h->ev_begin);
     if (h->ev_end) cudaEventDestroy(h->ev_end);
@@ -458,6 +465,11 @@ int b200sqp_solve_async(b200sqp_handle h, const b200sqp_lm_options* opts, int32_
     rc = ensureTrace(h, opts->iterations);
     if (rc) return rc;
     updateWeights(h, *opts, new_run != 0);
+    if (h->peer_attached)
+    {
+        h->st.peer_parity = (int)(h->peer_solves & 1);  // double-buffered: a fast peer's next solve never overwrites what we still read
+        h->peer_solves += 1;
+    }
     CUDA_TRY(cudaEventRecord(h->ev_begin, h->stream));
     h->kernels->solve(h->P, h->st, opts->iterations, h->threads_per_instance, h->stream);
     h->launches += 1;
@@ -608,6 +620,106 @@ int b200sqp_set_threads_per_instance(b200sqp_handle h, int32_t threads)
 {
     if (!h || threads < 0 || threads > 8) return fail(B200SQP_ERR_INVALID, "threads per instance must be 0 (auto), 1, 2, 4 or 8");
     h->threads_per_instance = threads;
+    return B200SQP_OK;
+}
+
+static size_t peerChi2Bytes(b200sqp_handle h) { return sizeof(double) * 2 * (size_t)h->peer_world * h->B; }
+
+int b200sqp_peer_export(b200sqp_handle h, int32_t world, int32_t rank, void* ipc_handle_out)
+{
+    int rc = checkHandle(h);
+    if (rc) return rc;
+    if (!ipc_handle_out || world < 1 || world > MAX_PEERS || rank < 0 || rank >= world) return fail(B200SQP_ERR_INVALID, "bad world/rank");
+    static_assert(sizeof(cudaIpcMemHandle_t) == B200SQP_IPC_HANDLE_BYTES, "IPC handle size");
+    if (h->peer_local) return fail(B200SQP_ERR_INVALID, "peer buffer already exported");
+    h->peer_world = world;
+    h->peer_rank  = rank;
+    const size_t bytes = peerChi2Bytes(h) + sizeof(unsigned long long) * world + 64;
+    CUDA_TRY(cudaMalloc(&h->peer_local, bytes));  // a dedicated allocation: IPC handles cover whole allocations
+    CUDA_TRY(cudaMemset(h->peer_local, 0, bytes));
+    cudaIpcMemHandle_t handle;
+    CUDA_TRY(cudaIpcGetMemHandle(&handle, h->peer_local));
+    std::memcpy(ipc_handle_out, &handle, sizeof(handle));
+    return B200SQP_OK;
+}
+
+int b200sqp_peer_attach(b200sqp_handle h, const void* ipc_handles)
+{
+    int rc = checkHandle(h);
+    if (rc) return rc;
+    if (!ipc_handles || !h->peer_local) return fail(B200SQP_ERR_INVALID, "call b200sqp_peer_export first");
+    const size_t chi2_bytes = peerChi2Bytes(h);
+    for (int r = 0; r < h->peer_world; ++r)
+    {
+        void* base = h->peer_local;
+        if (r != h->peer_rank)
+        {
+            cudaIpcMemHandle_t handle;
+            std::memcpy(&handle, (const char*)ipc_handles + (size_t)r * sizeof(handle), sizeof(handle));
+            CUDA_TRY(cudaIpcOpenMemHandle(&h->peer_mapped[r], handle, cudaIpcMemLazyEnablePeerAccess));
+            base = h->peer_mapped[r];
+        }
+        h->st.peer_chi2[r]     = (double*)base;
+        h->st.peer_arrivals[r] = (unsigned long long*)((char*)base + chi2_bytes);
+    }
+    h->st.peer_world  = h->peer_world;
+    h->st.peer_rank   = h->peer_rank;
+    h->st.peer_parity = 0;
+    h->peer_solves    = 0;
+    h->peer_attached  = true;
+    return B200SQP_OK;
+}
+
+int b200sqp_peer_wait(b200sqp_handle h)
+{
+    int rc = checkHandle(h);
+    if (rc) return rc;
+    if (!h->peer_attached || h->peer_solves == 0) return fail(B200SQP_ERR_INVALID, "not attached, or no solve launched since attach");
+    const size_t chi2_bytes = peerChi2Bytes(h);
+    const unsigned long long* arrivals = (const unsigned long long*)((char*)h->peer_local + chi2_bytes);
+    int* timed_out                     = (int*)((char*)h->peer_local + chi2_bytes + sizeof(unsigned long long) * h->peer_world);
+    const unsigned long long blocks    = (unsigned long long)((h->B + 31) / 32);
+    launchPeerWait(arrivals, h->peer_world, h->peer_solves * blocks, 2000000000ull /* 2 s */, timed_out, h->stream);
+    h->launches += 1;
+    CUDA_TRY(cudaGetLastError());
+    return B200SQP_OK;
+}
+
+int b200sqp_peer_gathered(b200sqp_handle h, void** chi2_all)
+{
+    if (!h || !chi2_all || !h->peer_attached || h->peer_solves == 0) return fail(B200SQP_ERR_INVALID, "not attached, or no solve yet");
+    const int parity = (int)((h->peer_solves - 1) & 1);
+    *chi2_all        = (double*)h->peer_local + (size_t)parity * h->peer_world * h->B;
+    return B200SQP_OK;
+}
+
+int b200sqp_peer_status(b200sqp_handle h, int32_t* timed_out)
+{
+    int rc = checkHandle(h);
+    if (rc) return rc;
+    if (!timed_out || !h->peer_attached) return fail(B200SQP_ERR_INVALID, "not attached");
+    const size_t off = peerChi2Bytes(h) + sizeof(unsigned long long) * h->peer_world;
+    CUDA_TRY(cudaMemcpyAsync(timed_out, (char*)h->peer_local + off, sizeof(int32_t), cudaMemcpyDeviceToHost, h->stream));
+    CUDA_TRY(cudaStreamSynchronize(h->stream));
+    return B200SQP_OK;
+}
+
+int b200sqp_peer_detach(b200sqp_handle h)
+{
+    if (!h) return B200SQP_OK;
+    cudaSetDevice(h->device);
+    cudaStreamSynchronize(h->stream);
+    for (int r = 0; r < MAX_PEERS; ++r)
+    {
+        if (h->peer_mapped[r]) cudaIpcCloseMemHandle(h->peer_mapped[r]);
+        h->peer_mapped[r]      = nullptr;
+        h->st.peer_chi2[r]     = nullptr;
+        h->st.peer_arrivals[r] = nullptr;
+    }
+    h->st.peer_world = 0;
+    h->peer_attached = false;
+    if (h->peer_local) cudaFree(h->peer_local);
+    h->peer_local = nullptr;
     return B200SQP_OK;
 }
 

@@ -224,4 +224,22 @@ __device__ __forceinline__ void defect(const DynParams& c, const double* x1, con
     }
 }
 
+// Large models (quadrotor: 56 defect evaluations per interval, each with two 12-state dynamics calls) are evaluated through one
+// out-of-line copy of the defect instead of 57 inlined ones: the inlined form is megabytes of straight-line code that neither
+// the instruction cache nor ptxas (10 minutes) copes with.  Small models keep the fully inlined, register-resident form.
+template <class M, int DEFECT>
+__device__ __noinline__ void defectOutlined(const DynParams& c, const double* x1, const double* u1, const double* x2, const StepSize& h, double* e)
+{
+    defect<M, DEFECT>(c, x1, u1, x2, h, e);
+}
+
+template <class M, int DEFECT>
+__device__ __forceinline__ void defectCall(const DynParams& c, const double* x1, const double* u1, const double* x2, const StepSize& h, double* e)
+{
+    if constexpr (M::NX >= 8)
+        defectOutlined<M, DEFECT>(c, x1, u1, x2, h, e);
+    else
+        defect<M, DEFECT>(c, x1, u1, x2, h, e);
+}
+
 }  // namespace b200sqp

@@ -47,4 +47,8 @@ void launchInitTrajectories(const double* x0 /*[nx][S]*/, const double* xref /*[
 // u_0 of every instance -> [B][nu]
 void launchFirstControls(const double* z0, const double* z1, const int* cur, int nu, int slots, double* u0, int B, int S, cudaStream_t);
 
+// bounded spin on the arrival counters of the fused peer-memory gather (b200sqp_peer_wait)
+void launchPeerWait(const unsigned long long* arrivals, int world, unsigned long long expected, unsigned long long timeout_ns, int* timed_out,
+                    cudaStream_t);
+
 }  // namespace b200sqp

@@ -26,6 +26,8 @@ struct DeviceOcp
     double x_lb[B200SQP_MAX_NX], x_ub[B200SQP_MAX_NX], u_lb[B200SQP_MAX_NU], u_ub[B200SQP_MAX_NU];
 };
 
+constexpr int MAX_PEERS = 8;  // GPUs of one NVSwitch box
+
 struct Weights
 {
     double eq, ineq, b;
@@ -56,6 +58,11 @@ struct DeviceState
     int* n_reject;
     int* n_linearize;
     double* trace;    // [(max_iterations+1)][S] chi2 after every outer iteration
+    // fused stop-test gather over NVLink peer memory (b200sqp_peer_*): every rank's LM kernel stores its per-instance chi2 straight
+    // into every peer's gather buffer and bumps a per-rank arrival counter there; null / 0 when not attached
+    double* peer_chi2[MAX_PEERS];              // peer r's gather buffer [2][world*B] (double-buffered by solve parity), own included
+    unsigned long long* peer_arrivals[MAX_PEERS];  // peer r's arrival counters [world]
+    int peer_world, peer_rank, peer_parity;
     long long* phase_cycles;  // [blocks][4] clock64() per phase (linearise, factor+solve, trial, control) or null (profiling off)
     double w_eq, w_ineq, w_b;  // current penalty weights (host-managed: reset / adapted per solve)
 };

@@ -341,6 +341,21 @@ __global__ void __launch_bounds__(32 * T) lmSolveKernel(const __grid_constant__ 
         for (int q = 0; q < 4; ++q) st.phase_cycles[(size_t)blockIdx.x * 4 + q] = prof_acc[q];
     }
 
+    // Fused stop-test exchange: instead of a separate all-gather launch after the solve, the per-instance
+    // chi2 goes straight into every rank's gather buffer through NVLink peer stores; after a system-scope fence one thread per
+    // block bumps this rank's arrival counter on every peer (b200sqp_peer_wait spins on those counters, bounded).
+    if (st.peer_world > 0)
+    {
+        if (p == 0 && valid)
+        {
+            const size_t slot = (size_t)st.peer_parity * st.peer_world * P.B + (size_t)st.peer_rank * P.B + i;
+            for (int r = 0; r < st.peer_world; ++r) st.peer_chi2[r][slot] = chi2_old;
+            __threadfence_system();
+        }
+        __syncthreads();
+        if (threadIdx.x == 0)
+            for (int r = 0; r < st.peer_world; ++r) atomicAdd_system(st.peer_arrivals[r] + st.peer_rank, 1ULL);
+    }
     if (p == 0 && valid)
     {
         st.cur[i]         = cur;

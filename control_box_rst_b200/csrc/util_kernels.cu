@@ -107,7 +107,37 @@ __global__ void fillPinnedKernel(const double* __restrict__ xref, double* __rest
 
 inline int blocksFor(int B) { return (B + 127) / 128; }
 
+// b200sqp_peer_wait: one thread per rank spins (bounded by `timeout_ns` of %globaltimer) until that rank's arrival counter in
+// OUR memory reaches `expected`, i.e. until all of its thread blocks have stored their chi2 of this solve into our gather buffer.
+__global__ void peerWaitKernel(const volatile unsigned long long* arrivals, int world, unsigned long long expected, unsigned long long timeout_ns,
+                               int* timed_out)
+{
+    const int r = threadIdx.x;
+    if (r < world)
+    {
+        unsigned long long t0, now;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+        while (arrivals[r] < expected)
+        {
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
+            if (now - t0 > timeout_ns)
+            {
+                *timed_out = 1;
+                break;
+            }
+            __nanosleep(100);
+        }
+    }
+    __threadfence_system();
+}
+
 }  // namespace
+
+void launchPeerWait(const unsigned long long* arrivals, int world, unsigned long long expected, unsigned long long timeout_ns, int* timed_out,
+                    cudaStream_t st)
+{
+    peerWaitKernel<<<1, 32, 0, st>>>(arrivals, world, expected, timeout_ns, timed_out);
+}
 
 void launchPack(const double* params, int n, const int* ref_of_internal, int slots, const double* pinned, double* z, const int* cur, double* z_alt,
                 int B, int S, cudaStream_t st)

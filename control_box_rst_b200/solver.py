@@ -27,6 +27,7 @@ ABI_SYMBOLS = [
     "b200sqp_solve_async", "b200sqp_synchronize", "b200sqp_step", "b200sqp_evaluate", "b200sqp_get_statistics", "b200sqp_get_chi2_trace",
     "b200sqp_last_solve_ms", "b200sqp_launch_count", "b200sqp_device_pointers", "b200sqp_set_stream", "b200sqp_set_threads_per_instance",
     "b200sqp_set_phase_profile", "b200sqp_get_phase_cycles", "b200sqp_final_constraint_indices",
+    "b200sqp_peer_export", "b200sqp_peer_attach", "b200sqp_peer_wait", "b200sqp_peer_gathered", "b200sqp_peer_detach", "b200sqp_peer_status",
 ]
 
 
@@ -261,6 +262,34 @@ class BatchedLevenbergMarquardt:
         out = np.zeros(4)
         _check(self._lib.b200sqp_get_phase_cycles(self._h, _d(out)))
         return dict(zip(("linearize", "factor_solve", "trial", "control"), out.tolist()))
+
+    # -- fused stop-test gather over NVLink peer memory (one process per GPU) ---------------------------------------------------
+    def peer_export(self, world, rank):
+        """-> 64-byte CUDA IPC handle of this rank's gather buffer (bytes)"""
+        buf = C.create_string_buffer(64)
+        _check(self._lib.b200sqp_peer_export(self._h, C.c_int32(world), C.c_int32(rank), buf))
+        return buf.raw
+
+    def peer_attach(self, handles):
+        """handles: list of the 64-byte IPC handles of all ranks, in rank order"""
+        blob = b"".join(handles)
+        _check(self._lib.b200sqp_peer_attach(self._h, C.c_char_p(blob)))
+
+    def peer_wait(self):
+        _check(self._lib.b200sqp_peer_wait(self._h))
+
+    def peer_gathered_ptr(self):
+        p = C.c_void_p()
+        _check(self._lib.b200sqp_peer_gathered(self._h, C.byref(p)))
+        return p.value
+
+    def peer_timed_out(self):
+        t = C.c_int32(0)
+        _check(self._lib.b200sqp_peer_status(self._h, C.byref(t)))
+        return bool(t.value)
+
+    def peer_detach(self):
+        _check(self._lib.b200sqp_peer_detach(self._h))
 
     def set_stream(self, cuda_stream):
         _check(self._lib.b200sqp_set_stream(self._h, C.c_void_p(cuda_stream)))

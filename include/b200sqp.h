@@ -203,6 +203,24 @@ int b200sqp_launch_count(b200sqp_handle h, int64_t* launches);
 /* raw device pointers for zero-copy interop (torch / NCCL all-gather of the stop-test residuals): chi2 [batch] doubles,
  * status [batch] int32, x0 [batch*nx] doubles.  Valid until destroy. */
 int b200sqp_device_pointers(b200sqp_handle h, void** chi2, void** status, void** x0);
+/* Fused stop-test exchange over NVLink peer memory (one process per GPU on one NVSwitch box).  Replaces the
+ * separate all-gather launch after each solve: once attached, the LM kernel of every rank stores its per-instance chi2 directly
+ * into every rank's gather buffer (peer stores) and signals arrival; b200sqp_peer_wait (stream-ordered, bounded spin) returns once
+ * all ranks' values of the last solve are present in this rank's buffer.
+ *   1. every rank: b200sqp_peer_export -> 64-byte CUDA IPC handle of its gather buffer
+ *   2. exchange the handles (e.g. torch.distributed all_gather), every rank: b200sqp_peer_attach(all handles in rank order)
+ *   3. per step: b200sqp_solve_async; b200sqp_peer_wait; read gathered[world*batch] (global instance order) via b200sqp_peer_gathered
+ * Equal `batch` on all ranks.  world <= 8. */
+#define B200SQP_IPC_HANDLE_BYTES 64
+int b200sqp_peer_export(b200sqp_handle h, int32_t world, int32_t rank, void* ipc_handle_out /*[64]*/);
+int b200sqp_peer_attach(b200sqp_handle h, const void* ipc_handles /*[world*64], rank order; own entry ignored*/);
+/* enqueue the bounded wait for the gathered chi2 of the last solve; returns B200SQP_ERR_CUDA from a later call if it timed out */
+int b200sqp_peer_wait(b200sqp_handle h);
+/* device pointer to this rank's gathered chi2 of the last solve, [world*batch] doubles */
+int b200sqp_peer_gathered(b200sqp_handle h, void** chi2_all);
+/* synchronises the stream and reports whether any b200sqp_peer_wait since attach hit its 2 s bound (a rank that never arrived) */
+int b200sqp_peer_status(b200sqp_handle h, int32_t* timed_out);
+int b200sqp_peer_detach(b200sqp_handle h);
 /* tuning knob: cooperating threads per instance in the LM kernel (1, 2, 4, 8; 0 = choose from the batch size) */
 int b200sqp_set_threads_per_instance(b200sqp_handle h, int32_t threads);
 /* measurement aid: when enabled, thread 0 of every thread block of the LM kernel accumulates clock64() per phase; get returns the
