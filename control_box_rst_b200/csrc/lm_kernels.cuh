@@ -33,7 +33,7 @@ struct FalseTag
     static constexpr bool value = false;
 };
 
-template <class M, int DEFECT, int VT, int T>
+template <class M, int DEFECT, int VT, int T, class F>
 __global__ void __launch_bounds__(32 * T) lmSolveKernel(const __grid_constant__ DeviceOcp P, const __grid_constant__ DeviceState st, int iterations)
 {
     using Dm = Dim<M, VT>;
@@ -124,8 +124,8 @@ __global__ void __launch_bounds__(32 * T) lmSolveKernel(const __grid_constant__ 
             for (int j = 0; j < NX; ++j) xn_last[j] = zp[(size_t)(XO + j) * TILE];
         }
         if (T > 1) __syncthreads();  // boundary states are read before any neighbour writes its perturbed copy back
-        NormalEquationSink<M, VT> sink(P, D, E, gg, ka, kb);
-        if (do_lin) linearizeSweep<M, DEFECT, VT>(P, w, z, x0p, xrefp, ka, kb, xn_last, sink);
+        NormalEquationSink<M, VT, F> sink(P, D, E, gg, ka, kb);
+        if (do_lin) linearizeSweep<M, DEFECT, VT, F>(P, w, z, x0p, xrefp, ka, kb, xn_last, sink);
         if (T > 1)
         {
             __syncthreads();  // all blocks stored; now the chunk-start contributions can be added to the neighbour's last block
@@ -258,7 +258,7 @@ __global__ void __launch_bounds__(32 * T) lmSolveKernel(const __grid_constant__ 
         {
             const bool do_trial = valid && (s_flags[g] & F_ACTIVE) && !step_small;
             double part         = 0.0;
-            if (do_trial) part = trialChi2<M, DEFECT, VT>(P, w, st.z[s_cur[g]] + zoff, dl, st.z[s_cur[g] ^ 1] + zoff, x0p, xrefp, ka, kb);
+            if (do_trial) part = trialChi2<M, DEFECT, VT, F>(P, w, st.z[s_cur[g]] + zoff, dl, st.z[s_cur[g] ^ 1] + zoff, x0p, xrefp, ka, kb);
             s_red[0][p][g] = part;
         }
         __syncthreads();
@@ -380,13 +380,25 @@ __global__ void __launch_bounds__(32) evaluateKernel(const __grid_constant__ Dev
     MaterializeSink<M, VT> sink{P, values ? values + i : nullptr, jac ? jac + i : nullptr, value_rows, jac_pos, v_count, j_count};
     using Dm          = Dim<M, VT>;
     const size_t tile = i >> 5, lane = i & 31;
-    linearizeSweep<M, DEFECT, VT>(P, w, st.z[st.cur[i]] + tile * ((size_t)P.K * Dm::NB * TILE) + lane, st.x0 + tile * ((size_t)Dm::NX * TILE) + lane,
+    linearizeSweep<M, DEFECT, VT, FeatAll>(P, w, st.z[st.cur[i]] + tile * ((size_t)P.K * Dm::NB * TILE) + lane, st.x0 + tile * ((size_t)Dm::NX * TILE) + lane,
                                   st.xref + tile * ((size_t)Dm::NX * TILE) + lane, 0, P.K, nullptr, sink);
 }
 
 // Cooperating threads per instance: small batches are latency bound (one warp per SM would leave the machine idle), so the
 // horizon is split T ways; once a batch alone fills the SMs with warps T = 1 is the most work-efficient mapping.
 // MAXT bounds the variants that get compiled for a (model, defect, grid) combination.
+template <class M, int DEFECT, int VT, int MAXT, class F>
+void launchSolveT(const DeviceOcp& P, const DeviceState& st, int iterations, int T, int blocks, cudaStream_t stream)
+{
+    if constexpr (MAXT >= 8)
+        if (T >= 8) return (void)lmSolveKernel<M, DEFECT, VT, 8, F><<<blocks, 256, 0, stream>>>(P, st, iterations);
+    if constexpr (MAXT >= 4)
+        if (T >= 4) return (void)lmSolveKernel<M, DEFECT, VT, 4, F><<<blocks, 128, 0, stream>>>(P, st, iterations);
+    if constexpr (MAXT >= 2)
+        if (T >= 2) return (void)lmSolveKernel<M, DEFECT, VT, 2, F><<<blocks, 64, 0, stream>>>(P, st, iterations);
+    lmSolveKernel<M, DEFECT, VT, 1, F><<<blocks, 32, 0, stream>>>(P, st, iterations);
+}
+
 template <class M, int DEFECT, int VT, int MAXT>
 void launchSolve(const DeviceOcp& P, const DeviceState& st, int iterations, int threads_per_instance, cudaStream_t stream)
 {
@@ -400,13 +412,13 @@ void launchSolve(const DeviceOcp& P, const DeviceState& st, int iterations, int 
         while (T < 8 && P.K / (2 * T) >= 3) T *= 2;
     }
     if (T > MAXT) T = MAXT;
-    if constexpr (MAXT >= 8)
-        if (T >= 8) return (void)lmSolveKernel<M, DEFECT, VT, 8><<<blocks, 256, 0, stream>>>(P, st, iterations);
-    if constexpr (MAXT >= 4)
-        if (T >= 4) return (void)lmSolveKernel<M, DEFECT, VT, 4><<<blocks, 128, 0, stream>>>(P, st, iterations);
-    if constexpr (MAXT >= 2)
-        if (T >= 2) return (void)lmSolveKernel<M, DEFECT, VT, 2><<<blocks, 64, 0, stream>>>(P, st, iterations);
-    lmSolveKernel<M, DEFECT, VT, 1><<<blocks, 32, 0, stream>>>(P, st, iterations);
+    // lean feature set: quadratic lsq stage cost, no state bounds, no pinned goal components, no final-stage constraint
+    bool lean = P.final_constraint == 0 && P.stage_cost == B200SQP_COST_QUADRATIC_LSQ;
+    for (int j = 0; j < M::NX; ++j) lean = lean && !P.x_bounded[j] && !P.xf_fixed[j];
+    if (lean)
+        launchSolveT<M, DEFECT, VT, MAXT, FeatLean>(P, st, iterations, T, blocks, stream);
+    else
+        launchSolveT<M, DEFECT, VT, MAXT, FeatAll>(P, st, iterations, T, blocks, stream);
 }
 
 template <class M, int DEFECT, int VT>
