@@ -563,6 +563,48 @@ int b200sqp_evaluate(b200sqp_handle h, double weight_eq, double weight_ineq, dou
     return B200SQP_OK;
 }
 
+int b200sqp_linearize_dynamics(int32_t dynamics, const double* dyn_params, int32_t method, int32_t batch, const double* x, const double* u,
+                               double* A, double* Bm, int32_t device)
+{
+    if (!dyn_params || !x || !u || batch < 1 || (method != 0 && method != 1) || (!A && !Bm)) return fail(B200SQP_ERR_INVALID, "bad argument");
+    b200sqp_ocp probe;
+    std::memset(&probe, 0, sizeof(probe));
+    int nx = 0, nu = 0;
+    if (!dynamicsDimensions(dynamics, nx, nu)) return fail(B200SQP_ERR_UNSUPPORTED, "unknown dynamics id (closed functor registry; no CPU fallback)");
+    int count = 0;
+    if (cudaGetDeviceCount(&count) != cudaSuccess || count == 0)
+    {
+        cudaGetLastError();
+        return fail(B200SQP_ERR_NO_DEVICE, "no CUDA device visible: the linearisation only exists as sm_100a kernels");
+    }
+    if (device < 0 || device >= count) return fail(B200SQP_ERR_INVALID, "device index out of range");
+    CUDA_TRY(cudaSetDevice(device));
+    DynParams dyn;
+    for (int i = 0; i < B200SQP_MAX_DYN_PARAMS; ++i) dyn.p[i] = dyn_params[i];
+    const size_t bx = sizeof(double) * (size_t)batch * nx, bu = sizeof(double) * (size_t)batch * nu;
+    const size_t bA = sizeof(double) * (size_t)batch * nx * nx, bB = sizeof(double) * (size_t)batch * nx * nu;
+    double *dx = nullptr, *du = nullptr, *dA = nullptr, *dB = nullptr;
+    cudaError_t e = cudaMalloc(&dx, bx);
+    if (e == cudaSuccess) e = cudaMalloc(&du, bu);
+    if (e == cudaSuccess && A) e = cudaMalloc(&dA, bA);
+    if (e == cudaSuccess && Bm) e = cudaMalloc(&dB, bB);
+    if (e == cudaSuccess) e = cudaMemcpy(dx, x, bx, cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) e = cudaMemcpy(du, u, bu, cudaMemcpyHostToDevice);
+    if (e == cudaSuccess)
+    {
+        launchLinearizeDynamics(dynamics, dyn, method, batch, dx, du, dA, dB, nullptr);
+        e = cudaGetLastError();
+    }
+    if (e == cudaSuccess && A) e = cudaMemcpy(A, dA, bA, cudaMemcpyDeviceToHost);
+    if (e == cudaSuccess && Bm) e = cudaMemcpy(Bm, dB, bB, cudaMemcpyDeviceToHost);
+    cudaFree(dx);
+    cudaFree(du);
+    cudaFree(dA);
+    cudaFree(dB);
+    if (e != cudaSuccess) return fail(B200SQP_ERR_CUDA, std::string("linearize_dynamics: ") + cudaGetErrorString(e));
+    return B200SQP_OK;
+}
+
 int b200sqp_get_statistics(b200sqp_handle h, int32_t* inner_passes, int32_t* rejects, int32_t* relinearizations, double* mu, double* rho)
 {
     int rc = checkHandle(h);

@@ -47,6 +47,11 @@ void launchInitTrajectories(const double* x0 /*[nx][S]*/, const double* xref /*[
 // u_0 of every instance -> [B][nu]
 void launchFirstControls(const double* z0, const double* z1, const int* cur, int nu, int slots, double* u0, int B, int S, cudaStream_t);
 
+// SystemDynamicsInterface::getLinearA/getLinearB by forward (method 0) or central (method 1) differences for B points (kernels_linearize.cu);
+// x [B][nx], u [B][nu], A [B][nx*nx] / Bm [B][nx*nu] column-major per point (either may be null); false = dynamics id not in the registry
+struct DynParams;
+bool launchLinearizeDynamics(int dynamics, const DynParams& dyn, int method, int B, const double* x, const double* u, double* A, double* Bm,
+                             cudaStream_t);
 // bounded spin on the arrival counters of the fused peer-memory gather (b200sqp_peer_wait)
 void launchPeerWait(const unsigned long long* arrivals, int world, unsigned long long expected, unsigned long long timeout_ns, int* timed_out,
                     cudaStream_t);

@@ -45,6 +45,15 @@ bool dynamicsDims(int id, Dim& d)
 
 }  // namespace
 
+bool dynamicsDimensions(int dynamics, int& nx, int& nu)
+{
+    Dim d;
+    if (!dynamicsDims(dynamics, d)) return false;
+    nx = d.nx;
+    nu = d.nu;
+    return true;
+}
+
 int buildStructure(const b200sqp_ocp& ocp, Structure& s, std::string& err)
 {
     s     = Structure();

@@ -63,6 +63,9 @@ struct Structure
     }
 };
 
+// (nx, nu) of a b200sqp_dynamics id; false if the id is not in the registry
+bool dynamicsDimensions(int dynamics, int& nx, int& nu);
+
 // Validates the descriptor against the closed registry and fills everything above.  Returns B200SQP_OK or an error code and
 // leaves a message in `err`.
 int buildStructure(const b200sqp_ocp& ocp, Structure& s, std::string& err);

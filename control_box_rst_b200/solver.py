@@ -27,7 +27,7 @@ ABI_SYMBOLS = [
     "b200sqp_solve_async", "b200sqp_synchronize", "b200sqp_step", "b200sqp_evaluate", "b200sqp_get_statistics", "b200sqp_get_chi2_trace",
     "b200sqp_last_solve_ms", "b200sqp_launch_count", "b200sqp_device_pointers", "b200sqp_set_stream", "b200sqp_set_threads_per_instance",
     "b200sqp_set_phase_profile", "b200sqp_get_phase_cycles", "b200sqp_final_constraint_indices",
-    "b200sqp_peer_export", "b200sqp_peer_attach", "b200sqp_peer_wait", "b200sqp_peer_gathered", "b200sqp_peer_detach", "b200sqp_peer_status",
+    "b200sqp_peer_export", "b200sqp_peer_attach", "b200sqp_peer_wait", "b200sqp_peer_gathered", "b200sqp_peer_detach", "b200sqp_peer_status", "b200sqp_linearize_dynamics",
 ]
 
 
@@ -106,6 +106,24 @@ def jacobian_pattern(ocp):
     col_ptr, row_idx = np.zeros(d.n_params + 1, np.int32), np.zeros(d.nnz_jacobian, np.int32)
     _check(load_library().b200sqp_jacobian_pattern(C.byref(ocp), _i(col_ptr), _i(row_idx)))
     return col_ptr, row_idx
+
+
+def linearize_dynamics(dynamics, dyn_params, x, u, method="forward", device=0):
+    """SystemDynamicsInterface::getLinearA / getLinearB for a batch of points on the device.
+    x [B, nx], u [B, nu] -> A [B, nx, nx], B [B, nx, nu]; method 'forward' (the reference's default) or 'central'."""
+    nx, nu = abi.DYN_DIMS[dynamics]
+    x = np.ascontiguousarray(x, np.float64).reshape(-1, nx)
+    u = np.ascontiguousarray(u, np.float64).reshape(-1, nu)
+    B = x.shape[0]
+    assert u.shape[0] == B
+    p = np.zeros(abi.MAX_DYN_PARAMS)
+    p[:len(dyn_params)] = dyn_params
+    A = np.zeros((B, nx, nx))
+    Bm = np.zeros((B, nu, nx))
+    _check(load_library().b200sqp_linearize_dynamics(C.c_int32(dynamics), _d(p), C.c_int32({"forward": 0, "central": 1}[method]), C.c_int32(B),
+                                                      _d(x), _d(u), _d(A), _d(Bm), C.c_int32(device)))
+    # the library writes column-major blocks per point
+    return A.transpose(0, 2, 1).copy(), Bm.transpose(0, 2, 1).copy()
 
 
 class BatchedLevenbergMarquardt:

@@ -189,6 +189,15 @@ int b200sqp_step(b200sqp_handle h, const b200sqp_lm_options* opts, int32_t cold_
  * Like the reference, evaluating the Jacobian perturbs the parameters in place (+d,-2d,+d; edge_interface.cpp:78-85). */
 int b200sqp_evaluate(b200sqp_handle h, double weight_eq, double weight_ineq, double weight_bounds, double* values, double* jac_values);
 
+/* Numerical linearisation of the system dynamics at `batch` points, A_i = df/dx, B_i = df/du at (x_i, u_i):
+ * SystemDynamicsInterface::getLinearA / getLinearB (src/systems/src/system_dynamics_interface.cpp:33-59) with the reference's
+ * finite-difference rules, method 0 = ForwardDifferences (the reference's default, finite_differences.hpp:29-48), 1 =
+ * CentralDifferences (finite_differences.hpp:167-188); delta = 1e-9, in-place perturbation, no FMA contraction.
+ * Host pointers: x [batch*nx], u [batch*nu]; A [batch*nx*nx], B [batch*nx*nu] column-major per point, either may be NULL.
+ * Handle-less: `dynamics` is a b200sqp_dynamics id, dyn_params its parameters [B200SQP_MAX_DYN_PARAMS]. */
+int b200sqp_linearize_dynamics(int32_t dynamics, const double* dyn_params, int32_t method, int32_t batch, const double* x, const double* u,
+                               double* A, double* B, int32_t device);
+
 /* Per-instance LM bookkeeping of the last solve: [batch] each, host pointers, any may be NULL.
  * inner_passes = number of factorisations, rejects = rejected trial steps, relinearizations = Jacobian evaluations. */
 int b200sqp_get_statistics(b200sqp_handle h, int32_t* inner_passes, int32_t* rejects, int32_t* relinearizations, double* mu, double* rho);

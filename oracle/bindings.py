@@ -93,6 +93,19 @@ class _Checker:
             raise RuntimeError(f"{self.prefix}edge_table failed: {cnt}")
         return table[:cnt].copy()
 
+    def linearize(self, ocp, x, u, method="forward"):
+        """getLinearA / getLinearB of the descriptor's dynamics at one point -> A [nx, nx], B [nx, nu]"""
+        nx, nu = ocp.nx, ocp.nu
+        x = np.ascontiguousarray(x, np.float64)
+        u = np.ascontiguousarray(u, np.float64)
+        A, Bm = np.zeros((nx, nx)), np.zeros((nu, nx))
+        fn = getattr(self.lib, self.prefix + "linearize")
+        fn.restype = C.c_int
+        rc = fn(C.byref(ocp), C.c_int({"forward": 0, "central": 1}[method]), _d(x), _d(u), _d(A), _d(Bm))
+        if rc != 0:
+            raise RuntimeError(f"{self.prefix}linearize failed: {rc}")
+        return A.T.copy(), Bm.T.copy()  # the checkers write column-major
+
     def initial_params(self, ocp, x0, xref=None):
         n = self.dims(ocp).n_params
         x0 = np.ascontiguousarray(x0, np.float64)

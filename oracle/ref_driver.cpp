@@ -13,6 +13,7 @@
 #include <corbo-core/reference_trajectory.h>
 #include <corbo-core/time.h>
 #include <corbo-numerics/explicit_integrators.h>
+#include <corbo-numerics/finite_differences.h>
 #include <corbo-numerics/finite_differences_collocation.h>
 #include <corbo-optimal-control/functions/final_state_constraints.h>
 #include <corbo-optimal-control/functions/final_state_cost.h>
@@ -624,6 +625,32 @@ int corbo_ref_closed_loop(const b200sqp_ocp* d, const b200sqp_lm_options* o, con
 
 // The reference's known-answer solver tests (optimization/test/test_levenberg_marquardt_sparse.cpp:72-296, excluded from its build)
 // run against the compiled reference: SimpleOptimizationProblemWithCallbacks + LevenbergMarquardtSparse, 100 iterations.
+// the reference's own getLinearA / getLinearB with its ForwardDifferences (method 0, the default) or CentralDifferences (method 1)
+int corbo_ref_linearize(const b200sqp_ocp* d, int method, const double* x0, const double* u0, double* A, double* B)
+{
+    SystemDynamicsInterface::Ptr dyn = makeDynamics(*d);
+    if (!dyn) return -1;
+    if (method == 0)
+        dyn->setLinearizationMethod(std::make_shared<ForwardDifferences>());
+    else
+        dyn->setLinearizationMethod(std::make_shared<CentralDifferences>());
+    const int nx = d->nx, nu = d->nu;
+    Eigen::VectorXd x = Eigen::Map<const Eigen::VectorXd>(x0, nx), u = Eigen::Map<const Eigen::VectorXd>(u0, nu);
+    if (A)
+    {
+        Eigen::MatrixXd Am(nx, nx);
+        dyn->getLinearA(x, u, Am);
+        Eigen::Map<Eigen::MatrixXd>(A, nx, nx) = Am;  // column-major
+    }
+    if (B)
+    {
+        Eigen::MatrixXd Bm(nx, nu);
+        dyn->getLinearB(x, u, Bm);
+        Eigen::Map<Eigen::MatrixXd>(B, nx, nu) = Bm;
+    }
+    return 0;
+}
+
 int corbo_ref_known_answer(int case_id, int stage, double* x_out, double* expected, double* tol, int32_t* n_out)
 {
     SimpleOptimizationProblemWithCallbacks optim;

@@ -1230,6 +1230,57 @@ int sqp_oracle_solve_batch(const b200sqp_ocp* d, const b200sqp_lm_options* o, in
     return failures.load() == 0 ? 0 : -1;
 }
 
+// SystemDynamicsInterface::getLinearA / getLinearB (systems/src/system_dynamics_interface.cpp:33-59) over
+// ForwardDifferences::jacobian (numerics/include/corbo-numerics/finite_differences.hpp:29-48, method 0) or
+// CentralDifferences::jacobian (:167-188, method 1): in-place perturbation of a copy of x (A) or u (B), delta = 1e-9.
+// A [nx*nx], B [nx*nu] column-major.
+int sqp_oracle_linearize(const b200sqp_ocp* d, int method, const double* x0, const double* u0, double* A, double* B)
+{
+    Dyn f = makeDynamics(*d);
+    if (!f) return -1;
+    const int nx = d->nx, nu = d->nu;
+    constexpr double delta = 1e-9, ddelta = 2 * delta;
+    std::vector<double> f0(nx), f1(nx);
+    auto jac = [&](std::vector<double>& v, int dim, const std::function<void(double*)>& eval, double* J) {
+        if (method == 0)
+        {
+            constexpr double scalar = 1.0 / delta;
+            eval(f0.data());
+            for (int i = 0; i < dim; ++i)
+            {
+                v[i] += delta;
+                eval(f1.data());
+                v[i] += -delta;
+                for (int r = 0; r < nx; ++r) J[i * nx + r] = scalar * (f1[r] - f0[r]);
+            }
+        }
+        else
+        {
+            constexpr double scalar = 1.0 / ddelta;
+            for (int i = 0; i < dim; ++i)
+            {
+                v[i] += delta;
+                eval(f1.data());
+                v[i] += -ddelta;
+                eval(f0.data());
+                for (int r = 0; r < nx; ++r) J[i * nx + r] = scalar * (f1[r] - f0[r]);
+                v[i] += delta;
+            }
+        }
+    };
+    if (A)
+    {
+        std::vector<double> x(x0, x0 + nx);
+        jac(x, nx, [&](double* out) { f(x.data(), u0, out); }, A);
+    }
+    if (B)
+    {
+        std::vector<double> u(u0, u0 + nu);
+        jac(u, nu, [&](double* out) { f(x0, u.data(), out); }, B);
+    }
+    return 0;
+}
+
 int sqp_oracle_known_answer(int case_id, int stage, double* x_out, double* expected, double* tol, int32_t* n_out)
 {
     KnownAnswer c;

@@ -42,3 +42,24 @@ def dense_to_csc_values(J, col_ptr, row_idx):
     for c in range(len(col_ptr) - 1):
         out[col_ptr[c]:col_ptr[c + 1]] = J[row_idx[col_ptr[c]:col_ptr[c + 1]], c]
     return out
+
+
+# dynamics linearisation fixtures: name -> (descriptor builder, polynomial?)
+LINEARIZE_MODELS = {
+    "van_der_pol": (lambda: problems.van_der_pol(5, a=1.3), True),
+    "duffing": (lambda: problems.make_ocp(grid=abi.GRID_FD_UNIFORM, dynamics=abi.DYN_DUFFING, n_grid=5, dt=0.1, q=(1, 1), r=(0.1,),
+                                          dyn_params=(1.0, -1.0, 1.0)), True),
+    "simple_pendulum": (lambda: problems.make_ocp(grid=abi.GRID_FD_UNIFORM, dynamics=abi.DYN_SIMPLE_PENDULUM, n_grid=5, dt=0.1, q=(1, 1), r=(0.1,),
+                                                  dyn_params=(0.205, 0.34, 9.81, 0.25)), False),
+    "cart_pole": (lambda: problems.cart_pole_shooting(5), False),
+    "double_integrator": (lambda: problems.make_ocp(grid=abi.GRID_FD_UNIFORM, dynamics=abi.DYN_DOUBLE_INTEGRATOR, n_grid=5, dt=0.1, q=(1, 1), r=(0.1,),
+                                                    dyn_params=(2.0,)), True),
+    "unicycle": (lambda: problems.unicycle_time_optimal(5), False),
+    "quadrotor": (lambda: problems.quadrotor(5), False),
+}
+LINEARIZE_POINTS = 6
+
+
+def linearize_points(ocp, seed=17):
+    rng = np.random.default_rng(seed)
+    return rng.uniform(-1.5, 1.5, (LINEARIZE_POINTS, ocp.nx)), rng.uniform(-1.0, 1.0, (LINEARIZE_POINTS, ocp.nu))

@@ -60,6 +60,19 @@ def main():
             trace_chi2=np.array([e[1] for e in tr["events"]]),
         )
         print(f"{name}: n={d.n_params} m={d.m} nnzJ={d.nnz_jacobian} chi2[0]={chi2[0]:.6g} events={tr['n_events']}")
+    if not only or "linearize" in only:
+        # SystemDynamicsInterface::getLinearA/getLinearB of the reference's own (and the two added) models, both FD rules
+        out = {}
+        for name, (make, _) in cases.LINEARIZE_MODELS.items():
+            ocp = make()
+            xs, us = cases.linearize_points(ocp)
+            for method in ("forward", "central"):
+                AB = [ref.linearize(ocp, xs[i], us[i], method) for i in range(len(xs))]
+                out[f"{name}_{method}_A"] = np.stack([a for a, _ in AB])
+                out[f"{name}_{method}_B"] = np.stack([b for _, b in AB])
+            out[f"{name}_x"], out[f"{name}_u"] = xs, us
+        np.savez_compressed(os.path.join(HERE, "linearize.npz"), **out)
+        print("linearize:", len(out), "arrays")
     if only:
         return
     ka = []
