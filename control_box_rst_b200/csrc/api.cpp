@@ -83,6 +83,7 @@ struct b200sqp_solver
     void* peer_local = nullptr;              // own buffer: [2*world*B] doubles, then [world] arrival counters, then 1 int timeout flag
     void* peer_mapped[MAX_PEERS] = {};       // cudaIpcOpenMemHandle results (null for own rank)
     unsigned long long peer_solves = 0;      // solves launched since attach
+    int* d_num_shift = nullptr;
     long long* d_phase_cycles = nullptr;
     int phase_blocks = 0;
     std::vector<void*> allocations;
@@ -414,6 +415,38 @@ int b200sqp_initialize_trajectories(b200sqp_handle h)
                            h->stream);
     h->launches += 1;
     CUDA_TRY(cudaGetLastError());
+    return B200SQP_OK;
+}
+
+int b200sqp_warm_start_shift(b200sqp_handle h, const double* x0_new, int32_t* num_shift)
+{
+    int rc = checkHandle(h);
+    if (rc) return rc;
+    if (!x0_new) return fail(B200SQP_ERR_INVALID, "x0_new is null");
+    if (h->s.ocp.grid != B200SQP_GRID_FD_UNIFORM)
+        return fail(B200SQP_ERR_UNSUPPORTED, "warm-start shifting is implemented for FiniteDifferencesGrid structures only");
+    const size_t bytes = sizeof(double) * (size_t)h->B * h->s.nx;
+    CUDA_TRY(cudaMemcpyAsync(h->d_x0_host_order, x0_new, bytes, cudaMemcpyHostToDevice, h->stream));
+    if (num_shift && !h->d_num_shift) CUDA_TRY(h->alloc(&h->d_num_shift, (size_t)h->B));
+    launchWarmStartShift(h->d_x0_host_order, h->st.x0, h->st.z[0], h->st.z[1], h->st.cur, h->s.K, h->s.nx, h->s.nu,
+                         num_shift ? h->d_num_shift : nullptr, h->B, h->stream);
+    h->launches += 1;
+    CUDA_TRY(cudaGetLastError());
+    // fixed goal components follow the reference (full_discretization_grid_base.cpp:102-106)
+    const int nb = h->s.nb, xo = h->s.nu + h->s.vt;
+    unsigned mask = 0;
+    for (int i = 0; i < h->s.nx; ++i)
+        if (h->s.xfFixed(i)) mask |= 1u << i;
+    if (mask)
+    {
+        launchFillPinned(h->st.xref, h->st.z[0], h->st.z[1], (h->s.K - 1) * nb + xo, h->s.K * nb, h->s.nx, mask, h->B, h->stream);
+        h->launches += 1;
+    }
+    if (num_shift)
+    {
+        CUDA_TRY(cudaMemcpyAsync(num_shift, h->d_num_shift, sizeof(int32_t) * h->B, cudaMemcpyDeviceToHost, h->stream));
+        CUDA_TRY(cudaStreamSynchronize(h->stream));
+    }
     return B200SQP_OK;
 }
 

@@ -52,6 +52,9 @@ void launchFirstControls(const double* z0, const double* z1, const int* cur, int
 struct DynParams;
 bool launchLinearizeDynamics(int dynamics, const DynParams& dyn, int method, int B, const double* x, const double* u, double* A, double* Bm,
                              cudaStream_t);
+// FullDiscretizationGridBase::warmStartShifting + findNearestState per instance, then x_seq.front() = x0_new (util_kernels.cu)
+void launchWarmStartShift(const double* x0_new /*[B][nx]*/, double* x0 /*tiled*/, double* z0, double* z1, const int* cur, int K, int nx, int nu,
+                          int* num_shift /*[B] or null*/, int B, cudaStream_t);
 // bounded spin on the arrival counters of the fused peer-memory gather (b200sqp_peer_wait)
 void launchPeerWait(const unsigned long long* arrivals, int world, unsigned long long expected, unsigned long long timeout_ns, int* timed_out,
                     cudaStream_t);

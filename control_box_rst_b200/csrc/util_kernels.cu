@@ -1,6 +1,7 @@
 // Layout kernels around the solver: host-order <-> instance-minor conversions, trajectory initialisation, first-control gather.
 // All are one-thread-per-instance (writes/reads of the instance-minor side coalesce; the host-order side is a short strided walk
 // through L1/L2) -- they move a few MB per solve and are not on the roofline-relevant path.
+#include "../../include/b200sqp.h"
 #include "launch.h"
 
 namespace b200sqp {
@@ -105,6 +106,103 @@ __global__ void fillPinnedKernel(const double* __restrict__ xref, double* __rest
         }
 }
 
+// Moving-horizon warm start of FullDiscretizationGridBase (full_discretization_grid_base.cpp): findNearestState (:285-318) picks
+// num_shift per instance (nearest of the first min(N-2, 20) states to the new measurement, l2 norm in Eigen's reduction order,
+// stop at the first non-improving state, 0 if the start did not move), warmStartShifting (:230-283) moves states and controls
+// forward by num_shift and extrapolates the tail linearly (x[idx] = x[idx-2] + 2 (x[idx-1] - x[idx-2]), controls repeated), then
+// update() overwrites the start with the measurement (:101).  x_seq[0] is the fixed start (x0 array), x_seq[k>=1] the x-part of
+// block k-1, u_seq[k] the u-part of block k.  One thread per instance, in place on the current parameter buffer.
+__device__ __forceinline__ double eigenNorm(const double* t, int n)
+{
+    // sqrt of Eigen's vectorised sum of squares: packets of two doubles, two accumulators, scalar tail (Eigen/src/Core/Redux.h)
+    const int aligned = (n / 2) * 2, aligned2 = (n / 4) * 4;
+    if (aligned == 0) return sqrt(t[0]);
+    double p0a = t[0], p0b = t[1];
+    if (aligned > 2)
+    {
+        double p1a = t[2], p1b = t[3];
+        for (int i = 4; i < aligned2; i += 4)
+        {
+            p0a += t[i];
+            p0b += t[i + 1];
+            p1a += t[i + 2];
+            p1b += t[i + 3];
+        }
+        p0a += p1a;
+        p0b += p1b;
+        if (aligned > aligned2)
+        {
+            p0a += t[aligned2];
+            p0b += t[aligned2 + 1];
+        }
+    }
+    double res = p0a + p0b;
+    for (int i = aligned; i < n; ++i) res += t[i];
+    return sqrt(res);
+}
+
+__global__ void warmStartShiftKernel(const double* __restrict__ x0_new /*[B][nx] host order*/, double* __restrict__ x0 /*tiled*/,
+                                     double* __restrict__ z0, double* __restrict__ z1, const int* __restrict__ cur, int K, int nx, int nu,
+                                     int* __restrict__ num_shift_out, int B)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= B) return;
+    const int nb = nu + nx, slots = K * nb, N = K + 1;
+    double* z = cur[i] ? z1 : z0;
+    auto X = [&](int k, int j) -> double& { return k == 0 ? x0[tiled(i, j, nx)] : z[tiled(i, (k - 1) * nb + nu + j, slots)]; };
+    auto U = [&](int k, int j) -> double& { return z[tiled(i, k * nb + j, slots)]; };
+    double xn[B200SQP_MAX_NX], sq[B200SQP_MAX_NX];
+    for (int j = 0; j < nx; ++j) xn[j] = x0_new[(size_t)i * nx + j];
+    auto dist = [&](int k) {
+        for (int j = 0; j < nx; ++j)
+        {
+            const double d = xn[j] - X(k, j);
+            sq[j]          = d * d;
+        }
+        return eigenNorm(sq, nx);
+    };
+    int shift               = 0;
+    const double first_dist = dist(0);
+    if (!(fabs(first_dist) < 1e-12))
+    {
+        const int lookahead = min((N - 1) - 1, 20);
+        double cache        = first_dist;
+        for (int k = 1; k <= lookahead; ++k)
+        {
+            const double d = dist(k);
+            if (d < cache)
+            {
+                cache = d;
+                shift = k;
+            }
+            else
+                break;
+        }
+    }
+    if (shift > 0 && shift <= N - 2)
+    {
+        for (int k = 0; k < N - shift; ++k)
+        {
+            const int idx = k + shift;
+            for (int j = 0; j < nx; ++j) X(k, j) = X(idx, j);
+            if (idx != N - 1)
+                for (int j = 0; j < nu; ++j) U(k, j) = U(idx, j);
+        }
+        int idx = N - shift;
+        for (int s = 0; s < shift; ++s, ++idx)
+        {
+            for (int j = 0; j < nx; ++j)
+            {
+                const double a = X(idx - 2, j), b = X(idx - 1, j);
+                X(idx, j)      = a + 2.0 * (b - a);
+            }
+            for (int j = 0; j < nu; ++j) U(idx - 1, j) = U(idx - 2, j);
+        }
+    }
+    for (int j = 0; j < nx; ++j) x0[tiled(i, j, nx)] = xn[j];  // the measured start always overwrites x_seq.front() (:101)
+    if (num_shift_out) num_shift_out[i] = shift;
+}
+
 inline int blocksFor(int B) { return (B + 127) / 128; }
 
 // b200sqp_peer_wait: one thread per rank spins (bounded by `timeout_ns` of %globaltimer) until that rank's arrival counter in
@@ -132,6 +230,12 @@ __global__ void peerWaitKernel(const volatile unsigned long long* arrivals, int 
 }
 
 }  // namespace
+
+void launchWarmStartShift(const double* x0_new, double* x0, double* z0, double* z1, const int* cur, int K, int nx, int nu, int* num_shift, int B,
+                          cudaStream_t st)
+{
+    warmStartShiftKernel<<<blocksFor(B), 128, 0, st>>>(x0_new, x0, z0, z1, cur, K, nx, nu, num_shift, B);
+}
 
 void launchPeerWait(const unsigned long long* arrivals, int world, unsigned long long expected, unsigned long long timeout_ns, int* timed_out,
                     cudaStream_t st)

@@ -27,7 +27,7 @@ ABI_SYMBOLS = [
     "b200sqp_solve_async", "b200sqp_synchronize", "b200sqp_step", "b200sqp_evaluate", "b200sqp_get_statistics", "b200sqp_get_chi2_trace",
     "b200sqp_last_solve_ms", "b200sqp_launch_count", "b200sqp_device_pointers", "b200sqp_set_stream", "b200sqp_set_threads_per_instance",
     "b200sqp_set_phase_profile", "b200sqp_get_phase_cycles", "b200sqp_final_constraint_indices",
-    "b200sqp_peer_export", "b200sqp_peer_attach", "b200sqp_peer_wait", "b200sqp_peer_gathered", "b200sqp_peer_detach", "b200sqp_peer_status", "b200sqp_linearize_dynamics",
+    "b200sqp_peer_export", "b200sqp_peer_attach", "b200sqp_peer_wait", "b200sqp_peer_gathered", "b200sqp_peer_detach", "b200sqp_peer_status", "b200sqp_linearize_dynamics", "b200sqp_warm_start_shift",
 ]
 
 
@@ -194,6 +194,14 @@ class BatchedLevenbergMarquardt:
 
     def initialize_trajectories(self):
         _check(self._lib.b200sqp_initialize_trajectories(self._h))
+
+    def warm_start_shift(self, x0_new):
+        """moving-horizon warm start on the device (FullDiscretizationGridBase::warmStartShifting per instance) -> num_shift [B]"""
+        x0_new = np.ascontiguousarray(x0_new, np.float64)
+        assert x0_new.shape == (self.batch, self.ocp.nx)
+        shifts = np.zeros(self.batch, np.int32)
+        _check(self._lib.b200sqp_warm_start_shift(self._h, _d(x0_new), _i(shifts)))
+        return shifts
 
     def set_params(self, params):
         params = np.ascontiguousarray(params, np.float64)

@@ -171,6 +171,13 @@ int b200sqp_get_params(b200sqp_handle h, double* params);
 /* FullDiscretizationGridBase::getFirstControlInput: u_0 of every instance, [batch*nu] */
 int b200sqp_get_first_controls(b200sqp_handle h, double* u0);
 
+/* Moving-horizon warm start between two MPC steps, on the device: for every instance
+ * FullDiscretizationGridBase::findNearestState + warmStartShifting (full_discretization_grid_base.cpp:230-318) against the new
+ * measurement x0_new [batch*nx] (host pointer), then the start state is replaced by the measurement (:101) and fixed goal components
+ * by the reference (:102-106).  num_shift [batch] (host, may be NULL) receives the shift each instance applied.
+ * FiniteDifferencesGrid structures only (B200SQP_ERR_UNSUPPORTED otherwise).  Follow with b200sqp_solve / b200sqp_step(cold_start=0). */
+int b200sqp_warm_start_shift(b200sqp_handle h, const double* x0_new, int32_t* num_shift);
+
 /* ---- the hot path ------------------------------------------------------------------------------------------------------ */
 /* LevenbergMarquardtSparse::solve (levenberg_marquardt_sparse.cpp:44-220) for all instances, entirely on the device:
  * opts->iterations outer passes each; new_run=1 resets the penalty weights, 0 adapts them (:83-86).

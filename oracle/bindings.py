@@ -223,6 +223,30 @@ class Reference(_Checker):
             raise RuntimeError(f"corbo_ref_closed_loop failed: {rc}")
         return u, x
 
+    def closed_loop_shift(self, ocp, opts, x0, steps):
+        """closed loop with the grid's moving-horizon warm start (warmStartShifting) active"""
+        x0 = np.ascontiguousarray(x0, np.float64)
+        u = np.zeros((steps, ocp.nu))
+        x = np.zeros((steps + 1, ocp.nx))
+        f = self.lib.corbo_ref_closed_loop_shift
+        f.restype = C.c_int
+        rc = f(C.byref(ocp), C.byref(opts), _d(x0), C.c_int(steps), _d(u), _d(x))
+        if rc != 0:
+            raise RuntimeError(f"corbo_ref_closed_loop_shift failed: {rc}")
+        return u, x
+
+    def warm_start_shift(self, ocp, x0_old, x0_new, params, xref=None):
+        """FullDiscretizationGridBase::warmStartShifting of the compiled reference on one trajectory -> shifted parameters"""
+        params = np.ascontiguousarray(params, np.float64)
+        out = np.zeros_like(params)
+        f = self.lib.corbo_ref_warm_start_shift
+        f.restype = C.c_int
+        rc = f(C.byref(ocp), _d(np.ascontiguousarray(x0_old, np.float64)), _d(np.ascontiguousarray(x0_new, np.float64)),
+               None if xref is None else _d(np.ascontiguousarray(xref, np.float64)), _d(params), _d(out))
+        if rc != 0:
+            raise RuntimeError(f"corbo_ref_warm_start_shift failed: {rc}")
+        return out
+
     def known_answer(self, case_id, stage=0):
         return _known_answer(self.lib, "corbo_ref_known_answer", case_id, stage)
 

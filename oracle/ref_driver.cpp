@@ -623,6 +623,55 @@ int corbo_ref_closed_loop(const b200sqp_ocp* d, const b200sqp_lm_options* o, con
     return 0;
 }
 
+// Moving-horizon warm start of the reference grid (FullDiscretizationGridBase::update -> warmStartShifting + findNearestState,
+// full_discretization_grid_base.cpp:95-107,230-318), isolated: initialise at x0_old, overwrite the parameters with params_in, run the
+// grid update for a new run at x0_new with warm start active, return the shifted parameters.
+int corbo_ref_warm_start_shift(const b200sqp_ocp* d, const double* x0_old, const double* x0_new, const double* xref, const double* params_in,
+                               double* params_out)
+{
+    b200sqp_lm_options o = {0, 2, 2, 2, 1, 1, 1, 500, 500, 500};
+    RefOcp r;
+    if (!buildOcp(*d, o, r)) return -1;
+    auto* grid = dynamic_cast<FullDiscretizationGridBase*>(r.grid.get());
+    if (!grid) return -4;
+    grid->setWarmStart(true);
+    if (!prepare(r, *d, x0_old, xref, true, nullptr)) return -2;
+    const int n = r.problem->getParameterDimension();
+    r.problem->setParameterVector(Eigen::Map<const Eigen::VectorXd>(params_in, n));
+    if (!prepare(r, *d, x0_new, xref, true, nullptr)) return -3;
+    Eigen::VectorXd p(n);
+    r.problem->getParameterVector(p);
+    std::memcpy(params_out, p.data(), sizeof(double) * n);
+    return 0;
+}
+
+// Closed loop like corbo_ref_closed_loop, with the grid's moving-horizon warm start switched on (setWarmStart(true))
+int corbo_ref_closed_loop_shift(const b200sqp_ocp* d, const b200sqp_lm_options* o, const double* x0, int steps, double* u_applied, double* x_closed)
+{
+    RefOcp r;
+    if (!buildOcp(*d, *o, r)) return -1;
+    auto* grid = dynamic_cast<FullDiscretizationGridBase*>(r.grid.get());
+    if (!grid) return -4;
+    grid->setWarmStart(true);
+    StaticReference xref(Eigen::VectorXd::Zero(d->nx));
+    ZeroReference uref(d->nu);
+    Eigen::VectorXd x = Eigen::Map<const Eigen::VectorXd>(x0, d->nx);
+    IntegratorExplicitRungeKutta4 rk4;
+    std::memcpy(x_closed, x.data(), sizeof(double) * d->nx);
+    for (int s = 0; s < steps; ++s)
+    {
+        if (!r.ocp->compute(x, xref, uref, nullptr, Time(s * d->dt_ref), true)) return -2;
+        Eigen::VectorXd u(d->nu);
+        if (!r.ocp->getFirstControlInput(u)) return -3;
+        std::memcpy(u_applied + (size_t)s * d->nu, u.data(), sizeof(double) * d->nu);
+        Eigen::VectorXd xn(d->nx);
+        rk4.solveIVP(x, u, d->dt_ref, *r.dynamics, xn);
+        x = xn;
+        std::memcpy(x_closed + (size_t)(s + 1) * d->nx, x.data(), sizeof(double) * d->nx);
+    }
+    return 0;
+}
+
 // The reference's known-answer solver tests (optimization/test/test_levenberg_marquardt_sparse.cpp:72-296, excluded from its build)
 // run against the compiled reference: SimpleOptimizationProblemWithCallbacks + LevenbergMarquardtSparse, 100 iterations.
 // the reference's own getLinearA / getLinearB with its ForwardDifferences (method 0, the default) or CentralDifferences (method 1)

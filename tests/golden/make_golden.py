@@ -73,6 +73,27 @@ def main():
             out[f"{name}_x"], out[f"{name}_u"] = xs, us
         np.savez_compressed(os.path.join(HERE, "linearize.npz"), **out)
         print("linearize:", len(out), "arrays")
+    if not only or "warm_start" in only:
+        # moving-horizon warm start of the reference grid, isolated (corbo_ref_warm_start_shift) and inside the closed loop
+        ocp = problems.van_der_pol(12)
+        rng = np.random.default_rng(4)
+        x0_old, x0_new, p_in, p_out = [], [], [], []
+        for trial in range(12):
+            xo = rng.uniform(-2, 2, 2)
+            p = ref.initial_params(ocp, xo, None) + rng.uniform(-0.02, 0.02, ref.dims(ocp).n_params)
+            x_idx, _, _ = ref.vertex_indices(ocp)
+            s = trial % 5  # aim at the s-th state of the old trajectory (0 = start did not move at all for trial 0)
+            target = xo if s == 0 else p[x_idx[s]:x_idx[s] + 2]
+            xn = target.copy() if trial == 0 else target + rng.uniform(-0.01, 0.01, 2)
+            x0_old.append(xo)
+            x0_new.append(xn)
+            p_in.append(p)
+            p_out.append(ref.warm_start_shift(ocp, xo, xn, p))
+        ocp20 = problems.van_der_pol(20)
+        u, x = ref.closed_loop_shift(ocp20, abi.LmOptions.defaults(), np.array([1.0, 0.5]), 15)
+        np.savez_compressed(os.path.join(HERE, "warm_start_shift.npz"), x0_old=np.array(x0_old), x0_new=np.array(x0_new), p_in=np.array(p_in),
+                            p_out=np.array(p_out), loop_u=u, loop_x=x)
+        print("warm_start: closed loop with shifting u[:3] =", u[:3, 0])
     if only:
         return
     ka = []

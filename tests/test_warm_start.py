@@ -1,0 +1,116 @@
+"""the moving-horizon warm start between MPC steps (FullDiscretizationGridBase::findNearestState +
+warmStartShifting, full_discretization_grid_base.cpp:230-318).  tests/golden/warm_start_shift.npz holds the compiled reference's
+shifted parameter vectors and a 15-step closed loop with the warm start active; the numpy restatement (oracle/warm_start.py) is pinned
+against it on CPU, the device path (b200sqp_warm_start_shift) against both on the GPU."""
+import os
+
+import numpy as np
+import pytest
+
+from control_box_rst_b200 import problems, solver
+from oracle import warm_start
+
+GOLD = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "warm_start_shift.npz"))
+
+
+def _split(ocp, p, x0):
+    """reference parameter vector -> x_seq [N, nx] (incl. start and xf), u_seq [N-1, nu]"""
+    x_idx, u_idx, _ = solver.vertex_indices(ocp)
+    N = ocp.n_grid
+    x = np.zeros((N, ocp.nx))
+    x[0] = x0
+    for k in range(1, N):
+        x[k] = p[x_idx[k]:x_idx[k] + ocp.nx]
+    u = np.stack([p[u_idx[k]:u_idx[k] + ocp.nu] for k in range(N - 1)])
+    return x, u
+
+
+def _join(ocp, x, u):
+    x_idx, u_idx, _ = solver.vertex_indices(ocp)
+    p = np.zeros(solver.dims_of(ocp).n_params)
+    for k in range(1, ocp.n_grid):
+        p[x_idx[k]:x_idx[k] + ocp.nx] = x[k]
+    for k in range(ocp.n_grid - 1):
+        p[u_idx[k]:u_idx[k] + ocp.nu] = u[k]
+    return p
+
+
+def test_restatement_matches_reference_fixture():
+    ocp = problems.van_der_pol(12)
+    shifts = []
+    for xo, xn, p_in, p_out in zip(GOLD["x0_old"], GOLD["x0_new"], GOLD["p_in"], GOLD["p_out"]):
+        x, u = _split(ocp, p_in, xo)
+        xs, us, s = warm_start.warm_start_shift(x, u, xn)
+        shifts.append(s)
+        assert np.array_equal(_join(ocp, xs, us), p_out)  # pure copies and a + 2 (b - a): bit-exact
+    assert set(shifts) >= {0, 1, 2, 3}, shifts  # the fixture exercises no shift, single and multiple shifts
+
+
+@pytest.mark.gpu
+def test_device_shift_matches_reference_fixture():
+    ocp = problems.van_der_pol(12)
+    B = len(GOLD["x0_old"])
+    lm = solver.BatchedLevenbergMarquardt(ocp, B)
+    lm.set_problem_data(GOLD["x0_old"], None)
+    lm.initialize_trajectories()
+    lm.set_params(GOLD["p_in"])
+    shifts = lm.warm_start_shift(GOLD["x0_new"])
+    assert np.array_equal(lm.get_params(), GOLD["p_out"])
+    want = [warm_start.find_nearest_state(_split(ocp, p, xo)[0], xn) for xo, xn, p in zip(GOLD["x0_old"], GOLD["x0_new"], GOLD["p_in"])]
+    assert np.array_equal(shifts, np.array(want, np.int32))
+    lm.clear()
+
+
+@pytest.mark.gpu
+def test_closed_loop_with_device_warm_start_matches_reference_controller():
+    """15 MPC steps with setWarmStart(true) in the reference (shift, then solve from the shifted trajectory) against
+    b200sqp_warm_start_shift + b200sqp_step(cold_start=0); plant = one RK4 step of the same dynamics."""
+    ocp = problems.van_der_pol(20)
+    lm = solver.BatchedLevenbergMarquardt(ocp, 1)
+    lm.setIterations(10)
+
+    def f(x, u):
+        return np.array([x[1], -1.0 * (x[0] * x[0] - 1) * x[1] - x[0] + u[0]])
+
+    x = np.array([1.0, 0.5])
+    dt = ocp.dt_ref
+    total_shift = 0
+    for s in range(15):
+        if s > 0:
+            total_shift += int(lm.warm_start_shift(x[None, :])[0])
+        lm.step(x[None, :], None, cold_start=(s == 0))
+        u = lm.get_first_controls()[0]
+        np.testing.assert_allclose(u, GOLD["loop_u"][s], rtol=0, atol=2e-6)
+        k1 = f(x, u) * dt
+        k2 = f(x + k1 / 2.0, u) * dt
+        k3 = f(x + k2 / 2.0, u) * dt
+        k4 = f(x + k3, u) * dt
+        x = x + (k1 + 2.0 * k2 + 2.0 * k3 + k4) / 6.0
+        np.testing.assert_allclose(x, GOLD["loop_x"][s + 1], rtol=0, atol=2e-6)
+    assert total_shift >= 10  # the horizon really moved
+    lm.clear()
+
+
+@pytest.mark.gpu
+def test_device_shift_large_batch_is_per_instance():
+    ocp = problems.van_der_pol(50)
+    B = 4096
+    x0, _ = problems.instance_data(ocp, B, seed=9)
+    lm = solver.BatchedLevenbergMarquardt(ocp, B)
+    lm.setIterations(10)
+    lm.set_problem_data(x0, None)
+    lm.initialize_trajectories()
+    lm.solve(new_run=True)
+    p = lm.get_params()
+    x_idx, _, _ = solver.vertex_indices(ocp)
+    x1 = p[:, x_idx[1]:x_idx[1] + 2]
+    x0_new = np.where((np.arange(B) % 2 == 0)[:, None], x1, x0)  # every other instance moved exactly one state ahead
+    shifts = lm.warm_start_shift(x0_new)
+    assert np.array_equal(shifts[1::2], np.zeros(B // 2, np.int32)) and shifts[0::2].min() >= 1
+    after = lm.get_params()
+    assert np.array_equal(after[1::2], p[1::2])  # untouched where the start did not move
+    idx = np.arange(0, B, 2)[:16]
+    for i in idx:
+        xs, us, s = warm_start.warm_start_shift(*_split(ocp, p[i], x0[i]), x0_new[i])
+        assert s == shifts[i] and np.array_equal(_join(ocp, xs, us), after[i])
+    lm.clear()
