@@ -350,6 +350,24 @@ def main_b200(args):
     e2e_value = B * world * iterations * args.steps / (e2e_ms * 1e-3)
     h2d = 2 * B * ocp.nx * 8
     d2h = B * n * 8 + B * 8 + B * 4
+
+    # ---- the closed-loop front-end: measured states in, first controls out (b200sqp_mpc_step, cold start) -----------------------------
+    h_u0 = torch.empty((B, ocp.nu), dtype=torch.float64).pin_memory()
+
+    def mpc_step():
+        lm.mpc_step_raw(0, h_x0.data_ptr(), h_xref.data_ptr(), h_u0.data_ptr(), h_chi2.data_ptr(), h_status.data_ptr())
+        exchange()
+
+    for _ in range(2):
+        mpc_step()
+    barrier()
+    mpc_ms, _ = timed(mpc_step, args.steps)
+    barrier()
+    t = torch.tensor([mpc_ms], dtype=torch.float64, device=f"cuda:{local_rank}")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    mpc_ms = float(t[0])
+    mpc_value = B * world * iterations * args.steps / (mpc_ms * 1e-3)
     stats = lm.statistics()
 
     if rank == 0:
@@ -382,6 +400,9 @@ def main_b200(args):
                        "wall_s_timed_region_incl_flush": wall},
             "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "ms_per_step": e2e_ms / args.steps},
+            "e2e_mpc_step": {"value": mpc_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": B * ocp.nu * 8 + B * 8 + B * 4,
+                             "ms_per_step": mpc_ms / args.steps,
+                             "note": "b200sqp_mpc_step: measured states in, first controls + chi2 + status out, trajectories stay in HBM"},
             "gpu_launches": int(launches),
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "traffic_source": traffic_src,
                          "kernel": "lmSolve", "kernel_ms": kernel_ms / args.steps, "algorithmic_bytes_per_launch": alg_bytes,

@@ -556,6 +556,37 @@ int b200sqp_step(b200sqp_handle h, const b200sqp_lm_options* opts, int32_t cold_
     return B200SQP_OK;
 }
 
+int b200sqp_mpc_step(b200sqp_handle h, const b200sqp_lm_options* opts, int32_t mode, const double* x0, const double* xref, double* u0_out,
+                     double* chi2_out, int32_t* status_out)
+{
+    if (mode < 0 || mode > 2) return fail(B200SQP_ERR_INVALID, "mode must be 0 (cold), 1 (keep) or 2 (shift)");
+    if (!u0_out) return fail(B200SQP_ERR_INVALID, "u0_out is null");
+    int rc;
+    if (mode == 2)
+    {
+        // the shift needs the previous start state, so it runs before the start/reference are replaced
+        rc = b200sqp_warm_start_shift(h, x0, nullptr);
+        if (rc) return rc;
+    }
+    rc = b200sqp_set_problem_data(h, x0, xref);
+    if (rc) return rc;
+    if (mode == 0)
+    {
+        rc = b200sqp_initialize_trajectories(h);
+        if (rc) return rc;
+    }
+    rc = b200sqp_solve_async(h, opts, 1);
+    if (rc) return rc;
+    launchFirstControls(h->st.z[0], h->st.z[1], h->st.cur, h->s.nu, h->s.K * h->s.nb, h->d_u0, h->B, h->S, h->stream);
+    h->launches += 1;
+    CUDA_TRY(cudaGetLastError());
+    CUDA_TRY(cudaMemcpyAsync(u0_out, h->d_u0, sizeof(double) * (size_t)h->B * h->s.nu, cudaMemcpyDeviceToHost, h->stream));
+    if (status_out) CUDA_TRY(cudaMemcpyAsync(status_out, h->st.status, sizeof(int32_t) * h->B, cudaMemcpyDeviceToHost, h->stream));
+    if (chi2_out) CUDA_TRY(cudaMemcpyAsync(chi2_out, h->st.chi2, sizeof(double) * h->B, cudaMemcpyDeviceToHost, h->stream));
+    CUDA_TRY(cudaStreamSynchronize(h->stream));
+    return B200SQP_OK;
+}
+
 int b200sqp_evaluate(b200sqp_handle h, double weight_eq, double weight_ineq, double weight_bounds, double* values, double* jac_values)
 {
     int rc = checkHandle(h);

@@ -25,13 +25,24 @@ __global__ void packKernel(const double* __restrict__ params, int n, const int* 
     }
 }
 
+// block order (tiled instance-minor) -> host order [B][n]: one thread block transposes 32 instances x 32 parameters through shared
+// memory so that both the reads (32 consecutive lanes of a slot) and the writes (32 consecutive parameters of an instance) coalesce
 __global__ void unpackKernel(const double* __restrict__ z0, const double* __restrict__ z1, const int* __restrict__ cur,
                              const int* __restrict__ internal_of_ref, int n, int slots, double* __restrict__ params, int B, int S)
 {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= B) return;
-    const double* src = cur[i] ? z1 : z0;
-    for (int r = 0; r < n; ++r) params[(size_t)i * n + r] = src[tiled(i, internal_of_ref[r], slots)];
+    __shared__ double tile[32][33];
+    const int lane = threadIdx.x, ty = threadIdx.y;
+    const int i0 = blockIdx.x * 32, r0 = blockIdx.y * 32;
+    const int i  = i0 + lane;
+    if (i < B)
+    {
+        const double* src = cur[i] ? z1 : z0;
+        for (int rr = ty; rr < 32; rr += 8)
+            if (r0 + rr < n) tile[rr][lane] = src[tiled(i, internal_of_ref[r0 + rr], slots)];
+    }
+    __syncthreads();
+    for (int ii = ty; ii < 32; ii += 8)
+        if (i0 + ii < B && r0 + lane < n) params[(size_t)(i0 + ii) * n + r0 + lane] = tile[lane][ii];
 }
 
 __global__ void transposeInKernel(const double* __restrict__ src, int dim, double* __restrict__ dst, int B, int S)
@@ -55,7 +66,9 @@ __global__ void transposeOutKernel(const double* __restrict__ src, int rows, dou
 __global__ void initTrajectoriesKernel(const double* __restrict__ x0, const double* __restrict__ xref, double* __restrict__ z, int* __restrict__ cur,
                                        int K, int nx, int nu, int vt, double dt_ref, int B, int S)
 {
+    // one thread per (instance, interval): the batch alone (4096 threads) would leave most of the machine idle
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    const int k = blockIdx.y;
     if (i >= B) return;
     const int nb = nu + vt + nx, slots = K * nb;
     double dist  = 0.0;
@@ -66,20 +79,17 @@ __global__ void initTrajectoriesKernel(const double* __restrict__ x0, const doub
     }
     dist              = sqrt(dist);
     const double step = dist / K;
-    for (int k = 0; k < K; ++k)
+    for (int j = 0; j < nu; ++j) z[tiled(i, k * nb + j, slots)] = 0.0;
+    if (vt) z[tiled(i, k * nb + nu, slots)] = dt_ref;
+    for (int j = 0; j < nx; ++j)
     {
-        for (int j = 0; j < nu; ++j) z[tiled(i, k * nb + j, slots)] = 0.0;
-        if (vt) z[tiled(i, k * nb + nu, slots)] = dt_ref;
-        for (int j = 0; j < nx; ++j)
-        {
-            const double a = x0[tiled(i, j, nx)], b = xref[tiled(i, j, nx)];
-            double dir     = b - a;
-            if (dist != 0) dir /= dist;
-            // block k holds x_{k+1}; the last block holds xf = xref
-            z[tiled(i, k * nb + nu + vt + j, slots)] = (k + 1 < K) ? a + (double)(k + 1) * step * dir : b;
-        }
+        const double a = x0[tiled(i, j, nx)], b = xref[tiled(i, j, nx)];
+        double dir     = b - a;
+        if (dist != 0) dir /= dist;
+        // block k holds x_{k+1}; the last block holds xf = xref
+        z[tiled(i, k * nb + nu + vt + j, slots)] = (k + 1 < K) ? a + (double)(k + 1) * step * dir : b;
     }
-    cur[i] = 0;
+    if (k == 0) cur[i] = 0;
 }
 
 __global__ void firstControlsKernel(const double* __restrict__ z0, const double* __restrict__ z1, const int* __restrict__ cur, int nu, int slots,
@@ -251,7 +261,7 @@ void launchPack(const double* params, int n, const int* ref_of_internal, int slo
 void launchUnpack(const double* z0, const double* z1, const int* cur, const int* internal_of_ref, int n, int slots, double* params, int B, int S,
                   cudaStream_t st)
 {
-    unpackKernel<<<blocksFor(B), 128, 0, st>>>(z0, z1, cur, internal_of_ref, n, slots, params, B, S);
+    unpackKernel<<<dim3((B + 31) / 32, (n + 31) / 32), dim3(32, 8), 0, st>>>(z0, z1, cur, internal_of_ref, n, slots, params, B, S);
 }
 void launchFillPinned(const double* xref, double* z0, double* z1, int slot0, int slots, int nx, unsigned mask, int B, cudaStream_t st)
 {
@@ -268,7 +278,7 @@ void launchTransposeOut(const double* src, int rows, double* dst, int B, int S, 
 void launchInitTrajectories(const double* x0, const double* xref, double* z, int* cur, int K, int nx, int nu, int vt, double dt_ref,
                             const int* /*xf_fixed_dev*/, int B, int S, cudaStream_t st)
 {
-    initTrajectoriesKernel<<<blocksFor(B), 128, 0, st>>>(x0, xref, z, cur, K, nx, nu, vt, dt_ref, B, S);
+    initTrajectoriesKernel<<<dim3(blocksFor(B), K), 128, 0, st>>>(x0, xref, z, cur, K, nx, nu, vt, dt_ref, B, S);
 }
 void launchFirstControls(const double* z0, const double* z1, const int* cur, int nu, int slots, double* u0, int B, int S, cudaStream_t st)
 {

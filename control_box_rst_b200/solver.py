@@ -27,7 +27,7 @@ ABI_SYMBOLS = [
     "b200sqp_solve_async", "b200sqp_synchronize", "b200sqp_step", "b200sqp_evaluate", "b200sqp_get_statistics", "b200sqp_get_chi2_trace",
     "b200sqp_last_solve_ms", "b200sqp_launch_count", "b200sqp_device_pointers", "b200sqp_set_stream", "b200sqp_set_threads_per_instance",
     "b200sqp_set_phase_profile", "b200sqp_get_phase_cycles", "b200sqp_final_constraint_indices",
-    "b200sqp_peer_export", "b200sqp_peer_attach", "b200sqp_peer_wait", "b200sqp_peer_gathered", "b200sqp_peer_detach", "b200sqp_peer_status", "b200sqp_linearize_dynamics", "b200sqp_warm_start_shift",
+    "b200sqp_peer_export", "b200sqp_peer_attach", "b200sqp_peer_wait", "b200sqp_peer_gathered", "b200sqp_peer_detach", "b200sqp_peer_status", "b200sqp_linearize_dynamics", "b200sqp_warm_start_shift", "b200sqp_mpc_step",
 ]
 
 
@@ -228,6 +228,24 @@ class BatchedLevenbergMarquardt:
         _check(self._lib.b200sqp_step(self._h, C.byref(self._opts), C.c_int32(1 if cold_start else 0), _d(x0), _d(xref), _d(params), _d(chi2),
                                       _i(status)))
         return params, chi2, status
+
+    MPC_COLD, MPC_KEEP, MPC_SHIFT = 0, 1, 2
+
+    def mpc_step(self, x0, xref=None, mode=1, out=None):
+        """One closed-loop MPC step of the batch: measured states in, first controls out (trajectories stay in HBM).
+        mode: MPC_COLD initialise, MPC_KEEP previous solution as guess, MPC_SHIFT moving-horizon warm start.  -> u0 [B, nu], chi2, status"""
+        x0 = np.ascontiguousarray(x0, np.float64)
+        xref = None if xref is None else np.ascontiguousarray(xref, np.float64)
+        if out is None:
+            out = (np.zeros((self.batch, self.ocp.nu)), np.zeros(self.batch), np.zeros(self.batch, np.int32))
+        u0, chi2, status = out
+        _check(self._lib.b200sqp_mpc_step(self._h, C.byref(self._opts), C.c_int32(mode), _d(x0), _d(xref), _d(u0), _d(chi2), _i(status)))
+        return u0, chi2, status
+
+    def mpc_step_raw(self, mode, x0_ptr, xref_ptr, u0_ptr, chi2_ptr, status_ptr):
+        """b200sqp_mpc_step on raw host addresses (pinned buffers)"""
+        _check(self._lib.b200sqp_mpc_step(self._h, C.byref(self._opts), C.c_int32(mode), C.c_void_p(x0_ptr), C.c_void_p(xref_ptr),
+                                          C.c_void_p(u0_ptr), C.c_void_p(chi2_ptr), C.c_void_p(status_ptr)))
 
     def step_raw(self, x0_ptr, xref_ptr, params_ptr, chi2_ptr, status_ptr, cold_start=True):
         """b200sqp_step on raw host addresses (e.g. pinned torch tensors' data_ptr())."""

@@ -191,6 +191,17 @@ int b200sqp_synchronize(b200sqp_handle h);
 int b200sqp_step(b200sqp_handle h, const b200sqp_lm_options* opts, int32_t cold_start, const double* x0, const double* xref,
                  double* params_out, double* chi2_out, int32_t* status_out);
 
+/* One closed-loop MPC step of the whole batch with minimal host traffic: what PredictiveController::step
+ * (src/controllers/src/predictive_controller.cpp:46-79) needs from StructuredOptimalControlProblem::compute + getFirstControlInput.
+ * H2D of the measured states x0 [batch*nx] (+ xref or NULL), then per `mode`
+ *   0  cold start: FullDiscretizationGridBase::initializeSequences
+ *   1  keep the previous solution as the initial guess, start state replaced (grid update with warm start off)
+ *   2  moving-horizon warm start: b200sqp_warm_start_shift (FiniteDifferencesGrid structures only)
+ * solve (new_run = 1), D2H of the first controls u0_out [batch*nu] and, if non-NULL, chi2_out [batch] / status_out [batch].
+ * The trajectories stay in HBM (b200sqp_get_params fetches them). */
+int b200sqp_mpc_step(b200sqp_handle h, const b200sqp_lm_options* opts, int32_t mode, const double* x0, const double* xref, double* u0_out,
+                     double* chi2_out, int32_t* status_out);
+
 /* LevenbergMarquardtSparse::computeValues (:222-246) and ...EdgeBased::computeCombinedSparseJacobian (:1480-1753) at the current
  * parameters, penalty weights applied: values [batch*m], jac_values [batch*nnzJ] in the CSC order of b200sqp_jacobian_pattern.
  * Like the reference, evaluating the Jacobian perturbs the parameters in place (+d,-2d,+d; edge_interface.cpp:78-85). */

@@ -114,3 +114,31 @@ def test_device_shift_large_batch_is_per_instance():
         xs, us, s = warm_start.warm_start_shift(*_split(ocp, p[i], x0[i]), x0_new[i])
         assert s == shifts[i] and np.array_equal(_join(ocp, xs, us), after[i])
     lm.clear()
+
+
+@pytest.mark.gpu
+def test_mpc_step_front_end_matches_reference_closed_loops():
+    """b200sqp_mpc_step (x0 in, u0 out) in its keep and shift modes against the reference's controller loops without / with
+    setWarmStart(true) (tests/golden/vdp20_closed_loop.npz, warm_start_shift.npz)."""
+    plain = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "vdp20_closed_loop.npz"))
+    ocp = problems.van_der_pol(20)
+
+    def f(x, u):
+        return np.array([x[1], -1.0 * (x[0] * x[0] - 1) * x[1] - x[0] + u[0]])
+
+    for mode, gold_u, gold_x in ((solver.BatchedLevenbergMarquardt.MPC_KEEP, plain["u"], plain["x"]),
+                                 (solver.BatchedLevenbergMarquardt.MPC_SHIFT, GOLD["loop_u"], GOLD["loop_x"])):
+        lm = solver.BatchedLevenbergMarquardt(ocp, 1)
+        lm.setIterations(10)
+        x = np.array([1.0, 0.5])
+        for s in range(15):
+            u, chi2, status = lm.mpc_step(x[None, :], None, mode=solver.BatchedLevenbergMarquardt.MPC_COLD if s == 0 else mode)
+            u = u[0]
+            np.testing.assert_allclose(u, gold_u[s], rtol=0, atol=2e-6)
+            k1 = f(x, u) * ocp.dt_ref
+            k2 = f(x + k1 / 2.0, u) * ocp.dt_ref
+            k3 = f(x + k2 / 2.0, u) * ocp.dt_ref
+            k4 = f(x + k3, u) * ocp.dt_ref
+            x = x + (k1 + 2.0 * k2 + 2.0 * k3 + k4) / 6.0
+            np.testing.assert_allclose(x, gold_x[s + 1], rtol=0, atol=2e-6)
+        lm.clear()
