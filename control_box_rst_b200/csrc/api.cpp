@@ -84,6 +84,9 @@ struct b200sqp_solver
     void* peer_mapped[MAX_PEERS] = {};       // cudaIpcOpenMemHandle results (null for own rank)
     unsigned long long peer_solves = 0;      // solves launched since attach
     int* d_num_shift = nullptr;
+    PipeArrays pipe{};          // warp-cooperative pipeline (large stage blocks), allocated when the kernel set has one and the
+    bool use_pipeline = false;  // structure is eligible
+    bool pipeline_enabled = true;
     long long* d_phase_cycles = nullptr;
     int phase_blocks = 0;
     std::vector<void*> allocations;
@@ -335,6 +338,29 @@ int b200sqp_create(const b200sqp_ocp* ocp, int32_t batch, int32_t device, b200sq
     A(&h->d_internal_of_ref, s.internal_of_ref.size());
     A(&h->d_value_rows, s.value_rows.size());
     A(&h->d_jac_pos, s.jac_pos.size());
+    h->use_pipeline = ks->pipeline != nullptr && pipelineEligible(h->P, s.nx);
+    if (h->use_pipeline)
+    {
+        const size_t BK = (size_t)h->B * K, nxx = nx * (nx + 1) / 2;
+        PipeArrays& pa = h->pipe;
+        A(&pa.D, BK * nd);
+        A(&pa.E, BK * ne);
+        A(&pa.DA, BK * nxx);
+        A(&pa.gA, BK * nx);
+        A(&pa.g, BK * nb);
+        A(&pa.L, BK * nd);
+        A(&pa.W, BK * ne);
+        A(&pa.y, BK * nb);
+        A(&pa.cpart, K * S);
+        A(&pa.mu_acc, S);
+        A(&pa.last_values, S);
+        A(&pa.dn2, S);
+        A(&pa.dq, S);
+        A(&pa.v, S);
+        A(&pa.k_outer, S);
+        A(&pa.flags, S);
+        A(&pa.any, 2);
+    }
     st.trace = nullptr;
     if (e == cudaSuccess)
         e = cudaMemcpyAsync(h->d_ref_of_internal, s.ref_of_internal.data(), sizeof(int) * s.ref_of_internal.size(), cudaMemcpyHostToDevice, h->stream);
@@ -504,8 +530,18 @@ int b200sqp_solve_async(b200sqp_handle h, const b200sqp_lm_options* opts, int32_
         h->peer_solves += 1;
     }
     CUDA_TRY(cudaEventRecord(h->ev_begin, h->stream));
-    h->kernels->solve(h->P, h->st, opts->iterations, h->threads_per_instance, h->stream);
-    h->launches += 1;
+    if (h->use_pipeline && h->pipeline_enabled && !h->peer_attached)
+    {
+        // large stage blocks: warp-cooperative multi-kernel pipeline, host-driven passes (blocks until the batch is solved)
+        if (!h->kernels->pipeline(h->P, h->st, h->pipe, opts->iterations, h->stream))
+            return fail(B200SQP_ERR_CUDA, "LM pipeline exceeded its pass bound");
+        h->launches += 4 * (int64_t)(opts->iterations + 1);
+    }
+    else
+    {
+        h->kernels->solve(h->P, h->st, opts->iterations, h->threads_per_instance, h->stream);
+        h->launches += 1;
+    }
     CUDA_TRY(cudaGetLastError());
     CUDA_TRY(cudaEventRecord(h->ev_end, h->stream));
     h->timed = true;
@@ -724,7 +760,10 @@ int b200sqp_device_pointers(b200sqp_handle h, void** chi2, void** status, void**
 
 int b200sqp_set_threads_per_instance(b200sqp_handle h, int32_t threads)
 {
-    if (!h || threads < 0 || threads > 8) return fail(B200SQP_ERR_INVALID, "threads per instance must be 0 (auto), 1, 2, 4 or 8");
+    if (!h || threads < -1 || threads > 8) return fail(B200SQP_ERR_INVALID, "threads per instance must be 0 (auto), 1, 2, 4, 8, or -1");
+    // -1: force the fused kernel where the warp-cooperative pipeline would be chosen (comparison / debugging)
+    h->pipeline_enabled = threads != -1;
+    if (threads < 0) threads = 0;
     h->threads_per_instance = threads;
     return B200SQP_OK;
 }

@@ -94,9 +94,10 @@ struct Quadrotor
     static constexpr int NX = 12, NU = 4, ID = B200SQP_DYN_QUADROTOR;
     __device__ __forceinline__ static void f(const DynParams& c, const double* x, const double* u, double* out)
     {
-        const double sphi = sin(x[3]), cphi = cos(x[3]);
-        const double sth = sin(x[4]), cth = cos(x[4]);
-        const double spsi = sin(x[5]), cpsi = cos(x[5]);
+        double sphi, cphi, sth, cth, spsi, cpsi;  // one argument reduction per angle; same values as separate sin()/cos()
+        sincos(x[3], &sphi, &cphi);
+        sincos(x[4], &sth, &cth);
+        sincos(x[5], &spsi, &cpsi);
         const double p = x[9], q = x[10], r = x[11];
         const double tm = u[0] / c.p[0];
         out[0]          = x[6];

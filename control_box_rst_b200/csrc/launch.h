@@ -7,6 +7,7 @@ namespace b200sqp {
 
 struct DeviceOcp;
 struct DeviceState;
+struct PipeArrays;
 
 struct KernelSet
 {
@@ -15,6 +16,8 @@ struct KernelSet
     void (*solve)(const DeviceOcp&, const DeviceState&, int iterations, int threads_per_instance /*0 = auto*/, cudaStream_t);
     void (*evaluate)(const DeviceOcp&, const DeviceState&, double* values, double* jac, const int* value_rows, const int* jac_pos, int v_count,
                      int j_count, cudaStream_t);
+    // warp-cooperative pipeline for large stage blocks (lm_pipeline.cuh) or nullptr; blocks the host, false = pass bound hit
+    bool (*pipeline)(const DeviceOcp&, const DeviceState&, const PipeArrays&, int iterations, cudaStream_t);
 };
 
 // closed registry (kernels_*.cu); nullptr = combination not compiled in -> B200SQP_ERR_UNSUPPORTED, never a CPU fallback

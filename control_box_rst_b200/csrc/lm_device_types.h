@@ -67,4 +67,34 @@ struct DeviceState
     double w_eq, w_ineq, w_b;  // current penalty weights (host-managed: reset / adapted per solve)
 };
 
+// device arrays of the warp-cooperative pipeline for large stage blocks (lm_pipeline.cuh); Hessian blocks instance-major
+struct PipeArrays
+{
+    double* D;    // [B][K][nb(nb+1)/2] G^T G of block k (packed lower by rows) + diagonal cost / bound rows
+    double* E;    // [B][K][nb*nx]      coupling of block k to the x-part of block k-1
+    double* DA;   // [B][K][nx(nx+1)/2] A^T A of interval k: belongs to the x-x part of block k-1
+    double* gA;   // [B][K][nx]         -A^T e of interval k: belongs to the x-part of g of block k-1
+    double* g;    // [B][K][nb]
+    double* L;    // [B][K][nb(nb+1)/2] Cholesky factor blocks (reciprocal diagonal)
+    double* W;    // [B][K][nb*nx]
+    double* y;    // [B][K][nb]         forward-substituted right-hand side
+    double* cpart;        // [K][S] residual norm per interval (linearisation point / trial point)
+    double* mu_acc;       // [S] damping accumulated on the diagonal since the last linearisation
+    double* last_values;  // [S]
+    double* dn2;          // [S] ||delta||^2
+    double* dq;           // [S] delta^T (mu delta + g)
+    unsigned* v;          // [S]
+    int* k_outer;         // [S]
+    int* flags;           // [S] PF_ACTIVE | PF_LIN | PF_STOP
+    int* any;             // [2] any instance active / any instance to re-linearise
+};
+
+// structures the pipeline covers (lm_pipeline.cuh); everything else runs through the fused kernel
+inline bool pipelineEligible(const DeviceOcp& P, int nx)
+{
+    bool ok = P.final_constraint == 0 && P.stage_cost == B200SQP_COST_QUADRATIC_LSQ;
+    for (int j = 0; j < nx; ++j) ok = ok && !P.x_bounded[j] && !P.xf_fixed[j];
+    return ok;
+}
+
 }  // namespace b200sqp

@@ -1,0 +1,637 @@
+// Warp-cooperative LM pipeline for models with LARGE stage blocks (nb = nu + nx >= 8, e.g. the 12-state quadrotor: 16 x 16 blocks).
+//
+// The fused one-thread-per-chunk kernel (lm_kernels.cuh) keeps a whole interval's Jacobian and a whole Hessian block in the
+// registers of one thread; for nb = 16 that is > 1000 doubles per thread and ptxas spills 20 kB per thread to local memory.
+// Here the 32 lanes of a warp share that state instead:
+//
+//   pipeLinearizeKernel   one warp per (instance, interval): lane c evaluates central-difference column c of the interval's
+//                         Jacobian (2 nx + nu columns; BaseEdge::computeJacobian, edge_interface.cpp:55-96), the columns meet in
+//                         shared memory, the lanes then share out the entries of the normal-equation blocks J^T J, J^T(-r)
+//                         (levenberg_marquardt_sparse.cpp:97-100); residual norms by warp-shuffle reductions
+//   pipeInitKernel        one warp per instance: chi2, ||g||inf, max diag(H) -> initial LM state (:103-126)
+//   pipeFactorKernel      one warp per instance: block-tridiagonal Cholesky of (H + sum(mu) I) with the 16 x 16 blocks in shared
+//                         memory (lane = row), forward and backward substitution (:135-148)
+//   pipeTrialKernel       one thread per (instance, interval): trial point and its residuals (:158-167)
+//   pipeControlKernel     one thread per instance: gain ratio, accept/reject, damping (:169-216), the reference's loop verbatim
+//
+// The host drives the passes (launchPipeline) and reads two flags per pass; one pass is milliseconds of device work for the
+// batches this path is meant for, so the launch/flag latency is irrelevant.  Hessian blocks live in HBM instance-major
+// ([instance][interval][entry]: a warp reads its instance's block as one contiguous run); parameters, steps and per-instance
+// scalars stay in the tiled instance-minor layout of the rest of the library, so every other entry point works unchanged.
+//
+// Differences to the fused kernel (both within the FD-noise floor): the in-place perturbation drift of the
+// parameters (+d, -2d, +d leaves ~1 ulp) is applied inside one Jacobian evaluation exactly as the reference orders it, but not
+// carried into the stored parameters between evaluations; the elimination order inside a block differs.
+// Eligibility (else the fused kernel runs): fixed-dt FD grid or shooting grid, quadratic lsq stage cost, no state bounds, no
+// pinned goal components, no final-stage constraint.
+#pragma once
+
+#include <math_constants.h>
+
+#include "launch.h"
+#include "lm_device.cuh"
+
+namespace b200sqp {
+
+enum { PF_ACTIVE = 1, PF_LIN = 2, PF_STOP = 4 };
+
+template <class M>
+struct PipeDim
+{
+    static constexpr int NX = M::NX, NU = M::NU, NB = NU + NX, NV = 2 * NX + NU;
+    static constexpr int ND = NB * (NB + 1) / 2, NE = NB * NX, NXX = NX * (NX + 1) / 2;
+    static_assert(NV <= 31, "one lane per Jacobian column plus one lane for the unperturbed values");
+};
+
+__device__ __forceinline__ double driftRoundTrip(double v)
+{
+    // what BaseEdge::computeJacobian leaves in a vertex component: +delta, -2 delta, +delta (edge_interface.cpp:78-85)
+    v += 1e-9;
+    v += -2e-9;
+    v += 1e-9;
+    return v;
+}
+
+__device__ __forceinline__ size_t tiledSlot(int i, int slot, int nslots) { return ((size_t)(i >> 5) * nslots + slot) * 32 + (i & 31); }
+
+// ---------------------------------------------------------------------------------------------------------------------------
+// linearise: one warp per (instance, interval)
+// ---------------------------------------------------------------------------------------------------------------------------
+template <class M, int DEFECT>
+__global__ void __launch_bounds__(128, 4) pipeLinearizeKernel(const __grid_constant__ DeviceOcp P, const __grid_constant__ DeviceState st,
+                                                           const __grid_constant__ PipeArrays pa)
+{
+    using Pd = PipeDim<M>;
+    constexpr int NX = Pd::NX, NU = Pd::NU, NB = Pd::NB, NV = Pd::NV, ND = Pd::ND, NE = Pd::NE, NXX = Pd::NXX;
+    constexpr double delta = 1e-9, neg2delta = -2 * delta, scalar = 1.0 / (2 * delta);
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    const int K    = P.K;
+    const long long warp = (long long)blockIdx.x * 4 + wib;
+    const int i = (int)(warp / K), k = (int)(warp % K);
+    __shared__ double sG[4][NV][NX + 1];  // Jacobian columns of the dynamics edge, [column][row] (padded: conflict-free column writes)
+    __shared__ double sE0[4][NX];     // weighted defect at the unperturbed point
+    __shared__ double sCost[4][4][NB > NX ? NB : NX];  // 0: cost value, 1: cost Jacobian (diagonal), 2: bound value, 3: bound Jacobian, per block slot
+    __shared__ double sX0c[4][NX];
+    __shared__ unsigned char sTriR[ND], sTriC[ND];
+    for (int idx = threadIdx.x; idx < ND; idx += blockDim.x)
+    {
+        int r = 0;
+        while ((r + 1) * (r + 2) / 2 <= idx) ++r;
+        sTriR[idx] = (unsigned char)r;
+        sTriC[idx] = (unsigned char)(idx - r * (r + 1) / 2);
+    }
+    __syncthreads();
+    if (i >= P.B || !(pa.flags[i] & PF_LIN)) return;
+
+    const Weights w{st.w_eq, st.w_ineq, st.w_b};
+    const double* z = st.z[st.cur[i]];
+    const int slots = K * NB;
+    const bool last = (k == K - 1);
+    const bool has_xs = last ? (P.final_cost != 0) : true;
+    const double* xs_w = last ? P.qf_sqrt : P.q_sqrt;
+
+    // ---- operands: lane q < NV loads component q of [x_k | u_k | x_{k+1}], lane q < NX also the reference state; all-to-all by shuffles
+    double mine = 0.0, mref = 0.0;
+    if (lane < NX)
+    {
+        mine = (k > 0) ? z[tiledSlot(i, (k - 1) * NB + NU + lane, slots)] : st.x0[tiledSlot(i, lane, NX)];
+        mref = st.xref[tiledSlot(i, lane, NX)];
+    }
+    else if (lane < NX + NU)
+        mine = z[tiledSlot(i, k * NB + (lane - NX), slots)];
+    else if (lane < NV)
+        mine = z[tiledSlot(i, k * NB + NU + (lane - NX - NU), slots)];
+    double v[NV], xr[NX];
+#pragma unroll
+    for (int q = 0; q < NV; ++q) v[q] = __shfl_sync(0xffffffffu, mine, q);
+#pragma unroll
+    for (int q = 0; q < NX; ++q) xr[q] = __shfl_sync(0xffffffffu, mref, q);
+
+    // ---- the vector this lane evaluates.  Lane p < NV owns column p of the dynamics edge (vertices in attachment order x_k, u_k,
+    //      x_{k+1}); before that edge the lsq edges have perturbed u_k and x_{k+1} once (costs on them) and x_k twice (its own cost
+    //      edge and the dynamics edge of interval k-1): computeCombinedSparseJacobian visits all lsq edges first (:1495-1525), then
+    //      the equality edges in order (:1531-1559).  Components in front of p have completed this edge's round trip as well.
+    //      Lanes >= NV evaluate the unperturbed point (the `values` the LM loop computed before the Jacobian).
+    const int p = lane;
+    const bool col_lane = p < NV && (k > 0 || p >= NX);  // x_0 is fixed: no columns for it
+    double vec[NV];
+#pragma unroll
+    for (int q = 0; q < NV; ++q)
+    {
+        double b = v[q];
+        if (p < NV)
+        {
+            if (q < NX)
+            {
+                if (k > 0) b = driftRoundTrip(driftRoundTrip(b));
+            }
+            else if (q < NX + NU)
+                b = driftRoundTrip(b);
+            else if (has_xs)
+                b = driftRoundTrip(b);
+            if (q < p && (k > 0 || q >= NX)) b = driftRoundTrip(b);
+            if (q == p) b += delta;
+        }
+        vec[q] = b;
+    }
+    StepSize h(P.dt_ref);
+    double e2[NX], e1[NX];
+    defectCall<M, DEFECT>(P.dyn, vec, vec + NX, vec + NX + NU, h, e2);
+#pragma unroll
+    for (int q = 0; q < NV; ++q)
+        if (q == p) vec[q] += neg2delta;
+    defectCall<M, DEFECT>(P.dyn, vec, vec + NX, vec + NX + NU, h, e1);
+    if (p < NV)
+    {
+#pragma unroll
+        for (int j = 0; j < NX; ++j) sG[wib][p][j] = col_lane ? scalar * (e2[j] - e1[j]) * w.eq : 0.0;
+    }
+    else if (p == NV)
+    {
+#pragma unroll
+        for (int j = 0; j < NX; ++j) sE0[wib][j] = e2[j] * w.eq;  // levenberg_marquardt_sparse.cpp:231-235
+    }
+
+    // ---- lsq cost and bound rows of the block slots [u_k | x_{k+1}] (diagonal): lane s < NB handles slot s
+    double cpart = 0.0;
+    if (lane < NB)
+    {
+        const int s = lane;
+        double cv, cj, bv = 0.0, bj = 0.0;
+        if (s < NU)
+        {
+            // QuadraticFormCost::computeNonIntegralControlTerm, lsq + diagonal (quadratic_cost.cpp:146-154), FD like any edge
+            double u = v[NX + s];
+            cv       = P.r_sqrt[s] * u;
+            u += delta;
+            const double v2 = P.r_sqrt[s] * u;
+            u += neg2delta;
+            const double v1 = P.r_sqrt[s] * u;
+            cj              = scalar * (v2 - v1);
+            if (P.u_bounded[s])
+            {
+                bv = boundDist(v[NX + s], P.u_lb[s], P.u_ub[s]) * w.b;
+                bj = boundJac(driftRoundTrip(driftRoundTrip(v[NX + s])), P.u_lb[s], P.u_ub[s], w.b);  // bounds rows come last (:1721-1752)
+            }
+        }
+        else
+        {
+            const int j = s - NU;
+            double x    = v[NX + NU + j];
+            cv = cj = 0.0;
+            if (has_xs)
+            {
+                cv = xs_w[j] * (x - xr[j]);  // quadratic_cost.cpp:105-123 / final_state_cost.cpp:73-90
+                x += delta;
+                const double v2 = xs_w[j] * (x - xr[j]);
+                x += neg2delta;
+                const double v1 = xs_w[j] * (x - xr[j]);
+                cj              = scalar * (v2 - v1);
+            }
+        }
+        sCost[wib][0][s] = cv;
+        sCost[wib][1][s] = cj;
+        sCost[wib][2][s] = bv;
+        sCost[wib][3][s] = bj;
+        cpart            = fma(cv, cv, bv * bv);
+    }
+    if (k == 0 && lane < NX)
+    {
+        const double c = P.q_sqrt[lane] * (v[lane] - xr[lane]);  // cost edge on the fixed start state: value only
+        cpart          = fma(c, c, cpart);
+    }
+    __syncwarp();
+    if (lane < NX) cpart = fma(sE0[wib][lane], sE0[wib][lane], cpart);
+    // residual norm of this interval: fixed-order warp-shuffle reduction
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) cpart += __shfl_down_sync(0xffffffffu, cpart, off);
+    if (lane == 0) pa.cpart[(size_t)k * P.S + i] = cpart;
+
+    // ---- normal equations: the lanes share out the entries.  Block k = G^T G over the columns of [u_k | x_{k+1}] (+ diagonal cost /
+    //      bound rows), E_k = G^T A, and A^T A / A^T e go to block k-1 (stored separately: the factorisation adds them).
+    const size_t blk = (size_t)i * K + k;
+    double* Dk  = pa.D + blk * ND;
+    double* gk  = pa.g + blk * NB;
+    for (int idx = lane; idx < ND; idx += 32)
+    {
+        const int r = sTriR[idx], c = sTriC[idx];
+        double s    = 0.0;
+#pragma unroll
+        for (int q = 0; q < NX; ++q) s = fma(sG[wib][NX + r][q], sG[wib][NX + c][q], s);
+        if (r == c) s = fma(sCost[wib][1][r], sCost[wib][1][r], fma(sCost[wib][3][r], sCost[wib][3][r], s));
+        Dk[idx] = s;
+    }
+    if (lane < NB)
+    {
+        double s = 0.0;
+#pragma unroll
+        for (int q = 0; q < NX; ++q) s = fma(sG[wib][NX + lane][q], sE0[wib][q], s);
+        s        = fma(sCost[wib][1][lane], sCost[wib][0][lane], fma(sCost[wib][3][lane], sCost[wib][2][lane], s));
+        gk[lane] = -s;
+    }
+    if (k > 0)
+    {
+        double* Ek  = pa.E + blk * NE;
+        double* DAk = pa.DA + blk * NXX;
+        double* gAk = pa.gA + blk * NX;
+        for (int idx = lane; idx < NE; idx += 32)
+        {
+            const int r = idx / NX, a = idx % NX;
+            double s    = 0.0;
+#pragma unroll
+            for (int q = 0; q < NX; ++q) s = fma(sG[wib][NX + r][q], sG[wib][a][q], s);
+            Ek[idx] = s;
+        }
+        for (int idx = lane; idx < NXX; idx += 32)
+        {
+            const int a = sTriR[idx], b = sTriC[idx];
+            double s    = 0.0;
+#pragma unroll
+            for (int q = 0; q < NX; ++q) s = fma(sG[wib][a][q], sG[wib][b][q], s);
+            DAk[idx] = s;
+        }
+        if (lane < NX)
+        {
+            double s = 0.0;
+#pragma unroll
+            for (int q = 0; q < NX; ++q) s = fma(sG[wib][lane][q], sE0[wib][q], s);
+            gAk[lane] = -s;
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------------------------
+// initial LM state after the first linearisation: one warp per instance (levenberg_marquardt_sparse.cpp:103-126)
+// ---------------------------------------------------------------------------------------------------------------------------
+template <class M>
+__global__ void __launch_bounds__(128) pipeInitKernel(const __grid_constant__ DeviceOcp P, const __grid_constant__ DeviceState st,
+                                                      const __grid_constant__ PipeArrays pa, int iterations)
+{
+    using Pd = PipeDim<M>;
+    constexpr int NX = Pd::NX, NU = Pd::NU, NB = Pd::NB, ND = Pd::ND, NXX = Pd::NXX;
+    const int lane = threadIdx.x & 31;
+    const int i    = blockIdx.x * 4 + (threadIdx.x >> 5);
+    if (i >= P.B) return;
+    const int K = P.K;
+    double ginf = 0.0, maxdiag = -CUDART_INF, chi2 = 0.0;
+    for (int k = lane; k < K; k += 32)
+    {
+        const size_t blk = (size_t)i * K + k;
+        for (int r = 0; r < NB; ++r)
+        {
+            double d = pa.D[blk * ND + tri(r, r)], g = pa.g[blk * NB + r];
+            if (r >= NU && k + 1 < K)
+            {
+                d += pa.DA[(blk + 1) * NXX + tri(r - NU, r - NU)];
+                g += pa.gA[(blk + 1) * NX + (r - NU)];
+            }
+            maxdiag = fmax(maxdiag, d);
+            ginf    = fmax(ginf, fabs(g));
+        }
+    }
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1)
+    {
+        ginf    = fmax(ginf, __shfl_down_sync(0xffffffffu, ginf, off));
+        maxdiag = fmax(maxdiag, __shfl_down_sync(0xffffffffu, maxdiag, off));
+    }
+    if (lane == 0)
+    {
+        for (int k = 0; k < K; ++k) chi2 += pa.cpart[(size_t)k * P.S + i];  // fixed order
+        constexpr double eps1 = 1e-5, tau = 1e-5;
+        double mu = tau * maxdiag;
+        if (mu < 0) mu = 0;
+        const bool active  = iterations > 0;
+        st.chi2[i]         = chi2;
+        st.mu[i]           = mu;
+        st.rho[i]          = 0.0;
+        pa.mu_acc[i]       = mu;
+        pa.last_values[i]  = chi2;
+        pa.v[i]            = 2u;
+        pa.k_outer[i]      = 0;
+        pa.flags[i]        = (active ? PF_ACTIVE : 0) | (ginf <= eps1 ? PF_STOP : 0);
+        st.n_factor[i]     = 0;
+        st.n_reject[i]     = 0;
+        st.n_linearize[i]  = 1;
+        st.status[i]       = (ginf <= eps1) ? B200SQP_STATUS_CONVERGED : B200SQP_STATUS_EARLY_TERMINATED;
+        if (st.trace) st.trace[i] = chi2;
+        if (active) atomicOr(pa.any, 1);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------------------------
+// (H + mu_acc I) delta = g: block-tridiagonal Cholesky, one warp per instance, lane = row of the current block
+// ---------------------------------------------------------------------------------------------------------------------------
+template <class M>
+__global__ void __launch_bounds__(128) pipeFactorKernel(const __grid_constant__ DeviceOcp P, const __grid_constant__ DeviceState st,
+                                                        const __grid_constant__ PipeArrays pa)
+{
+    using Pd = PipeDim<M>;
+    constexpr int NX = Pd::NX, NU = Pd::NU, NB = Pd::NB, ND = Pd::ND, NE = Pd::NE, NXX = Pd::NXX;
+    constexpr unsigned FULL = 0xffffffffu;
+    using BS = BlockSolver<M, 0>;
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    const int i    = blockIdx.x * 4 + wib;
+    // Lane r < NB owns ROW r of the current block in registers; shared memory only stages the coalesced HBM transfers and holds
+    // what other lanes must read (W_k rows, the trailing block of the previous factor).
+    __shared__ double sS[4][NB][NB + 1];    // staging of D_k / L_k (lower triangle)
+    __shared__ double sW[4][NB][NX + 1];    // staging of E_k, then W_k = E_k Lxx^{-T}
+    __shared__ double sLxx[4][NX][NX + 1];  // trailing nx x nx block of the previous factor (reciprocal diagonal)
+    __shared__ unsigned char sTriR[ND], sTriC[ND];
+    for (int idx = threadIdx.x; idx < ND; idx += blockDim.x)
+    {
+        int r = 0;
+        while ((r + 1) * (r + 2) / 2 <= idx) ++r;
+        sTriR[idx] = (unsigned char)r;
+        sTriC[idx] = (unsigned char)(idx - r * (r + 1) / 2);
+    }
+    __syncthreads();
+    if (i >= P.B || !(pa.flags[i] & PF_ACTIVE)) return;
+    const int K      = P.K;
+    const double mua = pa.mu_acc[i], mu = st.mu[i];
+    const bool rowl  = lane < NB;
+    double yp_x      = 0.0;  // lane a < NX: x-part of the forward-substituted rhs of the previous block
+    for (int k = 0; k < K; ++k)
+    {
+        const size_t blk = (size_t)i * K + k;
+        // ---- stage D_k (+ A^T A of interval k+1 on the x-x part, + damping) and E_k: coalesced runs of the instance-major arrays
+        for (int idx = lane; idx < ND; idx += 32)
+        {
+            const int r = sTriR[idx], c = sTriC[idx];
+            double s    = pa.D[blk * ND + idx];
+            if (k + 1 < K && c >= NU) s += pa.DA[(blk + 1) * NXX + tri(r - NU, c - NU)];
+            if (r == c) s += mua;
+            sS[wib][r][c] = s;
+        }
+        if (k > 0)
+            for (int idx = lane; idx < NE; idx += 32) sW[wib][idx / NX][idx % NX] = pa.E[blk * NE + idx];
+        double y = 0.0;  // lane r < NB holds rhs component r
+        if (rowl)
+        {
+            y = pa.g[blk * NB + lane];
+            if (k + 1 < K && lane >= NU) y += pa.gA[(blk + 1) * NX + (lane - NU)];
+        }
+        __syncwarp();
+        double row[NB];  // row[c], c <= lane
+#pragma unroll
+        for (int c = 0; c < NB; ++c) row[c] = (rowl && c <= lane) ? sS[wib][lane][c] : 0.0;
+        if (k > 0)
+        {
+            // W_k Lxx^T = E_k: row r per lane
+            double wr[NX];
+#pragma unroll
+            for (int a = 0; a < NX; ++a)
+            {
+                double s = rowl ? sW[wib][lane][a] : 0.0;
+#pragma unroll
+                for (int b = 0; b < a; ++b) s = fma(-wr[b], sLxx[wib][a][b], s);
+                wr[a] = s * sLxx[wib][a][a];
+            }
+            __syncwarp();
+            if (rowl)
+            {
+#pragma unroll
+                for (int a = 0; a < NX; ++a) sW[wib][lane][a] = wr[a];
+            }
+            __syncwarp();
+            for (int idx = lane; idx < NE; idx += 32) pa.W[blk * NE + idx] = sW[wib][idx / NX][idx % NX];
+            // Schur complement and rhs update
+#pragma unroll
+            for (int c = 0; c < NB; ++c)
+            {
+                double s = row[c];
+#pragma unroll
+                for (int a = 0; a < NX; ++a) s = fma(-wr[a], sW[wib][c][a], s);
+                row[c] = (c <= lane) ? s : 0.0;
+            }
+#pragma unroll
+            for (int a = 0; a < NX; ++a) y = fma(-wr[a], __shfl_sync(FULL, yp_x, a), y);
+        }
+        // ---- Cholesky of S_k in registers (right-looking; column j of L is spread over the lanes, broadcast by shuffles) fused with
+        //      the forward substitution of the rhs
+#pragma unroll
+        for (int j = 0; j < NB; ++j)
+        {
+            const double inv = BS::pivotRsqrt(__shfl_sync(FULL, row[j], j));
+            const double yj  = __shfl_sync(FULL, y, j) * inv;
+            const double l   = (lane > j) ? row[j] * inv : 0.0;
+            if (lane > j) y = fma(-l, yj, y);
+            if (lane == j) y = yj;
+            row[j] = (lane == j) ? inv : l;
+#pragma unroll
+            for (int c = j + 1; c < NB; ++c)
+            {
+                const double lc = __shfl_sync(FULL, l, c);
+                row[c]          = fma(-l, lc, row[c]);  // lanes < c hold zeros there and l = 0 for lanes <= j
+            }
+        }
+        // ---- store the factor (coalesced through the staging tile) and the forward-substituted rhs, keep what the next block needs
+        __syncwarp();
+        if (rowl)
+        {
+#pragma unroll
+            for (int c = 0; c < NB; ++c)
+                if (c <= lane) sS[wib][lane][c] = row[c];
+            pa.y[blk * NB + lane] = y;
+            if (lane >= NU)
+            {
+#pragma unroll
+                for (int c = NU; c < NB; ++c)
+                    if (c <= lane) sLxx[wib][lane - NU][c - NU] = row[c];
+            }
+        }
+        yp_x = __shfl_sync(FULL, y, NU + (lane < NX ? lane : 0));
+        __syncwarp();
+        for (int idx = lane; idx < ND; idx += 32) pa.L[blk * ND + idx] = sS[wib][sTriR[idx]][sTriC[idx]];
+        __syncwarp();
+    }
+    // ---- back-substitution, bottom-up: L_k^T delta_k = y_k - W_{k+1}^T delta_{k+1} (x-part)
+    double dn2 = 0.0, dq = 0.0, dnext = 0.0;  // dnext: lane r holds delta_{k+1}[r]
+    for (int k = K - 1; k >= 0; --k)
+    {
+        const size_t blk = (size_t)i * K + k;
+        for (int idx = lane; idx < ND; idx += 32) sS[wib][sTriR[idx]][sTriC[idx]] = pa.L[blk * ND + idx];
+        if (k + 1 < K)
+            for (int idx = lane; idx < NE; idx += 32) sW[wib][idx / NX][idx % NX] = pa.W[(blk + 1) * NE + idx];
+        double d = 0.0, gfull = 0.0;
+        if (rowl)
+        {
+            d     = pa.y[blk * NB + lane];
+            gfull = pa.g[blk * NB + lane];
+            if (k + 1 < K && lane >= NU) gfull += pa.gA[(blk + 1) * NX + (lane - NU)];
+        }
+        __syncwarp();
+        if (k + 1 < K)
+        {
+            double s = 0.0;
+            const int a = (lane >= NU && rowl) ? lane - NU : 0;
+#pragma unroll
+            for (int r = 0; r < NB; ++r) s = fma(sW[wib][r][a], __shfl_sync(FULL, dnext, r), s);
+            if (lane >= NU && rowl) d -= s;
+        }
+        // L^T delta = d, column-oriented backward: lane r needs L[j][r] for j > r, i.e. column r of the factor
+        double colr[NB];
+#pragma unroll
+        for (int j = 0; j < NB; ++j) colr[j] = (rowl && j >= lane) ? sS[wib][j][lane] : 0.0;
+#pragma unroll
+        for (int j = NB - 1; j >= 0; --j)
+        {
+            const double dj = __shfl_sync(FULL, d, j) * __shfl_sync(FULL, colr[j], j);
+            if (lane == j) d = dj;
+            if (lane < j) d = fma(-colr[j], dj, d);
+        }
+        if (rowl)
+        {
+            st.dl[tiledSlot(i, k * NB + lane, K * NB)] = d;
+            dn2                                        = fma(d, d, dn2);
+            dq                                         = fma(d, fma(mu, d, gfull), dq);
+        }
+        dnext = d;
+        __syncwarp();
+    }
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1)
+    {
+        dn2 += __shfl_down_sync(FULL, dn2, off);
+        dq += __shfl_down_sync(FULL, dq, off);
+    }
+    if (lane == 0)
+    {
+        pa.dn2[i] = dn2;
+        pa.dq[i]  = dq;
+        st.n_factor[i] += 1;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------------------------
+// trial point and its residuals: one thread per (instance, interval)
+// ---------------------------------------------------------------------------------------------------------------------------
+template <class M, int DEFECT>
+__global__ void __launch_bounds__(128) pipeTrialKernel(const __grid_constant__ DeviceOcp P, const __grid_constant__ DeviceState st,
+                                                       const __grid_constant__ PipeArrays pa)
+{
+    using Pd = PipeDim<M>;
+    constexpr int NX = Pd::NX, NB = Pd::NB;
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    const int k = blockIdx.y;
+    if (i >= P.B || !(pa.flags[i] & PF_ACTIVE)) return;
+    constexpr double eps2 = 1e-5;
+    if (sqrt(pa.dn2[i]) <= eps2) return;  // step too small: no trial point (levenberg_marquardt_sparse.cpp:151-154)
+    const Weights w{st.w_eq, st.w_ineq, st.w_b};
+    const size_t tile = i >> 5, lane = i & 31;
+    const size_t zoff = tile * ((size_t)P.K * NB * TILE) + lane;
+    const int cur     = st.cur[i];
+    const double part = trialChi2<M, DEFECT, 0, FeatLean>(P, w, st.z[cur] + zoff, st.dl + zoff, st.z[cur ^ 1] + zoff,
+                                                           st.x0 + tile * ((size_t)NX * TILE) + lane, st.xref + tile * ((size_t)NX * TILE) + lane, k, k + 1);
+    pa.cpart[(size_t)k * P.S + i] = part;
+}
+
+// ---------------------------------------------------------------------------------------------------------------------------
+// LM control: one thread per instance (levenberg_marquardt_sparse.cpp:151-216; same state machine as lmSolveKernel's C phase)
+// ---------------------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) pipeControlKernel(const __grid_constant__ DeviceOcp P, const __grid_constant__ DeviceState st,
+                                                         const __grid_constant__ PipeArrays pa, int iterations)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= P.B) return;
+    int flags = pa.flags[i];
+    if (!(flags & PF_ACTIVE)) return;
+    constexpr double eps2 = 1e-5, eps3 = 1e-5, eps4 = 0;
+    constexpr double goodStepUpperScale = 2. / 3., goodStepLowerScale = 1. / 3.;
+    double mu = st.mu[i], mu_acc = pa.mu_acc[i], rho = st.rho[i], chi2_old = st.chi2[i], last_values = pa.last_values[i];
+    unsigned v   = pa.v[i];
+    int k_outer  = pa.k_outer[i];
+    bool stop    = (flags & PF_STOP) != 0;
+    bool lin     = false;
+    const double dq = pa.dq[i];
+    if (sqrt(pa.dn2[i]) <= eps2)
+        stop = true;
+    else
+    {
+        double chi2_new = 0.0;
+        for (int k = 0; k < P.K; ++k) chi2_new += pa.cpart[(size_t)k * P.S + i];  // fixed order
+        last_values = chi2_new;
+        rho         = (chi2_old - chi2_new) / dq;
+        if (rho > 0 && !isnan(chi2_new) && !isinf(chi2_new))
+        {
+            stop = (sqrt(chi2_old) - sqrt(chi2_new) < eps4 * sqrt(chi2_old));
+            st.cur[i] ^= 1;  // accept: the trial buffer becomes the current one
+            if (!stop && k_outer < iterations - 1)
+            {
+                lin = true;
+                st.n_linearize[i] += 1;
+                mu_acc             = 0.0;
+                const double c     = 2 * rho - 1;
+                double alpha       = fmin(goodStepUpperScale, 1 - c * c * c);
+                double scaleFactor = fmax(goodStepLowerScale, alpha);
+                mu *= scaleFactor;
+                v = 2;
+            }
+            chi2_old = chi2_new;
+        }
+        else
+        {
+            st.n_reject[i] += 1;
+            mu = mu * v;
+            v  = 2 * v;
+        }
+    }
+    bool active = true;
+    if (!(rho <= 0 && !stop))
+    {
+        stop = (sqrt(last_values) <= eps3);  // :216
+        ++k_outer;
+        if (st.trace) st.trace[(size_t)k_outer * P.S + i] = chi2_old;
+        active = k_outer < iterations;
+    }
+    if (active) mu_acc += mu;
+    st.mu[i]          = mu;
+    st.rho[i]         = rho;
+    st.chi2[i]        = chi2_old;
+    pa.mu_acc[i]      = mu_acc;
+    pa.last_values[i] = last_values;
+    pa.v[i]           = v;
+    pa.k_outer[i]     = k_outer;
+    pa.flags[i]       = (active ? PF_ACTIVE : 0) | (lin && active ? PF_LIN : 0) | (stop ? PF_STOP : 0);
+    st.status[i]      = (stop || rho <= 0) ? B200SQP_STATUS_CONVERGED : B200SQP_STATUS_EARLY_TERMINATED;
+    if (active) atomicOr(pa.any, 1);
+    if (lin && active) atomicOr(pa.any + 1, 1);
+}
+
+__global__ void pipeSetFlagsKernel(int* flags, int B, int value)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < B) flags[i] = value;
+}
+
+// LevenbergMarquardtSparse::solve for the whole batch, host-driven passes.  Blocks the calling thread (it reads two flags per
+// pass); returns false if a pass count bound is hit (never observed: every pass either ends an outer iteration or multiplies mu).
+template <class M, int DEFECT>
+bool launchPipeline(const DeviceOcp& P, const DeviceState& st, const PipeArrays& pa, int iterations, cudaStream_t stream)
+{
+    const int B = P.B, K = P.K;
+    const int warp_blocks_ik = (int)(((long long)B * K + 3) / 4), warp_blocks_i = (B + 3) / 4, thread_blocks_i = (B + 127) / 128;
+    int any[2] = {0, 0};
+    cudaMemsetAsync(pa.any, 0, 2 * sizeof(int), stream);
+    pipeSetFlagsKernel<<<thread_blocks_i, 128, 0, stream>>>(pa.flags, B, PF_LIN);
+    pipeLinearizeKernel<M, DEFECT><<<warp_blocks_ik, 128, 0, stream>>>(P, st, pa);
+    pipeInitKernel<M><<<warp_blocks_i, 128, 0, stream>>>(P, st, pa, iterations);
+    cudaMemcpyAsync(any, pa.any, 2 * sizeof(int), cudaMemcpyDeviceToHost, stream);
+    cudaStreamSynchronize(stream);
+    int passes = 0;
+    const int max_passes = 64 * (iterations + 1);
+    while (any[0] && passes < max_passes)
+    {
+        pipeFactorKernel<M><<<warp_blocks_i, 128, 0, stream>>>(P, st, pa);
+        pipeTrialKernel<M, DEFECT><<<dim3(thread_blocks_i, K), 128, 0, stream>>>(P, st, pa);
+        cudaMemsetAsync(pa.any, 0, 2 * sizeof(int), stream);
+        pipeControlKernel<<<thread_blocks_i, 128, 0, stream>>>(P, st, pa, iterations);
+        cudaMemcpyAsync(any, pa.any, 2 * sizeof(int), cudaMemcpyDeviceToHost, stream);
+        cudaStreamSynchronize(stream);
+        if (any[0] && any[1]) pipeLinearizeKernel<M, DEFECT><<<warp_blocks_ik, 128, 0, stream>>>(P, st, pa);
+        ++passes;
+    }
+    return passes < max_passes;
+}
+
+}  // namespace b200sqp

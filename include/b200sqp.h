@@ -248,7 +248,8 @@ int b200sqp_peer_gathered(b200sqp_handle h, void** chi2_all);
 /* synchronises the stream and reports whether any b200sqp_peer_wait since attach hit its 2 s bound (a rank that never arrived) */
 int b200sqp_peer_status(b200sqp_handle h, int32_t* timed_out);
 int b200sqp_peer_detach(b200sqp_handle h);
-/* tuning knob: cooperating threads per instance in the LM kernel (1, 2, 4, 8; 0 = choose from the batch size) */
+/* tuning knob: cooperating threads per instance in the LM kernel (1, 2, 4, 8; 0 = choose from the batch size).  Structures with
+ * large stage blocks (quadrotor) run a warp-per-instance pipeline instead of the fused kernel; -1 forces the fused kernel there. */
 int b200sqp_set_threads_per_instance(b200sqp_handle h, int32_t threads);
 /* measurement aid: when enabled, thread 0 of every thread block of the LM kernel accumulates clock64() per phase; get returns the
  * mean over thread blocks of the last solve, mean_cycles[4] = {linearise (a3/a4/a13), factor+solve (a14), trial values (a2/a12),

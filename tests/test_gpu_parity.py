@@ -166,9 +166,15 @@ def test_matches_reference_golden(name):
     err = _traj_err(lm.get_params(), gold["p_final"])
     assert err.max() <= traj_tol, err
     np.testing.assert_allclose(chi2, gold["chi2"], rtol=chi2_tol)
-    assert np.array_equal(status, gold["status"])
+    # status = Converged iff the last trial step was rejected (rho <= 0) or ||r|| <= 1e-5 (levenberg_marquardt_sparse.cpp:218).  Once an
+    # instance sits on the FD-noise floor (chi2 no longer moves in 9 digits) the sign of the last gain ratio is one realisation of the
+    # Jacobian noise (DESIGN.md "FD-noise floor"), so the flag is only compared for instances that are still descending.
+    full_trace = lm.chi2_trace()
+    at_floor = np.abs(full_trace[:, -1] - full_trace[:, -2]) <= 1e-9 * np.abs(full_trace[:, -1])
+    assert np.array_equal(status[~at_floor], gold["status"][~at_floor])
+    assert name not in POLYNOMIAL or np.array_equal(status, gold["status"])
     # per-iteration chi2 of instance 0 against the reference's event trace (values at every Jacobian evaluation)
-    trace = lm.chi2_trace()[0]
+    trace = full_trace[0]
     ref_chi2 = gold["trace_chi2"][gold["trace_types"] == 0]
     np.testing.assert_allclose(trace[:len(ref_chi2)], ref_chi2, rtol=max(chi2_tol, 1e-7))
     lm.clear()
@@ -307,3 +313,39 @@ def test_ragged_batch_sizes(oracle):
         assert _traj_err(lm.get_params(), p_o).max() <= 1e-6
         np.testing.assert_allclose(chi2, chi2_o, rtol=1e-8)
         lm.clear()
+
+
+def test_large_block_pipeline_agrees_with_fused_kernel_and_oracle(oracle):
+    """The 12-state quadrotor (16 x 16 stage blocks) runs the warp-per-instance pipeline (lm_pipeline.cuh); the fused kernel is kept
+    behind set_threads_per_instance(-1).  Both must agree with each other and with the oracle within the FD-noise floor, the
+    pipeline must be deterministic, and instances must not depend on their neighbours."""
+    ocp = problems.quadrotor(16)
+    B = 96
+    x0, xref = problems.instance_data(ocp, B, seed=13)
+    opts = abi.LmOptions.defaults(iterations=6)
+
+    def run(T, batch=B):
+        lm = solver.BatchedLevenbergMarquardt(ocp, batch)
+        lm.setIterations(6)
+        lm.set_threads_per_instance(T)
+        lm.set_problem_data(x0[:batch], xref[:batch])
+        lm.initialize_trajectories()
+        status, chi2 = lm.solve(new_run=True)
+        out = lm.get_params(), chi2, status, lm.chi2_trace(), lm.statistics()
+        lm.clear()
+        return out
+
+    p_pipe, c_pipe, s_pipe, tr_pipe, st_pipe = run(0)
+    p_pipe2, c_pipe2, _, _, _ = run(0)
+    assert np.array_equal(p_pipe, p_pipe2) and np.array_equal(c_pipe, c_pipe2)
+    p_small, _, _, _, _ = run(0, batch=40)
+    assert np.array_equal(p_small, p_pipe[:40])
+    p_fused, c_fused, _, tr_fused, st_fused = run(-1)
+    assert _traj_err(p_pipe, p_fused).max() <= 1e-3
+    np.testing.assert_allclose(c_pipe, c_fused, rtol=1e-4)
+    np.testing.assert_allclose(tr_pipe[:, :3], tr_fused[:, :3], rtol=1e-6)  # the first iterations are not yet noise-dominated
+    assert np.all(np.diff(tr_pipe, axis=1) <= 0)
+    p_o, c_o, _, _ = oracle.solve_batch(ocp, opts, x0, xref, threads=8)
+    assert _traj_err(p_pipe, p_o).max() <= 1e-3
+    np.testing.assert_allclose(c_pipe, c_o, rtol=1e-4)
+    assert st_pipe["relinearizations"].min() >= 1 and st_pipe["inner_passes"].min() >= 6
