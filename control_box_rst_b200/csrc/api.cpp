@@ -145,6 +145,7 @@ void fillDeviceOcp(const Structure& s, int B, int S, DeviceOcp& P)
     P.dt_ub      = o.dt_ub;
     P.tcost_w    = std::sqrt((double)(o.n_grid - 1));  // MinimumTime::update, lsq form (minimum_time.h:56-66)
     for (int i = 0; i < B200SQP_MAX_DYN_PARAMS; ++i) P.dyn.p[i] = o.dyn_params[i];
+    prepareDynParams(P.dyn);
 }
 
 int checkHandle(b200sqp_handle h)
@@ -681,6 +682,7 @@ int b200sqp_linearize_dynamics(int32_t dynamics, const double* dyn_params, int32
     CUDA_TRY(cudaSetDevice(device));
     DynParams dyn;
     for (int i = 0; i < B200SQP_MAX_DYN_PARAMS; ++i) dyn.p[i] = dyn_params[i];
+    prepareDynParams(dyn);
     const size_t bx = sizeof(double) * (size_t)batch * nx, bu = sizeof(double) * (size_t)batch * nu;
     const size_t bA = sizeof(double) * (size_t)batch * nx * nx, bB = sizeof(double) * (size_t)batch * nx * nu;
     double *dx = nullptr, *du = nullptr, *dA = nullptr, *dB = nullptr;

@@ -15,6 +15,19 @@
 
 namespace b200sqp {
 
+// x / c.p[i] without an IEEE divide where the host found the parameter admissible (lm_device_types.h prepareDynParams): the same
+// correctly rounded sequence as StepSize::div below, so results equal the reference's `x / p`.
+__device__ __forceinline__ double divByParam(const DynParams& c, int i, double x)
+{
+    if (c.fast_div_mask & (1u << i))
+    {
+        const double q = x * c.rcp[i];
+        const double r = fma(-q, c.p[i], x);
+        return fma(r, c.rcp[i], q);
+    }
+    return x / c.p[i];
+}
+
 // VanDerPolOscillator::dynamics -- src/systems/include/corbo-systems/benchmark/nonlinear_benchmark_systems.h:52-60
 struct VanDerPol
 {
@@ -99,7 +112,7 @@ struct Quadrotor
         sincos(x[4], &sth, &cth);
         sincos(x[5], &spsi, &cpsi);
         const double p = x[9], q = x[10], r = x[11];
-        const double tm = u[0] / c.p[0];
+        const double tm = divByParam(c, 0, u[0]);
         out[0]          = x[6];
         out[1]          = x[7];
         out[2]          = x[8];
@@ -110,9 +123,9 @@ struct Quadrotor
         out[6]          = (cphi * sth * cpsi + sphi * spsi) * tm;
         out[7]          = (cphi * sth * spsi - sphi * cpsi) * tm;
         out[8]          = cphi * cth * tm - c.p[1];
-        out[9]          = (u[1] + (c.p[3] - c.p[4]) * q * r) / c.p[2];
-        out[10]         = (u[2] + (c.p[4] - c.p[2]) * p * r) / c.p[3];
-        out[11]         = (u[3] + (c.p[2] - c.p[3]) * p * q) / c.p[4];
+        out[9]          = divByParam(c, 2, u[1] + (c.p[3] - c.p[4]) * q * r);
+        out[10]         = divByParam(c, 3, u[2] + (c.p[4] - c.p[2]) * p * r);
+        out[11]         = divByParam(c, 4, u[3] + (c.p[2] - c.p[3]) * p * q);
     }
 };
 

@@ -8,7 +8,31 @@ namespace b200sqp {
 struct DynParams
 {
     double p[B200SQP_MAX_DYN_PARAMS];
+    // RN(1 / p[i]) and whether x / p[i] may be evaluated as the correctly rounded three-operation sequence of dynamics.cuh
+    // (StepSize): models that divide by a parameter (quadrotor: mass, inertias) then need no IEEE divide per evaluation
+    double rcp[B200SQP_MAX_DYN_PARAMS];
+    unsigned fast_div_mask;
 };
+
+// host side: fill rcp / fast_div_mask from p (same admissibility rule as StepSize: finite, normal, moderate exponent, significand not all ones)
+inline void prepareDynParams(DynParams& d)
+{
+    d.fast_div_mask = 0;
+    for (int i = 0; i < B200SQP_MAX_DYN_PARAMS; ++i)
+    {
+        d.rcp[i] = 0.0;
+        unsigned long long b;
+        static_assert(sizeof(b) == sizeof(double), "");
+        __builtin_memcpy(&b, &d.p[i], sizeof(b));
+        const unsigned long long man = b & 0xFFFFFFFFFFFFFull;
+        const unsigned ex            = (unsigned)(b >> 52) & 0x7FFu;
+        if (d.p[i] != 0.0 && man != 0xFFFFFFFFFFFFFull && ex > 523u && ex < 1523u)
+        {
+            d.rcp[i] = 1.0 / d.p[i];
+            d.fast_div_mask |= 1u << i;
+        }
+    }
+}
 
 struct DeviceOcp
 {

@@ -9,8 +9,9 @@
 //                         shared memory, the lanes then share out the entries of the normal-equation blocks J^T J, J^T(-r)
 //                         (levenberg_marquardt_sparse.cpp:97-100); residual norms by warp-shuffle reductions
 //   pipeInitKernel        one warp per instance: chi2, ||g||inf, max diag(H) -> initial LM state (:103-126)
-//   pipeFactorKernel      one warp per instance: block-tridiagonal Cholesky of (H + sum(mu) I) with the 16 x 16 blocks in shared
-//                         memory (lane = row), forward and backward substitution (:135-148)
+//   pipeFactorKernel      one warp per instance: block-tridiagonal Cholesky of (H + sum(mu) I); lane = row of the 16 x 16 block in
+//                         registers, pivot columns broadcast by shuffles, the next block prefetched from HBM by TMA bulk copies
+//                         (cp.async.bulk + mbarrier) while the current one is eliminated; forward and backward substitution (:135-148)
 //   pipeTrialKernel       one thread per (instance, interval): trial point and its residuals (:158-167)
 //   pipeControlKernel     one thread per instance: gain ratio, accept/reject, damping (:169-216), the reference's loop verbatim
 //
@@ -50,6 +51,39 @@ __device__ __forceinline__ double driftRoundTrip(double v)
     v += -2e-9;
     v += 1e-9;
     return v;
+}
+
+// ---- TMA bulk copies (cp.async.bulk, 1-D) with mbarrier completion: the factor kernel prefetches the next Hessian block from HBM
+//      into shared memory while the current one is eliminated (SASS: UBLKCP / SYNCS)
+__device__ __forceinline__ unsigned smemAddr(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbarInit(unsigned long long* bar, int count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smemAddr(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbarExpectTx(unsigned long long* bar, unsigned bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smemAddr(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulkLoad(void* dst_smem, const void* src_global, unsigned bytes, unsigned long long* bar)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smemAddr(dst_smem)),
+                 "l"(src_global), "r"(bytes), "r"(smemAddr(bar))
+                 : "memory");
+}
+// bounded wait (a lost copy must not hang the GPU): returns false after ~1e7 polls
+__device__ __forceinline__ bool mbarWait(unsigned long long* bar, unsigned parity)
+{
+    const unsigned addr = smemAddr(bar);
+    for (int spin = 0; spin < 10000000; ++spin)
+    {
+        unsigned ok;
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                     : "=r"(ok)
+                     : "r"(addr), "r"(parity)
+                     : "memory");
+        if (ok) return true;
+    }
+    return false;
 }
 
 __device__ __forceinline__ size_t tiledSlot(int i, int slot, int nslots) { return ((size_t)(i >> 5) * nslots + slot) * 32 + (i & 31); }
@@ -136,11 +170,11 @@ __global__ void __launch_bounds__(128, 4) pipeLinearizeKernel(const __grid_const
     }
     StepSize h(P.dt_ref);
     double e2[NX], e1[NX];
-    defectCall<M, DEFECT>(P.dyn, vec, vec + NX, vec + NX + NU, h, e2);
+    defect<M, DEFECT>(P.dyn, vec, vec + NX, vec + NX + NU, h, e2);  // inlined: the operands stay in registers
 #pragma unroll
     for (int q = 0; q < NV; ++q)
         if (q == p) vec[q] += neg2delta;
-    defectCall<M, DEFECT>(P.dyn, vec, vec + NX, vec + NX + NU, h, e1);
+    defect<M, DEFECT>(P.dyn, vec, vec + NX, vec + NX + NU, h, e1);
     if (p < NV)
     {
 #pragma unroll
@@ -323,58 +357,81 @@ __global__ void __launch_bounds__(128) pipeInitKernel(const __grid_constant__ De
 // (H + mu_acc I) delta = g: block-tridiagonal Cholesky, one warp per instance, lane = row of the current block
 // ---------------------------------------------------------------------------------------------------------------------------
 template <class M>
-__global__ void __launch_bounds__(128) pipeFactorKernel(const __grid_constant__ DeviceOcp P, const __grid_constant__ DeviceState st,
+__global__ void __launch_bounds__(128, 7) pipeFactorKernel(const __grid_constant__ DeviceOcp P, const __grid_constant__ DeviceState st,
                                                         const __grid_constant__ PipeArrays pa)
 {
     using Pd = PipeDim<M>;
     constexpr int NX = Pd::NX, NU = Pd::NU, NB = Pd::NB, ND = Pd::ND, NE = Pd::NE, NXX = Pd::NXX;
     constexpr unsigned FULL = 0xffffffffu;
+    static_assert((ND * 8) % 16 == 0 && (NE * 8) % 16 == 0 && (NXX * 8) % 16 == 0, "bulk copies move multiples of 16 bytes");
     using BS = BlockSolver<M, 0>;
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
     const int i    = blockIdx.x * 4 + wib;
-    // Lane r < NB owns ROW r of the current block in registers; shared memory only stages the coalesced HBM transfers and holds
-    // what other lanes must read (W_k rows, the trailing block of the previous factor).
-    __shared__ double sS[4][NB][NB + 1];    // staging of D_k / L_k (lower triangle)
-    __shared__ double sW[4][NB][NX + 1];    // staging of E_k, then W_k = E_k Lxx^{-T}
+    // Lane r < NB owns ROW r of the current block in registers.  The blocks arrive from HBM by TMA bulk copies into a two-stage
+    // ring per warp (the next block is in flight while the current one is eliminated); shared memory also holds what other lanes
+    // must read (W_k rows, the trailing block of the previous factor) and stages the coalesced stores.
+    __shared__ __align__(16) double stD[4][2][ND];    // forward: D_k        backward: L_k
+    __shared__ __align__(16) double stE[4][2][NE];    // forward: E_k        backward: W_{k+1}
+    __shared__ __align__(16) double stA[4][2][NXX];   // forward: A^T A of interval k+1
+    __shared__ __align__(8) unsigned long long bars[4][2];
     __shared__ double sLxx[4][NX][NX + 1];  // trailing nx x nx block of the previous factor (reciprocal diagonal)
-    __shared__ unsigned char sTriR[ND], sTriC[ND];
-    for (int idx = threadIdx.x; idx < ND; idx += blockDim.x)
+    // W_k overwrites E_k and L_k overwrites D_k in their stage (same packed layouts) once every lane holds its row in registers:
+    // the coalesced stores then run straight out of the stage, and 7 thread blocks (28 warps) fit one SM
+    if (lane == 0)
     {
-        int r = 0;
-        while ((r + 1) * (r + 2) / 2 <= idx) ++r;
-        sTriR[idx] = (unsigned char)r;
-        sTriC[idx] = (unsigned char)(idx - r * (r + 1) / 2);
+        mbarInit(&bars[wib][0], 1);
+        mbarInit(&bars[wib][1], 1);
     }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     __syncthreads();
     if (i >= P.B || !(pa.flags[i] & PF_ACTIVE)) return;
     const int K      = P.K;
     const double mua = pa.mu_acc[i], mu = st.mu[i];
     const bool rowl  = lane < NB;
-    double yp_x      = 0.0;  // lane a < NX: x-part of the forward-substituted rhs of the previous block
+    unsigned phase[2] = {0u, 0u};
+    bool ok           = true;
+    auto issueForward = [&](int k) {
+        if (lane == 0)
+        {
+            const size_t blk = (size_t)i * K + k;
+            const int sidx   = k & 1;
+            const unsigned bytes = ND * 8 + (k > 0 ? NE * 8 : 0) + (k + 1 < K ? NXX * 8 : 0);
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // our generic-proxy writes to this stage come first
+            mbarExpectTx(&bars[wib][sidx], bytes);
+            bulkLoad(stD[wib][sidx], pa.D + blk * ND, ND * 8, &bars[wib][sidx]);
+            if (k > 0) bulkLoad(stE[wib][sidx], pa.E + blk * NE, NE * 8, &bars[wib][sidx]);
+            if (k + 1 < K) bulkLoad(stA[wib][sidx], pa.DA + (blk + 1) * NXX, NXX * 8, &bars[wib][sidx]);
+        }
+    };
+    issueForward(0);
+    double yp_x = 0.0;  // lane a < NX: x-part of the forward-substituted rhs of the previous block
     for (int k = 0; k < K; ++k)
     {
         const size_t blk = (size_t)i * K + k;
-        // ---- stage D_k (+ A^T A of interval k+1 on the x-x part, + damping) and E_k: coalesced runs of the instance-major arrays
-        for (int idx = lane; idx < ND; idx += 32)
-        {
-            const int r = sTriR[idx], c = sTriC[idx];
-            double s    = pa.D[blk * ND + idx];
-            if (k + 1 < K && c >= NU) s += pa.DA[(blk + 1) * NXX + tri(r - NU, c - NU)];
-            if (r == c) s += mua;
-            sS[wib][r][c] = s;
-        }
-        if (k > 0)
-            for (int idx = lane; idx < NE; idx += 32) sW[wib][idx / NX][idx % NX] = pa.E[blk * NE + idx];
-        double y = 0.0;  // lane r < NB holds rhs component r
+        const int sidx   = k & 1;
+        if (k + 1 < K) issueForward(k + 1);  // its stage was last read two iterations ago (warp-synchronised since)
+        double y = 0.0;                       // lane r < NB holds rhs component r
         if (rowl)
         {
             y = pa.g[blk * NB + lane];
             if (k + 1 < K && lane >= NU) y += pa.gA[(blk + 1) * NX + (lane - NU)];
         }
-        __syncwarp();
+        ok = mbarWait(&bars[wib][sidx], phase[sidx]) && ok;
+        phase[sidx] ^= 1u;
+        // ---- row r of S_k = D_k (+ A^T A of interval k+1 on the x-x part, + damping)
         double row[NB];  // row[c], c <= lane
 #pragma unroll
-        for (int c = 0; c < NB; ++c) row[c] = (rowl && c <= lane) ? sS[wib][lane][c] : 0.0;
+        for (int c = 0; c < NB; ++c)
+        {
+            double v = 0.0;
+            if (rowl && c <= lane)
+            {
+                v = stD[wib][sidx][tri(lane, c)];
+                if (k + 1 < K && c >= NU) v += stA[wib][sidx][tri(lane - NU, c - NU)];
+                if (c == lane) v += mua;
+            }
+            row[c] = v;
+        }
         if (k > 0)
         {
             // W_k Lxx^T = E_k: row r per lane
@@ -382,26 +439,26 @@ __global__ void __launch_bounds__(128) pipeFactorKernel(const __grid_constant__ 
 #pragma unroll
             for (int a = 0; a < NX; ++a)
             {
-                double s = rowl ? sW[wib][lane][a] : 0.0;
+                double s = rowl ? stE[wib][sidx][lane * NX + a] : 0.0;
 #pragma unroll
                 for (int b = 0; b < a; ++b) s = fma(-wr[b], sLxx[wib][a][b], s);
                 wr[a] = s * sLxx[wib][a][a];
             }
-            __syncwarp();
+            __syncwarp();  // every lane has read its E row
             if (rowl)
             {
 #pragma unroll
-                for (int a = 0; a < NX; ++a) sW[wib][lane][a] = wr[a];
+                for (int a = 0; a < NX; ++a) stE[wib][sidx][lane * NX + a] = wr[a];
             }
             __syncwarp();
-            for (int idx = lane; idx < NE; idx += 32) pa.W[blk * NE + idx] = sW[wib][idx / NX][idx % NX];
+            for (int idx = lane; idx < NE; idx += 32) pa.W[blk * NE + idx] = stE[wib][sidx][idx];
             // Schur complement and rhs update
 #pragma unroll
             for (int c = 0; c < NB; ++c)
             {
                 double s = row[c];
 #pragma unroll
-                for (int a = 0; a < NX; ++a) s = fma(-wr[a], sW[wib][c][a], s);
+                for (int a = 0; a < NX; ++a) s = fma(-wr[a], stE[wib][sidx][c * NX + a], s);
                 row[c] = (c <= lane) ? s : 0.0;
             }
 #pragma unroll
@@ -425,13 +482,13 @@ __global__ void __launch_bounds__(128) pipeFactorKernel(const __grid_constant__ 
                 row[c]          = fma(-l, lc, row[c]);  // lanes < c hold zeros there and l = 0 for lanes <= j
             }
         }
-        // ---- store the factor (coalesced through the staging tile) and the forward-substituted rhs, keep what the next block needs
+        // ---- store the factor (coalesced, packed order) and the forward-substituted rhs, keep what the next block needs
         __syncwarp();
         if (rowl)
         {
 #pragma unroll
             for (int c = 0; c < NB; ++c)
-                if (c <= lane) sS[wib][lane][c] = row[c];
+                if (c <= lane) stD[wib][sidx][tri(lane, c)] = row[c];
             pa.y[blk * NB + lane] = y;
             if (lane >= NU)
             {
@@ -442,17 +499,33 @@ __global__ void __launch_bounds__(128) pipeFactorKernel(const __grid_constant__ 
         }
         yp_x = __shfl_sync(FULL, y, NU + (lane < NX ? lane : 0));
         __syncwarp();
-        for (int idx = lane; idx < ND; idx += 32) pa.L[blk * ND + idx] = sS[wib][sTriR[idx]][sTriC[idx]];
+        for (int idx = lane; idx < ND; idx += 32) pa.L[blk * ND + idx] = stD[wib][sidx][idx];
         __syncwarp();
     }
-    // ---- back-substitution, bottom-up: L_k^T delta_k = y_k - W_{k+1}^T delta_{k+1} (x-part)
+    // ---- back-substitution, bottom-up: L_k^T delta_k = y_k - W_{k+1}^T delta_{k+1} (x-part).  The factor blocks were written through
+    //      the generic proxy above and are read back by the async proxy: fence in between.
+    __threadfence();
+    asm volatile("fence.proxy.async;" ::: "memory");
+    __syncwarp();
+    auto issueBackward = [&](int k, int sidx) {
+        if (lane == 0)
+        {
+            const size_t blk = (size_t)i * K + k;
+            const unsigned bytes = ND * 8 + (k + 1 < K ? NE * 8 : 0);
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            mbarExpectTx(&bars[wib][sidx], bytes);
+            bulkLoad(stD[wib][sidx], pa.L + blk * ND, ND * 8, &bars[wib][sidx]);
+            if (k + 1 < K) bulkLoad(stE[wib][sidx], pa.W + (blk + 1) * NE, NE * 8, &bars[wib][sidx]);
+        }
+    };
+    issueBackward(K - 1, 0);
     double dn2 = 0.0, dq = 0.0, dnext = 0.0;  // dnext: lane r holds delta_{k+1}[r]
-    for (int k = K - 1; k >= 0; --k)
+    int step = 0;
+    for (int k = K - 1; k >= 0; --k, ++step)
     {
         const size_t blk = (size_t)i * K + k;
-        for (int idx = lane; idx < ND; idx += 32) sS[wib][sTriR[idx]][sTriC[idx]] = pa.L[blk * ND + idx];
-        if (k + 1 < K)
-            for (int idx = lane; idx < NE; idx += 32) sW[wib][idx / NX][idx % NX] = pa.W[(blk + 1) * NE + idx];
+        const int sidx   = step & 1;
+        if (k > 0) issueBackward(k - 1, sidx ^ 1);
         double d = 0.0, gfull = 0.0;
         if (rowl)
         {
@@ -460,19 +533,20 @@ __global__ void __launch_bounds__(128) pipeFactorKernel(const __grid_constant__ 
             gfull = pa.g[blk * NB + lane];
             if (k + 1 < K && lane >= NU) gfull += pa.gA[(blk + 1) * NX + (lane - NU)];
         }
-        __syncwarp();
+        ok = mbarWait(&bars[wib][sidx], phase[sidx]) && ok;
+        phase[sidx] ^= 1u;
         if (k + 1 < K)
         {
             double s = 0.0;
             const int a = (lane >= NU && rowl) ? lane - NU : 0;
 #pragma unroll
-            for (int r = 0; r < NB; ++r) s = fma(sW[wib][r][a], __shfl_sync(FULL, dnext, r), s);
+            for (int r = 0; r < NB; ++r) s = fma(stE[wib][sidx][r * NX + a], __shfl_sync(FULL, dnext, r), s);
             if (lane >= NU && rowl) d -= s;
         }
-        // L^T delta = d, column-oriented backward: lane r needs L[j][r] for j > r, i.e. column r of the factor
+        // L^T delta = d, column-oriented backward: lane r needs L[j][r] for j >= r, i.e. column r of the factor
         double colr[NB];
 #pragma unroll
-        for (int j = 0; j < NB; ++j) colr[j] = (rowl && j >= lane) ? sS[wib][j][lane] : 0.0;
+        for (int j = 0; j < NB; ++j) colr[j] = (rowl && j >= lane) ? stD[wib][sidx][tri(j, lane)] : 0.0;
 #pragma unroll
         for (int j = NB - 1; j >= 0; --j)
         {
@@ -497,7 +571,7 @@ __global__ void __launch_bounds__(128) pipeFactorKernel(const __grid_constant__ 
     }
     if (lane == 0)
     {
-        pa.dn2[i] = dn2;
+        pa.dn2[i] = ok ? dn2 : CUDART_NAN;  // a lost bulk copy poisons the step: the control kernel then rejects it
         pa.dq[i]  = dq;
         st.n_factor[i] += 1;
     }
