@@ -86,6 +86,12 @@ __device__ __forceinline__ bool mbarWait(unsigned long long* bar, unsigned parit
     return false;
 }
 
+// fp64 tensor-core tile: D(8x8) += A(8x4) B(4x8); per lane a = A[lane/4][lane%4], b = B[lane%4][lane/4], d0/d1 = D[lane/4][2(lane%4) + {0,1}]
+__device__ __forceinline__ void dmma884(double& d0, double& d1, double a, double b)
+{
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};" : "+d"(d0), "+d"(d1) : "d"(a), "d"(b));
+}
+
 __device__ __forceinline__ size_t tiledSlot(int i, int slot, int nslots) { return ((size_t)(i >> 5) * nslots + slot) * 32 + (i & 31); }
 
 // ---------------------------------------------------------------------------------------------------------------------------
@@ -246,14 +252,44 @@ __global__ void __launch_bounds__(128, 4) pipeLinearizeKernel(const __grid_const
     const size_t blk = (size_t)i * K + k;
     double* Dk  = pa.D + blk * ND;
     double* gk  = pa.g + blk * NB;
-    for (int idx = lane; idx < ND; idx += 32)
-    {
-        const int r = sTriR[idx], c = sTriC[idx];
-        double s    = 0.0;
+    // The three Gram products -- G_b G_b^T (nb x nb), G_b G_a^T (nb x nx), G_a G_a^T (nx x nx), inner dimension nx -- run on the
+    // tensor cores: fp64 mma.sync m8n8k4 tiles (SASS: DMMA) with fragments read straight from the column store in shared memory.
+    // Rows >= nx of a "G_a" tile are columns of G_b (the store is contiguous): those products are computed and dropped.
+    static_assert(NX % 4 == 0 && NB <= 16 && NX <= 16, "8x8 output tiles over a 16-column window, k in steps of 4");
+    const int fm = lane >> 2, fk = lane & 3;  // fragment coordinates: A(m = fm, k = fk), B(k = fk, n = fm), C(m = fm, n = 2 fk + {0,1})
+    auto gram = [&](int row_base, int r0, int col_base, int c0, double& d0, double& d1) {
+        d0 = 0.0;
+        d1 = 0.0;
 #pragma unroll
-        for (int q = 0; q < NX; ++q) s = fma(sG[wib][NX + r][q], sG[wib][NX + c][q], s);
-        if (r == c) s = fma(sCost[wib][1][r], sCost[wib][1][r], fma(sCost[wib][3][r], sCost[wib][3][r], s));
-        Dk[idx] = s;
+        for (int k0 = 0; k0 < NX; k0 += 4)
+        {
+            const double af = sG[wib][row_base + r0 + fm][k0 + fk];
+            const double bf = sG[wib][col_base + c0 + fm][k0 + fk];
+            dmma884(d0, d1, af, bf);
+        }
+    };
+    // block k: G_b G_b^T, lower triangle, + the diagonal cost / bound rows
+#pragma unroll
+    for (int t = 0; t < 3; ++t)
+    {
+        const int r0 = (t == 0) ? 0 : 8, c0 = (t == 2) ? 8 : 0;
+        if (r0 + 8 > NB && r0 >= NB) continue;
+        double d0, d1;
+        gram(NX, r0, NX, c0, d0, d1);
+        const int r = r0 + fm, c = c0 + 2 * fk;
+        if (r < NB)
+        {
+            if (c <= r)
+            {
+                if (r == c) d0 = fma(sCost[wib][1][r], sCost[wib][1][r], fma(sCost[wib][3][r], sCost[wib][3][r], d0));
+                Dk[tri(r, c)] = d0;
+            }
+            if (c + 1 <= r)
+            {
+                if (r == c + 1) d1 = fma(sCost[wib][1][r], sCost[wib][1][r], fma(sCost[wib][3][r], sCost[wib][3][r], d1));
+                Dk[tri(r, c + 1)] = d1;
+            }
+        }
     }
     if (lane < NB)
     {
@@ -268,21 +304,27 @@ __global__ void __launch_bounds__(128, 4) pipeLinearizeKernel(const __grid_const
         double* Ek  = pa.E + blk * NE;
         double* DAk = pa.DA + blk * NXX;
         double* gAk = pa.gA + blk * NX;
-        for (int idx = lane; idx < NE; idx += 32)
-        {
-            const int r = idx / NX, a = idx % NX;
-            double s    = 0.0;
+        // E_k = G_b G_a^T: rows = slots of block k, columns = x-part of block k-1
 #pragma unroll
-            for (int q = 0; q < NX; ++q) s = fma(sG[wib][NX + r][q], sG[wib][a][q], s);
-            Ek[idx] = s;
+        for (int t = 0; t < 4; ++t)
+        {
+            const int r0 = (t & 1) * 8, c0 = (t >> 1) * 8;
+            double d0, d1;
+            gram(NX, r0, 0, c0, d0, d1);
+            const int r = r0 + fm, c = c0 + 2 * fk;
+            if (r < NB && c < NX) Ek[r * NX + c] = d0;
+            if (r < NB && c + 1 < NX) Ek[r * NX + c + 1] = d1;
         }
-        for (int idx = lane; idx < NXX; idx += 32)
-        {
-            const int a = sTriR[idx], b = sTriC[idx];
-            double s    = 0.0;
+        // A^T A of this interval (belongs to block k-1): G_a G_a^T, lower triangle
 #pragma unroll
-            for (int q = 0; q < NX; ++q) s = fma(sG[wib][a][q], sG[wib][b][q], s);
-            DAk[idx] = s;
+        for (int t = 0; t < 3; ++t)
+        {
+            const int r0 = (t == 0) ? 0 : 8, c0 = (t == 2) ? 8 : 0;
+            double d0, d1;
+            gram(0, r0, 0, c0, d0, d1);
+            const int r = r0 + fm, c = c0 + 2 * fk;
+            if (r < NX && c <= r) DAk[tri(r, c)] = d0;
+            if (r < NX && c + 1 <= r) DAk[tri(r, c + 1)] = d1;
         }
         if (lane < NX)
         {
@@ -418,20 +460,6 @@ __global__ void __launch_bounds__(128, 7) pipeFactorKernel(const __grid_constant
         }
         ok = mbarWait(&bars[wib][sidx], phase[sidx]) && ok;
         phase[sidx] ^= 1u;
-        // ---- row r of S_k = D_k (+ A^T A of interval k+1 on the x-x part, + damping)
-        double row[NB];  // row[c], c <= lane
-#pragma unroll
-        for (int c = 0; c < NB; ++c)
-        {
-            double v = 0.0;
-            if (rowl && c <= lane)
-            {
-                v = stD[wib][sidx][tri(lane, c)];
-                if (k + 1 < K && c >= NU) v += stA[wib][sidx][tri(lane - NU, c - NU)];
-                if (c == lane) v += mua;
-            }
-            row[c] = v;
-        }
         if (k > 0)
         {
             // W_k Lxx^T = E_k: row r per lane
@@ -452,17 +480,45 @@ __global__ void __launch_bounds__(128, 7) pipeFactorKernel(const __grid_constant
             }
             __syncwarp();
             for (int idx = lane; idx < NE; idx += 32) pa.W[blk * NE + idx] = stE[wib][sidx][idx];
-            // Schur complement and rhs update
+            // Schur complement S_k -= W_k W_k^T on the staged block with fp64 tensor-core tiles (DMMA m8n8k4): lower triangle = the
+            // 8x8 tiles (0,0), (1,0), (1,1); fragments straight from the stage (W packed [r][a], S packed lower by rows)
+            const int fm = lane >> 2, fk = lane & 3;
 #pragma unroll
-            for (int c = 0; c < NB; ++c)
+            for (int t = 0; t < 3; ++t)
             {
-                double s = row[c];
+                const int r0 = (t == 0) ? 0 : 8, c0 = (t == 2) ? 8 : 0;
+                const int r = r0 + fm, c = c0 + 2 * fk;
+                const bool in0 = r < NB && c <= r, in1 = r < NB && c + 1 <= r;
+                double d0 = in0 ? stD[wib][sidx][tri(r, c)] : 0.0;
+                double d1 = in1 ? stD[wib][sidx][tri(r, c + 1)] : 0.0;
 #pragma unroll
-                for (int a = 0; a < NX; ++a) s = fma(-wr[a], stE[wib][sidx][c * NX + a], s);
-                row[c] = (c <= lane) ? s : 0.0;
+                for (int k0 = 0; k0 < NX; k0 += 4)
+                {
+                    const double af = (r0 + fm < NB) ? -stE[wib][sidx][(r0 + fm) * NX + k0 + fk] : 0.0;
+                    const double bf = (c0 + fm < NB) ? stE[wib][sidx][(c0 + fm) * NX + k0 + fk] : 0.0;
+                    dmma884(d0, d1, af, bf);
+                }
+                if (in0) stD[wib][sidx][tri(r, c)] = d0;
+                if (in1) stD[wib][sidx][tri(r, c + 1)] = d1;
             }
+            // rhs update
 #pragma unroll
             for (int a = 0; a < NX; ++a) y = fma(-wr[a], __shfl_sync(FULL, yp_x, a), y);
+            __syncwarp();
+        }
+        // ---- row r of S_k = D_k - W_k W_k^T (+ A^T A of interval k+1 on the x-x part, + damping)
+        double row[NB];  // row[c], c <= lane
+#pragma unroll
+        for (int c = 0; c < NB; ++c)
+        {
+            double v = 0.0;
+            if (rowl && c <= lane)
+            {
+                v = stD[wib][sidx][tri(lane, c)];
+                if (k + 1 < K && c >= NU) v += stA[wib][sidx][tri(lane - NU, c - NU)];
+                if (c == lane) v += mua;
+            }
+            row[c] = v;
         }
         // ---- Cholesky of S_k in registers (right-looking; column j of L is spread over the lanes, broadcast by shuffles) fused with
         //      the forward substitution of the rhs
