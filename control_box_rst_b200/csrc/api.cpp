@@ -4,6 +4,7 @@
 #include <cuda_runtime.h>
 
 #include <cmath>
+#include <algorithm>
 #include <cstring>
 #include <mutex>
 #include <string>
@@ -84,6 +85,10 @@ struct b200sqp_solver
     void* peer_mapped[MAX_PEERS] = {};       // cudaIpcOpenMemHandle results (null for own rank)
     unsigned long long peer_solves = 0;      // solves launched since attach
     int* d_num_shift = nullptr;
+    // closed-loop log (b200sqp_closed_loop)
+    double *d_loop_x = nullptr, *d_loop_u = nullptr, *d_loop_chi2 = nullptr;
+    int32_t* d_loop_status = nullptr;
+    int loop_steps = 0;
     PipeArrays pipe{};          // warp-cooperative pipeline (large stage blocks), allocated when the kernel set has one and the
     bool use_pipeline = false;  // structure is eligible
     bool pipeline_enabled = true;
@@ -403,23 +408,16 @@ int b200sqp_get_dims(b200sqp_handle h, b200sqp_dims* out)
     return B200SQP_OK;
 }
 
-int b200sqp_set_problem_data(b200sqp_handle h, const double* x0, const double* xref)
+// start states / references that are already in HBM ([B][nx], host order): the device half of b200sqp_set_problem_data
+static int startStatesFromDevice(b200sqp_handle h, const double* d_x0, const double* d_xref /*null = keep the current reference*/)
 {
-    int rc = checkHandle(h);
-    if (rc) return rc;
-    if (!x0) return fail(B200SQP_ERR_INVALID, "x0 is null");
-    const size_t bytes = sizeof(double) * (size_t)h->B * h->s.nx;
-    CUDA_TRY(cudaMemcpyAsync(h->d_x0_host_order, x0, bytes, cudaMemcpyHostToDevice, h->stream));
-    launchTransposeIn(h->d_x0_host_order, h->s.nx, h->st.x0, h->B, h->S, h->stream);
-    if (xref)
+    launchTransposeIn(d_x0, h->s.nx, h->st.x0, h->B, h->S, h->stream);
+    h->launches += 1;
+    if (d_xref)
     {
-        CUDA_TRY(cudaMemcpyAsync(h->d_xref_host_order, xref, bytes, cudaMemcpyHostToDevice, h->stream));
-        launchTransposeIn(h->d_xref_host_order, h->s.nx, h->st.xref, h->B, h->S, h->stream);
+        launchTransposeIn(d_xref, h->s.nx, h->st.xref, h->B, h->S, h->stream);
         h->launches += 1;
     }
-    else
-        CUDA_TRY(cudaMemsetAsync(h->st.xref, 0, sizeof(double) * (size_t)h->S * h->s.nx, h->stream));
-    h->launches += 1;
     // fixed goal components follow the reference: _xf.values()[i] = xref[i] (full_discretization_grid_base.cpp:102-106)
     const int nb = h->s.nb, xo = h->s.nu + h->s.vt;
     unsigned mask = 0;
@@ -432,6 +430,41 @@ int b200sqp_set_problem_data(b200sqp_handle h, const double* x0, const double* x
     }
     CUDA_TRY(cudaGetLastError());
     return B200SQP_OK;
+}
+
+// the device half of b200sqp_warm_start_shift: d_x0_new [B][nx] in HBM
+static int warmStartShiftFromDevice(b200sqp_handle h, const double* d_x0_new, int* d_num_shift)
+{
+    if (h->s.ocp.grid != B200SQP_GRID_FD_UNIFORM)
+        return fail(B200SQP_ERR_UNSUPPORTED, "warm-start shifting is implemented for FiniteDifferencesGrid structures only");
+    launchWarmStartShift(d_x0_new, h->st.x0, h->st.z[0], h->st.z[1], h->st.cur, h->s.K, h->s.nx, h->s.nu, d_num_shift, h->B, h->stream);
+    h->launches += 1;
+    CUDA_TRY(cudaGetLastError());
+    // fixed goal components follow the reference (full_discretization_grid_base.cpp:102-106)
+    const int nb = h->s.nb, xo = h->s.nu + h->s.vt;
+    unsigned mask = 0;
+    for (int i = 0; i < h->s.nx; ++i)
+        if (h->s.xfFixed(i)) mask |= 1u << i;
+    if (mask)
+    {
+        launchFillPinned(h->st.xref, h->st.z[0], h->st.z[1], (h->s.K - 1) * nb + xo, h->s.K * nb, h->s.nx, mask, h->B, h->stream);
+        h->launches += 1;
+    }
+    return B200SQP_OK;
+}
+
+int b200sqp_set_problem_data(b200sqp_handle h, const double* x0, const double* xref)
+{
+    int rc = checkHandle(h);
+    if (rc) return rc;
+    if (!x0) return fail(B200SQP_ERR_INVALID, "x0 is null");
+    const size_t bytes = sizeof(double) * (size_t)h->B * h->s.nx;
+    CUDA_TRY(cudaMemcpyAsync(h->d_x0_host_order, x0, bytes, cudaMemcpyHostToDevice, h->stream));
+    if (xref)
+        CUDA_TRY(cudaMemcpyAsync(h->d_xref_host_order, xref, bytes, cudaMemcpyHostToDevice, h->stream));
+    else
+        CUDA_TRY(cudaMemsetAsync(h->st.xref, 0, sizeof(double) * (size_t)h->S * h->s.nx, h->stream));
+    return startStatesFromDevice(h, h->d_x0_host_order, xref ? h->d_xref_host_order : nullptr);
 }
 
 int b200sqp_initialize_trajectories(b200sqp_handle h)
@@ -455,20 +488,8 @@ int b200sqp_warm_start_shift(b200sqp_handle h, const double* x0_new, int32_t* nu
     const size_t bytes = sizeof(double) * (size_t)h->B * h->s.nx;
     CUDA_TRY(cudaMemcpyAsync(h->d_x0_host_order, x0_new, bytes, cudaMemcpyHostToDevice, h->stream));
     if (num_shift && !h->d_num_shift) CUDA_TRY(h->alloc(&h->d_num_shift, (size_t)h->B));
-    launchWarmStartShift(h->d_x0_host_order, h->st.x0, h->st.z[0], h->st.z[1], h->st.cur, h->s.K, h->s.nx, h->s.nu,
-                         num_shift ? h->d_num_shift : nullptr, h->B, h->stream);
-    h->launches += 1;
-    CUDA_TRY(cudaGetLastError());
-    // fixed goal components follow the reference (full_discretization_grid_base.cpp:102-106)
-    const int nb = h->s.nb, xo = h->s.nu + h->s.vt;
-    unsigned mask = 0;
-    for (int i = 0; i < h->s.nx; ++i)
-        if (h->s.xfFixed(i)) mask |= 1u << i;
-    if (mask)
-    {
-        launchFillPinned(h->st.xref, h->st.z[0], h->st.z[1], (h->s.K - 1) * nb + xo, h->s.K * nb, h->s.nx, mask, h->B, h->stream);
-        h->launches += 1;
-    }
+    rc = warmStartShiftFromDevice(h, h->d_x0_host_order, num_shift ? h->d_num_shift : nullptr);
+    if (rc) return rc;
     if (num_shift)
     {
         CUDA_TRY(cudaMemcpyAsync(num_shift, h->d_num_shift, sizeof(int32_t) * h->B, cudaMemcpyDeviceToHost, h->stream));
@@ -620,6 +641,123 @@ int b200sqp_mpc_step(b200sqp_handle h, const b200sqp_lm_options* opts, int32_t m
     CUDA_TRY(cudaMemcpyAsync(u0_out, h->d_u0, sizeof(double) * (size_t)h->B * h->s.nu, cudaMemcpyDeviceToHost, h->stream));
     if (status_out) CUDA_TRY(cudaMemcpyAsync(status_out, h->st.status, sizeof(int32_t) * h->B, cudaMemcpyDeviceToHost, h->stream));
     if (chi2_out) CUDA_TRY(cudaMemcpyAsync(chi2_out, h->st.chi2, sizeof(double) * h->B, cudaMemcpyDeviceToHost, h->stream));
+    CUDA_TRY(cudaStreamSynchronize(h->stream));
+    return B200SQP_OK;
+}
+
+int b200sqp_plant_step(int32_t dynamics, const double* dyn_params, int32_t integrator, double dt, int32_t batch, const double* x, const double* u,
+                       double* x_next, int32_t device)
+{
+    if (!dyn_params || !x || !u || !x_next || batch < 1 || (integrator != 0 && integrator != 1)) return fail(B200SQP_ERR_INVALID, "bad argument");
+    int nx = 0, nu = 0;
+    if (!dynamicsDimensions(dynamics, nx, nu)) return fail(B200SQP_ERR_UNSUPPORTED, "unknown dynamics id (closed functor registry; no CPU fallback)");
+    int count = 0;
+    if (cudaGetDeviceCount(&count) != cudaSuccess || count == 0)
+    {
+        cudaGetLastError();
+        return fail(B200SQP_ERR_NO_DEVICE, "no CUDA device visible: the plant simulation only exists as sm_100a kernels");
+    }
+    if (device < 0 || device >= count) return fail(B200SQP_ERR_INVALID, "device index out of range");
+    CUDA_TRY(cudaSetDevice(device));
+    DynParams dyn;
+    for (int i = 0; i < B200SQP_MAX_DYN_PARAMS; ++i) dyn.p[i] = dyn_params[i];
+    prepareDynParams(dyn);
+    const size_t bx = sizeof(double) * (size_t)batch * nx, bu = sizeof(double) * (size_t)batch * nu;
+    double *dx = nullptr, *du = nullptr, *dn = nullptr;
+    cudaError_t e = cudaMalloc(&dx, bx);
+    if (e == cudaSuccess) e = cudaMalloc(&du, bu);
+    if (e == cudaSuccess) e = cudaMalloc(&dn, bx);
+    if (e == cudaSuccess) e = cudaMemcpy(dx, x, bx, cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) e = cudaMemcpy(du, u, bu, cudaMemcpyHostToDevice);
+    if (e == cudaSuccess)
+    {
+        launchPlantStep(dynamics, dyn, integrator, dt, batch, dx, du, dn, nullptr, nullptr);
+        e = cudaGetLastError();
+    }
+    if (e == cudaSuccess) e = cudaMemcpy(x_next, dn, bx, cudaMemcpyDeviceToHost);
+    cudaFree(dx);
+    cudaFree(du);
+    cudaFree(dn);
+    if (e != cudaSuccess) return fail(B200SQP_ERR_CUDA, std::string("plant_step: ") + cudaGetErrorString(e));
+    return B200SQP_OK;
+}
+
+int b200sqp_closed_loop(b200sqp_handle h, const b200sqp_lm_options* opts, int32_t mode, int32_t integrator, double plant_dt, int32_t steps,
+                        const double* x0, const double* xref, double* u_applied, double* x_closed, double* chi2_out, int32_t* status_out)
+{
+    int rc = checkHandle(h);
+    if (rc) return rc;
+    if (mode < 0 || mode > 2) return fail(B200SQP_ERR_INVALID, "mode must be 0 (cold every step), 1 (keep) or 2 (shift)");
+    if (integrator != 0 && integrator != 1) return fail(B200SQP_ERR_INVALID, "integrator must be 0 (explicit Euler) or 1 (Runge-Kutta 4)");
+    if (!x0 || steps < 1 || !(plant_dt > 0.0)) return fail(B200SQP_ERR_INVALID, "bad argument");
+    if (mode == 2 && h->s.ocp.grid != B200SQP_GRID_FD_UNIFORM)
+        return fail(B200SQP_ERR_UNSUPPORTED, "warm-start shifting is implemented for FiniteDifferencesGrid structures only");
+    const int nx = h->s.nx, nu = h->s.nu, B = h->B;
+    const size_t sx = (size_t)B * nx, su = (size_t)B * nu;
+    // the closed-loop log lives in HBM for the whole run: states [steps+1][B][nx], applied controls [steps][B][nu], chi2 / status [steps][B]
+    if (steps > h->loop_steps)
+    {
+        for (void* p : {(void*)h->d_loop_x, (void*)h->d_loop_u, (void*)h->d_loop_chi2, (void*)h->d_loop_status})
+            if (p)
+            {
+                h->allocations.erase(std::remove(h->allocations.begin(), h->allocations.end(), p), h->allocations.end());
+                cudaFree(p);
+            }
+        h->d_loop_x = h->d_loop_u = h->d_loop_chi2 = nullptr;
+        h->d_loop_status                            = nullptr;
+        h->loop_steps                               = 0;
+        CUDA_TRY(h->alloc(&h->d_loop_x, (size_t)(steps + 1) * sx));
+        CUDA_TRY(h->alloc(&h->d_loop_u, (size_t)steps * su));
+        CUDA_TRY(h->alloc(&h->d_loop_chi2, (size_t)steps * B));
+        CUDA_TRY(h->alloc(&h->d_loop_status, (size_t)steps * B));
+        h->loop_steps = steps;
+    }
+    CUDA_TRY(cudaMemcpyAsync(h->d_loop_x, x0, sizeof(double) * sx, cudaMemcpyHostToDevice, h->stream));
+    if (xref)
+        CUDA_TRY(cudaMemcpyAsync(h->d_xref_host_order, xref, sizeof(double) * sx, cudaMemcpyHostToDevice, h->stream));
+    else
+        CUDA_TRY(cudaMemsetAsync(h->st.xref, 0, sizeof(double) * (size_t)h->S * nx, h->stream));
+    // The reference keeps time in integer nanoseconds (corbo::Time / Duration over std::chrono, src/core/include/corbo-core/time.h:140,283:
+    // fromSec truncates t * 1e9; toSec divides the tick count by 1e9) and the plant integrates over the interval its control buffer
+    // hands back, (t + dt) - t in doubles (TimeValueBuffer::getValues, src/systems/src/time_value_buffer.cpp:74: `ts + dt - cur_t` with
+    // cur_t = ts), which differs from dt in the last bits for t != 0.  Mirrored here step by step.
+    const long long dt_ticks = (long long)(plant_dt * 1e9);
+    const double dt_sec      = (double)dt_ticks / 1e9;
+    for (int s = 0; s < steps; ++s)
+    {
+        const double t_sec    = (double)((long long)s * dt_ticks) / 1e9;
+        const volatile double t_end = t_sec + dt_sec;  // volatile: keep the two roundings apart
+        const double step_dt  = t_end - t_sec;
+        const double* d_x = h->d_loop_x + (size_t)s * sx;  // the measurement of this step (plant output = state, no observer dynamics)
+        // ---- controller: PredictiveController::step -> StructuredOptimalControlProblem::compute (grid update, solve) + getFirstControlInput
+        if (s > 0 && mode == 2)
+        {
+            rc = warmStartShiftFromDevice(h, d_x, nullptr);  // needs the previous start state: before it is replaced
+            if (rc) return rc;
+        }
+        rc = startStatesFromDevice(h, d_x, (s == 0 && xref) ? h->d_xref_host_order : nullptr);
+        if (rc) return rc;
+        if (s == 0 || mode == 0)
+        {
+            rc = b200sqp_initialize_trajectories(h);
+            if (rc) return rc;
+        }
+        rc = b200sqp_solve_async(h, opts, 1);
+        if (rc) return rc;
+        launchFirstControls(h->st.z[0], h->st.z[1], h->st.cur, nu, h->s.K * h->s.nb, h->d_u0, B, h->S, h->stream);
+        // ---- plant: SimulatedPlant::control, one solveIVP over plant_dt with the first control held
+        if (!launchPlantStep(h->s.ocp.dynamics, h->P.dyn, integrator, step_dt, B, d_x, h->d_u0, h->d_loop_x + (size_t)(s + 1) * sx,
+                             h->d_loop_u + (size_t)s * su, h->stream))
+            return fail(B200SQP_ERR_UNSUPPORTED, "dynamics id not in the plant registry");
+        h->launches += 2;
+        CUDA_TRY(cudaGetLastError());
+        CUDA_TRY(cudaMemcpyAsync(h->d_loop_chi2 + (size_t)s * B, h->st.chi2, sizeof(double) * B, cudaMemcpyDeviceToDevice, h->stream));
+        CUDA_TRY(cudaMemcpyAsync(h->d_loop_status + (size_t)s * B, h->st.status, sizeof(int32_t) * B, cudaMemcpyDeviceToDevice, h->stream));
+    }
+    if (u_applied) CUDA_TRY(cudaMemcpyAsync(u_applied, h->d_loop_u, sizeof(double) * steps * su, cudaMemcpyDeviceToHost, h->stream));
+    if (x_closed) CUDA_TRY(cudaMemcpyAsync(x_closed, h->d_loop_x, sizeof(double) * (steps + 1) * sx, cudaMemcpyDeviceToHost, h->stream));
+    if (chi2_out) CUDA_TRY(cudaMemcpyAsync(chi2_out, h->d_loop_chi2, sizeof(double) * (size_t)steps * B, cudaMemcpyDeviceToHost, h->stream));
+    if (status_out) CUDA_TRY(cudaMemcpyAsync(status_out, h->d_loop_status, sizeof(int32_t) * (size_t)steps * B, cudaMemcpyDeviceToHost, h->stream));
     CUDA_TRY(cudaStreamSynchronize(h->stream));
     return B200SQP_OK;
 }

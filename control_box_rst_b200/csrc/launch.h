@@ -55,6 +55,10 @@ void launchFirstControls(const double* z0, const double* z1, const int* cur, int
 struct DynParams;
 bool launchLinearizeDynamics(int dynamics, const DynParams& dyn, int method, int B, const double* x, const double* u, double* A, double* Bm,
                              cudaStream_t);
+// SimulatedPlant::control for B plants: x_next = solveIVP(x, u, dt), integrator 0 = explicit Euler, 1 = RK4 (kernels_plant.cu);
+// x, x_next [B][nx], u [B][nu]; u_log [B][nu] or null receives a copy of u; false = dynamics id not in the registry
+bool launchPlantStep(int dynamics, const DynParams& dyn, int integrator, double dt, int B, const double* x, const double* u, double* x_next,
+                     double* u_log, cudaStream_t);
 // FullDiscretizationGridBase::warmStartShifting + findNearestState per instance, then x_seq.front() = x0_new (util_kernels.cu)
 void launchWarmStartShift(const double* x0_new /*[B][nx]*/, double* x0 /*tiled*/, double* z0, double* z1, const int* cur, int K, int nx, int nu,
                           int* num_shift /*[B] or null*/, int B, cudaStream_t);

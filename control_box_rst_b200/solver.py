@@ -28,6 +28,7 @@ ABI_SYMBOLS = [
     "b200sqp_last_solve_ms", "b200sqp_launch_count", "b200sqp_device_pointers", "b200sqp_set_stream", "b200sqp_set_threads_per_instance",
     "b200sqp_set_phase_profile", "b200sqp_get_phase_cycles", "b200sqp_final_constraint_indices",
     "b200sqp_peer_export", "b200sqp_peer_attach", "b200sqp_peer_wait", "b200sqp_peer_gathered", "b200sqp_peer_detach", "b200sqp_peer_status", "b200sqp_linearize_dynamics", "b200sqp_warm_start_shift", "b200sqp_mpc_step",
+    "b200sqp_plant_step", "b200sqp_closed_loop",
 ]
 
 
@@ -124,6 +125,25 @@ def linearize_dynamics(dynamics, dyn_params, x, u, method="forward", device=0):
                                                       _d(x), _d(u), _d(A), _d(Bm), C.c_int32(device)))
     # the library writes column-major blocks per point
     return A.transpose(0, 2, 1).copy(), Bm.transpose(0, 2, 1).copy()
+
+
+INTEGRATORS = {"euler": 0, "rk4": 1}
+
+
+def plant_step(dynamics, dyn_params, x, u, dt, integrator="euler", device=0):
+    """SimulatedPlant::control for a batch of plants on the device: x [B, nx], u [B, nu] -> x_next [B, nx] after one solveIVP over dt
+    ('euler' = IntegratorExplicitEuler, the plant's default; 'rk4' = IntegratorExplicitRungeKutta4)."""
+    nx, nu = abi.DYN_DIMS[dynamics]
+    x = np.ascontiguousarray(x, np.float64).reshape(-1, nx)
+    u = np.ascontiguousarray(u, np.float64).reshape(-1, nu)
+    B = x.shape[0]
+    assert u.shape[0] == B
+    p = np.zeros(abi.MAX_DYN_PARAMS)
+    p[:len(dyn_params)] = dyn_params
+    xn = np.zeros((B, nx))
+    _check(load_library().b200sqp_plant_step(C.c_int32(dynamics), _d(p), C.c_int32(INTEGRATORS[integrator]), C.c_double(dt), C.c_int32(B),
+                                              _d(x), _d(u), _d(xn), C.c_int32(device)))
+    return xn
 
 
 class BatchedLevenbergMarquardt:
@@ -241,6 +261,21 @@ class BatchedLevenbergMarquardt:
         u0, chi2, status = out
         _check(self._lib.b200sqp_mpc_step(self._h, C.byref(self._opts), C.c_int32(mode), _d(x0), _d(xref), _d(u0), _d(chi2), _i(status)))
         return u0, chi2, status
+
+    def closed_loop(self, x0, steps, xref=None, mode=1, integrator="euler", plant_dt=None):
+        """The whole closed loop of the batch on the device: `steps` x (MPC step -> first control -> plant step over plant_dt), only
+        x0 in and the log out.  -> u_applied [steps, B, nu], x_closed [steps+1, B, nx], chi2 [steps, B], status [steps, B]"""
+        x0 = np.ascontiguousarray(x0, np.float64)
+        xref = None if xref is None else np.ascontiguousarray(xref, np.float64)
+        B, nx, nu = self.batch, self.ocp.nx, self.ocp.nu
+        u = np.zeros((steps, B, nu))
+        x = np.zeros((steps + 1, B, nx))
+        chi2 = np.zeros((steps, B))
+        status = np.zeros((steps, B), np.int32)
+        dt = float(self.ocp.dt_ref if plant_dt is None else plant_dt)
+        _check(self._lib.b200sqp_closed_loop(self._h, C.byref(self._opts), C.c_int32(mode), C.c_int32(INTEGRATORS[integrator]), C.c_double(dt),
+                                             C.c_int32(steps), _d(x0), _d(xref), _d(u), _d(x), _d(chi2), _i(status)))
+        return u, x, chi2, status
 
     def mpc_step_raw(self, mode, x0_ptr, xref_ptr, u0_ptr, chi2_ptr, status_ptr):
         """b200sqp_mpc_step on raw host addresses (pinned buffers)"""

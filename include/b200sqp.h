@@ -202,6 +202,28 @@ int b200sqp_step(b200sqp_handle h, const b200sqp_lm_options* opts, int32_t cold_
 int b200sqp_mpc_step(b200sqp_handle h, const b200sqp_lm_options* opts, int32_t mode, const double* x0, const double* xref, double* u0_out,
                      double* chi2_out, int32_t* status_out);
 
+/* Plant simulation for `batch` independent plants: SimulatedPlant::control
+ * (src/plants/src/simulated_plant.cpp:92-146; no dead time, no disturbances) = one solveIVP of the system dynamics over `dt` with the
+ * control held, integrator 0 = IntegratorExplicitEuler (the plant's default, simulated_plant.cpp:37;
+ * src/numerics/include/corbo-numerics/explicit_integrators.h:66-72), 1 = IntegratorExplicitRungeKutta4 (explicit_integrators.h:280-295);
+ * same expression order as the reference, no FMA contraction.  Host pointers: x [batch*nx], u [batch*nu], x_next [batch*nx].
+ * Handle-less like b200sqp_linearize_dynamics. */
+int b200sqp_plant_step(int32_t dynamics, const double* dyn_params, int32_t integrator, double dt, int32_t batch, const double* x, const double* u,
+                       double* x_next, int32_t device);
+
+/* The whole closed loop of the batch on the device -- what ClosedLoopControlTask::performTask
+ * (src/tasks/src/task_closed_loop_control.cpp:153-235) does per instance with a PredictiveController and a SimulatedPlant, and what
+ * BenchmarkTaskVaryingInitialState repeats over start states: for s = 0..steps-1
+ *   measurement = plant state (full-state output, no observer dynamics);
+ *   controller  = b200sqp_mpc_step's device half (step 0 always initialises the grid; later steps per `mode`: 0 re-initialise,
+ *                 1 keep the previous solution, 2 moving-horizon warm start), first control of the optimised trajectory;
+ *   plant       = b200sqp_plant_step's kernel over `plant_dt` with the dynamics and parameters of the handle's OCP.
+ * Only x0 [batch*nx] (+ xref [batch*nx] or NULL) go in; after the last step the log comes out (each may be NULL):
+ * u_applied [steps][batch*nu], x_closed [steps+1][batch*nx] (row 0 = x0), chi2_out / status_out [steps][batch].
+ * Nothing crosses PCIe between the steps. */
+int b200sqp_closed_loop(b200sqp_handle h, const b200sqp_lm_options* opts, int32_t mode, int32_t integrator, double plant_dt, int32_t steps,
+                        const double* x0, const double* xref, double* u_applied, double* x_closed, double* chi2_out, int32_t* status_out);
+
 /* LevenbergMarquardtSparse::computeValues (:222-246) and ...EdgeBased::computeCombinedSparseJacobian (:1480-1753) at the current
  * parameters, penalty weights applied: values [batch*m], jac_values [batch*nnzJ] in the CSC order of b200sqp_jacobian_pattern.
  * Like the reference, evaluating the Jacobian perturbs the parameters in place (+d,-2d,+d; edge_interface.cpp:78-85). */

@@ -106,6 +106,18 @@ class _Checker:
             raise RuntimeError(f"{self.prefix}linearize failed: {rc}")
         return A.T.copy(), Bm.T.copy()  # the checkers write column-major
 
+    def plant_step(self, ocp, x, u, dt, integrator="euler"):
+        """SimulatedPlant::control for a batch of points (dynamics of the descriptor): x [B, nx], u [B, nu] -> x_next [B, nx]"""
+        x = np.ascontiguousarray(x, np.float64).reshape(-1, ocp.nx)
+        u = np.ascontiguousarray(u, np.float64).reshape(-1, ocp.nu)
+        out = np.zeros_like(x)
+        fn = getattr(self.lib, self.prefix + "plant_step")
+        fn.restype = C.c_int
+        rc = fn(C.byref(ocp), C.c_int({"euler": 0, "rk4": 1}[integrator]), C.c_double(dt), C.c_int(x.shape[0]), _d(x), _d(u), _d(out))
+        if rc != 0:
+            raise RuntimeError(f"{self.prefix}plant_step failed: {rc}")
+        return out
+
     def initial_params(self, ocp, x0, xref=None):
         n = self.dims(ocp).n_params
         x0 = np.ascontiguousarray(x0, np.float64)
@@ -203,6 +215,12 @@ class Oracle(_Checker):
             raise RuntimeError(f"sqp_oracle_solve_sequence failed: {rc}")
         return p, chi2
 
+    def plant_interval(self, plant_dt, step):
+        """interval the reference's plant integrates over at closed-loop step `step` (integer-nanosecond time, (t + dt) - t)"""
+        f = self.lib.sqp_oracle_plant_interval
+        f.restype = C.c_double
+        return float(f(C.c_double(plant_dt), C.c_int(step)))
+
     def known_answer(self, case_id, stage=0):
         """reference's own LM known-answer tests restated: -> (x, expected, tol)"""
         return _known_answer(self.lib, "sqp_oracle_known_answer", case_id, stage)
@@ -233,6 +251,19 @@ class Reference(_Checker):
         rc = f(C.byref(ocp), C.byref(opts), _d(x0), C.c_int(steps), _d(u), _d(x))
         if rc != 0:
             raise RuntimeError(f"corbo_ref_closed_loop_shift failed: {rc}")
+        return u, x
+
+    def closed_loop_plant(self, ocp, opts, x0, steps, integrator="euler", plant_dt=None, warm_start=False):
+        """ClosedLoopControlTask's loop for one instance with the reference's PredictiveController and SimulatedPlant"""
+        x0 = np.ascontiguousarray(x0, np.float64)
+        u = np.zeros((steps, ocp.nu))
+        x = np.zeros((steps + 1, ocp.nx))
+        f = self.lib.corbo_ref_closed_loop_plant
+        f.restype = C.c_int
+        rc = f(C.byref(ocp), C.byref(opts), _d(x0), C.c_int(steps), C.c_int({"euler": 0, "rk4": 1}[integrator]),
+               C.c_double(ocp.dt_ref if plant_dt is None else plant_dt), C.c_int(1 if warm_start else 0), _d(u), _d(x))
+        if rc != 0:
+            raise RuntimeError(f"corbo_ref_closed_loop_plant failed: {rc}")
         return u, x
 
     def warm_start_shift(self, ocp, x0_old, x0_new, params, xref=None):

@@ -28,6 +28,9 @@
 #include <corbo-optimization/solver/levenberg_marquardt_sparse.h>
 #include <corbo-systems/benchmark/linear_benchmark_systems.h>
 #include <corbo-systems/benchmark/nonlinear_benchmark_systems.h>
+#include <corbo-systems/output_function_interface.h>
+#include <corbo-plants/simulated_plant.h>
+#include <corbo-controllers/predictive_controller.h>
 
 #include <atomic>
 #include <chrono>
@@ -669,6 +672,78 @@ int corbo_ref_closed_loop_shift(const b200sqp_ocp* d, const b200sqp_lm_options* 
         x = xn;
         std::memcpy(x_closed + (size_t)(s + 1) * d->nx, x.data(), sizeof(double) * d->nx);
     }
+    return 0;
+}
+
+// The reference's own plant: SimulatedPlant (FullStateSystemOutput, no disturbances / dead time) stepped once per point with
+// PlantInterface::control(u, dt, t) -> SimulatedPlant::control(u_sequence, ...) -> _integrator->solveIVP.
+// integrator 0 = IntegratorExplicitEuler (the plant's default), 1 = IntegratorExplicitRungeKutta4.
+static std::shared_ptr<SimulatedPlant> makePlant(const b200sqp_ocp& d, int integrator)
+{
+    SystemDynamicsInterface::Ptr dyn = makeDynamics(d);
+    if (!dyn) return {};
+    auto plant = std::make_shared<SimulatedPlant>(dyn, std::make_shared<FullStateSystemOutput>());
+    if (integrator == 1) plant->setIntegrator(std::make_shared<IntegratorExplicitRungeKutta4>());
+    return plant;
+}
+
+int corbo_ref_plant_step(const b200sqp_ocp* d, int integrator, double dt, int batch, const double* x, const double* u, double* x_next)
+{
+    const int nx = d->nx, nu = d->nu;
+    for (int i = 0; i < batch; ++i)
+    {
+        auto plant = makePlant(*d, integrator);  // fresh plant per point: the control buffer is stateful
+        if (!plant) return -1;
+        if (!plant->setState(Eigen::Map<const Eigen::VectorXd>(x + (size_t)i * nx, nx))) return -2;
+        Eigen::VectorXd ui = Eigen::Map<const Eigen::VectorXd>(u + (size_t)i * nu, nu);
+        if (!static_cast<PlantInterface&>(*plant).control(ui, Duration(dt), Time(0))) return -3;
+        Eigen::VectorXd y(nx);
+        if (!plant->output(y, Time(dt))) return -4;
+        std::memcpy(x_next + (size_t)i * nx, y.data(), sizeof(double) * nx);
+    }
+    return 0;
+}
+
+// The closed loop of ClosedLoopControlTask::performTask (task_closed_loop_control.cpp:153-235) for one instance with the reference's own
+// classes: plant->output -> PredictiveController::step (one OCP iteration) -> plant->control(u_sequence, x_sequence, dt, t).
+// warm_start != 0 switches the grid's moving-horizon warm start on.  u_applied [steps*nu], x_closed [(steps+1)*nx].
+int corbo_ref_closed_loop_plant(const b200sqp_ocp* d, const b200sqp_lm_options* o, const double* x0, int steps, int integrator, double plant_dt,
+                                int warm_start, double* u_applied, double* x_closed)
+{
+    RefOcp r;
+    if (!buildOcp(*d, *o, r)) return -1;
+    if (warm_start)
+    {
+        auto* grid = dynamic_cast<FullDiscretizationGridBase*>(r.grid.get());
+        if (!grid) return -4;
+        grid->setWarmStart(true);
+    }
+    auto plant = makePlant(*d, integrator);
+    if (!plant) return -5;
+    if (!plant->setState(Eigen::Map<const Eigen::VectorXd>(x0, d->nx))) return -6;
+    PredictiveController controller;
+    controller.setOptimalControlProblem(r.ocp);
+    controller.setNumOcpIterations(1);
+    controller.setAutoUpdatePreviousControl(false);
+    StaticReference xref(Eigen::VectorXd::Zero(d->nx));
+    ZeroReference uref(d->nu);
+    Eigen::VectorXd x(d->nx);
+    const Duration dt(plant_dt);
+    Time t(0);
+    for (int s = 0; s < steps; ++s)
+    {
+        if (!plant->output(x, t)) return -7;
+        std::memcpy(x_closed + (size_t)s * d->nx, x.data(), sizeof(double) * d->nx);
+        TimeSeries::Ptr u_seq = std::make_shared<TimeSeries>(), x_seq = std::make_shared<TimeSeries>();
+        if (!controller.step(x, xref, uref, dt, t, u_seq, x_seq)) return -2;
+        if (u_seq->getTimeDimension() < 1) return -3;
+        Eigen::VectorXd u = u_seq->getValuesMap(0);
+        std::memcpy(u_applied + (size_t)s * d->nu, u.data(), sizeof(double) * d->nu);
+        if (!plant->control(u_seq, x_seq, dt, t)) return -8;
+        t += dt;
+    }
+    if (!plant->output(x, t)) return -7;
+    std::memcpy(x_closed + (size_t)steps * d->nx, x.data(), sizeof(double) * d->nx);
     return 0;
 }
 

@@ -1230,6 +1230,33 @@ int sqp_oracle_solve_batch(const b200sqp_ocp* d, const b200sqp_lm_options* o, in
     return failures.load() == 0 ? 0 : -1;
 }
 
+// SimulatedPlant::control (plants/src/simulated_plant.cpp:92-146) without dead time / disturbances: one
+// _integrator->solveIVP(x, u, dt, dynamics, x_next) per plant; integrator 0 = IntegratorExplicitEuler (the plant's default, :37),
+// 1 = IntegratorExplicitRungeKutta4.  x [batch*nx], u [batch*nu], x_next [batch*nx].
+int sqp_oracle_plant_step(const b200sqp_ocp* d, int integrator, double dt, int batch, const double* x, const double* u, double* x_next)
+{
+    Dyn f = makeDynamics(*d);
+    if (!f) return -1;
+    const int nx = d->nx, nu = d->nu;
+    double zero[B200SQP_MAX_NX] = {0};
+    for (int i = 0; i < batch; ++i)
+        shooting(integrator == 0 ? B200SQP_INT_EULER : B200SQP_INT_RK4, f, nx, x + (size_t)i * nx, u + (size_t)i * nu, zero, dt,
+                 x_next + (size_t)i * nx);  // solveIVP - 0 (exact)
+    return 0;
+}
+
+// The interval the plant integrates over at closed-loop step s: corbo::Time / Duration count integer nanoseconds (core/include/corbo-core/
+// time.h:140,283: fromSec truncates t*1e9, toSec divides the tick count by 1e9); ClosedLoopControlTask advances t += dt in ticks
+// (tasks/src/task_closed_loop_control.cpp) and TimeValueBuffer::getValues (systems/src/time_value_buffer.cpp:74) hands the plant
+// `ts + dt - cur_t` with cur_t = ts, i.e. (t + dt) - t in doubles.
+double sqp_oracle_plant_interval(double plant_dt, int step)
+{
+    const long long ticks = (long long)(plant_dt * 1e9);
+    const double dt = (double)ticks / 1e9, t = (double)((long long)step * ticks) / 1e9;
+    volatile double t_end = t + dt;
+    return t_end - t;
+}
+
 // SystemDynamicsInterface::getLinearA / getLinearB (systems/src/system_dynamics_interface.cpp:33-59) over
 // ForwardDifferences::jacobian (numerics/include/corbo-numerics/finite_differences.hpp:29-48, method 0) or
 // CentralDifferences::jacobian (:167-188, method 1): in-place perturbation of a copy of x (A) or u (B), delta = 1e-9.

@@ -63,3 +63,13 @@ LINEARIZE_POINTS = 6
 def linearize_points(ocp, seed=17):
     rng = np.random.default_rng(seed)
     return rng.uniform(-1.5, 1.5, (LINEARIZE_POINTS, ocp.nx)), rng.uniform(-1.0, 1.0, (LINEARIZE_POINTS, ocp.nu))
+
+
+# plant fixtures: SimulatedPlant::control at the linearisation points, ClosedLoopControlTask's loop
+PLANT_DT = 0.05
+CLOSED_LOOP_STEPS = 12
+
+
+def closed_loop_starts(seed=23, count=6):
+    rng = np.random.default_rng(seed)
+    return np.vstack([[1.0, 0.5], rng.uniform(-1.5, 1.5, (count - 1, 2))])

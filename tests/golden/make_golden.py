@@ -94,6 +94,25 @@ def main():
         np.savez_compressed(os.path.join(HERE, "warm_start_shift.npz"), x0_old=np.array(x0_old), x0_new=np.array(x0_new), p_in=np.array(p_in),
                             p_out=np.array(p_out), loop_u=u, loop_x=x)
         print("warm_start: closed loop with shifting u[:3] =", u[:3, 0])
+    if not only or "plant" in only:
+        # SimulatedPlant::control of the reference (both integrators) at the linearisation points, and ClosedLoopControlTask's loop
+        # (PredictiveController + SimulatedPlant) for a few start states, with and without the moving-horizon warm start
+        out = {}
+        for name, (make, _) in cases.LINEARIZE_MODELS.items():
+            ocp = make()
+            xs, us = cases.linearize_points(ocp)
+            for integ in ("euler", "rk4"):
+                out[f"{name}_{integ}"] = ref.plant_step(ocp, xs, us, cases.PLANT_DT, integ)
+        ocp20 = problems.van_der_pol(20)
+        x0s = cases.closed_loop_starts()
+        for integ, warm in (("euler", False), ("rk4", False), ("rk4", True)):
+            ux = [ref.closed_loop_plant(ocp20, abi.LmOptions.defaults(), x0, cases.CLOSED_LOOP_STEPS, integ, None, warm) for x0 in x0s]
+            tag = f"loop_{integ}_{'shift' if warm else 'keep'}"
+            out[tag + "_u"] = np.stack([u for u, _ in ux], axis=1)  # [steps, B, nu]
+            out[tag + "_x"] = np.stack([x for _, x in ux], axis=1)  # [steps+1, B, nx]
+        out["loop_x0"] = x0s
+        np.savez_compressed(os.path.join(HERE, "plant.npz"), **out)
+        print("plant:", len(out), "arrays; closed loop (rk4, keep) u[:3, 0] =", out["loop_rk4_keep_u"][:3, 0, 0])
     if only:
         return
     ka = []
