@@ -435,8 +435,9 @@ static int startStatesFromDevice(b200sqp_handle h, const double* d_x0, const dou
 // the device half of b200sqp_warm_start_shift: d_x0_new [B][nx] in HBM
 static int warmStartShiftFromDevice(b200sqp_handle h, const double* d_x0_new, int* d_num_shift)
 {
-    if (h->s.ocp.grid != B200SQP_GRID_FD_UNIFORM)
-        return fail(B200SQP_ERR_UNSUPPORTED, "warm-start shifting is implemented for FiniteDifferencesGrid structures only");
+    if (h->s.vt)
+        return fail(B200SQP_ERR_UNSUPPORTED, "the reference never shifts a NonUniformFiniteDifferencesVariableGrid (isMovingHorizonWarmStartActive() "
+                                             "is false there): use mode 1 (keep)");
     launchWarmStartShift(d_x0_new, h->st.x0, h->st.z[0], h->st.z[1], h->st.cur, h->s.K, h->s.nx, h->s.nu, d_num_shift, h->B, h->stream);
     h->launches += 1;
     CUDA_TRY(cudaGetLastError());
@@ -483,8 +484,9 @@ int b200sqp_warm_start_shift(b200sqp_handle h, const double* x0_new, int32_t* nu
     int rc = checkHandle(h);
     if (rc) return rc;
     if (!x0_new) return fail(B200SQP_ERR_INVALID, "x0_new is null");
-    if (h->s.ocp.grid != B200SQP_GRID_FD_UNIFORM)
-        return fail(B200SQP_ERR_UNSUPPORTED, "warm-start shifting is implemented for FiniteDifferencesGrid structures only");
+    if (h->s.vt)
+        return fail(B200SQP_ERR_UNSUPPORTED, "the reference never shifts a NonUniformFiniteDifferencesVariableGrid (isMovingHorizonWarmStartActive() "
+                                             "is false there): use mode 1 (keep)");
     const size_t bytes = sizeof(double) * (size_t)h->B * h->s.nx;
     CUDA_TRY(cudaMemcpyAsync(h->d_x0_host_order, x0_new, bytes, cudaMemcpyHostToDevice, h->stream));
     if (num_shift && !h->d_num_shift) CUDA_TRY(h->alloc(&h->d_num_shift, (size_t)h->B));
@@ -690,8 +692,8 @@ int b200sqp_closed_loop(b200sqp_handle h, const b200sqp_lm_options* opts, int32_
     if (mode < 0 || mode > 2) return fail(B200SQP_ERR_INVALID, "mode must be 0 (cold every step), 1 (keep) or 2 (shift)");
     if (integrator != 0 && integrator != 1) return fail(B200SQP_ERR_INVALID, "integrator must be 0 (explicit Euler) or 1 (Runge-Kutta 4)");
     if (!x0 || steps < 1 || !(plant_dt > 0.0)) return fail(B200SQP_ERR_INVALID, "bad argument");
-    if (mode == 2 && h->s.ocp.grid != B200SQP_GRID_FD_UNIFORM)
-        return fail(B200SQP_ERR_UNSUPPORTED, "warm-start shifting is implemented for FiniteDifferencesGrid structures only");
+    if (mode == 2 && h->s.vt)
+        return fail(B200SQP_ERR_UNSUPPORTED, "the reference never shifts a NonUniformFiniteDifferencesVariableGrid: use mode 1 (keep)");
     const int nx = h->s.nx, nu = h->s.nu, B = h->B;
     const size_t sx = (size_t)B * nx, su = (size_t)B * nu;
     // the closed-loop log lives in HBM for the whole run: states [steps+1][B][nx], applied controls [steps][B][nu], chi2 / status [steps][B]

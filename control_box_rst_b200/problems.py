@@ -53,6 +53,12 @@ def van_der_pol(n_grid=50, dt=0.1, final_cost=True, collocation=abi.COLL_CRANK_N
                     q=(1.0, 1.0), r=(0.1,), qf=(1.0, 1.0) if final_cost else None, u_lb=(-1.0,), u_ub=(1.0,), dyn_params=(a,), **kw)
 
 
+def van_der_pol_shooting(n_grid=20, dt=0.1, integrator=abi.INT_RK4, a=1.0, **kw):
+    """Van der Pol on a MultipleShootingGrid (one control per interval): the polynomial shooting case of the parity tests."""
+    return make_ocp(grid=abi.GRID_MULTIPLE_SHOOTING, dynamics=abi.DYN_VAN_DER_POL, n_grid=n_grid, dt=dt, integrator=integrator,
+                    q=(1.0, 1.0), r=(0.1,), qf=(1.0, 1.0), u_lb=(-1.0,), u_ub=(1.0,), dyn_params=(a,), **kw)
+
+
 def unicycle_time_optimal(n_grid=50, dt=0.1):
     """configs[2]: unicycle, NonUniformFiniteDifferencesVariableGrid, MinimumTime(lsq), xf fixed, |v|,|w|<=1, dt in [0,1]."""
     return make_ocp(grid=abi.GRID_FD_NONUNIFORM_VARDT, dynamics=abi.DYN_UNICYCLE, n_grid=n_grid, dt=dt,

@@ -175,7 +175,10 @@ int b200sqp_get_first_controls(b200sqp_handle h, double* u0);
  * FullDiscretizationGridBase::findNearestState + warmStartShifting (full_discretization_grid_base.cpp:230-318) against the new
  * measurement x0_new [batch*nx] (host pointer), then the start state is replaced by the measurement (:101) and fixed goal components
  * by the reference (:102-106).  num_shift [batch] (host, may be NULL) receives the shift each instance applied.
- * FiniteDifferencesGrid structures only (B200SQP_ERR_UNSUPPORTED otherwise).  Follow with b200sqp_solve / b200sqp_step(cold_start=0). */
+ * FiniteDifferencesGrid and MultipleShootingGrid (ShootingGridBase::findNearestShootingInterval + warmStartShifting,
+ * shooting_grid_base.cpp:292-381: the same rule on the shooting nodes) structures.  NonUniformFiniteDifferencesVariableGrid returns
+ * B200SQP_ERR_UNSUPPORTED: the reference never shifts it (isMovingHorizonWarmStartActive() is false,
+ * non_uniform_finite_differences_variable_grid.h:79).  Follow with b200sqp_solve / b200sqp_step(cold_start=0). */
 int b200sqp_warm_start_shift(b200sqp_handle h, const double* x0_new, int32_t* num_shift);
 
 /* ---- the hot path ------------------------------------------------------------------------------------------------------ */
@@ -196,7 +199,7 @@ int b200sqp_step(b200sqp_handle h, const b200sqp_lm_options* opts, int32_t cold_
  * H2D of the measured states x0 [batch*nx] (+ xref or NULL), then per `mode`
  *   0  cold start: FullDiscretizationGridBase::initializeSequences
  *   1  keep the previous solution as the initial guess, start state replaced (grid update with warm start off)
- *   2  moving-horizon warm start: b200sqp_warm_start_shift (FiniteDifferencesGrid structures only)
+ *   2  moving-horizon warm start: b200sqp_warm_start_shift (fixed-dt grids)
  * solve (new_run = 1), D2H of the first controls u0_out [batch*nu] and, if non-NULL, chi2_out [batch] / status_out [batch].
  * The trajectories stay in HBM (b200sqp_get_params fetches them). */
 int b200sqp_mpc_step(b200sqp_handle h, const b200sqp_lm_options* opts, int32_t mode, const double* x0, const double* xref, double* u0_out,

@@ -626,6 +626,27 @@ int corbo_ref_closed_loop(const b200sqp_ocp* d, const b200sqp_lm_options* o, con
     return 0;
 }
 
+// setWarmStart of whichever grid base the descriptor built (FullDiscretizationGridBase / ShootingGridBase / NonUniformFullDiscretizationGridBase)
+static bool enableWarmStart(RefOcp& r)
+{
+    if (auto* g = dynamic_cast<FullDiscretizationGridBase*>(r.grid.get()))
+    {
+        g->setWarmStart(true);
+        return true;
+    }
+    if (auto* g = dynamic_cast<ShootingGridBase*>(r.grid.get()))
+    {
+        g->setWarmStart(true);
+        return true;
+    }
+    if (auto* g = dynamic_cast<NonUniformFullDiscretizationGridBase*>(r.grid.get()))
+    {
+        g->setWarmStart(true);
+        return true;
+    }
+    return false;
+}
+
 // Moving-horizon warm start of the reference grid (FullDiscretizationGridBase::update -> warmStartShifting + findNearestState,
 // full_discretization_grid_base.cpp:95-107,230-318), isolated: initialise at x0_old, overwrite the parameters with params_in, run the
 // grid update for a new run at x0_new with warm start active, return the shifted parameters.
@@ -635,9 +656,7 @@ int corbo_ref_warm_start_shift(const b200sqp_ocp* d, const double* x0_old, const
     b200sqp_lm_options o = {0, 2, 2, 2, 1, 1, 1, 500, 500, 500};
     RefOcp r;
     if (!buildOcp(*d, o, r)) return -1;
-    auto* grid = dynamic_cast<FullDiscretizationGridBase*>(r.grid.get());
-    if (!grid) return -4;
-    grid->setWarmStart(true);
+    if (!enableWarmStart(r)) return -4;
     if (!prepare(r, *d, x0_old, xref, true, nullptr)) return -2;
     const int n = r.problem->getParameterDimension();
     r.problem->setParameterVector(Eigen::Map<const Eigen::VectorXd>(params_in, n));
@@ -653,9 +672,7 @@ int corbo_ref_closed_loop_shift(const b200sqp_ocp* d, const b200sqp_lm_options* 
 {
     RefOcp r;
     if (!buildOcp(*d, *o, r)) return -1;
-    auto* grid = dynamic_cast<FullDiscretizationGridBase*>(r.grid.get());
-    if (!grid) return -4;
-    grid->setWarmStart(true);
+    if (!enableWarmStart(r)) return -4;
     StaticReference xref(Eigen::VectorXd::Zero(d->nx));
     ZeroReference uref(d->nu);
     Eigen::VectorXd x = Eigen::Map<const Eigen::VectorXd>(x0, d->nx);
@@ -714,9 +731,7 @@ int corbo_ref_closed_loop_plant(const b200sqp_ocp* d, const b200sqp_lm_options* 
     if (!buildOcp(*d, *o, r)) return -1;
     if (warm_start)
     {
-        auto* grid = dynamic_cast<FullDiscretizationGridBase*>(r.grid.get());
-        if (!grid) return -4;
-        grid->setWarmStart(true);
+        if (!enableWarmStart(r)) return -4;
     }
     auto plant = makePlant(*d, integrator);
     if (!plant) return -5;

@@ -89,10 +89,26 @@ def main():
             x0_new.append(xn)
             p_in.append(p)
             p_out.append(ref.warm_start_shift(ocp, xo, xn, p))
+        # the same on a MultipleShootingGrid (ShootingGridBase::findNearestShootingInterval + warmStartShifting)
+        ms = problems.van_der_pol_shooting(12)
+        ms_x0_old, ms_x0_new, ms_p_in, ms_p_out = [], [], [], []
+        for trial in range(12):
+            xo = rng.uniform(-2, 2, 2)
+            p = ref.initial_params(ms, xo, None) + rng.uniform(-0.02, 0.02, ref.dims(ms).n_params)
+            x_idx, _, _ = ref.vertex_indices(ms)
+            s = trial % 5
+            target = xo if s == 0 else p[x_idx[s]:x_idx[s] + 2]
+            xn = target.copy() if trial == 0 else target + rng.uniform(-0.01, 0.01, 2)
+            ms_x0_old.append(xo)
+            ms_x0_new.append(xn)
+            ms_p_in.append(p)
+            ms_p_out.append(ref.warm_start_shift(ms, xo, xn, p))
         ocp20 = problems.van_der_pol(20)
         u, x = ref.closed_loop_shift(ocp20, abi.LmOptions.defaults(), np.array([1.0, 0.5]), 15)
+        ms_u, ms_x = ref.closed_loop_plant(problems.van_der_pol_shooting(20), abi.LmOptions.defaults(), np.array([1.0, 0.5]), 15, "rk4", None, True)
         np.savez_compressed(os.path.join(HERE, "warm_start_shift.npz"), x0_old=np.array(x0_old), x0_new=np.array(x0_new), p_in=np.array(p_in),
-                            p_out=np.array(p_out), loop_u=u, loop_x=x)
+                            p_out=np.array(p_out), loop_u=u, loop_x=x, ms_x0_old=np.array(ms_x0_old), ms_x0_new=np.array(ms_x0_new),
+                            ms_p_in=np.array(ms_p_in), ms_p_out=np.array(ms_p_out), ms_loop_u=ms_u, ms_loop_x=ms_x)
         print("warm_start: closed loop with shifting u[:3] =", u[:3, 0])
     if not only or "plant" in only:
         # SimulatedPlant::control of the reference (both integrators) at the linearisation points, and ClosedLoopControlTask's loop

@@ -35,10 +35,16 @@ def _join(ocp, x, u):
     return p
 
 
-def test_restatement_matches_reference_fixture():
-    ocp = problems.van_der_pol(12)
+# FiniteDifferencesGrid (FullDiscretizationGridBase) and MultipleShootingGrid (ShootingGridBase::findNearestShootingInterval +
+# warmStartShifting, shooting_grid_base.cpp:292-381): fixture key prefix, descriptor
+GRIDS = [("", lambda n: problems.van_der_pol(n)), ("ms_", lambda n: problems.van_der_pol_shooting(n))]
+
+
+@pytest.mark.parametrize("prefix,make", GRIDS, ids=["fd_grid", "shooting_grid"])
+def test_restatement_matches_reference_fixture(prefix, make):
+    ocp = make(12)
     shifts = []
-    for xo, xn, p_in, p_out in zip(GOLD["x0_old"], GOLD["x0_new"], GOLD["p_in"], GOLD["p_out"]):
+    for xo, xn, p_in, p_out in zip(GOLD[prefix + "x0_old"], GOLD[prefix + "x0_new"], GOLD[prefix + "p_in"], GOLD[prefix + "p_out"]):
         x, u = _split(ocp, p_in, xo)
         xs, us, s = warm_start.warm_start_shift(x, u, xn)
         shifts.append(s)
@@ -47,17 +53,43 @@ def test_restatement_matches_reference_fixture():
 
 
 @pytest.mark.gpu
-def test_device_shift_matches_reference_fixture():
-    ocp = problems.van_der_pol(12)
-    B = len(GOLD["x0_old"])
+@pytest.mark.parametrize("prefix,make", GRIDS, ids=["fd_grid", "shooting_grid"])
+def test_device_shift_matches_reference_fixture(prefix, make):
+    ocp = make(12)
+    x0_old, x0_new, p_in, p_out = (GOLD[prefix + k] for k in ("x0_old", "x0_new", "p_in", "p_out"))
+    B = len(x0_old)
     lm = solver.BatchedLevenbergMarquardt(ocp, B)
-    lm.set_problem_data(GOLD["x0_old"], None)
+    lm.set_problem_data(x0_old, None)
     lm.initialize_trajectories()
-    lm.set_params(GOLD["p_in"])
-    shifts = lm.warm_start_shift(GOLD["x0_new"])
-    assert np.array_equal(lm.get_params(), GOLD["p_out"])
-    want = [warm_start.find_nearest_state(_split(ocp, p, xo)[0], xn) for xo, xn, p in zip(GOLD["x0_old"], GOLD["x0_new"], GOLD["p_in"])]
+    lm.set_params(p_in)
+    shifts = lm.warm_start_shift(x0_new)
+    assert np.array_equal(lm.get_params(), p_out)
+    want = [warm_start.find_nearest_state(_split(ocp, p, xo)[0], xn) for xo, xn, p in zip(x0_old, x0_new, p_in)]
     assert np.array_equal(shifts, np.array(want, np.int32))
+    lm.clear()
+
+
+@pytest.mark.gpu
+def test_shooting_grid_closed_loop_with_shift_matches_reference_controller_and_plant():
+    """MultipleShootingGrid with setWarmStart(true) under the reference's PredictiveController + SimulatedPlant (RK4) against one
+    b200sqp_closed_loop call in shift mode."""
+    ocp = problems.van_der_pol_shooting(20)
+    lm = solver.BatchedLevenbergMarquardt(ocp, 1)
+    lm.setIterations(10)
+    u, x, chi2, status = lm.closed_loop(np.array([[1.0, 0.5]]), 15, mode=solver.BatchedLevenbergMarquardt.MPC_SHIFT, integrator="rk4")
+    np.testing.assert_allclose(u[:, 0], GOLD["ms_loop_u"], rtol=0, atol=2e-6)
+    np.testing.assert_allclose(x[:, 0], GOLD["ms_loop_x"], rtol=0, atol=2e-6)
+    lm.clear()
+
+
+@pytest.mark.gpu
+def test_shift_is_refused_where_the_reference_never_shifts():
+    """NonUniformFiniteDifferencesVariableGrid::isMovingHorizonWarmStartActive() is false: no silent approximation"""
+    ocp = problems.unicycle_time_optimal(12)
+    lm = solver.BatchedLevenbergMarquardt(ocp, 4)
+    with pytest.raises(solver.B200SqpError) as e:
+        lm.warm_start_shift(np.zeros((4, 3)))
+    assert e.value.code == -2
     lm.clear()
 
 
