@@ -299,6 +299,55 @@ def test_full_size_properties():
     lm.clear()
 
 
+# (config index, trajectory tolerance of the oracle spot check, chi2 tolerance): the per-config FD-noise floors of the module docstring
+FULL_SIZE = [(2, 1e-3, 1e-6), (3, 5e-3, 1e-4), (4, 1e-3, 1e-4)]
+
+
+@pytest.mark.parametrize("index,tol_traj,tol_chi2", FULL_SIZE, ids=["unicycle_4096", "cartpole_16384", "quadrotor_65536"])
+def test_full_size_properties_other_configs(oracle, index, tol_traj, tol_chi2):
+    """BASELINE.json configs[2..4] at their full batch (unicycle time-optimal 4096 x N=50, cart-pole shooting 16384 x N=100, quadrotor
+    65536 x N=60; fp64 -- the reference has no fp32 path): determinism, batch independence (the first 64 instances alone give the same
+    bits), monotone accepted chi2, admissible status everywhere, and a spot check of 32 instances spread over the batch against
+    the oracle."""
+    ocp, kw, B = problems.config(index)
+    iters = 10
+    x0, xref = problems.instance_data(ocp, B, seed=77)
+    lm = solver.BatchedLevenbergMarquardt(ocp, B)
+    lm.setIterations(iters)
+    lm.setPenaltyWeights(*kw["weights"])
+    lm.set_problem_data(x0, xref)
+
+    def run():
+        lm.initialize_trajectories()
+        status, chi2 = lm.solve(new_run=True)
+        return lm.get_params(), chi2.copy(), status.copy()
+
+    p, c, st = run()
+    p2, c2, st2 = run()
+    assert np.array_equal(p, p2) and np.array_equal(c, c2) and np.array_equal(st, st2)
+    del p2
+    tr = lm.chi2_trace()
+    lm.clear()
+    assert np.all(np.isfinite(p)) and np.all(np.isfinite(c))
+    assert np.all(np.diff(tr, axis=1) <= 0)
+    assert np.all((st == abi.STATUS_CONVERGED) | (st == abi.STATUS_EARLY_TERMINATED))
+    small = solver.BatchedLevenbergMarquardt(ocp, 64)
+    small.setIterations(iters)
+    small.setPenaltyWeights(*kw["weights"])
+    small.set_problem_data(x0[:64], xref[:64])
+    small.initialize_trajectories()
+    small.solve(new_run=True)
+    assert np.array_equal(small.get_params(), p[:64])
+    small.clear()
+    idx = np.linspace(0, B - 1, 32).astype(int)
+    opts = abi.LmOptions.defaults(iterations=iters, weights=kw["weights"])
+    p_o, c_o, _, _ = oracle.solve_batch(ocp, opts, x0[idx], xref[idx], threads=8)
+    err = _traj_err(p[idx], p_o)
+    print(f"config {index}: B={B} spot-check traj err max {err.max():.2e}, chi2 rel {np.abs(c[idx] / c_o - 1).max():.2e}")
+    assert err.max() <= tol_traj
+    np.testing.assert_allclose(c[idx], c_o, rtol=tol_chi2)
+
+
 def test_ragged_batch_sizes(oracle):
     """batches that do not fill a warp / a block, including a single instance"""
     ocp = problems.van_der_pol(10)
