@@ -370,6 +370,24 @@ def main_b200(args):
     mpc_value = B * world * iterations * args.steps / (mpc_ms * 1e-3)
     stats = lm.statistics()
 
+    # ---- the whole closed loop on the device (b200sqp_closed_loop): x0 in, the log out, nothing crosses PCIe between the MPC steps ------
+    closed_loop = None
+    if world == 1 and lm.ocp.grid != abi.GRID_FD_NONUNIFORM_VARDT:
+        loop_steps = 20
+        h_ul = torch.empty((loop_steps, B, ocp.nu), dtype=torch.float64).pin_memory()
+        h_xl = torch.empty((loop_steps + 1, B, ocp.nx), dtype=torch.float64).pin_memory()
+
+        def loop_call():
+            lm.closed_loop_raw(2, 1, ocp.dt_ref, loop_steps, h_x0.data_ptr(), h_xref.data_ptr(), h_ul.data_ptr(), h_xl.data_ptr(), 0, 0)
+
+        loop_call()
+        reps = 3
+        loop_ms, _ = timed(loop_call, reps)
+        closed_loop = {"mpc_steps_per_s": B * loop_steps * reps / (loop_ms * 1e-3), "value": B * loop_steps * iterations * reps / (loop_ms * 1e-3),
+                       "unit": UNIT, "ms_per_mpc_step_of_the_batch": loop_ms / reps / loop_steps, "closed_loop_steps": loop_steps,
+                       "h2d_bytes_per_call": h2d, "d2h_bytes_per_call": int(h_ul.numel() + h_xl.numel()) * 8,
+                       "note": "b200sqp_closed_loop: moving-horizon warm start + solve + RK4 plant step per MPC step, all on the device"}
+
     if rank == 0:
         peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
         if os.path.exists(peaks_path):
@@ -403,6 +421,7 @@ def main_b200(args):
             "e2e_mpc_step": {"value": mpc_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": B * ocp.nu * 8 + B * 8 + B * 4,
                              "ms_per_step": mpc_ms / args.steps,
                              "note": "b200sqp_mpc_step: measured states in, first controls + chi2 + status out, trajectories stay in HBM"},
+            "closed_loop": closed_loop,
             "gpu_launches": int(launches),
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "traffic_source": traffic_src,
                          "kernel": "lmSolve", "kernel_ms": kernel_ms / args.steps, "algorithmic_bytes_per_launch": alg_bytes,

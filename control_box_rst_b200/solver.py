@@ -277,6 +277,12 @@ class BatchedLevenbergMarquardt:
                                              C.c_int32(steps), _d(x0), _d(xref), _d(u), _d(x), _d(chi2), _i(status)))
         return u, x, chi2, status
 
+    def closed_loop_raw(self, mode, integrator, plant_dt, steps, x0_ptr, xref_ptr, u_ptr, x_ptr, chi2_ptr, status_ptr):
+        """b200sqp_closed_loop on raw host addresses (pinned buffers; 0 = not wanted)"""
+        _check(self._lib.b200sqp_closed_loop(self._h, C.byref(self._opts), C.c_int32(mode), C.c_int32(integrator), C.c_double(plant_dt),
+                                             C.c_int32(steps), C.c_void_p(x0_ptr), C.c_void_p(xref_ptr), C.c_void_p(u_ptr or None),
+                                             C.c_void_p(x_ptr or None), C.c_void_p(chi2_ptr or None), C.c_void_p(status_ptr or None)))
+
     def mpc_step_raw(self, mode, x0_ptr, xref_ptr, u0_ptr, chi2_ptr, status_ptr):
         """b200sqp_mpc_step on raw host addresses (pinned buffers)"""
         _check(self._lib.b200sqp_mpc_step(self._h, C.byref(self._opts), C.c_int32(mode), C.c_void_p(x0_ptr), C.c_void_p(xref_ptr),
