@@ -847,6 +847,47 @@ int b200sqp_linearize_dynamics(int32_t dynamics, const double* dyn_params, int32
     return B200SQP_OK;
 }
 
+int b200sqp_dynamics_hessian(int32_t dynamics, const double* dyn_params, int32_t method, int32_t batch, const double* x, const double* u,
+                             const double* multipliers, double* H, int32_t device)
+{
+    if (!dyn_params || !x || !u || !H || batch < 1 || (method != 0 && method != 1)) return fail(B200SQP_ERR_INVALID, "bad argument");
+    int nx = 0, nu = 0;
+    if (!dynamicsDimensions(dynamics, nx, nu)) return fail(B200SQP_ERR_UNSUPPORTED, "unknown dynamics id (closed functor registry; no CPU fallback)");
+    int count = 0;
+    if (cudaGetDeviceCount(&count) != cudaSuccess || count == 0)
+    {
+        cudaGetLastError();
+        return fail(B200SQP_ERR_NO_DEVICE, "no CUDA device visible: the finite-difference Hessian only exists as sm_100a kernels");
+    }
+    if (device < 0 || device >= count) return fail(B200SQP_ERR_INVALID, "device index out of range");
+    CUDA_TRY(cudaSetDevice(device));
+    DynParams dyn;
+    for (int i = 0; i < B200SQP_MAX_DYN_PARAMS; ++i) dyn.p[i] = dyn_params[i];
+    prepareDynParams(dyn);
+    const int nz    = nx + nu;
+    const size_t bx = sizeof(double) * (size_t)batch * nx, bu = sizeof(double) * (size_t)batch * nu, bh = sizeof(double) * (size_t)batch * nz * nz;
+    double *dx = nullptr, *du = nullptr, *dm = nullptr, *dh = nullptr;
+    cudaError_t e = cudaMalloc(&dx, bx);
+    if (e == cudaSuccess) e = cudaMalloc(&du, bu);
+    if (e == cudaSuccess && multipliers) e = cudaMalloc(&dm, bx);
+    if (e == cudaSuccess) e = cudaMalloc(&dh, bh);
+    if (e == cudaSuccess) e = cudaMemcpy(dx, x, bx, cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) e = cudaMemcpy(du, u, bu, cudaMemcpyHostToDevice);
+    if (e == cudaSuccess && multipliers) e = cudaMemcpy(dm, multipliers, bx, cudaMemcpyHostToDevice);
+    if (e == cudaSuccess)
+    {
+        launchDynamicsHessian(dynamics, dyn, method, batch, dx, du, dm, dh, nullptr);
+        e = cudaGetLastError();
+    }
+    if (e == cudaSuccess) e = cudaMemcpy(H, dh, bh, cudaMemcpyDeviceToHost);
+    cudaFree(dx);
+    cudaFree(du);
+    cudaFree(dm);
+    cudaFree(dh);
+    if (e != cudaSuccess) return fail(B200SQP_ERR_CUDA, std::string("dynamics_hessian: ") + cudaGetErrorString(e));
+    return B200SQP_OK;
+}
+
 int b200sqp_get_statistics(b200sqp_handle h, int32_t* inner_passes, int32_t* rejects, int32_t* relinearizations, double* mu, double* rho)
 {
     int rc = checkHandle(h);

@@ -55,6 +55,10 @@ void launchFirstControls(const double* z0, const double* z1, const int* cur, int
 struct DynParams;
 bool launchLinearizeDynamics(int dynamics, const DynParams& dyn, int method, int B, const double* x, const double* u, double* A, double* Bm,
                              cudaStream_t);
+// ForwardDifferences::hessian (method 0) / CentralDifferences::hessian (method 1) of the dynamics w.r.t. [x; u] for B points
+// (kernels_linearize.cu); mult [B][nx] or null, H [B][(nx+nu)^2] column-major per point; false = dynamics id not in the registry
+bool launchDynamicsHessian(int dynamics, const DynParams& dyn, int method, int B, const double* x, const double* u, const double* mult, double* H,
+                           cudaStream_t);
 // SimulatedPlant::control for B plants: x_next = solveIVP(x, u, dt), integrator 0 = explicit Euler, 1 = RK4 (kernels_plant.cu);
 // x, x_next [B][nx], u [B][nu]; u_log [B][nu] or null receives a copy of u; false = dynamics id not in the registry
 bool launchPlantStep(int dynamics, const DynParams& dyn, int integrator, double dt, int B, const double* x, const double* u, double* x_next,

@@ -28,7 +28,7 @@ ABI_SYMBOLS = [
     "b200sqp_last_solve_ms", "b200sqp_launch_count", "b200sqp_device_pointers", "b200sqp_set_stream", "b200sqp_set_threads_per_instance",
     "b200sqp_set_phase_profile", "b200sqp_get_phase_cycles", "b200sqp_final_constraint_indices",
     "b200sqp_peer_export", "b200sqp_peer_attach", "b200sqp_peer_wait", "b200sqp_peer_gathered", "b200sqp_peer_detach", "b200sqp_peer_status", "b200sqp_linearize_dynamics", "b200sqp_warm_start_shift", "b200sqp_mpc_step",
-    "b200sqp_plant_step", "b200sqp_closed_loop",
+    "b200sqp_plant_step", "b200sqp_closed_loop", "b200sqp_dynamics_hessian",
 ]
 
 
@@ -125,6 +125,22 @@ def linearize_dynamics(dynamics, dyn_params, x, u, method="forward", device=0):
                                                       _d(x), _d(u), _d(A), _d(Bm), C.c_int32(device)))
     # the library writes column-major blocks per point
     return A.transpose(0, 2, 1).copy(), Bm.transpose(0, 2, 1).copy()
+
+
+def dynamics_hessian(dynamics, dyn_params, x, u, multipliers=None, method="forward", device=0):
+    """ForwardDifferences / CentralDifferences::hessian of the dynamics w.r.t. [x; u] for a batch of points on the device.
+    x [B, nx], u [B, nu], multipliers [B, nx] or None -> H [B, nx+nu, nx+nu] (H[b, i, j] = sum_v mult_v d2 f_v / dz_i dz_j)"""
+    nx, nu = abi.DYN_DIMS[dynamics]
+    x = np.ascontiguousarray(x, np.float64).reshape(-1, nx)
+    u = np.ascontiguousarray(u, np.float64).reshape(-1, nu)
+    B = x.shape[0]
+    m = None if multipliers is None else np.ascontiguousarray(multipliers, np.float64).reshape(B, nx)
+    p = np.zeros(abi.MAX_DYN_PARAMS)
+    p[:len(dyn_params)] = dyn_params
+    H = np.zeros((B, nx + nu, nx + nu))
+    _check(load_library().b200sqp_dynamics_hessian(C.c_int32(dynamics), _d(p), C.c_int32({"forward": 0, "central": 1}[method]), C.c_int32(B),
+                                                    _d(x), _d(u), _d(m), _d(H), C.c_int32(device)))
+    return H.transpose(0, 2, 1).copy()  # the library writes column-major blocks per point
 
 
 INTEGRATORS = {"euler": 0, "rk4": 1}

@@ -241,6 +241,15 @@ int b200sqp_evaluate(b200sqp_handle h, double weight_eq, double weight_ineq, dou
 int b200sqp_linearize_dynamics(int32_t dynamics, const double* dyn_params, int32_t method, int32_t batch, const double* x, const double* u,
                                double* A, double* B, int32_t device);
 
+/* Finite-difference Hessian of the system dynamics w.r.t. z = [x; u] at `batch` points, the remaining half of the reference's
+ * numerics/finite_differences: method 0 = ForwardDifferences::hessian
+ * (src/numerics/include/corbo-numerics/finite_differences.hpp:50-104), 1 = CentralDifferences::hessian (:190-273); delta = 1e-5,
+ * in-place increments in the reference's order, every (i, j) pair evaluated.  H_p = sum_v multipliers[p][v] * d2 f_v / dz dz
+ * (multipliers [batch*nx], NULL = plain sum over the components, as in the reference); H [batch*(nx+nu)^2], column-major per point.
+ * Host pointers; handle-less like b200sqp_linearize_dynamics. */
+int b200sqp_dynamics_hessian(int32_t dynamics, const double* dyn_params, int32_t method, int32_t batch, const double* x, const double* u,
+                             const double* multipliers, double* H, int32_t device);
+
 /* Per-instance LM bookkeeping of the last solve: [batch] each, host pointers, any may be NULL.
  * inner_passes = number of factorisations, rejects = rejected trial steps, relinearizations = Jacobian evaluations. */
 int b200sqp_get_statistics(b200sqp_handle h, int32_t* inner_passes, int32_t* rejects, int32_t* relinearizations, double* mu, double* rho);

@@ -106,6 +106,20 @@ class _Checker:
             raise RuntimeError(f"{self.prefix}linearize failed: {rc}")
         return A.T.copy(), Bm.T.copy()  # the checkers write column-major
 
+    def dynamics_hessian(self, ocp, x, u, multipliers=None, method="forward"):
+        """ForwardDifferences / CentralDifferences::hessian of the descriptor's dynamics w.r.t. [x; u] at one point -> H [nz, nz]"""
+        nz = ocp.nx + ocp.nu
+        x = np.ascontiguousarray(x, np.float64)
+        u = np.ascontiguousarray(u, np.float64)
+        m = None if multipliers is None else np.ascontiguousarray(multipliers, np.float64)
+        H = np.zeros((nz, nz))
+        fn = getattr(self.lib, self.prefix + "dynamics_hessian")
+        fn.restype = C.c_int
+        rc = fn(C.byref(ocp), C.c_int({"forward": 0, "central": 1}[method]), _d(x), _d(u), _d(m), _d(H))
+        if rc != 0:
+            raise RuntimeError(f"{self.prefix}dynamics_hessian failed: {rc}")
+        return H.T.copy()  # the checkers write column-major
+
     def plant_step(self, ocp, x, u, dt, integrator="euler"):
         """SimulatedPlant::control for a batch of points (dynamics of the descriptor): x [B, nx], u [B, nu] -> x_next [B, nx]"""
         x = np.ascontiguousarray(x, np.float64).reshape(-1, ocp.nx)

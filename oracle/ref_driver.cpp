@@ -790,6 +790,30 @@ int corbo_ref_linearize(const b200sqp_ocp* d, int method, const double* x0, cons
     return 0;
 }
 
+// the reference's own ForwardDifferences::hessian (method 0) / CentralDifferences::hessian (method 1) templates applied to its
+// SystemDynamicsInterface::dynamics as a function of z = [x; u]; H [(nx+nu)^2] column-major
+int corbo_ref_dynamics_hessian(const b200sqp_ocp* d, int method, const double* x0, const double* u0, const double* multipliers, double* H)
+{
+    SystemDynamicsInterface::Ptr dyn = makeDynamics(*d);
+    if (!dyn) return -1;
+    const int nx = d->nx, nu = d->nu, nz = nx + nu;
+    Eigen::VectorXd z(nz);
+    z.head(nx) = Eigen::Map<const Eigen::VectorXd>(x0, nx);
+    z.tail(nu) = Eigen::Map<const Eigen::VectorXd>(u0, nu);
+    auto inc  = [&z](int idx, double inc) { z[idx] += inc; };
+    auto eval = [&](Eigen::VectorXd& values) {
+        Eigen::VectorXd x = z.head(nx), u = z.tail(nu);
+        dyn->dynamics(x, u, values);
+    };
+    Eigen::MatrixXd Hm(nz, nz);
+    if (method == 0)
+        ForwardDifferences::hessian(inc, eval, nx, Hm, multipliers);
+    else
+        CentralDifferences::hessian(inc, eval, nx, Hm, multipliers);
+    Eigen::Map<Eigen::MatrixXd>(H, nz, nz) = Hm;
+    return 0;
+}
+
 int corbo_ref_known_answer(int case_id, int stage, double* x_out, double* expected, double* tol, int32_t* n_out)
 {
     SimpleOptimizationProblemWithCallbacks optim;

@@ -1308,6 +1308,77 @@ int sqp_oracle_linearize(const b200sqp_ocp* d, int method, const double* x0, con
     return 0;
 }
 
+// ForwardDifferences::hessian (numerics/include/corbo-numerics/finite_differences.hpp:50-104, method 0) and
+// CentralDifferences::hessian (:190-273, method 1) applied to the dynamics as a function of z = [x; u]: delta = 1e-5, in-place
+// increments in the reference's order, all (i, j) pairs, optional multipliers [nx].  H [(nx+nu)^2] column-major.
+int sqp_oracle_dynamics_hessian(const b200sqp_ocp* d, int method, const double* x0, const double* u0, const double* multipliers, double* H)
+{
+    Dyn f = makeDynamics(*d);
+    if (!f) return -1;
+    const int nx = d->nx, nu = d->nu, nz = nx + nu;
+    std::vector<double> z(nz);
+    for (int i = 0; i < nx; ++i) z[i] = x0[i];
+    for (int i = 0; i < nu; ++i) z[nx + i] = u0[i];
+    constexpr double delta = 1e-5, ddelta = 2 * delta;
+    std::vector<double> fa(nx), fb(nx), fc(nx), fd(nx);
+    auto eval = [&](std::vector<double>& out) { f(z.data(), z.data() + nx, out.data()); };
+    for (int i = 0; i < nz; ++i)
+    {
+        for (int j = 0; j < nz; ++j)
+        {
+            double h;
+            if (method == 0)
+            {
+                constexpr double scalar = 1 / (delta * delta);
+                z[i] += delta;
+                eval(fa);  // f1
+                z[j] += delta;
+                eval(fc);  // f3
+                z[i] += -delta;
+                eval(fb);  // f2
+                z[j] += -delta;
+                eval(fd);  // f0
+                h = multipliers ? scalar * (fc[0] - fa[0] - fb[0] + fd[0]) * multipliers[0] : scalar * (fc[0] - fa[0] - fb[0] + fd[0]);
+                for (int v = 1; v < nx; ++v)
+                    h += multipliers ? scalar * (fc[v] - fa[v] - fb[v] + fd[v]) * multipliers[v] : scalar * (fc[v] - fa[v] - fb[v] + fd[v]);
+            }
+            else if (i == j)
+            {
+                constexpr double scalar_xx = 1 / (delta * delta);
+                z[i] += delta;
+                eval(fa);  // f1
+                z[i] += -ddelta;
+                eval(fc);  // f3
+                z[i] += delta;
+                eval(fb);  // f2
+                h = multipliers ? scalar_xx * (fa[0] - 2 * fb[0] + fc[0]) * multipliers[0] : scalar_xx * (fa[0] - 2 * fb[0] + fc[0]);
+                for (int v = 1; v < nx; ++v)
+                    h += multipliers ? scalar_xx * (fa[v] - 2 * fb[v] + fc[v]) * multipliers[v] : scalar_xx * (fa[v] - 2 * fb[v] + fc[v]);
+            }
+            else
+            {
+                constexpr double scalar_xy = 1 / (4.0 * delta * delta);
+                z[i] += delta;
+                z[j] += delta;
+                eval(fa);  // f1 (+,+)
+                z[j] += -ddelta;
+                eval(fb);  // f2 (+,-)
+                z[i] += -ddelta;
+                eval(fd);  // f4 (-,-)
+                z[j] += ddelta;
+                eval(fc);  // f3 (-,+)
+                z[i] += delta;
+                z[j] += -delta;
+                h = multipliers ? scalar_xy * (fa[0] - fb[0] - fc[0] + fd[0]) * multipliers[0] : scalar_xy * (fa[0] - fb[0] - fc[0] + fd[0]);
+                for (int v = 1; v < nx; ++v)
+                    h += multipliers ? scalar_xy * (fa[v] - fb[v] - fc[v] + fd[v]) * multipliers[v] : scalar_xy * (fa[v] - fb[v] - fc[v] + fd[v]);
+            }
+            H[(size_t)j * nz + i] = h;
+        }
+    }
+    return 0;
+}
+
 int sqp_oracle_known_answer(int case_id, int stage, double* x_out, double* expected, double* tol, int32_t* n_out)
 {
     KnownAnswer c;

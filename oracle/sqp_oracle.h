@@ -24,6 +24,7 @@ int sqp_oracle_solve_sequence(const b200sqp_ocp* d, const b200sqp_lm_options* o,
                               double* params_out, double* chi2_out);
 int sqp_oracle_plant_step(const b200sqp_ocp* d, int integrator, double dt, int batch, const double* x, const double* u, double* x_next);
 double sqp_oracle_plant_interval(double plant_dt, int step);
+int sqp_oracle_dynamics_hessian(const b200sqp_ocp* d, int method, const double* x0, const double* u0, const double* multipliers, double* H);
 int sqp_oracle_linearize(const b200sqp_ocp* d, int method, const double* x0, const double* u0, double* A, double* B);
 int sqp_oracle_known_answer(int case_id, int stage, double* x_out, double* expected, double* tol, int32_t* n_out);
 

@@ -65,6 +65,10 @@ def linearize_points(ocp, seed=17):
     return rng.uniform(-1.5, 1.5, (LINEARIZE_POINTS, ocp.nx)), rng.uniform(-1.0, 1.0, (LINEARIZE_POINTS, ocp.nu))
 
 
+def hessian_multipliers(ocp, seed=29):
+    return np.random.default_rng(seed).uniform(-2.0, 2.0, (LINEARIZE_POINTS, ocp.nx))
+
+
 # plant fixtures: SimulatedPlant::control at the linearisation points, ClosedLoopControlTask's loop
 PLANT_DT = 0.05
 CLOSED_LOOP_STEPS = 12

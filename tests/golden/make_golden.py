@@ -71,6 +71,11 @@ def main():
                 out[f"{name}_{method}_A"] = np.stack([a for a, _ in AB])
                 out[f"{name}_{method}_B"] = np.stack([b for _, b in AB])
             out[f"{name}_x"], out[f"{name}_u"] = xs, us
+            # the second half of numerics/finite_differences: Forward/CentralDifferences::hessian (delta = 1e-5) of the same dynamics
+            mult = cases.hessian_multipliers(ocp)
+            for method in ("forward", "central"):
+                out[f"{name}_{method}_H"] = np.stack([ref.dynamics_hessian(ocp, xs[i], us[i], None, method) for i in range(len(xs))])
+                out[f"{name}_{method}_Hm"] = np.stack([ref.dynamics_hessian(ocp, xs[i], us[i], mult[i], method) for i in range(len(xs))])
         np.savez_compressed(os.path.join(HERE, "linearize.npz"), **out)
         print("linearize:", len(out), "arrays")
     if not only or "warm_start" in only:
