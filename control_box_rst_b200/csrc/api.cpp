@@ -408,6 +408,36 @@ int b200sqp_get_dims(b200sqp_handle h, b200sqp_dims* out)
     return B200SQP_OK;
 }
 
+// Device view of a caller's host buffer if it is pinned (cudaHostAlloc / cudaHostRegister: mapped into the device's address space
+// under unified addressing), else null.  Small per-step transfers (start states in; first controls, chi2, status out) then go
+// through the kernels that consume / produce them instead of one cudaMemcpyAsync each: five DMA set-ups per step cost more than the
+// bytes they move.  Pageable buffers keep the memcpy path.
+static void* pinnedView(const void* p)
+{
+    if (!p) return nullptr;
+    cudaPointerAttributes a;
+    if (cudaPointerGetAttributes(&a, p) != cudaSuccess)
+    {
+        cudaGetLastError();
+        return nullptr;
+    }
+    return (a.type == cudaMemoryTypeHost) ? a.devicePointer : nullptr;
+}
+
+// fixed goal components follow the reference: _xf.values()[i] = xref[i] (full_discretization_grid_base.cpp:102-106)
+static void fillPinnedGoal(b200sqp_handle h)
+{
+    const int nb = h->s.nb, xo = h->s.nu + h->s.vt;
+    unsigned mask = 0;
+    for (int i = 0; i < h->s.nx; ++i)
+        if (h->s.xfFixed(i)) mask |= 1u << i;
+    if (mask)
+    {
+        launchFillPinned(h->st.xref, h->st.z[0], h->st.z[1], (h->s.K - 1) * nb + xo, h->s.K * nb, h->s.nx, mask, h->B, h->stream);
+        h->launches += 1;
+    }
+}
+
 // start states / references that are already in HBM ([B][nx], host order): the device half of b200sqp_set_problem_data
 static int startStatesFromDevice(b200sqp_handle h, const double* d_x0, const double* d_xref /*null = keep the current reference*/)
 {
@@ -460,12 +490,24 @@ int b200sqp_set_problem_data(b200sqp_handle h, const double* x0, const double* x
     if (rc) return rc;
     if (!x0) return fail(B200SQP_ERR_INVALID, "x0 is null");
     const size_t bytes = sizeof(double) * (size_t)h->B * h->s.nx;
-    CUDA_TRY(cudaMemcpyAsync(h->d_x0_host_order, x0, bytes, cudaMemcpyHostToDevice, h->stream));
-    if (xref)
+    // pinned buffers are read in place by the ingest kernel; pageable ones are staged with a copy first
+    const double* x0_src   = (const double*)pinnedView(x0);
+    const double* xref_src = xref ? (const double*)pinnedView(xref) : nullptr;
+    if (!x0_src)
+    {
+        CUDA_TRY(cudaMemcpyAsync(h->d_x0_host_order, x0, bytes, cudaMemcpyHostToDevice, h->stream));
+        x0_src = h->d_x0_host_order;
+    }
+    if (xref && !xref_src)
+    {
         CUDA_TRY(cudaMemcpyAsync(h->d_xref_host_order, xref, bytes, cudaMemcpyHostToDevice, h->stream));
-    else
-        CUDA_TRY(cudaMemsetAsync(h->st.xref, 0, sizeof(double) * (size_t)h->S * h->s.nx, h->stream));
-    return startStatesFromDevice(h, h->d_x0_host_order, xref ? h->d_xref_host_order : nullptr);
+        xref_src = h->d_xref_host_order;
+    }
+    launchIngest(x0_src, xref_src, h->s.nx, h->st.x0, h->st.xref, h->d_x0_host_order, h->d_xref_host_order, h->B, h->stream);
+    h->launches += 1;
+    fillPinnedGoal(h);
+    CUDA_TRY(cudaGetLastError());
+    return B200SQP_OK;
 }
 
 int b200sqp_initialize_trajectories(b200sqp_handle h)
@@ -590,6 +632,26 @@ int b200sqp_solve(b200sqp_handle h, const b200sqp_lm_options* opts, int32_t new_
     return B200SQP_OK;
 }
 
+// first controls (when u0_out is given), chi2 and status of the last solve to the caller's host buffers: one kernel writes pinned
+// buffers in place; pageable ones get a cudaMemcpyAsync each.  Asynchronous on the handle's stream.
+static int exportSmallResults(b200sqp_handle h, double* u0_out, double* chi2_out, int32_t* status_out)
+{
+    double* u0_view   = (double*)pinnedView(u0_out);
+    double* chi2_view = (double*)pinnedView(chi2_out);
+    int* status_view  = (int*)pinnedView(status_out);
+    if (u0_out || chi2_view || status_view)
+    {
+        launchExport(h->st.z[0], h->st.z[1], h->st.cur, h->s.nu, h->s.K * h->s.nb, h->st.chi2, h->st.status, u0_out ? h->d_u0 : nullptr, u0_view,
+                     chi2_view, status_view, h->B, h->stream);
+        h->launches += 1;
+        CUDA_TRY(cudaGetLastError());
+    }
+    if (u0_out && !u0_view) CUDA_TRY(cudaMemcpyAsync(u0_out, h->d_u0, sizeof(double) * (size_t)h->B * h->s.nu, cudaMemcpyDeviceToHost, h->stream));
+    if (status_out && !status_view) CUDA_TRY(cudaMemcpyAsync(status_out, h->st.status, sizeof(int32_t) * h->B, cudaMemcpyDeviceToHost, h->stream));
+    if (chi2_out && !chi2_view) CUDA_TRY(cudaMemcpyAsync(chi2_out, h->st.chi2, sizeof(double) * h->B, cudaMemcpyDeviceToHost, h->stream));
+    return B200SQP_OK;
+}
+
 int b200sqp_step(b200sqp_handle h, const b200sqp_lm_options* opts, int32_t cold_start, const double* x0, const double* xref, double* params_out,
                  double* chi2_out, int32_t* status_out)
 {
@@ -610,8 +672,8 @@ int b200sqp_step(b200sqp_handle h, const b200sqp_lm_options* opts, int32_t cold_
         CUDA_TRY(cudaGetLastError());
         CUDA_TRY(cudaMemcpyAsync(params_out, h->d_params, sizeof(double) * (size_t)h->B * n, cudaMemcpyDeviceToHost, h->stream));
     }
-    if (status_out) CUDA_TRY(cudaMemcpyAsync(status_out, h->st.status, sizeof(int32_t) * h->B, cudaMemcpyDeviceToHost, h->stream));
-    if (chi2_out) CUDA_TRY(cudaMemcpyAsync(chi2_out, h->st.chi2, sizeof(double) * h->B, cudaMemcpyDeviceToHost, h->stream));
+    rc = exportSmallResults(h, nullptr, chi2_out, status_out);
+    if (rc) return rc;
     CUDA_TRY(cudaStreamSynchronize(h->stream));
     return B200SQP_OK;
 }
@@ -637,12 +699,8 @@ int b200sqp_mpc_step(b200sqp_handle h, const b200sqp_lm_options* opts, int32_t m
     }
     rc = b200sqp_solve_async(h, opts, 1);
     if (rc) return rc;
-    launchFirstControls(h->st.z[0], h->st.z[1], h->st.cur, h->s.nu, h->s.K * h->s.nb, h->d_u0, h->B, h->S, h->stream);
-    h->launches += 1;
-    CUDA_TRY(cudaGetLastError());
-    CUDA_TRY(cudaMemcpyAsync(u0_out, h->d_u0, sizeof(double) * (size_t)h->B * h->s.nu, cudaMemcpyDeviceToHost, h->stream));
-    if (status_out) CUDA_TRY(cudaMemcpyAsync(status_out, h->st.status, sizeof(int32_t) * h->B, cudaMemcpyDeviceToHost, h->stream));
-    if (chi2_out) CUDA_TRY(cudaMemcpyAsync(chi2_out, h->st.chi2, sizeof(double) * h->B, cudaMemcpyDeviceToHost, h->stream));
+    rc = exportSmallResults(h, u0_out, chi2_out, status_out);
+    if (rc) return rc;
     CUDA_TRY(cudaStreamSynchronize(h->stream));
     return B200SQP_OK;
 }

@@ -42,6 +42,12 @@ void launchUnpack(const double* z0, const double* z1, const int* cur, const int*
 void launchFillPinned(const double* xref, double* z0, double* z1, int slot0, int slots, int nx, unsigned mask, int B, cudaStream_t);
 // x0/xref: [B][nx] -> tiled [tile][nx][32]
 void launchTransposeIn(const double* src, int dim, double* dst, int B, int S, cudaStream_t);
+// x0 (+ xref or null = zero) [B][nx], device or pinned-host-mapped -> tiled arrays + host-order device copies, one launch
+void launchIngest(const double* x0_src, const double* xref_src, int nx, double* x0_tiled, double* xref_tiled, double* x0_copy, double* xref_copy,
+                  int B, cudaStream_t);
+// first controls -> u0_dev (+ u0_out), chi2 -> chi2_out, status -> status_out; the *_out are device views of pinned host buffers or null
+void launchExport(const double* z0, const double* z1, const int* cur, int nu, int slots, const double* chi2, const int* status, double* u0_dev,
+                  double* u0_out, double* chi2_out, int* status_out, int B, cudaStream_t);
 // [rows][S] -> [B][rows]
 void launchTransposeOut(const double* src, int rows, double* dst, int B, int S, cudaStream_t);
 // FullDiscretizationGridBase::initializeSequences (full_discretization_grid_base.cpp:134-179) on the device

@@ -52,6 +52,46 @@ __global__ void transposeInKernel(const double* __restrict__ src, int dim, doubl
     for (int j = 0; j < dim; ++j) dst[tiled(i, j, dim)] = src[(size_t)i * dim + j];
 }
 
+// Start states and references of a step in one launch: [B][nx] (device memory, or pinned host memory read in place over PCIe) ->
+// tiled [tile][nx][32], plus the host-order device copies the other entry points use.  xref_src null = zero reference.
+__global__ void ingestKernel(const double* __restrict__ x0_src, const double* __restrict__ xref_src, int nx, double* __restrict__ x0_tiled,
+                             double* __restrict__ xref_tiled, double* __restrict__ x0_copy, double* __restrict__ xref_copy, int B)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= B) return;
+    for (int j = 0; j < nx; ++j)
+    {
+        const double v         = x0_src[(size_t)i * nx + j];
+        x0_tiled[tiled(i, j, nx)] = v;
+        if (x0_copy != x0_src) x0_copy[(size_t)i * nx + j] = v;
+        const double r = xref_src ? xref_src[(size_t)i * nx + j] : 0.0;
+        xref_tiled[tiled(i, j, nx)] = r;
+        if (xref_src && xref_copy != xref_src) xref_copy[(size_t)i * nx + j] = r;
+    }
+}
+
+// Small per-instance results of a step in one launch: first controls -> u0_dev [B][nu] (always) and, where the caller's buffers
+// are pinned host memory, u0 / chi2 / status written in place over PCIe (any may be null)
+__global__ void exportKernel(const double* __restrict__ z0, const double* __restrict__ z1, const int* __restrict__ cur, int nu, int slots,
+                             const double* __restrict__ chi2, const int* __restrict__ status, double* __restrict__ u0_dev, double* __restrict__ u0_out,
+                             double* __restrict__ chi2_out, int* __restrict__ status_out, int B)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= B) return;
+    if (u0_dev || u0_out)
+    {
+        const double* src = cur[i] ? z1 : z0;
+        for (int j = 0; j < nu; ++j)
+        {
+            const double v = src[tiled(i, j, slots)];
+            if (u0_dev) u0_dev[(size_t)i * nu + j] = v;
+            if (u0_out) u0_out[(size_t)i * nu + j] = v;
+        }
+    }
+    if (chi2_out) chi2_out[i] = chi2[i];
+    if (status_out) status_out[i] = status[i];
+}
+
 __global__ void transposeOutKernel(const double* __restrict__ src, int rows, double* __restrict__ dst, int B, int S)
 {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -270,6 +310,16 @@ void launchFillPinned(const double* xref, double* z0, double* z1, int slot0, int
 void launchTransposeIn(const double* src, int dim, double* dst, int B, int S, cudaStream_t st)
 {
     transposeInKernel<<<blocksFor(B), 128, 0, st>>>(src, dim, dst, B, S);
+}
+void launchIngest(const double* x0_src, const double* xref_src, int nx, double* x0_tiled, double* xref_tiled, double* x0_copy, double* xref_copy,
+                  int B, cudaStream_t st)
+{
+    ingestKernel<<<blocksFor(B), 128, 0, st>>>(x0_src, xref_src, nx, x0_tiled, xref_tiled, x0_copy, xref_copy, B);
+}
+void launchExport(const double* z0, const double* z1, const int* cur, int nu, int slots, const double* chi2, const int* status, double* u0_dev,
+                  double* u0_out, double* chi2_out, int* status_out, int B, cudaStream_t st)
+{
+    exportKernel<<<blocksFor(B), 128, 0, st>>>(z0, z1, cur, nu, slots, chi2, status, u0_dev, u0_out, chi2_out, status_out, B);
 }
 void launchTransposeOut(const double* src, int rows, double* dst, int B, int S, cudaStream_t st)
 {
