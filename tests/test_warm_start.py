@@ -174,3 +174,37 @@ def test_mpc_step_front_end_matches_reference_closed_loops():
             x = x + (k1 + 2.0 * k2 + 2.0 * k3 + k4) / 6.0
             np.testing.assert_allclose(x, gold_x[s + 1], rtol=0, atol=2e-6)
         lm.clear()
+
+
+@pytest.mark.gpu
+def test_pinned_and_pageable_host_buffers_give_the_same_bits():
+    """b200sqp_step / b200sqp_mpc_step read pinned start states in place and write the small results straight into pinned buffers
+    (ingest / export kernels); pageable buffers take the cudaMemcpyAsync path.  Both must deliver identical results."""
+    import torch
+
+    ocp = problems.van_der_pol(30)
+    B = 200  # not a multiple of the tile or the block size
+    x0, _ = problems.instance_data(ocp, B, seed=21)
+    xref = np.tile(np.array([0.2, -0.1]), (B, 1))
+    lm = solver.BatchedLevenbergMarquardt(ocp, B)
+    lm.setIterations(6)
+    n = lm.dims.n_params
+    # pageable (numpy) path
+    p_a, chi2_a, st_a = lm.step(x0, xref, cold_start=True)
+    u_a, chi2_ma, st_ma = lm.mpc_step(x0, xref, mode=solver.BatchedLevenbergMarquardt.MPC_COLD)
+    # pinned path
+    h_x0, h_xref = torch.from_numpy(x0.copy()).pin_memory(), torch.from_numpy(xref.copy()).pin_memory()
+    h_p = torch.zeros((B, n), dtype=torch.float64).pin_memory()
+    h_chi2, h_st = torch.zeros(B, dtype=torch.float64).pin_memory(), torch.zeros(B, dtype=torch.int32).pin_memory()
+    h_u = torch.zeros((B, ocp.nu), dtype=torch.float64).pin_memory()
+    lm.step_raw(h_x0.data_ptr(), h_xref.data_ptr(), h_p.data_ptr(), h_chi2.data_ptr(), h_st.data_ptr(), cold_start=True)
+    assert np.array_equal(h_p.numpy(), p_a) and np.array_equal(h_chi2.numpy(), chi2_a) and np.array_equal(h_st.numpy(), st_a)
+    h_chi2.zero_()
+    h_st.zero_()
+    lm.mpc_step_raw(0, h_x0.data_ptr(), h_xref.data_ptr(), h_u.data_ptr(), h_chi2.data_ptr(), h_st.data_ptr())
+    assert np.array_equal(h_u.numpy(), u_a) and np.array_equal(h_chi2.numpy(), chi2_ma) and np.array_equal(h_st.numpy(), st_ma)
+    # zero reference through the pinned path (xref = NULL)
+    u_b, chi2_b, _ = lm.mpc_step(x0, None, mode=0)
+    lm.mpc_step_raw(0, h_x0.data_ptr(), 0, h_u.data_ptr(), h_chi2.data_ptr(), h_st.data_ptr())
+    assert np.array_equal(h_u.numpy(), u_b) and np.array_equal(h_chi2.numpy(), chi2_b)
+    lm.clear()
