@@ -208,7 +208,7 @@ def main_reference(args):
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line))
+    emit(line)
     return 0
 
 
@@ -434,7 +434,7 @@ def main_b200(args):
             v, dt, kind, cores = run_cpu(ocp, opts, args.cpu_sample, seed=1234 + args.config)
             line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": cores, "kind": kind,
                                     "sample": f"{args.cpu_sample} instances of the same workload, {dt:.2f} s wall on {cores} threads"}
-        print(json.dumps(line))
+        emit(line)
     if use_p2p:
         if lm.peer_timed_out():
             raise SystemExit("bench.py: a peer never arrived in b200sqp_peer_wait (2 s bound)")
@@ -446,6 +446,24 @@ def main_b200(args):
     return 0
 
 
+_JSON_FD = None
+
+
+def emit(line):
+    """the ONE JSON line, on the process's original stdout"""
+    data = (json.dumps(line) + "\n").encode()
+    if _JSON_FD is None:
+        sys.stdout.write(data.decode())
+        sys.stdout.flush()
+    else:
+        os.write(_JSON_FD, data)
+
+
 if __name__ == "__main__":
     a = parse_args()
+    # libraries print to file descriptor 1 behind Python's back (NCCL's "NCCL version ..." banner at communicator creation): keep the
+    # original stdout for the JSON line only and send everything else that lands on fd 1 to stderr
+    sys.stdout.flush()
+    _JSON_FD = os.dup(1)
+    os.dup2(2, 1)
     sys.exit(main_reference(a) if a.impl == "reference" else main_b200(a))
