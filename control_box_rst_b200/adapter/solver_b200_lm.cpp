@@ -480,4 +480,88 @@ bool SolverB200Lm::solveBatch(const std::vector<OptimizationProblemInterface*>& 
     return true;
 }
 
+bool SolverB200Lm::evaluateOnDevice(OptimizationProblemInterface& problem, double weight_eq, double weight_ineq, double weight_bounds,
+                                    Eigen::VectorXd* values, Eigen::SparseMatrix<double>* jacobian)
+{
+    if (!upload(problem, 1))
+    {
+        fail(_error);
+        return false;
+    }
+    const int n = _dims.n_params, m = _dims.m_lsq + _dims.m_eq + _dims.m_ineq + _dims.m_bounds, nnz = _dims.nnz_jacobian;
+    if (_fresh || (int)_col_ptr.size() != n + 1)
+    {
+        _col_ptr.assign(n + 1, 0);
+        _row_idx.assign(nnz, 0);
+        if (b200sqp_jacobian_pattern(&_ocp, _col_ptr.data(), _row_idx.data()) != 0)
+        {
+            fail(std::string("b200sqp_jacobian_pattern: ") + b200sqp_last_error());
+            return false;
+        }
+    }
+    std::vector<double> x0, xref;
+    b200sqp_ocp d;
+    if (!describe(problem, d, x0, xref))
+    {
+        fail(_error);
+        return false;
+    }
+    Eigen::VectorXd params(n);
+    problem.getParameterVector(params);
+    if (b200sqp_set_problem_data(_handle, x0.data(), xref.data()) != 0 || b200sqp_set_params(_handle, params.data()) != 0)
+    {
+        fail(std::string("upload failed: ") + b200sqp_last_error());
+        return false;
+    }
+    if (_fresh)
+    {
+        // new structure on the device: run the guard once, then restore the unperturbed parameters
+        if (!selfCheck(problem) || b200sqp_set_params(_handle, params.data()) != 0)
+        {
+            fail(_error);
+            return false;
+        }
+    }
+    std::vector<double> vals(m), jac(jacobian ? nnz : 0);
+    if (b200sqp_evaluate(_handle, weight_eq, weight_ineq, weight_bounds, vals.data(), jacobian ? jac.data() : nullptr) != 0 ||
+        b200sqp_get_params(_handle, params.data()) != 0)
+    {
+        fail(std::string("b200sqp_evaluate: ") + b200sqp_last_error());
+        return false;
+    }
+    if (jacobian) problem.setParameterVector(params);  // the in-place differences leave their drift in the vertices, as in the reference
+    if (values) *values = Eigen::Map<const Eigen::VectorXd>(vals.data(), m);
+    if (jacobian)
+    {
+        // compressed CSC with the reference's pattern (explicit zeros included, rows ascending within a column)
+        Eigen::Map<const Eigen::SparseMatrix<double, Eigen::ColMajor, int32_t>> view(m, n, nnz, _col_ptr.data(), _row_idx.data(), jac.data());
+        *jacobian = view;
+    }
+    return true;
+}
+
+void HyperGraphOptimizationProblemB200::computeCombinedSparseJacobian(Eigen::SparseMatrix<double>& jacobian, bool objective_lsq, bool equality,
+                                                                      bool inequality, bool finite_combined_bounds, bool active_ineq,
+                                                                      double weight_eq, double weight_ineq, double weight_bounds,
+                                                                      const Eigen::VectorXd* /*values*/, const Eigen::VectorXi* /*col_nnz*/)
+{
+    // the device evaluates the combined Jacobian the least-squares solvers ask for: all four categories, active-set inequality rows
+    // (it recomputes the activity from the residuals at the same point, which is what the caller's `values` hold)
+    if (!_evaluator || !(objective_lsq && equality && inequality && finite_combined_bounds && active_ineq))
+    {
+        PRINT_ERROR("HyperGraphOptimizationProblemB200: no device evaluator set, or a category selection the device path does not serve");
+        _failed = true;
+        jacobian.setZero();
+        return;
+    }
+    if (!_evaluator->evaluateOnDevice(*this, weight_eq, weight_ineq, weight_bounds, nullptr, &jacobian))
+    {
+        PRINT_ERROR("HyperGraphOptimizationProblemB200: " << _evaluator->lastError());
+        _failed = true;
+        jacobian.setZero();
+        return;
+    }
+    ++_device_evaluations;
+}
+
 }  // namespace corbo

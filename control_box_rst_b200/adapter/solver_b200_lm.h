@@ -19,6 +19,7 @@
 #include <corbo-numerics/finite_differences_collocation.h>
 #include <corbo-numerics/integrator_interface.h>
 #include <corbo-optimal-control/functions/stage_functions.h>
+#include <corbo-optimization/hyper_graph/hyper_graph_optimization_problem_edge_based.h>
 #include <corbo-optimization/solver/nlp_solver_interface.h>
 #include <corbo-systems/system_dynamics_interface.h>
 
@@ -65,6 +66,13 @@ class SolverB200Lm : public NlpSolverInterface
     bool solveBatch(const std::vector<OptimizationProblemInterface*>& problems, bool new_run, std::vector<SolverStatus>* statuses,
                     std::vector<double>* obj_values);
 
+    // ---- second plugin surface: the residual vector and the combined sparse Jacobian of `problem` at its current
+    // parameters, evaluated on the device (b200sqp_evaluate) -- what LevenbergMarquardtSparse::computeValues (:222-246) and
+    // ...EdgeBased::computeCombinedSparseJacobian (:1480-1753) deliver, for solvers other than this one.  Like the reference's Jacobian
+    // evaluation it leaves the round-trip drift of the in-place differences in the problem's parameters.  values / jacobian may be null.
+    bool evaluateOnDevice(OptimizationProblemInterface& problem, double weight_eq, double weight_ineq, double weight_bounds, Eigen::VectorXd* values,
+                          Eigen::SparseMatrix<double>* jacobian);
+
     const std::string& lastError() const { return _error; }
     double lastSolveMilliseconds() const;
 
@@ -90,9 +98,37 @@ class SolverB200Lm : public NlpSolverInterface
     FinalStageCost::Ptr _final_cost;
     FinalStageConstraint::Ptr _final_constraint;
     ReferenceTrajectoryInterface::Ptr _xref;
+    std::vector<int32_t> _col_ptr, _row_idx;  // CSC pattern of the combined Jacobian of the uploaded structure
 };
 
 FACTORY_REGISTER_NLP_SOLVER(SolverB200Lm)
+
+// The second surface as a reference-side class: a hypergraph optimisation problem whose combined sparse Jacobian comes from the
+// device, so that ANY least-squares solver of the reference (e.g. its own LevenbergMarquardtSparse) runs on device Jacobians.
+// Registered like the reference's problem classes (hyper_graph_optimization_problem_base.h:266).  Everything else (values,
+// increments, backups, indices) is inherited: only the 91 % of an iteration the survey measured in computeCombinedSparseJacobian move.
+// The evaluator is a SolverB200Lm that was handed the functors (setSystemDynamics, setStageCost, ...); calls the device cannot serve
+// (partial category selections, structures outside the registry) are an error, not a silent host evaluation.
+class HyperGraphOptimizationProblemB200 : public HyperGraphOptimizationProblemEdgeBased
+{
+ public:
+    BaseHyperGraphOptimizationProblem::Ptr getInstance() const override { return std::make_shared<HyperGraphOptimizationProblemB200>(); }
+    void setDeviceEvaluator(std::shared_ptr<SolverB200Lm> evaluator) { _evaluator = evaluator; }
+    int deviceJacobianEvaluations() const { return _device_evaluations; }
+    bool failed() const { return _failed; }
+
+    void computeCombinedSparseJacobian(Eigen::SparseMatrix<double>& jacobian, bool objective_lsq, bool equality, bool inequality,
+                                       bool finite_combined_bounds, bool active_ineq = false, double weight_eq = 1.0, double weight_ineq = 1.0,
+                                       double weight_bounds = 1.0, const Eigen::VectorXd* values = nullptr,
+                                       const Eigen::VectorXi* col_nnz = nullptr) override;
+
+ private:
+    std::shared_ptr<SolverB200Lm> _evaluator;
+    int _device_evaluations = 0;
+    bool _failed            = false;
+};
+
+FACTORY_REGISTER_HYPER_GRAPH_OPTIMIZATION_PROBLEM(HyperGraphOptimizationProblemB200)
 
 }  // namespace corbo
 

@@ -33,7 +33,8 @@ struct Loop
     std::shared_ptr<FiniteDifferencesGrid> grid;
 };
 
-static Loop makeLoop(NlpSolverInterface::Ptr solver, int n, FinalStageConstraint::Ptr final_constraint = {})
+static Loop makeLoop(NlpSolverInterface::Ptr solver, int n, FinalStageConstraint::Ptr final_constraint = {},
+                     std::shared_ptr<HyperGraphOptimizationProblemEdgeBased> problem = {}, std::shared_ptr<SolverB200Lm> evaluator = {})
 {
     Loop l;
     l.dynamics = std::make_shared<VanDerPolOscillator>();
@@ -41,7 +42,7 @@ static Loop makeLoop(NlpSolverInterface::Ptr solver, int n, FinalStageConstraint
     l.grid->setNRef(n);
     l.grid->setDtRef(0.1);
     l.grid->setCostIntegrationRule(FullDiscretizationGridBase::CostIntegrationRule::LeftSum);
-    l.problem = std::make_shared<HyperGraphOptimizationProblemEdgeBased>();
+    l.problem = problem ? problem : std::make_shared<HyperGraphOptimizationProblemEdgeBased>();
     l.ocp     = std::make_shared<StructuredOptimalControlProblem>(l.grid, l.dynamics, l.problem, solver);
     Eigen::MatrixXd Q = Eigen::MatrixXd::Identity(2, 2), R = Eigen::MatrixXd::Constant(1, 1, 0.1);
     auto stage_cost = std::make_shared<QuadraticFormCost>(Q, R, false, true);
@@ -52,7 +53,9 @@ static Loop makeLoop(NlpSolverInterface::Ptr solver, int n, FinalStageConstraint
     Eigen::VectorXd xlb = Eigen::VectorXd::Constant(2, -CORBO_INF_DBL), xub = Eigen::VectorXd::Constant(2, CORBO_INF_DBL);
     Eigen::VectorXd ulb = Eigen::VectorXd::Constant(1, -1.0), uub = Eigen::VectorXd::Constant(1, 1.0);
     l.ocp->setBounds(xlb, xub, ulb, uub);
-    if (auto b200 = std::dynamic_pointer_cast<SolverB200Lm>(solver))
+    auto b200 = std::dynamic_pointer_cast<SolverB200Lm>(solver);
+    if (!b200) b200 = evaluator;  // second surface: the evaluator behind HyperGraphOptimizationProblemB200 needs the same objects
+    if (b200)
     {
         // the same objects the OCP got (the functors behind the edges are private in the reference)
         b200->setSystemDynamics(l.dynamics);
@@ -229,6 +232,53 @@ int main()
         }
         else
             std::printf("ok: unsupported structure -> SolverStatus::Error (%s)\n", s->lastError().c_str());
+    }
+    // ---- 5. second surface: the reference's OWN LevenbergMarquardtSparse on a HyperGraphOptimizationProblemB200 (created by name through
+    //         the reference's factory), i.e. its Jacobians come from the device; against the same solver on the stock problem class.
+    //         Van der Pol is polynomial: Jacobian values, pattern and parameter drift are bit-identical, so the iterates must be too.
+    {
+        auto from_problem_factory = HyperGraphOptimizationProblemFactory::instance().create("HyperGraphOptimizationProblemB200");
+        auto device_problem       = std::dynamic_pointer_cast<HyperGraphOptimizationProblemB200>(from_problem_factory);
+        if (!device_problem)
+        {
+            std::printf("FAIL: HyperGraphOptimizationProblemB200 not registered in Factory<BaseHyperGraphOptimizationProblem>\n");
+            return 1;
+        }
+        auto evaluator = std::make_shared<SolverB200Lm>();
+        device_problem->setDeviceEvaluator(evaluator);
+        auto s_ref = std::make_shared<LevenbergMarquardtSparse>(), s_dev = std::make_shared<LevenbergMarquardtSparse>();
+        s_ref->setIterations(10);
+        s_dev->setIterations(10);
+        Loop lr = makeLoop(s_ref, 30);
+        Loop ld = makeLoop(s_dev, 30, {}, device_problem, evaluator);
+        lr.ocp->initialize();
+        ld.ocp->initialize();
+        Eigen::VectorXd x0(2);
+        x0 << -1.2, 0.8;
+        double worst_p = 0;
+        bool ok5 = true;
+        for (int s = 0; s < 3; ++s)  // cold start, then two warm-started solves with a moved start state
+        {
+            ok5 = lr.ocp->compute(x0, xref, uref, nullptr, Time(0.1 * s), true) && ok5;
+            ok5 = ld.ocp->compute(x0, xref, uref, nullptr, Time(0.1 * s), true) && ok5;
+            Eigen::VectorXd pr(lr.problem->getParameterDimension()), pd(ld.problem->getParameterDimension());
+            lr.problem->getParameterVector(pr);
+            ld.problem->getParameterVector(pd);
+            worst_p = std::max(worst_p, pr.size() == pd.size() ? (pr - pd).cwiseAbs().maxCoeff() : 1e30);
+            Eigen::VectorXd u(1);
+            lr.ocp->getFirstControlInput(u);
+            Eigen::VectorXd xn(2);
+            rk4.solveIVP(x0, u, 0.1, *lr.dynamics, xn);
+            x0 = xn;
+        }
+        std::printf("second surface: reference LevenbergMarquardtSparse on device Jacobians (%d device evaluations): max |p_ref - p_dev| = %.3e, "
+                    "objective %.12g vs %.12g\n",
+                    device_problem->deviceJacobianEvaluations(), worst_p, lr.ocp->getCurrentObjectiveValue(), ld.ocp->getCurrentObjectiveValue());
+        if (!ok5 || device_problem->failed() || device_problem->deviceJacobianEvaluations() < 3 || worst_p != 0.0)
+        {
+            std::printf("FAIL: second surface (ok=%d failed=%d, %s)\n", (int)ok5, (int)device_problem->failed(), evaluator->lastError().c_str());
+            ++failures;
+        }
     }
     std::printf(failures ? "DROP-IN TEST FAILED\n" : "DROP-IN TEST PASSED\n");
     return failures ? 1 : 0;
