@@ -25,6 +25,26 @@ CASES = {
                                             (2.0, 2.0, 2.0), 4),
     "cartpole20_terminal_ball": (lambda: problems.cart_pole_shooting(20, terminal_ball=((1.0, 2.0, 0.5, 0.25), 0.05)), (10.0, 10.0, 10.0), 4),
     "quadrotor8_terminal_ball": (lambda: problems.quadrotor(8, terminal_ball=(tuple(0.5 + 0.1 * i for i in range(12)), 0.02)), (2.0, 2.0, 2.0), 2),
+    # one reference-pinned fixture for every remaining (dynamics, defect, grid) combination the library compiles (kernels_*.cu)
+    "duffing20_cn": (lambda: problems.make_ocp(grid=abi.GRID_FD_UNIFORM, dynamics=abi.DYN_DUFFING, n_grid=20, dt=0.1, q=(1, 1), r=(0.1,), qf=(1, 1),
+                                               u_lb=(-1.5,), u_ub=(1.5,), dyn_params=(1.0, -1.0, 1.0)), (2.0, 2.0, 2.0), 3),
+    "pendulum20_cn": (lambda: problems.make_ocp(grid=abi.GRID_FD_UNIFORM, dynamics=abi.DYN_SIMPLE_PENDULUM, n_grid=20, dt=0.1, q=(1, 1), r=(0.1,),
+                                                qf=(1, 1), u_lb=(-2.0,), u_ub=(2.0,), dyn_params=(0.205, 0.34, 9.81, 0.25)), (2.0, 2.0, 2.0), 3),
+    "dint20_cn": (lambda: problems.make_ocp(grid=abi.GRID_FD_UNIFORM, dynamics=abi.DYN_DOUBLE_INTEGRATOR, n_grid=20, dt=0.1, q=(1, 1), r=(0.1,),
+                                            qf=(1, 1), u_lb=(-1.0,), u_ub=(1.0,), dyn_params=(2.0,)), (2.0, 2.0, 2.0), 3),
+    "dint20_forward": (lambda: problems.make_ocp(grid=abi.GRID_FD_UNIFORM, dynamics=abi.DYN_DOUBLE_INTEGRATOR, n_grid=20, dt=0.1,
+                                                 collocation=abi.COLL_FORWARD, q=(1, 1), r=(0.1,), qf=(1, 1), u_lb=(-1.0,), u_ub=(1.0,),
+                                                 dyn_params=(2.0,)), (2.0, 2.0, 2.0), 3),
+    "cartpole20_cn_fd_grid": (lambda: problems.make_ocp(grid=abi.GRID_FD_UNIFORM, dynamics=abi.DYN_CART_POLE, n_grid=20, dt=0.05, q=(1.0,) * 4,
+                                                        r=(0.01,), qf=(10.0,) * 4, u_lb=(-20.0,), u_ub=(20.0,),
+                                                        dyn_params=(1.0, 0.3, 0.5, 9.81)), (10.0, 10.0, 10.0), 3),
+    "unicycle20_cn_fixed_dt": (lambda: problems.make_ocp(grid=abi.GRID_FD_UNIFORM, dynamics=abi.DYN_UNICYCLE, n_grid=20, dt=0.1, q=(1.0,) * 3,
+                                                         r=(0.1, 0.1), qf=(5.0,) * 3, u_lb=(-1.0, -1.0), u_ub=(1.0, 1.0)), (2.0, 2.0, 2.0), 3),
+    "vdp20_timeopt": (lambda: problems.make_ocp(grid=abi.GRID_FD_NONUNIFORM_VARDT, dynamics=abi.DYN_VAN_DER_POL, n_grid=20, dt=0.1,
+                                                stage_cost=abi.COST_MINIMUM_TIME_LSQ, u_lb=(-1.0,), u_ub=(1.0,), xf_fixed=(1, 1), dt_lb=0.0,
+                                                dt_ub=1.0, dyn_params=(1.0,)), (2.0, 2.0, 2.0), 3),
+    "vdp20_ms_euler": (lambda: problems.van_der_pol_shooting(20, integrator=abi.INT_EULER), (2.0, 2.0, 2.0), 3),
+    "vdp20_ms_rk4": (lambda: problems.van_der_pol_shooting(20), (2.0, 2.0, 2.0), 3),
 }
 
 EVAL_WEIGHTS = (2.0, 3.0, 5.0)

