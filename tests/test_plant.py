@@ -128,3 +128,31 @@ def test_device_closed_loop_monte_carlo_batch_regulates_and_is_instancewise():
     u2, x2, chi2_2, _ = lm2.closed_loop(x0[idx], steps, mode=2, integrator="rk4")
     lm2.clear()
     assert np.array_equal(u2, u[:, idx]) and np.array_equal(x2, x[:, idx]) and np.array_equal(chi2_2, chi2[:, idx])
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name,make,mode,integrator", [
+    ("quadrotor_pipeline", lambda: problems.quadrotor(12), 2, "rk4"),          # warp-cooperative pipeline inside the loop
+    ("cartpole_shooting", lambda: problems.cart_pole_shooting(20), 2, "euler"),  # shooting grid, shift mode, trigonometric model
+    ("unicycle_timeopt", lambda: problems.unicycle_time_optimal(15), 1, "rk4"),  # non-uniform grid: keep mode (the reference never shifts it)
+], ids=lambda v: v if isinstance(v, str) else None)
+def test_device_closed_loop_equals_host_driven_loop_on_other_models(oracle, name, make, mode, integrator):
+    """b200sqp_closed_loop against the same loop driven from the host through b200sqp_mpc_step + b200sqp_plant_step: identical bits
+    for every model family / solver path, and plant steps consistent with the oracle's restatement of SimulatedPlant::control."""
+    ocp = make()
+    B, steps = 5, 4
+    x0, xref = problems.instance_data(ocp, B, seed=31)
+    lm = solver.BatchedLevenbergMarquardt(ocp, B)
+    lm.setIterations(4)
+    u, x, chi2, status = lm.closed_loop(x0, steps, xref=xref, mode=mode, integrator=integrator)
+    assert np.isfinite(u).all() and np.isfinite(x).all() and (status >= 0).all()
+    xs = x0.copy()
+    for s in range(steps):
+        us, chi2_s, _ = lm.mpc_step(xs, xref, mode=(0 if s == 0 else mode))
+        assert np.array_equal(us, u[s]) and np.array_equal(chi2_s, chi2[s])
+        dt_s = oracle.plant_interval(ocp.dt_ref, s)
+        xs = solver.plant_step(ocp.dynamics, list(ocp.dyn_params), xs, us, dt_s, integrator)
+        assert np.array_equal(xs, x[s + 1])
+        xo = oracle.plant_step(ocp, x[s], u[s], dt_s, integrator)
+        np.testing.assert_allclose(x[s + 1], xo, rtol=0, atol=_ulp_tol(xo))
+    lm.clear()
