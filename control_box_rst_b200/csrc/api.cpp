@@ -84,7 +84,7 @@ struct b200sqp_solver
     void* peer_local = nullptr;              // own buffer: [2*world*B] doubles, then [world] arrival counters, then 1 int timeout flag
     void* peer_mapped[MAX_PEERS] = {};       // cudaIpcOpenMemHandle results (null for own rank)
     unsigned long long peer_solves = 0;      // solves launched since attach
-    int* d_num_shift = nullptr;
+    int* d_num_shift = nullptr, *d_shift_plan = nullptr;
     // closed-loop log (b200sqp_closed_loop)
     double *d_loop_x = nullptr, *d_loop_u = nullptr, *d_loop_chi2 = nullptr;
     int32_t* d_loop_status = nullptr;
@@ -468,8 +468,10 @@ static int warmStartShiftFromDevice(b200sqp_handle h, const double* d_x0_new, in
     if (h->s.vt)
         return fail(B200SQP_ERR_UNSUPPORTED, "the reference never shifts a NonUniformFiniteDifferencesVariableGrid (isMovingHorizonWarmStartActive() "
                                              "is false there): use mode 1 (keep)");
-    launchWarmStartShift(d_x0_new, h->st.x0, h->st.z[0], h->st.z[1], h->st.cur, h->s.K, h->s.nx, h->s.nu, d_num_shift, h->B, h->stream);
-    h->launches += 1;
+    if (!h->d_shift_plan) CUDA_TRY(h->alloc(&h->d_shift_plan, (size_t)h->B));
+    launchWarmStartShift(d_x0_new, h->st.x0, h->st.z[0], h->st.z[1], h->st.cur, h->s.K, h->s.nx, h->s.nu, h->d_shift_plan, d_num_shift, h->B,
+                         h->stream);
+    h->launches += 2;
     CUDA_TRY(cudaGetLastError());
     // fixed goal components follow the reference (full_discretization_grid_base.cpp:102-106)
     const int nb = h->s.nb, xo = h->s.nu + h->s.vt;

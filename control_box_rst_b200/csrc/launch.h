@@ -69,9 +69,10 @@ bool launchDynamicsHessian(int dynamics, const DynParams& dyn, int method, int B
 // x, x_next [B][nx], u [B][nu]; u_log [B][nu] or null receives a copy of u; false = dynamics id not in the registry
 bool launchPlantStep(int dynamics, const DynParams& dyn, int integrator, double dt, int B, const double* x, const double* u, double* x_next,
                      double* u_log, cudaStream_t);
-// FullDiscretizationGridBase::warmStartShifting + findNearestState per instance, then x_seq.front() = x0_new (util_kernels.cu)
-void launchWarmStartShift(const double* x0_new /*[B][nx]*/, double* x0 /*tiled*/, double* z0, double* z1, const int* cur, int K, int nx, int nu,
-                          int* num_shift /*[B] or null*/, int B, cudaStream_t);
+// FullDiscretizationGridBase::warmStartShifting + findNearestState per instance, then x_seq.front() = x0_new (util_kernels.cu): a
+// per-instance search kernel and a per-(instance, block) move into the instance's other parameter buffer (roles swap); plan [B] scratch
+void launchWarmStartShift(const double* x0_new /*[B][nx]*/, double* x0 /*tiled*/, double* z0, double* z1, int* cur, int K, int nx, int nu,
+                          int* plan /*[B]*/, int* num_shift /*[B] or null*/, int B, cudaStream_t);
 // bounded spin on the arrival counters of the fused peer-memory gather (b200sqp_peer_wait)
 void launchPeerWait(const unsigned long long* arrivals, int world, unsigned long long expected, unsigned long long timeout_ns, int* timed_out,
                     cudaStream_t);

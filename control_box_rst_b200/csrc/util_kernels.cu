@@ -191,16 +191,18 @@ __device__ __forceinline__ double eigenNorm(const double* t, int n)
     return sqrt(res);
 }
 
-__global__ void warmStartShiftKernel(const double* __restrict__ x0_new /*[B][nx] host order*/, double* __restrict__ x0 /*tiled*/,
-                                     double* __restrict__ z0, double* __restrict__ z1, const int* __restrict__ cur, int K, int nx, int nu,
-                                     int* __restrict__ num_shift_out, int B)
+// Phase 1, one thread per instance: findNearestState against the current trajectory -> shift (0 = none), the buffer the trajectory
+// lives in (cur) packed next to it for phase 2, and x_seq.front() = measurement (update :101).
+__global__ void warmStartFindKernel(const double* __restrict__ x0_new /*[B][nx] host order*/, double* __restrict__ x0 /*tiled*/,
+                                    const double* __restrict__ z0, const double* __restrict__ z1, const int* __restrict__ cur, int K, int nx, int nu,
+                                    int* __restrict__ plan /*[B]: shift | src buffer << 8*/, int* __restrict__ num_shift_out, int B)
 {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= B) return;
     const int nb = nu + nx, slots = K * nb, N = K + 1;
-    double* z = cur[i] ? z1 : z0;
-    auto X = [&](int k, int j) -> double& { return k == 0 ? x0[tiled(i, j, nx)] : z[tiled(i, (k - 1) * nb + nu + j, slots)]; };
-    auto U = [&](int k, int j) -> double& { return z[tiled(i, k * nb + j, slots)]; };
+    const int src   = cur[i];
+    const double* z = src ? z1 : z0;
+    auto X = [&](int k, int j) -> double { return k == 0 ? x0[tiled(i, j, nx)] : z[tiled(i, (k - 1) * nb + nu + j, slots)]; };
     double xn[B200SQP_MAX_NX], sq[B200SQP_MAX_NX];
     for (int j = 0; j < nx; ++j) xn[j] = x0_new[(size_t)i * nx + j];
     auto dist = [&](int k) {
@@ -229,28 +231,56 @@ __global__ void warmStartShiftKernel(const double* __restrict__ x0_new /*[B][nx]
                 break;
         }
     }
-    if (shift > 0 && shift <= N - 2)
+    plan[i] = shift | (src << 8);
+    if (num_shift_out) num_shift_out[i] = shift;
+    // the shifted x_seq[0] is never read again (phase 2 takes its values from the old buffer): only the measurement lands here
+    for (int j = 0; j < nx; ++j) x0[tiled(i, j, nx)] = xn[j];
+}
+
+// Phase 2, one thread per (instance, block k): warmStartShifting written out of place into the instance's other parameter buffer
+// (the LM loop's trial buffer, free between solves), then the instance's buffer roles swap.  With s = shift, block k = [u_k, x_{k+1}]:
+//   x_{j}   <- x_old_{j+s}                         for j <  N-s          (x_old_{N-1} = xf)
+//   u_{k}   <- u_old_{k+s}                         for k <  N-1-s
+//   x_{idx} <- a + 2 (b - a) chained from a = x_old_{N-2}, b = x_old_{N-1}   for idx = N-s .. N-1 (the reference's linear extrapolation;
+//              every thread replays the chain up to its own idx: same operations in the same order, no cross-thread dependence)
+//   u_{k}   <- u_old_{N-2}                         for k >= N-1-s        (u[idx-1] = u[idx-2] repeated)
+// Instances with s = 0 or s > N-2 are left untouched (:233-239).
+__global__ void warmStartMoveKernel(double* __restrict__ z0, double* __restrict__ z1, int* __restrict__ cur, const int* __restrict__ plan, int K,
+                                    int nx, int nu, int B)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    const int k = blockIdx.y;
+    if (i >= B) return;
+    const int nb = nu + nx, slots = K * nb, N = K + 1;
+    const int s = plan[i] & 0xff, src = plan[i] >> 8;
+    if (s <= 0 || s > N - 2) return;
+    const double* zo = src ? z1 : z0;
+    double* zn       = src ? z0 : z1;
+    auto Xo = [&](int q, int j) -> double { return zo[tiled(i, (q - 1) * nb + nu + j, slots)]; };  // q >= 1 only
+    // controls of block k
+    const int ku = (k < N - 1 - s) ? k + s : N - 2;
+    for (int j = 0; j < nu; ++j) zn[tiled(i, k * nb + j, slots)] = zo[tiled(i, ku * nb + j, slots)];
+    // state x_{k+1}
+    const int q = k + 1;
+    if (q < N - s)
     {
-        for (int k = 0; k < N - shift; ++k)
+        for (int j = 0; j < nx; ++j) zn[tiled(i, k * nb + nu + j, slots)] = Xo(q + s, j);
+    }
+    else
+    {
+        for (int j = 0; j < nx; ++j)
         {
-            const int idx = k + shift;
-            for (int j = 0; j < nx; ++j) X(k, j) = X(idx, j);
-            if (idx != N - 1)
-                for (int j = 0; j < nu; ++j) U(k, j) = U(idx, j);
-        }
-        int idx = N - shift;
-        for (int s = 0; s < shift; ++s, ++idx)
-        {
-            for (int j = 0; j < nx; ++j)
+            double a = Xo(N - 2, j), b = Xo(N - 1, j), c = 0.0;
+            for (int idx = N - s; idx <= q; ++idx)
             {
-                const double a = X(idx - 2, j), b = X(idx - 1, j);
-                X(idx, j)      = a + 2.0 * (b - a);
+                c = a + 2.0 * (b - a);
+                a = b;
+                b = c;
             }
-            for (int j = 0; j < nu; ++j) U(idx - 1, j) = U(idx - 2, j);
+            zn[tiled(i, k * nb + nu + j, slots)] = c;
         }
     }
-    for (int j = 0; j < nx; ++j) x0[tiled(i, j, nx)] = xn[j];  // the measured start always overwrites x_seq.front() (:101)
-    if (num_shift_out) num_shift_out[i] = shift;
+    if (k == 0) cur[i] = 1 - src;  // nobody reads cur in this kernel (the plan carries the source buffer)
 }
 
 inline int blocksFor(int B) { return (B + 127) / 128; }
@@ -281,10 +311,11 @@ __global__ void peerWaitKernel(const volatile unsigned long long* arrivals, int 
 
 }  // namespace
 
-void launchWarmStartShift(const double* x0_new, double* x0, double* z0, double* z1, const int* cur, int K, int nx, int nu, int* num_shift, int B,
-                          cudaStream_t st)
+void launchWarmStartShift(const double* x0_new, double* x0, double* z0, double* z1, int* cur, int K, int nx, int nu, int* plan, int* num_shift,
+                          int B, cudaStream_t st)
 {
-    warmStartShiftKernel<<<blocksFor(B), 128, 0, st>>>(x0_new, x0, z0, z1, cur, K, nx, nu, num_shift, B);
+    warmStartFindKernel<<<blocksFor(B), 128, 0, st>>>(x0_new, x0, z0, z1, cur, K, nx, nu, plan, num_shift, B);
+    warmStartMoveKernel<<<dim3(blocksFor(B), K), 128, 0, st>>>(z0, z1, cur, plan, K, nx, nu, B);
 }
 
 void launchPeerWait(const unsigned long long* arrivals, int world, unsigned long long expected, unsigned long long timeout_ns, int* timed_out,
