@@ -733,7 +733,7 @@ int b200sqp_plant_step(int32_t dynamics, const double* dyn_params, int32_t integ
     if (e == cudaSuccess) e = cudaMemcpy(du, u, bu, cudaMemcpyHostToDevice);
     if (e == cudaSuccess)
     {
-        launchPlantStep(dynamics, dyn, integrator, dt, batch, dx, du, dn, nullptr, nullptr);
+        launchPlantStep(dynamics, dyn, integrator, dt, batch, dx, du, dn, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr);
         e = cudaGetLastError();
     }
     if (e == cudaSuccess) e = cudaMemcpy(x_next, dn, bx, cudaMemcpyDeviceToHost);
@@ -797,8 +797,11 @@ int b200sqp_closed_loop(b200sqp_handle h, const b200sqp_lm_options* opts, int32_
             rc = warmStartShiftFromDevice(h, d_x, nullptr);  // needs the previous start state: before it is replaced
             if (rc) return rc;
         }
-        rc = startStatesFromDevice(h, d_x, (s == 0 && xref) ? h->d_xref_host_order : nullptr);
-        if (rc) return rc;
+        if (!(s > 0 && mode == 2))  // the shift already replaced the start state by the measurement (and refreshed fixed goal components)
+        {
+            rc = startStatesFromDevice(h, d_x, (s == 0 && xref) ? h->d_xref_host_order : nullptr);
+            if (rc) return rc;
+        }
         if (s == 0 || mode == 0)
         {
             rc = b200sqp_initialize_trajectories(h);
@@ -809,12 +812,11 @@ int b200sqp_closed_loop(b200sqp_handle h, const b200sqp_lm_options* opts, int32_
         launchFirstControls(h->st.z[0], h->st.z[1], h->st.cur, nu, h->s.K * h->s.nb, h->d_u0, B, h->S, h->stream);
         // ---- plant: SimulatedPlant::control, one solveIVP over plant_dt with the first control held
         if (!launchPlantStep(h->s.ocp.dynamics, h->P.dyn, integrator, step_dt, B, d_x, h->d_u0, h->d_loop_x + (size_t)(s + 1) * sx,
-                             h->d_loop_u + (size_t)s * su, h->stream))
+                             h->d_loop_u + (size_t)s * su, h->st.chi2, h->d_loop_chi2 + (size_t)s * B, h->st.status,
+                             h->d_loop_status + (size_t)s * B, h->stream))
             return fail(B200SQP_ERR_UNSUPPORTED, "dynamics id not in the plant registry");
         h->launches += 2;
         CUDA_TRY(cudaGetLastError());
-        CUDA_TRY(cudaMemcpyAsync(h->d_loop_chi2 + (size_t)s * B, h->st.chi2, sizeof(double) * B, cudaMemcpyDeviceToDevice, h->stream));
-        CUDA_TRY(cudaMemcpyAsync(h->d_loop_status + (size_t)s * B, h->st.status, sizeof(int32_t) * B, cudaMemcpyDeviceToDevice, h->stream));
     }
     if (u_applied) CUDA_TRY(cudaMemcpyAsync(u_applied, h->d_loop_u, sizeof(double) * steps * su, cudaMemcpyDeviceToHost, h->stream));
     if (x_closed) CUDA_TRY(cudaMemcpyAsync(x_closed, h->d_loop_x, sizeof(double) * (steps + 1) * sx, cudaMemcpyDeviceToHost, h->stream));

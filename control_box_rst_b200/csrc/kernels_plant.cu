@@ -21,7 +21,8 @@ namespace {
 
 template <class M>
 __global__ void plantStepKernel(const DynParams dyn, int integrator, double dt, int B, const double* __restrict__ xs, const double* __restrict__ us,
-                                double* __restrict__ xn, double* __restrict__ u_log)
+                                double* __restrict__ xn, double* __restrict__ u_log, const double* __restrict__ chi2_src, double* __restrict__ chi2_log,
+                                const int* __restrict__ status_src, int* __restrict__ status_log)
 {
     constexpr int NX = M::NX, NU = M::NU;
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -47,28 +48,32 @@ __global__ void plantStepKernel(const DynParams dyn, int integrator, double dt, 
 #pragma unroll
         for (int j = 0; j < NU; ++j) u_log[(size_t)i * NU + j] = u[j];
     }
+    // closed-loop log of the controller's chi2 / status of this step (saves two device-to-device copies per step)
+    if (chi2_log) chi2_log[i] = chi2_src[i];
+    if (status_log) status_log[i] = status_src[i];
 }
 
 template <class M>
-void launchOne(const DynParams& dyn, int integrator, double dt, int B, const double* x, const double* u, double* xn, double* u_log, cudaStream_t st)
+void launchOne(const DynParams& dyn, int integrator, double dt, int B, const double* x, const double* u, double* xn, double* u_log,
+               const double* chi2_src, double* chi2_log, const int* status_src, int* status_log, cudaStream_t st)
 {
-    plantStepKernel<M><<<(B + 127) / 128, 128, 0, st>>>(dyn, integrator, dt, B, x, u, xn, u_log);
+    plantStepKernel<M><<<(B + 127) / 128, 128, 0, st>>>(dyn, integrator, dt, B, x, u, xn, u_log, chi2_src, chi2_log, status_src, status_log);
 }
 
 }  // namespace
 
 bool launchPlantStep(int dynamics, const DynParams& dyn, int integrator, double dt, int B, const double* x, const double* u, double* x_next,
-                     double* u_log, cudaStream_t st)
+                     double* u_log, const double* chi2_src, double* chi2_log, const int* status_src, int* status_log, cudaStream_t st)
 {
     switch (dynamics)
     {
-        case B200SQP_DYN_VAN_DER_POL: launchOne<VanDerPol>(dyn, integrator, dt, B, x, u, x_next, u_log, st); return true;
-        case B200SQP_DYN_DUFFING: launchOne<Duffing>(dyn, integrator, dt, B, x, u, x_next, u_log, st); return true;
-        case B200SQP_DYN_SIMPLE_PENDULUM: launchOne<SimplePendulum>(dyn, integrator, dt, B, x, u, x_next, u_log, st); return true;
-        case B200SQP_DYN_CART_POLE: launchOne<CartPole>(dyn, integrator, dt, B, x, u, x_next, u_log, st); return true;
-        case B200SQP_DYN_DOUBLE_INTEGRATOR: launchOne<DoubleIntegrator>(dyn, integrator, dt, B, x, u, x_next, u_log, st); return true;
-        case B200SQP_DYN_UNICYCLE: launchOne<Unicycle>(dyn, integrator, dt, B, x, u, x_next, u_log, st); return true;
-        case B200SQP_DYN_QUADROTOR: launchOne<Quadrotor>(dyn, integrator, dt, B, x, u, x_next, u_log, st); return true;
+        case B200SQP_DYN_VAN_DER_POL: launchOne<VanDerPol>(dyn, integrator, dt, B, x, u, x_next, u_log, chi2_src, chi2_log, status_src, status_log, st); return true;
+        case B200SQP_DYN_DUFFING: launchOne<Duffing>(dyn, integrator, dt, B, x, u, x_next, u_log, chi2_src, chi2_log, status_src, status_log, st); return true;
+        case B200SQP_DYN_SIMPLE_PENDULUM: launchOne<SimplePendulum>(dyn, integrator, dt, B, x, u, x_next, u_log, chi2_src, chi2_log, status_src, status_log, st); return true;
+        case B200SQP_DYN_CART_POLE: launchOne<CartPole>(dyn, integrator, dt, B, x, u, x_next, u_log, chi2_src, chi2_log, status_src, status_log, st); return true;
+        case B200SQP_DYN_DOUBLE_INTEGRATOR: launchOne<DoubleIntegrator>(dyn, integrator, dt, B, x, u, x_next, u_log, chi2_src, chi2_log, status_src, status_log, st); return true;
+        case B200SQP_DYN_UNICYCLE: launchOne<Unicycle>(dyn, integrator, dt, B, x, u, x_next, u_log, chi2_src, chi2_log, status_src, status_log, st); return true;
+        case B200SQP_DYN_QUADROTOR: launchOne<Quadrotor>(dyn, integrator, dt, B, x, u, x_next, u_log, chi2_src, chi2_log, status_src, status_log, st); return true;
     }
     return false;
 }

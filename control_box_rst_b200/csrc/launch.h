@@ -66,9 +66,10 @@ bool launchLinearizeDynamics(int dynamics, const DynParams& dyn, int method, int
 bool launchDynamicsHessian(int dynamics, const DynParams& dyn, int method, int B, const double* x, const double* u, const double* mult, double* H,
                            cudaStream_t);
 // SimulatedPlant::control for B plants: x_next = solveIVP(x, u, dt), integrator 0 = explicit Euler, 1 = RK4 (kernels_plant.cu);
-// x, x_next [B][nx], u [B][nu]; u_log [B][nu] or null receives a copy of u; false = dynamics id not in the registry
+// x, x_next [B][nx], u [B][nu]; u_log [B][nu] or null receives a copy of u, chi2_log / status_log [B] or null a copy of chi2_src /
+// status_src (the closed-loop log); false = dynamics id not in the registry
 bool launchPlantStep(int dynamics, const DynParams& dyn, int integrator, double dt, int B, const double* x, const double* u, double* x_next,
-                     double* u_log, cudaStream_t);
+                     double* u_log, const double* chi2_src, double* chi2_log, const int* status_src, int* status_log, cudaStream_t);
 // FullDiscretizationGridBase::warmStartShifting + findNearestState per instance, then x_seq.front() = x0_new (util_kernels.cu): a
 // per-instance search kernel and a per-(instance, block) move into the instance's other parameter buffer (roles swap); plan [B] scratch
 void launchWarmStartShift(const double* x0_new /*[B][nx]*/, double* x0 /*tiled*/, double* z0, double* z1, int* cur, int K, int nx, int nu,
