@@ -155,4 +155,7 @@ def test_device_closed_loop_equals_host_driven_loop_on_other_models(oracle, name
         assert np.array_equal(xs, x[s + 1])
         xo = oracle.plant_step(ocp, x[s], u[s], dt_s, integrator)
         np.testing.assert_allclose(x[s + 1], xo, rtol=0, atol=_ulp_tol(xo))
+    # a longer run on the same handle (the log buffers grow) starts cold again and reproduces the shorter one as its prefix
+    u2, x2, chi2_2, _ = lm.closed_loop(x0, steps + 3, xref=xref, mode=mode, integrator=integrator)
+    assert np.array_equal(u2[:steps], u) and np.array_equal(x2[:steps + 1], x) and np.array_equal(chi2_2[:steps], chi2)
     lm.clear()
