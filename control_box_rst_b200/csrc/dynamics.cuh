@@ -68,7 +68,8 @@ struct CartPole
     __device__ __forceinline__ static void f(const DynParams&, const double* x, const double* u, double* out)
     {
         const double mc = 1.0, mp = 0.3, l = 0.5, g = 9.81;
-        const double s = sin(x[1]), co = cos(x[1]);
+        double s, co;  // one argument reduction for both; same values as separate sin()/cos()
+        sincos(x[1], &s, &co);
         double sin_phi_phidot_sq = s * x[3] * x[3];
         double denum             = mc + mp * (1 - co * co);  // std::pow(cos, 2) == cos*cos in IEEE arithmetic
         out[0]                   = x[2];
@@ -95,8 +96,10 @@ struct Unicycle
     static constexpr int NX = 3, NU = 2, ID = B200SQP_DYN_UNICYCLE;
     __device__ __forceinline__ static void f(const DynParams&, const double* x, const double* u, double* out)
     {
-        out[0] = u[0] * cos(x[2]);
-        out[1] = u[0] * sin(x[2]);
+        double s, co;  // one argument reduction for both; same values as separate sin()/cos()
+        sincos(x[2], &s, &co);
+        out[0] = u[0] * co;
+        out[1] = u[0] * s;
         out[2] = u[1];
     }
 };
