@@ -218,6 +218,7 @@ __device__ __forceinline__ void defect(const DynParams& c, const double* x1, con
     else  // RK4: explicit_integrators.h:280-295, then "- x2"
     {
         double k1[NX], k2[NX], k3[NX], k4[NX], xt[NX];
+        const StepSize six(6.0);  // `/ 6.0` correctly rounded without a divide per component (constant-folded reciprocal)
         M::f(c, x1, u1, k1);
 #pragma unroll
         for (int i = 0; i < NX; ++i) k1[i] *= dt;
@@ -237,7 +238,7 @@ __device__ __forceinline__ void defect(const DynParams& c, const double* x1, con
 #pragma unroll
         for (int i = 0; i < NX; ++i) k4[i] *= dt;
 #pragma unroll
-        for (int i = 0; i < NX; ++i) e[i] = (x1[i] + (k1[i] + 2.0 * k2[i] + 2.0 * k3[i] + k4[i]) / 6.0) - x2[i];
+        for (int i = 0; i < NX; ++i) e[i] = (x1[i] + six.div(k1[i] + 2.0 * k2[i] + 2.0 * k3[i] + k4[i])) - x2[i];
     }
 }
 
