@@ -30,7 +30,37 @@ for name, ocp, T, w in CASES:
     if ocp.grid == 0:
         lm.warm_start_shift(x0 + 0.01)
     lm.get_first_controls()
+    if ocp.grid != 1:  # the whole closed loop on the device (shift mode: search + out-of-place move kernels, plant kernel with the log)
+        lm.closed_loop(x0, 3, xref=xref, mode=2, integrator="rk4")
+    lm.closed_loop(x0, 2, xref=xref, mode=1, integrator="euler")
     print(name, "chi2[0] =", chi2[0], "finite:", bool(np.isfinite(chi2).all()), flush=True)
     lm.clear()
 A, B_ = solver.linearize_dynamics(0, [1.0], np.ones((70, 2)), np.ones((70, 1)), "central")
 print("linearize ok", A.shape)
+H = solver.dynamics_hessian(0, [1.0], np.ones((70, 2)), np.ones((70, 1)), np.ones((70, 2)), "central")
+xn = solver.plant_step(6, [1.0, 9.81, 0.01, 0.01, 0.02], np.zeros((70, 12)), np.ones((70, 4)), 0.05, "rk4")
+print("hessian / plant ok", H.shape, xn.shape)
+# quadrotor: warp-cooperative pipeline (TMA-prefetched factor kernel, DMMA tiles), small horizon
+ocp = problems.quadrotor(8)
+x0, xref = problems.instance_data(ocp, 37, seed=3)
+lm = solver.BatchedLevenbergMarquardt(ocp, 37)
+lm.setIterations(2)
+lm.set_problem_data(x0, xref)
+lm.initialize_trajectories()
+status, chi2 = lm.solve(new_run=True)
+print("quadrotor8 pipeline chi2[0] =", chi2[0], flush=True)
+lm.clear()
+# pinned host buffers: ingest / export kernels reading and writing host memory in place
+import torch  # noqa: E402
+
+ocp = problems.van_der_pol(20)
+B = 70
+x0, xref = problems.instance_data(ocp, B, seed=3)
+lm = solver.BatchedLevenbergMarquardt(ocp, B)
+lm.setIterations(3)
+hx, hr = torch.from_numpy(x0.copy()).pin_memory(), torch.from_numpy(xref.copy()).pin_memory()
+hu, hc, hs = torch.zeros((B, 1), dtype=torch.float64).pin_memory(), torch.zeros(B, dtype=torch.float64).pin_memory(), torch.zeros(B, dtype=torch.int32).pin_memory()
+lm.mpc_step_raw(0, hx.data_ptr(), hr.data_ptr(), hu.data_ptr(), hc.data_ptr(), hs.data_ptr())
+lm.mpc_step_raw(2, hx.data_ptr(), 0, hu.data_ptr(), hc.data_ptr(), hs.data_ptr())
+print("pinned mpc_step ok", float(hc[0]))
+lm.clear()
