@@ -108,12 +108,18 @@ struct Unicycle
 struct Quadrotor
 {
     static constexpr int NX = 12, NU = 4, ID = B200SQP_DYN_QUADROTOR;
-    __device__ __forceinline__ static void f(const DynParams& c, const double* x, const double* u, double* out)
+    // The attitude angles x[3..5] enter only through their sines and cosines: callers that evaluate f at many points which share
+    // most angles (the finite-difference columns of the pipeline, lm_pipeline.cuh) keep the six values and refresh one pair.
+    static constexpr int NANG = 3, ANG0 = 3;
+    __device__ __forceinline__ static void trig(const double* x, double* sc /*[2*NANG]: sin, cos per angle*/)
     {
-        double sphi, cphi, sth, cth, spsi, cpsi;  // one argument reduction per angle; same values as separate sin()/cos()
-        sincos(x[3], &sphi, &cphi);
-        sincos(x[4], &sth, &cth);
-        sincos(x[5], &spsi, &cpsi);
+        sincos(x[3], &sc[0], &sc[1]);  // one argument reduction per angle; same values as separate sin()/cos()
+        sincos(x[4], &sc[2], &sc[3]);
+        sincos(x[5], &sc[4], &sc[5]);
+    }
+    __device__ __forceinline__ static void fTrig(const DynParams& c, const double* x, const double* u, const double* sc, double* out)
+    {
+        const double sphi = sc[0], cphi = sc[1], sth = sc[2], cth = sc[3], spsi = sc[4], cpsi = sc[5];
         const double p = x[9], q = x[10], r = x[11];
         const double tm = divByParam(c, 0, u[0]);
         out[0]          = x[6];
@@ -129,6 +135,12 @@ struct Quadrotor
         out[9]          = divByParam(c, 2, u[1] + (c.p[3] - c.p[4]) * q * r);
         out[10]         = divByParam(c, 3, u[2] + (c.p[4] - c.p[2]) * p * r);
         out[11]         = divByParam(c, 4, u[3] + (c.p[2] - c.p[3]) * p * q);
+    }
+    __device__ __forceinline__ static void f(const DynParams& c, const double* x, const double* u, double* out)
+    {
+        double sc[2 * NANG];
+        trig(x, sc);
+        fTrig(c, x, u, sc, out);
     }
 };
 

@@ -92,6 +92,18 @@ __device__ __forceinline__ void dmma884(double& d0, double& d1, double a, double
     asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};" : "+d"(d0), "+d"(d1) : "d"(a), "d"(b));
 }
 
+// models that expose trig()/fTrig() (dynamics.cuh): their angles' sines and cosines can be carried between evaluations
+template <class M, class = void>
+struct PipeTrig
+{
+    static constexpr bool value = false;
+};
+template <class M>
+struct PipeTrig<M, decltype((void)M::NANG)>
+{
+    static constexpr bool value = true;
+};
+
 __device__ __forceinline__ size_t tiledSlot(int i, int slot, int nslots) { return ((size_t)(i >> 5) * nslots + slot) * 32 + (i & 31); }
 
 // ---------------------------------------------------------------------------------------------------------------------------
@@ -176,11 +188,57 @@ __global__ void __launch_bounds__(128, 4) pipeLinearizeKernel(const __grid_const
     }
     StepSize h(P.dt_ref);
     double e2[NX], e1[NX];
-    defect<M, DEFECT>(P.dyn, vec, vec + NX, vec + NX + NU, h, e2);  // inlined: the operands stay in registers
+    if constexpr (DEFECT == DEFECT_CRANK_NICOLSON && PipeTrig<M>::value)
+    {
+        // The model's angles enter only through sin/cos and a column perturbs at most one of them: keep the sines and cosines of
+        // both states from the +delta evaluation and refresh the one pair the perturbation touched for the -delta evaluation (one
+        // uniform sincos per lane instead of six; same arguments -> same values as evaluating f from scratch).
+        constexpr int NA = M::NANG, A0 = M::ANG0;
+        double sc1[2 * NA], sc2[2 * NA];
+        M::trig(vec, sc1);
+        M::trig(vec + NX + NU, sc2);
+        auto cn = [&](double* e) {
+            double f1[NX], f2[NX];
+            M::fTrig(P.dyn, vec, vec + NX, sc1, f1);
+            M::fTrig(P.dyn, vec + NX + NU, vec + NX, sc2, f2);
 #pragma unroll
-    for (int q = 0; q < NV; ++q)
-        if (q == p) vec[q] += neg2delta;
-    defect<M, DEFECT>(P.dyn, vec, vec + NX, vec + NX + NU, h, e1);
+            for (int j = 0; j < NX; ++j) e[j] = h.div(vec[NX + NU + j] - vec[j]) - 0.5 * (f1[j] + f2[j]);  // dynamics.cuh defect<>, Crank-Nicolson
+        };
+        cn(e2);
+        double ang = 0.0;
+#pragma unroll
+        for (int q = 0; q < NV; ++q)
+            if (q == p)
+            {
+                vec[q] += neg2delta;
+                ang = vec[q];
+            }
+        double sa, ca;
+        sincos(ang, &sa, &ca);
+#pragma unroll
+        for (int a = 0; a < NA; ++a)
+        {
+            if (p == A0 + a)
+            {
+                sc1[2 * a]     = sa;
+                sc1[2 * a + 1] = ca;
+            }
+            if (p == NX + NU + A0 + a)
+            {
+                sc2[2 * a]     = sa;
+                sc2[2 * a + 1] = ca;
+            }
+        }
+        cn(e1);
+    }
+    else
+    {
+        defect<M, DEFECT>(P.dyn, vec, vec + NX, vec + NX + NU, h, e2);  // inlined: the operands stay in registers
+#pragma unroll
+        for (int q = 0; q < NV; ++q)
+            if (q == p) vec[q] += neg2delta;
+        defect<M, DEFECT>(P.dyn, vec, vec + NX, vec + NX + NU, h, e1);
+    }
     if (p < NV)
     {
 #pragma unroll
