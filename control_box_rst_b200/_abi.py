@@ -19,6 +19,10 @@ DYN_CART_POLE = 3
 DYN_DOUBLE_INTEGRATOR = 4
 DYN_UNICYCLE = 5
 DYN_QUADROTOR = 6
+DYN_FREE_SPACE_ROCKET = 7
+DYN_MASSLESS_PENDULUM = 8
+DYN_TOY_EXAMPLE = 9
+DYN_ARTSTEINS_CIRCLE = 10
 DYN_DIMS = {  # id -> (nx, nu)
     DYN_VAN_DER_POL: (2, 1),
     DYN_DUFFING: (2, 1),
@@ -27,6 +31,10 @@ DYN_DIMS = {  # id -> (nx, nu)
     DYN_DOUBLE_INTEGRATOR: (2, 1),
     DYN_UNICYCLE: (3, 2),
     DYN_QUADROTOR: (12, 4),
+    DYN_FREE_SPACE_ROCKET: (3, 1),
+    DYN_MASSLESS_PENDULUM: (2, 1),
+    DYN_TOY_EXAMPLE: (2, 1),
+    DYN_ARTSTEINS_CIRCLE: (2, 1),
 }
 
 # b200sqp_grid

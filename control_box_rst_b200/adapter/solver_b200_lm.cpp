@@ -159,9 +159,13 @@ bool SolverB200Lm::describe(OptimizationProblemInterface& problem, b200sqp_ocp& 
         d.dynamics      = B200SQP_DYN_DOUBLE_INTEGRATOR;
         d.dyn_params[0] = s->getTimeConstant();
     }
+    else if (dynamic_cast<FreeSpaceRocket*>(_dynamics.get()))
+        d.dynamics = B200SQP_DYN_FREE_SPACE_ROCKET;  // no parameters
+    else if (dynamic_cast<ArtsteinsCircle*>(_dynamics.get()))
+        d.dynamics = B200SQP_DYN_ARTSTEINS_CIRCLE;  // no parameters
     else
     {
-        _error = "system dynamics type is not in the device registry (Duffing/SimplePendulum expose no parameter getters)";
+        _error = "system dynamics type is not in the device registry (Duffing/SimplePendulum/MasslessPendulum/ToyExample expose no parameter getters)";
         return false;
     }
 

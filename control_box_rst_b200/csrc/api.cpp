@@ -44,7 +44,7 @@ const KernelSet* findKernels(int dynamics, int defect, int vt)
     const KernelSet* (*tables[])(int*) = {kernelTableVdpCn};
 #else
     const KernelSet* (*tables[])(int*) = {kernelTableVdpCn,       kernelTableVdpFd,    kernelTableVdpMs,   kernelTableOscillators,
-                                          kernelTableCartPole,    kernelTableUnicycle, kernelTableQuadrotor};
+                                          kernelTableCartPole,    kernelTableUnicycle, kernelTableQuadrotor, kernelTableBenchmarkSystems};
 #endif
     for (auto t : tables)
     {

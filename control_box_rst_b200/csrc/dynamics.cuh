@@ -90,6 +90,51 @@ struct DoubleIntegrator
     }
 };
 
+// FreeSpaceRocket::dynamics -- nonlinear_benchmark_systems.h:174-183; x = (s, v, m), no parameters
+struct FreeSpaceRocket
+{
+    static constexpr int NX = 3, NU = 1, ID = B200SQP_DYN_FREE_SPACE_ROCKET;
+    __device__ __forceinline__ static void f(const DynParams&, const double* x, const double* u, double* out)
+    {
+        out[0] = x[1];
+        out[1] = (u[0] - 0.02 * x[1] * x[1]) / x[2];
+        out[2] = -0.01 * u[0] * u[0];
+    }
+};
+
+// MasslessPendulum::dynamics -- nonlinear_benchmark_systems.h:281-290; p = omega0
+struct MasslessPendulum
+{
+    static constexpr int NX = 2, NU = 1, ID = B200SQP_DYN_MASSLESS_PENDULUM;
+    __device__ __forceinline__ static void f(const DynParams& c, const double* x, const double* u, double* out)
+    {
+        out[0] = x[1];
+        out[1] = u[0] - c.p[0] * sin(x[0]);
+    }
+};
+
+// ToyExample::dynamics -- nonlinear_benchmark_systems.h:426-436; p = mu
+struct ToyExample
+{
+    static constexpr int NX = 2, NU = 1, ID = B200SQP_DYN_TOY_EXAMPLE;
+    __device__ __forceinline__ static void f(const DynParams& c, const double* x, const double* u, double* out)
+    {
+        out[0] = x[1] + u[0] * (c.p[0] + (1.0 - c.p[0]) * x[0]);
+        out[1] = x[0] + u[0] * (c.p[0] - 4.0 * (1.0 - c.p[0]) * x[1]);
+    }
+};
+
+// ArtsteinsCircle::dynamics -- nonlinear_benchmark_systems.h:483-492; no parameters
+struct ArtsteinsCircle
+{
+    static constexpr int NX = 2, NU = 1, ID = B200SQP_DYN_ARTSTEINS_CIRCLE;
+    __device__ __forceinline__ static void f(const DynParams&, const double* x, const double* u, double* out)
+    {
+        out[0] = (x[0] * x[0] - x[1] * x[1]) * u[0];
+        out[1] = 2 * x[0] * x[1] * u[0];
+    }
+};
+
 // New model (absent from the reference; same equations as oracle/ref_models.h Unicycle)
 struct Unicycle
 {

@@ -221,6 +221,10 @@ bool launchLinearizeDynamics(int dynamics, const DynParams& dyn, int method, int
         case B200SQP_DYN_DOUBLE_INTEGRATOR: launchOne<DoubleIntegrator>(dyn, method, B, x, u, A, Bm, st); return true;
         case B200SQP_DYN_UNICYCLE: launchOne<Unicycle>(dyn, method, B, x, u, A, Bm, st); return true;
         case B200SQP_DYN_QUADROTOR: launchOne<Quadrotor>(dyn, method, B, x, u, A, Bm, st); return true;
+        case B200SQP_DYN_FREE_SPACE_ROCKET: launchOne<FreeSpaceRocket>(dyn, method, B, x, u, A, Bm, st); return true;
+        case B200SQP_DYN_MASSLESS_PENDULUM: launchOne<MasslessPendulum>(dyn, method, B, x, u, A, Bm, st); return true;
+        case B200SQP_DYN_TOY_EXAMPLE: launchOne<ToyExample>(dyn, method, B, x, u, A, Bm, st); return true;
+        case B200SQP_DYN_ARTSTEINS_CIRCLE: launchOne<ArtsteinsCircle>(dyn, method, B, x, u, A, Bm, st); return true;
     }
     return false;
 }
@@ -237,6 +241,10 @@ bool launchDynamicsHessian(int dynamics, const DynParams& dyn, int method, int B
         case B200SQP_DYN_DOUBLE_INTEGRATOR: launchHess<DoubleIntegrator>(dyn, method, B, x, u, mult, H, st); return true;
         case B200SQP_DYN_UNICYCLE: launchHess<Unicycle>(dyn, method, B, x, u, mult, H, st); return true;
         case B200SQP_DYN_QUADROTOR: launchHess<Quadrotor>(dyn, method, B, x, u, mult, H, st); return true;
+        case B200SQP_DYN_FREE_SPACE_ROCKET: launchHess<FreeSpaceRocket>(dyn, method, B, x, u, mult, H, st); return true;
+        case B200SQP_DYN_MASSLESS_PENDULUM: launchHess<MasslessPendulum>(dyn, method, B, x, u, mult, H, st); return true;
+        case B200SQP_DYN_TOY_EXAMPLE: launchHess<ToyExample>(dyn, method, B, x, u, mult, H, st); return true;
+        case B200SQP_DYN_ARTSTEINS_CIRCLE: launchHess<ArtsteinsCircle>(dyn, method, B, x, u, mult, H, st); return true;
     }
     return false;
 }

@@ -28,7 +28,13 @@ bool dynamicsDims(int id, Dim& d)
         case B200SQP_DYN_DUFFING:
         case B200SQP_DYN_SIMPLE_PENDULUM:
         case B200SQP_DYN_DOUBLE_INTEGRATOR:
+        case B200SQP_DYN_MASSLESS_PENDULUM:
+        case B200SQP_DYN_TOY_EXAMPLE:
+        case B200SQP_DYN_ARTSTEINS_CIRCLE:
             d = {2, 1};
+            return true;
+        case B200SQP_DYN_FREE_SPACE_ROCKET:
+            d = {3, 1};
             return true;
         case B200SQP_DYN_CART_POLE:
             d = {4, 1};

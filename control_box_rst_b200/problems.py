@@ -71,6 +71,21 @@ def cart_pole_shooting(n_grid=100, dt=0.02, **kw):
                     q=(1.0,) * 4, r=(0.01,), qf=(10.0,) * 4, u_lb=(-20.0,), u_ub=(20.0,), dyn_params=(1.0, 0.3, 0.5, 9.81), **kw)
 
 
+def free_space_rocket(n_grid=20, dt=0.1, **kw):
+    """FreeSpaceRocket (nonlinear_benchmark_systems.h:154-184; states s, v, m) on the fixed-dt FiniteDifferencesGrid."""
+    return make_ocp(grid=abi.GRID_FD_UNIFORM, dynamics=abi.DYN_FREE_SPACE_ROCKET, n_grid=n_grid, dt=dt, q=(1.0, 1.0, 1.0), r=(0.1,),
+                    qf=(1.0, 1.0, 1.0), u_lb=(-1.1,), u_ub=(1.1,), **kw)
+
+
+def free_space_rocket_time_optimal(n_grid=20, dt=0.1):
+    """The reference's classic time-optimal rocket: MinimumTime(lsq) on the NonUniformFiniteDifferencesVariableGrid, position and
+    velocity of the final state fixed, final mass free, |u| <= 1.1, v in [-0.5, 1.7], m >= 0."""
+    inf = abi.CORBO_INF_DBL
+    return make_ocp(grid=abi.GRID_FD_NONUNIFORM_VARDT, dynamics=abi.DYN_FREE_SPACE_ROCKET, n_grid=n_grid, dt=dt,
+                    stage_cost=abi.COST_MINIMUM_TIME_LSQ, u_lb=(-1.1,), u_ub=(1.1,), x_lb=(-inf, -0.5, 0.0), x_ub=(inf, 1.7, inf),
+                    xf_fixed=(1, 1, 0), dt_lb=0.0, dt_ub=1.0)
+
+
 def quadrotor(n_grid=60, dt=0.05, **kw):
     """configs[4]: 12-state quadrotor, FiniteDifferencesGrid, quadratic lsq cost, thrust/torque bounds."""
     m, g = 1.0, 9.81
@@ -112,8 +127,12 @@ def instance_data(ocp, batch, seed=1234, offset=0):
         x0 = np.zeros((total, nx))
         x0[:, 0:3] = rng.uniform(-1.0, 1.0, (total, 3))
         x0[:, 3:6] = rng.uniform(-0.2, 0.2, (total, 3))
+    elif ocp.dynamics == abi.DYN_FREE_SPACE_ROCKET:  # (s, v, m): the mass stays away from the pole of (u - 0.02 v^2) / m
+        x0 = np.stack([rng.uniform(-1.0, 1.0, total), rng.uniform(-0.5, 0.5, total), rng.uniform(0.9, 1.3, total)], axis=1)
     else:
         x0 = rng.uniform(-2.0, 2.0, (total, nx))
     x0 = np.ascontiguousarray(x0[offset:], dtype=np.float64)
     xref = np.zeros_like(x0)
+    if ocp.dynamics == abi.DYN_FREE_SPACE_ROCKET:
+        xref[:, 2] = 0.8  # reference (and, on a grid with a fixed goal, final) mass
     return x0, xref

@@ -36,7 +36,8 @@ typedef enum {
 typedef enum { B200SQP_STATUS_CONVERGED = 0, B200SQP_STATUS_EARLY_TERMINATED = 1, B200SQP_STATUS_INFEASIBLE = 2, B200SQP_STATUS_ERROR = 3 } b200sqp_status;
 
 /* System dynamics registry: corbo::SystemDynamicsInterface::dynamics (src/systems/include/corbo-systems/system_dynamics_interface.h:121).
- * 0..5 restate models of src/systems/include/corbo-systems/benchmark/nonlinear_benchmark_systems.h and linear_benchmark_systems.h;
+ * 0..4 and 7..10 restate models of src/systems/include/corbo-systems/benchmark/nonlinear_benchmark_systems.h and
+ * linear_benchmark_systems.h (every model of the nonlinear header is in the registry);
  * UNICYCLE and QUADROTOR do not exist in the reference and are defined by this project on both sides. */
 typedef enum {
     B200SQP_DYN_VAN_DER_POL      = 0, /* nonlinear_benchmark_systems.h:52-60, params[0] = a */
@@ -45,7 +46,11 @@ typedef enum {
     B200SQP_DYN_CART_POLE        = 3, /* nonlinear_benchmark_systems.h:337-352, params = mc,mp,l,g */
     B200SQP_DYN_DOUBLE_INTEGRATOR = 4, /* linear_benchmark_systems.h DoubleIntegratorDiscreteTime's continuous twin: x'' = u */
     B200SQP_DYN_UNICYCLE         = 5, /* new: x' = v cos(th), y' = v sin(th), th' = w */
-    B200SQP_DYN_QUADROTOR        = 6  /* new: 12-state rigid-body quadrotor, params = m,g,Ixx,Iyy,Izz */
+    B200SQP_DYN_QUADROTOR        = 6, /* new: 12-state rigid-body quadrotor, params = m,g,Ixx,Iyy,Izz */
+    B200SQP_DYN_FREE_SPACE_ROCKET = 7, /* nonlinear_benchmark_systems.h:174-183 FreeSpaceRocket (s, v, m), no parameters */
+    B200SQP_DYN_MASSLESS_PENDULUM = 8, /* nonlinear_benchmark_systems.h:281-290 MasslessPendulum, params[0] = omega0 */
+    B200SQP_DYN_TOY_EXAMPLE      = 9, /* nonlinear_benchmark_systems.h:426-436 ToyExample, params[0] = mu */
+    B200SQP_DYN_ARTSTEINS_CIRCLE = 10 /* nonlinear_benchmark_systems.h:483-492 ArtsteinsCircle, no parameters */
 } b200sqp_dynamics;
 
 /* Discretization grids (vertex sets + edge factories), src/optimal_control/.../discretization_grids/ */

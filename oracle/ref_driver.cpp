@@ -161,6 +161,22 @@ SystemDynamicsInterface::Ptr makeDynamics(const b200sqp_ocp& d)
             s->setTimeConstant(d.dyn_params[0]);
             return s;
         }
+        case B200SQP_DYN_FREE_SPACE_ROCKET:
+            return std::make_shared<FreeSpaceRocket>();
+        case B200SQP_DYN_MASSLESS_PENDULUM:
+        {
+            auto s = std::make_shared<MasslessPendulum>();
+            s->setParameter(d.dyn_params[0]);
+            return s;
+        }
+        case B200SQP_DYN_TOY_EXAMPLE:
+        {
+            auto s = std::make_shared<ToyExample>();
+            s->setParameters(d.dyn_params[0]);
+            return s;
+        }
+        case B200SQP_DYN_ARTSTEINS_CIRCLE:
+            return std::make_shared<ArtsteinsCircle>();
         case B200SQP_DYN_UNICYCLE:
             return std::make_shared<b200ref::Unicycle>();
         case B200SQP_DYN_QUADROTOR:

@@ -178,6 +178,33 @@ Dyn makeDynamics(const b200sqp_ocp& d)
                 f[1] = u[0] / T;
             };
         }
+        case B200SQP_DYN_FREE_SPACE_ROCKET:  // nonlinear_benchmark_systems.h:174-183
+            return [](const double* x, const double* u, double* f) {
+                f[0] = x[1];
+                f[1] = (u[0] - 0.02 * x[1] * x[1]) / x[2];
+                f[2] = -0.01 * u[0] * u[0];
+            };
+        case B200SQP_DYN_MASSLESS_PENDULUM:  // nonlinear_benchmark_systems.h:281-290
+        {
+            const double omega0 = p[0];
+            return [omega0](const double* x, const double* u, double* f) {
+                f[0] = x[1];
+                f[1] = u[0] - omega0 * std::sin(x[0]);
+            };
+        }
+        case B200SQP_DYN_TOY_EXAMPLE:  // nonlinear_benchmark_systems.h:426-436
+        {
+            const double mu = p[0];
+            return [mu](const double* x, const double* u, double* f) {
+                f[0] = x[1] + u[0] * (mu + (1.0 - mu) * x[0]);
+                f[1] = x[0] + u[0] * (mu - 4.0 * (1.0 - mu) * x[1]);
+            };
+        }
+        case B200SQP_DYN_ARTSTEINS_CIRCLE:  // nonlinear_benchmark_systems.h:483-492
+            return [](const double* x, const double* u, double* f) {
+                f[0] = (x[0] * x[0] - x[1] * x[1]) * u[0];
+                f[1] = 2 * x[0] * x[1] * u[0];
+            };
         case B200SQP_DYN_UNICYCLE:  // oracle/ref_models.h Unicycle
             return [](const double* x, const double* u, double* f) {
                 f[0] = u[0] * std::cos(x[2]);

@@ -43,6 +43,15 @@ CASES = {
     "vdp20_timeopt": (lambda: problems.make_ocp(grid=abi.GRID_FD_NONUNIFORM_VARDT, dynamics=abi.DYN_VAN_DER_POL, n_grid=20, dt=0.1,
                                                 stage_cost=abi.COST_MINIMUM_TIME_LSQ, u_lb=(-1.0,), u_ub=(1.0,), xf_fixed=(1, 1), dt_lb=0.0,
                                                 dt_ub=1.0, dyn_params=(1.0,)), (2.0, 2.0, 2.0), 3),
+    # the remaining systems of nonlinear_benchmark_systems.h (rocket, massless pendulum, toy example, Artstein's circle)
+    "rocket20_cn": (lambda: problems.free_space_rocket(20), (2.0, 2.0, 2.0), 3),
+    "rocket20_timeopt": (lambda: problems.free_space_rocket_time_optimal(20), (2.0, 2.0, 2.0), 3),
+    "massless_pendulum20_cn": (lambda: problems.make_ocp(grid=abi.GRID_FD_UNIFORM, dynamics=abi.DYN_MASSLESS_PENDULUM, n_grid=20, dt=0.1, q=(1, 1),
+                                                         r=(0.1,), qf=(1, 1), u_lb=(-2.0,), u_ub=(2.0,), dyn_params=(1.5,)), (2.0, 2.0, 2.0), 3),
+    "toy20_cn": (lambda: problems.make_ocp(grid=abi.GRID_FD_UNIFORM, dynamics=abi.DYN_TOY_EXAMPLE, n_grid=20, dt=0.05, q=(1, 1), r=(0.1,), qf=(1, 1),
+                                           u_lb=(-2.0,), u_ub=(2.0,), dyn_params=(0.5,)), (2.0, 2.0, 2.0), 3),
+    "artstein20_cn": (lambda: problems.make_ocp(grid=abi.GRID_FD_UNIFORM, dynamics=abi.DYN_ARTSTEINS_CIRCLE, n_grid=20, dt=0.1, q=(1, 1), r=(0.1,),
+                                                qf=(1, 1), u_lb=(-1.0,), u_ub=(1.0,)), (2.0, 2.0, 2.0), 3),
     "vdp20_ms_euler": (lambda: problems.van_der_pol_shooting(20, integrator=abi.INT_EULER), (2.0, 2.0, 2.0), 3),
     "vdp20_ms_rk4": (lambda: problems.van_der_pol_shooting(20), (2.0, 2.0, 2.0), 3),
 }
@@ -75,6 +84,12 @@ LINEARIZE_MODELS = {
     "double_integrator": (lambda: problems.make_ocp(grid=abi.GRID_FD_UNIFORM, dynamics=abi.DYN_DOUBLE_INTEGRATOR, n_grid=5, dt=0.1, q=(1, 1), r=(0.1,),
                                                     dyn_params=(2.0,)), True),
     "unicycle": (lambda: problems.unicycle_time_optimal(5), False),
+    "free_space_rocket": (lambda: problems.free_space_rocket(5), True),
+    "massless_pendulum": (lambda: problems.make_ocp(grid=abi.GRID_FD_UNIFORM, dynamics=abi.DYN_MASSLESS_PENDULUM, n_grid=5, dt=0.1, q=(1, 1), r=(0.1,),
+                                                    dyn_params=(1.5,)), False),
+    "toy_example": (lambda: problems.make_ocp(grid=abi.GRID_FD_UNIFORM, dynamics=abi.DYN_TOY_EXAMPLE, n_grid=5, dt=0.1, q=(1, 1), r=(0.1,),
+                                              dyn_params=(0.5,)), True),
+    "artsteins_circle": (lambda: problems.make_ocp(grid=abi.GRID_FD_UNIFORM, dynamics=abi.DYN_ARTSTEINS_CIRCLE, n_grid=5, dt=0.1, q=(1, 1), r=(0.1,)), True),
     "quadrotor": (lambda: problems.quadrotor(5), False),
 }
 LINEARIZE_POINTS = 6
