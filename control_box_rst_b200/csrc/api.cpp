@@ -44,7 +44,8 @@ const KernelSet* findKernels(int dynamics, int defect, int vt)
     const KernelSet* (*tables[])(int*) = {kernelTableVdpCn};
 #else
     const KernelSet* (*tables[])(int*) = {kernelTableVdpCn,       kernelTableVdpFd,    kernelTableVdpMs,   kernelTableOscillators,
-                                          kernelTableCartPole,    kernelTableUnicycle, kernelTableQuadrotor, kernelTableBenchmarkSystems};
+                                          kernelTableCartPole,    kernelTableUnicycle, kernelTableQuadrotor, kernelTableBenchmarkSystems,
+                                          kernelTableCombosFd,    kernelTableCombosMs};
 #endif
     for (auto t : tables)
     {

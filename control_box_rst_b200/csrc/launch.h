@@ -32,6 +32,8 @@ const KernelSet* kernelTableCartPole(int* count);
 const KernelSet* kernelTableUnicycle(int* count);
 const KernelSet* kernelTableQuadrotor(int* count);
 const KernelSet* kernelTableBenchmarkSystems(int* count);
+const KernelSet* kernelTableCombosFd(int* count);
+const KernelSet* kernelTableCombosMs(int* count);
 
 // layout helpers (util_kernels.cu); all arrays device pointers
 // params [B][n] (reference order)  <->  z (block order, tiled instance-minor [tile][K*NB][32]); pinned slots (ref index -1) are left alone

@@ -5,6 +5,20 @@ import numpy as np
 from control_box_rst_b200 import _abi as abi
 from control_box_rst_b200 import problems
 
+def _timeopt(dynamics, n_grid, dt, u_lb, u_ub, dyn_params):
+    """MinimumTime(lsq) on the NonUniformFiniteDifferencesVariableGrid, goal state fixed, dt in [0, 1]."""
+    nx, _ = abi.DYN_DIMS[dynamics]
+    return problems.make_ocp(grid=abi.GRID_FD_NONUNIFORM_VARDT, dynamics=dynamics, n_grid=n_grid, dt=dt, stage_cost=abi.COST_MINIMUM_TIME_LSQ,
+                             u_lb=u_lb, u_ub=u_ub, xf_fixed=(1,) * nx, dt_lb=0.0, dt_ub=1.0, dyn_params=dyn_params)
+
+
+def _quadratic(grid, dynamics, n_grid, dt, u_lb, u_ub, dyn_params, **kw):
+    """Quadratic lsq stage cost (Q = I, R = 0.1 I) and final cost (Qf = 2 I) with control bounds."""
+    nx, nu = abi.DYN_DIMS[dynamics]
+    return problems.make_ocp(grid=grid, dynamics=dynamics, n_grid=n_grid, dt=dt, q=(1.0,) * nx, r=(0.1,) * nu, qf=(2.0,) * nx, u_lb=u_lb, u_ub=u_ub,
+                             dyn_params=dyn_params, **kw)
+
+
 # name -> (ocp builder, LM weights, instances in the fixture)
 CASES = {
     "vdp20_cn": (lambda: problems.van_der_pol(20), (2.0, 2.0, 2.0), 8),
@@ -52,6 +66,25 @@ CASES = {
                                            u_lb=(-2.0,), u_ub=(2.0,), dyn_params=(0.5,)), (2.0, 2.0, 2.0), 3),
     "artstein20_cn": (lambda: problems.make_ocp(grid=abi.GRID_FD_UNIFORM, dynamics=abi.DYN_ARTSTEINS_CIRCLE, n_grid=20, dt=0.1, q=(1, 1), r=(0.1,),
                                                 qf=(1, 1), u_lb=(-1.0,), u_ub=(1.0,)), (2.0, 2.0, 2.0), 3),
+    # further compiled combinations (kernels_combos_fd.cu, kernels_combos_ms.cu)
+    "dint20_timeopt": (lambda: _timeopt(abi.DYN_DOUBLE_INTEGRATOR, 20, 0.1, (-1.0,), (1.0,), (1.0,)), (2.0, 2.0, 2.0), 3),
+    "pendulum20_timeopt": (lambda: _timeopt(abi.DYN_SIMPLE_PENDULUM, 20, 0.1, (-2.0,), (2.0,), (0.205, 0.34, 9.81, 0.25)), (2.0, 2.0, 2.0), 3),
+    "cartpole20_timeopt": (lambda: _timeopt(abi.DYN_CART_POLE, 20, 0.05, (-20.0,), (20.0,), (1.0, 0.3, 0.5, 9.81)), (10.0, 10.0, 10.0), 3),
+    "pendulum20_midpoint": (lambda: _quadratic(abi.GRID_FD_UNIFORM, abi.DYN_SIMPLE_PENDULUM, 20, 0.1, (-2.0,), (2.0,), (0.205, 0.34, 9.81, 0.25),
+                                               collocation=abi.COLL_MIDPOINT), (2.0, 2.0, 2.0), 3),
+    "cartpole20_forward": (lambda: _quadratic(abi.GRID_FD_UNIFORM, abi.DYN_CART_POLE, 20, 0.05, (-20.0,), (20.0,), (1.0, 0.3, 0.5, 9.81),
+                                              collocation=abi.COLL_FORWARD), (10.0, 10.0, 10.0), 3),
+    "unicycle20_backward": (lambda: _quadratic(abi.GRID_FD_UNIFORM, abi.DYN_UNICYCLE, 20, 0.1, (-1.0, -1.0), (1.0, 1.0), (),
+                                               collocation=abi.COLL_BACKWARD), (2.0, 2.0, 2.0), 3),
+    "cartpole20_ms_euler": (lambda: _quadratic(abi.GRID_MULTIPLE_SHOOTING, abi.DYN_CART_POLE, 20, 0.02, (-20.0,), (20.0,), (1.0, 0.3, 0.5, 9.81),
+                                               integrator=abi.INT_EULER), (10.0, 10.0, 10.0), 3),
+    "unicycle20_ms_rk4": (lambda: _quadratic(abi.GRID_MULTIPLE_SHOOTING, abi.DYN_UNICYCLE, 20, 0.1, (-1.0, -1.0), (1.0, 1.0), ()), (2.0, 2.0, 2.0), 3),
+    "duffing20_ms_rk4": (lambda: _quadratic(abi.GRID_MULTIPLE_SHOOTING, abi.DYN_DUFFING, 20, 0.1, (-1.5,), (1.5,), (1.0, -1.0, 1.0)), (2.0, 2.0, 2.0), 3),
+    "pendulum20_ms_rk4": (lambda: _quadratic(abi.GRID_MULTIPLE_SHOOTING, abi.DYN_SIMPLE_PENDULUM, 20, 0.1, (-2.0,), (2.0,),
+                                             (0.205, 0.34, 9.81, 0.25)), (2.0, 2.0, 2.0), 3),
+    "dint20_ms_rk4": (lambda: _quadratic(abi.GRID_MULTIPLE_SHOOTING, abi.DYN_DOUBLE_INTEGRATOR, 20, 0.1, (-1.0,), (1.0,), (2.0,)), (2.0, 2.0, 2.0), 3),
+    "dint20_ms_euler": (lambda: _quadratic(abi.GRID_MULTIPLE_SHOOTING, abi.DYN_DOUBLE_INTEGRATOR, 20, 0.1, (-1.0,), (1.0,), (2.0,),
+                                           integrator=abi.INT_EULER), (2.0, 2.0, 2.0), 3),
     "vdp20_ms_euler": (lambda: problems.van_der_pol_shooting(20, integrator=abi.INT_EULER), (2.0, 2.0, 2.0), 3),
     "vdp20_ms_rk4": (lambda: problems.van_der_pol_shooting(20), (2.0, 2.0, 2.0), 3),
 }
