@@ -159,13 +159,31 @@ bool SolverB200Lm::describe(OptimizationProblemInterface& problem, b200sqp_ocp& 
         d.dynamics      = B200SQP_DYN_DOUBLE_INTEGRATOR;
         d.dyn_params[0] = s->getTimeConstant();
     }
+    else if (dynamic_cast<DuffingOscillator*>(_dynamics.get()) || dynamic_cast<SimplePendulum*>(_dynamics.get()) ||
+             dynamic_cast<MasslessPendulum*>(_dynamics.get()) || dynamic_cast<ToyExample*>(_dynamics.get()))
+    {
+        // setters without getters in the reference: the user repeats the values through setSystemDynamicsParameters(); selfCheck()
+        // compares the device residuals with the reference's own computeValues after the upload, so a wrong value cannot go unnoticed
+        int count = 0;
+        if (dynamic_cast<DuffingOscillator*>(_dynamics.get())) { d.dynamics = B200SQP_DYN_DUFFING; count = 3; }
+        else if (dynamic_cast<SimplePendulum*>(_dynamics.get())) { d.dynamics = B200SQP_DYN_SIMPLE_PENDULUM; count = 4; }
+        else if (dynamic_cast<MasslessPendulum*>(_dynamics.get())) { d.dynamics = B200SQP_DYN_MASSLESS_PENDULUM; count = 1; }
+        else { d.dynamics = B200SQP_DYN_TOY_EXAMPLE; count = 1; }
+        if ((int)_dynamics_parameters.size() != count)
+        {
+            _error = "this system dynamics class exposes no parameter getters: hand its " + std::to_string(count) +
+                     " parameter(s) to setSystemDynamicsParameters()";
+            return false;
+        }
+        for (int i = 0; i < count; ++i) d.dyn_params[i] = _dynamics_parameters[i];
+    }
     else if (dynamic_cast<FreeSpaceRocket*>(_dynamics.get()))
         d.dynamics = B200SQP_DYN_FREE_SPACE_ROCKET;  // no parameters
     else if (dynamic_cast<ArtsteinsCircle*>(_dynamics.get()))
         d.dynamics = B200SQP_DYN_ARTSTEINS_CIRCLE;  // no parameters
     else
     {
-        _error = "system dynamics type is not in the device registry (Duffing/SimplePendulum/MasslessPendulum/ToyExample expose no parameter getters)";
+        _error = "system dynamics type is not in the device registry";
         return false;
     }
 

@@ -53,6 +53,10 @@ class SolverB200Lm : public NlpSolverInterface
 
     // ---- the objects behind the edges (same shared_ptrs the user gave to StructuredOptimalControlProblem / the grid) -----------
     void setSystemDynamics(SystemDynamicsInterface::Ptr dynamics) { _dynamics = dynamics; }
+    // parameters of a dynamics class that has setters but no getters in the reference (DuffingOscillator: damping, spring_alpha,
+    // spring_beta; SimplePendulum: m, l, g, rho; MasslessPendulum: omega0; ToyExample: mu -- nonlinear_benchmark_systems.h): the values
+    // the user passed to setParameters().  A mismatch is caught by the residual self-check after every structure upload.
+    void setSystemDynamicsParameters(const std::vector<double>& parameters) { _dynamics_parameters = parameters; }
     void setCollocation(FiniteDifferencesCollocationInterface::Ptr collocation) { _collocation = collocation; }
     void setIntegrator(NumericalIntegratorExplicitInterface::Ptr integrator) { _integrator = integrator; }
     void setStageCost(StageCost::Ptr stage_cost) { _stage_cost = stage_cost; }
@@ -92,6 +96,7 @@ class SolverB200Lm : public NlpSolverInterface
     std::string _error;
 
     SystemDynamicsInterface::Ptr _dynamics;
+    std::vector<double> _dynamics_parameters;
     FiniteDifferencesCollocationInterface::Ptr _collocation;
     NumericalIntegratorExplicitInterface::Ptr _integrator;
     StageCost::Ptr _stage_cost;

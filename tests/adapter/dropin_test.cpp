@@ -69,6 +69,42 @@ static Loop makeLoop(NlpSolverInterface::Ptr solver, int n, FinalStageConstraint
     return l;
 }
 
+// one cold-started OCP solve of a 2-state / 1-input benchmark system under StructuredOptimalControlProblem with `solver`; returns the
+// optimised parameter vector (empty on failure)
+static Eigen::VectorXd solveBenchmarkSystem(SystemDynamicsInterface::Ptr dynamics, NlpSolverInterface::Ptr solver, const std::vector<double>* parameters,
+                                            bool* ok)
+{
+    auto grid = std::make_shared<FiniteDifferencesGrid>();
+    grid->setNRef(20);
+    grid->setDtRef(0.1);
+    grid->setCostIntegrationRule(FullDiscretizationGridBase::CostIntegrationRule::LeftSum);
+    auto problem = std::make_shared<HyperGraphOptimizationProblemEdgeBased>();
+    auto ocp     = std::make_shared<StructuredOptimalControlProblem>(grid, dynamics, problem, solver);
+    Eigen::MatrixXd Q = Eigen::MatrixXd::Identity(2, 2), R = Eigen::MatrixXd::Constant(1, 1, 0.1);
+    auto stage_cost = std::make_shared<QuadraticFormCost>(Q, R, false, true);
+    auto final_cost = std::make_shared<QuadraticFinalStateCost>(Q, true);
+    ocp->setStageCost(stage_cost);
+    ocp->setFinalStageCost(final_cost);
+    Eigen::VectorXd xlb = Eigen::VectorXd::Constant(2, -CORBO_INF_DBL), xub = Eigen::VectorXd::Constant(2, CORBO_INF_DBL);
+    Eigen::VectorXd ulb = Eigen::VectorXd::Constant(1, -1.5), uub = Eigen::VectorXd::Constant(1, 1.5);
+    ocp->setBounds(xlb, xub, ulb, uub);
+    if (auto b200 = std::dynamic_pointer_cast<SolverB200Lm>(solver))
+    {
+        b200->setSystemDynamics(dynamics);
+        b200->setStageCost(stage_cost);
+        b200->setFinalStageCost(final_cost);
+        if (parameters) b200->setSystemDynamicsParameters(*parameters);
+    }
+    ocp->initialize();
+    ZeroReference xref(2), uref(1);
+    Eigen::VectorXd x0(2);
+    x0 << 1.2, -0.4;
+    *ok = ocp->compute(x0, xref, uref, nullptr, Time(0), true);
+    Eigen::VectorXd p(problem->getParameterDimension());
+    problem->getParameterVector(p);
+    return p;
+}
+
 int main()
 {
     int failures = 0;
@@ -279,6 +315,39 @@ int main()
             std::printf("FAIL: second surface (ok=%d failed=%d, %s)\n", (int)ok5, (int)device_problem->failed(), evaluator->lastError().c_str());
             ++failures;
         }
+    }
+    // ---- 6. the other benchmark systems behind the plugin: a parameter-free class is recognised by its type, a class with setters but no
+    //         getters (nonlinear_benchmark_systems.h) needs setSystemDynamicsParameters(); a wrong or missing value is an Error, never a
+    //         silently different model
+    {
+        auto newRef = [] { auto s = std::make_shared<LevenbergMarquardtSparse>(); s->setIterations(10); return s; };
+        auto newDev = [] { auto s = std::make_shared<SolverB200Lm>(); s->setIterations(10); return s; };
+        auto makeDuffing = [] { auto d = std::make_shared<DuffingOscillator>(); d->setParameters(1.0, -1.0, 1.0); return d; };
+        const std::vector<double> duffing_parameters{1.0, -1.0, 1.0}, wrong_parameters{1.0, -1.0, 2.0};
+        bool ok_r = false, ok_d = false;
+        Eigen::VectorXd p_r = solveBenchmarkSystem(makeDuffing(), newRef(), nullptr, &ok_r);
+        Eigen::VectorXd p_d = solveBenchmarkSystem(makeDuffing(), newDev(), &duffing_parameters, &ok_d);
+        double err = (ok_r && ok_d && p_r.size() == p_d.size()) ? (p_r - p_d).cwiseAbs().maxCoeff() : 1e30;
+        std::printf("Duffing oscillator behind the plugin: max |p_ref - p_b200| = %.3e\n", err);
+        if (!(err <= 2e-5)) { std::printf("FAIL: Duffing solve differs\n"); ++failures; }
+        ok_r = ok_d = false;
+        p_r = solveBenchmarkSystem(std::make_shared<ArtsteinsCircle>(), newRef(), nullptr, &ok_r);
+        p_d = solveBenchmarkSystem(std::make_shared<ArtsteinsCircle>(), newDev(), nullptr, &ok_d);
+        err = (ok_r && ok_d && p_r.size() == p_d.size()) ? (p_r - p_d).cwiseAbs().maxCoeff() : 1e30;
+        std::printf("Artstein's circle behind the plugin (recognised by type): max |p_ref - p_b200| = %.3e\n", err);
+        if (!(err <= 2e-5)) { std::printf("FAIL: Artstein's circle solve differs\n"); ++failures; }
+        auto dev_wrong = newDev(), dev_missing = newDev();
+        bool ok_w = true, ok_m = true;
+        solveBenchmarkSystem(makeDuffing(), dev_wrong, &wrong_parameters, &ok_w);
+        solveBenchmarkSystem(makeDuffing(), dev_missing, nullptr, &ok_m);
+        if (ok_w || ok_m)
+        {
+            std::printf("FAIL: wrong (%d) / missing (%d) dynamics parameters must fail the solve\n", (int)ok_w, (int)ok_m);
+            ++failures;
+        }
+        else
+            std::printf("ok: wrong parameters -> Error (%s); missing parameters -> Error (%s)\n", dev_wrong->lastError().c_str(),
+                        dev_missing->lastError().c_str());
     }
     std::printf(failures ? "DROP-IN TEST FAILED\n" : "DROP-IN TEST PASSED\n");
     return failures ? 1 : 0;
