@@ -23,6 +23,7 @@ DYN_FREE_SPACE_ROCKET = 7
 DYN_MASSLESS_PENDULUM = 8
 DYN_TOY_EXAMPLE = 9
 DYN_ARTSTEINS_CIRCLE = 10
+DYN_LINEAR_2X1 = 11
 DYN_DIMS = {  # id -> (nx, nu)
     DYN_VAN_DER_POL: (2, 1),
     DYN_DUFFING: (2, 1),
@@ -35,6 +36,7 @@ DYN_DIMS = {  # id -> (nx, nu)
     DYN_MASSLESS_PENDULUM: (2, 1),
     DYN_TOY_EXAMPLE: (2, 1),
     DYN_ARTSTEINS_CIRCLE: (2, 1),
+    DYN_LINEAR_2X1: (2, 1),
 }
 
 # b200sqp_grid

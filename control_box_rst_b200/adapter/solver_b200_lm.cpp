@@ -160,7 +160,8 @@ bool SolverB200Lm::describe(OptimizationProblemInterface& problem, b200sqp_ocp& 
         d.dyn_params[0] = s->getTimeConstant();
     }
     else if (dynamic_cast<DuffingOscillator*>(_dynamics.get()) || dynamic_cast<SimplePendulum*>(_dynamics.get()) ||
-             dynamic_cast<MasslessPendulum*>(_dynamics.get()) || dynamic_cast<ToyExample*>(_dynamics.get()))
+             dynamic_cast<MasslessPendulum*>(_dynamics.get()) || dynamic_cast<ToyExample*>(_dynamics.get()) ||
+             (dynamic_cast<LinearStateSpaceModel*>(_dynamics.get()) && d.nx == 2 && d.nu == 1))
     {
         // setters without getters in the reference: the user repeats the values through setSystemDynamicsParameters(); selfCheck()
         // compares the device residuals with the reference's own computeValues after the upload, so a wrong value cannot go unnoticed
@@ -168,7 +169,8 @@ bool SolverB200Lm::describe(OptimizationProblemInterface& problem, b200sqp_ocp& 
         if (dynamic_cast<DuffingOscillator*>(_dynamics.get())) { d.dynamics = B200SQP_DYN_DUFFING; count = 3; }
         else if (dynamic_cast<SimplePendulum*>(_dynamics.get())) { d.dynamics = B200SQP_DYN_SIMPLE_PENDULUM; count = 4; }
         else if (dynamic_cast<MasslessPendulum*>(_dynamics.get())) { d.dynamics = B200SQP_DYN_MASSLESS_PENDULUM; count = 1; }
-        else { d.dynamics = B200SQP_DYN_TOY_EXAMPLE; count = 1; }
+        else if (dynamic_cast<ToyExample*>(_dynamics.get())) { d.dynamics = B200SQP_DYN_TOY_EXAMPLE; count = 1; }
+        else { d.dynamics = B200SQP_DYN_LINEAR_2X1; count = 6; }  // A (2x2, column-major) then B (2x1), as given to setParameters(A, B)
         if ((int)_dynamics_parameters.size() != count)
         {
             _error = "this system dynamics class exposes no parameter getters: hand its " + std::to_string(count) +

@@ -135,6 +135,18 @@ struct ArtsteinsCircle
     }
 };
 
+// LinearStateSpaceModel::dynamics, f = A x + B u -- linear_benchmark_systems.h:206-214, for a 2x2 A and a 2x1 B;
+// p = A column-major, then B.  Summation order of Eigen's evaluation: the product A x column by column, then + B u.
+struct LinearStateSpace2x1
+{
+    static constexpr int NX = 2, NU = 1, ID = B200SQP_DYN_LINEAR_2X1;
+    __device__ __forceinline__ static void f(const DynParams& c, const double* x, const double* u, double* out)
+    {
+        out[0] = (c.p[0] * x[0] + c.p[2] * x[1]) + c.p[4] * u[0];
+        out[1] = (c.p[1] * x[0] + c.p[3] * x[1]) + c.p[5] * u[0];
+    }
+};
+
 // New model (absent from the reference; same equations as oracle/ref_models.h Unicycle)
 struct Unicycle
 {

@@ -225,6 +225,7 @@ bool launchLinearizeDynamics(int dynamics, const DynParams& dyn, int method, int
         case B200SQP_DYN_MASSLESS_PENDULUM: launchOne<MasslessPendulum>(dyn, method, B, x, u, A, Bm, st); return true;
         case B200SQP_DYN_TOY_EXAMPLE: launchOne<ToyExample>(dyn, method, B, x, u, A, Bm, st); return true;
         case B200SQP_DYN_ARTSTEINS_CIRCLE: launchOne<ArtsteinsCircle>(dyn, method, B, x, u, A, Bm, st); return true;
+        case B200SQP_DYN_LINEAR_2X1: launchOne<LinearStateSpace2x1>(dyn, method, B, x, u, A, Bm, st); return true;
     }
     return false;
 }
@@ -245,6 +246,7 @@ bool launchDynamicsHessian(int dynamics, const DynParams& dyn, int method, int B
         case B200SQP_DYN_MASSLESS_PENDULUM: launchHess<MasslessPendulum>(dyn, method, B, x, u, mult, H, st); return true;
         case B200SQP_DYN_TOY_EXAMPLE: launchHess<ToyExample>(dyn, method, B, x, u, mult, H, st); return true;
         case B200SQP_DYN_ARTSTEINS_CIRCLE: launchHess<ArtsteinsCircle>(dyn, method, B, x, u, mult, H, st); return true;
+        case B200SQP_DYN_LINEAR_2X1: launchHess<LinearStateSpace2x1>(dyn, method, B, x, u, mult, H, st); return true;
     }
     return false;
 }

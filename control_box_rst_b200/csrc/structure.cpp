@@ -31,6 +31,7 @@ bool dynamicsDims(int id, Dim& d)
         case B200SQP_DYN_MASSLESS_PENDULUM:
         case B200SQP_DYN_TOY_EXAMPLE:
         case B200SQP_DYN_ARTSTEINS_CIRCLE:
+        case B200SQP_DYN_LINEAR_2X1:
             d = {2, 1};
             return true;
         case B200SQP_DYN_FREE_SPACE_ROCKET:

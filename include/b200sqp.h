@@ -50,7 +50,9 @@ typedef enum {
     B200SQP_DYN_FREE_SPACE_ROCKET = 7, /* nonlinear_benchmark_systems.h:174-183 FreeSpaceRocket (s, v, m), no parameters */
     B200SQP_DYN_MASSLESS_PENDULUM = 8, /* nonlinear_benchmark_systems.h:281-290 MasslessPendulum, params[0] = omega0 */
     B200SQP_DYN_TOY_EXAMPLE      = 9, /* nonlinear_benchmark_systems.h:426-436 ToyExample, params[0] = mu */
-    B200SQP_DYN_ARTSTEINS_CIRCLE = 10 /* nonlinear_benchmark_systems.h:483-492 ArtsteinsCircle, no parameters */
+    B200SQP_DYN_ARTSTEINS_CIRCLE = 10, /* nonlinear_benchmark_systems.h:483-492 ArtsteinsCircle, no parameters */
+    B200SQP_DYN_LINEAR_2X1       = 11 /* linear_benchmark_systems.h:186-214 LinearStateSpaceModel with a 2x2 A and a 2x1 B:
+                                         params = A column-major (a00,a10,a01,a11), then B (b0,b1) */
 } b200sqp_dynamics;
 
 /* Discretization grids (vertex sets + edge factories), src/optimal_control/.../discretization_grids/ */

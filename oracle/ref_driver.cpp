@@ -177,6 +177,14 @@ SystemDynamicsInterface::Ptr makeDynamics(const b200sqp_ocp& d)
         }
         case B200SQP_DYN_ARTSTEINS_CIRCLE:
             return std::make_shared<ArtsteinsCircle>();
+        case B200SQP_DYN_LINEAR_2X1:
+        {
+            auto s = std::make_shared<LinearStateSpaceModel>();
+            Eigen::MatrixXd A = Eigen::Map<const Eigen::Matrix<double, 2, 2>>(d.dyn_params);  // column-major
+            Eigen::MatrixXd B = Eigen::Map<const Eigen::Matrix<double, 2, 1>>(d.dyn_params + 4);
+            s->setParameters(A, B);
+            return s;
+        }
         case B200SQP_DYN_UNICYCLE:
             return std::make_shared<b200ref::Unicycle>();
         case B200SQP_DYN_QUADROTOR:

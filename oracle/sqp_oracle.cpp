@@ -205,6 +205,14 @@ Dyn makeDynamics(const b200sqp_ocp& d)
                 f[0] = (x[0] * x[0] - x[1] * x[1]) * u[0];
                 f[1] = 2 * x[0] * x[1] * u[0];
             };
+        case B200SQP_DYN_LINEAR_2X1:  // linear_benchmark_systems.h:206-214, f = A x + B u (A column-major in p[0..3], B in p[4..5])
+        {
+            const double a00 = p[0], a10 = p[1], a01 = p[2], a11 = p[3], b0 = p[4], b1 = p[5];
+            return [=](const double* x, const double* u, double* f) {
+                f[0] = (a00 * x[0] + a01 * x[1]) + b0 * u[0];
+                f[1] = (a10 * x[0] + a11 * x[1]) + b1 * u[0];
+            };
+        }
         case B200SQP_DYN_UNICYCLE:  // oracle/ref_models.h Unicycle
             return [](const double* x, const double* u, double* f) {
                 f[0] = u[0] * std::cos(x[2]);

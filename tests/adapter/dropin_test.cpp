@@ -14,6 +14,7 @@
 #include <corbo-optimal-control/structured_ocp/structured_optimal_control_problem.h>
 #include <corbo-optimization/hyper_graph/hyper_graph_optimization_problem_edge_based.h>
 #include <corbo-optimization/solver/levenberg_marquardt_sparse.h>
+#include <corbo-systems/benchmark/linear_benchmark_systems.h>
 #include <corbo-systems/benchmark/nonlinear_benchmark_systems.h>
 
 #include <cmath>
@@ -336,6 +337,21 @@ int main()
         err = (ok_r && ok_d && p_r.size() == p_d.size()) ? (p_r - p_d).cwiseAbs().maxCoeff() : 1e30;
         std::printf("Artstein's circle behind the plugin (recognised by type): max |p_ref - p_b200| = %.3e\n", err);
         if (!(err <= 2e-5)) { std::printf("FAIL: Artstein's circle solve differs\n"); ++failures; }
+        auto makeLinear = [] {
+            auto d = std::make_shared<LinearStateSpaceModel>();
+            Eigen::MatrixXd A(2, 2), Bm(2, 1);
+            A << -0.3, 1.1, -2.0, -0.5;
+            Bm << 0.2, 1.5;
+            d->setParameters(A, Bm);
+            return d;
+        };
+        const std::vector<double> linear_parameters{-0.3, -2.0, 1.1, -0.5, 0.2, 1.5};  // A column-major, then B
+        ok_r = ok_d = false;
+        p_r = solveBenchmarkSystem(makeLinear(), newRef(), nullptr, &ok_r);
+        p_d = solveBenchmarkSystem(makeLinear(), newDev(), &linear_parameters, &ok_d);
+        err = (ok_r && ok_d && p_r.size() == p_d.size()) ? (p_r - p_d).cwiseAbs().maxCoeff() : 1e30;
+        std::printf("LinearStateSpaceModel (2x2 A, 2x1 B) behind the plugin: max |p_ref - p_b200| = %.3e\n", err);
+        if (!(err <= 2e-5)) { std::printf("FAIL: linear state-space solve differs\n"); ++failures; }
         auto dev_wrong = newDev(), dev_missing = newDev();
         bool ok_w = true, ok_m = true;
         solveBenchmarkSystem(makeDuffing(), dev_wrong, &wrong_parameters, &ok_w);

@@ -19,6 +19,8 @@ def _quadratic(grid, dynamics, n_grid, dt, u_lb, u_ub, dyn_params, **kw):
                              dyn_params=dyn_params, **kw)
 
 
+LINEAR_AB = (-0.3, -2.0, 1.1, -0.5, 0.2, 1.5)  # A = [[-0.3, 1.1], [-2.0, -0.5]] column-major, B = [0.2, 1.5]
+
 # name -> (ocp builder, LM weights, instances in the fixture)
 CASES = {
     "vdp20_cn": (lambda: problems.van_der_pol(20), (2.0, 2.0, 2.0), 8),
@@ -85,6 +87,10 @@ CASES = {
     "dint20_ms_rk4": (lambda: _quadratic(abi.GRID_MULTIPLE_SHOOTING, abi.DYN_DOUBLE_INTEGRATOR, 20, 0.1, (-1.0,), (1.0,), (2.0,)), (2.0, 2.0, 2.0), 3),
     "dint20_ms_euler": (lambda: _quadratic(abi.GRID_MULTIPLE_SHOOTING, abi.DYN_DOUBLE_INTEGRATOR, 20, 0.1, (-1.0,), (1.0,), (2.0,),
                                            integrator=abi.INT_EULER), (2.0, 2.0, 2.0), 3),
+    # LinearStateSpaceModel (linear_benchmark_systems.h:186-214) with a full 2x2 A and a 2x1 B on all three grids
+    "linear20_cn": (lambda: _quadratic(abi.GRID_FD_UNIFORM, abi.DYN_LINEAR_2X1, 20, 0.1, (-1.0,), (1.0,), LINEAR_AB), (2.0, 2.0, 2.0), 3),
+    "linear20_timeopt": (lambda: _timeopt(abi.DYN_LINEAR_2X1, 20, 0.1, (-1.0,), (1.0,), LINEAR_AB), (2.0, 2.0, 2.0), 3),
+    "linear20_ms_rk4": (lambda: _quadratic(abi.GRID_MULTIPLE_SHOOTING, abi.DYN_LINEAR_2X1, 20, 0.1, (-1.0,), (1.0,), LINEAR_AB), (2.0, 2.0, 2.0), 3),
     "vdp20_ms_euler": (lambda: problems.van_der_pol_shooting(20, integrator=abi.INT_EULER), (2.0, 2.0, 2.0), 3),
     "vdp20_ms_rk4": (lambda: problems.van_der_pol_shooting(20), (2.0, 2.0, 2.0), 3),
 }
@@ -117,6 +123,7 @@ LINEARIZE_MODELS = {
     "double_integrator": (lambda: problems.make_ocp(grid=abi.GRID_FD_UNIFORM, dynamics=abi.DYN_DOUBLE_INTEGRATOR, n_grid=5, dt=0.1, q=(1, 1), r=(0.1,),
                                                     dyn_params=(2.0,)), True),
     "unicycle": (lambda: problems.unicycle_time_optimal(5), False),
+    "linear_2x1": (lambda: _quadratic(abi.GRID_FD_UNIFORM, abi.DYN_LINEAR_2X1, 5, 0.1, (-1.0,), (1.0,), LINEAR_AB), True),
     "free_space_rocket": (lambda: problems.free_space_rocket(5), True),
     "massless_pendulum": (lambda: problems.make_ocp(grid=abi.GRID_FD_UNIFORM, dynamics=abi.DYN_MASSLESS_PENDULUM, n_grid=5, dt=0.1, q=(1, 1), r=(0.1,),
                                                     dyn_params=(1.5,)), False),

@@ -134,7 +134,8 @@ POLYNOMIAL = {"vdp20_cn", "vdp50_cn", "vdp50_cn_nofinal", "vdp30_forward", "vdp3
               "vdp30_terminal_eq", "vdp30_terminal_ball", "vdp20_terminal_ball_xf_partly_fixed",
               "duffing20_cn", "dint20_cn", "dint20_forward", "vdp20_timeopt", "vdp20_ms_euler", "vdp20_ms_rk4",
               "rocket20_cn", "rocket20_timeopt", "toy20_cn", "artstein20_cn",
-              "dint20_timeopt", "duffing20_ms_rk4", "dint20_ms_rk4", "dint20_ms_euler"}
+              "dint20_timeopt", "duffing20_ms_rk4", "dint20_ms_rk4", "dint20_ms_euler",
+              "linear20_cn", "linear20_timeopt", "linear20_ms_rk4"}
 GOLD_TOL = {"unicycle30_timeopt": (1e-3, 1e-4), "cartpole40_rk4": (5e-3, 1e-3), "quadrotor12_cn": (1e-3, 1e-4),
             "cartpole20_terminal_ball": (5e-3, 1e-3), "quadrotor8_terminal_ball": (1e-3, 1e-4),
             "pendulum20_cn": (1e-3, 1e-4), "cartpole20_cn_fd_grid": (5e-3, 1e-3), "unicycle20_cn_fixed_dt": (1e-3, 1e-4),
@@ -143,6 +144,7 @@ GOLD_TOL = {"unicycle30_timeopt": (1e-3, 1e-4), "cartpole40_rk4": (5e-3, 1e-3), 
             "pendulum20_timeopt": (1e-3, 1e-4), "cartpole20_timeopt": (5e-3, 1e-3), "pendulum20_midpoint": (1e-3, 1e-4),
             "cartpole20_forward": (5e-3, 1e-3), "unicycle20_backward": (1e-3, 1e-4), "cartpole20_ms_euler": (5e-3, 1e-3),
             "unicycle20_ms_rk4": (1e-3, 1e-4), "duffing20_ms_rk4": (1e-5, 1e-6), "pendulum20_ms_rk4": (1e-3, 1e-4),
+            "linear20_timeopt": (2e-5, 1e-5), "linear20_ms_rk4": (1e-5, 1e-6),
             "artstein20_cn": (1e-6, 1e-6),  # same optimum to 1e-8 in chi2; the intermediate iterates of this poorly controllable system differ by 1.3e-7
             "vdp20_ms_rk4": (1e-5, 1e-6)}  # (trajectory, chi2); RK4 shooting: four nested evaluations per defect amplify the FD noise (1.5e-6 observed)
 
