@@ -7,7 +7,7 @@ import ctypes as C
 
 MAX_NX = 16
 MAX_NU = 8
-MAX_DYN_PARAMS = 8
+MAX_DYN_PARAMS = 32
 
 CORBO_INF_DBL = 2e30  # core/include/corbo-core/types.h:53
 
@@ -24,6 +24,9 @@ DYN_MASSLESS_PENDULUM = 8
 DYN_TOY_EXAMPLE = 9
 DYN_ARTSTEINS_CIRCLE = 10
 DYN_LINEAR_2X1 = 11
+DYN_LINEAR_3X1 = 12
+DYN_LINEAR_4X1 = 13
+DYN_LINEAR_4X2 = 14
 DYN_DIMS = {  # id -> (nx, nu)
     DYN_VAN_DER_POL: (2, 1),
     DYN_DUFFING: (2, 1),
@@ -37,6 +40,9 @@ DYN_DIMS = {  # id -> (nx, nu)
     DYN_TOY_EXAMPLE: (2, 1),
     DYN_ARTSTEINS_CIRCLE: (2, 1),
     DYN_LINEAR_2X1: (2, 1),
+    DYN_LINEAR_3X1: (3, 1),
+    DYN_LINEAR_4X1: (4, 1),
+    DYN_LINEAR_4X2: (4, 2),
 }
 
 # b200sqp_grid

@@ -161,7 +161,8 @@ bool SolverB200Lm::describe(OptimizationProblemInterface& problem, b200sqp_ocp& 
     }
     else if (dynamic_cast<DuffingOscillator*>(_dynamics.get()) || dynamic_cast<SimplePendulum*>(_dynamics.get()) ||
              dynamic_cast<MasslessPendulum*>(_dynamics.get()) || dynamic_cast<ToyExample*>(_dynamics.get()) ||
-             (dynamic_cast<LinearStateSpaceModel*>(_dynamics.get()) && d.nx == 2 && d.nu == 1))
+             (dynamic_cast<LinearStateSpaceModel*>(_dynamics.get()) &&
+              ((d.nx == 2 && d.nu == 1) || (d.nx == 3 && d.nu == 1) || (d.nx == 4 && d.nu == 1) || (d.nx == 4 && d.nu == 2))))
     {
         // setters without getters in the reference: the user repeats the values through setSystemDynamicsParameters(); selfCheck()
         // compares the device residuals with the reference's own computeValues after the upload, so a wrong value cannot go unnoticed
@@ -170,7 +171,11 @@ bool SolverB200Lm::describe(OptimizationProblemInterface& problem, b200sqp_ocp& 
         else if (dynamic_cast<SimplePendulum*>(_dynamics.get())) { d.dynamics = B200SQP_DYN_SIMPLE_PENDULUM; count = 4; }
         else if (dynamic_cast<MasslessPendulum*>(_dynamics.get())) { d.dynamics = B200SQP_DYN_MASSLESS_PENDULUM; count = 1; }
         else if (dynamic_cast<ToyExample*>(_dynamics.get())) { d.dynamics = B200SQP_DYN_TOY_EXAMPLE; count = 1; }
-        else { d.dynamics = B200SQP_DYN_LINEAR_2X1; count = 6; }  // A (2x2, column-major) then B (2x1), as given to setParameters(A, B)
+        else  // LinearStateSpaceModel: A (column-major) then B (column-major), as given to setParameters(A, B)
+        {
+            d.dynamics = d.nx == 2 ? B200SQP_DYN_LINEAR_2X1 : d.nx == 3 ? B200SQP_DYN_LINEAR_3X1 : d.nu == 1 ? B200SQP_DYN_LINEAR_4X1 : B200SQP_DYN_LINEAR_4X2;
+            count      = d.nx * d.nx + d.nx * d.nu;
+        }
         if ((int)_dynamics_parameters.size() != count)
         {
             _error = "this system dynamics class exposes no parameter getters: hand its " + std::to_string(count) +

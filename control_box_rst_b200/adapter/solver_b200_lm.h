@@ -54,8 +54,8 @@ class SolverB200Lm : public NlpSolverInterface
     // ---- the objects behind the edges (same shared_ptrs the user gave to StructuredOptimalControlProblem / the grid) -----------
     void setSystemDynamics(SystemDynamicsInterface::Ptr dynamics) { _dynamics = dynamics; }
     // parameters of a dynamics class that has setters but no getters in the reference (DuffingOscillator: damping, spring_alpha,
-    // spring_beta; SimplePendulum: m, l, g, rho; MasslessPendulum: omega0; ToyExample: mu -- nonlinear_benchmark_systems.h; a 2-state,
-    // 1-input LinearStateSpaceModel: A column-major then B -- linear_benchmark_systems.h:216): the values
+    // spring_beta; SimplePendulum: m, l, g, rho; MasslessPendulum: omega0; ToyExample: mu -- nonlinear_benchmark_systems.h; a LinearStateSpaceModel
+    // of 2x1, 3x1, 4x1 or 4x2 states x inputs: A column-major then B column-major -- linear_benchmark_systems.h:216): the values
     // the user passed to setParameters().  A mismatch is caught by the residual self-check after every structure upload.
     void setSystemDynamicsParameters(const std::vector<double>& parameters) { _dynamics_parameters = parameters; }
     void setCollocation(FiniteDifferencesCollocationInterface::Ptr collocation) { _collocation = collocation; }

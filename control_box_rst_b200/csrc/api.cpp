@@ -45,7 +45,7 @@ const KernelSet* findKernels(int dynamics, int defect, int vt)
 #else
     const KernelSet* (*tables[])(int*) = {kernelTableVdpCn,       kernelTableVdpFd,    kernelTableVdpMs,   kernelTableOscillators,
                                           kernelTableCartPole,    kernelTableUnicycle, kernelTableQuadrotor, kernelTableBenchmarkSystems,
-                                          kernelTableCombosFd,    kernelTableCombosMs};
+                                          kernelTableCombosFd,    kernelTableCombosMs, kernelTableLinear};
 #endif
     for (auto t : tables)
     {

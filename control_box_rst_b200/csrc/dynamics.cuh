@@ -135,17 +135,34 @@ struct ArtsteinsCircle
     }
 };
 
-// LinearStateSpaceModel::dynamics, f = A x + B u -- linear_benchmark_systems.h:206-214, for a 2x2 A and a 2x1 B;
-// p = A column-major, then B.  Summation order of Eigen's evaluation: the product A x column by column, then + B u.
-struct LinearStateSpace2x1
+// LinearStateSpaceModel::dynamics, f = A x + B u -- linear_benchmark_systems.h:206-214; p = A column-major (NX*NX), then B
+// column-major (NX*NU).  Summation order of Eigen's evaluation for fewer than four columns: the product A x accumulated column by
+// column from zero, the product B u likewise into its own temporary, then their sum (bit-identical to the compiled reference for
+// NX <= 3; from four columns on Eigen's kernel pairs the columns depending on the alignment of the destination, so NX = 4 agrees to
+// rounding only).
+template <int NX_, int NU_, int ID_>
+struct LinearStateSpace
 {
-    static constexpr int NX = 2, NU = 1, ID = B200SQP_DYN_LINEAR_2X1;
+    static constexpr int NX = NX_, NU = NU_, ID = ID_;
     __device__ __forceinline__ static void f(const DynParams& c, const double* x, const double* u, double* out)
     {
-        out[0] = (c.p[0] * x[0] + c.p[2] * x[1]) + c.p[4] * u[0];
-        out[1] = (c.p[1] * x[0] + c.p[3] * x[1]) + c.p[5] * u[0];
+#pragma unroll
+        for (int i = 0; i < NX; ++i)
+        {
+            double ax = c.p[i] * x[0];
+#pragma unroll
+            for (int j = 1; j < NX; ++j) ax = ax + c.p[i + j * NX] * x[j];
+            double bu = c.p[NX * NX + i] * u[0];
+#pragma unroll
+            for (int j = 1; j < NU; ++j) bu = bu + c.p[NX * NX + i + j * NX] * u[j];
+            out[i] = ax + bu;
+        }
     }
 };
+using LinearStateSpace2x1 = LinearStateSpace<2, 1, B200SQP_DYN_LINEAR_2X1>;
+using LinearStateSpace3x1 = LinearStateSpace<3, 1, B200SQP_DYN_LINEAR_3X1>;
+using LinearStateSpace4x1 = LinearStateSpace<4, 1, B200SQP_DYN_LINEAR_4X1>;
+using LinearStateSpace4x2 = LinearStateSpace<4, 2, B200SQP_DYN_LINEAR_4X2>;
 
 // New model (absent from the reference; same equations as oracle/ref_models.h Unicycle)
 struct Unicycle

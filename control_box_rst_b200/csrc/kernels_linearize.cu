@@ -226,6 +226,9 @@ bool launchLinearizeDynamics(int dynamics, const DynParams& dyn, int method, int
         case B200SQP_DYN_TOY_EXAMPLE: launchOne<ToyExample>(dyn, method, B, x, u, A, Bm, st); return true;
         case B200SQP_DYN_ARTSTEINS_CIRCLE: launchOne<ArtsteinsCircle>(dyn, method, B, x, u, A, Bm, st); return true;
         case B200SQP_DYN_LINEAR_2X1: launchOne<LinearStateSpace2x1>(dyn, method, B, x, u, A, Bm, st); return true;
+        case B200SQP_DYN_LINEAR_3X1: launchOne<LinearStateSpace3x1>(dyn, method, B, x, u, A, Bm, st); return true;
+        case B200SQP_DYN_LINEAR_4X1: launchOne<LinearStateSpace4x1>(dyn, method, B, x, u, A, Bm, st); return true;
+        case B200SQP_DYN_LINEAR_4X2: launchOne<LinearStateSpace4x2>(dyn, method, B, x, u, A, Bm, st); return true;
     }
     return false;
 }
@@ -247,6 +250,9 @@ bool launchDynamicsHessian(int dynamics, const DynParams& dyn, int method, int B
         case B200SQP_DYN_TOY_EXAMPLE: launchHess<ToyExample>(dyn, method, B, x, u, mult, H, st); return true;
         case B200SQP_DYN_ARTSTEINS_CIRCLE: launchHess<ArtsteinsCircle>(dyn, method, B, x, u, mult, H, st); return true;
         case B200SQP_DYN_LINEAR_2X1: launchHess<LinearStateSpace2x1>(dyn, method, B, x, u, mult, H, st); return true;
+        case B200SQP_DYN_LINEAR_3X1: launchHess<LinearStateSpace3x1>(dyn, method, B, x, u, mult, H, st); return true;
+        case B200SQP_DYN_LINEAR_4X1: launchHess<LinearStateSpace4x1>(dyn, method, B, x, u, mult, H, st); return true;
+        case B200SQP_DYN_LINEAR_4X2: launchHess<LinearStateSpace4x2>(dyn, method, B, x, u, mult, H, st); return true;
     }
     return false;
 }

@@ -35,7 +35,14 @@ bool dynamicsDims(int id, Dim& d)
             d = {2, 1};
             return true;
         case B200SQP_DYN_FREE_SPACE_ROCKET:
+        case B200SQP_DYN_LINEAR_3X1:
             d = {3, 1};
+            return true;
+        case B200SQP_DYN_LINEAR_4X1:
+            d = {4, 1};
+            return true;
+        case B200SQP_DYN_LINEAR_4X2:
+            d = {4, 2};
             return true;
         case B200SQP_DYN_CART_POLE:
             d = {4, 1};

@@ -21,7 +21,7 @@ extern "C" {
 
 #define B200SQP_MAX_NX 16
 #define B200SQP_MAX_NU 8
-#define B200SQP_MAX_DYN_PARAMS 8
+#define B200SQP_MAX_DYN_PARAMS 32
 
 typedef enum {
     B200SQP_OK                = 0,
@@ -51,8 +51,11 @@ typedef enum {
     B200SQP_DYN_MASSLESS_PENDULUM = 8, /* nonlinear_benchmark_systems.h:281-290 MasslessPendulum, params[0] = omega0 */
     B200SQP_DYN_TOY_EXAMPLE      = 9, /* nonlinear_benchmark_systems.h:426-436 ToyExample, params[0] = mu */
     B200SQP_DYN_ARTSTEINS_CIRCLE = 10, /* nonlinear_benchmark_systems.h:483-492 ArtsteinsCircle, no parameters */
-    B200SQP_DYN_LINEAR_2X1       = 11 /* linear_benchmark_systems.h:186-214 LinearStateSpaceModel with a 2x2 A and a 2x1 B:
-                                         params = A column-major (a00,a10,a01,a11), then B (b0,b1) */
+    B200SQP_DYN_LINEAR_2X1       = 11, /* linear_benchmark_systems.h:186-214 LinearStateSpaceModel, f = A x + B u, with a 2x2 A and a
+                                          2x1 B: params = A column-major (nx*nx values), then B column-major (nx*nu values) */
+    B200SQP_DYN_LINEAR_3X1       = 12, /* the same with a 3x3 A and a 3x1 B */
+    B200SQP_DYN_LINEAR_4X1       = 13, /* the same with a 4x4 A and a 4x1 B */
+    B200SQP_DYN_LINEAR_4X2       = 14  /* the same with a 4x4 A and a 4x2 B */
 } b200sqp_dynamics;
 
 /* Discretization grids (vertex sets + edge factories), src/optimal_control/.../discretization_grids/ */

@@ -178,10 +178,13 @@ SystemDynamicsInterface::Ptr makeDynamics(const b200sqp_ocp& d)
         case B200SQP_DYN_ARTSTEINS_CIRCLE:
             return std::make_shared<ArtsteinsCircle>();
         case B200SQP_DYN_LINEAR_2X1:
+        case B200SQP_DYN_LINEAR_3X1:
+        case B200SQP_DYN_LINEAR_4X1:
+        case B200SQP_DYN_LINEAR_4X2:
         {
             auto s = std::make_shared<LinearStateSpaceModel>();
-            Eigen::MatrixXd A = Eigen::Map<const Eigen::Matrix<double, 2, 2>>(d.dyn_params);  // column-major
-            Eigen::MatrixXd B = Eigen::Map<const Eigen::Matrix<double, 2, 1>>(d.dyn_params + 4);
+            Eigen::MatrixXd A = Eigen::Map<const Eigen::MatrixXd>(d.dyn_params, d.nx, d.nx);  // column-major
+            Eigen::MatrixXd B = Eigen::Map<const Eigen::MatrixXd>(d.dyn_params + d.nx * d.nx, d.nx, d.nu);
             s->setParameters(A, B);
             return s;
         }

@@ -205,12 +205,23 @@ Dyn makeDynamics(const b200sqp_ocp& d)
                 f[0] = (x[0] * x[0] - x[1] * x[1]) * u[0];
                 f[1] = 2 * x[0] * x[1] * u[0];
             };
-        case B200SQP_DYN_LINEAR_2X1:  // linear_benchmark_systems.h:206-214, f = A x + B u (A column-major in p[0..3], B in p[4..5])
+        case B200SQP_DYN_LINEAR_2X1:  // linear_benchmark_systems.h:206-214, f = A x + B u (A column-major, then B column-major)
+        case B200SQP_DYN_LINEAR_3X1:
+        case B200SQP_DYN_LINEAR_4X1:
+        case B200SQP_DYN_LINEAR_4X2:
         {
-            const double a00 = p[0], a10 = p[1], a01 = p[2], a11 = p[3], b0 = p[4], b1 = p[5];
+            const int nx = d.nx, nu = d.nu;
+            std::vector<double> ab(p, p + nx * nx + nx * nu);
             return [=](const double* x, const double* u, double* f) {
-                f[0] = (a00 * x[0] + a01 * x[1]) + b0 * u[0];
-                f[1] = (a10 * x[0] + a11 * x[1]) + b1 * u[0];
+                // Eigen evaluates both products column by column from zero (fewer than four columns) and then adds them
+                for (int i = 0; i < nx; ++i)
+                {
+                    double ax = ab[i] * x[0];
+                    for (int j = 1; j < nx; ++j) ax = ax + ab[i + j * nx] * x[j];
+                    double bu = ab[nx * nx + i] * u[0];
+                    for (int j = 1; j < nu; ++j) bu = bu + ab[nx * nx + i + j * nx] * u[j];
+                    f[i] = ax + bu;
+                }
             };
         }
         case B200SQP_DYN_UNICYCLE:  // oracle/ref_models.h Unicycle

@@ -21,6 +21,12 @@ def _quadratic(grid, dynamics, n_grid, dt, u_lb, u_ub, dyn_params, **kw):
 
 LINEAR_AB = (-0.3, -2.0, 1.1, -0.5, 0.2, 1.5)  # A = [[-0.3, 1.1], [-2.0, -0.5]] column-major, B = [0.2, 1.5]
 
+# a chain of three lags with feedback, and a two-mass oscillator (positions, velocities) driven at one / both masses
+LINEAR_AB_3X1 = (-0.5, 0.2, -0.1, 1.0, -0.4, 0.3, 0.1, 1.2, -0.8) + (0.3, -0.2, 1.0)
+_A4 = (0.0, 0.0, -2.0, 1.0, 0.0, 0.0, 1.0, -1.5, 1.0, 0.0, -0.3, 0.1, 0.0, 1.0, 0.1, -0.2)  # column-major
+LINEAR_AB_4X1 = _A4 + (0.0, 0.0, 1.0, 0.25)
+LINEAR_AB_4X2 = _A4 + (0.0, 0.0, 1.0, 0.25) + (0.1, 0.0, -0.2, 0.8)
+
 # name -> (ocp builder, LM weights, instances in the fixture)
 CASES = {
     "vdp20_cn": (lambda: problems.van_der_pol(20), (2.0, 2.0, 2.0), 8),
@@ -91,6 +97,16 @@ CASES = {
     "linear20_cn": (lambda: _quadratic(abi.GRID_FD_UNIFORM, abi.DYN_LINEAR_2X1, 20, 0.1, (-1.0,), (1.0,), LINEAR_AB), (2.0, 2.0, 2.0), 3),
     "linear20_timeopt": (lambda: _timeopt(abi.DYN_LINEAR_2X1, 20, 0.1, (-1.0,), (1.0,), LINEAR_AB), (2.0, 2.0, 2.0), 3),
     "linear20_ms_rk4": (lambda: _quadratic(abi.GRID_MULTIPLE_SHOOTING, abi.DYN_LINEAR_2X1, 20, 0.1, (-1.0,), (1.0,), LINEAR_AB), (2.0, 2.0, 2.0), 3),
+    "linear3_20_cn": (lambda: _quadratic(abi.GRID_FD_UNIFORM, abi.DYN_LINEAR_3X1, 20, 0.1, (-1.0,), (1.0,), LINEAR_AB_3X1), (2.0, 2.0, 2.0), 3),
+    "linear3_20_timeopt": (lambda: _timeopt(abi.DYN_LINEAR_3X1, 20, 0.1, (-1.0,), (1.0,), LINEAR_AB_3X1), (2.0, 2.0, 2.0), 3),
+    "linear3_20_ms_rk4": (lambda: _quadratic(abi.GRID_MULTIPLE_SHOOTING, abi.DYN_LINEAR_3X1, 20, 0.1, (-1.0,), (1.0,), LINEAR_AB_3X1),
+                          (2.0, 2.0, 2.0), 3),
+    "linear4_20_cn": (lambda: _quadratic(abi.GRID_FD_UNIFORM, abi.DYN_LINEAR_4X1, 20, 0.1, (-1.0,), (1.0,), LINEAR_AB_4X1), (2.0, 2.0, 2.0), 3),
+    "linear4_20_ms_rk4": (lambda: _quadratic(abi.GRID_MULTIPLE_SHOOTING, abi.DYN_LINEAR_4X1, 20, 0.1, (-1.0,), (1.0,), LINEAR_AB_4X1),
+                          (2.0, 2.0, 2.0), 3),
+    "linear4x2_20_cn": (lambda: _quadratic(abi.GRID_FD_UNIFORM, abi.DYN_LINEAR_4X2, 20, 0.1, (-1.0, -1.0), (1.0, 1.0), LINEAR_AB_4X2),
+                        (2.0, 2.0, 2.0), 3),
+    "linear4x2_20_timeopt": (lambda: _timeopt(abi.DYN_LINEAR_4X2, 20, 0.1, (-1.0, -1.0), (1.0, 1.0), LINEAR_AB_4X2), (2.0, 2.0, 2.0), 3),
     "vdp20_ms_euler": (lambda: problems.van_der_pol_shooting(20, integrator=abi.INT_EULER), (2.0, 2.0, 2.0), 3),
     "vdp20_ms_rk4": (lambda: problems.van_der_pol_shooting(20), (2.0, 2.0, 2.0), 3),
 }
@@ -123,6 +139,9 @@ LINEARIZE_MODELS = {
     "double_integrator": (lambda: problems.make_ocp(grid=abi.GRID_FD_UNIFORM, dynamics=abi.DYN_DOUBLE_INTEGRATOR, n_grid=5, dt=0.1, q=(1, 1), r=(0.1,),
                                                     dyn_params=(2.0,)), True),
     "unicycle": (lambda: problems.unicycle_time_optimal(5), False),
+    "linear_3x1": (lambda: _quadratic(abi.GRID_FD_UNIFORM, abi.DYN_LINEAR_3X1, 5, 0.1, (-1.0,), (1.0,), LINEAR_AB_3X1), True),
+    "linear_4x1": (lambda: _quadratic(abi.GRID_FD_UNIFORM, abi.DYN_LINEAR_4X1, 5, 0.1, (-1.0,), (1.0,), LINEAR_AB_4X1), False),
+    "linear_4x2": (lambda: _quadratic(abi.GRID_FD_UNIFORM, abi.DYN_LINEAR_4X2, 5, 0.1, (-1.0, -1.0), (1.0, 1.0), LINEAR_AB_4X2), False),
     "linear_2x1": (lambda: _quadratic(abi.GRID_FD_UNIFORM, abi.DYN_LINEAR_2X1, 5, 0.1, (-1.0,), (1.0,), LINEAR_AB), True),
     "free_space_rocket": (lambda: problems.free_space_rocket(5), True),
     "massless_pendulum": (lambda: problems.make_ocp(grid=abi.GRID_FD_UNIFORM, dynamics=abi.DYN_MASSLESS_PENDULUM, n_grid=5, dt=0.1, q=(1, 1), r=(0.1,),

@@ -135,7 +135,7 @@ POLYNOMIAL = {"vdp20_cn", "vdp50_cn", "vdp50_cn_nofinal", "vdp30_forward", "vdp3
               "duffing20_cn", "dint20_cn", "dint20_forward", "vdp20_timeopt", "vdp20_ms_euler", "vdp20_ms_rk4",
               "rocket20_cn", "rocket20_timeopt", "toy20_cn", "artstein20_cn",
               "dint20_timeopt", "duffing20_ms_rk4", "dint20_ms_rk4", "dint20_ms_euler",
-              "linear20_cn", "linear20_timeopt", "linear20_ms_rk4"}
+              "linear20_cn", "linear20_timeopt", "linear20_ms_rk4", "linear3_20_cn", "linear3_20_timeopt", "linear3_20_ms_rk4"}
 GOLD_TOL = {"unicycle30_timeopt": (1e-3, 1e-4), "cartpole40_rk4": (5e-3, 1e-3), "quadrotor12_cn": (1e-3, 1e-4),
             "cartpole20_terminal_ball": (5e-3, 1e-3), "quadrotor8_terminal_ball": (1e-3, 1e-4),
             "pendulum20_cn": (1e-3, 1e-4), "cartpole20_cn_fd_grid": (5e-3, 1e-3), "unicycle20_cn_fixed_dt": (1e-3, 1e-4),
