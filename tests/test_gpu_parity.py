@@ -144,7 +144,9 @@ GOLD_TOL = {"unicycle30_timeopt": (1e-3, 1e-4), "cartpole40_rk4": (5e-3, 1e-3), 
             "pendulum20_timeopt": (1e-3, 1e-4), "cartpole20_timeopt": (5e-3, 1e-3), "pendulum20_midpoint": (1e-3, 1e-4),
             "cartpole20_forward": (5e-3, 1e-3), "unicycle20_backward": (1e-3, 1e-4), "cartpole20_ms_euler": (5e-3, 1e-3),
             "unicycle20_ms_rk4": (1e-3, 1e-4), "duffing20_ms_rk4": (1e-5, 1e-6), "pendulum20_ms_rk4": (1e-3, 1e-4),
-            "linear20_timeopt": (2e-5, 1e-5), "linear20_ms_rk4": (1e-5, 1e-6),
+            "linear20_timeopt": (2e-5, 1e-5), "linear20_ms_rk4": (1e-5, 1e-6), "linear3_20_timeopt": (2e-5, 1e-5),
+            "linear4x2_20_timeopt": (2e-5, 1e-5), "linear4x2_20_cn": (1e-6, 1e-6), "linear4_20_cn": (1e-6, 1e-6),
+            "linear3_20_ms_rk4": (1e-5, 1e-6), "linear4_20_ms_rk4": (1e-5, 1e-6),
             "artstein20_cn": (1e-6, 1e-6),  # same optimum to 1e-8 in chi2; the intermediate iterates of this poorly controllable system differ by 1.3e-7
             "vdp20_ms_rk4": (1e-5, 1e-6)}  # (trajectory, chi2); RK4 shooting: four nested evaluations per defect amplify the FD noise (1.5e-6 observed)
 
