@@ -27,6 +27,8 @@ DYN_LINEAR_2X1 = 11
 DYN_LINEAR_3X1 = 12
 DYN_LINEAR_4X1 = 13
 DYN_LINEAR_4X2 = 14
+DYN_TRIPLE_INTEGRATOR = 15
+DYN_QUAD_INTEGRATOR = 16
 DYN_DIMS = {  # id -> (nx, nu)
     DYN_VAN_DER_POL: (2, 1),
     DYN_DUFFING: (2, 1),
@@ -43,6 +45,8 @@ DYN_DIMS = {  # id -> (nx, nu)
     DYN_LINEAR_3X1: (3, 1),
     DYN_LINEAR_4X1: (4, 1),
     DYN_LINEAR_4X2: (4, 2),
+    DYN_TRIPLE_INTEGRATOR: (3, 1),
+    DYN_QUAD_INTEGRATOR: (4, 1),
 }
 
 # b200sqp_grid

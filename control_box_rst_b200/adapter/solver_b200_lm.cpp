@@ -151,12 +151,12 @@ bool SolverB200Lm::describe(OptimizationProblemInterface& problem, b200sqp_ocp& 
         d.dynamics = B200SQP_DYN_CART_POLE;  // parameters are private constants in the reference
     else if (auto* s = dynamic_cast<SerialIntegratorSystem*>(_dynamics.get()))
     {
-        if (s->getDimension() != 2)
+        if (s->getDimension() < 2 || s->getDimension() > 4)
         {
-            _error = "SerialIntegratorSystem: only dimension 2 is in the device registry";
+            _error = "SerialIntegratorSystem: only dimensions 2, 3 and 4 are in the device registry";
             return false;
         }
-        d.dynamics      = B200SQP_DYN_DOUBLE_INTEGRATOR;
+        d.dynamics = s->getDimension() == 2 ? B200SQP_DYN_DOUBLE_INTEGRATOR : s->getDimension() == 3 ? B200SQP_DYN_TRIPLE_INTEGRATOR : B200SQP_DYN_QUAD_INTEGRATOR;
         d.dyn_params[0] = s->getTimeConstant();
     }
     else if (dynamic_cast<DuffingOscillator*>(_dynamics.get()) || dynamic_cast<SimplePendulum*>(_dynamics.get()) ||

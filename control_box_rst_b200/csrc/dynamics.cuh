@@ -164,6 +164,21 @@ using LinearStateSpace3x1 = LinearStateSpace<3, 1, B200SQP_DYN_LINEAR_3X1>;
 using LinearStateSpace4x1 = LinearStateSpace<4, 1, B200SQP_DYN_LINEAR_4X1>;
 using LinearStateSpace4x2 = LinearStateSpace<4, 2, B200SQP_DYN_LINEAR_4X2>;
 
+// SerialIntegratorSystem(dimension P)::dynamics for P = 3, 4 -- linear_benchmark_systems.h:71-82; p = time constant
+template <int P, int ID_>
+struct SerialIntegrator
+{
+    static constexpr int NX = P, NU = 1, ID = ID_;
+    __device__ __forceinline__ static void f(const DynParams& c, const double* x, const double* u, double* out)
+    {
+#pragma unroll
+        for (int i = 0; i < P - 1; ++i) out[i] = x[i + 1];
+        out[P - 1] = u[0] / c.p[0];
+    }
+};
+using TripleIntegrator = SerialIntegrator<3, B200SQP_DYN_TRIPLE_INTEGRATOR>;
+using QuadIntegrator   = SerialIntegrator<4, B200SQP_DYN_QUAD_INTEGRATOR>;
+
 // New model (absent from the reference; same equations as oracle/ref_models.h Unicycle)
 struct Unicycle
 {

@@ -229,6 +229,8 @@ bool launchLinearizeDynamics(int dynamics, const DynParams& dyn, int method, int
         case B200SQP_DYN_LINEAR_3X1: launchOne<LinearStateSpace3x1>(dyn, method, B, x, u, A, Bm, st); return true;
         case B200SQP_DYN_LINEAR_4X1: launchOne<LinearStateSpace4x1>(dyn, method, B, x, u, A, Bm, st); return true;
         case B200SQP_DYN_LINEAR_4X2: launchOne<LinearStateSpace4x2>(dyn, method, B, x, u, A, Bm, st); return true;
+        case B200SQP_DYN_TRIPLE_INTEGRATOR: launchOne<TripleIntegrator>(dyn, method, B, x, u, A, Bm, st); return true;
+        case B200SQP_DYN_QUAD_INTEGRATOR: launchOne<QuadIntegrator>(dyn, method, B, x, u, A, Bm, st); return true;
     }
     return false;
 }
@@ -253,6 +255,8 @@ bool launchDynamicsHessian(int dynamics, const DynParams& dyn, int method, int B
         case B200SQP_DYN_LINEAR_3X1: launchHess<LinearStateSpace3x1>(dyn, method, B, x, u, mult, H, st); return true;
         case B200SQP_DYN_LINEAR_4X1: launchHess<LinearStateSpace4x1>(dyn, method, B, x, u, mult, H, st); return true;
         case B200SQP_DYN_LINEAR_4X2: launchHess<LinearStateSpace4x2>(dyn, method, B, x, u, mult, H, st); return true;
+        case B200SQP_DYN_TRIPLE_INTEGRATOR: launchHess<TripleIntegrator>(dyn, method, B, x, u, mult, H, st); return true;
+        case B200SQP_DYN_QUAD_INTEGRATOR: launchHess<QuadIntegrator>(dyn, method, B, x, u, mult, H, st); return true;
     }
     return false;
 }

@@ -82,6 +82,8 @@ bool launchPlantStep(int dynamics, const DynParams& dyn, int integrator, double 
         case B200SQP_DYN_LINEAR_3X1: launchOne<LinearStateSpace3x1>(dyn, integrator, dt, B, x, u, x_next, u_log, chi2_src, chi2_log, status_src, status_log, st); return true;
         case B200SQP_DYN_LINEAR_4X1: launchOne<LinearStateSpace4x1>(dyn, integrator, dt, B, x, u, x_next, u_log, chi2_src, chi2_log, status_src, status_log, st); return true;
         case B200SQP_DYN_LINEAR_4X2: launchOne<LinearStateSpace4x2>(dyn, integrator, dt, B, x, u, x_next, u_log, chi2_src, chi2_log, status_src, status_log, st); return true;
+        case B200SQP_DYN_TRIPLE_INTEGRATOR: launchOne<TripleIntegrator>(dyn, integrator, dt, B, x, u, x_next, u_log, chi2_src, chi2_log, status_src, status_log, st); return true;
+        case B200SQP_DYN_QUAD_INTEGRATOR: launchOne<QuadIntegrator>(dyn, integrator, dt, B, x, u, x_next, u_log, chi2_src, chi2_log, status_src, status_log, st); return true;
     }
     return false;
 }

@@ -36,9 +36,11 @@ bool dynamicsDims(int id, Dim& d)
             return true;
         case B200SQP_DYN_FREE_SPACE_ROCKET:
         case B200SQP_DYN_LINEAR_3X1:
+        case B200SQP_DYN_TRIPLE_INTEGRATOR:
             d = {3, 1};
             return true;
         case B200SQP_DYN_LINEAR_4X1:
+        case B200SQP_DYN_QUAD_INTEGRATOR:
             d = {4, 1};
             return true;
         case B200SQP_DYN_LINEAR_4X2:

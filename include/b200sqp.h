@@ -55,7 +55,9 @@ typedef enum {
                                           2x1 B: params = A column-major (nx*nx values), then B column-major (nx*nu values) */
     B200SQP_DYN_LINEAR_3X1       = 12, /* the same with a 3x3 A and a 3x1 B */
     B200SQP_DYN_LINEAR_4X1       = 13, /* the same with a 4x4 A and a 4x1 B */
-    B200SQP_DYN_LINEAR_4X2       = 14  /* the same with a 4x4 A and a 4x2 B */
+    B200SQP_DYN_LINEAR_4X2       = 14, /* the same with a 4x4 A and a 4x2 B */
+    B200SQP_DYN_TRIPLE_INTEGRATOR = 15, /* linear_benchmark_systems.h:71-82 SerialIntegratorSystem(3): x''' = u / T, params[0] = T */
+    B200SQP_DYN_QUAD_INTEGRATOR  = 16  /* SerialIntegratorSystem(4), params[0] = T */
 } b200sqp_dynamics;
 
 /* Discretization grids (vertex sets + edge factories), src/optimal_control/.../discretization_grids/ */

@@ -188,6 +188,13 @@ SystemDynamicsInterface::Ptr makeDynamics(const b200sqp_ocp& d)
             s->setParameters(A, B);
             return s;
         }
+        case B200SQP_DYN_TRIPLE_INTEGRATOR:
+        case B200SQP_DYN_QUAD_INTEGRATOR:
+        {
+            auto s = std::make_shared<SerialIntegratorSystem>(d.nx);
+            s->setTimeConstant(d.dyn_params[0]);
+            return s;
+        }
         case B200SQP_DYN_UNICYCLE:
             return std::make_shared<b200ref::Unicycle>();
         case B200SQP_DYN_QUADROTOR:

@@ -224,6 +224,16 @@ Dyn makeDynamics(const b200sqp_ocp& d)
                 }
             };
         }
+        case B200SQP_DYN_TRIPLE_INTEGRATOR:  // linear_benchmark_systems.h:71-82 (SerialIntegratorSystem, dimension 3 / 4)
+        case B200SQP_DYN_QUAD_INTEGRATOR:
+        {
+            const double T = p[0];
+            const int n    = d.nx;
+            return [T, n](const double* x, const double* u, double* f) {
+                for (int i = 0; i < n - 1; ++i) f[i] = x[i + 1];
+                f[n - 1] = u[0] / T;
+            };
+        }
         case B200SQP_DYN_UNICYCLE:  // oracle/ref_models.h Unicycle
             return [](const double* x, const double* u, double* f) {
                 f[0] = u[0] * std::cos(x[2]);

@@ -107,6 +107,9 @@ CASES = {
     "linear4x2_20_cn": (lambda: _quadratic(abi.GRID_FD_UNIFORM, abi.DYN_LINEAR_4X2, 20, 0.1, (-1.0, -1.0), (1.0, 1.0), LINEAR_AB_4X2),
                         (2.0, 2.0, 2.0), 3),
     "linear4x2_20_timeopt": (lambda: _timeopt(abi.DYN_LINEAR_4X2, 20, 0.1, (-1.0, -1.0), (1.0, 1.0), LINEAR_AB_4X2), (2.0, 2.0, 2.0), 3),
+    "tint20_cn": (lambda: _quadratic(abi.GRID_FD_UNIFORM, abi.DYN_TRIPLE_INTEGRATOR, 20, 0.1, (-1.0,), (1.0,), (1.5,)), (2.0, 2.0, 2.0), 3),
+    "tint20_timeopt": (lambda: _timeopt(abi.DYN_TRIPLE_INTEGRATOR, 20, 0.1, (-1.0,), (1.0,), (1.0,)), (2.0, 2.0, 2.0), 3),
+    "qint20_cn": (lambda: _quadratic(abi.GRID_FD_UNIFORM, abi.DYN_QUAD_INTEGRATOR, 20, 0.1, (-1.0,), (1.0,), (1.5,)), (2.0, 2.0, 2.0), 3),
     "vdp20_ms_euler": (lambda: problems.van_der_pol_shooting(20, integrator=abi.INT_EULER), (2.0, 2.0, 2.0), 3),
     "vdp20_ms_rk4": (lambda: problems.van_der_pol_shooting(20), (2.0, 2.0, 2.0), 3),
 }
@@ -139,6 +142,8 @@ LINEARIZE_MODELS = {
     "double_integrator": (lambda: problems.make_ocp(grid=abi.GRID_FD_UNIFORM, dynamics=abi.DYN_DOUBLE_INTEGRATOR, n_grid=5, dt=0.1, q=(1, 1), r=(0.1,),
                                                     dyn_params=(2.0,)), True),
     "unicycle": (lambda: problems.unicycle_time_optimal(5), False),
+    "triple_integrator": (lambda: _quadratic(abi.GRID_FD_UNIFORM, abi.DYN_TRIPLE_INTEGRATOR, 5, 0.1, (-1.0,), (1.0,), (1.5,)), True),
+    "quad_integrator": (lambda: _quadratic(abi.GRID_FD_UNIFORM, abi.DYN_QUAD_INTEGRATOR, 5, 0.1, (-1.0,), (1.0,), (1.5,)), True),
     "linear_3x1": (lambda: _quadratic(abi.GRID_FD_UNIFORM, abi.DYN_LINEAR_3X1, 5, 0.1, (-1.0,), (1.0,), LINEAR_AB_3X1), True),
     "linear_4x1": (lambda: _quadratic(abi.GRID_FD_UNIFORM, abi.DYN_LINEAR_4X1, 5, 0.1, (-1.0,), (1.0,), LINEAR_AB_4X1), False),
     "linear_4x2": (lambda: _quadratic(abi.GRID_FD_UNIFORM, abi.DYN_LINEAR_4X2, 5, 0.1, (-1.0, -1.0), (1.0, 1.0), LINEAR_AB_4X2), False),

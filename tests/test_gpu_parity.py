@@ -135,7 +135,8 @@ POLYNOMIAL = {"vdp20_cn", "vdp50_cn", "vdp50_cn_nofinal", "vdp30_forward", "vdp3
               "duffing20_cn", "dint20_cn", "dint20_forward", "vdp20_timeopt", "vdp20_ms_euler", "vdp20_ms_rk4",
               "rocket20_cn", "rocket20_timeopt", "toy20_cn", "artstein20_cn",
               "dint20_timeopt", "duffing20_ms_rk4", "dint20_ms_rk4", "dint20_ms_euler",
-              "linear20_cn", "linear20_timeopt", "linear20_ms_rk4", "linear3_20_cn", "linear3_20_timeopt", "linear3_20_ms_rk4"}
+              "linear20_cn", "linear20_timeopt", "linear20_ms_rk4", "linear3_20_cn", "linear3_20_timeopt", "linear3_20_ms_rk4",
+              "tint20_cn", "tint20_timeopt", "qint20_cn"}
 GOLD_TOL = {"unicycle30_timeopt": (1e-3, 1e-4), "cartpole40_rk4": (5e-3, 1e-3), "quadrotor12_cn": (1e-3, 1e-4),
             "cartpole20_terminal_ball": (5e-3, 1e-3), "quadrotor8_terminal_ball": (1e-3, 1e-4),
             "pendulum20_cn": (1e-3, 1e-4), "cartpole20_cn_fd_grid": (5e-3, 1e-3), "unicycle20_cn_fixed_dt": (1e-3, 1e-4),
@@ -147,6 +148,7 @@ GOLD_TOL = {"unicycle30_timeopt": (1e-3, 1e-4), "cartpole40_rk4": (5e-3, 1e-3), 
             "linear20_timeopt": (2e-5, 1e-5), "linear20_ms_rk4": (1e-5, 1e-6), "linear3_20_timeopt": (2e-5, 1e-5),
             "linear4x2_20_timeopt": (2e-5, 1e-5), "linear4x2_20_cn": (1e-6, 1e-6), "linear4_20_cn": (1e-6, 1e-6),
             "linear3_20_ms_rk4": (1e-5, 1e-6), "linear4_20_ms_rk4": (1e-5, 1e-6),
+            "tint20_timeopt": (2e-5, 1e-5), "tint20_cn": (1e-6, 1e-6), "qint20_cn": (1e-6, 1e-6),
             "artstein20_cn": (1e-6, 1e-6),  # same optimum to 1e-8 in chi2; the intermediate iterates of this poorly controllable system differ by 1.3e-7
             "vdp20_ms_rk4": (1e-5, 1e-6)}  # (trajectory, chi2); RK4 shooting: four nested evaluations per defect amplify the FD noise (1.5e-6 observed)
 

@@ -20,7 +20,8 @@ POLYNOMIAL = {"vdp20_cn", "vdp50_cn", "vdp50_cn_nofinal", "vdp30_forward", "vdp3
               "duffing20_cn", "dint20_cn", "dint20_forward", "vdp20_timeopt", "vdp20_ms_euler", "vdp20_ms_rk4",
               "rocket20_cn", "rocket20_timeopt", "toy20_cn", "artstein20_cn",
               "dint20_timeopt", "duffing20_ms_rk4", "dint20_ms_rk4", "dint20_ms_euler",
-              "linear20_cn", "linear20_timeopt", "linear20_ms_rk4", "linear3_20_cn", "linear3_20_timeopt", "linear3_20_ms_rk4"}
+              "linear20_cn", "linear20_timeopt", "linear20_ms_rk4", "linear3_20_cn", "linear3_20_timeopt", "linear3_20_ms_rk4",
+              "tint20_cn", "tint20_timeopt", "qint20_cn"}
 # FD-noise floor of the reference algorithm per case: trajectory tolerance for 10 LM iterations
 TRAJ_TOL = {"unicycle30_timeopt": 1e-3, "cartpole40_rk4": 5e-3, "quadrotor12_cn": 1e-3, "cartpole20_terminal_ball": 5e-3,
             "quadrotor8_terminal_ball": 1e-3, "pendulum20_cn": 1e-3, "cartpole20_cn_fd_grid": 5e-3, "unicycle20_cn_fixed_dt": 1e-3,
@@ -28,7 +29,7 @@ TRAJ_TOL = {"unicycle30_timeopt": 1e-3, "cartpole40_rk4": 5e-3, "quadrotor12_cn"
             # rational / bilinear right-hand sides: values and Jacobians bit-exact, the solve meets the FD-noise floor within 10 iterations
             "rocket20_cn": 2e-5, "rocket20_timeopt": 2e-5, "toy20_cn": 2e-5,
             "pendulum20_timeopt": 1e-3, "cartpole20_timeopt": 5e-3, "cartpole20_forward": 5e-3, "cartpole20_ms_euler": 5e-3,
-            "unicycle20_ms_rk4": 1e-3, "duffing20_ms_rk4": 1e-5, "linear20_timeopt": 2e-5}  # time-optimal: polynomial values/Jacobians (bit-exact), but the free dt makes the solve noise-sensitive
+            "unicycle20_ms_rk4": 1e-3, "duffing20_ms_rk4": 1e-5, "linear20_timeopt": 2e-5, "tint20_timeopt": 2e-5}  # time-optimal: polynomial values/Jacobians (bit-exact), but the free dt makes the solve noise-sensitive
 
 
 @pytest.mark.parametrize("name", list(cases.CASES))
