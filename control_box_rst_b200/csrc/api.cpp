@@ -45,7 +45,8 @@ const KernelSet* findKernels(int dynamics, int defect, int vt)
 #else
     const KernelSet* (*tables[])(int*) = {kernelTableVdpCn,       kernelTableVdpFd,    kernelTableVdpMs,   kernelTableOscillators,
                                           kernelTableCartPole,    kernelTableUnicycle, kernelTableQuadrotor, kernelTableBenchmarkSystems,
-                                          kernelTableCombosFd,    kernelTableCombosMs, kernelTableLinear};
+                                          kernelTableCombosFd,    kernelTableCombosMs, kernelTableLinear,   kernelTableLinear4,
+                                          kernelTableIntegrators};
 #endif
     for (auto t : tables)
     {

@@ -1,5 +1,5 @@
-// Kernel instantiations: LinearStateSpaceModel with 3 and 4 states on the fixed-dt finite-difference grid, the time-optimal
-// non-uniform grid and the multiple-shooting grid (RK4); SerialIntegratorSystem of dimension 3 (also time-optimal) and 4.
+// Kernel instantiations: LinearStateSpaceModel with 3 states on the fixed-dt finite-difference grid, the time-optimal
+// non-uniform grid and the multiple-shooting grid (RK4).
 #include "lm_kernels.cuh"
 
 namespace b200sqp {
@@ -10,13 +10,6 @@ const KernelSet* kernelTableLinear(int* count)
         B200SQP_KERNEL_ENTRY(LinearStateSpace3x1, DEFECT_CRANK_NICOLSON, 0, 4),
         B200SQP_KERNEL_ENTRY(LinearStateSpace3x1, DEFECT_CRANK_NICOLSON, 1, 4),
         B200SQP_KERNEL_ENTRY(LinearStateSpace3x1, DEFECT_RK4, 0, 4),
-        B200SQP_KERNEL_ENTRY(LinearStateSpace4x1, DEFECT_CRANK_NICOLSON, 0, 4),
-        B200SQP_KERNEL_ENTRY(LinearStateSpace4x1, DEFECT_RK4, 0, 4),
-        B200SQP_KERNEL_ENTRY(LinearStateSpace4x2, DEFECT_CRANK_NICOLSON, 0, 4),
-        B200SQP_KERNEL_ENTRY(LinearStateSpace4x2, DEFECT_CRANK_NICOLSON, 1, 4),
-        B200SQP_KERNEL_ENTRY(TripleIntegrator, DEFECT_CRANK_NICOLSON, 0, 4),
-        B200SQP_KERNEL_ENTRY(TripleIntegrator, DEFECT_CRANK_NICOLSON, 1, 4),
-        B200SQP_KERNEL_ENTRY(QuadIntegrator, DEFECT_CRANK_NICOLSON, 0, 4),
     };
     *count = (int)(sizeof(table) / sizeof(table[0]));
     return table;

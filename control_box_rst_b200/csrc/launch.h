@@ -35,6 +35,8 @@ const KernelSet* kernelTableBenchmarkSystems(int* count);
 const KernelSet* kernelTableCombosFd(int* count);
 const KernelSet* kernelTableCombosMs(int* count);
 const KernelSet* kernelTableLinear(int* count);
+const KernelSet* kernelTableLinear4(int* count);
+const KernelSet* kernelTableIntegrators(int* count);
 
 // layout helpers (util_kernels.cu); all arrays device pointers
 // params [B][n] (reference order)  <->  z (block order, tiled instance-minor [tile][K*NB][32]); pinned slots (ref index -1) are left alone
