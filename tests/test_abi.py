@@ -90,3 +90,25 @@ def test_product_never_imports_the_oracle():
             if f.endswith((".py", ".cpp", ".cu", ".cuh", ".h")):
                 text = open(os.path.join(dirpath, f), errors="ignore").read()
                 assert "sqp_oracle" not in text and "corbo_ref" not in text and "import oracle" not in text and "from oracle" not in text, f
+
+
+def test_every_golden_combination_is_compiled_into_the_library():
+    """b200sqp_create looks the (dynamics, defect, grid) combination up in the kernel tables before it asks for a device: without a
+    GPU a compiled-in combination answers B200SQP_ERR_NO_DEVICE, one missing from kernels_*.cu B200SQP_ERR_UNSUPPORTED.  Every case
+    of the golden table must be compiled in; a combination outside the tables must not be."""
+    if solver.device_available():
+        pytest.skip("a GPU is present (the GPU parity suite creates a handle for every case)")
+    import sys
+
+    sys.path.insert(0, os.path.join(ROOT, "tests", "golden"))
+    import cases
+
+    for name, (make, _, _) in cases.CASES.items():
+        with pytest.raises(solver.B200SqpError) as e:
+            solver.BatchedLevenbergMarquardt(make(), 4)
+        assert e.value.code == abi.ERR_NO_DEVICE, name
+    missing = problems.quadrotor(8)
+    missing.grid = abi.GRID_MULTIPLE_SHOOTING  # a shooting quadrotor is a valid structure but not in the kernel tables
+    with pytest.raises(solver.B200SqpError) as e:
+        solver.BatchedLevenbergMarquardt(missing, 4)
+    assert e.value.code == abi.ERR_UNSUPPORTED
