@@ -12,7 +12,10 @@ from control_box_rst_b200 import problems
     (lambda: problems.van_der_pol(13, collocation=abi.COLL_MIDPOINT), (2.0, 5.0, 7.0), 1e-5),
     (lambda: problems.unicycle_time_optimal(20), (2.0, 2.0, 2.0), 1e-3),
     (lambda: problems.cart_pole_shooting(25), (10.0, 10.0, 10.0), 5e-3),
-], ids=["vdp50", "vdp13_midpoint", "unicycle20", "cartpole25"])
+    (lambda: problems.free_space_rocket_time_optimal(16), (2.0, 3.0, 4.0), 1e-4),
+    (lambda: problems.make_ocp(grid=abi.GRID_MULTIPLE_SHOOTING, dynamics=abi.DYN_TOY_EXAMPLE, n_grid=15, dt=0.05, q=(1, 1), r=(0.1,), qf=(1, 1),
+                               u_lb=(-2.0,), u_ub=(2.0,), dyn_params=(0.3,), integrator=abi.INT_EULER), (2.0, 2.0, 2.0), 1e-4),
+], ids=["vdp50", "vdp13_midpoint", "unicycle20", "cartpole25", "rocket16_timeopt", "toy15_ms_euler"])
 def test_oracle_matches_compiled_reference(oracle, reference, make, weights, tol):
     ocp = make()
     B = 24
@@ -21,7 +24,7 @@ def test_oracle_matches_compiled_reference(oracle, reference, make, weights, tol
     v_r, J_r, P_r, a_r = reference.evaluate(ocp, x0[0], xref[0], None, weights)
     v_o, J_o, P_o, a_o = oracle.evaluate(ocp, x0[0], xref[0], None, weights)
     assert np.array_equal(P_r, P_o)
-    if ocp.dynamics == abi.DYN_VAN_DER_POL:
+    if ocp.dynamics in (abi.DYN_VAN_DER_POL, abi.DYN_FREE_SPACE_ROCKET, abi.DYN_TOY_EXAMPLE):  # + - * / only
         assert np.array_equal(v_r, v_o) and np.array_equal(J_r, J_o) and np.array_equal(a_r, a_o)
     else:
         np.testing.assert_allclose(v_o, v_r, rtol=1e-13, atol=1e-13)
