@@ -47,3 +47,59 @@ def test_weight_adaptation_and_warm_start_sequence(oracle, reference):
     tr_o = oracle.trace(ocp, opts, x0)
     assert [e[0] for e in tr_r["events"]] == [e[0] for e in tr_o["events"]]
     np.testing.assert_allclose(tr_o["params"], tr_r["params"], rtol=0, atol=1e-6)
+
+
+def _random_ocp(rng):
+    """A random member of the supported family: model, grid, defect, horizon, step, weights of the cost, bounds, goal handling."""
+    poly = [(abi.DYN_VAN_DER_POL, (1.0 + rng.uniform(-0.5, 0.5),)), (abi.DYN_DUFFING, (1.0, -1.0, 1.0)), (abi.DYN_TOY_EXAMPLE, (rng.uniform(0.2, 0.8),)),
+            (abi.DYN_ARTSTEINS_CIRCLE, ()), (abi.DYN_DOUBLE_INTEGRATOR, (rng.uniform(0.5, 2.0),)), (abi.DYN_TRIPLE_INTEGRATOR, (1.5,)),
+            (abi.DYN_LINEAR_2X1, (-0.3, -2.0, 1.1, -0.5, 0.2, 1.5)), (abi.DYN_LINEAR_3X1, (-0.5, 0.2, -0.1, 1.0, -0.4, 0.3, 0.1, 1.2, -0.8, 0.3, -0.2, 1.0))]
+    dynamics, params = poly[rng.integers(len(poly))]
+    nx, nu = abi.DYN_DIMS[dynamics]
+    grid = int(rng.integers(3))
+    n_grid = int(rng.integers(3, 24))
+    dt = float(rng.choice([0.05, 0.1, 0.2]))
+    kw = dict(grid=grid, dynamics=dynamics, n_grid=n_grid, dt=dt, dyn_params=params, u_lb=(-1.0,) * nu, u_ub=(1.5,) * nu)
+    if grid == abi.GRID_FD_NONUNIFORM_VARDT:
+        kw.update(stage_cost=abi.COST_MINIMUM_TIME_LSQ, xf_fixed=(1,) * nx, dt_lb=0.0, dt_ub=1.0, collocation=int(rng.integers(4)))
+    else:
+        kw.update(q=tuple(rng.uniform(0.5, 2.0, nx)), r=tuple(rng.uniform(0.05, 0.5, nu)))
+        if rng.random() < 0.7:
+            kw.update(qf=tuple(rng.uniform(0.5, 5.0, nx)))
+        if rng.random() < 0.4:
+            kw.update(x_lb=(-3.0,) * nx, x_ub=(2.5,) * nx)
+        if grid == abi.GRID_FD_UNIFORM:
+            kw.update(collocation=int(rng.integers(4)))
+            if rng.random() < 0.3:
+                kw.update(xf_fixed=tuple(int(b) for b in rng.integers(0, 2, nx)))
+        else:
+            kw.update(integrator=int(rng.choice([abi.INT_EULER, abi.INT_RK4])))
+    return problems.make_ocp(**kw)
+
+
+@pytest.mark.parametrize("seed", range(16))
+def test_random_structures_match_compiled_reference(oracle, reference, seed):
+    """Seeded random OCPs over the polynomial / rational models: dimensions, vertex and edge indices, the initial guess, the value
+    vector, the combined Jacobian (pattern and values) and the parameter drift of the in-place differences equal the compiled
+    reference's bit for bit, at a perturbed point with random penalty weights."""
+    rng = np.random.default_rng(1000 + seed)
+    ocp = _random_ocp(rng)
+    d_r, d_o = reference.dims(ocp), oracle.dims(ocp)
+    for f in ("n_params", "m_lsq", "m_eq", "m_ineq", "m_bounds", "nnz_jacobian", "nnz_hessian_upper", "algorithmic_bytes_per_iteration"):
+        assert getattr(d_r, f) == getattr(d_o, f), f
+    for a, b in zip(reference.vertex_indices(ocp), oracle.vertex_indices(ocp)):
+        assert np.array_equal(a, b)
+    for cat in range(3):
+        assert np.array_equal(reference.edge_table(ocp, cat), oracle.edge_table(ocp, cat))
+    x0, xref = problems.instance_data(ocp, 1, seed=seed)
+    p_r, p_o = reference.initial_params(ocp, x0[0], xref[0]), oracle.initial_params(ocp, x0[0], xref[0])
+    np.testing.assert_allclose(p_o, p_r, rtol=0, atol=1e-15)
+    p = p_r + rng.uniform(-0.3, 0.3, p_r.shape)
+    if ocp.grid == abi.GRID_FD_NONUNIFORM_VARDT:
+        dt_idx = reference.vertex_indices(ocp)[2]
+        p[dt_idx] = np.abs(p[dt_idx]) + 0.05
+    weights = tuple(rng.uniform(1.0, 10.0, 3))
+    v_r, J_r, P_r, a_r = reference.evaluate(ocp, x0[0], xref[0], p, weights)
+    v_o, J_o, P_o, a_o = oracle.evaluate(ocp, x0[0], xref[0], p, weights)
+    assert np.array_equal(P_r, P_o)
+    assert np.array_equal(v_r, v_o) and np.array_equal(J_r, J_o) and np.array_equal(a_r, a_o)
