@@ -212,18 +212,11 @@ def main_reference(args):
     return 0
 
 
-class _CudaArray:
-    """Zero-copy view of a raw device pointer for torch.as_tensor (CUDA array interface v2)."""
-
-    def __init__(self, ptr, shape, typestr):
-        self.__cuda_array_interface__ = {"shape": shape, "typestr": typestr, "data": (int(ptr), False), "version": 2}
-
-
 def main_b200(args):
     import torch
     import torch.distributed as dist
 
-    from control_box_rst_b200 import solver
+    from control_box_rst_b200 import distributed, solver
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -250,26 +243,16 @@ def main_b200(args):
     x0, xref = problems.instance_data(ocp, B, seed=1234 + args.config, offset=rank * B)
     lm.set_problem_data(x0, xref)
     ptrs = lm.device_pointers()
-    chi2_local = torch.as_tensor(_CudaArray(ptrs["chi2"], (B,), "<f8"), device=f"cuda:{local_rank}")
+    chi2_local = distributed.device_view(ptrs["chi2"], B, f"cuda:{local_rank}")
     chi2_all = torch.empty(B * world, dtype=torch.float64, device=f"cuda:{local_rank}") if world > 1 else None
     flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=f"cuda:{local_rank}")  # > 126 MB L2
     rendezvous = torch.zeros(1, dtype=torch.float32, device=f"cuda:{local_rank}")
 
-    # the single stop-test exchange.  p2p: NCCL/torch.distributed only carries the 64-byte IPC handles at
-    # set-up; per step the LM kernel's epilogue stores chi2 into every rank's gather buffer and b200sqp_peer_wait (stream-ordered,
-    # bounded) returns when all ranks' values have arrived.  nccl: one all_gather_into_tensor after the solve.
-    use_p2p = world > 1 and args.collective == "p2p"
-    if use_p2p:
-        handles = [None] * world
-        dist.all_gather_object(handles, lm.peer_export(world, rank))
-        lm.peer_attach(handles)
-        dist.barrier()
-
-    def exchange():
-        if use_p2p:
-            lm.peer_wait()
-        elif world > 1:
-            dist.all_gather_into_tensor(chi2_all, chi2_local)
+    # the single stop-test exchange: control_box_rst_b200.distributed.StopTestExchange -- fused into the LM kernel
+    # over NVLink peer memory (p2p) or one NCCL all-gather after the solve (nccl)
+    exch = distributed.StopTestExchange(lm, mode=args.collective, device=torch.device("cuda", local_rank))
+    use_p2p = exch.mode == "p2p"
+    exchange = exch.wait
 
     def device_step():
         lm.initialize_trajectories()
@@ -304,7 +287,7 @@ def main_b200(args):
     barrier()
     if use_p2p:
         # the fused gather must deliver exactly what an NCCL all-gather of the same solve delivers
-        gathered = torch.as_tensor(_CudaArray(lm.peer_gathered_ptr(), (B * world,), "<f8"), device=f"cuda:{local_rank}").clone()
+        gathered = exch.gathered().clone()
         dist.all_gather_into_tensor(chi2_all, chi2_local)
         torch.cuda.synchronize()
         if not torch.equal(gathered, chi2_all):
@@ -436,10 +419,9 @@ def main_b200(args):
                                     "sample": f"{args.cpu_sample} instances of the same workload, {dt:.2f} s wall on {cores} threads"}
         emit(line)
     if use_p2p:
-        if lm.peer_timed_out():
+        if exch.timed_out():
             raise SystemExit("bench.py: a peer never arrived in b200sqp_peer_wait (2 s bound)")
-        barrier()  # nobody unmaps while a peer may still store
-        lm.peer_detach()
+        exch.close()
     lm.clear()
     if world > 1:
         dist.destroy_process_group()

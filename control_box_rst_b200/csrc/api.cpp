@@ -74,6 +74,7 @@ struct b200sqp_solver
     int64_t launches = 0;
     bool weights_initialised = false;
     int threads_per_instance = 0;  // 0 = heuristic (launchSolve)
+    int solve_flags = 0;           // SOLVE_* (launch.h)
     // staging
     double* d_params = nullptr;   // [B][n]
     double* d_x0_host_order = nullptr, *d_xref_host_order = nullptr;  // [B][nx]
@@ -609,7 +610,7 @@ int b200sqp_solve_async(b200sqp_handle h, const b200sqp_lm_options* opts, int32_
     }
     else
     {
-        h->kernels->solve(h->P, h->st, opts->iterations, h->threads_per_instance, h->stream);
+        h->kernels->solve(h->P, h->st, opts->iterations, h->threads_per_instance, h->solve_flags, h->stream);
         h->launches += 1;
     }
     CUDA_TRY(cudaGetLastError());
@@ -1015,6 +1016,13 @@ int b200sqp_set_threads_per_instance(b200sqp_handle h, int32_t threads)
     return B200SQP_OK;
 }
 
+int b200sqp_set_feature_set(b200sqp_handle h, int32_t general)
+{
+    if (!h) return fail(B200SQP_ERR_INVALID, "null handle");
+    h->solve_flags = general ? (h->solve_flags | SOLVE_FORCE_GENERAL_FEATURES) : (h->solve_flags & ~SOLVE_FORCE_GENERAL_FEATURES);
+    return B200SQP_OK;
+}
+
 static size_t peerChi2Bytes(b200sqp_handle h) { return sizeof(double) * 2 * (size_t)h->peer_world * h->B; }
 
 int b200sqp_peer_export(b200sqp_handle h, int32_t world, int32_t rank, void* ipc_handle_out)
@@ -1040,6 +1048,8 @@ int b200sqp_peer_attach(b200sqp_handle h, const void* ipc_handles)
     int rc = checkHandle(h);
     if (rc) return rc;
     if (!ipc_handles || !h->peer_local) return fail(B200SQP_ERR_INVALID, "call b200sqp_peer_export first");
+    // a second attach would leak the IPC mappings and reset the solve count while the peers' arrival counters keep counting
+    if (h->peer_attached) return fail(B200SQP_ERR_INVALID, "already attached: b200sqp_peer_detach first");
     const size_t chi2_bytes = peerChi2Bytes(h);
     for (int r = 0; r < h->peer_world; ++r)
     {

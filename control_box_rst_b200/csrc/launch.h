@@ -9,11 +9,13 @@ struct DeviceOcp;
 struct DeviceState;
 struct PipeArrays;
 
+enum { SOLVE_FORCE_GENERAL_FEATURES = 1 };  // flags of KernelSet::solve
+
 struct KernelSet
 {
     int dynamics, defect, vt, nx, nu;
     int max_threads;  // widest cooperating-thread variant compiled for this combination
-    void (*solve)(const DeviceOcp&, const DeviceState&, int iterations, int threads_per_instance /*0 = auto*/, cudaStream_t);
+    void (*solve)(const DeviceOcp&, const DeviceState&, int iterations, int threads_per_instance /*0 = auto*/, int flags /*SOLVE_**/, cudaStream_t);
     void (*evaluate)(const DeviceOcp&, const DeviceState&, double* values, double* jac, const int* value_rows, const int* jac_pos, int v_count,
                      int j_count, cudaStream_t);
     // warp-cooperative pipeline for large stage blocks (lm_pipeline.cuh) or nullptr; blocks the host, false = pass bound hit

@@ -400,7 +400,7 @@ void launchSolveT(const DeviceOcp& P, const DeviceState& st, int iterations, int
 }
 
 template <class M, int DEFECT, int VT, int MAXT>
-void launchSolve(const DeviceOcp& P, const DeviceState& st, int iterations, int threads_per_instance, cudaStream_t stream)
+void launchSolve(const DeviceOcp& P, const DeviceState& st, int iterations, int threads_per_instance, int flags, cudaStream_t stream)
 {
     const int blocks = (P.B + 31) / 32;
     int T            = threads_per_instance;
@@ -415,6 +415,7 @@ void launchSolve(const DeviceOcp& P, const DeviceState& st, int iterations, int 
     // lean feature set: quadratic lsq stage cost, no state bounds, no pinned goal components, no final-stage constraint
     bool lean = P.final_constraint == 0 && P.stage_cost == B200SQP_COST_QUADRATIC_LSQ;
     for (int j = 0; j < M::NX; ++j) lean = lean && !P.x_bounded[j] && !P.xf_fixed[j];
+    if (flags & SOLVE_FORCE_GENERAL_FEATURES) lean = false;  // b200sqp_set_feature_set: parity tests run both variants on one structure
     if (lean)
         launchSolveT<M, DEFECT, VT, MAXT, FeatLean>(P, st, iterations, T, blocks, stream);
     else

@@ -172,7 +172,9 @@ int b200sqp_jacobian_pattern(const b200sqp_ocp* ocp, int32_t* col_ptr /*[n+1]*/,
 
 /* ---- per-instance data ------------------------------------------------------------------------------------------------- */
 /* x0: [batch*nx] measured start states (FullDiscretizationGridBase::update :101); xref: [batch*nx] static state reference or NULL
- * (then zero / xf = 0).  Host pointers. */
+ * (then zero / xf = 0).  Host pointers.  Asynchronous on the handle's stream: pageable buffers are staged before the call returns,
+ * PINNED buffers (cudaHostAlloc / cudaHostRegister) are read in place by a kernel and must stay valid and unchanged until
+ * b200sqp_synchronize or the next blocking call on the handle (b200sqp_solve / _step / _mpc_step / _get_*). */
 int b200sqp_set_problem_data(b200sqp_handle h, const double* x0, const double* xref);
 /* FullDiscretizationGridBase::initializeSequences (full_discretization_grid_base.cpp:134-179): linear x0 -> xref interpolation,
  * u = 0, dt = dt_ref, on the device. */
@@ -286,6 +288,7 @@ int b200sqp_device_pointers(b200sqp_handle h, void** chi2, void** status, void**
  * Equal `batch` on all ranks.  world <= 8. */
 #define B200SQP_IPC_HANDLE_BYTES 64
 int b200sqp_peer_export(b200sqp_handle h, int32_t world, int32_t rank, void* ipc_handle_out /*[64]*/);
+/* B200SQP_ERR_INVALID when already attached (detach first) */
 int b200sqp_peer_attach(b200sqp_handle h, const void* ipc_handles /*[world*64], rank order; own entry ignored*/);
 /* enqueue the bounded wait for the gathered chi2 of the last solve; returns B200SQP_ERR_CUDA from a later call if it timed out */
 int b200sqp_peer_wait(b200sqp_handle h);
@@ -297,6 +300,10 @@ int b200sqp_peer_detach(b200sqp_handle h);
 /* tuning knob: cooperating threads per instance in the LM kernel (1, 2, 4, 8; 0 = choose from the batch size).  Structures with
  * large stage blocks (quadrotor) run a warp-per-instance pipeline instead of the fused kernel; -1 forces the fused kernel there. */
 int b200sqp_set_threads_per_instance(b200sqp_handle h, int32_t threads);
+/* test knob: the LM kernel is compiled per structure family in two feature sets -- the general one (state bounds, partially fixed goal,
+ * final-stage constraint, any stage cost) and a lean one for structures that need none of these (picked automatically).  general = 1
+ * forces the general set on a lean-eligible structure so that parity tests can run both variants on the same problem; 0 = automatic. */
+int b200sqp_set_feature_set(b200sqp_handle h, int32_t general);
 /* measurement aid: when enabled, thread 0 of every thread block of the LM kernel accumulates clock64() per phase; get returns the
  * mean over thread blocks of the last solve, mean_cycles[4] = {linearise (a3/a4/a13), factor+solve (a14), trial values (a2/a12),
  * LM control (a1)} in SM clock cycles.  Off by default (the kernel then only tests one pointer). */
