@@ -45,6 +45,7 @@ def parse_args():
     ap.add_argument("--batch", type=int, default=4096, help="instances per GPU (north_star target batch; weak scaling)")
     ap.add_argument("--cpu-sample", type=int, default=4096, help="instances of the same workload timed on the host cores")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-other-configs", action="store_true", help="skip the short runs of configs[2..4] appended to the default N=1 line")
     ap.add_argument("--collective", default="p2p", choices=["p2p", "nccl"],
                     help="stop-test exchange at N>1: chi2 stored into every rank's gather buffer by the LM kernel itself over NVLink peer "
                          "memory (p2p, default) or a separate NCCL all-gather after the solve (nccl)")
@@ -173,43 +174,157 @@ def cpu_checker():
 
 
 def run_cpu(ocp, opts, sample, seed):
+    """-> dict: the reference's CPU path on `sample` instances over all host threads.  `value` follows SURVEY.md section 8d: iterations
+    per second timed around the solver call (`_solver->solve`, summed per thread -> x threads / sum), fresh solver objects per instance;
+    `wall_value` is the same batch by the wall clock including object construction and the grid update."""
     checker, kind = cpu_checker()
     cores = os.cpu_count() or 1
     x0, xref = problems.instance_data(ocp, sample, seed=seed)
     t0 = time.perf_counter()
-    checker.solve_batch(ocp, opts, x0, xref, threads=cores)
-    dt = time.perf_counter() - t0
-    return sample * opts.iterations / dt, dt, kind, cores
+    _, _, _, secs = checker.solve_batch(ocp, opts, x0, xref, threads=cores)
+    wall = time.perf_counter() - t0
+    threads = min(cores, sample)
+    solve_wall = float(secs[1]) / threads if secs[1] > 0 else wall  # per-thread sums run side by side
+    return {"value": sample * opts.iterations / solve_wall, "wall_value": sample * opts.iterations / wall, "wall_s": wall,
+            "solver_s_per_thread": solve_wall, "kind": kind, "cores": cores, "sample": sample}
+
+
+def b200_config_keys(args, ocp, n_params, world):
+    return {"workload": workload_name(args.config, ocp, args.batch, problems.config(args.config)[1]["iterations"]),
+            "instances_total": args.batch * world, "n_grid": ocp.n_grid, "n_params": n_params}
 
 
 def main_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return 0
+    from control_box_rst_b200 import solver
+
     ocp, kw, _ = problems.config(args.config)
     opts = abi.LmOptions.defaults(iterations=kw["iterations"], weights=kw["weights"])
-    sample = min(args.cpu_sample, 2048)
+    sample = args.batch if args.config == 1 else min(args.batch, args.cpu_sample)  # the headline workload: every instance the GPU arm solves per GPU
     for _ in range(max(0, min(args.warmup, 1))):
         run_cpu(ocp, opts, 64, seed=99)
-    times, kind, cores = [], "port", 1
+    solver_s, wall_s, r = 0.0, 0.0, None
     for s in range(args.steps):
-        v, dt, kind, cores = run_cpu(ocp, opts, sample, seed=1234 + args.config)
-        times.append(dt)
-    total = sum(times)
-    value = sample * opts.iterations * args.steps / total
+        r = run_cpu(ocp, opts, sample, seed=1234 + args.config)
+        solver_s += r["solver_s_per_thread"]
+        wall_s += r["wall_s"]
+    value = sample * opts.iterations * args.steps / solver_s
+    cfg = b200_config_keys(args, ocp, solver.dims_of(ocp).n_params, 1)
+    cfg["note"] = ("reference CPU path (LevenbergMarquardtSparse through its hypergraph problem), fresh solver objects per instance; timed around "
+                   "the solver call as SURVEY.md section 8d defines the metric; wall_value includes object construction and the grid update")
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
-        "ms_per_step": 1e3 * total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
-        "data": "synthetic",
-        "config": {"workload": workload_name(args.config, ocp, args.batch, opts.iterations),
-                   "note": "reference CPU path (LevenbergMarquardtSparse through its hypergraph problem), fresh solver objects per instance"},
-        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": kind,
-                         "sample": f"{sample} instances of the workload per step, {args.steps} steps, std::thread static partition"},
+        "ms_per_step": 1e3 * solver_s / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+        "data": "synthetic", "config": cfg,
+        "wall_value": sample * opts.iterations * args.steps / wall_s, "wall_ms_per_step": 1e3 * wall_s / args.steps,
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": r["cores"], "kind": r["kind"],
+                         "sample": f"{sample} instances of the workload per step, {args.steps} steps, std::thread static partition, solver-call time"},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
     emit(line)
     return 0
+
+
+CPU_SAMPLE_CAP = {0: 4096, 1: 4096, 2: 1024, 3: 256, 4: 128}  # instances of the workload the host cores solve for cpu_baseline (seconds of work)
+
+
+def cpu_baseline_entry(r):
+    return {"value": r["value"], "unit": UNIT, "cores": r["cores"], "kind": r["kind"], "wall_value": r["wall_value"],
+            "sample": f"{r['sample']} instances of the same workload on {r['cores']} threads: {r['solver_s_per_thread']:.2f} s inside the solver call per "
+                      f"thread, {r['wall_s']:.2f} s wall with object construction"}
+
+
+def csrc_hash():
+    """sha256 over the kernel sources and build flags: identifies the binary a profile was captured from (the .so itself is not in git)"""
+    import hashlib
+
+    h = hashlib.sha256()
+    d = os.path.join(ROOT, "control_box_rst_b200", "csrc")
+    for name in sorted(os.listdir(d)):
+        if name.endswith((".cu", ".cuh", ".h", ".cpp")) or name == "Makefile":
+            h.update(name.encode())
+            h.update(open(os.path.join(d, name), "rb").read())
+    return h.hexdigest()[:16]
+
+
+def measured_traffic(key):
+    """DRAM bytes of one launch of the dominant kernel from the `ncu --set full` capture in profiles/traffic.json -- only if the capture
+    was taken from THIS source tree (the entry carries the hash of the kernel sources; a stale capture reads as null + the reason)."""
+    try:
+        t_all = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
+        if key not in t_all:
+            return None, "no ncu capture of this workload in profiles/traffic.json"
+        e = t_all[key]
+        if e.get("csrc_sha256") != csrc_hash():
+            return None, f"stale: profiles/traffic.json was captured from kernel sources {e.get('csrc_sha256')}, this tree is {csrc_hash()}"
+        return e["dram_bytes_read"] + e["dram_bytes_write"], e["source"]
+    except (OSError, ValueError, KeyError) as exc:
+        return None, f"profiles/traffic.json unreadable: {exc}"
+
+
+def fp64_roofline(ocp, dims, B, iterations, kernel_ms, fp64_peak):
+    """SURVEY.md section 8d "also report the fp64 FMA bound": algorithmic flops of the launch (control_box_rst_b200/roofline.py) over the
+    kernel's time, against the fp64 FMA throughput measured live on this GPU (b200sqp_measure_fp64_peak)."""
+    from control_box_rst_b200 import roofline
+
+    flops = roofline.flops_per_iteration(ocp, dims) * B * iterations
+    achieved = flops / (kernel_ms * 1e-3) / 1e12
+    return {"bound": "fp64_fma", "achieved": achieved, "peak": fp64_peak, "unit": "TFLOP/s", "frac": achieved / fp64_peak if fp64_peak else None,
+            "flops_per_iteration": roofline.flops_per_iteration(ocp, dims), "algorithmic_flops_per_launch": flops,
+            "peak_source": "b200sqp_measure_fp64_peak: independent DFMA chains on every SM, best of 3 launches, measured in this run",
+            "note": "binding roof of the fused kernel (J, H and L never reach DRAM); one count per +,-,*,/ and libm call, rejected steps not counted"}
+
+
+def other_configs(device, stream, hbm_peak, fp64_peak, with_cpu):
+    """BASELINE.json configs[2..4] at their full batch on this GPU, a few steps each (parity-test cases, not bench lines: recorded so
+    that the driver's run carries their throughput, roofline fractions and CPU baseline too).  Same timing rules as the main line."""
+    import torch
+
+    from control_box_rst_b200 import solver
+
+    out = {}
+    for cfg in (2, 3, 4):
+        try:
+            ocp, kw, B = problems.config(cfg)
+            iterations = kw["iterations"]
+            lm = solver.BatchedLevenbergMarquardt(ocp, B, device=device)
+            lm.setIterations(iterations)
+            lm.setPenaltyWeights(*kw["weights"])
+            lm.set_stream(stream.cuda_stream)
+            x0, xref = problems.instance_data(ocp, B, seed=1234 + cfg)
+            lm.set_problem_data(x0, xref)
+            flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=f"cuda:{device}")
+            steps, total_ms, kernel_ms = (3 if cfg == 4 else 5), 0.0, 0.0
+            for it in range(steps + 1):
+                flush.zero_()
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record(stream)
+                lm.initialize_trajectories()
+                lm.solve(new_run=True, fetch=False)
+                e1.record(stream)
+                e1.synchronize()
+                if it > 0:  # the first step is the warm-up
+                    total_ms += e0.elapsed_time(e1)
+                    kernel_ms += lm.last_solve_ms()
+            alg = lm.dims.algorithmic_bytes_per_iteration * B * iterations
+            achieved = alg / (kernel_ms / steps * 1e-3) / 1e9
+            entry = {"workload": workload_name(cfg, ocp, B, iterations), "value": B * iterations * steps / (total_ms * 1e-3), "unit": UNIT,
+                     "steps": steps, "ms_per_step": total_ms / steps, "kernel_ms": kernel_ms / steps,
+                     "roofline": {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak},
+                     "roofline_fp64": fp64_roofline(ocp, lm.dims, B, iterations, kernel_ms / steps, fp64_peak)}
+            lm.clear()
+            del flush
+            torch.cuda.empty_cache()
+            if with_cpu:
+                opts = abi.LmOptions.defaults(iterations=iterations, weights=kw["weights"])
+                entry["cpu_baseline"] = cpu_baseline_entry(run_cpu(ocp, opts, CPU_SAMPLE_CAP[cfg], seed=1234 + cfg))
+            out[str(cfg)] = entry
+        except Exception as exc:  # the main line must not depend on the extra configurations
+            out[str(cfg)] = {"error": f"{type(exc).__name__}: {exc}"}
+    return out
 
 
 def main_b200(args):
@@ -371,6 +486,7 @@ def main_b200(args):
                        "h2d_bytes_per_call": h2d, "d2h_bytes_per_call": int(h_ul.numel() + h_xl.numel()) * 8,
                        "note": "b200sqp_closed_loop: moving-horizon warm start + solve + RK4 plant step per MPC step, all on the device"}
 
+    fp64_peak = solver.measure_fp64_peak(local_rank) if rank == 0 else None  # live microbenchmark (b200sqp_measure_fp64_peak), after the timed regions
     if rank == 0:
         peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
         if os.path.exists(peaks_path):
@@ -378,23 +494,13 @@ def main_b200(args):
         else:
             peak, peak_src = 6650.0, "B200_PROFILING.md fallback"
         alg_bytes = lm.dims.algorithmic_bytes_per_iteration * B * iterations  # per launch of the LM kernel
-        # DRAM traffic of one launch from the committed `ncu --set full` capture of the same workload (profiles/traffic.json)
-        traffic, traffic_src = None, None
-        try:
-            t_all = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
-            key = f"{workload_name(args.config, ocp, B, iterations).split('_per_gpu')[0]}"
-            if key in t_all:
-                traffic = t_all[key]["dram_bytes_read"] + t_all[key]["dram_bytes_write"]
-                traffic_src = t_all[key]["source"]
-        except (OSError, ValueError, KeyError):
-            pass
+        traffic, traffic_src = measured_traffic(workload_name(args.config, ocp, B, iterations).split("_per_gpu")[0])
         achieved = alg_bytes / (kernel_ms / args.steps * 1e-3) / 1e9
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": n_gpus, "steps": args.steps, "warmup": max(args.warmup, 3),
             "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
             "data": "synthetic",
-            "config": {"workload": workload_name(args.config, ocp, B, iterations), "instances_total": B * world, "n_grid": ocp.n_grid,
-                       "n_params": n, "parallelism": (f"instance-sharded x{world}, stop-test gather of chi2 fused into the LM kernel over NVLink peer memory"
+            "config": {**b200_config_keys(args, ocp, n, world), "parallelism": (f"instance-sharded x{world}, stop-test gather of chi2 fused into the LM kernel over NVLink peer memory"
                                        if use_p2p else f"instance-sharded x{world}, one NCCL chi2 all-gather per step") if world > 1 else "single GPU",
                        "timing": "CUDA events per step on the launch stream, L2 flushed (256 MiB memset) between steps"
                                  + (", ranks rendezvous on the device before each timed step" if world > 1 else "") + ", max over ranks",
@@ -409,14 +515,18 @@ def main_b200(args):
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "traffic_source": traffic_src,
                          "kernel": "lmSolve", "kernel_ms": kernel_ms / args.steps, "algorithmic_bytes_per_launch": alg_bytes,
                          "peak_source": peak_src},
+            "roofline_fp64": fp64_roofline(ocp, lm.dims, B, iterations, kernel_ms / args.steps, fp64_peak),
             "lm": {"inner_passes_per_instance": float(stats["inner_passes"].mean()), "rejects_per_instance": float(stats["rejects"].mean()),
                    "relinearizations_per_instance": float(stats["relinearizations"].mean())},
         }
         if n_gpus == 1 and not args.no_cpu_baseline:
             opts = abi.LmOptions.defaults(iterations=iterations, weights=kw["weights"])
-            v, dt, kind, cores = run_cpu(ocp, opts, args.cpu_sample, seed=1234 + args.config)
-            line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": cores, "kind": kind,
-                                    "sample": f"{args.cpu_sample} instances of the same workload, {dt:.2f} s wall on {cores} threads"}
+            line["cpu_baseline"] = cpu_baseline_entry(run_cpu(ocp, opts, min(args.cpu_sample, CPU_SAMPLE_CAP[args.config]), seed=1234 + args.config))
+        if n_gpus == 1 and args.config == 1 and not args.no_other_configs:
+            lm.clear()
+            del flush
+            torch.cuda.empty_cache()
+            line["configs"] = other_configs(local_rank, stream, peak, fp64_peak, not args.no_cpu_baseline)
         emit(line)
     if use_p2p:
         if exch.timed_out():

@@ -16,7 +16,20 @@
 #include <cmath>
 #include <cstring>
 
+#include "b200_systems.h"
+
 namespace corbo {
+
+// Structure identity of two descriptors: everything but LIVE vertex values.  On a variable-dt grid dt_ref is read from the first dt
+// vertex, i.e. it is the optimised value of the previous solve and differs per instance; the device only uses it to initialise
+// trajectories, which the adapter never asks for (it uploads the parameters).  Fixed-dt grids keep it: there it IS the structure.
+static bool sameStructure(const b200sqp_ocp& a, const b200sqp_ocp& b)
+{
+    b200sqp_ocp x = a, y = b;
+    if (x.grid == B200SQP_GRID_FD_NONUNIFORM_VARDT) x.dt_ref = 0.0;
+    if (y.grid == B200SQP_GRID_FD_NONUNIFORM_VARDT) y.dt_ref = 0.0;
+    return std::memcmp(&x, &y, sizeof(x)) == 0;
+}
 
 SolverB200Lm::SolverB200Lm()
 {
@@ -184,6 +197,17 @@ bool SolverB200Lm::describe(OptimizationProblemInterface& problem, b200sqp_ocp& 
         }
         for (int i = 0; i < count; ++i) d.dyn_params[i] = _dynamics_parameters[i];
     }
+    else if (dynamic_cast<Unicycle*>(_dynamics.get()))
+        d.dynamics = B200SQP_DYN_UNICYCLE;  // b200_systems.h; no parameters
+    else if (auto* s = dynamic_cast<Quadrotor*>(_dynamics.get()))
+    {
+        d.dynamics      = B200SQP_DYN_QUADROTOR;  // b200_systems.h; parameters through its getters
+        d.dyn_params[0] = s->getMass();
+        d.dyn_params[1] = s->getGravity();
+        d.dyn_params[2] = s->getInertiaXX();
+        d.dyn_params[3] = s->getInertiaYY();
+        d.dyn_params[4] = s->getInertiaZZ();
+    }
     else if (dynamic_cast<FreeSpaceRocket*>(_dynamics.get()))
         d.dynamics = B200SQP_DYN_FREE_SPACE_ROCKET;  // no parameters
     else if (dynamic_cast<ArtsteinsCircle*>(_dynamics.get()))
@@ -224,6 +248,8 @@ bool SolverB200Lm::describe(OptimizationProblemInterface& problem, b200sqp_ocp& 
     else
         d.grid = single_dt ? B200SQP_GRID_FD_UNIFORM : B200SQP_GRID_FD_NONUNIFORM_VARDT;
     d.dt_ref = dt0->getData()[0];
+    // variable-dt grids: a live vertex value, not structure (sameStructure() masks it); it only has to be a valid step size
+    if (d.grid == B200SQP_GRID_FD_NONUNIFORM_VARDT && !(d.dt_ref > 0)) d.dt_ref = 0.1;
     d.dt_lb  = dt0->getLowerBounds()[0];
     d.dt_ub  = dt0->getUpperBounds()[0];
     if (ms)
@@ -373,7 +399,7 @@ bool SolverB200Lm::describe(OptimizationProblemInterface& problem, b200sqp_ocp& 
     return true;
 }
 
-bool SolverB200Lm::upload(OptimizationProblemInterface& problem, int batch)
+bool SolverB200Lm::upload(OptimizationProblemInterface& problem, int batch, std::vector<double>* x0_out, std::vector<double>* xref_out)
 {
     std::vector<double> x0, xref;
     b200sqp_ocp d;
@@ -392,7 +418,7 @@ bool SolverB200Lm::upload(OptimizationProblemInterface& problem, int batch)
         _error = "device structure does not match the hypergraph's dimensions";
         return false;
     }
-    if (_handle && (std::memcmp(&d, &_ocp, sizeof(d)) != 0 || batch != _batch)) clear();
+    if (_handle && (!sameStructure(d, _ocp) || batch != _batch)) clear();
     _fresh = false;
     if (!_handle)
     {
@@ -407,6 +433,62 @@ bool SolverB200Lm::upload(OptimizationProblemInterface& problem, int batch)
         _dims  = dims;
         _batch = batch;
     }
+    if (x0_out) *x0_out = x0;
+    if (xref_out) *xref_out = xref;
+    return true;
+}
+
+// Per-instance data of a further problem of a batch whose structure `_ocp` was derived from the first one: start state and
+// reference, plus the cheap structural checks (dimensions, edge counts, bounds) -- not another full hypergraph walk per object.
+bool SolverB200Lm::instanceData(OptimizationProblemInterface& problem, double* x0, double* xref)
+{
+    auto* hg = dynamic_cast<BaseHyperGraphOptimizationProblem*>(&problem);
+    if (!hg || !hg->getGraph().hasEdgeSet())
+    {
+        _error = "problem is not a hypergraph optimization problem";
+        return false;
+    }
+    if (problem.getParameterDimension() != _dims.n_params || problem.getLsqObjectiveDimension() != _dims.m_lsq ||
+        problem.getEqualityDimension() != _dims.m_eq || problem.getInequalityDimension() != _dims.m_ineq ||
+        problem.finiteCombinedBoundsDimension() != _dims.m_bounds)
+    {
+        _error = "dimensions differ from the first problem of the batch";
+        return false;
+    }
+    OptimizationEdgeSet* edges        = hg->getGraph().getEdgeSetRaw();
+    std::vector<BaseEdge::Ptr>& eq    = edges->getEqualityEdgesRef();
+    const int K                       = _ocp.n_grid - 1;
+    const int n_eq                    = K + (_ocp.final_constraint == B200SQP_FINAL_CONSTRAINT_EQUALITY ? 1 : 0);
+    if ((int)eq.size() != n_eq || !edges->getMixedEdgesRef().empty() || !edges->getObjectiveEdgesRef().empty() ||
+        eq.front()->getNumVertices() != 4 || eq[K - 1]->getNumVertices() != 4)
+    {
+        _error = "edge lists differ from the first problem of the batch";
+        return false;
+    }
+    const VertexInterface* x_first = eq.front()->getVertexRaw(0);
+    const VertexInterface* u_first = eq.front()->getVertexRaw(1);
+    const VertexInterface* dt0     = eq.front()->getVertexRaw(3);
+    const VertexInterface* x_last  = eq[K - 1]->getVertexRaw(2);
+    bool same = x_first->isFixed() && x_first->getDimension() == _ocp.nx && u_first->getDimension() == _ocp.nu;
+    for (int i = 0; same && i < _ocp.nx; ++i)
+        same = x_last->getLowerBounds()[i] == _ocp.x_lb[i] && x_last->getUpperBounds()[i] == _ocp.x_ub[i] &&
+               (x_last->isFixedComponent(i) ? 1 : 0) == _ocp.xf_fixed[i];
+    for (int i = 0; same && i < _ocp.nu; ++i) same = u_first->getLowerBounds()[i] == _ocp.u_lb[i] && u_first->getUpperBounds()[i] == _ocp.u_ub[i];
+    same = same && dt0->getLowerBounds()[0] == _ocp.dt_lb && dt0->getUpperBounds()[0] == _ocp.dt_ub;
+    if (_ocp.grid != B200SQP_GRID_FD_NONUNIFORM_VARDT) same = same && dt0->getData()[0] == _ocp.dt_ref;
+    if (!same)
+    {
+        _error = "bounds, fixed components or step size differ from the first problem of the batch";
+        return false;
+    }
+    for (int i = 0; i < _ocp.nx; ++i) x0[i] = x_first->getData()[i];
+    if (_xref)
+    {
+        const ReferenceTrajectoryInterface::OutputVector& r = _xref->getReferenceCached(0);
+        for (int i = 0; i < _ocp.nx; ++i) xref[i] = r[i];
+    }
+    else
+        for (int i = 0; i < _ocp.nx; ++i) xref[i] = _ocp.xf_fixed[i] ? x_last->getData()[i] : 0.0;
     return true;
 }
 
@@ -456,24 +538,23 @@ bool SolverB200Lm::solveBatch(const std::vector<OptimizationProblemInterface*>& 
 {
     const int B = (int)problems.size();
     if (B == 0) return true;
-    if (!upload(*problems[0], B))
+    std::vector<double> x0_first, xref_first;
+    if (!upload(*problems[0], B, &x0_first, &xref_first))
     {
         fail(_error);
         return false;
     }
     const int n = _dims.n_params, nx = _ocp.nx;
     std::vector<double> x0((size_t)B * nx), xref((size_t)B * nx), params((size_t)B * n);
+    std::copy(x0_first.begin(), x0_first.end(), x0.begin());
+    std::copy(xref_first.begin(), xref_first.end(), xref.begin());
     for (int i = 0; i < B; ++i)
     {
-        std::vector<double> x0i, xrefi;
-        b200sqp_ocp di;
-        if (!describe(*problems[i], di, x0i, xrefi) || std::memcmp(&di, &_ocp, sizeof(di)) != 0)
+        if (i > 0 && !instanceData(*problems[i], x0.data() + (size_t)i * nx, xref.data() + (size_t)i * nx))
         {
             fail("problems of one batch must share one structure: " + _error);
             return false;
         }
-        std::copy(x0i.begin(), x0i.end(), x0.begin() + (size_t)i * nx);
-        std::copy(xrefi.begin(), xrefi.end(), xref.begin() + (size_t)i * nx);
         Eigen::Map<Eigen::VectorXd> p(params.data() + (size_t)i * n, n);
         problems[i]->getParameterVector(p);
     }

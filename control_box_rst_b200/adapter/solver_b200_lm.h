@@ -28,6 +28,7 @@
 #include <vector>
 
 #include "../../include/b200sqp.h"
+#include "b200_systems.h"  // corbo::Unicycle, corbo::Quadrotor: the models of BASELINE configs[2] / configs[4] for the reference's object model
 
 namespace corbo {
 
@@ -83,7 +84,8 @@ class SolverB200Lm : public NlpSolverInterface
 
  private:
     bool describe(OptimizationProblemInterface& problem, b200sqp_ocp& ocp, std::vector<double>& x0, std::vector<double>& xref);
-    bool upload(OptimizationProblemInterface& problem, int batch);
+    bool upload(OptimizationProblemInterface& problem, int batch, std::vector<double>* x0_out = nullptr, std::vector<double>* xref_out = nullptr);
+    bool instanceData(OptimizationProblemInterface& problem, double* x0, double* xref);
     bool selfCheck(OptimizationProblemInterface& problem);
     SolverStatus fail(const std::string& msg);
 

@@ -1016,6 +1016,25 @@ int b200sqp_set_threads_per_instance(b200sqp_handle h, int32_t threads)
     return B200SQP_OK;
 }
 
+int b200sqp_measure_fp64_peak(int32_t device, double* tflops)
+{
+    if (!tflops) return fail(B200SQP_ERR_INVALID, "null argument");
+    int count = 0;
+    if (cudaGetDeviceCount(&count) != cudaSuccess || count == 0)
+    {
+        cudaGetLastError();
+        return fail(B200SQP_ERR_NO_DEVICE, "no CUDA device visible");
+    }
+    if (device < 0 || device >= count) return fail(B200SQP_ERR_INVALID, "device index out of range");
+    CUDA_TRY(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    CUDA_TRY(cudaGetDeviceProperties(&prop, device));
+    const double v = measureFp64PeakTflops(prop.multiProcessorCount, nullptr);
+    if (v < 0) return fail(B200SQP_ERR_CUDA, "fp64 peak measurement failed");
+    *tflops = v;
+    return B200SQP_OK;
+}
+
 int b200sqp_set_feature_set(b200sqp_handle h, int32_t general)
 {
     if (!h) return fail(B200SQP_ERR_INVALID, "null handle");

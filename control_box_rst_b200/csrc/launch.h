@@ -86,4 +86,7 @@ void launchWarmStartShift(const double* x0_new /*[B][nx]*/, double* x0 /*tiled*/
 void launchPeerWait(const unsigned long long* arrivals, int world, unsigned long long expected, unsigned long long timeout_ns, int* timed_out,
                     cudaStream_t);
 
+// measured fp64 FMA throughput of the device (TFLOP/s, 2 flops per FMA), all SMs, best of three timed launches; < 0 on failure
+double measureFp64PeakTflops(int sm_count, cudaStream_t);
+
 }  // namespace b200sqp

@@ -309,7 +309,54 @@ __global__ void peerWaitKernel(const volatile unsigned long long* arrivals, int 
     __threadfence_system();
 }
 
+// b200sqp_measure_fp64_peak: 8 independent DFMA chains per thread, 16 warps per block, every SM loaded: the fp64 FMA issue bound
+// the fused LM kernel is compared with (bench.py roofline_fp64).  fma() is explicit, so --fmad=false does not matter here.
+__global__ void __launch_bounds__(512) fp64PeakKernel(double* out, double a, double b, int n)
+{
+    double x[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) x[j] = a + j + threadIdx.x * 1e-9;
+#pragma unroll 1
+    for (int i = 0; i < n; ++i)
+    {
+#pragma unroll
+        for (int r = 0; r < 4; ++r)
+#pragma unroll
+            for (int j = 0; j < 8; ++j) x[j] = fma(x[j], b, b);
+    }
+    double s = 0;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) s += x[j];
+    out[(size_t)blockIdx.x * blockDim.x + threadIdx.x] = s;
+}
+
 }  // namespace
+
+double measureFp64PeakTflops(int sm_count, cudaStream_t st)
+{
+    const int blocks = sm_count * 4, threads = 512, n = 20000;
+    double* out = nullptr;
+    if (cudaMalloc(&out, sizeof(double) * (size_t)blocks * threads) != cudaSuccess) return -1.0;
+    cudaEvent_t e0, e1;
+    cudaEventCreate(&e0);
+    cudaEventCreate(&e1);
+    double best = -1.0;
+    for (int rep = 0; rep < 4; ++rep)  // first repetition warms the clocks up
+    {
+        cudaEventRecord(e0, st);
+        fp64PeakKernel<<<blocks, threads, 0, st>>>(out, 1.0, 0.999999, n);
+        cudaEventRecord(e1, st);
+        if (cudaEventSynchronize(e1) != cudaSuccess) break;
+        float ms = 0.f;
+        cudaEventElapsedTime(&ms, e0, e1);
+        const double tflops = 2.0 * blocks * threads * (double)n * 32.0 / (ms * 1e-3) / 1e12;
+        if (rep > 0 && tflops > best) best = tflops;
+    }
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    cudaFree(out);
+    return cudaGetLastError() == cudaSuccess ? best : -1.0;
+}
 
 void launchWarmStartShift(const double* x0_new, double* x0, double* z0, double* z1, int* cur, int K, int nx, int nu, int* plan, int* num_shift,
                           int B, cudaStream_t st)

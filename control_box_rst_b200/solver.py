@@ -28,7 +28,7 @@ ABI_SYMBOLS = [
     "b200sqp_last_solve_ms", "b200sqp_launch_count", "b200sqp_device_pointers", "b200sqp_set_stream", "b200sqp_set_threads_per_instance",
     "b200sqp_set_phase_profile", "b200sqp_get_phase_cycles", "b200sqp_final_constraint_indices",
     "b200sqp_peer_export", "b200sqp_peer_attach", "b200sqp_peer_wait", "b200sqp_peer_gathered", "b200sqp_peer_detach", "b200sqp_peer_status", "b200sqp_linearize_dynamics", "b200sqp_warm_start_shift", "b200sqp_mpc_step",
-    "b200sqp_plant_step", "b200sqp_closed_loop", "b200sqp_dynamics_hessian", "b200sqp_set_feature_set",
+    "b200sqp_plant_step", "b200sqp_closed_loop", "b200sqp_dynamics_hessian", "b200sqp_set_feature_set", "b200sqp_measure_fp64_peak",
 ]
 
 
@@ -141,6 +141,13 @@ def dynamics_hessian(dynamics, dyn_params, x, u, multipliers=None, method="forwa
     _check(load_library().b200sqp_dynamics_hessian(C.c_int32(dynamics), _d(p), C.c_int32({"forward": 0, "central": 1}[method]), C.c_int32(B),
                                                     _d(x), _d(u), _d(m), _d(H), C.c_int32(device)))
     return H.transpose(0, 2, 1).copy()  # the library writes column-major blocks per point
+
+
+def measure_fp64_peak(device=0):
+    """fp64 FMA throughput of the device in TFLOP/s, measured live (the issue bound of the fused LM kernel)"""
+    v = C.c_double(0)
+    _check(load_library().b200sqp_measure_fp64_peak(C.c_int32(device), C.byref(v)))
+    return v.value
 
 
 INTEGRATORS = {"euler": 0, "rk4": 1}

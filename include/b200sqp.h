@@ -309,6 +309,10 @@ int b200sqp_set_feature_set(b200sqp_handle h, int32_t general);
  * LM control (a1)} in SM clock cycles.  Off by default (the kernel then only tests one pointer). */
 int b200sqp_set_phase_profile(b200sqp_handle h, int32_t enable);
 int b200sqp_get_phase_cycles(b200sqp_handle h, double* mean_cycles /*[4]*/);
+/* measurement aid: fp64 FMA throughput of `device` in TFLOP/s (2 flops per FMA), measured live with a register-resident kernel of
+ * independent FMA chains on every SM -- the issue bound the fused LM kernel is reported against next to the HBM roofline
+ * (SURVEY.md section 8d "also report the fp64 FMA bound"). */
+int b200sqp_measure_fp64_peak(int32_t device, double* tflops);
 /* make the handle launch on an external stream (e.g. torch's current stream); pass NULL to restore its own */
 int b200sqp_set_stream(b200sqp_handle h, void* cuda_stream);
 

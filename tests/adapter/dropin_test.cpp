@@ -10,15 +10,20 @@
 #include <corbo-optimal-control/functions/final_state_constraints.h>
 #include <corbo-optimal-control/functions/final_state_cost.h>
 #include <corbo-optimal-control/functions/quadratic_cost.h>
+#include <corbo-optimal-control/functions/minimum_time.h>
 #include <corbo-optimal-control/structured_ocp/discretization_grids/finite_differences_grid.h>
+#include <corbo-optimal-control/structured_ocp/discretization_grids/non_uniform_finite_differences_variable_grid.h>
 #include <corbo-optimal-control/structured_ocp/structured_optimal_control_problem.h>
 #include <corbo-optimization/hyper_graph/hyper_graph_optimization_problem_edge_based.h>
 #include <corbo-optimization/solver/levenberg_marquardt_sparse.h>
 #include <corbo-systems/benchmark/linear_benchmark_systems.h>
 #include <corbo-systems/benchmark/nonlinear_benchmark_systems.h>
 
+#include <chrono>
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
+#include <cstring>
 #include <random>
 
 #include "../../control_box_rst_b200/adapter/solver_b200_lm.h"
@@ -106,8 +111,113 @@ static Eigen::VectorXd solveBenchmarkSystem(SystemDynamicsInterface::Ptr dynamic
     return p;
 }
 
-int main()
+// ---- BASELINE.json configs[2]: time-optimal unicycle on the NonUniformFiniteDifferencesVariableGrid (TEB-style: one free dt per interval),
+//      MinimumTime in lsq form, goal pose fixed, |v|, |omega| <= 1, dt in [0, 1]; the model class is the product's corbo::Unicycle
+struct TebLoop
 {
+    std::shared_ptr<StructuredOptimalControlProblem> ocp;
+    std::shared_ptr<HyperGraphOptimizationProblemEdgeBased> problem;
+    SystemDynamicsInterface::Ptr dynamics;
+};
+
+static TebLoop makeTebUnicycle(NlpSolverInterface::Ptr solver, int n)
+{
+    TebLoop l;
+    l.dynamics = std::make_shared<Unicycle>();
+    auto grid  = std::make_shared<NonUniformFiniteDifferencesVariableGrid>();
+    grid->setNRef(n);
+    grid->setDtRef(0.1);
+    grid->setDtBounds(0.0, 1.0);
+    grid->disableGridAdaptation();
+    grid->setDtEqConstraint(false);
+    grid->setCostIntegrationRule(NonUniformFullDiscretizationGridBase::CostIntegrationRule::LeftSum);
+    Eigen::Matrix<bool, -1, 1> xf_fixed = Eigen::Matrix<bool, -1, 1>::Constant(3, true);
+    grid->setXfFixed(xf_fixed);
+    l.problem       = std::make_shared<HyperGraphOptimizationProblemEdgeBased>();
+    l.ocp           = std::make_shared<StructuredOptimalControlProblem>(grid, l.dynamics, l.problem, solver);
+    auto stage_cost = std::make_shared<MinimumTime>(true);
+    l.ocp->setStageCost(stage_cost);
+    Eigen::VectorXd xlb = Eigen::VectorXd::Constant(3, -CORBO_INF_DBL), xub = Eigen::VectorXd::Constant(3, CORBO_INF_DBL);
+    Eigen::VectorXd ulb = Eigen::VectorXd::Constant(2, -1.0), uub = Eigen::VectorXd::Constant(2, 1.0);
+    l.ocp->setBounds(xlb, xub, ulb, uub);
+    if (auto b200 = std::dynamic_pointer_cast<SolverB200Lm>(solver))
+    {
+        b200->setSystemDynamics(l.dynamics);
+        b200->setStageCost(stage_cost);
+    }
+    return l;
+}
+
+static double relDiff(const Eigen::VectorXd& a, const Eigen::VectorXd& b)
+{
+    return a.size() == b.size() ? (a - b).cwiseAbs().maxCoeff() / std::max(1.0, a.cwiseAbs().maxCoeff()) : 1e30;
+}
+
+static Eigen::VectorXd paramsOf(HyperGraphOptimizationProblemEdgeBased& p)
+{
+    Eigen::VectorXd v(p.getParameterDimension());
+    p.getParameterVector(v);
+    return v;
+}
+
+// `dropin_test --bench B`: the reference's own API route at batch size B -- B StructuredOptimalControlProblem objects (Van der Pol,
+// FiniteDifferencesGrid N=50: BASELINE configs[1]) prepared by the reference's grid update, solved by ONE SolverB200Lm::solveBatch call.
+// Timed: the whole solveBatch call on the host clock (hypergraph walks, parameter gather over the vertex objects, H2D, the device
+// solve, D2H, parameter scatter back into the vertices).  Prints one JSON object on the last line.
+static int benchPlugin(int B, int repetitions)
+{
+    ZeroReference xref(2), uref(1);
+    std::mt19937_64 rng(1235);
+    std::uniform_real_distribution<double> dist(-2.0, 2.0);
+    std::vector<Loop> loops;
+    std::vector<OptimizationProblemInterface*> problems;
+    std::vector<Eigen::VectorXd> initial;
+    const auto t_build0 = std::chrono::steady_clock::now();
+    for (int i = 0; i < B; ++i)
+    {
+        Eigen::VectorXd x0(2);
+        x0 << dist(rng), dist(rng);
+        auto dummy = std::make_shared<LevenbergMarquardtSparse>();
+        dummy->setIterations(0);  // compute() with zero iterations: grid update + index precomputation only, the initial guess stays
+        loops.push_back(makeLoop(dummy, 50));
+        loops.back().ocp->initialize();
+        loops.back().ocp->compute(x0, xref, uref, nullptr, Time(0), true);
+        problems.push_back(loops.back().problem.get());
+        initial.push_back(paramsOf(*loops.back().problem));
+    }
+    const double build_s = std::chrono::duration<double>(std::chrono::steady_clock::now() - t_build0).count();
+    auto solver = std::make_shared<SolverB200Lm>();
+    solver->setIterations(10);
+    solver->setSystemDynamics(loops[0].dynamics);
+    solver->setStageCost(std::make_shared<QuadraticFormCost>(Eigen::MatrixXd::Identity(2, 2), Eigen::MatrixXd::Constant(1, 1, 0.1), false, true));
+    solver->setFinalStageCost(std::make_shared<QuadraticFinalStateCost>(Eigen::MatrixXd::Identity(2, 2), true));
+    double best = 1e30, total = 0;
+    for (int r = 0; r < repetitions + 1; ++r)
+    {
+        for (int i = 0; i < B; ++i) problems[i]->setParameterVector(initial[i]);  // cold start again (not timed)
+        const auto t0 = std::chrono::steady_clock::now();
+        if (!solver->solveBatch(problems, true, nullptr, nullptr))
+        {
+            std::printf("{\"error\": \"solveBatch: %s\"}\n", solver->lastError().c_str());
+            return 1;
+        }
+        const double s = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+        if (r > 0)  // the first call creates the device handle and runs the structure self-check
+        {
+            best = std::min(best, s);
+            total += s;
+        }
+    }
+    const double mean = total / repetitions;
+    std::printf("{\"objects\": %d, \"n_grid\": 50, \"iterations\": 10, \"repetitions\": %d, \"solve_batch_ms_mean\": %.4f, \"solve_batch_ms_best\": %.4f, "
+                "\"value\": %.6g, \"unit\": \"iters/s\", \"kernel_ms\": %.4f, \"build_objects_s\": %.3f}\n",
+                B, repetitions, 1e3 * mean, 1e3 * best, B * 10.0 / mean, solver->lastSolveMilliseconds(), build_s);
+    return 0;
+}
+
+int main(int argc, char** argv)
+{
+    if (argc >= 3 && std::strcmp(argv[1], "--bench") == 0) return benchPlugin(std::atoi(argv[2]), argc >= 4 ? std::atoi(argv[3]) : 5);
     int failures = 0;
     // ---- 1. factory registration: the plugin is found by name like every reference solver -------------------------------------
     NlpSolverInterface::Ptr from_factory = NlpSolverFactory::instance().create("SolverB200Lm");
@@ -364,6 +474,154 @@ int main()
         else
             std::printf("ok: wrong parameters -> Error (%s); missing parameters -> Error (%s)\n", dev_wrong->lastError().c_str(),
                         dev_missing->lastError().c_str());
+    }
+    // ---- 7. BASELINE configs[2] through the plugin: time-optimal unicycle (corbo::Unicycle, b200_systems.h) on the non-uniform grid.
+    //         Two consecutive solves per object (the live dt vertices change after every solve and must not count as a new structure:
+    //         the device handle survives, and with new_run = false the penalty weights are ADAPTED like LevenbergMarquardtSparse's), then
+    //         a batch of 8 objects solved twice with one device call each (every instance then has its own dt values).
+    {
+        ZeroReference xref3(3), uref2(2);
+        auto s_ref = std::make_shared<LevenbergMarquardtSparse>();
+        auto s_dev = std::make_shared<SolverB200Lm>();
+        s_ref->setIterations(5);
+        s_dev->setIterations(5);
+        s_ref->setWeightAdapation(2, 2, 2, 50, 50, 50);
+        s_dev->setWeightAdapation(2, 2, 2, 50, 50, 50);
+        TebLoop lr = makeTebUnicycle(s_ref, 20), lb = makeTebUnicycle(s_dev, 20);
+        lr.ocp->initialize();
+        lb.ocp->initialize();
+        Eigen::VectorXd x0(3);
+        x0 << -1.5, 0.8, 0.6;
+        double worst7 = 0;
+        bool ok7      = true;
+        for (int s = 0; s < 3; ++s)
+        {
+            const bool new_run = s != 1;  // the second solve continues the run: weights adapted, not reset
+            ok7 = lr.ocp->compute(x0, xref3, uref2, nullptr, Time(0.1 * s), new_run) && ok7;
+            ok7 = lb.ocp->compute(x0, xref3, uref2, nullptr, Time(0.1 * s), new_run) && ok7;
+            worst7 = std::max(worst7, relDiff(paramsOf(*lr.problem), paramsOf(*lb.problem)));
+            x0[0] += 0.05;
+            x0[2] -= 0.02;
+        }
+        std::printf("time-optimal unicycle (non-uniform grid, N=20), 3 consecutive solves incl. one with adapted weights: max relative "
+                    "trajectory difference vs reference = %.3e (objective %.9g vs %.9g)\n",
+                    worst7, lr.ocp->getCurrentObjectiveValue(), lb.ocp->getCurrentObjectiveValue());
+        if (!ok7 || !(worst7 <= 1e-4))
+        {
+            std::printf("FAIL: time-optimal unicycle through the plugin (ok=%d, %s)\n", (int)ok7, s_dev->lastError().c_str());
+            ++failures;
+        }
+        const int Bt = 8;
+        std::vector<TebLoop> refs, devs;
+        std::vector<OptimizationProblemInterface*> probs;
+        std::mt19937_64 rng7(77);
+        std::uniform_real_distribution<double> pos(-2.0, 2.0), ang(-3.0, 3.0);
+        std::vector<Eigen::VectorXd> starts;
+        for (int i = 0; i < Bt; ++i)
+        {
+            Eigen::VectorXd xs(3);
+            xs << pos(rng7), pos(rng7), ang(rng7);
+            starts.push_back(xs);
+            auto si = std::make_shared<LevenbergMarquardtSparse>();
+            si->setIterations(5);
+            refs.push_back(makeTebUnicycle(si, 20));
+            refs.back().ocp->initialize();
+            auto dummy = std::make_shared<LevenbergMarquardtSparse>();
+            dummy->setIterations(0);
+            devs.push_back(makeTebUnicycle(dummy, 20));
+            devs.back().ocp->initialize();
+            probs.push_back(devs.back().problem.get());
+        }
+        auto batch7 = std::make_shared<SolverB200Lm>();
+        batch7->setIterations(5);
+        batch7->setSystemDynamics(devs[0].dynamics);
+        batch7->setStageCost(std::make_shared<MinimumTime>(true));
+        double worst7b = 0;
+        bool ok7b      = true;
+        for (int round = 0; round < 2; ++round)
+        {
+            for (int i = 0; i < Bt; ++i)
+            {
+                ok7b = refs[i].ocp->compute(starts[i], xref3, uref2, nullptr, Time(0.1 * round), true) && ok7b;
+                ok7b = devs[i].ocp->compute(starts[i], xref3, uref2, nullptr, Time(0.1 * round), true) && ok7b;  // grid update only (0 iterations)
+            }
+            if (!batch7->solveBatch(probs, true, nullptr, nullptr))
+            {
+                std::printf("FAIL: solveBatch on the non-uniform grid, round %d: %s\n", round, batch7->lastError().c_str());
+                ok7b = false;
+                break;
+            }
+            for (int i = 0; i < Bt; ++i)
+            {
+                worst7b = std::max(worst7b, relDiff(paramsOf(*refs[i].problem), paramsOf(*devs[i].problem)));
+                starts[i][0] += 0.03;
+            }
+        }
+        std::printf("time-optimal unicycle, %d objects x 2 rounds through solveBatch: max relative trajectory difference vs reference = %.3e\n", Bt, worst7b);
+        if (!ok7b || !(worst7b <= 1e-4))
+        {
+            std::printf("FAIL: batched time-optimal unicycle\n");
+            ++failures;
+        }
+    }
+    // ---- 8. BASELINE configs[4] through the plugin: 12-state quadrotor (corbo::Quadrotor, parameters through its getters), FD grid N=12
+    {
+        auto build = [](NlpSolverInterface::Ptr solver, std::shared_ptr<HyperGraphOptimizationProblemEdgeBased>& problem) {
+            auto dynamics = std::make_shared<Quadrotor>(1.2, 9.81, 0.012, 0.011, 0.021);
+            auto grid     = std::make_shared<FiniteDifferencesGrid>();
+            grid->setNRef(12);
+            grid->setDtRef(0.05);
+            grid->setCostIntegrationRule(FullDiscretizationGridBase::CostIntegrationRule::LeftSum);
+            problem  = std::make_shared<HyperGraphOptimizationProblemEdgeBased>();
+            auto ocp = std::make_shared<StructuredOptimalControlProblem>(grid, dynamics, problem, solver);
+            Eigen::MatrixXd Q = Eigen::MatrixXd::Identity(12, 12), R = 0.1 * Eigen::MatrixXd::Identity(4, 4);
+            auto stage_cost = std::make_shared<QuadraticFormCost>(Q, R, false, true);
+            auto final_cost = std::make_shared<QuadraticFinalStateCost>(Q, true);
+            ocp->setStageCost(stage_cost);
+            ocp->setFinalStageCost(final_cost);
+            Eigen::VectorXd xlb = Eigen::VectorXd::Constant(12, -CORBO_INF_DBL), xub = Eigen::VectorXd::Constant(12, CORBO_INF_DBL);
+            Eigen::VectorXd ulb(4), uub(4);
+            ulb << 0.0, -1.0, -1.0, -1.0;
+            uub << 2.0 * 1.2 * 9.81, 1.0, 1.0, 1.0;
+            ocp->setBounds(xlb, xub, ulb, uub);
+            if (auto b200 = std::dynamic_pointer_cast<SolverB200Lm>(solver))
+            {
+                b200->setSystemDynamics(dynamics);
+                b200->setStageCost(stage_cost);
+                b200->setFinalStageCost(final_cost);
+            }
+            ocp->initialize();
+            return ocp;
+        };
+        auto s_ref = std::make_shared<LevenbergMarquardtSparse>();
+        auto s_dev = std::make_shared<SolverB200Lm>();
+        s_ref->setIterations(6);
+        s_dev->setIterations(6);
+        std::shared_ptr<HyperGraphOptimizationProblemEdgeBased> pr, pd;
+        auto ocp_r = build(s_ref, pr), ocp_d = build(s_dev, pd);
+        ZeroReference xref12(12), uref4(4);
+        Eigen::VectorXd x0 = Eigen::VectorXd::Zero(12);
+        x0[0] = 0.6;
+        x0[1] = -0.4;
+        x0[2] = 0.3;
+        x0[3] = 0.1;
+        x0[4] = -0.15;
+        x0[5] = 0.05;
+        const bool ok_r = ocp_r->compute(x0, xref12, uref4, nullptr, Time(0), true);
+        const bool ok_d = ocp_d->compute(x0, xref12, uref4, nullptr, Time(0), true);
+        const double diff = relDiff(paramsOf(*pr), paramsOf(*pd));
+        std::printf("quadrotor (12 states, FD grid N=12) through the plugin: max relative trajectory difference vs reference = %.3e "
+                    "(objective %.9g vs %.9g)\n", diff, ocp_r->getCurrentObjectiveValue(), ocp_d->getCurrentObjectiveValue());
+        if (!ok_r || !ok_d || !(diff <= 1e-4))
+        {
+            std::printf("FAIL: quadrotor through the plugin (ok_ref=%d ok_b200=%d, %s)\n", (int)ok_r, (int)ok_d, s_dev->lastError().c_str());
+            ++failures;
+        }
+        if (!SystemDynamicsFactory::instance().create("Unicycle") || !SystemDynamicsFactory::instance().create("Quadrotor"))
+        {
+            std::printf("FAIL: corbo::Unicycle / corbo::Quadrotor not registered in Factory<SystemDynamicsInterface>\n");
+            ++failures;
+        }
     }
     std::printf(failures ? "DROP-IN TEST FAILED\n" : "DROP-IN TEST PASSED\n");
     return failures ? 1 : 0;
