@@ -278,6 +278,29 @@ def fp64_roofline(ocp, dims, B, iterations, kernel_ms, fp64_peak):
             "note": "binding roof of the fused kernel (J, H and L never reach DRAM); one count per +,-,*,/ and libm call, rejected steps not counted"}
 
 
+def plugin_e2e(batch, iterations):
+    """The reference's OWN API route: `batch` StructuredOptimalControlProblem objects of the workload (built and grid-updated by the
+    unmodified reference), solved by one corbo::SolverB200Lm::solveBatch call -- the C++ plugin of control_box_rst_b200/adapter over the
+    same C ABI.  Timed inside the drop-in binary (tests/adapter/dropin_test.cpp --bench) on the host clock around solveBatch: hypergraph
+    walk, parameter gather from / scatter to the vertex objects, H2D, device solve, D2H.  The binary links the compiled reference, so it
+    only exists where /root/reference was present at build time (it travels to the GPU box with the snapshot)."""
+    exe = os.path.join(ROOT, "tests", "adapter", "_build", "dropin_test")
+    if not os.path.exists(exe):
+        return {"unavailable": "tests/adapter/_build/dropin_test not built (needs /root/reference at build time)"}
+    try:
+        out = subprocess.run([exe, "--bench", str(batch), "5"], capture_output=True, text=True, timeout=300)
+        r = json.loads(out.stdout.strip().splitlines()[-1])
+    except Exception as exc:
+        return {"unavailable": f"{type(exc).__name__}: {exc}"}
+    if "error" in r:
+        return {"unavailable": r["error"]}
+    n = 147
+    return {"value": r["value"], "unit": UNIT, "ms_per_step": r["solve_batch_ms_mean"], "ms_per_step_best": r["solve_batch_ms_best"],
+            "objects": r["objects"], "kernel_ms": r["kernel_ms"], "h2d_bytes_per_step": batch * (2 * 2 + n) * 8, "d2h_bytes_per_step": batch * (n * 8 + 8 + 4),
+            "build_objects_s": r["build_objects_s"],
+            "note": "corbo::SolverB200Lm::solveBatch over reference OCP objects (host clock around the call; per-object vertex gather/scatter on one host thread)"}
+
+
 def other_configs(device, stream, hbm_peak, fp64_peak, with_cpu):
     """BASELINE.json configs[2..4] at their full batch on this GPU, a few steps each (parity-test cases, not bench lines: recorded so
     that the driver's run carries their throughput, roofline fractions and CPU baseline too).  Same timing rules as the main line."""
@@ -527,6 +550,7 @@ def main_b200(args):
             del flush
             torch.cuda.empty_cache()
             line["configs"] = other_configs(local_rank, stream, peak, fp64_peak, not args.no_cpu_baseline)
+            line["e2e_plugin"] = plugin_e2e(B, iterations)
         emit(line)
     if use_p2p:
         if exch.timed_out():

@@ -13,12 +13,38 @@
 #include <corbo-systems/benchmark/linear_benchmark_systems.h>
 #include <corbo-systems/benchmark/nonlinear_benchmark_systems.h>
 
+#include <algorithm>
+#include <atomic>
 #include <cmath>
 #include <cstring>
+#include <mutex>
+#include <thread>
 
 #include "b200_systems.h"
 
 namespace corbo {
+
+// The per-object halves of a batched solve (reading x0 / the parameter vector out of the vertex objects, writing the result back) touch
+// one reference object each and nothing shared: they run on all host threads for large batches (8.5 us per object on one thread
+// would otherwise be 100x the device time of the whole batch).
+template <class F>
+static void forEachObject(int count, F&& body)
+{
+    const int hw = (int)std::thread::hardware_concurrency();
+    const int threads = count >= 256 ? std::max(1, std::min(hw > 0 ? hw : 1, count / 64)) : 1;
+    if (threads == 1)
+    {
+        for (int i = 0; i < count; ++i) body(i);
+        return;
+    }
+    std::vector<std::thread> pool;
+    for (int t = 1; t < threads; ++t)
+        pool.emplace_back([&, t] {
+            for (int i = (int)((long long)count * t / threads), e = (int)((long long)count * (t + 1) / threads); i < e; ++i) body(i);
+        });
+    for (int i = 0, e = count / threads; i < e; ++i) body(i);
+    for (auto& th : pool) th.join();
+}
 
 // Structure identity of two descriptors: everything but LIVE vertex values.  On a variable-dt grid dt_ref is read from the first dt
 // vertex, i.e. it is the optimised value of the previous solve and differs per instance; the device only uses it to initialise
@@ -440,19 +466,19 @@ bool SolverB200Lm::upload(OptimizationProblemInterface& problem, int batch, std:
 
 // Per-instance data of a further problem of a batch whose structure `_ocp` was derived from the first one: start state and
 // reference, plus the cheap structural checks (dimensions, edge counts, bounds) -- not another full hypergraph walk per object.
-bool SolverB200Lm::instanceData(OptimizationProblemInterface& problem, double* x0, double* xref)
+bool SolverB200Lm::instanceData(OptimizationProblemInterface& problem, double* x0, double* xref, std::string& error) const
 {
     auto* hg = dynamic_cast<BaseHyperGraphOptimizationProblem*>(&problem);
     if (!hg || !hg->getGraph().hasEdgeSet())
     {
-        _error = "problem is not a hypergraph optimization problem";
+        error = "problem is not a hypergraph optimization problem";
         return false;
     }
     if (problem.getParameterDimension() != _dims.n_params || problem.getLsqObjectiveDimension() != _dims.m_lsq ||
         problem.getEqualityDimension() != _dims.m_eq || problem.getInequalityDimension() != _dims.m_ineq ||
         problem.finiteCombinedBoundsDimension() != _dims.m_bounds)
     {
-        _error = "dimensions differ from the first problem of the batch";
+        error = "dimensions differ from the first problem of the batch";
         return false;
     }
     OptimizationEdgeSet* edges        = hg->getGraph().getEdgeSetRaw();
@@ -462,7 +488,7 @@ bool SolverB200Lm::instanceData(OptimizationProblemInterface& problem, double* x
     if ((int)eq.size() != n_eq || !edges->getMixedEdgesRef().empty() || !edges->getObjectiveEdgesRef().empty() ||
         eq.front()->getNumVertices() != 4 || eq[K - 1]->getNumVertices() != 4)
     {
-        _error = "edge lists differ from the first problem of the batch";
+        error = "edge lists differ from the first problem of the batch";
         return false;
     }
     const VertexInterface* x_first = eq.front()->getVertexRaw(0);
@@ -478,7 +504,7 @@ bool SolverB200Lm::instanceData(OptimizationProblemInterface& problem, double* x
     if (_ocp.grid != B200SQP_GRID_FD_NONUNIFORM_VARDT) same = same && dt0->getData()[0] == _ocp.dt_ref;
     if (!same)
     {
-        _error = "bounds, fixed components or step size differ from the first problem of the batch";
+        error = "bounds, fixed components or step size differ from the first problem of the batch";
         return false;
     }
     for (int i = 0; i < _ocp.nx; ++i) x0[i] = x_first->getData()[i];
@@ -548,15 +574,28 @@ bool SolverB200Lm::solveBatch(const std::vector<OptimizationProblemInterface*>& 
     std::vector<double> x0((size_t)B * nx), xref((size_t)B * nx), params((size_t)B * n);
     std::copy(x0_first.begin(), x0_first.end(), x0.begin());
     std::copy(xref_first.begin(), xref_first.end(), xref.begin());
-    for (int i = 0; i < B; ++i)
-    {
-        if (i > 0 && !instanceData(*problems[i], x0.data() + (size_t)i * nx, xref.data() + (size_t)i * nx))
+    std::atomic<int> first_bad(B);
+    std::vector<std::string> errors(B > 0 ? 1 : 0);
+    std::mutex error_mutex;
+    forEachObject(B, [&](int i) {
+        std::string err;
+        if (i > 0 && !instanceData(*problems[i], x0.data() + (size_t)i * nx, xref.data() + (size_t)i * nx, err))
         {
-            fail("problems of one batch must share one structure: " + _error);
-            return false;
+            std::lock_guard<std::mutex> lock(error_mutex);
+            if (i < first_bad.load())
+            {
+                first_bad = i;
+                errors[0] = err;
+            }
+            return;
         }
         Eigen::Map<Eigen::VectorXd> p(params.data() + (size_t)i * n, n);
         problems[i]->getParameterVector(p);
+    });
+    if (first_bad.load() < B)
+    {
+        fail("problems of one batch must share one structure (object " + std::to_string(first_bad.load()) + "): " + errors[0]);
+        return false;
     }
     if (b200sqp_set_problem_data(_handle, x0.data(), xref.data()) != 0 || b200sqp_set_params(_handle, params.data()) != 0)
     {
@@ -579,8 +618,7 @@ bool SolverB200Lm::solveBatch(const std::vector<OptimizationProblemInterface*>& 
         fail(std::string("solve failed: ") + b200sqp_last_error());
         return false;
     }
-    for (int i = 0; i < B; ++i)
-        problems[i]->setParameterVector(Eigen::Map<const Eigen::VectorXd>(params.data() + (size_t)i * n, n));
+    forEachObject(B, [&](int i) { problems[i]->setParameterVector(Eigen::Map<const Eigen::VectorXd>(params.data() + (size_t)i * n, n)); });
     if (statuses)
     {
         statuses->resize(B);
