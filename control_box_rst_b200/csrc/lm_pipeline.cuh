@@ -92,17 +92,9 @@ __device__ __forceinline__ void dmma884(double& d0, double& d1, double a, double
     asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};" : "+d"(d0), "+d"(d1) : "d"(a), "d"(b));
 }
 
-// models that expose trig()/fTrig() (dynamics.cuh): their angles' sines and cosines can be carried between evaluations
-template <class M, class = void>
-struct PipeTrig
-{
-    static constexpr bool value = false;
-};
+// models that expose trig()/fTrig() (dynamics.cuh HasTrig): their angles' sines and cosines can be carried between evaluations
 template <class M>
-struct PipeTrig<M, decltype((void)M::NANG)>
-{
-    static constexpr bool value = true;
-};
+using PipeTrig = HasTrig<M>;
 
 __device__ __forceinline__ size_t tiledSlot(int i, int slot, int nslots) { return ((size_t)(i >> 5) * nslots + slot) * 32 + (i & 31); }
 
