@@ -442,7 +442,14 @@ def main_b200(args):
     launches = lm.launch_count() - launches0
     clocks = sampler.stop() if rank == 0 else None
     t = torch.tensor([total_ms, kernel_ms], dtype=torch.float64, device=f"cuda:{local_rank}")
+    per_rank = None
     if world > 1:
+        # what every rank measured on its own device (the reported figures are the maxima): separates a slow GPU / rank skew from
+        # a cost that every rank pays (the exchange)
+        every = torch.empty(2 * world, dtype=torch.float64, device=f"cuda:{local_rank}")
+        dist.all_gather_into_tensor(every, t)
+        every = (every.view(world, 2) / args.steps).cpu().tolist()
+        per_rank = {"step_ms": [round(e[0], 5) for e in every], "kernel_ms": [round(e[1], 5) for e in every]}
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     total_ms, kernel_ms = float(t[0]), float(t[1])
     value = B * world * iterations * args.steps / (total_ms * 1e-3)
@@ -529,10 +536,16 @@ def main_b200(args):
                                  + (", ranks rendezvous on the device before each timed step" if world > 1 else "") + ", max over ranks",
                        "wall_s_timed_region_incl_flush": wall},
             "clocks": clocks,
-            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "ms_per_step": e2e_ms / args.steps},
-            "e2e_mpc_step": {"value": mpc_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": B * ocp.nu * 8 + B * 8 + B * 4,
-                             "ms_per_step": mpc_ms / args.steps,
-                             "note": "b200sqp_mpc_step: measured states in, first controls + chi2 + status out, trajectories stay in HBM"},
+            "per_rank": per_rank,
+            # the call a controller makes per MPC step (PredictiveController::step needs the first control, predictive_controller.cpp:46-79):
+            # pinned host buffers, H2D of the measured states + references, cold start, solve, D2H of first controls + chi2 + status
+            "e2e": {"value": mpc_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": B * ocp.nu * 8 + B * 8 + B * 4,
+                    "ms_per_step": mpc_ms / args.steps,
+                    "call": "b200sqp_mpc_step: measured states in, first controls + chi2 + status out; the optimised trajectories stay in HBM "
+                            "(b200sqp_get_params fetches them on demand)"},
+            # the same step with EVERY optimised trajectory copied back as well (b200sqp_step): 4.9 MB per 4096 instances
+            "e2e_full_trajectories": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                                      "ms_per_step": e2e_ms / args.steps, "call": "b200sqp_step"},
             "closed_loop": closed_loop,
             "gpu_launches": int(launches),
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "traffic_source": traffic_src,

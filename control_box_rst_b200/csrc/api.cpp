@@ -40,7 +40,9 @@ namespace b200sqp {
 
 const KernelSet* findKernels(int dynamics, int defect, int vt)
 {
-#ifdef B200SQP_DEV_VDP_CN_ONLY  // development build (make dev): only the benchmark kernels, seconds instead of minutes to compile
+#if defined(B200SQP_DEV_TRIO)  // development build (make dev3): the kernels of BASELINE configs[1..3] only
+    const KernelSet* (*tables[])(int*) = {kernelTableVdpCn, kernelTableCartPole, kernelTableUnicycle};
+#elif defined(B200SQP_DEV_VDP_CN_ONLY)  // development build (make dev): only the benchmark kernels, seconds instead of minutes to compile
     const KernelSet* (*tables[])(int*) = {kernelTableVdpCn};
 #else
     const KernelSet* (*tables[])(int*) = {kernelTableVdpCn,       kernelTableVdpFd,    kernelTableVdpMs,   kernelTableOscillators,
