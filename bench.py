@@ -44,6 +44,8 @@ def parse_args():
     ap.add_argument("--config", type=int, default=1, help="BASELINE.json configs[] index of the OCP (1 = Van der Pol N=50)")
     ap.add_argument("--batch", type=int, default=4096, help="instances per GPU (north_star target batch; weak scaling)")
     ap.add_argument("--cpu-sample", type=int, default=4096, help="instances of the same workload timed on the host cores")
+    ap.add_argument("--precision", default=None, choices=["f64", "f32"],
+                    help="arithmetic of the solve: f64 (the reference's; default) or f32 (default for --config 4, which BASELINE.json quotes in fp32)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-other-configs", action="store_true", help="skip the short runs of configs[2..4] appended to the default N=1 line")
     ap.add_argument("--collective", default="p2p", choices=["p2p", "nccl"],
@@ -52,9 +54,13 @@ def parse_args():
     return ap.parse_args()
 
 
-def workload_name(cfg, ocp, batch, iterations):
+def workload_name(cfg, ocp, batch, iterations, precision="f64"):
     names = {0: "van_der_pol_fd_n20", 1: "van_der_pol_fd_n50", 2: "unicycle_time_optimal_n50", 3: "cart_pole_shooting_n100", 4: "quadrotor_fd_n60"}
-    return f"{names[cfg]}_batch{batch}_per_gpu_fp64_{iterations}_lm_iterations_cold_start"
+    return f"{names[cfg]}_batch{batch}_per_gpu_{'fp32' if precision == 'f32' else 'fp64'}_{iterations}_lm_iterations_cold_start"
+
+
+def default_precision(args):
+    return args.precision or ("f32" if args.config == 4 else "f64")
 
 
 # ---------------------------------------------------------------------------------------------------------------------------
@@ -190,7 +196,7 @@ def run_cpu(ocp, opts, sample, seed):
 
 
 def b200_config_keys(args, ocp, n_params, world):
-    return {"workload": workload_name(args.config, ocp, args.batch, problems.config(args.config)[1]["iterations"]),
+    return {"workload": workload_name(args.config, ocp, args.batch, problems.config(args.config)[1]["iterations"], default_precision(args)),
             "instances_total": args.batch * world, "n_grid": ocp.n_grid, "n_params": n_params}
 
 
@@ -309,13 +315,14 @@ def other_configs(device, stream, hbm_peak, fp64_peak, with_cpu):
     from control_box_rst_b200 import solver
 
     out = {}
-    for cfg in (2, 3, 4):
+    for cfg, precision, key in ((2, "f64", "2"), (3, "f64", "3"), (4, "f32", "4"), (4, "f64", "4_f64")):
         try:
             ocp, kw, B = problems.config(cfg)
             iterations = kw["iterations"]
             lm = solver.BatchedLevenbergMarquardt(ocp, B, device=device)
             lm.setIterations(iterations)
             lm.setPenaltyWeights(*kw["weights"])
+            lm.set_precision(precision)
             lm.set_stream(stream.cuda_stream)
             x0, xref = problems.instance_data(ocp, B, seed=1234 + cfg)
             lm.set_problem_data(x0, xref)
@@ -332,21 +339,21 @@ def other_configs(device, stream, hbm_peak, fp64_peak, with_cpu):
                 if it > 0:  # the first step is the warm-up
                     total_ms += e0.elapsed_time(e1)
                     kernel_ms += lm.last_solve_ms()
-            alg = lm.dims.algorithmic_bytes_per_iteration * B * iterations
+            alg = lm.dims.algorithmic_bytes_per_iteration // (2 if precision == "f32" else 1) * B * iterations
             achieved = alg / (kernel_ms / steps * 1e-3) / 1e9
-            entry = {"workload": workload_name(cfg, ocp, B, iterations), "value": B * iterations * steps / (total_ms * 1e-3), "unit": UNIT,
+            entry = {"workload": workload_name(cfg, ocp, B, iterations, precision), "dtype": precision, "value": B * iterations * steps / (total_ms * 1e-3), "unit": UNIT,
                      "steps": steps, "ms_per_step": total_ms / steps, "kernel_ms": kernel_ms / steps,
                      "roofline": {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak},
                      "roofline_fp64": fp64_roofline(ocp, lm.dims, B, iterations, kernel_ms / steps, fp64_peak)}
             lm.clear()
             del flush
             torch.cuda.empty_cache()
-            if with_cpu:
+            if with_cpu and key != "4_f64":
                 opts = abi.LmOptions.defaults(iterations=iterations, weights=kw["weights"])
                 entry["cpu_baseline"] = cpu_baseline_entry(run_cpu(ocp, opts, CPU_SAMPLE_CAP[cfg], seed=1234 + cfg))
-            out[str(cfg)] = entry
+            out[key] = entry
         except Exception as exc:  # the main line must not depend on the extra configurations
-            out[str(cfg)] = {"error": f"{type(exc).__name__}: {exc}"}
+            out[key] = {"error": f"{type(exc).__name__}: {exc}"}
     return out
 
 
@@ -372,6 +379,9 @@ def main_b200(args):
     lm.setIterations(kw["iterations"])
     lm.setPenaltyWeights(*kw["weights"])
     iterations = kw["iterations"]
+    precision = default_precision(args)
+    lm.set_precision(precision)  # f32 raises for structures without a reduced-precision path
+    alg_bytes_per_iteration = lm.dims.algorithmic_bytes_per_iteration // (2 if precision == "f32" else 1)  # s = 8 (fp64) / 4 (fp32)
     # a dedicated (non-default) torch stream: the library launches on it, torch's events, the L2 flush and NCCL are ordered on it
     stream = torch.cuda.Stream(device=local_rank)
     torch.cuda.set_stream(stream)
@@ -523,12 +533,12 @@ def main_b200(args):
             peak, peak_src = float(json.load(open(peaks_path))["hbm_gbs"]), "MEASURED_PEAKS.json hbm_gbs (measured)"
         else:
             peak, peak_src = 6650.0, "B200_PROFILING.md fallback"
-        alg_bytes = lm.dims.algorithmic_bytes_per_iteration * B * iterations  # per launch of the LM kernel
+        alg_bytes = alg_bytes_per_iteration * B * iterations  # per launch of the LM kernel
         traffic, traffic_src = measured_traffic(workload_name(args.config, ocp, B, iterations).split("_per_gpu")[0])
         achieved = alg_bytes / (kernel_ms / args.steps * 1e-3) / 1e9
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": n_gpus, "steps": args.steps, "warmup": max(args.warmup, 3),
-            "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+            "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": precision,
             "data": "synthetic",
             "config": {**b200_config_keys(args, ocp, n, world), "parallelism": (f"instance-sharded x{world}, stop-test gather of chi2 fused into the LM kernel over NVLink peer memory"
                                        if use_p2p else f"instance-sharded x{world}, one NCCL chi2 all-gather per step") if world > 1 else "single GPU",

@@ -412,7 +412,22 @@ bool SolverB200Lm::describe(OptimizationProblemInterface& problem, b200sqp_ocp& 
     }
     else if (has_term_ball)
     {
-        const Eigen::MatrixXd& S = term_ball->getWeightS();
+        // TerminalBallInheritFromCost (final_state_constraints.h:98-128): the same row with S = Qf of the quadratic final cost
+        // (its update() copies the weight, final_state_constraints.cpp:170-194) and its OWN gamma member, which shadows TerminalBall's
+        auto* inherit = dynamic_cast<TerminalBallInheritFromCost*>(_final_constraint.get());
+        Eigen::MatrixXd S = term_ball->getWeightS();
+        double gamma      = term_ball->getGamma();
+        if (inherit)
+        {
+            auto* qf = dynamic_cast<QuadraticFinalStateCost*>(_final_cost.get());
+            if (!qf)
+            {
+                _error = "TerminalBallInheritFromCost needs the QuadraticFinalStateCost handed to setFinalStageCost()";
+                return false;
+            }
+            S     = qf->getWeightQf();
+            gamma = inherit->_gamma;
+        }
         if (S.rows() != d.nx || !S.isDiagonal(1e-10))  // TerminalBall::setWeightS switches to its diagonal mode by the same test
         {
             _error = "TerminalBall: only a diagonal weight S is in the device registry";
@@ -420,7 +435,7 @@ bool SolverB200Lm::describe(OptimizationProblemInterface& problem, b200sqp_ocp& 
         }
         d.final_constraint = B200SQP_FINAL_CONSTRAINT_BALL;
         for (int i = 0; i < d.nx; ++i) d.term_s_diag[i] = S(i, i);
-        d.term_gamma = term_ball->getGamma();
+        d.term_gamma = gamma;
     }
     return true;
 }

@@ -96,6 +96,8 @@ struct b200sqp_solver
     int loop_steps = 0;
     PipeArrays pipe{};          // warp-cooperative pipeline (large stage blocks), allocated when the kernel set has one and the
     bool use_pipeline = false;  // structure is eligible
+    PipeArraysF32 pipe32{};     // its reduced-precision twin (b200sqp_set_precision), allocated on first use
+    int precision = B200SQP_PRECISION_F64;
     bool pipeline_enabled = true;
     long long* d_phase_cycles = nullptr;
     int phase_blocks = 0;
@@ -156,6 +158,43 @@ void fillDeviceOcp(const Structure& s, int B, int S, DeviceOcp& P)
     P.tcost_w    = std::sqrt((double)(o.n_grid - 1));  // MinimumTime::update, lsq form (minimum_time.h:56-66)
     for (int i = 0; i < B200SQP_MAX_DYN_PARAMS; ++i) P.dyn.p[i] = o.dyn_params[i];
     prepareDynParams(P.dyn);
+}
+
+// device arrays of the warp-cooperative pipeline in precision Real; the small per-instance LM state arrays are shared between the
+// fp64 and the fp32 set (only one of them is in use during a solve)
+template <class Real>
+cudaError_t allocPipeArrays(b200sqp_handle h, PipeArraysT<Real>& pa)
+{
+    const size_t K = h->s.K, nb = h->s.nb, nx = h->s.nx, S = h->S;
+    const size_t nd = nb * (nb + 1) / 2, ne = nb * nx, BK = (size_t)h->B * K, nxxp = paddedTriangle((int)nx, (int)sizeof(Real));
+    cudaError_t e = cudaSuccess;
+    auto A = [&](auto** p, size_t cnt) {
+        if (e == cudaSuccess) e = h->alloc(p, cnt);
+    };
+    A(&pa.D, BK * nd);
+    A(&pa.E, BK * ne);
+    A(&pa.DA, BK * nxxp);
+    A(&pa.gA, BK * nx);
+    A(&pa.g, BK * nb);
+    A(&pa.L, BK * nd);
+    A(&pa.W, BK * ne);
+    A(&pa.y, BK * nb);
+    if (h->pipe.cpart && (void*)&pa != (void*)&h->pipe)
+    {
+        pa.cpart = h->pipe.cpart, pa.mu_acc = h->pipe.mu_acc, pa.last_values = h->pipe.last_values, pa.dn2 = h->pipe.dn2, pa.dq = h->pipe.dq;
+        pa.v = h->pipe.v, pa.k_outer = h->pipe.k_outer, pa.flags = h->pipe.flags, pa.any = h->pipe.any;
+        return e;
+    }
+    A(&pa.cpart, K * S);
+    A(&pa.mu_acc, S);
+    A(&pa.last_values, S);
+    A(&pa.dn2, S);
+    A(&pa.dq, S);
+    A(&pa.v, S);
+    A(&pa.k_outer, S);
+    A(&pa.flags, S);
+    A(&pa.any, 2);
+    return e;
 }
 
 int checkHandle(b200sqp_handle h)
@@ -350,28 +389,7 @@ int b200sqp_create(const b200sqp_ocp* ocp, int32_t batch, int32_t device, b200sq
     A(&h->d_value_rows, s.value_rows.size());
     A(&h->d_jac_pos, s.jac_pos.size());
     h->use_pipeline = ks->pipeline != nullptr && pipelineEligible(h->P, s.nx);
-    if (h->use_pipeline)
-    {
-        const size_t BK = (size_t)h->B * K, nxx = nx * (nx + 1) / 2;
-        PipeArrays& pa = h->pipe;
-        A(&pa.D, BK * nd);
-        A(&pa.E, BK * ne);
-        A(&pa.DA, BK * nxx);
-        A(&pa.gA, BK * nx);
-        A(&pa.g, BK * nb);
-        A(&pa.L, BK * nd);
-        A(&pa.W, BK * ne);
-        A(&pa.y, BK * nb);
-        A(&pa.cpart, K * S);
-        A(&pa.mu_acc, S);
-        A(&pa.last_values, S);
-        A(&pa.dn2, S);
-        A(&pa.dq, S);
-        A(&pa.v, S);
-        A(&pa.k_outer, S);
-        A(&pa.flags, S);
-        A(&pa.any, 2);
-    }
+    if (h->use_pipeline && e == cudaSuccess) e = allocPipeArrays(h, h->pipe);
     st.trace = nullptr;
     if (e == cudaSuccess)
         e = cudaMemcpyAsync(h->d_ref_of_internal, s.ref_of_internal.data(), sizeof(int) * s.ref_of_internal.size(), cudaMemcpyHostToDevice, h->stream);
@@ -603,12 +621,19 @@ int b200sqp_solve_async(b200sqp_handle h, const b200sqp_lm_options* opts, int32_
         h->peer_solves += 1;
     }
     CUDA_TRY(cudaEventRecord(h->ev_begin, h->stream));
-    if (h->use_pipeline && h->pipeline_enabled && !h->peer_attached)
+    if (h->use_pipeline && h->pipeline_enabled)
     {
         // large stage blocks: warp-cooperative multi-kernel pipeline, host-driven passes (blocks until the batch is solved)
-        if (!h->kernels->pipeline(h->P, h->st, h->pipe, opts->iterations, h->stream))
-            return fail(B200SQP_ERR_CUDA, "LM pipeline exceeded its pass bound");
+        const bool ok = h->precision == B200SQP_PRECISION_F32 ? h->kernels->pipeline_f32(h->P, h->st, h->pipe32, opts->iterations, h->stream)
+                                                              : h->kernels->pipeline(h->P, h->st, h->pipe, opts->iterations, h->stream);
+        if (!ok) return fail(B200SQP_ERR_CUDA, "LM pipeline exceeded its pass bound");
         h->launches += 4 * (int64_t)(opts->iterations + 1);
+        if (h->peer_attached)
+        {
+            // the fused kernel's epilogue as a launch of its own: chi2 into every rank's gather buffer + arrival counters
+            launchPeerPublish(h->st, h->B, h->stream);
+            h->launches += 1;
+        }
     }
     else
     {
@@ -1015,6 +1040,28 @@ int b200sqp_set_threads_per_instance(b200sqp_handle h, int32_t threads)
     h->pipeline_enabled = threads != -1;
     if (threads < 0) threads = 0;
     h->threads_per_instance = threads;
+    return B200SQP_OK;
+}
+
+int b200sqp_set_precision(b200sqp_handle h, int32_t precision)
+{
+    int rc = checkHandle(h);
+    if (rc) return rc;
+    if (precision != B200SQP_PRECISION_F64 && precision != B200SQP_PRECISION_F32) return fail(B200SQP_ERR_INVALID, "unknown precision");
+    if (precision == B200SQP_PRECISION_F32)
+    {
+        if (!h->use_pipeline || !h->kernels->pipeline_f32)
+            return fail(B200SQP_ERR_UNSUPPORTED, "the fp32 variant exists for structures that run the warp-cooperative pipeline (large stage blocks: "
+                                                 "quadrotor on the fixed-dt grid); everything else is fp64 only -- the reference's 1e-9 central "
+                                                 "differences do not exist in fp32");
+        if (!h->pipe32.D)
+        {
+            cudaError_t e = allocPipeArrays(h, h->pipe32);
+            if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
+            if (e != cudaSuccess) return fail(B200SQP_ERR_CUDA, std::string("fp32 pipeline arrays: ") + cudaGetErrorString(e));
+        }
+    }
+    h->precision = precision;
     return B200SQP_OK;
 }
 

@@ -28,6 +28,15 @@ __device__ __forceinline__ double divByParam(const DynParams& c, int i, double x
     return x / c.p[i];
 }
 
+// scalar-type helpers for models that also exist in reduced precision (the fp32 variant of the warp-cooperative pipeline)
+__device__ __forceinline__ void sincosT(double a, double* s, double* c) { sincos(a, s, c); }
+__device__ __forceinline__ void sincosT(float a, float* s, float* c) { sincosf(a, s, c); }
+__device__ __forceinline__ float divByParam(const DynParams& c, int i, float x)
+{
+    // fp32: the reciprocal the host prepared (rounded to float) where admissible; no bit-parity to keep in this precision
+    return (c.fast_div_mask & (1u << i)) ? x * (float)c.rcp[i] : x / (float)c.p[i];
+}
+
 // VanDerPolOscillator::dynamics -- src/systems/include/corbo-systems/benchmark/nonlinear_benchmark_systems.h:52-60
 struct VanDerPol
 {
@@ -242,30 +251,33 @@ struct Quadrotor
     // The attitude angles x[3..5] enter only through their sines and cosines: callers that evaluate f at many points which share
     // most angles (the finite-difference columns of the pipeline, lm_pipeline.cuh) keep the six values and refresh one pair.
     static constexpr int NANG = 3, ANG0 = 3;
-    __device__ __forceinline__ static void trig(const double* x, double* sc /*[2*NANG]: sin, cos per angle*/)
+    // templated on the scalar type: double everywhere, float only in the reduced-precision pipeline (b200sqp_set_precision)
+    template <class T>
+    __device__ __forceinline__ static void trig(const T* x, T* sc /*[2*NANG]: sin, cos per angle*/)
     {
-        sincos(x[3], &sc[0], &sc[1]);  // one argument reduction per angle; same values as separate sin()/cos()
-        sincos(x[4], &sc[2], &sc[3]);
-        sincos(x[5], &sc[4], &sc[5]);
+        sincosT(x[3], &sc[0], &sc[1]);  // one argument reduction per angle; same values as separate sin()/cos()
+        sincosT(x[4], &sc[2], &sc[3]);
+        sincosT(x[5], &sc[4], &sc[5]);
     }
-    __device__ __forceinline__ static void fTrig(const DynParams& c, const double* x, const double* u, const double* sc, double* out)
+    template <class T>
+    __device__ __forceinline__ static void fTrig(const DynParams& c, const T* x, const T* u, const T* sc, T* out)
     {
-        const double sphi = sc[0], cphi = sc[1], sth = sc[2], cth = sc[3], spsi = sc[4], cpsi = sc[5];
-        const double p = x[9], q = x[10], r = x[11];
-        const double tm = divByParam(c, 0, u[0]);
-        out[0]          = x[6];
-        out[1]          = x[7];
-        out[2]          = x[8];
-        const double qr = q * sphi + r * cphi;
-        out[3]          = p + qr * (sth / cth);
-        out[4]          = q * cphi - r * sphi;
-        out[5]          = qr / cth;
-        out[6]          = (cphi * sth * cpsi + sphi * spsi) * tm;
-        out[7]          = (cphi * sth * spsi - sphi * cpsi) * tm;
-        out[8]          = cphi * cth * tm - c.p[1];
-        out[9]          = divByParam(c, 2, u[1] + (c.p[3] - c.p[4]) * q * r);
-        out[10]         = divByParam(c, 3, u[2] + (c.p[4] - c.p[2]) * p * r);
-        out[11]         = divByParam(c, 4, u[3] + (c.p[2] - c.p[3]) * p * q);
+        const T sphi = sc[0], cphi = sc[1], sth = sc[2], cth = sc[3], spsi = sc[4], cpsi = sc[5];
+        const T p = x[9], q = x[10], r = x[11];
+        const T tm = divByParam(c, 0, u[0]);
+        out[0]     = x[6];
+        out[1]     = x[7];
+        out[2]     = x[8];
+        const T qr = q * sphi + r * cphi;
+        out[3]     = p + qr * (sth / cth);
+        out[4]     = q * cphi - r * sphi;
+        out[5]     = qr / cth;
+        out[6]     = (cphi * sth * cpsi + sphi * spsi) * tm;
+        out[7]     = (cphi * sth * spsi - sphi * cpsi) * tm;
+        out[8]     = cphi * cth * tm - (T)c.p[1];
+        out[9]     = divByParam(c, 2, u[1] + (T)(c.p[3] - c.p[4]) * q * r);
+        out[10]    = divByParam(c, 3, u[2] + (T)(c.p[4] - c.p[2]) * p * r);
+        out[11]    = divByParam(c, 4, u[3] + (T)(c.p[2] - c.p[3]) * p * q);
     }
     __device__ __forceinline__ static void f(const DynParams& c, const double* x, const double* u, double* out)
     {

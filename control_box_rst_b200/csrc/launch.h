@@ -7,7 +7,8 @@ namespace b200sqp {
 
 struct DeviceOcp;
 struct DeviceState;
-struct PipeArrays;
+template <class Real>
+struct PipeArraysT;
 
 enum { SOLVE_FORCE_GENERAL_FEATURES = 1 };  // flags of KernelSet::solve
 
@@ -19,7 +20,9 @@ struct KernelSet
     void (*evaluate)(const DeviceOcp&, const DeviceState&, double* values, double* jac, const int* value_rows, const int* jac_pos, int v_count,
                      int j_count, cudaStream_t);
     // warp-cooperative pipeline for large stage blocks (lm_pipeline.cuh) or nullptr; blocks the host, false = pass bound hit
-    bool (*pipeline)(const DeviceOcp&, const DeviceState&, const PipeArrays&, int iterations, cudaStream_t);
+    bool (*pipeline)(const DeviceOcp&, const DeviceState&, const PipeArraysT<double>&, int iterations, cudaStream_t);
+    // the same in reduced precision (normal equations and factor in fp32; b200sqp_set_precision) or nullptr
+    bool (*pipeline_f32)(const DeviceOcp&, const DeviceState&, const PipeArraysT<float>&, int iterations, cudaStream_t);
 };
 
 // closed registry (kernels_*.cu); nullptr = combination not compiled in -> B200SQP_ERR_UNSUPPORTED, never a CPU fallback
@@ -82,6 +85,9 @@ bool launchPlantStep(int dynamics, const DynParams& dyn, int integrator, double 
 // per-instance search kernel and a per-(instance, block) move into the instance's other parameter buffer (roles swap); plan [B] scratch
 void launchWarmStartShift(const double* x0_new /*[B][nx]*/, double* x0 /*tiled*/, double* z0, double* z1, int* cur, int K, int nx, int nu,
                           int* plan /*[B]*/, int* num_shift /*[B] or null*/, int B, cudaStream_t);
+// epilogue of a solve that did not run the fused LM kernel (the pipeline): stores chi2 of this rank's instances into every rank's gather
+// buffer and bumps the arrival counters, with the same protocol and the same number of arriving thread blocks as lmSolveKernel's epilogue
+void launchPeerPublish(const DeviceState& st, int B, cudaStream_t);
 // bounded spin on the arrival counters of the fused peer-memory gather (b200sqp_peer_wait)
 void launchPeerWait(const unsigned long long* arrivals, int world, unsigned long long expected, unsigned long long timeout_ns, int* timed_out,
                     cudaStream_t);

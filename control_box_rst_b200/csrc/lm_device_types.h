@@ -91,27 +91,40 @@ struct DeviceState
     double w_eq, w_ineq, w_b;  // current penalty weights (host-managed: reset / adapted per solve)
 };
 
-// device arrays of the warp-cooperative pipeline for large stage blocks (lm_pipeline.cuh); Hessian blocks instance-major
-struct PipeArrays
+// device arrays of the warp-cooperative pipeline for large stage blocks (lm_pipeline.cuh); Hessian blocks instance-major.
+// Real = double, or float for the reduced-precision variant of BASELINE configs[4] (b200sqp_set_precision): the normal equations and
+// their factor are then evaluated, stored and factorised in fp32 (half the HBM traffic of the factorisation, twice the FMA rate),
+// while parameters, steps, residual norms and the LM control state stay fp64.
+template <class Real>
+struct PipeArraysT
 {
-    double* D;    // [B][K][nb(nb+1)/2] G^T G of block k (packed lower by rows) + diagonal cost / bound rows
-    double* E;    // [B][K][nb*nx]      coupling of block k to the x-part of block k-1
-    double* DA;   // [B][K][nx(nx+1)/2] A^T A of interval k: belongs to the x-x part of block k-1
-    double* gA;   // [B][K][nx]         -A^T e of interval k: belongs to the x-part of g of block k-1
-    double* g;    // [B][K][nb]
-    double* L;    // [B][K][nb(nb+1)/2] Cholesky factor blocks (reciprocal diagonal)
-    double* W;    // [B][K][nb*nx]
-    double* y;    // [B][K][nb]         forward-substituted right-hand side
+    Real* D;    // [B][K][nb(nb+1)/2] G^T G of block k (packed lower by rows) + diagonal cost / bound rows
+    Real* E;    // [B][K][nb*nx]      coupling of block k to the x-part of block k-1
+    Real* DA;   // [B][K][nxxp]       A^T A of interval k: belongs to the x-x part of block k-1 (nxxp = nx(nx+1)/2 rounded up to 16 bytes)
+    Real* gA;   // [B][K][nx]         -A^T e of interval k: belongs to the x-part of g of block k-1
+    Real* g;    // [B][K][nb]
+    Real* L;    // [B][K][nb(nb+1)/2] Cholesky factor blocks (reciprocal diagonal)
+    Real* W;    // [B][K][nb*nx]
+    Real* y;    // [B][K][nb]         forward-substituted right-hand side
     double* cpart;        // [K][S] residual norm per interval (linearisation point / trial point)
     double* mu_acc;       // [S] damping accumulated on the diagonal since the last linearisation
     double* last_values;  // [S]
-    double* dn2;          // [S] ||delta||^2
+    double* dn2;          // [S] ||delta||^2 (NaN: the factorisation of this pass failed -> the control kernel rejects the step)
     double* dq;           // [S] delta^T (mu delta + g)
     unsigned* v;          // [S]
     int* k_outer;         // [S]
     int* flags;           // [S] PF_ACTIVE | PF_LIN | PF_STOP
     int* any;             // [2] any instance active / any instance to re-linearise
 };
+using PipeArrays    = PipeArraysT<double>;
+using PipeArraysF32 = PipeArraysT<float>;
+
+// packed size of an nx x nx lower triangle, padded so that consecutive blocks stay 16-byte aligned for the bulk copies
+inline int paddedTriangle(int nx, int bytes_per_value)
+{
+    const int n = nx * (nx + 1) / 2, per16 = 16 / bytes_per_value;
+    return (n + per16 - 1) / per16 * per16;
+}
 
 // structures the pipeline covers (lm_pipeline.cuh); everything else runs through the fused kernel
 inline bool pipelineEligible(const DeviceOcp& P, int nx)

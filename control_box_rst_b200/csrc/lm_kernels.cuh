@@ -465,6 +465,6 @@ void launchEvaluate(const DeviceOcp& P, const DeviceState& st, double* values, d
 // the same plus the warp-cooperative pipeline (include lm_pipeline.cuh); fixed-dt grids only
 #define B200SQP_KERNEL_ENTRY_PIPELINE(MODEL, DEFECT, MAXT)                                                                            \
     KernelSet { MODEL::ID, DEFECT, 0, MODEL::NX, MODEL::NU, MAXT, &launchSolve<MODEL, DEFECT, 0, MAXT>, &launchEvaluate<MODEL, DEFECT, 0>, \
-                &launchPipeline<MODEL, DEFECT> }
+                &launchPipeline<MODEL, DEFECT>, &launchPipelineF32<MODEL, DEFECT> }
 
 }  // namespace b200sqp

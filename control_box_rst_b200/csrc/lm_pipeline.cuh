@@ -23,6 +23,12 @@
 // Differences to the fused kernel (both within the FD-noise floor): the in-place perturbation drift of the
 // parameters (+d, -2d, +d leaves ~1 ulp) is applied inside one Jacobian evaluation exactly as the reference orders it, but not
 // carried into the stored parameters between evaluations; the elimination order inside a block differs.
+// Reduced precision (BASELINE configs[4] names fp32; b200sqp_set_precision): every kernel below is templated on the scalar type `Real`.
+// With Real = float the Jacobian columns are central differences with delta = 2^-10 evaluated in fp32 (the reference's delta = 1e-9
+// does not exist in fp32), the normal equations, their Cholesky factor and the substitutions are fp32 (half the HBM traffic of the
+// factorisation, twice the FMA rate, cheap sincosf), the Gram products run on the FMA pipe instead of the fp64 tensor-core tiles;
+// parameters, steps, the trial-point residuals (pipeTrialKernel) and the whole LM control state stay fp64.  Parity of that variant is
+// judged against the fp64 oracle at 1e-3 relative on the trajectories, not bit-wise.
 // Eligibility (else the fused kernel runs): fixed-dt FD grid or shooting grid, quadratic lsq stage cost, no state bounds, no
 // pinned goal components, no final-stage constraint.
 #pragma once
@@ -42,7 +48,61 @@ struct PipeDim
     static constexpr int NX = M::NX, NU = M::NU, NB = NU + NX, NV = 2 * NX + NU;
     static constexpr int ND = NB * (NB + 1) / 2, NE = NB * NX, NXX = NX * (NX + 1) / 2;
     static_assert(NV <= 31, "one lane per Jacobian column plus one lane for the unperturbed values");
+    // storage stride of the A^T A triangles: padded to a multiple of 16 bytes for the bulk copies (lm_device_types.h paddedTriangle)
+    template <class Real>
+    struct Padded
+    {
+        static constexpr int per16 = 16 / (int)sizeof(Real);
+        static constexpr int nxxp  = (NXX + per16 - 1) / per16 * per16;
+    };
 };
+
+// finite-difference step of the Jacobian columns: the reference's 1e-9 in fp64; 2^-10 in fp32 (rounding ~ 6e-8 / 2^-10 = 6e-5 relative,
+// truncation ~ delta^2 = 1e-6: the Jacobian carries ~1e-4 relative error, far inside the 1e-3 trajectory tolerance of that variant)
+template <class Real>
+struct FdStep;
+template <>
+struct FdStep<double>
+{
+    static constexpr double delta = 1e-9;
+};
+template <>
+struct FdStep<float>
+{
+    static constexpr float delta = 0.0009765625f;
+};
+
+// x / dt in the precision of the pipeline: the correctly rounded sequence of dynamics.cuh in fp64, a plain multiplication by the reciprocal in fp32
+template <class Real>
+struct StepSizeT;
+template <>
+struct StepSizeT<double> : public StepSize
+{
+    __device__ __forceinline__ explicit StepSizeT(double t) : StepSize(t) {}
+};
+template <>
+struct StepSizeT<float>
+{
+    float dt, rcp;
+    __device__ __forceinline__ explicit StepSizeT(double t) : dt((float)t), rcp((float)(1.0 / t)) {}
+    __device__ __forceinline__ float div(float x) const { return x * rcp; }
+};
+
+__device__ __forceinline__ float pivotRsqrtT(float d)
+{
+    const float y = rsqrtf(d);
+    return y * (1.5f - 0.5f * d * y * y);  // one Newton step on the hardware approximation
+}
+__device__ __forceinline__ double pivotRsqrtT(double d)
+{
+    double y;
+    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(d));  // BlockSolver::pivotRsqrt (lm_device.cuh)
+    const double e = fma(-d * y, y, 1.0);
+    const double p = fma(e, 0.375, 0.5);
+    return fma(y * e, p, y);
+}
+__device__ __forceinline__ float fmaT(float a, float b, float c) { return fmaf(a, b, c); }
+__device__ __forceinline__ double fmaT(double a, double b, double c) { return fma(a, b, c); }
 
 __device__ __forceinline__ double driftRoundTrip(double v)
 {
@@ -52,6 +112,7 @@ __device__ __forceinline__ double driftRoundTrip(double v)
     v += 1e-9;
     return v;
 }
+__device__ __forceinline__ float driftRoundTrip(float v) { return v; }  // fp32 variant: no bit-parity to keep
 
 // ---- TMA bulk copies (cp.async.bulk, 1-D) with mbarrier completion: the factor kernel prefetches the next Hessian block from HBM
 //      into shared memory while the current one is eliminated (SASS: UBLKCP / SYNCS)
@@ -101,21 +162,24 @@ __device__ __forceinline__ size_t tiledSlot(int i, int slot, int nslots) { retur
 // ---------------------------------------------------------------------------------------------------------------------------
 // linearise: one warp per (instance, interval)
 // ---------------------------------------------------------------------------------------------------------------------------
-template <class M, int DEFECT>
+template <class M, int DEFECT, class Real>
 __global__ void __launch_bounds__(128, 4) pipeLinearizeKernel(const __grid_constant__ DeviceOcp P, const __grid_constant__ DeviceState st,
-                                                           const __grid_constant__ PipeArrays pa)
+                                                           const __grid_constant__ PipeArraysT<Real> pa)
 {
     using Pd = PipeDim<M>;
-    constexpr int NX = Pd::NX, NU = Pd::NU, NB = Pd::NB, NV = Pd::NV, ND = Pd::ND, NE = Pd::NE, NXX = Pd::NXX;
-    constexpr double delta = 1e-9, neg2delta = -2 * delta, scalar = 1.0 / (2 * delta);
+    constexpr int NX = Pd::NX, NU = Pd::NU, NB = Pd::NB, NV = Pd::NV, ND = Pd::ND, NE = Pd::NE, NXXP = Pd::template Padded<Real>::nxxp;
+    constexpr bool F64 = sizeof(Real) == 8;
+    constexpr Real delta = FdStep<Real>::delta, neg2delta = -2 * delta, scalar = Real(1) / (2 * delta);
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
     const int K    = P.K;
     const long long warp = (long long)blockIdx.x * 4 + wib;
     const int i = (int)(warp / K), k = (int)(warp % K);
-    __shared__ double sG[4][NV][NX + 1];  // Jacobian columns of the dynamics edge, [column][row] (padded: conflict-free column writes)
-    __shared__ double sE0[4][NX];     // weighted defect at the unperturbed point
-    __shared__ double sCost[4][4][NB > NX ? NB : NX];  // 0: cost value, 1: cost Jacobian (diagonal), 2: bound value, 3: bound Jacobian, per block slot
-    __shared__ double sX0c[4][NX];
+    // Jacobian columns of the dynamics edge, [column][row]; fp64: padded by one (conflict-free column writes, scalar fragment reads);
+    // fp32: rows of NX floats = whole 16-byte vectors (the Gram products read them as float4)
+    constexpr int GS = F64 ? NX + 1 : NX;
+    __shared__ __align__(16) Real sG[4][NV][GS];
+    __shared__ __align__(16) Real sE0[4][NX];     // weighted defect at the unperturbed point
+    __shared__ Real sCost[4][4][NB > NX ? NB : NX];  // 0: cost value, 1: cost Jacobian (diagonal), 2: bound value, 3: bound Jacobian, per block slot
     __shared__ unsigned char sTriR[ND], sTriC[ND];
     for (int idx = threadIdx.x; idx < ND; idx += blockDim.x)
     {
@@ -127,7 +191,7 @@ __global__ void __launch_bounds__(128, 4) pipeLinearizeKernel(const __grid_const
     __syncthreads();
     if (i >= P.B || !(pa.flags[i] & PF_LIN)) return;
 
-    const Weights w{st.w_eq, st.w_ineq, st.w_b};
+    const Real w_eq = (Real)st.w_eq, w_b = (Real)st.w_b;
     const double* z = st.z[st.cur[i]];
     const int slots = K * NB;
     const bool last = (k == K - 1);
@@ -135,17 +199,17 @@ __global__ void __launch_bounds__(128, 4) pipeLinearizeKernel(const __grid_const
     const double* xs_w = last ? P.qf_sqrt : P.q_sqrt;
 
     // ---- operands: lane q < NV loads component q of [x_k | u_k | x_{k+1}], lane q < NX also the reference state; all-to-all by shuffles
-    double mine = 0.0, mref = 0.0;
+    Real mine = 0, mref = 0;
     if (lane < NX)
     {
-        mine = (k > 0) ? z[tiledSlot(i, (k - 1) * NB + NU + lane, slots)] : st.x0[tiledSlot(i, lane, NX)];
-        mref = st.xref[tiledSlot(i, lane, NX)];
+        mine = (Real)((k > 0) ? z[tiledSlot(i, (k - 1) * NB + NU + lane, slots)] : st.x0[tiledSlot(i, lane, NX)]);
+        mref = (Real)st.xref[tiledSlot(i, lane, NX)];
     }
     else if (lane < NX + NU)
-        mine = z[tiledSlot(i, k * NB + (lane - NX), slots)];
+        mine = (Real)z[tiledSlot(i, k * NB + (lane - NX), slots)];
     else if (lane < NV)
-        mine = z[tiledSlot(i, k * NB + NU + (lane - NX - NU), slots)];
-    double v[NV], xr[NX];
+        mine = (Real)z[tiledSlot(i, k * NB + NU + (lane - NX - NU), slots)];
+    Real v[NV], xr[NX];
 #pragma unroll
     for (int q = 0; q < NV; ++q) v[q] = __shfl_sync(0xffffffffu, mine, q);
 #pragma unroll
@@ -156,13 +220,14 @@ __global__ void __launch_bounds__(128, 4) pipeLinearizeKernel(const __grid_const
     //      edge and the dynamics edge of interval k-1): computeCombinedSparseJacobian visits all lsq edges first (:1495-1525), then
     //      the equality edges in order (:1531-1559).  Components in front of p have completed this edge's round trip as well.
     //      Lanes >= NV evaluate the unperturbed point (the `values` the LM loop computed before the Jacobian).
+    //      (fp32: driftRoundTrip is the identity -- there is no bit-parity to keep in that precision.)
     const int p = lane;
     const bool col_lane = p < NV && (k > 0 || p >= NX);  // x_0 is fixed: no columns for it
-    double vec[NV];
+    Real vec[NV];
 #pragma unroll
     for (int q = 0; q < NV; ++q)
     {
-        double b = v[q];
+        Real b = v[q];
         if (p < NV)
         {
             if (q < NX)
@@ -178,26 +243,26 @@ __global__ void __launch_bounds__(128, 4) pipeLinearizeKernel(const __grid_const
         }
         vec[q] = b;
     }
-    StepSize h(P.dt_ref);
-    double e2[NX], e1[NX];
+    StepSizeT<Real> h(P.dt_ref);
+    Real e2[NX], e1[NX];
     if constexpr (DEFECT == DEFECT_CRANK_NICOLSON && PipeTrig<M>::value)
     {
         // The model's angles enter only through sin/cos and a column perturbs at most one of them: keep the sines and cosines of
         // both states from the +delta evaluation and refresh the one pair the perturbation touched for the -delta evaluation (one
         // uniform sincos per lane instead of six; same arguments -> same values as evaluating f from scratch).
         constexpr int NA = M::NANG, A0 = M::ANG0;
-        double sc1[2 * NA], sc2[2 * NA];
+        Real sc1[2 * NA], sc2[2 * NA];
         M::trig(vec, sc1);
         M::trig(vec + NX + NU, sc2);
-        auto cn = [&](double* e) {
-            double f1[NX], f2[NX];
+        auto cn = [&](Real* e) {
+            Real f1[NX], f2[NX];
             M::fTrig(P.dyn, vec, vec + NX, sc1, f1);
             M::fTrig(P.dyn, vec + NX + NU, vec + NX, sc2, f2);
 #pragma unroll
-            for (int j = 0; j < NX; ++j) e[j] = h.div(vec[NX + NU + j] - vec[j]) - 0.5 * (f1[j] + f2[j]);  // dynamics.cuh defect<>, Crank-Nicolson
+            for (int j = 0; j < NX; ++j) e[j] = h.div(vec[NX + NU + j] - vec[j]) - Real(0.5) * (f1[j] + f2[j]);  // dynamics.cuh defect<>, Crank-Nicolson
         };
         cn(e2);
-        double ang = 0.0;
+        Real ang = 0;
 #pragma unroll
         for (int q = 0; q < NV; ++q)
             if (q == p)
@@ -205,8 +270,8 @@ __global__ void __launch_bounds__(128, 4) pipeLinearizeKernel(const __grid_const
                 vec[q] += neg2delta;
                 ang = vec[q];
             }
-        double sa, ca;
-        sincos(ang, &sa, &ca);
+        Real sa, ca;
+        sincosT(ang, &sa, &ca);
 #pragma unroll
         for (int a = 0; a < NA; ++a)
         {
@@ -225,73 +290,79 @@ __global__ void __launch_bounds__(128, 4) pipeLinearizeKernel(const __grid_const
     }
     else
     {
-        defect<M, DEFECT>(P.dyn, vec, vec + NX, vec + NX + NU, h, e2);  // inlined: the operands stay in registers
+        static_assert(F64 || (DEFECT == DEFECT_CRANK_NICOLSON && PipeTrig<M>::value), "the fp32 variant exists for the trig-cached Crank-Nicolson path");
+        if constexpr (F64)
+        {
+            defect<M, DEFECT>(P.dyn, vec, vec + NX, vec + NX + NU, h, e2);  // inlined: the operands stay in registers
 #pragma unroll
-        for (int q = 0; q < NV; ++q)
-            if (q == p) vec[q] += neg2delta;
-        defect<M, DEFECT>(P.dyn, vec, vec + NX, vec + NX + NU, h, e1);
+            for (int q = 0; q < NV; ++q)
+                if (q == p) vec[q] += neg2delta;
+            defect<M, DEFECT>(P.dyn, vec, vec + NX, vec + NX + NU, h, e1);
+        }
     }
     if (p < NV)
     {
 #pragma unroll
-        for (int j = 0; j < NX; ++j) sG[wib][p][j] = col_lane ? scalar * (e2[j] - e1[j]) * w.eq : 0.0;
+        for (int j = 0; j < NX; ++j) sG[wib][p][j] = col_lane ? scalar * (e2[j] - e1[j]) * w_eq : Real(0);
     }
     else if (p == NV)
     {
 #pragma unroll
-        for (int j = 0; j < NX; ++j) sE0[wib][j] = e2[j] * w.eq;  // levenberg_marquardt_sparse.cpp:231-235
+        for (int j = 0; j < NX; ++j) sE0[wib][j] = e2[j] * w_eq;  // levenberg_marquardt_sparse.cpp:231-235
     }
 
     // ---- lsq cost and bound rows of the block slots [u_k | x_{k+1}] (diagonal): lane s < NB handles slot s
-    double cpart = 0.0;
+    double cpart = 0.0;  // residual norms are accumulated in fp64 in both variants (the gain ratio differences them)
     if (lane < NB)
     {
         const int s = lane;
-        double cv, cj, bv = 0.0, bj = 0.0;
+        Real cv, cj, bv = 0, bj = 0;
         if (s < NU)
         {
             // QuadraticFormCost::computeNonIntegralControlTerm, lsq + diagonal (quadratic_cost.cpp:146-154), FD like any edge
-            double u = v[NX + s];
-            cv       = P.r_sqrt[s] * u;
+            const Real rs = (Real)P.r_sqrt[s];
+            Real u        = v[NX + s];
+            cv            = rs * u;
             u += delta;
-            const double v2 = P.r_sqrt[s] * u;
+            const Real v2 = rs * u;
             u += neg2delta;
-            const double v1 = P.r_sqrt[s] * u;
-            cj              = scalar * (v2 - v1);
+            const Real v1 = rs * u;
+            cj            = scalar * (v2 - v1);
             if (P.u_bounded[s])
             {
-                bv = boundDist(v[NX + s], P.u_lb[s], P.u_ub[s]) * w.b;
-                bj = boundJac(driftRoundTrip(driftRoundTrip(v[NX + s])), P.u_lb[s], P.u_ub[s], w.b);  // bounds rows come last (:1721-1752)
+                bv = (Real)(boundDist((double)v[NX + s], P.u_lb[s], P.u_ub[s])) * w_b;
+                bj = (Real)boundJac((double)driftRoundTrip(driftRoundTrip(v[NX + s])), P.u_lb[s], P.u_ub[s], (double)w_b);  // bounds rows come last (:1721-1752)
             }
         }
         else
         {
             const int j = s - NU;
-            double x    = v[NX + NU + j];
-            cv = cj = 0.0;
+            Real x      = v[NX + NU + j];
+            cv = cj = 0;
             if (has_xs)
             {
-                cv = xs_w[j] * (x - xr[j]);  // quadratic_cost.cpp:105-123 / final_state_cost.cpp:73-90
+                const Real ws = (Real)xs_w[j];
+                cv = ws * (x - xr[j]);  // quadratic_cost.cpp:105-123 / final_state_cost.cpp:73-90
                 x += delta;
-                const double v2 = xs_w[j] * (x - xr[j]);
+                const Real v2 = ws * (x - xr[j]);
                 x += neg2delta;
-                const double v1 = xs_w[j] * (x - xr[j]);
-                cj              = scalar * (v2 - v1);
+                const Real v1 = ws * (x - xr[j]);
+                cj            = scalar * (v2 - v1);
             }
         }
         sCost[wib][0][s] = cv;
         sCost[wib][1][s] = cj;
         sCost[wib][2][s] = bv;
         sCost[wib][3][s] = bj;
-        cpart            = fma(cv, cv, bv * bv);
+        cpart            = fma((double)cv, (double)cv, (double)bv * (double)bv);
     }
     if (k == 0 && lane < NX)
     {
-        const double c = P.q_sqrt[lane] * (v[lane] - xr[lane]);  // cost edge on the fixed start state: value only
+        const double c = (double)((Real)P.q_sqrt[lane] * (v[lane] - xr[lane]));  // cost edge on the fixed start state: value only
         cpart          = fma(c, c, cpart);
     }
     __syncwarp();
-    if (lane < NX) cpart = fma(sE0[wib][lane], sE0[wib][lane], cpart);
+    if (lane < NX) cpart = fma((double)sE0[wib][lane], (double)sE0[wib][lane], cpart);
     // residual norm of this interval: fixed-order warp-shuffle reduction
 #pragma unroll
     for (int off = 16; off > 0; off >>= 1) cpart += __shfl_down_sync(0xffffffffu, cpart, off);
@@ -300,101 +371,133 @@ __global__ void __launch_bounds__(128, 4) pipeLinearizeKernel(const __grid_const
     // ---- normal equations: the lanes share out the entries.  Block k = G^T G over the columns of [u_k | x_{k+1}] (+ diagonal cost /
     //      bound rows), E_k = G^T A, and A^T A / A^T e go to block k-1 (stored separately: the factorisation adds them).
     const size_t blk = (size_t)i * K + k;
-    double* Dk  = pa.D + blk * ND;
-    double* gk  = pa.g + blk * NB;
-    // The three Gram products -- G_b G_b^T (nb x nb), G_b G_a^T (nb x nx), G_a G_a^T (nx x nx), inner dimension nx -- run on the
-    // tensor cores: fp64 mma.sync m8n8k4 tiles (SASS: DMMA) with fragments read straight from the column store in shared memory.
-    // Rows >= nx of a "G_a" tile are columns of G_b (the store is contiguous): those products are computed and dropped.
-    static_assert(NX % 4 == 0 && NB <= 16 && NX <= 16, "8x8 output tiles over a 16-column window, k in steps of 4");
-    const int fm = lane >> 2, fk = lane & 3;  // fragment coordinates: A(m = fm, k = fk), B(k = fk, n = fm), C(m = fm, n = 2 fk + {0,1})
-    auto gram = [&](int row_base, int r0, int col_base, int c0, double& d0, double& d1) {
-        d0 = 0.0;
-        d1 = 0.0;
-#pragma unroll
-        for (int k0 = 0; k0 < NX; k0 += 4)
-        {
-            const double af = sG[wib][row_base + r0 + fm][k0 + fk];
-            const double bf = sG[wib][col_base + c0 + fm][k0 + fk];
-            dmma884(d0, d1, af, bf);
-        }
-    };
-    // block k: G_b G_b^T, lower triangle, + the diagonal cost / bound rows
-#pragma unroll
-    for (int t = 0; t < 3; ++t)
+    Real* Dk  = pa.D + blk * ND;
+    Real* gk  = pa.g + blk * NB;
+    static_assert(NX % 4 == 0 && NB <= 16 && NX <= 16, "8x8 output tiles over a 16-column window, k in steps of 4 / float4 rows");
+    if constexpr (F64)
     {
-        const int r0 = (t == 0) ? 0 : 8, c0 = (t == 2) ? 8 : 0;
-        if (r0 + 8 > NB && r0 >= NB) continue;
-        double d0, d1;
-        gram(NX, r0, NX, c0, d0, d1);
-        const int r = r0 + fm, c = c0 + 2 * fk;
-        if (r < NB)
-        {
-            if (c <= r)
+        // The three Gram products -- G_b G_b^T (nb x nb), G_b G_a^T (nb x nx), G_a G_a^T (nx x nx), inner dimension nx -- run on the
+        // tensor cores: fp64 mma.sync m8n8k4 tiles (SASS: DMMA) with fragments read straight from the column store in shared memory.
+        // Rows >= nx of a "G_a" tile are columns of G_b (the store is contiguous): those products are computed and dropped.
+        const int fm = lane >> 2, fk = lane & 3;  // fragment coordinates: A(m = fm, k = fk), B(k = fk, n = fm), C(m = fm, n = 2 fk + {0,1})
+        auto gram = [&](int row_base, int r0, int col_base, int c0, double& d0, double& d1) {
+            d0 = 0.0;
+            d1 = 0.0;
+#pragma unroll
+            for (int k0 = 0; k0 < NX; k0 += 4)
             {
-                if (r == c) d0 = fma(sCost[wib][1][r], sCost[wib][1][r], fma(sCost[wib][3][r], sCost[wib][3][r], d0));
-                Dk[tri(r, c)] = d0;
+                const double af = sG[wib][row_base + r0 + fm][k0 + fk];
+                const double bf = sG[wib][col_base + c0 + fm][k0 + fk];
+                dmma884(d0, d1, af, bf);
             }
-            if (c + 1 <= r)
-            {
-                if (r == c + 1) d1 = fma(sCost[wib][1][r], sCost[wib][1][r], fma(sCost[wib][3][r], sCost[wib][3][r], d1));
-                Dk[tri(r, c + 1)] = d1;
-            }
-        }
-    }
-    if (lane < NB)
-    {
-        double s = 0.0;
-#pragma unroll
-        for (int q = 0; q < NX; ++q) s = fma(sG[wib][NX + lane][q], sE0[wib][q], s);
-        s        = fma(sCost[wib][1][lane], sCost[wib][0][lane], fma(sCost[wib][3][lane], sCost[wib][2][lane], s));
-        gk[lane] = -s;
-    }
-    if (k > 0)
-    {
-        double* Ek  = pa.E + blk * NE;
-        double* DAk = pa.DA + blk * NXX;
-        double* gAk = pa.gA + blk * NX;
-        // E_k = G_b G_a^T: rows = slots of block k, columns = x-part of block k-1
-#pragma unroll
-        for (int t = 0; t < 4; ++t)
-        {
-            const int r0 = (t & 1) * 8, c0 = (t >> 1) * 8;
-            double d0, d1;
-            gram(NX, r0, 0, c0, d0, d1);
-            const int r = r0 + fm, c = c0 + 2 * fk;
-            if (r < NB && c < NX) Ek[r * NX + c] = d0;
-            if (r < NB && c + 1 < NX) Ek[r * NX + c + 1] = d1;
-        }
-        // A^T A of this interval (belongs to block k-1): G_a G_a^T, lower triangle
+        };
+        // block k: G_b G_b^T, lower triangle, + the diagonal cost / bound rows
 #pragma unroll
         for (int t = 0; t < 3; ++t)
         {
             const int r0 = (t == 0) ? 0 : 8, c0 = (t == 2) ? 8 : 0;
+            if (r0 + 8 > NB && r0 >= NB) continue;
             double d0, d1;
-            gram(0, r0, 0, c0, d0, d1);
+            gram(NX, r0, NX, c0, d0, d1);
             const int r = r0 + fm, c = c0 + 2 * fk;
-            if (r < NX && c <= r) DAk[tri(r, c)] = d0;
-            if (r < NX && c + 1 <= r) DAk[tri(r, c + 1)] = d1;
+            if (r < NB)
+            {
+                if (c <= r)
+                {
+                    if (r == c) d0 = fma(sCost[wib][1][r], sCost[wib][1][r], fma(sCost[wib][3][r], sCost[wib][3][r], d0));
+                    Dk[tri(r, c)] = d0;
+                }
+                if (c + 1 <= r)
+                {
+                    if (r == c + 1) d1 = fma(sCost[wib][1][r], sCost[wib][1][r], fma(sCost[wib][3][r], sCost[wib][3][r], d1));
+                    Dk[tri(r, c + 1)] = d1;
+                }
+            }
         }
-        if (lane < NX)
+        if (k > 0)
         {
-            double s = 0.0;
+            Real* Ek  = pa.E + blk * NE;
+            Real* DAk = pa.DA + blk * NXXP;
+            // E_k = G_b G_a^T: rows = slots of block k, columns = x-part of block k-1
 #pragma unroll
-            for (int q = 0; q < NX; ++q) s = fma(sG[wib][lane][q], sE0[wib][q], s);
-            gAk[lane] = -s;
+            for (int t = 0; t < 4; ++t)
+            {
+                const int r0 = (t & 1) * 8, c0 = (t >> 1) * 8;
+                double d0, d1;
+                gram(NX, r0, 0, c0, d0, d1);
+                const int r = r0 + fm, c = c0 + 2 * fk;
+                if (r < NB && c < NX) Ek[r * NX + c] = d0;
+                if (r < NB && c + 1 < NX) Ek[r * NX + c + 1] = d1;
+            }
+            // A^T A of this interval (belongs to block k-1): G_a G_a^T, lower triangle
+#pragma unroll
+            for (int t = 0; t < 3; ++t)
+            {
+                const int r0 = (t == 0) ? 0 : 8, c0 = (t == 2) ? 8 : 0;
+                double d0, d1;
+                gram(0, r0, 0, c0, d0, d1);
+                const int r = r0 + fm, c = c0 + 2 * fk;
+                if (r < NX && c <= r) DAk[tri(r, c)] = d0;
+                if (r < NX && c + 1 <= r) DAk[tri(r, c + 1)] = d1;
+            }
         }
+    }
+    else
+    {
+        // fp32: the same three Gram products on the FMA pipe; a lane owns every 32nd entry and reads the two columns as float4 rows
+        auto dot = [&](int ra, int rb) {
+            float s = 0.f;
+#pragma unroll
+            for (int q = 0; q < NX; q += 4)
+            {
+                const float4 a = *reinterpret_cast<const float4*>(&sG[wib][ra][q]);
+                const float4 b = *reinterpret_cast<const float4*>(&sG[wib][rb][q]);
+                s = fmaf(a.x, b.x, fmaf(a.y, b.y, fmaf(a.z, b.z, fmaf(a.w, b.w, s))));
+            }
+            return s;
+        };
+        for (int idx = lane; idx < ND; idx += 32)
+        {
+            const int r = sTriR[idx], c = sTriC[idx];
+            float s = dot(NX + r, NX + c);
+            if (r == c) s = fmaf(sCost[wib][1][r], sCost[wib][1][r], fmaf(sCost[wib][3][r], sCost[wib][3][r], s));
+            Dk[idx] = s;
+        }
+        if (k > 0)
+        {
+            Real* Ek  = pa.E + blk * NE;
+            Real* DAk = pa.DA + blk * NXXP;
+            for (int idx = lane; idx < NE; idx += 32) Ek[idx] = dot(NX + idx / NX, idx % NX);
+            for (int idx = lane; idx < Pd::NXX; idx += 32) DAk[idx] = dot(sTriR[idx], sTriC[idx]);
+        }
+    }
+    if (lane < NB)
+    {
+        Real s = 0;
+#pragma unroll
+        for (int q = 0; q < NX; ++q) s = fmaT(sG[wib][NX + lane][q], sE0[wib][q], s);
+        s        = fmaT(sCost[wib][1][lane], sCost[wib][0][lane], fmaT(sCost[wib][3][lane], sCost[wib][2][lane], s));
+        gk[lane] = -s;
+    }
+    if (k > 0 && lane < NX)
+    {
+        Real* gAk = pa.gA + blk * NX;
+        Real s    = 0;
+#pragma unroll
+        for (int q = 0; q < NX; ++q) s = fmaT(sG[wib][lane][q], sE0[wib][q], s);
+        gAk[lane] = -s;
     }
 }
 
 // ---------------------------------------------------------------------------------------------------------------------------
 // initial LM state after the first linearisation: one warp per instance (levenberg_marquardt_sparse.cpp:103-126)
 // ---------------------------------------------------------------------------------------------------------------------------
-template <class M>
+template <class M, class Real>
 __global__ void __launch_bounds__(128) pipeInitKernel(const __grid_constant__ DeviceOcp P, const __grid_constant__ DeviceState st,
-                                                      const __grid_constant__ PipeArrays pa, int iterations)
+                                                      const __grid_constant__ PipeArraysT<Real> pa, int iterations)
 {
     using Pd = PipeDim<M>;
-    constexpr int NX = Pd::NX, NU = Pd::NU, NB = Pd::NB, ND = Pd::ND, NXX = Pd::NXX;
+    constexpr int NX = Pd::NX, NU = Pd::NU, NB = Pd::NB, ND = Pd::ND, NXXP = Pd::template Padded<Real>::nxxp;
     const int lane = threadIdx.x & 31;
     const int i    = blockIdx.x * 4 + (threadIdx.x >> 5);
     if (i >= P.B) return;
@@ -405,11 +508,11 @@ __global__ void __launch_bounds__(128) pipeInitKernel(const __grid_constant__ De
         const size_t blk = (size_t)i * K + k;
         for (int r = 0; r < NB; ++r)
         {
-            double d = pa.D[blk * ND + tri(r, r)], g = pa.g[blk * NB + r];
+            double d = (double)pa.D[blk * ND + tri(r, r)], g = (double)pa.g[blk * NB + r];
             if (r >= NU && k + 1 < K)
             {
-                d += pa.DA[(blk + 1) * NXX + tri(r - NU, r - NU)];
-                g += pa.gA[(blk + 1) * NX + (r - NU)];
+                d += (double)pa.DA[(blk + 1) * NXXP + tri(r - NU, r - NU)];
+                g += (double)pa.gA[(blk + 1) * NX + (r - NU)];
             }
             maxdiag = fmax(maxdiag, d);
             ginf    = fmax(ginf, fabs(g));
@@ -448,25 +551,26 @@ __global__ void __launch_bounds__(128) pipeInitKernel(const __grid_constant__ De
 // ---------------------------------------------------------------------------------------------------------------------------
 // (H + mu_acc I) delta = g: block-tridiagonal Cholesky, one warp per instance, lane = row of the current block
 // ---------------------------------------------------------------------------------------------------------------------------
-template <class M>
+template <class M, class Real>
 __global__ void __launch_bounds__(128, 7) pipeFactorKernel(const __grid_constant__ DeviceOcp P, const __grid_constant__ DeviceState st,
-                                                        const __grid_constant__ PipeArrays pa)
+                                                        const __grid_constant__ PipeArraysT<Real> pa)
 {
     using Pd = PipeDim<M>;
-    constexpr int NX = Pd::NX, NU = Pd::NU, NB = Pd::NB, ND = Pd::ND, NE = Pd::NE, NXX = Pd::NXX;
+    constexpr int NX = Pd::NX, NU = Pd::NU, NB = Pd::NB, ND = Pd::ND, NE = Pd::NE, NXXP = Pd::template Padded<Real>::nxxp;
+    constexpr bool F64 = sizeof(Real) == 8;
+    constexpr int RB   = (int)sizeof(Real);
     constexpr unsigned FULL = 0xffffffffu;
-    static_assert((ND * 8) % 16 == 0 && (NE * 8) % 16 == 0 && (NXX * 8) % 16 == 0, "bulk copies move multiples of 16 bytes");
-    using BS = BlockSolver<M, 0>;
+    static_assert((ND * RB) % 16 == 0 && (NE * RB) % 16 == 0 && (NXXP * RB) % 16 == 0, "bulk copies move multiples of 16 bytes");
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
     const int i    = blockIdx.x * 4 + wib;
     // Lane r < NB owns ROW r of the current block in registers.  The blocks arrive from HBM by TMA bulk copies into a two-stage
     // ring per warp (the next block is in flight while the current one is eliminated); shared memory also holds what other lanes
     // must read (W_k rows, the trailing block of the previous factor) and stages the coalesced stores.
-    __shared__ __align__(16) double stD[4][2][ND];    // forward: D_k        backward: L_k
-    __shared__ __align__(16) double stE[4][2][NE];    // forward: E_k        backward: W_{k+1}
-    __shared__ __align__(16) double stA[4][2][NXX];   // forward: A^T A of interval k+1
+    __shared__ __align__(16) Real stD[4][2][ND];    // forward: D_k        backward: L_k
+    __shared__ __align__(16) Real stE[4][2][NE];    // forward: E_k        backward: W_{k+1}
+    __shared__ __align__(16) Real stA[4][2][NXXP];  // forward: A^T A of interval k+1
     __shared__ __align__(8) unsigned long long bars[4][2];
-    __shared__ double sLxx[4][NX][NX + 1];  // trailing nx x nx block of the previous factor (reciprocal diagonal)
+    __shared__ Real sLxx[4][NX][NX + 1];  // trailing nx x nx block of the previous factor (reciprocal diagonal)
     // W_k overwrites E_k and L_k overwrites D_k in their stage (same packed layouts) once every lane holds its row in registers:
     // the coalesced stores then run straight out of the stage, and 7 thread blocks (28 warps) fit one SM
     if (lane == 0)
@@ -478,7 +582,8 @@ __global__ void __launch_bounds__(128, 7) pipeFactorKernel(const __grid_constant
     __syncthreads();
     if (i >= P.B || !(pa.flags[i] & PF_ACTIVE)) return;
     const int K      = P.K;
-    const double mua = pa.mu_acc[i], mu = st.mu[i];
+    const Real mua   = (Real)pa.mu_acc[i];
+    const double mu  = st.mu[i];
     const bool rowl  = lane < NB;
     unsigned phase[2] = {0u, 0u};
     bool ok           = true;
@@ -487,22 +592,22 @@ __global__ void __launch_bounds__(128, 7) pipeFactorKernel(const __grid_constant
         {
             const size_t blk = (size_t)i * K + k;
             const int sidx   = k & 1;
-            const unsigned bytes = ND * 8 + (k > 0 ? NE * 8 : 0) + (k + 1 < K ? NXX * 8 : 0);
+            const unsigned bytes = ND * RB + (k > 0 ? NE * RB : 0) + (k + 1 < K ? NXXP * RB : 0);
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // our generic-proxy writes to this stage come first
             mbarExpectTx(&bars[wib][sidx], bytes);
-            bulkLoad(stD[wib][sidx], pa.D + blk * ND, ND * 8, &bars[wib][sidx]);
-            if (k > 0) bulkLoad(stE[wib][sidx], pa.E + blk * NE, NE * 8, &bars[wib][sidx]);
-            if (k + 1 < K) bulkLoad(stA[wib][sidx], pa.DA + (blk + 1) * NXX, NXX * 8, &bars[wib][sidx]);
+            bulkLoad(stD[wib][sidx], pa.D + blk * ND, ND * RB, &bars[wib][sidx]);
+            if (k > 0) bulkLoad(stE[wib][sidx], pa.E + blk * NE, NE * RB, &bars[wib][sidx]);
+            if (k + 1 < K) bulkLoad(stA[wib][sidx], pa.DA + (blk + 1) * NXXP, NXXP * RB, &bars[wib][sidx]);
         }
     };
     issueForward(0);
-    double yp_x = 0.0;  // lane a < NX: x-part of the forward-substituted rhs of the previous block
+    Real yp_x = 0;  // lane a < NX: x-part of the forward-substituted rhs of the previous block
     for (int k = 0; k < K; ++k)
     {
         const size_t blk = (size_t)i * K + k;
         const int sidx   = k & 1;
         if (k + 1 < K) issueForward(k + 1);  // its stage was last read two iterations ago (warp-synchronised since)
-        double y = 0.0;                       // lane r < NB holds rhs component r
+        Real y = 0;                           // lane r < NB holds rhs component r
         if (rowl)
         {
             y = pa.g[blk * NB + lane];
@@ -513,13 +618,13 @@ __global__ void __launch_bounds__(128, 7) pipeFactorKernel(const __grid_constant
         if (k > 0)
         {
             // W_k Lxx^T = E_k: row r per lane
-            double wr[NX];
+            Real wr[NX];
 #pragma unroll
             for (int a = 0; a < NX; ++a)
             {
-                double s = rowl ? stE[wib][sidx][lane * NX + a] : 0.0;
+                Real s = rowl ? stE[wib][sidx][lane * NX + a] : Real(0);
 #pragma unroll
-                for (int b = 0; b < a; ++b) s = fma(-wr[b], sLxx[wib][a][b], s);
+                for (int b = 0; b < a; ++b) s = fmaT(-wr[b], sLxx[wib][a][b], s);
                 wr[a] = s * sLxx[wib][a][a];
             }
             __syncwarp();  // every lane has read its E row
@@ -530,38 +635,64 @@ __global__ void __launch_bounds__(128, 7) pipeFactorKernel(const __grid_constant
             }
             __syncwarp();
             for (int idx = lane; idx < NE; idx += 32) pa.W[blk * NE + idx] = stE[wib][sidx][idx];
-            // Schur complement S_k -= W_k W_k^T on the staged block with fp64 tensor-core tiles (DMMA m8n8k4): lower triangle = the
-            // 8x8 tiles (0,0), (1,0), (1,1); fragments straight from the stage (W packed [r][a], S packed lower by rows)
-            const int fm = lane >> 2, fk = lane & 3;
-#pragma unroll
-            for (int t = 0; t < 3; ++t)
+            if constexpr (F64)
             {
-                const int r0 = (t == 0) ? 0 : 8, c0 = (t == 2) ? 8 : 0;
-                const int r = r0 + fm, c = c0 + 2 * fk;
-                const bool in0 = r < NB && c <= r, in1 = r < NB && c + 1 <= r;
-                double d0 = in0 ? stD[wib][sidx][tri(r, c)] : 0.0;
-                double d1 = in1 ? stD[wib][sidx][tri(r, c + 1)] : 0.0;
+                // Schur complement S_k -= W_k W_k^T on the staged block with fp64 tensor-core tiles (DMMA m8n8k4): lower triangle = the
+                // 8x8 tiles (0,0), (1,0), (1,1); fragments straight from the stage (W packed [r][a], S packed lower by rows)
+                const int fm = lane >> 2, fk = lane & 3;
 #pragma unroll
-                for (int k0 = 0; k0 < NX; k0 += 4)
+                for (int t = 0; t < 3; ++t)
                 {
-                    const double af = (r0 + fm < NB) ? -stE[wib][sidx][(r0 + fm) * NX + k0 + fk] : 0.0;
-                    const double bf = (c0 + fm < NB) ? stE[wib][sidx][(c0 + fm) * NX + k0 + fk] : 0.0;
-                    dmma884(d0, d1, af, bf);
+                    const int r0 = (t == 0) ? 0 : 8, c0 = (t == 2) ? 8 : 0;
+                    const int r = r0 + fm, c = c0 + 2 * fk;
+                    const bool in0 = r < NB && c <= r, in1 = r < NB && c + 1 <= r;
+                    double d0 = in0 ? stD[wib][sidx][tri(r, c)] : 0.0;
+                    double d1 = in1 ? stD[wib][sidx][tri(r, c + 1)] : 0.0;
+#pragma unroll
+                    for (int k0 = 0; k0 < NX; k0 += 4)
+                    {
+                        const double af = (r0 + fm < NB) ? -stE[wib][sidx][(r0 + fm) * NX + k0 + fk] : 0.0;
+                        const double bf = (c0 + fm < NB) ? stE[wib][sidx][(c0 + fm) * NX + k0 + fk] : 0.0;
+                        dmma884(d0, d1, af, bf);
+                    }
+                    if (in0) stD[wib][sidx][tri(r, c)] = d0;
+                    if (in1) stD[wib][sidx][tri(r, c + 1)] = d1;
                 }
-                if (in0) stD[wib][sidx][tri(r, c)] = d0;
-                if (in1) stD[wib][sidx][tri(r, c + 1)] = d1;
+            }
+            else
+            {
+                // fp32: S_k -= W_k W_k^T on the FMA pipe: lane r updates its own row; the rows of W are read from the stage as float4
+                // (every lane reads the same W_c: a broadcast)
+                if (rowl)
+                {
+#pragma unroll
+                    for (int c = 0; c < NB; ++c)
+                    {
+                        if (c <= lane)
+                        {
+                            float s = stD[wib][sidx][tri(lane, c)];
+#pragma unroll
+                            for (int q = 0; q < NX; q += 4)
+                            {
+                                const float4 wc = *reinterpret_cast<const float4*>(&stE[wib][sidx][c * NX + q]);
+                                s = fmaf(-wr[q], wc.x, fmaf(-wr[q + 1], wc.y, fmaf(-wr[q + 2], wc.z, fmaf(-wr[q + 3], wc.w, s))));
+                            }
+                            stD[wib][sidx][tri(lane, c)] = s;
+                        }
+                    }
+                }
             }
             // rhs update
 #pragma unroll
-            for (int a = 0; a < NX; ++a) y = fma(-wr[a], __shfl_sync(FULL, yp_x, a), y);
+            for (int a = 0; a < NX; ++a) y = fmaT(-wr[a], __shfl_sync(FULL, yp_x, a), y);
             __syncwarp();
         }
         // ---- row r of S_k = D_k - W_k W_k^T (+ A^T A of interval k+1 on the x-x part, + damping)
-        double row[NB];  // row[c], c <= lane
+        Real row[NB];  // row[c], c <= lane
 #pragma unroll
         for (int c = 0; c < NB; ++c)
         {
-            double v = 0.0;
+            Real v = 0;
             if (rowl && c <= lane)
             {
                 v = stD[wib][sidx][tri(lane, c)];
@@ -575,17 +706,17 @@ __global__ void __launch_bounds__(128, 7) pipeFactorKernel(const __grid_constant
 #pragma unroll
         for (int j = 0; j < NB; ++j)
         {
-            const double inv = BS::pivotRsqrt(__shfl_sync(FULL, row[j], j));
-            const double yj  = __shfl_sync(FULL, y, j) * inv;
-            const double l   = (lane > j) ? row[j] * inv : 0.0;
-            if (lane > j) y = fma(-l, yj, y);
+            const Real inv = pivotRsqrtT(__shfl_sync(FULL, row[j], j));
+            const Real yj  = __shfl_sync(FULL, y, j) * inv;
+            const Real l   = (lane > j) ? row[j] * inv : Real(0);
+            if (lane > j) y = fmaT(-l, yj, y);
             if (lane == j) y = yj;
             row[j] = (lane == j) ? inv : l;
 #pragma unroll
             for (int c = j + 1; c < NB; ++c)
             {
-                const double lc = __shfl_sync(FULL, l, c);
-                row[c]          = fma(-l, lc, row[c]);  // lanes < c hold zeros there and l = 0 for lanes <= j
+                const Real lc = __shfl_sync(FULL, l, c);
+                row[c]        = fmaT(-l, lc, row[c]);  // lanes < c hold zeros there and l = 0 for lanes <= j
             }
         }
         // ---- store the factor (coalesced, packed order) and the forward-substituted rhs, keep what the next block needs
@@ -617,22 +748,23 @@ __global__ void __launch_bounds__(128, 7) pipeFactorKernel(const __grid_constant
         if (lane == 0)
         {
             const size_t blk = (size_t)i * K + k;
-            const unsigned bytes = ND * 8 + (k + 1 < K ? NE * 8 : 0);
+            const unsigned bytes = ND * RB + (k + 1 < K ? NE * RB : 0);
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
             mbarExpectTx(&bars[wib][sidx], bytes);
-            bulkLoad(stD[wib][sidx], pa.L + blk * ND, ND * 8, &bars[wib][sidx]);
-            if (k + 1 < K) bulkLoad(stE[wib][sidx], pa.W + (blk + 1) * NE, NE * 8, &bars[wib][sidx]);
+            bulkLoad(stD[wib][sidx], pa.L + blk * ND, ND * RB, &bars[wib][sidx]);
+            if (k + 1 < K) bulkLoad(stE[wib][sidx], pa.W + (blk + 1) * NE, NE * RB, &bars[wib][sidx]);
         }
     };
     issueBackward(K - 1, 0);
-    double dn2 = 0.0, dq = 0.0, dnext = 0.0;  // dnext: lane r holds delta_{k+1}[r]
+    double dn2 = 0.0, dq = 0.0;  // accumulated in fp64 in both variants
+    Real dnext = 0;              // lane r holds delta_{k+1}[r]
     int step = 0;
     for (int k = K - 1; k >= 0; --k, ++step)
     {
         const size_t blk = (size_t)i * K + k;
         const int sidx   = step & 1;
         if (k > 0) issueBackward(k - 1, sidx ^ 1);
-        double d = 0.0, gfull = 0.0;
+        Real d = 0, gfull = 0;
         if (rowl)
         {
             d     = pa.y[blk * NB + lane];
@@ -643,28 +775,29 @@ __global__ void __launch_bounds__(128, 7) pipeFactorKernel(const __grid_constant
         phase[sidx] ^= 1u;
         if (k + 1 < K)
         {
-            double s = 0.0;
+            Real s = 0;
             const int a = (lane >= NU && rowl) ? lane - NU : 0;
 #pragma unroll
-            for (int r = 0; r < NB; ++r) s = fma(stE[wib][sidx][r * NX + a], __shfl_sync(FULL, dnext, r), s);
+            for (int r = 0; r < NB; ++r) s = fmaT(stE[wib][sidx][r * NX + a], __shfl_sync(FULL, dnext, r), s);
             if (lane >= NU && rowl) d -= s;
         }
         // L^T delta = d, column-oriented backward: lane r needs L[j][r] for j >= r, i.e. column r of the factor
-        double colr[NB];
+        Real colr[NB];
 #pragma unroll
-        for (int j = 0; j < NB; ++j) colr[j] = (rowl && j >= lane) ? stD[wib][sidx][tri(j, lane)] : 0.0;
+        for (int j = 0; j < NB; ++j) colr[j] = (rowl && j >= lane) ? stD[wib][sidx][tri(j, lane)] : Real(0);
 #pragma unroll
         for (int j = NB - 1; j >= 0; --j)
         {
-            const double dj = __shfl_sync(FULL, d, j) * __shfl_sync(FULL, colr[j], j);
+            const Real dj = __shfl_sync(FULL, d, j) * __shfl_sync(FULL, colr[j], j);
             if (lane == j) d = dj;
-            if (lane < j) d = fma(-colr[j], dj, d);
+            if (lane < j) d = fmaT(-colr[j], dj, d);
         }
         if (rowl)
         {
-            st.dl[tiledSlot(i, k * NB + lane, K * NB)] = d;
-            dn2                                        = fma(d, d, dn2);
-            dq                                         = fma(d, fma(mu, d, gfull), dq);
+            const double dd = (double)d;
+            st.dl[tiledSlot(i, k * NB + lane, K * NB)] = dd;
+            dn2                                        = fma(dd, dd, dn2);
+            dq                                         = fma(dd, fma(mu, dd, (double)gfull), dq);
         }
         dnext = d;
         __syncwarp();
@@ -677,7 +810,9 @@ __global__ void __launch_bounds__(128, 7) pipeFactorKernel(const __grid_constant
     }
     if (lane == 0)
     {
-        pa.dn2[i] = ok ? dn2 : CUDART_NAN;  // a lost bulk copy poisons the step: the control kernel then rejects it
+        // a lost bulk copy (or a non-finite factor) poisons the pass: the trial kernel then skips the instance and the control kernel
+        // takes the reject branch (mu *= v), exactly as for a step that did not reduce chi2
+        pa.dn2[i] = (ok && isfinite(dn2) && isfinite(dq)) ? dn2 : CUDART_NAN;
         pa.dq[i]  = dq;
         st.n_factor[i] += 1;
     }
@@ -686,9 +821,9 @@ __global__ void __launch_bounds__(128, 7) pipeFactorKernel(const __grid_constant
 // ---------------------------------------------------------------------------------------------------------------------------
 // trial point and its residuals: one thread per (instance, interval)
 // ---------------------------------------------------------------------------------------------------------------------------
-template <class M, int DEFECT>
+template <class M, int DEFECT, class Real>
 __global__ void __launch_bounds__(128) pipeTrialKernel(const __grid_constant__ DeviceOcp P, const __grid_constant__ DeviceState st,
-                                                       const __grid_constant__ PipeArrays pa)
+                                                       const __grid_constant__ PipeArraysT<Real> pa)
 {
     using Pd = PipeDim<M>;
     constexpr int NX = Pd::NX, NB = Pd::NB;
@@ -696,7 +831,8 @@ __global__ void __launch_bounds__(128) pipeTrialKernel(const __grid_constant__ D
     const int k = blockIdx.y;
     if (i >= P.B || !(pa.flags[i] & PF_ACTIVE)) return;
     constexpr double eps2 = 1e-5;
-    if (sqrt(pa.dn2[i]) <= eps2) return;  // step too small: no trial point (levenberg_marquardt_sparse.cpp:151-154)
+    const double dn2 = pa.dn2[i];
+    if (isnan(dn2) || sqrt(dn2) <= eps2) return;  // failed factorisation, or step too small: no trial point (levenberg_marquardt_sparse.cpp:151-154)
     const Weights w{st.w_eq, st.w_ineq, st.w_b};
     const size_t tile = i >> 5, lane = i & 31;
     const size_t zoff = tile * ((size_t)P.K * NB * TILE) + lane;
@@ -709,8 +845,9 @@ __global__ void __launch_bounds__(128) pipeTrialKernel(const __grid_constant__ D
 // ---------------------------------------------------------------------------------------------------------------------------
 // LM control: one thread per instance (levenberg_marquardt_sparse.cpp:151-216; same state machine as lmSolveKernel's C phase)
 // ---------------------------------------------------------------------------------------------------------------------------
+template <class Real>
 __global__ void __launch_bounds__(128) pipeControlKernel(const __grid_constant__ DeviceOcp P, const __grid_constant__ DeviceState st,
-                                                         const __grid_constant__ PipeArrays pa, int iterations)
+                                                         const __grid_constant__ PipeArraysT<Real> pa, int iterations)
 {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= P.B) return;
@@ -724,7 +861,16 @@ __global__ void __launch_bounds__(128) pipeControlKernel(const __grid_constant__
     bool stop    = (flags & PF_STOP) != 0;
     bool lin     = false;
     const double dq = pa.dq[i];
-    if (sqrt(pa.dn2[i]) <= eps2)
+    const bool factor_failed = isnan(pa.dn2[i]);
+    if (factor_failed)
+    {
+        // the factorisation of this pass did not complete: reject like a step that increased chi2 (more damping, same linearisation)
+        st.n_reject[i] += 1;
+        rho = -1.0;
+        mu  = mu * v;
+        v   = 2 * v;
+    }
+    else if (sqrt(pa.dn2[i]) <= eps2)
         stop = true;
     else
     {
@@ -786,32 +932,43 @@ __global__ void pipeSetFlagsKernel(int* flags, int B, int value)
 
 // LevenbergMarquardtSparse::solve for the whole batch, host-driven passes.  Blocks the calling thread (it reads two flags per
 // pass); returns false if a pass count bound is hit (never observed: every pass either ends an outer iteration or multiplies mu).
-template <class M, int DEFECT>
-bool launchPipeline(const DeviceOcp& P, const DeviceState& st, const PipeArrays& pa, int iterations, cudaStream_t stream)
+template <class M, int DEFECT, class Real>
+bool launchPipelineT(const DeviceOcp& P, const DeviceState& st, const PipeArraysT<Real>& pa, int iterations, cudaStream_t stream)
 {
     const int B = P.B, K = P.K;
     const int warp_blocks_ik = (int)(((long long)B * K + 3) / 4), warp_blocks_i = (B + 3) / 4, thread_blocks_i = (B + 127) / 128;
     int any[2] = {0, 0};
     cudaMemsetAsync(pa.any, 0, 2 * sizeof(int), stream);
     pipeSetFlagsKernel<<<thread_blocks_i, 128, 0, stream>>>(pa.flags, B, PF_LIN);
-    pipeLinearizeKernel<M, DEFECT><<<warp_blocks_ik, 128, 0, stream>>>(P, st, pa);
-    pipeInitKernel<M><<<warp_blocks_i, 128, 0, stream>>>(P, st, pa, iterations);
+    pipeLinearizeKernel<M, DEFECT, Real><<<warp_blocks_ik, 128, 0, stream>>>(P, st, pa);
+    pipeInitKernel<M, Real><<<warp_blocks_i, 128, 0, stream>>>(P, st, pa, iterations);
     cudaMemcpyAsync(any, pa.any, 2 * sizeof(int), cudaMemcpyDeviceToHost, stream);
     cudaStreamSynchronize(stream);
     int passes = 0;
     const int max_passes = 64 * (iterations + 1);
     while (any[0] && passes < max_passes)
     {
-        pipeFactorKernel<M><<<warp_blocks_i, 128, 0, stream>>>(P, st, pa);
-        pipeTrialKernel<M, DEFECT><<<dim3(thread_blocks_i, K), 128, 0, stream>>>(P, st, pa);
+        pipeFactorKernel<M, Real><<<warp_blocks_i, 128, 0, stream>>>(P, st, pa);
+        pipeTrialKernel<M, DEFECT, Real><<<dim3(thread_blocks_i, K), 128, 0, stream>>>(P, st, pa);
         cudaMemsetAsync(pa.any, 0, 2 * sizeof(int), stream);
-        pipeControlKernel<<<thread_blocks_i, 128, 0, stream>>>(P, st, pa, iterations);
+        pipeControlKernel<Real><<<thread_blocks_i, 128, 0, stream>>>(P, st, pa, iterations);
         cudaMemcpyAsync(any, pa.any, 2 * sizeof(int), cudaMemcpyDeviceToHost, stream);
         cudaStreamSynchronize(stream);
-        if (any[0] && any[1]) pipeLinearizeKernel<M, DEFECT><<<warp_blocks_ik, 128, 0, stream>>>(P, st, pa);
+        if (any[0] && any[1]) pipeLinearizeKernel<M, DEFECT, Real><<<warp_blocks_ik, 128, 0, stream>>>(P, st, pa);
         ++passes;
     }
     return passes < max_passes;
+}
+
+template <class M, int DEFECT>
+bool launchPipeline(const DeviceOcp& P, const DeviceState& st, const PipeArraysT<double>& pa, int iterations, cudaStream_t stream)
+{
+    return launchPipelineT<M, DEFECT, double>(P, st, pa, iterations, stream);
+}
+template <class M, int DEFECT>
+bool launchPipelineF32(const DeviceOcp& P, const DeviceState& st, const PipeArraysT<float>& pa, int iterations, cudaStream_t stream)
+{
+    return launchPipelineT<M, DEFECT, float>(P, st, pa, iterations, stream);
 }
 
 }  // namespace b200sqp

@@ -3,6 +3,7 @@
 // through L1/L2) -- they move a few MB per solve and are not on the roofline-relevant path.
 #include "../../include/b200sqp.h"
 #include "launch.h"
+#include "lm_device_types.h"
 
 namespace b200sqp {
 
@@ -309,6 +310,23 @@ __global__ void peerWaitKernel(const volatile unsigned long long* arrivals, int 
     __threadfence_system();
 }
 
+// epilogue of lmSolveKernel (lm_kernels.cuh) as a kernel of its own, for solves that ran the multi-kernel pipeline: one warp per 32
+// instances stores chi2 into every rank's gather buffer, fences at system scope and bumps this rank's arrival counter on every peer
+__global__ void __launch_bounds__(32) peerPublishKernel(const __grid_constant__ DeviceState st, int B)
+{
+    const int i = blockIdx.x * 32 + threadIdx.x;
+    if (i < B)
+    {
+        const size_t slot = (size_t)st.peer_parity * st.peer_world * B + (size_t)st.peer_rank * B + i;
+        const double c    = st.chi2[i];
+        for (int r = 0; r < st.peer_world; ++r) st.peer_chi2[r][slot] = c;
+        __threadfence_system();
+    }
+    __syncwarp();
+    if (threadIdx.x == 0)
+        for (int r = 0; r < st.peer_world; ++r) atomicAdd_system(st.peer_arrivals[r] + st.peer_rank, 1ULL);
+}
+
 // b200sqp_measure_fp64_peak: 8 independent DFMA chains per thread, 16 warps per block, every SM loaded: the fp64 FMA issue bound
 // the fused LM kernel is compared with (bench.py roofline_fp64).  fma() is explicit, so --fmad=false does not matter here.
 __global__ void __launch_bounds__(512) fp64PeakKernel(double* out, double a, double b, int n)
@@ -364,6 +382,8 @@ void launchWarmStartShift(const double* x0_new, double* x0, double* z0, double* 
     warmStartFindKernel<<<blocksFor(B), 128, 0, st>>>(x0_new, x0, z0, z1, cur, K, nx, nu, plan, num_shift, B);
     warmStartMoveKernel<<<dim3(blocksFor(B), K), 128, 0, st>>>(z0, z1, cur, plan, K, nx, nu, B);
 }
+
+void launchPeerPublish(const DeviceState& st, int B, cudaStream_t stream) { peerPublishKernel<<<(B + 31) / 32, 32, 0, stream>>>(st, B); }
 
 void launchPeerWait(const unsigned long long* arrivals, int world, unsigned long long expected, unsigned long long timeout_ns, int* timed_out,
                     cudaStream_t st)

@@ -28,7 +28,7 @@ ABI_SYMBOLS = [
     "b200sqp_last_solve_ms", "b200sqp_launch_count", "b200sqp_device_pointers", "b200sqp_set_stream", "b200sqp_set_threads_per_instance",
     "b200sqp_set_phase_profile", "b200sqp_get_phase_cycles", "b200sqp_final_constraint_indices",
     "b200sqp_peer_export", "b200sqp_peer_attach", "b200sqp_peer_wait", "b200sqp_peer_gathered", "b200sqp_peer_detach", "b200sqp_peer_status", "b200sqp_linearize_dynamics", "b200sqp_warm_start_shift", "b200sqp_mpc_step",
-    "b200sqp_plant_step", "b200sqp_closed_loop", "b200sqp_dynamics_hessian", "b200sqp_set_feature_set", "b200sqp_measure_fp64_peak",
+    "b200sqp_plant_step", "b200sqp_closed_loop", "b200sqp_dynamics_hessian", "b200sqp_set_feature_set", "b200sqp_measure_fp64_peak", "b200sqp_set_precision",
 ]
 
 
@@ -360,6 +360,11 @@ class BatchedLevenbergMarquardt:
     def set_threads_per_instance(self, threads):
         """cooperating threads per instance (1, 2, 4, 8; 0 = pick from the batch size)"""
         _check(self._lib.b200sqp_set_threads_per_instance(self._h, C.c_int32(threads)))
+
+    def set_precision(self, precision):
+        """'f64' (default, the reference's arithmetic) or 'f32' (reduced-precision variant of BASELINE configs[4]; structures that run the
+        warp-cooperative pipeline only, raises B200SqpError(UNSUPPORTED) otherwise)"""
+        _check(self._lib.b200sqp_set_precision(self._h, C.c_int32({"f64": 0, "f32": 1}[precision])))
 
     def set_feature_set(self, general):
         """test knob: force the general compile-time feature set of the LM kernel on a lean-eligible structure (False = automatic)"""

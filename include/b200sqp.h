@@ -309,6 +309,13 @@ int b200sqp_set_feature_set(b200sqp_handle h, int32_t general);
  * LM control (a1)} in SM clock cycles.  Off by default (the kernel then only tests one pointer). */
 int b200sqp_set_phase_profile(b200sqp_handle h, int32_t enable);
 int b200sqp_get_phase_cycles(b200sqp_handle h, double* mean_cycles /*[4]*/);
+/* Arithmetic of the solve.  The reference is fp64 only and so is every path here by default.  B200SQP_PRECISION_F32 is the reduced-
+ * precision variant BASELINE.json configs[4] names (12-state quadrotor): Jacobian columns by central differences with delta = 2^-10 in
+ * fp32, normal equations, Cholesky factor and substitutions in fp32; parameters, steps, trial-point residuals and the LM control state
+ * stay fp64.  It has no reference counterpart: parity is judged against the fp64 path at 1e-3 relative on the trajectories (SURVEY.md
+ * section 8d).  Available for structures that run the warp-cooperative pipeline, else B200SQP_ERR_UNSUPPORTED. */
+typedef enum { B200SQP_PRECISION_F64 = 0, B200SQP_PRECISION_F32 = 1 } b200sqp_precision;
+int b200sqp_set_precision(b200sqp_handle h, int32_t precision);
 /* measurement aid: fp64 FMA throughput of `device` in TFLOP/s (2 flops per FMA), measured live with a register-resident kernel of
  * independent FMA chains on every SM -- the issue bound the fused LM kernel is reported against next to the HBM roofline
  * (SURVEY.md section 8d "also report the fp64 FMA bound"). */

@@ -12,6 +12,7 @@ ap.add_argument("--cfg", type=int, default=1)
 ap.add_argument("--batch", type=int, default=4096)
 ap.add_argument("--T", type=int, default=0)
 ap.add_argument("--solves", type=int, default=3)
+ap.add_argument("--precision", default="f64")
 a = ap.parse_args()
 ocp, kw, _ = problems.config(a.cfg)
 x0, xref = problems.instance_data(ocp, a.batch, seed=1234 + a.cfg)
@@ -20,6 +21,8 @@ lm.setIterations(kw["iterations"])
 lm.setPenaltyWeights(*kw["weights"])
 lm.set_problem_data(x0, xref)
 lm.set_threads_per_instance(a.T)
+if a.precision != "f64":
+    lm.set_precision(a.precision)
 for _ in range(a.solves):
     lm.initialize_trajectories()
     lm.solve(new_run=True, fetch=False)

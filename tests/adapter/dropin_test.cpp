@@ -324,7 +324,7 @@ int main(int argc, char** argv)
     }
 
     // ---- 3b. final-stage constraints: TerminalBall (the inequality edge with its active-set rows) and TerminalEqualityConstraint ----
-    for (int variant = 0; variant < 2; ++variant)
+    for (int variant = 0; variant < 3; ++variant)
     {
         FinalStageConstraint::Ptr fc;
         if (variant == 0)
@@ -333,6 +333,13 @@ int main(int argc, char** argv)
             S(0, 0) = 2.0;
             S(1, 1) = 0.5;
             fc = std::make_shared<TerminalBall>(S, 0.01);
+        }
+        else if (variant == 2)
+        {
+            // TerminalBallInheritFromCost: S is taken from the quadratic final cost (here Qf = I), gamma is its own member
+            auto inherit    = std::make_shared<TerminalBallInheritFromCost>();
+            inherit->_gamma = 0.02;
+            fc              = inherit;
         }
         else
         {
@@ -353,7 +360,7 @@ int main(int argc, char** argv)
         lb.problem->getParameterVector(pb);
         double diff = pr.size() == pb.size() ? (pr - pb).cwiseAbs().maxCoeff() / std::max(1.0, pr.cwiseAbs().maxCoeff()) : 1e30;
         std::printf("final-stage constraint %s: ineq dim %d, eq dim %d, max relative trajectory difference vs reference = %.3e\n",
-                    variant == 0 ? "TerminalBall" : "TerminalEqualityConstraint", lb.problem->getInequalityDimension(),
+                    variant == 0 ? "TerminalBall" : (variant == 2 ? "TerminalBallInheritFromCost" : "TerminalEqualityConstraint"), lb.problem->getInequalityDimension(),
                     lb.problem->getEqualityDimension(), diff);
         if (!ok_r || !ok_b || !(diff <= 1e-5))
         {
