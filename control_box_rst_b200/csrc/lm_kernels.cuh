@@ -462,9 +462,4 @@ void launchEvaluate(const DeviceOcp& P, const DeviceState& st, double* values, d
 
 #define B200SQP_KERNEL_ENTRY(MODEL, DEFECT, VT, MAXT) \
     KernelSet { MODEL::ID, DEFECT, VT, MODEL::NX, MODEL::NU, MAXT, &launchSolve<MODEL, DEFECT, VT, MAXT>, &launchEvaluate<MODEL, DEFECT, VT>, nullptr }
-// the same plus the warp-cooperative pipeline (include lm_pipeline.cuh); fixed-dt grids only
-#define B200SQP_KERNEL_ENTRY_PIPELINE(MODEL, DEFECT, MAXT)                                                                            \
-    KernelSet { MODEL::ID, DEFECT, 0, MODEL::NX, MODEL::NU, MAXT, &launchSolve<MODEL, DEFECT, 0, MAXT>, &launchEvaluate<MODEL, DEFECT, 0>, \
-                &launchPipeline<MODEL, DEFECT>, &launchPipelineF32<MODEL, DEFECT> }
-
 }  // namespace b200sqp

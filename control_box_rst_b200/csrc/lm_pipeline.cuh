@@ -57,8 +57,8 @@ struct PipeDim
     };
 };
 
-// finite-difference step of the Jacobian columns: the reference's 1e-9 in fp64; 2^-10 in fp32 (rounding ~ 6e-8 / 2^-10 = 6e-5 relative,
-// truncation ~ delta^2 = 1e-6: the Jacobian carries ~1e-4 relative error, far inside the 1e-3 trajectory tolerance of that variant)
+// finite-difference step of the Jacobian columns: the reference's 1e-9 in fp64; 2^-8 in fp32, near the optimum (3 eps)^(1/3) of a central
+// difference (rounding ~ 6e-8 / 2^-8 = 1.5e-5 relative, truncation ~ delta^2 / 6 = 2.5e-6): the Jacobian carries ~2e-5 relative error
 template <class Real>
 struct FdStep;
 template <>
@@ -69,7 +69,7 @@ struct FdStep<double>
 template <>
 struct FdStep<float>
 {
-    static constexpr float delta = 0.0009765625f;
+    static constexpr float delta = 0.00390625f;
 };
 
 // x / dt in the precision of the pipeline: the correctly rounded sequence of dynamics.cuh in fp64, a plain multiplication by the reciprocal in fp32
@@ -551,53 +551,66 @@ __global__ void __launch_bounds__(128) pipeInitKernel(const __grid_constant__ De
 // ---------------------------------------------------------------------------------------------------------------------------
 // (H + mu_acc I) delta = g: block-tridiagonal Cholesky, one warp per instance, lane = row of the current block
 // ---------------------------------------------------------------------------------------------------------------------------
-template <class M, class Real>
-__global__ void __launch_bounds__(128, 7) pipeFactorKernel(const __grid_constant__ DeviceOcp P, const __grid_constant__ DeviceState st,
-                                                        const __grid_constant__ PipeArraysT<Real> pa)
+// IPW = instances per warp: a block row needs NB <= 16 lanes, so in fp32 (half the registers and shared memory per instance) two
+// instances share a warp, one per half-warp (shuffles of width 16); fp64 keeps one instance per warp and the tensor-core Schur update.
+template <class M, class Real, int IPW>
+__global__ void __launch_bounds__(128, IPW == 1 ? 7 : 6) pipeFactorKernel(const __grid_constant__ DeviceOcp P, const __grid_constant__ DeviceState st,
+                                                                        const __grid_constant__ PipeArraysT<Real> pa)
 {
     using Pd = PipeDim<M>;
     constexpr int NX = Pd::NX, NU = Pd::NU, NB = Pd::NB, ND = Pd::ND, NE = Pd::NE, NXXP = Pd::template Padded<Real>::nxxp;
     constexpr bool F64 = sizeof(Real) == 8;
     constexpr int RB   = (int)sizeof(Real);
+    constexpr int HL   = 32 / IPW;  // lanes per instance
     constexpr unsigned FULL = 0xffffffffu;
     static_assert((ND * RB) % 16 == 0 && (NE * RB) % 16 == 0 && (NXXP * RB) % 16 == 0, "bulk copies move multiples of 16 bytes");
+    static_assert(NB <= HL && (IPW == 1 || !F64), "one lane per block row; the fp64 tensor-core tiles span the whole warp");
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
-    const int i    = blockIdx.x * 4 + wib;
-    // Lane r < NB owns ROW r of the current block in registers.  The blocks arrive from HBM by TMA bulk copies into a two-stage
-    // ring per warp (the next block is in flight while the current one is eliminated); shared memory also holds what other lanes
-    // must read (W_k rows, the trailing block of the previous factor) and stages the coalesced stores.
-    __shared__ __align__(16) Real stD[4][2][ND];    // forward: D_k        backward: L_k
-    __shared__ __align__(16) Real stE[4][2][NE];    // forward: E_k        backward: W_{k+1}
-    __shared__ __align__(16) Real stA[4][2][NXXP];  // forward: A^T A of interval k+1
-    __shared__ __align__(8) unsigned long long bars[4][2];
-    __shared__ Real sLxx[4][NX][NX + 1];  // trailing nx x nx block of the previous factor (reciprocal diagonal)
+    const int sub = lane / HL, hl = lane % HL;  // instance of this warp, lane within the instance
+    const int i_raw = (blockIdx.x * 4 + wib) * IPW + sub;
+    // Lane r < NB of an instance owns ROW r of the current block in registers.  The blocks arrive from HBM by TMA bulk copies into a
+    // two-stage ring per instance (the next block is in flight while the current one is eliminated); shared memory also holds what
+    // other lanes must read (W_k rows, the trailing block of the previous factor) and stages the coalesced stores.
+    __shared__ __align__(16) Real stD[4][IPW][2][ND];    // forward: D_k        backward: L_k
+    __shared__ __align__(16) Real stE[4][IPW][2][NE];    // forward: E_k        backward: W_{k+1}
+    __shared__ __align__(16) Real stA[4][IPW][2][NXXP];  // forward: A^T A of interval k+1
+    __shared__ __align__(8) unsigned long long bars[4][IPW][2];
+    __shared__ Real sLxx[4][IPW][NX][NX + 1];  // trailing nx x nx block of the previous factor (reciprocal diagonal)
     // W_k overwrites E_k and L_k overwrites D_k in their stage (same packed layouts) once every lane holds its row in registers:
-    // the coalesced stores then run straight out of the stage, and 7 thread blocks (28 warps) fit one SM
-    if (lane == 0)
+    // the coalesced stores then run straight out of the stage
+    if (hl == 0)
     {
-        mbarInit(&bars[wib][0], 1);
-        mbarInit(&bars[wib][1], 1);
+        mbarInit(&bars[wib][sub][0], 1);
+        mbarInit(&bars[wib][sub][1], 1);
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     __syncthreads();
-    if (i >= P.B || !(pa.flags[i] & PF_ACTIVE)) return;
+    // an instance that is out of range or not active this pass still walks through the code with its half-warp (the warp's control
+    // flow is shared) on the data of a valid instance, but writes nothing
+    const bool valid = i_raw < P.B && (pa.flags[i_raw < P.B ? i_raw : 0] & PF_ACTIVE);
+    if (!__any_sync(FULL, valid)) return;
+    const int i      = i_raw < P.B ? i_raw : P.B - 1;
     const int K      = P.K;
     const Real mua   = (Real)pa.mu_acc[i];
     const double mu  = st.mu[i];
-    const bool rowl  = lane < NB;
+    const bool rowl  = hl < NB;
+    Real* sD[2] = {stD[wib][sub][0], stD[wib][sub][1]};
+    Real* sE[2] = {stE[wib][sub][0], stE[wib][sub][1]};
+    Real* sA[2] = {stA[wib][sub][0], stA[wib][sub][1]};
+    unsigned long long* bar[2] = {&bars[wib][sub][0], &bars[wib][sub][1]};
     unsigned phase[2] = {0u, 0u};
     bool ok           = true;
     auto issueForward = [&](int k) {
-        if (lane == 0)
+        if (hl == 0)
         {
             const size_t blk = (size_t)i * K + k;
             const int sidx   = k & 1;
             const unsigned bytes = ND * RB + (k > 0 ? NE * RB : 0) + (k + 1 < K ? NXXP * RB : 0);
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // our generic-proxy writes to this stage come first
-            mbarExpectTx(&bars[wib][sidx], bytes);
-            bulkLoad(stD[wib][sidx], pa.D + blk * ND, ND * RB, &bars[wib][sidx]);
-            if (k > 0) bulkLoad(stE[wib][sidx], pa.E + blk * NE, NE * RB, &bars[wib][sidx]);
-            if (k + 1 < K) bulkLoad(stA[wib][sidx], pa.DA + (blk + 1) * NXXP, NXXP * RB, &bars[wib][sidx]);
+            mbarExpectTx(bar[sidx], bytes);
+            bulkLoad(sD[sidx], pa.D + blk * ND, ND * RB, bar[sidx]);
+            if (k > 0) bulkLoad(sE[sidx], pa.E + blk * NE, NE * RB, bar[sidx]);
+            if (k + 1 < K) bulkLoad(sA[sidx], pa.DA + (blk + 1) * NXXP, NXXP * RB, bar[sidx]);
         }
     };
     issueForward(0);
@@ -610,11 +623,13 @@ __global__ void __launch_bounds__(128, 7) pipeFactorKernel(const __grid_constant
         Real y = 0;                           // lane r < NB holds rhs component r
         if (rowl)
         {
-            y = pa.g[blk * NB + lane];
-            if (k + 1 < K && lane >= NU) y += pa.gA[(blk + 1) * NX + (lane - NU)];
+            y = pa.g[blk * NB + hl];
+            if (k + 1 < K && hl >= NU) y += pa.gA[(blk + 1) * NX + (hl - NU)];
         }
-        ok = mbarWait(&bars[wib][sidx], phase[sidx]) && ok;
+        ok = mbarWait(bar[sidx], phase[sidx]) && ok;
         phase[sidx] ^= 1u;
+        Real* cD = sD[sidx];
+        Real* cE = sE[sidx];
         if (k > 0)
         {
             // W_k Lxx^T = E_k: row r per lane
@@ -622,19 +637,20 @@ __global__ void __launch_bounds__(128, 7) pipeFactorKernel(const __grid_constant
 #pragma unroll
             for (int a = 0; a < NX; ++a)
             {
-                Real s = rowl ? stE[wib][sidx][lane * NX + a] : Real(0);
+                Real s = rowl ? cE[hl * NX + a] : Real(0);
 #pragma unroll
-                for (int b = 0; b < a; ++b) s = fmaT(-wr[b], sLxx[wib][a][b], s);
-                wr[a] = s * sLxx[wib][a][a];
+                for (int b = 0; b < a; ++b) s = fmaT(-wr[b], sLxx[wib][sub][a][b], s);
+                wr[a] = s * sLxx[wib][sub][a][a];
             }
             __syncwarp();  // every lane has read its E row
             if (rowl)
             {
 #pragma unroll
-                for (int a = 0; a < NX; ++a) stE[wib][sidx][lane * NX + a] = wr[a];
+                for (int a = 0; a < NX; ++a) cE[hl * NX + a] = wr[a];
             }
             __syncwarp();
-            for (int idx = lane; idx < NE; idx += 32) pa.W[blk * NE + idx] = stE[wib][sidx][idx];
+            if (valid)
+                for (int idx = hl; idx < NE; idx += HL) pa.W[blk * NE + idx] = cE[idx];
             if constexpr (F64)
             {
                 // Schur complement S_k -= W_k W_k^T on the staged block with fp64 tensor-core tiles (DMMA m8n8k4): lower triangle = the
@@ -646,58 +662,58 @@ __global__ void __launch_bounds__(128, 7) pipeFactorKernel(const __grid_constant
                     const int r0 = (t == 0) ? 0 : 8, c0 = (t == 2) ? 8 : 0;
                     const int r = r0 + fm, c = c0 + 2 * fk;
                     const bool in0 = r < NB && c <= r, in1 = r < NB && c + 1 <= r;
-                    double d0 = in0 ? stD[wib][sidx][tri(r, c)] : 0.0;
-                    double d1 = in1 ? stD[wib][sidx][tri(r, c + 1)] : 0.0;
+                    double d0 = in0 ? cD[tri(r, c)] : 0.0;
+                    double d1 = in1 ? cD[tri(r, c + 1)] : 0.0;
 #pragma unroll
                     for (int k0 = 0; k0 < NX; k0 += 4)
                     {
-                        const double af = (r0 + fm < NB) ? -stE[wib][sidx][(r0 + fm) * NX + k0 + fk] : 0.0;
-                        const double bf = (c0 + fm < NB) ? stE[wib][sidx][(c0 + fm) * NX + k0 + fk] : 0.0;
+                        const double af = (r0 + fm < NB) ? -cE[(r0 + fm) * NX + k0 + fk] : 0.0;
+                        const double bf = (c0 + fm < NB) ? cE[(c0 + fm) * NX + k0 + fk] : 0.0;
                         dmma884(d0, d1, af, bf);
                     }
-                    if (in0) stD[wib][sidx][tri(r, c)] = d0;
-                    if (in1) stD[wib][sidx][tri(r, c + 1)] = d1;
+                    if (in0) cD[tri(r, c)] = d0;
+                    if (in1) cD[tri(r, c + 1)] = d1;
                 }
             }
             else
             {
                 // fp32: S_k -= W_k W_k^T on the FMA pipe: lane r updates its own row; the rows of W are read from the stage as float4
-                // (every lane reads the same W_c: a broadcast)
+                // (all lanes of an instance read the same W_c: a broadcast)
                 if (rowl)
                 {
 #pragma unroll
                     for (int c = 0; c < NB; ++c)
                     {
-                        if (c <= lane)
+                        if (c <= hl)
                         {
-                            float s = stD[wib][sidx][tri(lane, c)];
+                            float s = cD[tri(hl, c)];
 #pragma unroll
                             for (int q = 0; q < NX; q += 4)
                             {
-                                const float4 wc = *reinterpret_cast<const float4*>(&stE[wib][sidx][c * NX + q]);
+                                const float4 wc = *reinterpret_cast<const float4*>(&cE[c * NX + q]);
                                 s = fmaf(-wr[q], wc.x, fmaf(-wr[q + 1], wc.y, fmaf(-wr[q + 2], wc.z, fmaf(-wr[q + 3], wc.w, s))));
                             }
-                            stD[wib][sidx][tri(lane, c)] = s;
+                            cD[tri(hl, c)] = s;
                         }
                     }
                 }
             }
             // rhs update
 #pragma unroll
-            for (int a = 0; a < NX; ++a) y = fmaT(-wr[a], __shfl_sync(FULL, yp_x, a), y);
+            for (int a = 0; a < NX; ++a) y = fmaT(-wr[a], __shfl_sync(FULL, yp_x, a, HL), y);
             __syncwarp();
         }
         // ---- row r of S_k = D_k - W_k W_k^T (+ A^T A of interval k+1 on the x-x part, + damping)
-        Real row[NB];  // row[c], c <= lane
+        Real row[NB];  // row[c], c <= hl
 #pragma unroll
         for (int c = 0; c < NB; ++c)
         {
             Real v = 0;
-            if (rowl && c <= lane)
+            if (rowl && c <= hl)
             {
-                v = stD[wib][sidx][tri(lane, c)];
-                if (k + 1 < K && c >= NU) v += stA[wib][sidx][tri(lane - NU, c - NU)];
-                if (c == lane) v += mua;
+                v = cD[tri(hl, c)];
+                if (k + 1 < K && c >= NU) v += sA[sidx][tri(hl - NU, c - NU)];
+                if (c == hl) v += mua;
             }
             row[c] = v;
         }
@@ -706,16 +722,16 @@ __global__ void __launch_bounds__(128, 7) pipeFactorKernel(const __grid_constant
 #pragma unroll
         for (int j = 0; j < NB; ++j)
         {
-            const Real inv = pivotRsqrtT(__shfl_sync(FULL, row[j], j));
-            const Real yj  = __shfl_sync(FULL, y, j) * inv;
-            const Real l   = (lane > j) ? row[j] * inv : Real(0);
-            if (lane > j) y = fmaT(-l, yj, y);
-            if (lane == j) y = yj;
-            row[j] = (lane == j) ? inv : l;
+            const Real inv = pivotRsqrtT(__shfl_sync(FULL, row[j], j, HL));
+            const Real yj  = __shfl_sync(FULL, y, j, HL) * inv;
+            const Real l   = (hl > j) ? row[j] * inv : Real(0);
+            if (hl > j) y = fmaT(-l, yj, y);
+            if (hl == j) y = yj;
+            row[j] = (hl == j) ? inv : l;
 #pragma unroll
             for (int c = j + 1; c < NB; ++c)
             {
-                const Real lc = __shfl_sync(FULL, l, c);
+                const Real lc = __shfl_sync(FULL, l, c, HL);
                 row[c]        = fmaT(-l, lc, row[c]);  // lanes < c hold zeros there and l = 0 for lanes <= j
             }
         }
@@ -725,34 +741,36 @@ __global__ void __launch_bounds__(128, 7) pipeFactorKernel(const __grid_constant
         {
 #pragma unroll
             for (int c = 0; c < NB; ++c)
-                if (c <= lane) stD[wib][sidx][tri(lane, c)] = row[c];
-            pa.y[blk * NB + lane] = y;
-            if (lane >= NU)
+                if (c <= hl) cD[tri(hl, c)] = row[c];
+            if (valid) pa.y[blk * NB + hl] = y;
+            if (hl >= NU)
             {
 #pragma unroll
                 for (int c = NU; c < NB; ++c)
-                    if (c <= lane) sLxx[wib][lane - NU][c - NU] = row[c];
+                    if (c <= hl) sLxx[wib][sub][hl - NU][c - NU] = row[c];
             }
         }
-        yp_x = __shfl_sync(FULL, y, NU + (lane < NX ? lane : 0));
+        yp_x = __shfl_sync(FULL, y, NU + (hl < NX ? hl : 0), HL);
         __syncwarp();
-        for (int idx = lane; idx < ND; idx += 32) pa.L[blk * ND + idx] = stD[wib][sidx][idx];
+        if (valid)
+            for (int idx = hl; idx < ND; idx += HL) pa.L[blk * ND + idx] = cD[idx];
         __syncwarp();
     }
     // ---- back-substitution, bottom-up: L_k^T delta_k = y_k - W_{k+1}^T delta_{k+1} (x-part).  The factor blocks were written through
-    //      the generic proxy above and are read back by the async proxy: fence in between.
+    //      the generic proxy above and are read back by the async proxy: fence in between.  (A half-warp that writes nothing reads the
+    //      factor an earlier pass left for its instance: finite data, results discarded.)
     __threadfence();
     asm volatile("fence.proxy.async;" ::: "memory");
     __syncwarp();
     auto issueBackward = [&](int k, int sidx) {
-        if (lane == 0)
+        if (hl == 0)
         {
             const size_t blk = (size_t)i * K + k;
             const unsigned bytes = ND * RB + (k + 1 < K ? NE * RB : 0);
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-            mbarExpectTx(&bars[wib][sidx], bytes);
-            bulkLoad(stD[wib][sidx], pa.L + blk * ND, ND * RB, &bars[wib][sidx]);
-            if (k + 1 < K) bulkLoad(stE[wib][sidx], pa.W + (blk + 1) * NE, NE * RB, &bars[wib][sidx]);
+            mbarExpectTx(bar[sidx], bytes);
+            bulkLoad(sD[sidx], pa.L + blk * ND, ND * RB, bar[sidx]);
+            if (k + 1 < K) bulkLoad(sE[sidx], pa.W + (blk + 1) * NE, NE * RB, bar[sidx]);
         }
     };
     issueBackward(K - 1, 0);
@@ -767,48 +785,48 @@ __global__ void __launch_bounds__(128, 7) pipeFactorKernel(const __grid_constant
         Real d = 0, gfull = 0;
         if (rowl)
         {
-            d     = pa.y[blk * NB + lane];
-            gfull = pa.g[blk * NB + lane];
-            if (k + 1 < K && lane >= NU) gfull += pa.gA[(blk + 1) * NX + (lane - NU)];
+            d     = pa.y[blk * NB + hl];
+            gfull = pa.g[blk * NB + hl];
+            if (k + 1 < K && hl >= NU) gfull += pa.gA[(blk + 1) * NX + (hl - NU)];
         }
-        ok = mbarWait(&bars[wib][sidx], phase[sidx]) && ok;
+        ok = mbarWait(bar[sidx], phase[sidx]) && ok;
         phase[sidx] ^= 1u;
         if (k + 1 < K)
         {
             Real s = 0;
-            const int a = (lane >= NU && rowl) ? lane - NU : 0;
+            const int a = (hl >= NU && rowl) ? hl - NU : 0;
 #pragma unroll
-            for (int r = 0; r < NB; ++r) s = fmaT(stE[wib][sidx][r * NX + a], __shfl_sync(FULL, dnext, r), s);
-            if (lane >= NU && rowl) d -= s;
+            for (int r = 0; r < NB; ++r) s = fmaT(sE[sidx][r * NX + a], __shfl_sync(FULL, dnext, r, HL), s);
+            if (hl >= NU && rowl) d -= s;
         }
         // L^T delta = d, column-oriented backward: lane r needs L[j][r] for j >= r, i.e. column r of the factor
         Real colr[NB];
 #pragma unroll
-        for (int j = 0; j < NB; ++j) colr[j] = (rowl && j >= lane) ? stD[wib][sidx][tri(j, lane)] : Real(0);
+        for (int j = 0; j < NB; ++j) colr[j] = (rowl && j >= hl) ? sD[sidx][tri(j, hl)] : Real(0);
 #pragma unroll
         for (int j = NB - 1; j >= 0; --j)
         {
-            const Real dj = __shfl_sync(FULL, d, j) * __shfl_sync(FULL, colr[j], j);
-            if (lane == j) d = dj;
-            if (lane < j) d = fmaT(-colr[j], dj, d);
+            const Real dj = __shfl_sync(FULL, d, j, HL) * __shfl_sync(FULL, colr[j], j, HL);
+            if (hl == j) d = dj;
+            if (hl < j) d = fmaT(-colr[j], dj, d);
         }
         if (rowl)
         {
             const double dd = (double)d;
-            st.dl[tiledSlot(i, k * NB + lane, K * NB)] = dd;
-            dn2                                        = fma(dd, dd, dn2);
-            dq                                         = fma(dd, fma(mu, dd, (double)gfull), dq);
+            if (valid) st.dl[tiledSlot(i, k * NB + hl, K * NB)] = dd;
+            dn2 = fma(dd, dd, dn2);
+            dq  = fma(dd, fma(mu, dd, (double)gfull), dq);
         }
         dnext = d;
         __syncwarp();
     }
 #pragma unroll
-    for (int off = 16; off > 0; off >>= 1)
+    for (int off = HL / 2; off > 0; off >>= 1)
     {
-        dn2 += __shfl_down_sync(FULL, dn2, off);
-        dq += __shfl_down_sync(FULL, dq, off);
+        dn2 += __shfl_down_sync(FULL, dn2, off, HL);
+        dq += __shfl_down_sync(FULL, dq, off, HL);
     }
-    if (lane == 0)
+    if (hl == 0 && valid)
     {
         // a lost bulk copy (or a non-finite factor) poisons the pass: the trial kernel then skips the instance and the control kernel
         // takes the reject branch (mu *= v), exactly as for a step that did not reduce chi2
@@ -937,6 +955,7 @@ bool launchPipelineT(const DeviceOcp& P, const DeviceState& st, const PipeArrays
 {
     const int B = P.B, K = P.K;
     const int warp_blocks_ik = (int)(((long long)B * K + 3) / 4), warp_blocks_i = (B + 3) / 4, thread_blocks_i = (B + 127) / 128;
+    constexpr int IPW = (sizeof(Real) == 4 && PipeDim<M>::NB <= 16) ? 2 : 1;  // instances per warp of the factor kernel
     int any[2] = {0, 0};
     cudaMemsetAsync(pa.any, 0, 2 * sizeof(int), stream);
     pipeSetFlagsKernel<<<thread_blocks_i, 128, 0, stream>>>(pa.flags, B, PF_LIN);
@@ -948,7 +967,7 @@ bool launchPipelineT(const DeviceOcp& P, const DeviceState& st, const PipeArrays
     const int max_passes = 64 * (iterations + 1);
     while (any[0] && passes < max_passes)
     {
-        pipeFactorKernel<M, Real><<<warp_blocks_i, 128, 0, stream>>>(P, st, pa);
+        pipeFactorKernel<M, Real, IPW><<<(B + 4 * IPW - 1) / (4 * IPW), 128, 0, stream>>>(P, st, pa);
         pipeTrialKernel<M, DEFECT, Real><<<dim3(thread_blocks_i, K), 128, 0, stream>>>(P, st, pa);
         cudaMemsetAsync(pa.any, 0, 2 * sizeof(int), stream);
         pipeControlKernel<Real><<<thread_blocks_i, 128, 0, stream>>>(P, st, pa, iterations);

@@ -26,13 +26,14 @@ ap.add_argument("--batch", type=int, default=4096)
 ap.add_argument("--kernel", default="lmSolve")
 ap.add_argument("--tag", default="r2")
 ap.add_argument("--skip", type=int, default=2, help="matching launches to skip (warm-up solves)")
+ap.add_argument("--precision", default="f64")
 a = ap.parse_args()
 
 out_dir = os.path.join(ROOT, "gpurun_out")
 os.makedirs(out_dir, exist_ok=True)
-base = os.path.join(out_dir, f"{a.tag}_{a.kernel}_cfg{a.cfg}_b{a.batch}")
+base = os.path.join(out_dir, f"{a.tag}_{a.kernel}_cfg{a.cfg}_b{a.batch}" + ("" if a.precision == "f64" else "_" + a.precision))
 cmd = ["ncu", "--set", "full", "--clock-control", "none", "--import-source", "on", "-k", f"regex:{a.kernel}", "-s", str(a.skip), "-c", "1", "-f", "-o", base,
-       sys.executable, os.path.join(ROOT, "profiles", "prof_solve.py"), "--cfg", str(a.cfg), "--batch", str(a.batch), "--solves", str(a.skip + 1)]
+       sys.executable, os.path.join(ROOT, "profiles", "prof_solve.py"), "--cfg", str(a.cfg), "--batch", str(a.batch), "--solves", str(a.skip + 1), "--precision", a.precision]
 subprocess.run(cmd, check=True, stdout=subprocess.DEVNULL)
 raw = subprocess.run(["ncu", "-i", base + ".ncu-rep", "--page", "raw", "--csv"], capture_output=True, text=True, check=True).stdout
 rows = list(csv.reader(io.StringIO(raw)))
@@ -53,7 +54,7 @@ def num(k):
 
 
 ocp, kw, _ = problems.config(a.cfg)
-key = bench.workload_name(a.cfg, ocp, a.batch, kw["iterations"]).split("_per_gpu")[0]
+key = bench.workload_name(a.cfg, ocp, a.batch, kw["iterations"]).split("_per_gpu")[0] + ("" if a.precision == "f64" else "_" + a.precision)
 entry = {key: {"kernel": get("Kernel Name"), "dram_bytes_read": int(num("dram__bytes_read.sum")), "dram_bytes_write": int(num("dram__bytes_write.sum")),
                "csrc_sha256": bench.csrc_hash(),
                "source": f"profiles/{os.path.basename(base)}.txt (ncu --set full, one launch, B={a.batch}, {kw['iterations']} LM iterations, kernel sources {bench.csrc_hash()})"}}
