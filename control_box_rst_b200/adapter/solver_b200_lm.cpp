@@ -335,12 +335,9 @@ bool SolverB200Lm::describe(OptimizationProblemInterface& problem, b200sqp_ocp& 
     xref.assign(d.nx, 0.0);
     if (_xref)
     {
-        if (!_xref->isStatic())
-        {
-            _error = "only static state references are supported";
-            return false;
-        }
-        const ReferenceTrajectoryInterface::OutputVector& r = _xref->getReferenceCached(0);
+        // a static reference is one vector; of a non-static one (reference_trajectory.h:60-95) the LAST cached row is the "static" part
+        // (goal, fixed goal components, final-stage constraint) and all rows go to the device through b200sqp_set_reference_trajectory
+        const ReferenceTrajectoryInterface::OutputVector& r = _xref->getReferenceCached(_xref->isStatic() ? 0 : K);
         for (int i = 0; i < d.nx; ++i) xref[i] = r[i];
     }
     else
@@ -525,12 +522,28 @@ bool SolverB200Lm::instanceData(OptimizationProblemInterface& problem, double* x
     for (int i = 0; i < _ocp.nx; ++i) x0[i] = x_first->getData()[i];
     if (_xref)
     {
-        const ReferenceTrajectoryInterface::OutputVector& r = _xref->getReferenceCached(0);
+        const ReferenceTrajectoryInterface::OutputVector& r = _xref->getReferenceCached(_xref->isStatic() ? 0 : K);
         for (int i = 0; i < _ocp.nx; ++i) xref[i] = r[i];
     }
     else
         for (int i = 0; i < _ocp.nx; ++i) xref[i] = _ocp.xf_fixed[i] ? x_last->getData()[i] : 0.0;
     return true;
+}
+
+// A non-static state reference (setStateReference): its cached rows 0..N-1 -- the same for every problem of a batch, the reference object
+// is the solver's -- go to the device as a time-varying reference.  Static references need nothing here.
+bool SolverB200Lm::uploadReferenceTrajectory(int batch)
+{
+    if (!_xref || _xref->isStatic()) return true;
+    const int N = _ocp.n_grid, nx = _ocp.nx;
+    std::vector<double> rows((size_t)batch * N * nx);
+    for (int k = 0; k < N; ++k)
+    {
+        const ReferenceTrajectoryInterface::OutputVector& r = _xref->getReferenceCached(k);
+        for (int i = 0; i < nx; ++i) rows[(size_t)k * nx + i] = r[i];
+    }
+    for (int b = 1; b < batch; ++b) std::copy(rows.begin(), rows.begin() + (size_t)N * nx, rows.begin() + (size_t)b * N * nx);
+    return b200sqp_set_reference_trajectory(_handle, rows.data()) == 0;
 }
 
 // Guard of SURVEY.md section 8b: the device residual vector at the current parameters must equal the reference's computeValues.
@@ -612,7 +625,8 @@ bool SolverB200Lm::solveBatch(const std::vector<OptimizationProblemInterface*>& 
         fail("problems of one batch must share one structure (object " + std::to_string(first_bad.load()) + "): " + errors[0]);
         return false;
     }
-    if (b200sqp_set_problem_data(_handle, x0.data(), xref.data()) != 0 || b200sqp_set_params(_handle, params.data()) != 0)
+    if (b200sqp_set_problem_data(_handle, x0.data(), xref.data()) != 0 || !uploadReferenceTrajectory(B) ||
+        b200sqp_set_params(_handle, params.data()) != 0)
     {
         fail(std::string("upload failed: ") + b200sqp_last_error());
         return false;
@@ -671,7 +685,7 @@ bool SolverB200Lm::evaluateOnDevice(OptimizationProblemInterface& problem, doubl
     }
     Eigen::VectorXd params(n);
     problem.getParameterVector(params);
-    if (b200sqp_set_problem_data(_handle, x0.data(), xref.data()) != 0 || b200sqp_set_params(_handle, params.data()) != 0)
+    if (b200sqp_set_problem_data(_handle, x0.data(), xref.data()) != 0 || !uploadReferenceTrajectory(1) || b200sqp_set_params(_handle, params.data()) != 0)
     {
         fail(std::string("upload failed: ") + b200sqp_last_error());
         return false;

@@ -86,6 +86,7 @@ class SolverB200Lm : public NlpSolverInterface
     bool describe(OptimizationProblemInterface& problem, b200sqp_ocp& ocp, std::vector<double>& x0, std::vector<double>& xref);
     bool upload(OptimizationProblemInterface& problem, int batch, std::vector<double>* x0_out = nullptr, std::vector<double>* xref_out = nullptr);
     bool instanceData(OptimizationProblemInterface& problem, double* x0, double* xref, std::string& error) const;
+    bool uploadReferenceTrajectory(int batch);
     bool selfCheck(OptimizationProblemInterface& problem);
     SolverStatus fail(const std::string& msg);
 

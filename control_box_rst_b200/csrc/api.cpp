@@ -80,6 +80,7 @@ struct b200sqp_solver
     // staging
     double* d_params = nullptr;   // [B][n]
     double* d_x0_host_order = nullptr, *d_xref_host_order = nullptr;  // [B][nx]
+    double* d_xref_traj = nullptr, *d_xref_traj_host_order = nullptr;  // time-varying reference: tiled [(K+1)*nx][S] and its staging [B][(K+1)*nx]
     double* d_u0 = nullptr;       // [B][nu]
     int* d_ref_of_internal = nullptr, *d_internal_of_ref = nullptr, *d_value_rows = nullptr, *d_jac_pos = nullptr;
     double* d_values = nullptr, *d_jac = nullptr, *d_eval_out = nullptr;
@@ -528,6 +529,8 @@ int b200sqp_set_problem_data(b200sqp_handle h, const double* x0, const double* x
         CUDA_TRY(cudaMemcpyAsync(h->d_xref_host_order, xref, bytes, cudaMemcpyHostToDevice, h->stream));
         xref_src = h->d_xref_host_order;
     }
+    // an xref argument (or a missing one = zero reference) is a STATIC reference: it ends a time-varying one
+    h->st.xref_traj = nullptr;
     launchIngest(x0_src, xref_src, h->s.nx, h->st.x0, h->st.xref, h->d_x0_host_order, h->d_xref_host_order, h->B, h->stream);
     h->launches += 1;
     fillPinnedGoal(h);
@@ -535,12 +538,49 @@ int b200sqp_set_problem_data(b200sqp_handle h, const double* x0, const double* x
     return B200SQP_OK;
 }
 
+int b200sqp_set_reference_trajectory(b200sqp_handle h, const double* xref_traj)
+{
+    int rc = checkHandle(h);
+    if (rc) return rc;
+    if (!xref_traj)
+    {
+        h->st.xref_traj = nullptr;
+        return B200SQP_OK;
+    }
+    if (h->s.ocp.grid == B200SQP_GRID_MULTIPLE_SHOOTING)
+        return fail(B200SQP_ERR_UNSUPPORTED, "time-varying references on the shooting grids: the reference's cold start puts xref(0) into the first "
+                                             "shooting node and fixes it there (shooting_grid_base.cpp:259,278), i.e. it ignores the measured state; "
+                                             "not mirrored");
+    if (h->s.ocp.stage_cost == B200SQP_COST_QUADRATIC_LSQ && h->s.ocp.zero_x_ref)
+        return fail(B200SQP_ERR_INVALID, "the descriptor says zero_x_ref = 1 but a reference trajectory is given");
+    const int nx = h->s.nx, n_points = h->s.K + 1;
+    const size_t row = (size_t)n_points * nx, bytes = sizeof(double) * (size_t)h->B * row;
+    if (!h->d_xref_traj)
+    {
+        CUDA_TRY(h->alloc(&h->d_xref_traj, (size_t)h->S * row));
+        CUDA_TRY(h->alloc(&h->d_xref_traj_host_order, (size_t)h->B * row));
+    }
+    CUDA_TRY(cudaMemcpyAsync(h->d_xref_traj_host_order, xref_traj, bytes, cudaMemcpyHostToDevice, h->stream));
+    launchTransposeIn(h->d_xref_traj_host_order, (int)row, h->d_xref_traj, h->B, h->S, h->stream);
+    // the static reference array holds the LAST grid point: goal of the initial guess, value of fixed goal components, reference of the
+    // final-stage constraint (getReferenceCached(n - 1) everywhere in the reference)
+    CUDA_TRY(cudaMemcpy2DAsync(h->d_xref_host_order, sizeof(double) * nx, h->d_xref_traj_host_order + (row - nx), sizeof(double) * row,
+                               sizeof(double) * nx, h->B, cudaMemcpyDeviceToDevice, h->stream));
+    launchTransposeIn(h->d_xref_host_order, nx, h->st.xref, h->B, h->S, h->stream);
+    h->launches += 2;
+    h->st.xref_traj = h->d_xref_traj;
+    fillPinnedGoal(h);
+    CUDA_TRY(cudaGetLastError());
+    CUDA_TRY(cudaStreamSynchronize(h->stream));  // the caller's buffer may be pageable and reused
+    return B200SQP_OK;
+}
+
 int b200sqp_initialize_trajectories(b200sqp_handle h)
 {
     int rc = checkHandle(h);
     if (rc) return rc;
-    launchInitTrajectories(h->st.x0, h->st.xref, h->st.z[0], h->st.cur, h->s.K, h->s.nx, h->s.nu, h->s.vt, h->s.ocp.dt_ref, nullptr, h->B, h->S,
-                           h->stream);
+    launchInitTrajectories(h->st.x0, h->st.xref, h->st.xref_traj, h->st.z[0], h->st.cur, h->s.K, h->s.nx, h->s.nu, h->s.vt, h->s.ocp.dt_ref, h->B,
+                           h->S, h->stream);
     h->launches += 1;
     CUDA_TRY(cudaGetLastError());
     return B200SQP_OK;
@@ -621,7 +661,7 @@ int b200sqp_solve_async(b200sqp_handle h, const b200sqp_lm_options* opts, int32_
         h->peer_solves += 1;
     }
     CUDA_TRY(cudaEventRecord(h->ev_begin, h->stream));
-    if (h->use_pipeline && h->pipeline_enabled)
+    if (h->use_pipeline && h->pipeline_enabled && !h->st.xref_traj)
     {
         // large stage blocks: warp-cooperative multi-kernel pipeline, host-driven passes (blocks until the batch is solved)
         const bool ok = h->precision == B200SQP_PRECISION_F32 ? h->kernels->pipeline_f32(h->P, h->st, h->pipe32, opts->iterations, h->stream)

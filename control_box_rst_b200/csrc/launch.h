@@ -62,8 +62,8 @@ void launchExport(const double* z0, const double* z1, const int* cur, int nu, in
 // [rows][S] -> [B][rows]
 void launchTransposeOut(const double* src, int rows, double* dst, int B, int S, cudaStream_t);
 // FullDiscretizationGridBase::initializeSequences (full_discretization_grid_base.cpp:134-179) on the device
-void launchInitTrajectories(const double* x0 /*[nx][S]*/, const double* xref /*[nx][S]*/, double* z, int* cur, int K, int nx, int nu, int vt,
-                            double dt_ref, const int* xf_fixed_dev, int B, int S, cudaStream_t);
+void launchInitTrajectories(const double* x0 /*[nx][S]*/, const double* xref /*[nx][S]*/, const double* xtraj /*[(K+1)*nx][S] or null*/, double* z,
+                            int* cur, int K, int nx, int nu, int vt, double dt_ref, int B, int S, cudaStream_t);
 // u_0 of every instance -> [B][nu]
 void launchFirstControls(const double* z0, const double* z1, const int* cur, int nu, int slots, double* u0, int B, int S, cudaStream_t);
 

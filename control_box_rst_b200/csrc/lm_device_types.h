@@ -62,7 +62,8 @@ struct DeviceState
 {
     double* z[2];     // [K*NB][S] two parameter buffers: current and trial (roles swap per instance on accept)
     double* x0;       // [NX][S]
-    double* xref;     // [NX][S]
+    double* xref;     // [NX][S]   static state reference = the reference at the last grid point
+    double* xref_traj;  // [(K+1)*NX][S] time-varying state reference, row m = getReferenceCached(m), or null (static reference)
     double* D;        // [K*ND][S] diagonal blocks of J^T J (packed lower)
     double* E;        // [K*NB*NX][S] sub-diagonal coupling blocks
     double* g;        // [K*NB][S]  J^T(-r)

@@ -64,6 +64,7 @@ __global__ void __launch_bounds__(32 * T) lmSolveKernel(const __grid_constant__ 
     const size_t tile   = blockIdx.x;
     const double* x0p   = st.x0 + tile * ((size_t)NX * TILE) + g;
     const double* xrefp = st.xref + tile * ((size_t)NX * TILE) + g;
+    const double* xtrajp = (F::xref_traj && st.xref_traj) ? st.xref_traj + tile * ((size_t)(K + 1) * NX * TILE) + g : nullptr;
     double* D  = st.D + tile * ((size_t)K * ND * TILE) + g;
     double* E  = st.E + tile * ((size_t)K * NE_ * TILE) + g;
     double* gg = st.g + tile * ((size_t)K * NB * TILE) + g;
@@ -125,7 +126,7 @@ __global__ void __launch_bounds__(32 * T) lmSolveKernel(const __grid_constant__ 
         }
         if (T > 1) __syncthreads();  // boundary states are read before any neighbour writes its perturbed copy back
         NormalEquationSink<M, VT, F> sink(P, D, E, gg, ka, kb);
-        if (do_lin) linearizeSweep<M, DEFECT, VT, F>(P, w, z, x0p, xrefp, ka, kb, xn_last, sink);
+        if (do_lin) linearizeSweep<M, DEFECT, VT, F>(P, w, z, x0p, xrefp, xtrajp, ka, kb, xn_last, sink);
         if (T > 1)
         {
             __syncthreads();  // all blocks stored; now the chunk-start contributions can be added to the neighbour's last block
@@ -283,7 +284,7 @@ __global__ void __launch_bounds__(32 * T) lmSolveKernel(const __grid_constant__ 
         {
             const bool do_trial = valid && (s_flags[g] & F_ACTIVE) && !step_small;
             double part         = 0.0;
-            if (do_trial) part = trialChi2<M, DEFECT, VT, F>(P, w, st.z[s_cur[g]] + zoff, dl, st.z[s_cur[g] ^ 1] + zoff, x0p, xrefp, ka, kb);
+            if (do_trial) part = trialChi2<M, DEFECT, VT, F>(P, w, st.z[s_cur[g]] + zoff, dl, st.z[s_cur[g] ^ 1] + zoff, x0p, xrefp, xtrajp, ka, kb);
             s_red[0][p][g] = part;
         }
         __syncthreads();
@@ -411,7 +412,8 @@ __global__ void __launch_bounds__(32) evaluateKernel(const __grid_constant__ Dev
     using Dm          = Dim<M, VT>;
     const size_t tile = i >> 5, lane = i & 31;
     linearizeSweep<M, DEFECT, VT, FeatAll>(P, w, st.z[st.cur[i]] + tile * ((size_t)P.K * Dm::NB * TILE) + lane, st.x0 + tile * ((size_t)Dm::NX * TILE) + lane,
-                                  st.xref + tile * ((size_t)Dm::NX * TILE) + lane, 0, P.K, nullptr, sink);
+                                  st.xref + tile * ((size_t)Dm::NX * TILE) + lane,
+                                  st.xref_traj ? st.xref_traj + tile * ((size_t)(P.K + 1) * Dm::NX * TILE) + lane : nullptr, 0, P.K, nullptr, sink);
 }
 
 // Cooperating threads per instance: small batches are latency bound (one warp per SM would leave the machine idle), so the
@@ -445,7 +447,8 @@ void launchSolve(const DeviceOcp& P, const DeviceState& st, int iterations, int 
     // lean feature set: quadratic lsq stage cost, no state bounds, no pinned goal components, no final-stage constraint
     bool lean = P.final_constraint == 0 && P.stage_cost == B200SQP_COST_QUADRATIC_LSQ;
     for (int j = 0; j < M::NX; ++j) lean = lean && !P.x_bounded[j] && !P.xf_fixed[j];
-    if (flags & SOLVE_FORCE_GENERAL_FEATURES) lean = false;  // b200sqp_set_feature_set: parity tests run both variants on one structure
+    if (flags & SOLVE_FORCE_GENERAL_FEATURES) lean = false;
+    if (st.xref_traj) lean = false;  // a time-varying state reference is a feature of the general set only  // b200sqp_set_feature_set: parity tests run both variants on one structure
     if (lean)
         launchSolveT<M, DEFECT, VT, MAXT, FeatLean>(P, st, iterations, T, blocks, stream);
     else

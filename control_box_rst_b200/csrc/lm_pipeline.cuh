@@ -856,7 +856,7 @@ __global__ void __launch_bounds__(128) pipeTrialKernel(const __grid_constant__ D
     const size_t zoff = tile * ((size_t)P.K * NB * TILE) + lane;
     const int cur     = st.cur[i];
     const double part = trialChi2<M, DEFECT, 0, FeatLean>(P, w, st.z[cur] + zoff, st.dl + zoff, st.z[cur ^ 1] + zoff,
-                                                           st.x0 + tile * ((size_t)NX * TILE) + lane, st.xref + tile * ((size_t)NX * TILE) + lane, k, k + 1);
+                                                           st.x0 + tile * ((size_t)NX * TILE) + lane, st.xref + tile * ((size_t)NX * TILE) + lane, nullptr, k, k + 1);
     pa.cpart[(size_t)k * P.S + i] = part;
 }
 

@@ -103,9 +103,10 @@ __global__ void transposeOutKernel(const double* __restrict__ src, int rows, dou
 // FullDiscretizationGridBase::initializeSequences (optimal_control/src/structured_ocp/discretization_grids/
 // full_discretization_grid_base.cpp:134-179; same code in non_uniform_full_discretization_grid_base.cpp:146-190 and
 // shooting_grid_base.cpp:141-200): dir = (xf - x0)/||xf - x0||, step = ||xf - x0||/(N-1), x_k = x0 + k*step*dir, u_k = uref = 0,
-// dt_k = dt_ref, xf = xref.
-__global__ void initTrajectoriesKernel(const double* __restrict__ x0, const double* __restrict__ xref, double* __restrict__ z, int* __restrict__ cur,
-                                       int K, int nx, int nu, int vt, double dt_ref, int B, int S)
+// dt_k = dt_ref, xf = xref.  With a non-static reference (xtraj: [(K+1)*nx] slots per instance, row m = getReferenceCached(m)) the reference
+// trajectory itself is the initial guess: x_k = xref(k), k >= 1 (full_discretization_grid_base.cpp:181-228).
+__global__ void initTrajectoriesKernel(const double* __restrict__ x0, const double* __restrict__ xref, const double* __restrict__ xtraj,
+                                       double* __restrict__ z, int* __restrict__ cur, int K, int nx, int nu, int vt, double dt_ref, int B, int S)
 {
     // one thread per (instance, interval): the batch alone (4096 threads) would leave most of the machine idle
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -128,7 +129,7 @@ __global__ void initTrajectoriesKernel(const double* __restrict__ x0, const doub
         double dir     = b - a;
         if (dist != 0) dir /= dist;
         // block k holds x_{k+1}; the last block holds xf = xref
-        z[tiled(i, k * nb + nu + vt + j, slots)] = (k + 1 < K) ? a + (double)(k + 1) * step * dir : b;
+        z[tiled(i, k * nb + nu + vt + j, slots)] = xtraj ? xtraj[tiled(i, (k + 1) * nx + j, (K + 1) * nx)] : ((k + 1 < K) ? a + (double)(k + 1) * step * dir : b);
     }
     if (k == 0) cur[i] = 0;
 }
@@ -423,10 +424,10 @@ void launchTransposeOut(const double* src, int rows, double* dst, int B, int S, 
 {
     transposeOutKernel<<<blocksFor(B), 128, 0, st>>>(src, rows, dst, B, S);
 }
-void launchInitTrajectories(const double* x0, const double* xref, double* z, int* cur, int K, int nx, int nu, int vt, double dt_ref,
-                            const int* /*xf_fixed_dev*/, int B, int S, cudaStream_t st)
+void launchInitTrajectories(const double* x0, const double* xref, const double* xtraj, double* z, int* cur, int K, int nx, int nu, int vt, double dt_ref,
+                            int B, int S, cudaStream_t st)
 {
-    initTrajectoriesKernel<<<dim3(blocksFor(B), K), 128, 0, st>>>(x0, xref, z, cur, K, nx, nu, vt, dt_ref, B, S);
+    initTrajectoriesKernel<<<dim3(blocksFor(B), K), 128, 0, st>>>(x0, xref, xtraj, z, cur, K, nx, nu, vt, dt_ref, B, S);
 }
 void launchFirstControls(const double* z0, const double* z1, const int* cur, int nu, int slots, double* u0, int B, int S, cudaStream_t st)
 {

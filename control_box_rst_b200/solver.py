@@ -28,7 +28,7 @@ ABI_SYMBOLS = [
     "b200sqp_last_solve_ms", "b200sqp_launch_count", "b200sqp_device_pointers", "b200sqp_set_stream", "b200sqp_set_threads_per_instance",
     "b200sqp_set_phase_profile", "b200sqp_get_phase_cycles", "b200sqp_final_constraint_indices",
     "b200sqp_peer_export", "b200sqp_peer_attach", "b200sqp_peer_wait", "b200sqp_peer_gathered", "b200sqp_peer_detach", "b200sqp_peer_status", "b200sqp_linearize_dynamics", "b200sqp_warm_start_shift", "b200sqp_mpc_step",
-    "b200sqp_plant_step", "b200sqp_closed_loop", "b200sqp_dynamics_hessian", "b200sqp_set_feature_set", "b200sqp_measure_fp64_peak", "b200sqp_set_precision",
+    "b200sqp_plant_step", "b200sqp_closed_loop", "b200sqp_dynamics_hessian", "b200sqp_set_feature_set", "b200sqp_measure_fp64_peak", "b200sqp_set_precision", "b200sqp_set_reference_trajectory",
 ]
 
 
@@ -234,6 +234,16 @@ class BatchedLevenbergMarquardt:
             xref = np.ascontiguousarray(xref, np.float64)
             assert xref.shape == x0.shape
         _check(self._lib.b200sqp_set_problem_data(self._h, _d(x0), _d(xref)))
+
+    def set_reference_trajectory(self, xref_traj):
+        """time-varying state reference [batch, n_grid, nx] (row k = getReferenceCached(k)); None = back to the static reference.  Call after
+        set_problem_data."""
+        if xref_traj is None:
+            _check(self._lib.b200sqp_set_reference_trajectory(self._h, None))
+            return
+        xref_traj = np.ascontiguousarray(xref_traj, np.float64)
+        assert xref_traj.shape == (self.batch, self.ocp.n_grid, self.ocp.nx), xref_traj.shape
+        _check(self._lib.b200sqp_set_reference_trajectory(self._h, _d(xref_traj)))
 
     def initialize_trajectories(self):
         _check(self._lib.b200sqp_initialize_trajectories(self._h))

@@ -176,6 +176,14 @@ int b200sqp_jacobian_pattern(const b200sqp_ocp* ocp, int32_t* col_ptr /*[n+1]*/,
  * PINNED buffers (cudaHostAlloc / cudaHostRegister) are read in place by a kernel and must stay valid and unchanged until
  * b200sqp_synchronize or the next blocking call on the handle (b200sqp_solve / _step / _mpc_step / _get_*). */
 int b200sqp_set_problem_data(b200sqp_handle h, const double* x0, const double* xref);
+/* Time-varying state reference (a ReferenceTrajectoryInterface with isStatic() == false, src/core/include/corbo-core/reference_trajectory.h:60-95):
+ * xref_traj [batch][n_grid][nx], row k = what getReferenceCached(k) returns for that instance.  The cost edge of grid point k then measures
+ * x_k against row k (quadratic_cost.cpp:116-121, final_state_cost.cpp); the initial guess of b200sqp_initialize_trajectories becomes the
+ * reference trajectory itself (full_discretization_grid_base.cpp:181-228); goal, fixed goal components and the final-stage constraint use
+ * the last row.  Call after b200sqp_set_problem_data (whose xref argument, also NULL, re-establishes a static reference); NULL here does the
+ * same.  Full-discretisation grids only: B200SQP_ERR_UNSUPPORTED on the shooting grid, whose cold start in the reference ignores the
+ * measured state for non-static references (shooting_grid_base.cpp:259,278).  Host pointer, copied before the call returns. */
+int b200sqp_set_reference_trajectory(b200sqp_handle h, const double* xref_traj);
 /* FullDiscretizationGridBase::initializeSequences (full_discretization_grid_base.cpp:134-179): linear x0 -> xref interpolation,
  * u = 0, dt = dt_ref, on the device. */
 int b200sqp_initialize_trajectories(b200sqp_handle h);

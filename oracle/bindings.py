@@ -68,6 +68,13 @@ class _Checker:
     def available(cls):
         return os.path.exists(cls.path)
 
+    def set_xref_points(self, n_points):
+        """n_points > 1: every xref argument is a time-varying reference [n_grid, nx] per instance (row k = what the reference's
+        getReferenceCached(k) returns); 0: static reference [nx] (the default).  Process-global switch of the checker library."""
+        f = getattr(self.lib, self.prefix + "set_xref_points")
+        f.restype = C.c_int
+        f(C.c_int(int(n_points)))
+
     def dims(self, ocp):
         out = abi.Dims()
         rc = self._dims(C.byref(ocp), C.byref(out))

@@ -126,7 +126,7 @@ struct RefOcp
     std::shared_ptr<TracingProblem> problem;
     std::shared_ptr<LevenbergMarquardtSparse> solver;
     SystemDynamicsInterface::Ptr dynamics;
-    StaticReference::Ptr xref;
+    ReferenceTrajectoryInterface::Ptr xref;  // StaticReference, or TableReference when a trajectory is given (corbo_ref_set_xref_points)
     ZeroReference::Ptr uref;
     int grid_kind = 0;
 };
@@ -325,14 +325,50 @@ bool buildOcp(const b200sqp_ocp& d, const b200sqp_lm_options& o, RefOcp& r)
 
 // Everything StructuredOptimalControlProblem::compute (structured_optimal_control_problem.cpp:77-154) does before
 // _solver->solve(): grid update (initialises the trajectories on the first call) and index precomputation.
+// A user-side reference trajectory for the reference's ReferenceTrajectoryInterface (core/reference_trajectory.h:60-95): non-static, its
+// cached value at grid point k is row k of a table.  The reference's own non-static classes (DiscreteTimeReferenceTrajectory, ...)
+// produce such rows by interpolating a time series; handing the rows over directly keeps the checkers' inputs bit-identical.
+class TableReference : public ReferenceTrajectoryInterface
+{
+ public:
+    TableReference(const double* rows, int n, int dim) : _rows(n, OutputVector(dim))
+    {
+        for (int k = 0; k < n; ++k)
+            for (int i = 0; i < dim; ++i) _rows[k][i] = rows[(size_t)k * dim + i];
+    }
+    Ptr getInstance() const override { return std::make_shared<TableReference>(nullptr, 0, 0); }
+    bool isStatic() const override { return false; }
+    bool isZero() const override { return false; }
+    int getDimension() const override { return _rows.empty() ? 0 : (int)_rows[0].size(); }
+    void precompute(double, int, Time) override {}
+    void precompute(const std::vector<double>&, Time) override {}
+    void getReference(const Time&, OutputVector& ref) const override { ref = _rows.front(); }
+    const OutputVector& getReferenceCached(int k) const override { return _rows[std::min<int>(std::max(k, 0), (int)_rows.size() - 1)]; }
+    const OutputVector& getNextSteadyState(const Time&) override { return _rows.back(); }
+    bool isCached(double, int, Time) const override { return true; }
+    bool isCached(const std::vector<double>&, Time) const override { return true; }
+
+ private:
+    std::vector<OutputVector> _rows;
+};
+
+// see sqp_oracle_set_xref_points: > 1 = every `xref` argument is a trajectory [n_grid][nx] (row k = getReferenceCached(k))
+static int g_xref_points = 0;
+static int xrefStride(const b200sqp_ocp& d) { return g_xref_points > 1 ? d.n_grid * d.nx : d.nx; }
+
 bool prepare(RefOcp& r, const b200sqp_ocp& d, const double* x0, const double* xref, bool new_run, bool* structure_changed)
 {
     Eigen::VectorXd x0v = Eigen::Map<const Eigen::VectorXd>(x0, d.nx);
-    Eigen::VectorXd xr  = xref ? Eigen::VectorXd(Eigen::Map<const Eigen::VectorXd>(xref, d.nx)) : Eigen::VectorXd(Eigen::VectorXd::Zero(d.nx));
-    if (!r.xref)
-        r.xref = std::make_shared<StaticReference>(xr);
+    if (g_xref_points > 1 && xref)
+    {
+        if (g_xref_points != d.n_grid) return false;
+        r.xref = std::make_shared<TableReference>(xref, d.n_grid, d.nx);
+    }
     else
-        r.xref->setReference(xr);
+    {
+        Eigen::VectorXd xr = xref ? Eigen::VectorXd(Eigen::Map<const Eigen::VectorXd>(xref, d.nx)) : Eigen::VectorXd(Eigen::VectorXd::Zero(d.nx));
+        r.xref             = std::make_shared<StaticReference>(xr);
+    }
     Eigen::VectorXd uprev = Eigen::VectorXd::Zero(d.nu);
     GridUpdateResult res  = r.grid->update(x0v, *r.xref, *r.uref, r.ocp->functions(), *r.ocp->edges(), r.dynamics, new_run, Time(0), nullptr, &uprev,
                                            r.grid->getInitialDt(), nullptr, nullptr);
@@ -457,6 +493,12 @@ int corbo_ref_edge_table(const b200sqp_ocp* d, int category /*0 lsq, 1 eq, 2 ine
 }
 
 // Reference initial guess (FullDiscretizationGridBase::initializeSequences) as a parameter vector [n]
+int corbo_ref_set_xref_points(int n_points)
+{
+    g_xref_points = n_points;
+    return 0;
+}
+
 int corbo_ref_initial_params(const b200sqp_ocp* d, const double* x0, const double* xref, double* params)
 {
     b200sqp_lm_options o = {10, 2, 2, 2, 1, 1, 1, 500, 500, 500};
@@ -597,7 +639,7 @@ int corbo_ref_solve_batch(const b200sqp_ocp* d, const b200sqp_lm_options* o, int
             }
             auto t0      = std::chrono::steady_clock::now();
             bool changed = false;
-            prepare(r, *d, x0 + (size_t)i * d->nx, xref ? xref + (size_t)i * d->nx : nullptr, true, &changed);
+            prepare(r, *d, x0 + (size_t)i * d->nx, xref ? xref + (size_t)i * xrefStride(*d) : nullptr, true, &changed);
             if (params_in) r.problem->setParameterVector(Eigen::Map<const Eigen::VectorXd>(params_in + (size_t)i * n, n));
             auto t1         = std::chrono::steady_clock::now();
             double obj      = -1;

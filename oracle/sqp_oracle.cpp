@@ -328,12 +328,19 @@ struct BuildInput
 {
     const b200sqp_ocp* d;
     const double* x0;
-    const double* xref;  // static reference (may be null -> zeros)
+    const double* xref;  // static reference [nx] (may be null -> zeros), or -- see sqp_oracle_set_xref_points -- a trajectory [N][nx]
 };
+
+// Time-varying state reference (ReferenceTrajectoryInterface with isStatic() == false, core/reference_trajectory.h:60-95): when set to
+// the number of grid points N (> 1), every `xref` argument of this library is a trajectory [N][nx] whose row k is what the reference's
+// getReferenceCached(k) returns; 0 or 1 = static reference [nx].  Process-global test switch (this library is test infrastructure).
+static int g_xref_points = 0;
+int xrefStride(const b200sqp_ocp& d) { return g_xref_points > 1 ? d.n_grid * d.nx : d.nx; }
 
 // NlpFunctions::getNonIntegralStageFunctionEdges (optimal_control/src/functions/nlp_functions.cpp:70-132) for the supported stage
 // costs: state term, control term, dt term (created TWICE, :91-107), in that order.
-void addStageCostEdges(Graph& g, const b200sqp_ocp& d, int k, Vertex* xk, Vertex* uk, Vertex* dtk, const std::vector<double>& xref, bool single_dt)
+void addStageCostEdges(Graph& g, const b200sqp_ocp& d, int k, Vertex* xk, Vertex* uk, Vertex* dtk, const std::vector<double>& xref, bool single_dt,
+                       bool nonstatic_ref = false)
 {
     const int nx = d.nx, nu = d.nu;
     if (d.stage_cost == B200SQP_COST_QUADRATIC_LSQ)
@@ -342,7 +349,7 @@ void addStageCostEdges(Graph& g, const b200sqp_ocp& d, int k, Vertex* xk, Vertex
         std::vector<double> qs(nx), rs(nu);
         for (int i = 0; i < nx; ++i) qs[i] = std::sqrt(d.q_diag[i]);  // setWeightQ: cwiseSqrt (:62)
         for (int i = 0; i < nu; ++i) rs[i] = std::sqrt(d.r_diag[i]);
-        bool zero_ref = true;
+        bool zero_ref = !nonstatic_ref;  // a non-static reference is never "zero" here (isZero() is a property of the whole trajectory)
         for (double r : xref) zero_ref = zero_ref && (r == 0.0);  // StaticReference::isZero (core/reference_trajectory.h:123)
         Edge ex;
         ex.dim = nx;
@@ -498,10 +505,15 @@ std::unique_ptr<Graph> buildGraph(const BuildInput& in)
     std::unique_ptr<Graph> gp(new Graph);
     Graph& g = *gp;
 
-    std::vector<double> xref(nx, 0.0);
+    // reference per grid point: getReferenceCached(k); a static reference repeats one vector
+    const bool traj = g_xref_points > 1 && in.xref;
+    if (g_xref_points > 1 && g_xref_points != N) return nullptr;
+    std::vector<std::vector<double>> xref_at(N, std::vector<double>(nx, 0.0));
     if (in.xref)
-        for (int i = 0; i < nx; ++i) xref[i] = in.xref[i];
-    const std::vector<double>& xf_goal = xref;  // xref.getReferenceCached(n-1) of a static reference
+        for (int k = 0; k < N; ++k)
+            for (int i = 0; i < nx; ++i) xref_at[k][i] = in.xref[(traj ? k * nx : 0) + i];
+    const std::vector<double>& xref    = xref_at[N - 1];
+    const std::vector<double>& xf_goal = xref;  // xref.getReferenceCached(n-1)
 
     const bool var_dt    = d.grid == B200SQP_GRID_FD_NONUNIFORM_VARDT;
     const bool single_dt = !var_dt;  // hasSingleDt(): FullDiscretizationGridBase true; NonUniform... false
@@ -533,7 +545,9 @@ std::unique_ptr<Graph> buildGraph(const BuildInput& in)
         Vertex* x = g.add(nx);
         for (int i = 0; i < nx; ++i)
         {
-            x->val[i] = in.x0[i] + (double)k * step * dir[i];
+            // static reference: linear interpolation x0 -> xf (full_discretization_grid_base.cpp:134-179); non-static: the reference
+            // trajectory itself is the initial guess, x_k = xref(k) for k >= 1 (:181-228; shooting_grid_base.cpp likewise)
+            x->val[i] = (traj && k > 0) ? xref_at[k][i] : in.x0[i] + (double)k * step * dir[i];
             x->lb[i]  = d.x_lb[i];
             x->ub[i]  = d.x_ub[i];
         }
@@ -583,7 +597,7 @@ std::unique_ptr<Graph> buildGraph(const BuildInput& in)
     for (int k = 0; k < intervals; ++k)
     {
         Vertex *xk = g.xs[k], *uk = g.us[k], *xn = g.xs[k + 1], *dtk = g.dts[k];
-        addStageCostEdges(g, d, k, xk, uk, dtk, xref, single_dt);
+        addStageCostEdges(g, d, k, xk, uk, dtk, xref_at[k], single_dt, traj);
         Edge e;
         e.dim = nx;
         e.v   = {xk, uk, xn, dtk};  // FDCollocationEdge / MSVariableDynamicsOnlyEdge vertex order (x1,u1,x2,dt)
@@ -1122,6 +1136,12 @@ bool knownAnswerCase(int id, int stage, KnownAnswer& c)
 
 extern "C" {
 
+int sqp_oracle_set_xref_points(int n_points)
+{
+    g_xref_points = n_points;
+    return 0;
+}
+
 int sqp_oracle_dims(const b200sqp_ocp* d, b200sqp_dims* out)
 {
     std::vector<double> x0(d->nx, 0.25);
@@ -1248,7 +1268,7 @@ int sqp_oracle_solve_batch(const b200sqp_ocp* d, const b200sqp_lm_options* o, in
         for (int i = lo; i < hi; ++i)
         {
             auto t0 = std::chrono::steady_clock::now();
-            auto g  = buildGraph({d, x0 + (size_t)i * d->nx, xref ? xref + (size_t)i * d->nx : nullptr});
+            auto g  = buildGraph({d, x0 + (size_t)i * d->nx, xref ? xref + (size_t)i * xrefStride(*d) : nullptr});
             if (!g)
             {
                 ++failures;

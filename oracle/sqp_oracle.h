@@ -8,6 +8,8 @@
 extern "C" {
 #endif
 
+/* > 1: every `xref` argument below is a time-varying reference [n_grid][nx] (row k = getReferenceCached(k)); 0 / 1: static [nx] */
+int sqp_oracle_set_xref_points(int n_points);
 int sqp_oracle_dims(const b200sqp_ocp* d, b200sqp_dims* out);
 int sqp_oracle_vertex_indices(const b200sqp_ocp* d, int32_t* x_idx, int32_t* u_idx, int32_t* dt_idx);
 int sqp_oracle_edge_table(const b200sqp_ocp* d, int category, int32_t* table, int max_edges);

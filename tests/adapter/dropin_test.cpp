@@ -6,6 +6,7 @@
 // sequence.  Also exercises the batch front-end.  Built where /root/reference exists (tests/adapter/Makefile), run on the GPU box.
 #include <corbo-controllers/predictive_controller.h>
 #include <corbo-core/reference_trajectory.h>
+#include <corbo-core/time_series.h>
 #include <corbo-numerics/explicit_integrators.h>
 #include <corbo-optimal-control/functions/final_state_constraints.h>
 #include <corbo-optimal-control/functions/final_state_cost.h>
@@ -627,6 +628,53 @@ int main(int argc, char** argv)
         if (!SystemDynamicsFactory::instance().create("Unicycle") || !SystemDynamicsFactory::instance().create("Quadrotor"))
         {
             std::printf("FAIL: corbo::Unicycle / corbo::Quadrotor not registered in Factory<SystemDynamicsInterface>\n");
+            ++failures;
+        }
+    }
+    // ---- 9. a time-varying state reference: the reference's own DiscreteTimeReferenceTrajectory (a time series, linearly interpolated)
+    //         handed to compute() and -- the same kind of object -- to the plugin through setStateReference(); three MPC steps with
+    //         the reference window moving along the series
+    {
+        auto makeReference = [] {
+            auto series = std::make_shared<TimeSeries>();
+            for (int k = 0; k < 60; ++k)
+            {
+                Eigen::VectorXd v(2);
+                v << 0.5 * std::sin(0.15 * k), 0.02 * k;
+                series->add(0.1 * k, v);
+            }
+            return std::make_shared<DiscreteTimeReferenceTrajectory>(series, TimeSeries::Interpolation::Linear);
+        };
+        auto xr_ref = makeReference(), xr_dev = makeReference();
+        auto s_ref = std::make_shared<LevenbergMarquardtSparse>();
+        auto s_dev = std::make_shared<SolverB200Lm>();
+        s_ref->setIterations(8);
+        s_dev->setIterations(8);
+        Loop lr = makeLoop(s_ref, 25), ld = makeLoop(s_dev, 25);
+        s_dev->setStateReference(xr_dev);
+        lr.ocp->initialize();
+        ld.ocp->initialize();
+        ZeroReference uref1(1);
+        Eigen::VectorXd x0(2);
+        x0 << 0.3, -0.2;
+        double worst9 = 0;
+        bool ok9      = true;
+        for (int s = 0; s < 3; ++s)
+        {
+            ok9 = lr.ocp->compute(x0, *xr_ref, uref1, nullptr, Time(0.1 * s), true) && ok9;
+            ok9 = ld.ocp->compute(x0, *xr_dev, uref1, nullptr, Time(0.1 * s), true) && ok9;
+            worst9 = std::max(worst9, relDiff(paramsOf(*lr.problem), paramsOf(*ld.problem)));
+            Eigen::VectorXd u(1), xn(2);
+            lr.ocp->getFirstControlInput(u);
+            IntegratorExplicitRungeKutta4 rk;
+            rk.solveIVP(x0, u, 0.1, *lr.dynamics, xn);
+            x0 = xn;
+        }
+        std::printf("time-varying reference (DiscreteTimeReferenceTrajectory, 3 MPC steps): max relative trajectory difference vs reference = %.3e "
+                    "(objective %.9g vs %.9g)\n", worst9, lr.ocp->getCurrentObjectiveValue(), ld.ocp->getCurrentObjectiveValue());
+        if (!ok9 || !(worst9 <= 1e-5))
+        {
+            std::printf("FAIL: time-varying reference through the plugin (ok=%d, %s)\n", (int)ok9, s_dev->lastError().c_str());
             ++failures;
         }
     }

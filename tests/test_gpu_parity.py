@@ -504,3 +504,72 @@ def test_quadrotor_fp32_variant_against_the_fp64_oracle(oracle):
         vdp.set_precision("f32")
     assert info.value.code == abi.ERR_UNSUPPORTED
     vdp.clear()
+
+
+@pytest.mark.parametrize("make", [lambda: problems.van_der_pol(12), lambda: problems.van_der_pol(11, collocation=abi.COLL_FORWARD, final_cost=False),
+                                  lambda: problems.make_ocp(grid=abi.GRID_FD_UNIFORM, dynamics=abi.DYN_DUFFING, n_grid=9, dt=0.1, q=(1.0, 2.0), r=(0.3,),
+                                                            qf=(2.0, 1.0), u_lb=(-1.0,), u_ub=(1.0,), dyn_params=(1.0, -1.0, 1.0)),
+                                  lambda: problems.van_der_pol(50)],
+                         ids=["vdp12_fd", "vdp11_forward_nofinal", "duffing9_fd", "vdp50_fd"])
+def test_time_varying_reference_matches_the_checkers(oracle, make):
+    """Non-static state reference (b200sqp_set_reference_trajectory; ReferenceTrajectoryInterface::isStatic() == false): the cost edge of
+    grid point k measures x_k against getReferenceCached(k), the cold start is the reference trajectory itself.  Initial guess, values,
+    Jacobian and drift bit-identical to the checker (the compiled reference where present -- the CPU suite shows oracle == reference bit
+    for bit on the same cases), solves within the polynomial-model bars for T = 1 and the widest thread mapping; switching back to a
+    static reference works; the shooting grid refuses (see include/b200sqp.h)."""
+    from oracle import bindings
+
+    ocp = make()
+    N, nx = ocp.n_grid, ocp.nx
+    B = 40
+    rng = np.random.default_rng(5)
+    x0, _ = problems.instance_data(ocp, B, seed=3)
+    t = np.linspace(0.0, 1.0, N)
+    xref = np.stack([np.stack([0.5 * np.sin(2.0 * t + 0.3 * i) + 0.1 * j for j in range(nx)], axis=1) for i in range(B)])  # [B, N, nx]
+    chk = bindings.Reference() if bindings.Reference.available() else oracle
+    chk.set_xref_points(N)
+    try:
+        lm = solver.BatchedLevenbergMarquardt(ocp, B)
+        lm.set_problem_data(x0, None)
+        lm.set_reference_trajectory(xref)
+        lm.initialize_trajectories()
+        p_init = lm.get_params()
+        for i in range(4):
+            assert np.array_equal(p_init[i], chk.initial_params(ocp, x0[i], xref[i]))
+        p = p_init + rng.uniform(-0.2, 0.2, p_init.shape)
+        lm.set_params(p)
+        w = (2.0, 3.0, 4.0)
+        values, jac = lm.evaluate(w)
+        after = lm.get_params()
+        for i in range(4):
+            v_c, J_c, _, a_c = chk.evaluate(ocp, x0[i], xref[i], p[i], w)
+            assert np.array_equal(values[i], v_c), np.abs(values[i] - v_c).max()
+            assert np.array_equal(_csc_to_dense(ocp, jac[i]), J_c)
+            assert np.array_equal(after[i], a_c)
+        opts = abi.LmOptions.defaults(iterations=8)
+        p_c, c_c, s_c, _ = chk.solve_batch(ocp, opts, x0, xref, threads=4)
+        for T in (1, 8):
+            lm.setIterations(8)
+            lm.set_threads_per_instance(T)
+            lm.initialize_trajectories()
+            status, chi2 = lm.solve(new_run=True)
+            err = _traj_err(lm.get_params(), p_c)
+            assert (err <= 1e-6).mean() >= 0.95 and err.max() <= 1e-4, (T, err.max())
+            np.testing.assert_allclose(chi2, c_c, rtol=1e-6)
+        # back to a static reference (the last row): same as never having set a trajectory
+        chk.set_xref_points(0)
+        last = np.ascontiguousarray(xref[:, -1, :])
+        lm.set_problem_data(x0, last)
+        lm.initialize_trajectories()
+        _, chi2_s = lm.solve(new_run=True)
+        p_s, c_s, _, _ = chk.solve_batch(ocp, opts, x0, last, threads=4)
+        assert _traj_err(lm.get_params(), p_s).max() <= 1e-4 and np.abs(lm.get_params() - p_c).max() > 1e-3
+        np.testing.assert_allclose(chi2_s, c_s, rtol=1e-6)
+        lm.clear()
+    finally:
+        chk.set_xref_points(0)
+    ms = solver.BatchedLevenbergMarquardt(problems.van_der_pol_shooting(10), 4)
+    with pytest.raises(solver.B200SqpError) as info:
+        ms.set_reference_trajectory(np.zeros((4, 10, 2)))
+    assert info.value.code == abi.ERR_UNSUPPORTED
+    ms.clear()

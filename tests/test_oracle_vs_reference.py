@@ -123,3 +123,45 @@ def test_random_structures_first_lm_iterations_match_compiled_reference(oracle, 
     assert np.array_equal(s_r, s_o)
     tr_r, tr_o = reference.trace(ocp, opts, x0[0], xref[0]), oracle.trace(ocp, opts, x0[0], xref[0])
     assert [e[0] for e in tr_r["events"]] == [e[0] for e in tr_o["events"]]
+
+
+@pytest.mark.parametrize("make", [lambda: problems.van_der_pol(12), lambda: problems.van_der_pol(11, collocation=abi.COLL_FORWARD, final_cost=False),
+                                  lambda: problems.make_ocp(grid=abi.GRID_FD_UNIFORM, dynamics=abi.DYN_DUFFING, n_grid=9, dt=0.1, q=(1.0, 2.0), r=(0.3,),
+                                                            qf=(2.0, 1.0), u_lb=(-1.0,), u_ub=(1.0,), dyn_params=(1.0, -1.0, 1.0))],
+                         ids=["vdp12_fd", "vdp11_forward_nofinal", "duffing9_fd"])
+def test_time_varying_reference_oracle_matches_compiled_reference(oracle, reference, make):
+    """A non-static state reference (ReferenceTrajectoryInterface::isStatic() == false, core/reference_trajectory.h:60-95): the cost edge of
+    grid point k measures x_k against getReferenceCached(k), the initial guess is the reference trajectory itself
+    (full_discretization_grid_base.cpp:181-228), the goal is its last point.  Values, Jacobian and drift bit-identical; solves agree.
+    (Full-discretisation grids only: on a cold start the shooting grids put xref(0) into the FIRST shooting node and fix it there,
+    shooting_grid_base.cpp:259,278, i.e. they ignore the measured state -- the device refuses that combination instead of mirroring it.)"""
+    ocp = make()
+    N, nx = ocp.n_grid, ocp.nx
+    rng = np.random.default_rng(5)
+    B = 6
+    x0, _ = problems.instance_data(ocp, B, seed=3)
+    t = np.linspace(0.0, 1.0, N)
+    xref = np.stack([np.stack([0.5 * np.sin(2.0 * t + i) + 0.1 * j for j in range(nx)], axis=1) for i in range(B)])  # [B, N, nx]
+    for chk in (oracle, reference):
+        chk.set_xref_points(N)
+    try:
+        p_r, p_o = reference.initial_params(ocp, x0[0], xref[0]), oracle.initial_params(ocp, x0[0], xref[0])
+        assert np.array_equal(p_r, p_o)
+        p = p_r + rng.uniform(-0.2, 0.2, p_r.shape)
+        v_r, J_r, P_r, a_r = reference.evaluate(ocp, x0[0], xref[0], p, (2.0, 3.0, 4.0))
+        v_o, J_o, P_o, a_o = oracle.evaluate(ocp, x0[0], xref[0], p, (2.0, 3.0, 4.0))
+        assert np.array_equal(P_r, P_o) and np.array_equal(v_r, v_o) and np.array_equal(J_r, J_o) and np.array_equal(a_r, a_o)
+        opts = abi.LmOptions.defaults(iterations=6)
+        pr, cr, sr, _ = reference.solve_batch(ocp, opts, x0, xref, threads=2)
+        po, co, so, _ = oracle.solve_batch(ocp, opts, x0, xref, threads=2)
+        err = np.abs(po - pr).max(axis=1) / np.maximum(1.0, np.abs(pr).max(axis=1))
+        assert err.max() <= 1e-5, err
+        np.testing.assert_allclose(co, cr, rtol=1e-6)
+        # and the trajectory really matters: a static reference at the last point gives another optimum
+        for chk in (oracle, reference):
+            chk.set_xref_points(0)
+        ps, _, _, _ = oracle.solve_batch(ocp, opts, x0, np.ascontiguousarray(xref[:, -1, :]), threads=2)
+        assert np.abs(ps - po).max() > 1e-3
+    finally:
+        for chk in (oracle, reference):
+            chk.set_xref_points(0)
