@@ -1240,7 +1240,7 @@ int b200sqp_set_phase_profile(b200sqp_handle h, int32_t enable)
     if (enable && !h->d_phase_cycles)
     {
         h->phase_blocks = (h->B + 31) / 32;
-        CUDA_TRY(h->alloc(&h->d_phase_cycles, (size_t)h->phase_blocks * 4));
+        CUDA_TRY(h->alloc(&h->d_phase_cycles, (size_t)h->phase_blocks * 5));
     }
     h->st.phase_cycles = enable ? h->d_phase_cycles : nullptr;
     return B200SQP_OK;
@@ -1251,13 +1251,13 @@ int b200sqp_get_phase_cycles(b200sqp_handle h, double* mean_cycles)
     int rc = checkHandle(h);
     if (rc) return rc;
     if (!mean_cycles || !h->st.phase_cycles) return fail(B200SQP_ERR_INVALID, "phase profile is off");
-    std::vector<long long> tmp((size_t)h->phase_blocks * 4);
+    std::vector<long long> tmp((size_t)h->phase_blocks * 5);
     CUDA_TRY(cudaMemcpyAsync(tmp.data(), h->d_phase_cycles, sizeof(long long) * tmp.size(), cudaMemcpyDeviceToHost, h->stream));
     CUDA_TRY(cudaStreamSynchronize(h->stream));
-    for (int q = 0; q < 4; ++q)
+    for (int q = 0; q < 5; ++q)
     {
         double s = 0.0;
-        for (int b = 0; b < h->phase_blocks; ++b) s += (double)tmp[(size_t)b * 4 + q];
+        for (int b = 0; b < h->phase_blocks; ++b) s += (double)tmp[(size_t)b * 5 + q];
         mean_cycles[q] = s / h->phase_blocks;
     }
     return B200SQP_OK;

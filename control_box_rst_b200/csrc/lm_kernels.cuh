@@ -92,7 +92,7 @@ __global__ void __launch_bounds__(32 * T) lmSolveKernel(const __grid_constant__ 
     double mu = 0, mu_acc = 0, rho = 0, chi2_old = 0, last_values = 0, dq = 0;
 
     // optional phase profile (b200sqp_set_phase_profile): thread 0 of the block accumulates clock64() deltas per phase
-    long long prof_acc[4] = {0, 0, 0, 0};
+    long long prof_acc[5] = {0, 0, 0, 0, 0};
     long long prof_last   = 0;
     const bool prof       = st.phase_cycles != nullptr && threadIdx.x == 0;
     if (prof) prof_last = clock64();
@@ -366,11 +366,6 @@ __global__ void __launch_bounds__(32 * T) lmSolveKernel(const __grid_constant__ 
             tick(0);
         }
     }
-    if (prof)
-    {
-#pragma unroll
-        for (int q = 0; q < 4; ++q) st.phase_cycles[(size_t)blockIdx.x * 4 + q] = prof_acc[q];
-    }
 
     // Fused stop-test exchange: instead of a separate all-gather launch after the solve, the per-instance
     // chi2 goes straight into every rank's gather buffer through NVLink peer stores; after a system-scope fence one thread per
@@ -386,6 +381,12 @@ __global__ void __launch_bounds__(32 * T) lmSolveKernel(const __grid_constant__ 
         __syncthreads();
         if (threadIdx.x == 0)
             for (int r = 0; r < st.peer_world; ++r) atomicAdd_system(st.peer_arrivals[r] + st.peer_rank, 1ULL);
+    }
+    tick(4);  // the exchange epilogue (zero without attached peers)
+    if (prof)
+    {
+#pragma unroll
+        for (int q = 0; q < 5; ++q) st.phase_cycles[(size_t)blockIdx.x * 5 + q] = prof_acc[q];
     }
     if (p == 0 && valid)
     {

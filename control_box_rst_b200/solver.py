@@ -385,10 +385,10 @@ class BatchedLevenbergMarquardt:
         _check(self._lib.b200sqp_set_phase_profile(self._h, C.c_int32(1 if enable else 0)))
 
     def phase_cycles(self):
-        """mean SM cycles per thread block of the last solve: dict(linearize, factor_solve, trial, control)"""
-        out = np.zeros(4)
+        """mean SM cycles per thread block of the last solve: dict(linearize, factor_solve, trial, control, exchange)"""
+        out = np.zeros(5)
         _check(self._lib.b200sqp_get_phase_cycles(self._h, _d(out)))
-        return dict(zip(("linearize", "factor_solve", "trial", "control"), out.tolist()))
+        return dict(zip(("linearize", "factor_solve", "trial", "control", "exchange"), out.tolist()))
 
     # -- fused stop-test gather over NVLink peer memory (one process per GPU) ---------------------------------------------------
     def peer_export(self, world, rank):

@@ -313,10 +313,11 @@ int b200sqp_set_threads_per_instance(b200sqp_handle h, int32_t threads);
  * forces the general set on a lean-eligible structure so that parity tests can run both variants on the same problem; 0 = automatic. */
 int b200sqp_set_feature_set(b200sqp_handle h, int32_t general);
 /* measurement aid: when enabled, thread 0 of every thread block of the LM kernel accumulates clock64() per phase; get returns the
- * mean over thread blocks of the last solve, mean_cycles[4] = {linearise (a3/a4/a13), factor+solve (a14), trial values (a2/a12),
- * LM control (a1)} in SM clock cycles.  Off by default (the kernel then only tests one pointer). */
+ * mean over thread blocks of the last solve, mean_cycles[5] = {linearise (a3/a4/a13), factor+solve (a14), trial values (a2/a12),
+ * LM control (a1), stop-test exchange epilogue (peer stores + fence + arrivals; 0 without attached peers)} in SM clock cycles.  Off by
+ * default (the kernel then only tests one pointer). */
 int b200sqp_set_phase_profile(b200sqp_handle h, int32_t enable);
-int b200sqp_get_phase_cycles(b200sqp_handle h, double* mean_cycles /*[4]*/);
+int b200sqp_get_phase_cycles(b200sqp_handle h, double* mean_cycles /*[5]*/);
 /* Arithmetic of the solve.  The reference is fp64 only and so is every path here by default.  B200SQP_PRECISION_F32 is the reduced-
  * precision variant BASELINE.json configs[4] names (12-state quadrotor): Jacobian columns by central differences with delta = 2^-10 in
  * fp32, normal equations, Cholesky factor and substitutions in fp32; parameters, steps, trial-point residuals and the LM control state
