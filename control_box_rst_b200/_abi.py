@@ -118,6 +118,12 @@ class Ocp(C.Structure):
         ("term_xref", C.c_double * MAX_NX),
         ("term_s_diag", C.c_double * MAX_NX),
         ("term_gamma", C.c_double),
+        ("q_dense", C.c_int32),
+        ("r_dense", C.c_int32),
+        ("qf_dense", C.c_int32),
+        ("q_full", C.c_double * (MAX_NX * MAX_NX)),
+        ("r_full", C.c_double * (MAX_NU * MAX_NU)),
+        ("qf_full", C.c_double * (MAX_NX * MAX_NX)),
     ]
 
 

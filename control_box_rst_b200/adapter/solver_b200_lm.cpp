@@ -360,14 +360,28 @@ bool SolverB200Lm::describe(OptimizationProblemInterface& problem, b200sqp_ocp& 
             }
             const Eigen::MatrixXd& Q = q->getWeightQ();
             const Eigen::MatrixXd& R = q->getWeightR();
-            if (Q.rows() != d.nx || R.rows() != d.nu || !Q.isDiagonal(1e-10) || !R.isDiagonal(1e-10))
+            if (Q.rows() != d.nx || Q.cols() != d.nx || R.rows() != d.nu || R.cols() != d.nu)
             {
-                _error = "QuadraticFormCost: diagonal Q (nx) and R (nu) expected";
+                _error = "QuadraticFormCost: Q (nx x nx) and R (nu x nu) expected";
                 return false;
             }
             d.stage_cost = B200SQP_COST_QUADRATIC_LSQ;
             for (int i = 0; i < d.nx; ++i) d.q_diag[i] = Q(i, i);
             for (int i = 0; i < d.nu; ++i) d.r_diag[i] = R(i, i);
+            // full matrices travel as they are: the library takes their square roots like setWeightQ / setWeightR do (diagonal to 1e-10 ->
+            // element-wise, else the upper Cholesky factor; quadratic_cost.cpp:32-96)
+            if (!Q.isDiagonal(1e-10))
+            {
+                d.q_dense = 1;
+                for (int i = 0; i < d.nx; ++i)
+                    for (int j = 0; j < d.nx; ++j) d.q_full[i * d.nx + j] = Q(i, j);
+            }
+            if (!R.isDiagonal(1e-10))
+            {
+                d.r_dense = 1;
+                for (int i = 0; i < d.nu; ++i)
+                    for (int j = 0; j < d.nu; ++j) d.r_full[i * d.nu + j] = R(i, j);
+            }
         }
         else if (auto* t = dynamic_cast<MinimumTime*>(_stage_cost.get()))
         {
@@ -388,13 +402,19 @@ bool SolverB200Lm::describe(OptimizationProblemInterface& problem, b200sqp_ocp& 
     if (_final_cost)
     {
         auto* qf = dynamic_cast<QuadraticFinalStateCost*>(_final_cost.get());
-        if (!qf || !qf->isLsqFormNonIntegralStateTerm(0) || !qf->getWeightQf().isDiagonal(1e-10) || qf->getWeightQf().rows() != d.nx)
+        if (!qf || !qf->isLsqFormNonIntegralStateTerm(0) || qf->getWeightQf().rows() != d.nx || qf->getWeightQf().cols() != d.nx)
         {
-            _error = "final cost must be a diagonal QuadraticFinalStateCost in lsq form";
+            _error = "final cost must be a QuadraticFinalStateCost (nx x nx) in lsq form";
             return false;
         }
         d.final_cost = 1;
         for (int i = 0; i < d.nx; ++i) d.qf_diag[i] = qf->getWeightQf()(i, i);
+        if (!qf->getWeightQf().isDiagonal(1e-10))
+        {
+            d.qf_dense = 1;
+            for (int i = 0; i < d.nx; ++i)
+                for (int j = 0; j < d.nx; ++j) d.qf_full[i * d.nx + j] = qf->getWeightQf()(i, j);
+        }
     }
     d.final_constraint = B200SQP_FINAL_CONSTRAINT_NONE;
     if (has_term_eq)

@@ -60,6 +60,19 @@ const KernelSet* findKernels(int dynamics, int defect, int vt)
     return nullptr;
 }
 
+const KernelSet* findDenseCostKernels(int dynamics, int defect, int vt)
+{
+#if defined(B200SQP_DEV_TRIO) || defined(B200SQP_DEV_VDP_CN_ONLY)
+    return nullptr;
+#else
+    int count            = 0;
+    const KernelSet* set = kernelTableDenseCost(&count);
+    for (int i = 0; i < count; ++i)
+        if (set[i].dynamics == dynamics && set[i].defect == defect && set[i].vt == vt) return &set[i];
+    return nullptr;
+#endif
+}
+
 }  // namespace b200sqp
 
 struct b200sqp_solver
@@ -135,16 +148,21 @@ void fillDeviceOcp(const Structure& s, int B, int S, DeviceOcp& P)
         P.x_lb[i]      = o.x_lb[i];
         P.x_ub[i]      = o.x_ub[i];
         P.x_bounded[i] = (o.x_lb[i] > -kCorboInf || o.x_ub[i] < kCorboInf) ? 1 : 0;
-        P.q_sqrt[i]    = std::sqrt(o.q_diag[i]);   // QuadraticFormCost::setWeightQ -> cwiseSqrt (quadratic_cost.cpp:62)
-        P.qf_sqrt[i]   = std::sqrt(o.qf_diag[i]);  // QuadraticFinalStateCost::setWeightQf (final_state_cost.cpp:66)
+        // QuadraticFormCost::setWeightQ -> cwiseSqrt (quadratic_cost.cpp:62), QuadraticFinalStateCost::setWeightQf (final_state_cost.cpp:66);
+        // with full matrices: the diagonal mode of structure.cpp weightSqrt, or unused (dense factors travel separately)
+        P.q_sqrt[i]    = (!s.q_w.dense && (int)s.q_w.w.size() == s.nx) ? s.q_w.w[i] : std::sqrt(o.q_diag[i]);
+        P.qf_sqrt[i]   = (!s.qf_w.dense && (int)s.qf_w.w.size() == s.nx) ? s.qf_w.w[i] : std::sqrt(o.qf_diag[i]);
     }
     for (int i = 0; i < s.nu; ++i)
     {
         P.u_lb[i]      = o.u_lb[i];
         P.u_ub[i]      = o.u_ub[i];
         P.u_bounded[i] = (o.u_lb[i] > -kCorboInf || o.u_ub[i] < kCorboInf) ? 1 : 0;
-        P.r_sqrt[i]    = std::sqrt(o.r_diag[i]);
+        P.r_sqrt[i]    = (!s.r_w.dense && (int)s.r_w.w.size() == s.nu) ? s.r_w.w[i] : std::sqrt(o.r_diag[i]);
     }
+    P.q_dense  = s.q_w.dense ? 1 : 0;
+    P.r_dense  = s.r_w.dense ? 1 : 0;
+    P.qf_dense = (s.qf_w.dense && P.final_cost) ? 1 : 0;
     P.final_constraint = s.xfFullyFixed() ? 0 : o.final_constraint;
     for (int i = 0; i < s.nx; ++i)
     {
@@ -328,8 +346,11 @@ int b200sqp_create(const b200sqp_ocp* ocp, int32_t batch, int32_t device, b200sq
     std::string err;
     int rc = buildStructure(*ocp, s, err);
     if (rc != B200SQP_OK) return fail(rc, err);
-    const KernelSet* ks = findKernels(ocp->dynamics, s.defect, s.vt);
-    if (!ks) return fail(B200SQP_ERR_UNSUPPORTED, "no device kernel for this (dynamics, defect, grid) combination; no CPU fallback");
+    const KernelSet* ks = s.denseCost() ? findDenseCostKernels(ocp->dynamics, s.defect, s.vt) : findKernels(ocp->dynamics, s.defect, s.vt);
+    if (!ks)
+        return fail(B200SQP_ERR_UNSUPPORTED, s.denseCost() ? "full (non-diagonal) cost weights are not compiled for this (dynamics, defect, grid) combination "
+                                                              "(kernels_dense_cost.cu); no CPU fallback"
+                                                            : "no device kernel for this (dynamics, defect, grid) combination; no CPU fallback");
     int count = 0;
     if (cudaGetDeviceCount(&count) != cudaSuccess || count == 0)
     {
@@ -392,6 +413,19 @@ int b200sqp_create(const b200sqp_ocp* ocp, int32_t batch, int32_t device, b200sq
     h->use_pipeline = ks->pipeline != nullptr && pipelineEligible(h->P, s.nx);
     if (h->use_pipeline && e == cudaSuccess) e = allocPipeArrays(h, h->pipe);
     st.trace = nullptr;
+    if (s.denseCost() && e == cudaSuccess)
+    {
+        // upper Cholesky factors of the full weights: [nx*nx | nu*nu | nx*nx] (Q, R, Qf), zeros where a weight is diagonal
+        std::vector<double> wfull(2 * nx * nx + (size_t)s.nu * s.nu, 0.0);
+        if (s.q_w.dense) std::copy(s.q_w.w.begin(), s.q_w.w.end(), wfull.begin());
+        if (s.r_w.dense) std::copy(s.r_w.w.begin(), s.r_w.w.end(), wfull.begin() + nx * nx);
+        if (s.qf_w.dense) std::copy(s.qf_w.w.begin(), s.qf_w.w.end(), wfull.begin() + nx * nx + (size_t)s.nu * s.nu);
+        double* d_w = nullptr;
+        e           = h->alloc(&d_w, wfull.size());
+        if (e == cudaSuccess) e = cudaMemcpyAsync(d_w, wfull.data(), sizeof(double) * wfull.size(), cudaMemcpyHostToDevice, h->stream);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);  // wfull is a local
+        st.cost_sqrt_full = d_w;
+    }
     if (e == cudaSuccess)
         e = cudaMemcpyAsync(h->d_ref_of_internal, s.ref_of_internal.data(), sizeof(int) * s.ref_of_internal.size(), cudaMemcpyHostToDevice, h->stream);
     if (e == cudaSuccess)

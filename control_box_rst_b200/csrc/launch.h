@@ -42,6 +42,9 @@ const KernelSet* kernelTableCombosMs(int* count);
 const KernelSet* kernelTableLinear(int* count);
 const KernelSet* kernelTableLinear4(int* count);
 const KernelSet* kernelTableIntegrators(int* count);
+// structures with full (non-diagonal) cost weights: their own (smaller) registry; nullptr = combination not compiled in
+const KernelSet* kernelTableDenseCost(int* count);
+const KernelSet* findDenseCostKernels(int dynamics, int defect, int vt);
 
 // layout helpers (util_kernels.cu); all arrays device pointers
 // params [B][n] (reference order)  <->  z (block order, tiled instance-minor [tile][K*NB][32]); pinned slots (ref index -1) are left alone

@@ -43,6 +43,7 @@ struct DeviceOcp
     int xf_fixed[B200SQP_MAX_NX];
     int x_bounded[B200SQP_MAX_NX], u_bounded[B200SQP_MAX_NU], dt_bounded;
     int final_constraint;  // b200sqp_final_constraint (0 if xf is fully fixed: the reference then creates no final-stage edge)
+    int q_dense, r_dense, qf_dense;  // full (non-diagonal) cost weights: the upper Cholesky factors are in DeviceState::cost_sqrt_full
     double term_xref[B200SQP_MAX_NX], term_s[B200SQP_MAX_NX], term_gamma;
     DynParams dyn;
     double dt_ref, dt_lb, dt_ub, tcost_w;
@@ -63,6 +64,7 @@ struct DeviceState
     double* z[2];     // [K*NB][S] two parameter buffers: current and trial (roles swap per instance on accept)
     double* x0;       // [NX][S]
     double* xref;     // [NX][S]   static state reference = the reference at the last grid point
+    const double* cost_sqrt_full;  // [nx*nx | nu*nu | nx*nx] row-major upper factors of Q, R, Qf (structure constants, not per instance) or null
     double* xref_traj;  // [(K+1)*NX][S] time-varying state reference, row m = getReferenceCached(m), or null (static reference)
     double* D;        // [K*ND][S] diagonal blocks of J^T J (packed lower)
     double* E;        // [K*NB*NX][S] sub-diagonal coupling blocks

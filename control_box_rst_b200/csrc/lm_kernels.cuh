@@ -126,7 +126,7 @@ __global__ void __launch_bounds__(32 * T) lmSolveKernel(const __grid_constant__ 
         }
         if (T > 1) __syncthreads();  // boundary states are read before any neighbour writes its perturbed copy back
         NormalEquationSink<M, VT, F> sink(P, D, E, gg, ka, kb);
-        if (do_lin) linearizeSweep<M, DEFECT, VT, F>(P, w, z, x0p, xrefp, xtrajp, ka, kb, xn_last, sink);
+        if (do_lin) linearizeSweep<M, DEFECT, VT, F>(P, w, z, x0p, xrefp, xtrajp, ka, kb, xn_last, sink, F::dense ? st.cost_sqrt_full : nullptr);
         if (T > 1)
         {
             __syncthreads();  // all blocks stored; now the chunk-start contributions can be added to the neighbour's last block
@@ -284,7 +284,8 @@ __global__ void __launch_bounds__(32 * T) lmSolveKernel(const __grid_constant__ 
         {
             const bool do_trial = valid && (s_flags[g] & F_ACTIVE) && !step_small;
             double part         = 0.0;
-            if (do_trial) part = trialChi2<M, DEFECT, VT, F>(P, w, st.z[s_cur[g]] + zoff, dl, st.z[s_cur[g] ^ 1] + zoff, x0p, xrefp, xtrajp, ka, kb);
+            if (do_trial) part = trialChi2<M, DEFECT, VT, F>(P, w, st.z[s_cur[g]] + zoff, dl, st.z[s_cur[g] ^ 1] + zoff, x0p, xrefp, xtrajp, ka, kb,
+                                                                 F::dense ? st.cost_sqrt_full : nullptr);
             s_red[0][p][g] = part;
         }
         __syncthreads();
@@ -402,19 +403,20 @@ __global__ void __launch_bounds__(32 * T) lmSolveKernel(const __grid_constant__ 
 }
 
 // LevenbergMarquardtSparse::computeValues + computeCombinedSparseJacobian, materialised (b200sqp_evaluate)
-template <class M, int DEFECT, int VT>
+template <class M, int DEFECT, int VT, class F>
 __global__ void __launch_bounds__(32) evaluateKernel(const __grid_constant__ DeviceOcp P, const __grid_constant__ DeviceState st, double* values,
                                                      double* jac, const int* value_rows, const int* jac_pos, int v_count, int j_count)
 {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= P.B) return;
     const Weights w{st.w_eq, st.w_ineq, st.w_b};
-    MaterializeSink<M, VT> sink{P, values ? values + i : nullptr, jac ? jac + i : nullptr, value_rows, jac_pos, v_count, j_count};
+    MaterializeSink<M, VT, F> sink{P, values ? values + i : nullptr, jac ? jac + i : nullptr, value_rows, jac_pos, v_count, j_count};
     using Dm          = Dim<M, VT>;
     const size_t tile = i >> 5, lane = i & 31;
-    linearizeSweep<M, DEFECT, VT, FeatAll>(P, w, st.z[st.cur[i]] + tile * ((size_t)P.K * Dm::NB * TILE) + lane, st.x0 + tile * ((size_t)Dm::NX * TILE) + lane,
-                                  st.xref + tile * ((size_t)Dm::NX * TILE) + lane,
-                                  st.xref_traj ? st.xref_traj + tile * ((size_t)(P.K + 1) * Dm::NX * TILE) + lane : nullptr, 0, P.K, nullptr, sink);
+    linearizeSweep<M, DEFECT, VT, F>(P, w, st.z[st.cur[i]] + tile * ((size_t)P.K * Dm::NB * TILE) + lane, st.x0 + tile * ((size_t)Dm::NX * TILE) + lane,
+                                     st.xref + tile * ((size_t)Dm::NX * TILE) + lane,
+                                     st.xref_traj ? st.xref_traj + tile * ((size_t)(P.K + 1) * Dm::NX * TILE) + lane : nullptr, 0, P.K, nullptr, sink,
+                                     F::dense ? st.cost_sqrt_full : nullptr);
 }
 
 // Cooperating threads per instance: small batches are latency bound (one warp per SM would leave the machine idle), so the
@@ -461,9 +463,33 @@ void launchEvaluate(const DeviceOcp& P, const DeviceState& st, double* values, d
                     int j_count, cudaStream_t stream)
 {
     const int blocks = (P.B + 31) / 32;
-    evaluateKernel<M, DEFECT, VT><<<blocks, 32, 0, stream>>>(P, st, values, jac, value_rows, jac_pos, v_count, j_count);
+    evaluateKernel<M, DEFECT, VT, FeatAll><<<blocks, 32, 0, stream>>>(P, st, values, jac, value_rows, jac_pos, v_count, j_count);
 }
 
+// the same two entry points for structures with full (non-diagonal) cost weights: the general feature set + dense cost blocks
+template <class M, int DEFECT, int VT, int MAXT>
+void launchSolveDense(const DeviceOcp& P, const DeviceState& st, int iterations, int threads_per_instance, int /*flags*/, cudaStream_t stream)
+{
+    const int blocks = (P.B + 31) / 32;
+    int T            = threads_per_instance;
+    if (T <= 0)
+    {
+        T = 1;
+        while (T < 8 && P.K / (2 * T) >= 3) T *= 2;
+    }
+    if (T > MAXT) T = MAXT;
+    launchSolveT<M, DEFECT, VT, MAXT, FeatDense>(P, st, iterations, T, blocks, stream);
+}
+template <class M, int DEFECT, int VT>
+void launchEvaluateDense(const DeviceOcp& P, const DeviceState& st, double* values, double* jac, const int* value_rows, const int* jac_pos, int v_count,
+                         int j_count, cudaStream_t stream)
+{
+    const int blocks = (P.B + 31) / 32;
+    evaluateKernel<M, DEFECT, VT, FeatDense><<<blocks, 32, 0, stream>>>(P, st, values, jac, value_rows, jac_pos, v_count, j_count);
+}
+
+#define B200SQP_KERNEL_ENTRY_DENSE(MODEL, DEFECT, VT, MAXT) \
+    KernelSet { MODEL::ID, DEFECT, VT, MODEL::NX, MODEL::NU, MAXT, &launchSolveDense<MODEL, DEFECT, VT, MAXT>, &launchEvaluateDense<MODEL, DEFECT, VT>, nullptr }
 #define B200SQP_KERNEL_ENTRY(MODEL, DEFECT, VT, MAXT) \
     KernelSet { MODEL::ID, DEFECT, VT, MODEL::NX, MODEL::NU, MAXT, &launchSolve<MODEL, DEFECT, VT, MAXT>, &launchEvaluate<MODEL, DEFECT, VT>, nullptr }
 }  // namespace b200sqp

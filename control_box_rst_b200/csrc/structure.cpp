@@ -70,6 +70,71 @@ bool dynamicsDimensions(int dynamics, int& nx, int& nu)
     return true;
 }
 
+WeightSqrt weightSqrt(const double* diag, const double* full, int dense_flag, int dim)
+{
+    WeightSqrt r;
+    auto fromDiagonal = [&](const double* d, int stride) {
+        r.w.resize(dim);
+        for (int i = 0; i < dim; ++i) r.w[i] = std::sqrt(d[(size_t)i * stride]);
+    };
+    if (!dense_flag)
+    {
+        fromDiagonal(diag, 1);
+        return r;
+    }
+    double max_diag = 0;
+    for (int i = 0; i < dim; ++i) max_diag = std::max(max_diag, std::fabs(full[i * dim + i]));
+    bool is_diag = true, is_zero = true;
+    for (int i = 0; i < dim; ++i)
+        for (int j = 0; j < dim; ++j)
+        {
+            if (i != j && !(std::fabs(full[i * dim + j]) <= max_diag * 1e-10)) is_diag = false;  // MatrixBase::isDiagonal(1e-10)
+            if (!(std::fabs(full[i * dim + j]) <= 1e-12)) is_zero = false;                      // MatrixBase::isZero()
+        }
+    if (is_diag)
+    {
+        fromDiagonal(full, dim + 1);
+        for (double v : r.w) r.ok = r.ok && !(v != v);
+        return r;
+    }
+    r.dense = true;
+    r.w.assign((size_t)dim * dim, 0.0);
+    if (is_zero) return r;
+    // llt_inplace<double, Lower>::unblocked on the transposed view (LLT.h:290-320): column k of L = U^T from the upper triangle of M
+    std::vector<double> L((size_t)dim * dim, 0.0);
+    for (int k = 0; k < dim && r.ok; ++k)
+    {
+        double x = full[k * dim + k];
+        if (k > 0)
+        {
+            double sq = L[k * dim] * L[k * dim];
+            for (int j = 1; j < k; ++j) sq += L[k * dim + j] * L[k * dim + j];
+            x -= sq;
+        }
+        if (!(x > 0))
+        {
+            r.ok = false;
+            break;
+        }
+        x              = std::sqrt(x);
+        L[k * dim + k] = x;
+        for (int i = k + 1; i < dim; ++i)
+        {
+            double a = full[k * dim + i];
+            if (k > 0)
+            {
+                double dot = L[i * dim] * L[k * dim];
+                for (int j = 1; j < k; ++j) dot += L[i * dim + j] * L[k * dim + j];
+                a -= dot;
+            }
+            L[i * dim + k] = a / x;
+        }
+    }
+    for (int i = 0; i < dim; ++i)
+        for (int j = i; j < dim; ++j) r.w[i * dim + j] = L[j * dim + i];
+    return r;
+}
+
 int buildStructure(const b200sqp_ocp& ocp, Structure& s, std::string& err)
 {
     s     = Structure();
@@ -138,17 +203,39 @@ int buildStructure(const b200sqp_ocp& ocp, Structure& s, std::string& err)
     if (ocp.stage_cost == B200SQP_COST_QUADRATIC_LSQ)
     {
         for (int i = 0; i < ocp.nx; ++i)
-            if (ocp.q_diag[i] < 0)
+            if (!ocp.q_dense && ocp.q_diag[i] < 0)
             {
                 err = "negative Q diagonal";
                 return B200SQP_ERR_INVALID;
             }
         for (int i = 0; i < ocp.nu; ++i)
-            if (ocp.r_diag[i] < 0)
+            if (!ocp.r_dense && ocp.r_diag[i] < 0)
             {
                 err = "negative R diagonal";
                 return B200SQP_ERR_INVALID;
             }
+        s.q_w = weightSqrt(ocp.q_diag, ocp.q_full, ocp.q_dense, ocp.nx);
+        s.r_w = weightSqrt(ocp.r_diag, ocp.r_full, ocp.r_dense, ocp.nu);
+        if (!s.q_w.ok || !s.r_w.ok)
+        {
+            err = "Q / R is not positive definite (the reference's setWeightQ / setWeightR fail on it too)";
+            return B200SQP_ERR_INVALID;
+        }
+        if (s.q_w.dense && ocp.zero_x_ref)
+        {
+            // quadratic_cost.cpp:112: lsq form + zero reference + non-diagonal Q assigns the SCALAR x^T U x to the cost vector
+            err = "a non-diagonal Q needs a non-zero state reference: the reference's zero-reference lsq branch returns a scalar (quadratic_cost.cpp:112)";
+            return B200SQP_ERR_UNSUPPORTED;
+        }
+    }
+    if (ocp.final_cost == 1)
+    {
+        s.qf_w = weightSqrt(ocp.qf_diag, ocp.qf_full, ocp.qf_dense, ocp.nx);
+        if (!s.qf_w.ok)
+        {
+            err = "Qf is not positive definite";
+            return B200SQP_ERR_INVALID;
+        }
     }
 
     const int nx = ocp.nx, nu = ocp.nu, N = ocp.n_grid, K = N - 1;
@@ -395,8 +482,13 @@ int buildStructure(const b200sqp_ocp& ocp, Structure& s, std::string& err)
                 vr[L.v_xb() + i] = br >= 0 ? b_start + br : -1;
                 jp[L.j_xb() + i] = br >= 0 ? at(ncol[i], b_start + br) : -1;
                 if (xs_row >= 0) jp[L.j_xs() + i] = at(ncol[i], xs_row + i);
+                if (xs_row >= 0)
+                    for (int r = 0; r < nx; ++r) jp[L.j_xsd() + i * nx + r] = at(ncol[i], xs_row + r);
             }
         }
+        if (s.control_cost_idx[k] >= 0)
+            for (int c = 0; c < nu; ++c)
+                for (int r = 0; r < nu; ++r) jp[L.j_ucd() + c * nu + r] = at(ucol[c], s.control_cost_idx[k] + r);
         const int erow = eq_start + s.dynamics_idx[k];
         for (int c = 0; c < nx; ++c)
             for (int r = 0; r < nx; ++r)

@@ -25,6 +25,17 @@ namespace b200sqp {
 
 constexpr double kCorboInf = 2e30;  // CORBO_INF_DBL, core/include/corbo-core/types.h:53
 
+// Square root of a cost weight the way the reference takes it (QuadraticFormCost::setWeightQ / setWeightR, quadratic_cost.cpp:32-96;
+// QuadraticFinalStateCost::setWeightQf, final_state_cost.cpp:38-69): diagonal to 1e-10 -> element-wise square root of the diagonal;
+// else the UPPER Cholesky factor U, M = U^T U (Eigen::LLT<MatrixXd, Upper>, unblocked below 32 rows).
+struct WeightSqrt
+{
+    bool dense = false;
+    std::vector<double> w;  // diagonal: [dim]; dense: [dim*dim] row-major, zeros below the diagonal
+    bool ok = true;          // false: not positive definite (LLT reports NumericalIssue -> the reference's setter returns false)
+};
+WeightSqrt weightSqrt(const double* diag, const double* full, int dense_flag, int dim);
+
 struct Structure
 {
     b200sqp_ocp ocp;
@@ -50,6 +61,8 @@ struct Structure
     std::vector<int32_t> internal_of_ref;                      // [n]
 
     // per-interval scatter tables for b200sqp_evaluate (values rows and CSC positions), see lm_device.cuh
+    WeightSqrt q_w, r_w, qf_w;                                  // square roots of the stage / control / final weights
+    bool denseCost() const { return q_w.dense || r_w.dense || qf_w.dense; }
     std::vector<int32_t> value_rows;                           // [K * values_per_interval]
     std::vector<int32_t> jac_pos;                              // [K * jac_per_interval]
     int values_per_interval = 0, jac_per_interval = 0;
@@ -101,7 +114,13 @@ struct EvalLayout
     int j_xb() const { return j_tb() + 1; }
     int j_teq() const { return j_xb() + nx; }        // nx*nx (col-major), final-stage equality block
     int j_tin() const { return j_teq() + nx * nx; }  // nx, final-stage inequality row
-    int j_count() const { return j_tin() + nx; }
+    // full (non-diagonal) cost weights: the whole nu x nu / nx x nx block of the control-cost edge and of the cost edge on x_{k+1}
+    // (col-major: [column c][row i]); the diagonal slots above stay unused then
+    int j_ucd() const { return j_tin() + nx; }
+    int j_xsd() const { return j_ucd() + nu * nu; }
+    int j_count() const { return j_xsd() + nx * nx; }
 };
+
+
 
 }  // namespace b200sqp

@@ -17,7 +17,7 @@ def _fill(arr, values, default=0.0):
 
 def make_ocp(*, grid, dynamics, n_grid, dt, collocation=abi.COLL_CRANK_NICOLSON, integrator=abi.INT_RK4, stage_cost=abi.COST_QUADRATIC_LSQ,
              q=(), r=(), qf=None, x_lb=None, x_ub=None, u_lb=None, u_ub=None, xf_fixed=None, dt_lb=0.0, dt_ub=abi.CORBO_INF_DBL,
-             dyn_params=(), terminal_equality=None, terminal_ball=None):
+             dyn_params=(), terminal_equality=None, terminal_ball=None, q_full=None, r_full=None, qf_full=None):
     nx, nu = abi.DYN_DIMS[dynamics]
     d = abi.Ocp()
     d.grid, d.dynamics, d.collocation, d.integrator = grid, dynamics, collocation, integrator
@@ -36,6 +36,14 @@ def make_ocp(*, grid, dynamics, n_grid, dt, collocation=abi.COLL_CRANK_NICOLSON,
     _fill(d.x_ub, list(x_ub) if x_ub is not None else [inf] * nx, inf)
     _fill(d.u_lb, list(u_lb) if u_lb is not None else [-inf] * nu, -inf)
     _fill(d.u_ub, list(u_ub) if u_ub is not None else [inf] * nu, inf)
+    # full (non-diagonal) weight matrices: row-major nx x nx / nu x nu (quadratic_cost.cpp:32-76: Cholesky-upper square root)
+    for name, mat, dim in (("q", q_full, nx), ("r", r_full, nu), ("qf", qf_full, nx)):
+        if mat is not None:
+            m = np.asarray(mat, np.float64).reshape(dim, dim)
+            setattr(d, name + "_dense", 1)
+            _fill(getattr(d, name + "_full"), list(m.reshape(-1)))
+            if name == "qf":
+                d.final_cost = 1
     # final-stage constraint: TerminalEqualityConstraint(xref) or TerminalBall(diag S, gamma)
     if terminal_equality is not None:
         d.final_constraint = abi.FINAL_CONSTRAINT_EQUALITY

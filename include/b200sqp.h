@@ -119,6 +119,16 @@ typedef struct b200sqp_ocp {
     double term_xref[B200SQP_MAX_NX];    /* TerminalEqualityConstraint::setXRef (final_state_constraints.h:167-232): rows x_N - term_xref */
     double term_s_diag[B200SQP_MAX_NX];  /* TerminalBall::setWeightS, diagonal S (final_state_constraints.h:38-107) */
     double term_gamma;                   /* TerminalBall::setGamma: one inequality row (x_N - xref)^T S (x_N - xref) - gamma <= 0 */
+    /* Full (non-diagonal) weight matrices, row-major, used instead of q_diag / r_diag / qf_diag when the flag is 1.  Like the reference
+     * (QuadraticFormCost::setWeightQ / setWeightR, quadratic_cost.cpp:32-76; QuadraticFinalStateCost::setWeightQf, final_state_cost.cpp:38-58)
+     * a matrix that is diagonal to 1e-10 falls back to the element-wise square root of its diagonal; otherwise the lsq residual is
+     * U (x - xref) with the UPPER Cholesky factor U, Q = U^T U (Eigen::LLT<MatrixXd, Upper>::matrixU()).  A non-diagonal Q needs a non-zero
+     * state reference: with a zero reference the reference's lsq branch returns the scalar x^T U x into a vector (quadratic_cost.cpp:112),
+     * which is not reproduced (B200SQP_ERR_UNSUPPORTED). */
+    int32_t q_dense, r_dense, qf_dense;
+    double q_full[B200SQP_MAX_NX * B200SQP_MAX_NX];
+    double r_full[B200SQP_MAX_NU * B200SQP_MAX_NU];
+    double qf_full[B200SQP_MAX_NX * B200SQP_MAX_NX];
 } b200sqp_ocp;
 
 /* LevenbergMarquardtSparse parameters (levenberg_marquardt_sparse.h:85-90,112-124); defaults 10 / 2,2,2 / 1,1,1 / 500,500,500 */

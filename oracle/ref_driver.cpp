@@ -280,6 +280,8 @@ bool buildOcp(const b200sqp_ocp& d, const b200sqp_lm_options& o, RefOcp& r)
         Eigen::MatrixXd Q = Eigen::MatrixXd::Zero(d.nx, d.nx), R = Eigen::MatrixXd::Zero(d.nu, d.nu);
         for (int i = 0; i < d.nx; ++i) Q(i, i) = d.q_diag[i];
         for (int i = 0; i < d.nu; ++i) R(i, i) = d.r_diag[i];
+        if (d.q_dense) Q = Eigen::Map<const Eigen::Matrix<double, -1, -1, Eigen::RowMajor>>(d.q_full, d.nx, d.nx);
+        if (d.r_dense) R = Eigen::Map<const Eigen::Matrix<double, -1, -1, Eigen::RowMajor>>(d.r_full, d.nu, d.nu);
         r.ocp->setStageCost(std::make_shared<QuadraticFormCost>(Q, R, false, true));
     }
     else if (d.stage_cost == B200SQP_COST_MINIMUM_TIME_LSQ)
@@ -290,6 +292,7 @@ bool buildOcp(const b200sqp_ocp& d, const b200sqp_lm_options& o, RefOcp& r)
     {
         Eigen::MatrixXd Qf = Eigen::MatrixXd::Zero(d.nx, d.nx);
         for (int i = 0; i < d.nx; ++i) Qf(i, i) = d.qf_diag[i];
+        if (d.qf_dense) Qf = Eigen::Map<const Eigen::Matrix<double, -1, -1, Eigen::RowMajor>>(d.qf_full, d.nx, d.nx);
         r.ocp->setFinalStageCost(std::make_shared<QuadraticFinalStateCost>(Qf, true));
     }
 

@@ -329,6 +329,7 @@ struct BuildInput
     const b200sqp_ocp* d;
     const double* x0;
     const double* xref;  // static reference [nx] (may be null -> zeros), or -- see sqp_oracle_set_xref_points -- a trajectory [N][nx]
+    bool structure_only = false;  // dimensions / indices only: no values will be evaluated
 };
 
 // Time-varying state reference (ReferenceTrajectoryInterface with isStatic() == false, core/reference_trajectory.h:60-95): when set to
@@ -336,6 +337,88 @@ struct BuildInput
 // getReferenceCached(k) returns; 0 or 1 = static reference [nx].  Process-global test switch (this library is test infrastructure).
 static int g_xref_points = 0;
 int xrefStride(const b200sqp_ocp& d) { return g_xref_points > 1 ? d.n_grid * d.nx : d.nx; }
+
+// Weight handling of QuadraticFormCost::setWeightQ / setWeightR (optimal_control/src/functions/quadratic_cost.cpp:32-96) and
+// QuadraticFinalStateCost::setWeightQf (final_state_cost.cpp:38-69): a matrix that is diagonal to 1e-10 (Eigen's isDiagonal: every
+// off-diagonal entry <= 1e-10 * max |diagonal|) takes the element-wise square root of its diagonal; otherwise the square root is the
+// upper Cholesky factor U, M = U^T U, of Eigen::LLT<MatrixXd, Upper> -- restated as the unblocked left-looking algorithm of
+// extern/eigen3/Eigen/src/Cholesky/LLT.h:290-320 (sizes < 32), whose sums are sequential up to three terms.
+struct WeightSqrt
+{
+    bool dense = false;
+    std::vector<double> w;  // diagonal mode: [dim]; dense mode: [dim*dim] row-major upper factor (zeros below the diagonal)
+};
+WeightSqrt weightSqrt(const double* diag, const double* full, int dense_flag, int dim)
+{
+    WeightSqrt r;
+    if (!dense_flag)
+    {
+        r.w.resize(dim);
+        for (int i = 0; i < dim; ++i) r.w[i] = std::sqrt(diag[i]);
+        return r;
+    }
+    double max_diag = 0;
+    for (int i = 0; i < dim; ++i) max_diag = std::max(max_diag, std::abs(full[i * dim + i]));
+    bool is_diag = true, is_zero = true;
+    for (int i = 0; i < dim; ++i)
+        for (int j = 0; j < dim; ++j)
+        {
+            if (i != j && !(std::abs(full[i * dim + j]) <= std::abs(max_diag) * 1e-10)) is_diag = false;
+            if (!(std::abs(full[i * dim + j]) <= 1e-12)) is_zero = false;  // isZero(): |x| <= dummy_precision
+        }
+    if (is_diag)
+    {
+        r.w.resize(dim);
+        for (int i = 0; i < dim; ++i) r.w[i] = std::sqrt(full[i * dim + i]);
+        return r;
+    }
+    r.dense = true;
+    r.w.assign((size_t)dim * dim, 0.0);
+    if (is_zero) return r;
+    // L = U^T, column by column: L_kk = sqrt(A_kk - sum_j L_kj^2), L_ik = (A_ik - sum_j L_ij L_kj) / L_kk  (only the upper triangle of A is read)
+    std::vector<double> L((size_t)dim * dim, 0.0);
+    for (int k = 0; k < dim; ++k)
+    {
+        double x = full[k * dim + k];
+        if (k > 0)
+        {
+            double sq = L[k * dim + 0] * L[k * dim + 0];
+            for (int j = 1; j < k; ++j) sq += L[k * dim + j] * L[k * dim + j];
+            x -= sq;
+        }
+        x              = std::sqrt(x);
+        L[k * dim + k] = x;
+        for (int i = k + 1; i < dim; ++i)
+        {
+            double a = full[k * dim + i];  // A_ik = A_ki: upper triangle
+            if (k > 0)
+            {
+                double dot = L[i * dim + 0] * L[k * dim + 0];
+                for (int j = 1; j < k; ++j) dot += L[i * dim + j] * L[k * dim + j];
+                a -= dot;
+            }
+            L[i * dim + k] = a / x;
+        }
+    }
+    for (int i = 0; i < dim; ++i)
+        for (int j = i; j < dim; ++j) r.w[i * dim + j] = L[j * dim + i];
+    return r;
+}
+// `_Q_sqrt * xd` (Eigen's column-major matrix-vector product: sequential over the columns for fewer than four of them), diagonal or dense
+void applyWeightSqrt(const WeightSqrt& ws, int dim, const double* xd, double* out)
+{
+    if (!ws.dense)
+    {
+        for (int i = 0; i < dim; ++i) out[i] = ws.w[i] * xd[i];
+        return;
+    }
+    for (int i = 0; i < dim; ++i)
+    {
+        double s = ws.w[i * dim + i] * xd[i];
+        for (int j = i + 1; j < dim; ++j) s += ws.w[i * dim + j] * xd[j];
+        out[i] = s;
+    }
+}
 
 // NlpFunctions::getNonIntegralStageFunctionEdges (optimal_control/src/functions/nlp_functions.cpp:70-132) for the supported stage
 // costs: state term, control term, dt term (created TWICE, :91-107), in that order.
@@ -346,30 +429,24 @@ void addStageCostEdges(Graph& g, const b200sqp_ocp& d, int k, Vertex* xk, Vertex
     if (d.stage_cost == B200SQP_COST_QUADRATIC_LSQ)
     {
         // QuadraticFormCost::computeNonIntegralStateTerm, lsq + diagonal branch (optimal_control/src/functions/quadratic_cost.cpp:105-123)
-        std::vector<double> qs(nx), rs(nu);
-        for (int i = 0; i < nx; ++i) qs[i] = std::sqrt(d.q_diag[i]);  // setWeightQ: cwiseSqrt (:62)
-        for (int i = 0; i < nu; ++i) rs[i] = std::sqrt(d.r_diag[i]);
+        const WeightSqrt qs = weightSqrt(d.q_diag, d.q_full, d.q_dense, nx), rs = weightSqrt(d.r_diag, d.r_full, d.r_dense, nu);
         bool zero_ref = !nonstatic_ref;  // a non-static reference is never "zero" here (isZero() is a property of the whole trajectory)
         for (double r : xref) zero_ref = zero_ref && (r == 0.0);  // StaticReference::isZero (core/reference_trajectory.h:123)
+        // (dense Q with a zero reference: the reference writes a scalar into the vector, quadratic_cost.cpp:112 -- refused by buildGraph)
         Edge ex;
-        ex.dim = nx;
-        ex.v   = {xk};
-        if (zero_ref)
-            ex.values = [xk, qs, nx](double* out) {
-                for (int i = 0; i < nx; ++i) out[i] = qs[i] * xk->val[i];
-            };
-        else
-            ex.values = [xk, qs, nx, xref](double* out) {
-                for (int i = 0; i < nx; ++i) out[i] = qs[i] * (xk->val[i] - xref[i]);
-            };
+        ex.dim    = nx;
+        ex.v      = {xk};
+        ex.values = [xk, qs, nx, xref, zero_ref](double* out) {
+            std::vector<double> xd(nx);
+            for (int i = 0; i < nx; ++i) xd[i] = zero_ref ? xk->val[i] : xk->val[i] - xref[i];
+            applyWeightSqrt(qs, nx, xd.data(), out);
+        };
         g.lsq.push_back(ex);
-        // computeNonIntegralControlTerm, lsq + zero uref + diagonal (:146-154)
+        // computeNonIntegralControlTerm, lsq + zero uref (:146-154)
         Edge eu;
         eu.dim    = nu;
         eu.v      = {uk};
-        eu.values = [uk, rs, nu](double* out) {
-            for (int i = 0; i < nu; ++i) out[i] = rs[i] * uk->val[i];
-        };
+        eu.values = [uk, rs, nu](double* out) { applyWeightSqrt(rs, nu, uk->val.data(), out); };
         g.lsq.push_back(eu);
     }
     else if (d.stage_cost == B200SQP_COST_MINIMUM_TIME_LSQ)
@@ -396,21 +473,17 @@ void addFinalCostEdge(Graph& g, const b200sqp_ocp& d, Vertex* xf, const std::vec
 {
     if (d.final_cost != 1) return;
     const int nx = d.nx;
-    std::vector<double> qs(nx);
-    for (int i = 0; i < nx; ++i) qs[i] = std::sqrt(d.qf_diag[i]);
+    const WeightSqrt qs = weightSqrt(d.qf_diag, d.qf_full, d.qf_dense, nx);
     bool zero_ref = true;
     for (double r : xref) zero_ref = zero_ref && (r == 0.0);
     Edge e;
-    e.dim = nx;
-    e.v   = {xf};
-    if (zero_ref)
-        e.values = [xf, qs, nx](double* out) {
-            for (int i = 0; i < nx; ++i) out[i] = qs[i] * xf->val[i];
-        };
-    else
-        e.values = [xf, qs, nx, xref](double* out) {
-            for (int i = 0; i < nx; ++i) out[i] = qs[i] * (xf->val[i] - xref[i]);
-        };
+    e.dim    = nx;
+    e.v      = {xf};
+    e.values = [xf, qs, nx, xref, zero_ref](double* out) {
+        std::vector<double> xd(nx);
+        for (int i = 0; i < nx; ++i) xd[i] = zero_ref ? xf->val[i] : xf->val[i] - xref[i];
+        applyWeightSqrt(qs, nx, xd.data(), out);
+    };
     g.lsq.push_back(e);
 }
 
@@ -512,6 +585,12 @@ std::unique_ptr<Graph> buildGraph(const BuildInput& in)
     if (in.xref)
         for (int k = 0; k < N; ++k)
             for (int i = 0; i < nx; ++i) xref_at[k][i] = in.xref[(traj ? k * nx : 0) + i];
+    if (!in.structure_only && d.stage_cost == B200SQP_COST_QUADRATIC_LSQ && weightSqrt(d.q_diag, d.q_full, d.q_dense, nx).dense && !traj)
+    {
+        bool zero = true;
+        for (double r : xref_at[0]) zero = zero && r == 0.0;
+        if (zero) return nullptr;  // the reference's scalar branch (quadratic_cost.cpp:112)
+    }
     const std::vector<double>& xref    = xref_at[N - 1];
     const std::vector<double>& xf_goal = xref;  // xref.getReferenceCached(n-1)
 
@@ -1145,7 +1224,7 @@ int sqp_oracle_set_xref_points(int n_points)
 int sqp_oracle_dims(const b200sqp_ocp* d, b200sqp_dims* out)
 {
     std::vector<double> x0(d->nx, 0.25);
-    auto g = buildGraph({d, x0.data(), nullptr});
+    auto g = buildGraph({d, x0.data(), nullptr, true});
     if (!g) return -1;
     fillDims(*g, out);
     return 0;
@@ -1154,7 +1233,7 @@ int sqp_oracle_dims(const b200sqp_ocp* d, b200sqp_dims* out)
 int sqp_oracle_vertex_indices(const b200sqp_ocp* d, int32_t* x_idx, int32_t* u_idx, int32_t* dt_idx)
 {
     std::vector<double> x0(d->nx, 0.25);
-    auto g = buildGraph({d, x0.data(), nullptr});
+    auto g = buildGraph({d, x0.data(), nullptr, true});
     if (!g) return -1;
     auto idx = [](Vertex* v) { return v->dimUnfixed() > 0 ? v->idx : -1; };
     for (int k = 0; k < d->n_grid - 1; ++k)
@@ -1170,7 +1249,7 @@ int sqp_oracle_vertex_indices(const b200sqp_ocp* d, int32_t* x_idx, int32_t* u_i
 int sqp_oracle_edge_table(const b200sqp_ocp* d, int category, int32_t* table, int max_edges)
 {
     std::vector<double> x0(d->nx, 0.25);
-    auto g = buildGraph({d, x0.data(), nullptr});
+    auto g = buildGraph({d, x0.data(), nullptr, true});
     if (!g) return -1;
     std::vector<Edge>& list = category == 0 ? g->lsq : (category == 1 ? g->eq : g->ineq);
     int cnt                 = 0;

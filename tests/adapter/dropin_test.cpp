@@ -678,6 +678,60 @@ int main(int argc, char** argv)
             ++failures;
         }
     }
+    // ---- 10. full (non-diagonal) weight matrices: QuadraticFormCost / QuadraticFinalStateCost with the upper Cholesky square root and a
+    //          non-zero static reference (the reference's zero-reference branch for a non-diagonal Q is broken, quadratic_cost.cpp:112)
+    {
+        auto build = [](NlpSolverInterface::Ptr solver, std::shared_ptr<HyperGraphOptimizationProblemEdgeBased>& problem) {
+            auto dynamics = std::make_shared<VanDerPolOscillator>();
+            auto grid     = std::make_shared<FiniteDifferencesGrid>();
+            grid->setNRef(20);
+            grid->setDtRef(0.1);
+            grid->setCostIntegrationRule(FullDiscretizationGridBase::CostIntegrationRule::LeftSum);
+            problem  = std::make_shared<HyperGraphOptimizationProblemEdgeBased>();
+            auto ocp = std::make_shared<StructuredOptimalControlProblem>(grid, dynamics, problem, solver);
+            Eigen::MatrixXd Q(2, 2), Qf(2, 2), R = Eigen::MatrixXd::Constant(1, 1, 0.1);
+            Q << 2.0, 0.3, 0.3, 1.0;
+            Qf << 3.0, -0.4, -0.4, 2.0;
+            auto stage_cost = std::make_shared<QuadraticFormCost>(Q, R, false, true);
+            auto final_cost = std::make_shared<QuadraticFinalStateCost>(Qf, true);
+            ocp->setStageCost(stage_cost);
+            ocp->setFinalStageCost(final_cost);
+            Eigen::VectorXd xlb = Eigen::VectorXd::Constant(2, -CORBO_INF_DBL), xub = Eigen::VectorXd::Constant(2, CORBO_INF_DBL);
+            Eigen::VectorXd ulb = Eigen::VectorXd::Constant(1, -1.0), uub = Eigen::VectorXd::Constant(1, 1.0);
+            ocp->setBounds(xlb, xub, ulb, uub);
+            if (auto b200 = std::dynamic_pointer_cast<SolverB200Lm>(solver))
+            {
+                b200->setSystemDynamics(dynamics);
+                b200->setStageCost(stage_cost);
+                b200->setFinalStageCost(final_cost);
+            }
+            ocp->initialize();
+            return ocp;
+        };
+        auto s_ref = std::make_shared<LevenbergMarquardtSparse>();
+        auto s_dev = std::make_shared<SolverB200Lm>();
+        s_ref->setIterations(8);
+        s_dev->setIterations(8);
+        Eigen::VectorXd goal(2);
+        goal << 0.2, -0.1;
+        auto xr_ref = std::make_shared<StaticReference>(goal), xr_dev = std::make_shared<StaticReference>(goal);
+        s_dev->setStateReference(xr_dev);
+        std::shared_ptr<HyperGraphOptimizationProblemEdgeBased> pr, pd;
+        auto ocp_r = build(s_ref, pr), ocp_d = build(s_dev, pd);
+        ZeroReference uref1(1);
+        Eigen::VectorXd x0(2);
+        x0 << 1.1, -0.6;
+        const bool ok_r = ocp_r->compute(x0, *xr_ref, uref1, nullptr, Time(0), true);
+        const bool ok_d = ocp_d->compute(x0, *xr_dev, uref1, nullptr, Time(0), true);
+        const double diff = relDiff(paramsOf(*pr), paramsOf(*pd));
+        std::printf("full weight matrices Q, Qf (upper Cholesky square roots): max relative trajectory difference vs reference = %.3e "
+                    "(objective %.9g vs %.9g)\n", diff, ocp_r->getCurrentObjectiveValue(), ocp_d->getCurrentObjectiveValue());
+        if (!ok_r || !ok_d || !(diff <= 1e-5))
+        {
+            std::printf("FAIL: full weight matrices through the plugin (ok_ref=%d ok_b200=%d, %s)\n", (int)ok_r, (int)ok_d, s_dev->lastError().c_str());
+            ++failures;
+        }
+    }
     std::printf(failures ? "DROP-IN TEST FAILED\n" : "DROP-IN TEST PASSED\n");
     return failures ? 1 : 0;
 }

@@ -573,3 +573,54 @@ def test_time_varying_reference_matches_the_checkers(oracle, make):
         ms.set_reference_trajectory(np.zeros((4, 10, 2)))
     assert info.value.code == abi.ERR_UNSUPPORTED
     ms.clear()
+
+
+def test_full_weight_matrices_match_the_checkers(oracle):
+    """Non-diagonal Q / R / Qf (upper Cholesky square roots, dense Jacobian blocks of the cost edges): values, Jacobian and drift
+    bit-identical to the checker for up to three states, solves within the bars of the polynomial models; a combination without a
+    compiled dense-cost kernel is refused."""
+    import sys as _sys
+    _sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+    from test_oracle_vs_reference import DENSE_CASES
+    from oracle import bindings
+
+    chk = bindings.Reference() if bindings.Reference.available() else oracle
+    for name, (make, xr, exact) in DENSE_CASES.items():
+        ocp = make()
+        B = 24
+        x0, _ = problems.instance_data(ocp, B, seed=2)
+        xref = np.tile(np.array(xr, dtype=float), (B, 1))
+        rng = np.random.default_rng(1)
+        lm = solver.BatchedLevenbergMarquardt(ocp, B)
+        lm.set_problem_data(x0, xref)
+        lm.initialize_trajectories()
+        p = lm.get_params() + rng.uniform(-0.2, 0.2, (B, lm.dims.n_params))
+        lm.set_params(p)
+        w = (2.0, 3.0, 4.0)
+        values, jac = lm.evaluate(w)
+        after = lm.get_params()
+        for i in range(3):
+            v_c, J_c, _, a_c = chk.evaluate(ocp, x0[i], xref[i], p[i], w)
+            J = _csc_to_dense(ocp, jac[i])
+            if exact:
+                assert np.array_equal(values[i], v_c), (name, np.abs(values[i] - v_c).max())
+                assert np.array_equal(J, J_c), (name, np.abs(J - J_c).max())
+                assert np.array_equal(after[i], a_c), name
+            else:
+                np.testing.assert_allclose(values[i], v_c, rtol=1e-13, atol=1e-13)
+                np.testing.assert_allclose(J, J_c, rtol=0, atol=2e-6 * max(1.0, np.abs(J_c).max()))
+        opts = abi.LmOptions.defaults(iterations=8)
+        p_c, c_c, _, _ = chk.solve_batch(ocp, opts, x0, xref, threads=4)
+        for T in (1, 4):
+            lm.setIterations(8)
+            lm.set_threads_per_instance(T)
+            lm.initialize_trajectories()
+            _, chi2 = lm.solve(new_run=True)
+            err = _traj_err(lm.get_params(), p_c)
+            assert err.max() <= (1e-5 if exact else 1e-3), (name, T, err.max())
+            np.testing.assert_allclose(chi2, c_c, rtol=1e-6)
+        lm.clear()
+    Q4 = np.eye(4) + 0.1 * np.ones((4, 4))
+    with pytest.raises(solver.B200SqpError) as info:
+        solver.BatchedLevenbergMarquardt(problems.cart_pole_shooting(10, q_full=Q4), 4)
+    assert info.value.code == abi.ERR_UNSUPPORTED

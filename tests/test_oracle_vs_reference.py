@@ -165,3 +165,52 @@ def test_time_varying_reference_oracle_matches_compiled_reference(oracle, refere
     finally:
         for chk in (oracle, reference):
             chk.set_xref_points(0)
+
+
+def _dense_weight_cases():
+    Q2 = np.array([[2.0, 0.3], [0.3, 1.0]])
+    Qf2 = np.array([[3.0, -0.4], [-0.4, 2.0]])
+    Q3 = np.array([[2.0, 0.3, -0.2], [0.3, 1.0, 0.1], [-0.2, 0.1, 1.5]])
+    R2 = np.array([[0.5, 0.1], [0.1, 0.3]])
+    return {
+        "vdp10_full_q_qf": (lambda: problems.van_der_pol(10, q_full=Q2, qf_full=Qf2), (0.2, -0.1), True),
+        "vdp9_ms_full_q": (lambda: problems.van_der_pol_shooting(9, q_full=Q2), (0.1, 0.3), True),
+        "rocket8_full_q3": (lambda: problems.make_ocp(grid=abi.GRID_FD_UNIFORM, dynamics=abi.DYN_FREE_SPACE_ROCKET, n_grid=8, dt=0.1, q=(1, 1, 1), r=(0.1,),
+                                                      qf=(1, 1, 1), u_lb=(-1.1,), u_ub=(1.1,), q_full=Q3, qf_full=2.0 * Q3), (0.1, 0.2, 0.8), True),
+        "unicycle8_full_q3_r2": (lambda: problems.make_ocp(grid=abi.GRID_FD_UNIFORM, dynamics=abi.DYN_UNICYCLE, n_grid=8, dt=0.1, q=(1, 1, 1), r=(0.1, 0.1),
+                                                           qf=(1, 1, 1), u_lb=(-1, -1), u_ub=(1, 1), q_full=Q3, r_full=R2), (0.1, 0.2, 0.3), False),
+        "vdp10_full_but_diagonal": (lambda: problems.van_der_pol(10, q_full=np.diag([2.0, 0.5]), qf_full=np.diag([1.5, 1.0])), (0.2, -0.1), True),
+    }
+
+
+DENSE_CASES = _dense_weight_cases()
+
+
+@pytest.mark.parametrize("name", list(DENSE_CASES))
+def test_full_weight_matrices_oracle_matches_compiled_reference(oracle, reference, name):
+    """Non-diagonal Q / R / Qf: QuadraticFormCost / QuadraticFinalStateCost take the upper Cholesky factor as square root
+    (quadratic_cost.cpp:32-96, final_state_cost.cpp:38-58) and the cost edges get dense Jacobian blocks.  Values, Jacobian (pattern and
+    entries) and drift bit-identical for up to three states (Eigen's sums are sequential there); a matrix handed over in full but
+    diagonal takes the reference's diagonal branch."""
+    make, xr, exact = DENSE_CASES[name]
+    ocp = make()
+    B = 5
+    x0, _ = problems.instance_data(ocp, B, seed=2)
+    xref = np.tile(np.array(xr, dtype=float), (B, 1))
+    rng = np.random.default_rng(1)
+    p_r = reference.initial_params(ocp, x0[0], xref[0])
+    p = p_r + rng.uniform(-0.2, 0.2, p_r.shape)
+    v_r, J_r, P_r, a_r = reference.evaluate(ocp, x0[0], xref[0], p, (2.0, 3.0, 4.0))
+    v_o, J_o, P_o, a_o = oracle.evaluate(ocp, x0[0], xref[0], p, (2.0, 3.0, 4.0))
+    assert np.array_equal(P_r, P_o)
+    if exact:
+        assert np.array_equal(v_r, v_o) and np.array_equal(J_r, J_o) and np.array_equal(a_r, a_o)
+    else:
+        np.testing.assert_allclose(v_o, v_r, rtol=1e-13, atol=1e-13)
+        np.testing.assert_allclose(J_o, J_r, rtol=0, atol=2e-6 * max(1.0, np.abs(J_r).max()))
+    opts = abi.LmOptions.defaults(iterations=6)
+    pr, cr, sr, _ = reference.solve_batch(ocp, opts, x0, xref, threads=2)
+    po, co, so, _ = oracle.solve_batch(ocp, opts, x0, xref, threads=2)
+    err = np.abs(po - pr).max(axis=1) / np.maximum(1.0, np.abs(pr).max(axis=1))
+    assert err.max() <= (1e-5 if exact else 1e-3), err
+    np.testing.assert_allclose(co, cr, rtol=1e-6)

@@ -117,3 +117,28 @@ def test_survey_numbers():
     assert (dc.n_params, dc.m_lsq, dc.m_eq, dc.m_bounds) == (495, 499, 396, 99)
     du = solver.dims_of(problems.unicycle_time_optimal(30))
     assert du.m_lsq == 58  # the dt-cost edge is created twice per interval (nlp_functions.cpp:91-107)
+
+
+def test_full_weight_matrices_structure_and_refusals(oracle):
+    """Full (non-diagonal) Q / R / Qf in the descriptor: same dimensions and Jacobian pattern as with diagonal weights (the cost edges'
+    blocks are dense in the pattern either way); the reference's broken branch (non-diagonal Q with a zero state reference,
+    quadratic_cost.cpp:112) and matrices that are not positive definite are refused."""
+    import numpy as np
+    from control_box_rst_b200 import _abi as abi, problems, solver
+
+    Q = np.array([[2.0, 0.3], [0.3, 1.0]])
+    dense, diag = problems.van_der_pol(12, q_full=Q, qf_full=2.0 * Q), problems.van_der_pol(12)
+    d1, d2 = solver.dims_of(dense), solver.dims_of(diag)
+    for f in ("n_params", "m_lsq", "m_eq", "m_ineq", "m_bounds", "nnz_jacobian", "nnz_hessian_upper"):
+        assert getattr(d1, f) == getattr(d2, f) == getattr(oracle.dims(dense), f), f
+    for a, b in zip(solver.jacobian_pattern(dense), solver.jacobian_pattern(diag)):
+        assert np.array_equal(a, b)
+    zero_ref = problems.van_der_pol(12, q_full=Q)
+    zero_ref.zero_x_ref = 1
+    with pytest.raises(solver.B200SqpError) as info:
+        solver.dims_of(zero_ref)
+    assert info.value.code == abi.ERR_UNSUPPORTED
+    with pytest.raises(solver.B200SqpError) as info:
+        solver.dims_of(problems.van_der_pol(12, q_full=np.array([[1.0, 2.0], [2.0, 1.0]])))
+    assert info.value.code == abi.ERR_INVALID
+    solver.dims_of(problems.van_der_pol(12, q_full=np.diag([2.0, 0.5])))  # full but diagonal: the diagonal branch, zero reference allowed
