@@ -124,6 +124,7 @@ class Ocp(C.Structure):
         ("q_full", C.c_double * (MAX_NX * MAX_NX)),
         ("r_full", C.c_double * (MAX_NU * MAX_NU)),
         ("qf_full", C.c_double * (MAX_NX * MAX_NX)),
+        ("dt_eq_constraint", C.c_int32),
     ]
 
 

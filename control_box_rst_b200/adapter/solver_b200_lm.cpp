@@ -8,6 +8,7 @@
 #include <corbo-optimal-control/functions/minimum_time.h>
 #include <corbo-optimal-control/functions/quadratic_cost.h>
 #include <corbo-optimal-control/structured_ocp/edges/finite_differences_collocation_edges.h>
+#include <corbo-optimal-control/structured_ocp/edges/misc_edges.h>
 #include <corbo-optimal-control/structured_ocp/edges/multiple_shooting_edges.h>
 #include <corbo-optimization/hyper_graph/hyper_graph_optimization_problem_base.h>
 #include <corbo-systems/benchmark/linear_benchmark_systems.h>
@@ -164,12 +165,40 @@ bool SolverB200Lm::describe(OptimizationProblemInterface& problem, b200sqp_ocp& 
         }
         has_term_ball = true;
     }
+    // TwoScalarEqualEdges (NonUniformFiniteDifferencesVariableGrid::setDtEqConstraint, non_uniform_finite_differences_variable_grid.cpp:150-154)
+    // sit between the dynamics edges, one after the dynamics edge of every interval k >= 1: split them off, the descriptor carries a flag
+    int n_dt_eq = 0;
+    {
+        std::vector<BaseEdge::Ptr> dyn_edges;
+        for (size_t i = 0; i < eq.size(); ++i)
+        {
+            if (dynamic_cast<TwoScalarEqualEdge*>(eq[i].get()))
+            {
+                // expected position: right after the dynamics edge of interval k = number of dynamics edges so far - 1 >= 1
+                if (dyn_edges.size() < 2 || (int)dyn_edges.size() - 1 != n_dt_eq + 1)
+                {
+                    _error = "TwoScalarEqualEdge at an unexpected position";
+                    return false;
+                }
+                ++n_dt_eq;
+            }
+            else
+                dyn_edges.push_back(eq[i]);
+        }
+        eq.swap(dyn_edges);
+    }
     if (eq.empty() || !_dynamics)
     {
         _error = "no dynamics edges, or setSystemDynamics() was not called";
         return false;
     }
+    if (n_dt_eq != 0 && n_dt_eq != (int)eq.size() - 1)
+    {
+        _error = "dt equality edges are expected between all consecutive intervals or none";
+        return false;
+    }
     std::memset(&d, 0, sizeof(d));
+    d.dt_eq_constraint = n_dt_eq > 0 ? 1 : 0;
     const int K = (int)eq.size();
     d.n_grid    = K + 1;
     d.nx        = _dynamics->getStateDimension();
@@ -516,9 +545,12 @@ bool SolverB200Lm::instanceData(OptimizationProblemInterface& problem, double* x
     OptimizationEdgeSet* edges        = hg->getGraph().getEdgeSetRaw();
     std::vector<BaseEdge::Ptr>& eq    = edges->getEqualityEdgesRef();
     const int K                       = _ocp.n_grid - 1;
-    const int n_eq                    = K + (_ocp.final_constraint == B200SQP_FINAL_CONSTRAINT_EQUALITY ? 1 : 0);
+    const int n_dt_eq                 = (_ocp.dt_eq_constraint && K > 1) ? K - 1 : 0;
+    const int n_eq                    = K + n_dt_eq + (_ocp.final_constraint == B200SQP_FINAL_CONSTRAINT_EQUALITY ? 1 : 0);
+    // the last dynamics edge: dynamics edges and (from interval 1 on) dt equality edges alternate
+    const int last_dyn                = n_dt_eq ? 2 * K - 3 : K - 1;
     if ((int)eq.size() != n_eq || !edges->getMixedEdgesRef().empty() || !edges->getObjectiveEdgesRef().empty() ||
-        eq.front()->getNumVertices() != 4 || eq[K - 1]->getNumVertices() != 4)
+        eq.front()->getNumVertices() != 4 || eq[last_dyn]->getNumVertices() != 4)
     {
         error = "edge lists differ from the first problem of the batch";
         return false;
@@ -526,7 +558,7 @@ bool SolverB200Lm::instanceData(OptimizationProblemInterface& problem, double* x
     const VertexInterface* x_first = eq.front()->getVertexRaw(0);
     const VertexInterface* u_first = eq.front()->getVertexRaw(1);
     const VertexInterface* dt0     = eq.front()->getVertexRaw(3);
-    const VertexInterface* x_last  = eq[K - 1]->getVertexRaw(2);
+    const VertexInterface* x_last  = eq[last_dyn]->getVertexRaw(2);
     bool same = x_first->isFixed() && x_first->getDimension() == _ocp.nx && u_first->getDimension() == _ocp.nu;
     for (int i = 0; same && i < _ocp.nx; ++i)
         same = x_last->getLowerBounds()[i] == _ocp.x_lb[i] && x_last->getUpperBounds()[i] == _ocp.x_ub[i] &&

@@ -48,7 +48,7 @@ const KernelSet* findKernels(int dynamics, int defect, int vt)
     const KernelSet* (*tables[])(int*) = {kernelTableVdpCn,       kernelTableVdpFd,    kernelTableVdpMs,   kernelTableOscillators,
                                           kernelTableCartPole,    kernelTableUnicycle, kernelTableQuadrotor, kernelTableBenchmarkSystems,
                                           kernelTableCombosFd,    kernelTableCombosMs, kernelTableLinear,   kernelTableLinear4,
-                                          kernelTableIntegrators};
+                                          kernelTableIntegrators, kernelTableDtEquality};
 #endif
     for (auto t : tables)
     {
@@ -314,6 +314,17 @@ int b200sqp_edge_indices(const b200sqp_ocp* ocp, int32_t* state_cost_idx, int32_
     return B200SQP_OK;
 }
 
+int b200sqp_dt_equality_indices(const b200sqp_ocp* ocp, int32_t* dt_eq_idx)
+{
+    if (!ocp || !dt_eq_idx) return fail(B200SQP_ERR_INVALID, "null argument");
+    Structure s;
+    std::string err;
+    int rc = buildStructure(*ocp, s, err);
+    if (rc != B200SQP_OK) return fail(rc, err);
+    std::memcpy(dt_eq_idx, s.dt_eq_idx.data(), sizeof(int32_t) * s.dt_eq_idx.size());
+    return B200SQP_OK;
+}
+
 int b200sqp_final_constraint_indices(const b200sqp_ocp* ocp, int32_t* eq_idx, int32_t* ineq_idx)
 {
     if (!ocp) return fail(B200SQP_ERR_INVALID, "null argument");
@@ -346,7 +357,9 @@ int b200sqp_create(const b200sqp_ocp* ocp, int32_t batch, int32_t device, b200sq
     std::string err;
     int rc = buildStructure(*ocp, s, err);
     if (rc != B200SQP_OK) return fail(rc, err);
-    const KernelSet* ks = s.denseCost() ? findDenseCostKernels(ocp->dynamics, s.defect, s.vt) : findKernels(ocp->dynamics, s.defect, s.vt);
+    // kernel key: 0 fixed dt, 1 one free dt per interval, 2 the same with equality edges between consecutive dt vertices
+    const int vt_key    = s.vt + s.dteq;
+    const KernelSet* ks = s.denseCost() ? findDenseCostKernels(ocp->dynamics, s.defect, vt_key) : findKernels(ocp->dynamics, s.defect, vt_key);
     if (!ks)
         return fail(B200SQP_ERR_UNSUPPORTED, s.denseCost() ? "full (non-diagonal) cost weights are not compiled for this (dynamics, defect, grid) combination "
                                                               "(kernels_dense_cost.cu); no CPU fallback"
@@ -376,7 +389,7 @@ int b200sqp_create(const b200sqp_ocp* ocp, int32_t batch, int32_t device, b200sq
     fillDeviceOcp(s, h->B, h->S, h->P);
 
     const size_t S = h->S, K = s.K, nb = s.nb, nx = s.nx;
-    const size_t nd = nb * (nb + 1) / 2, ne = nb * nx, n = s.dims.n_params;
+    const size_t nd = nb * (nb + 1) / 2, ne = nb * (nx + s.dteq), n = s.dims.n_params;  // sub-diagonal blocks: nb x coupling slots
     DeviceState& st = h->st;
     auto A = [&](auto** p, size_t cnt) {
         if (e == cudaSuccess) e = h->alloc(p, cnt);

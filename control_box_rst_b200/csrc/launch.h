@@ -42,6 +42,7 @@ const KernelSet* kernelTableCombosMs(int* count);
 const KernelSet* kernelTableLinear(int* count);
 const KernelSet* kernelTableLinear4(int* count);
 const KernelSet* kernelTableIntegrators(int* count);
+const KernelSet* kernelTableDtEquality(int* count);
 // structures with full (non-diagonal) cost weights: their own (smaller) registry; nullptr = combination not compiled in
 const KernelSet* kernelTableDenseCost(int* count);
 const KernelSet* findDenseCostKernels(int dynamics, int defect, int vt);

@@ -48,11 +48,12 @@ __global__ void __launch_bounds__(32 * T) lmSolveKernel(const __grid_constant__ 
     const int S      = P.S;
 
     using BS = BlockSolver<M, VT>;
-    constexpr int NXX = Dm::NXX;
+    // coupling slots of a block (lm_device.cuh Dim): the state, plus the dt slot when consecutive dt vertices are coupled (VT == 2)
+    constexpr int NC = Dm::NC, NCC = Dm::NCC;
     constexpr bool TWISTED = T >= 2;  // two threads of an instance eliminate from both ends of the horizon
     __shared__ double s_red[3][T][32];
     __shared__ double s_muacc[32], s_mu[32];
-    __shared__ double s_xc[TWISTED ? NXX + 2 * NX : 1][32];  // chain B -> A: Schur contribution; chain A -> B: x-part of delta_m
+    __shared__ double s_xc[TWISTED ? NCC + 2 * NC : 1][32];  // chain B -> A: Schur contribution; chain A -> B: coupling part of delta_m
     __shared__ double s_dn[2][T][32];                        // partial ||delta||^2 and delta^T(mu delta + g) per cooperating thread
     __shared__ int s_cur[32], s_flags[32];
     enum { F_ACTIVE = 1, F_LIN = 2 };
@@ -118,15 +119,18 @@ __global__ void __launch_bounds__(32 * T) lmSolveKernel(const __grid_constant__ 
         const bool do_lin = valid && (s_flags[g] & F_LIN);
         double* z         = st.z[s_cur[g]] + zoff;
         double xn_last[NX];
+        double t_prev = 0.0, t_last = 0.0;  // VT == 2: dt_{ka-1} and dt_{kb-1} before this linearisation (each is rewritten by a neighbouring chunk)
         if (do_lin && kb < K)
         {
             const double* zp = z + (size_t)(kb - 1) * NB * TILE;
 #pragma unroll
             for (int j = 0; j < NX; ++j) xn_last[j] = zp[(size_t)(XO + j) * TILE];
+            if (Dm::DTEQ) t_last = zp[(size_t)Dm::NU * TILE];
         }
+        if (Dm::DTEQ && do_lin && ka > 0) t_prev = z[(size_t)((ka - 1) * NB + Dm::NU) * TILE];
         if (T > 1) __syncthreads();  // boundary states are read before any neighbour writes its perturbed copy back
         NormalEquationSink<M, VT, F> sink(P, D, E, gg, ka, kb);
-        if (do_lin) linearizeSweep<M, DEFECT, VT, F>(P, w, z, x0p, xrefp, xtrajp, ka, kb, xn_last, sink, F::dense ? st.cost_sqrt_full : nullptr);
+        if (do_lin) linearizeSweep<M, DEFECT, VT, F>(P, w, z, x0p, xrefp, xtrajp, ka, kb, xn_last, sink, F::dense ? st.cost_sqrt_full : nullptr, t_prev, t_last);
         if (T > 1)
         {
             __syncthreads();  // all blocks stored; now the chunk-start contributions can be added to the neighbour's last block
@@ -211,38 +215,38 @@ __global__ void __launch_bounds__(32 * T) lmSolveKernel(const __grid_constant__ 
                                     double mu_add) {
                 constexpr bool ACC = decltype(acc_tag)::value;
                 const int mid      = Kb / 2;
-                double Lp[ND], yp[NX], carry[NX], dx[NX];
+                double Lp[ND], yp[NC], carry[NC], dx[NC];
                 if (p == 0 && inst_active) BS::chainAEliminate(P, Dq, Eq, gq, Lq, Wq, dlq, mu_add, 0, mid, Lp, yp, nullptr, nullptr);
                 if (p == 1 && inst_active)
                 {
-                    double cxx[NXX], cgx[NX];
+                    double cxx[NCC], cgx[NC];
                     BS::chainBEliminate(P, Dq, Eq, gq, Lq, Wq, dlq, mu_add, mid + 1, Kb, cxx, cgx);
 #pragma unroll
-                    for (int q = 0; q < NXX; ++q) s_xc[q][g] = cxx[q];
+                    for (int q = 0; q < NCC; ++q) s_xc[q][g] = cxx[q];
 #pragma unroll
-                    for (int q = 0; q < NX; ++q) s_xc[NXX + q][g] = cgx[q];
+                    for (int q = 0; q < NC; ++q) s_xc[NCC + q][g] = cgx[q];
                 }
                 __syncthreads();
                 if (p == 0 && inst_active)
                 {
-                    double cxx[NXX], cgx[NX];
+                    double cxx[NCC], cgx[NC];
 #pragma unroll
-                    for (int q = 0; q < NXX; ++q) cxx[q] = s_xc[q][g];
+                    for (int q = 0; q < NCC; ++q) cxx[q] = s_xc[q][g];
 #pragma unroll
-                    for (int q = 0; q < NX; ++q) cgx[q] = s_xc[NXX + q][g];
+                    for (int q = 0; q < NC; ++q) cgx[q] = s_xc[NCC + q][g];
                     BS::chainAEliminate(P, Dq, Eq, gq, Lq, Wq, dlq, mu_add, mid, mid + 1, Lp, yp, cxx, cgx);
 #pragma unroll
-                    for (int q = 0; q < NX; ++q) carry[q] = 0.0;
+                    for (int q = 0; q < NC; ++q) carry[q] = 0.0;
                     BS::template chainABacksub<ACC>(P, gq, Lq, Wq, dlq, mucur, mid, mid, carry, dx, pdn2, pdq);
 #pragma unroll
-                    for (int q = 0; q < NX; ++q) s_xc[NXX + NX + q][g] = dx[q];
+                    for (int q = 0; q < NC; ++q) s_xc[NCC + NC + q][g] = dx[q];
                 }
                 __syncthreads();
                 if (p == 0 && inst_active) BS::template chainABacksub<ACC>(P, gq, Lq, Wq, dlq, mucur, mid - 1, 0, carry, nullptr, pdn2, pdq);
                 if (p == 1 && inst_active)
                 {
 #pragma unroll
-                    for (int q = 0; q < NX; ++q) dx[q] = s_xc[NXX + NX + q][g];
+                    for (int q = 0; q < NC; ++q) dx[q] = s_xc[NCC + NC + q][g];
                     BS::template chainBSubst<ACC>(P, gq, Lq, Wq, dlq, mucur, mid + 1, Kb, dx, pdn2, pdq);
                 }
             };
@@ -251,7 +255,7 @@ __global__ void __launch_bounds__(32 * T) lmSolveKernel(const __grid_constant__ 
                 if (use_part)
                 {
                     const bool has_up = p > 0, has_low = p < T - 1;
-                    double cxx[NXX], cgx[NX];
+                    double cxx[NCC], cgx[NC];
                     if (inst_active) BS::partEliminate(D, E, gg, L, W, Yf, dl, Dr, Er, gr, mua, ka, kb, has_up, has_low, p, cxx, cgx);
                     __syncthreads();
                     if (inst_active && has_up) BS::partAddToUpper(Dr, gr, p - 1, cxx, cgx);
@@ -265,10 +269,10 @@ __global__ void __launch_bounds__(32 * T) lmSolveKernel(const __grid_constant__ 
             }
             else if (p == 0 && inst_active)
             {
-                double Lp[ND], yp[NX], carry[NX];
+                double Lp[ND], yp[NC], carry[NC];
                 BS::chainAEliminate(P, D, E, gg, L, W, dl, mua, 0, K, Lp, yp, nullptr, nullptr);
 #pragma unroll
-                for (int q = 0; q < NX; ++q) carry[q] = 0.0;
+                for (int q = 0; q < NC; ++q) carry[q] = 0.0;
                 BS::chainABacksub(P, gg, L, W, dl, mucur, K - 1, 0, carry, nullptr, pdn2, pdq);
             }
             s_dn[0][p][g] = pdn2;
@@ -333,6 +337,10 @@ __global__ void __launch_bounds__(32 * T) lmSolveKernel(const __grid_constant__ 
                         ++n_reject;  // restoreBackupParameters: the current buffer was never touched
                         mu = mu * v;
                         v  = 2 * v;
+                        // `v` is an unsigned int in the reference (:108): after 31 consecutive rejections it wraps to 0, mu becomes 0 and
+                        // -- if the trial point keeps failing (e.g. non-finite residuals) -- LevenbergMarquardtSparse::solve never returns.
+                        // A batched kernel must: the iteration is ended instead.
+                        if (v == 0) stop = true;
                     }
                 }
                 if (!(rho <= 0 && !stop))

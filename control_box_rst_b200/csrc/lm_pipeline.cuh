@@ -887,6 +887,7 @@ __global__ void __launch_bounds__(128) pipeControlKernel(const __grid_constant__
         rho = -1.0;
         mu  = mu * v;
         v   = 2 * v;
+        if (v == 0) stop = true;
     }
     else if (sqrt(pa.dn2[i]) <= eps2)
         stop = true;
@@ -918,6 +919,7 @@ __global__ void __launch_bounds__(128) pipeControlKernel(const __grid_constant__
             st.n_reject[i] += 1;
             mu = mu * v;
             v  = 2 * v;
+            if (v == 0) stop = true;  // see lm_kernels.cuh: the reference's unsigned `v` wraps and its loop would never end
         }
     }
     bool active = true;

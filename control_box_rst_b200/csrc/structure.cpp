@@ -245,6 +245,12 @@ int buildStructure(const b200sqp_ocp& ocp, Structure& s, std::string& err)
     s.vt = ocp.grid == B200SQP_GRID_FD_NONUNIFORM_VARDT ? 1 : 0;
     s.nb = nu + s.vt + nx;
     const bool single_dt = !s.vt;  // hasSingleDt()
+    if (ocp.dt_eq_constraint && !s.vt)
+    {
+        err = "dt_eq_constraint belongs to the NonUniformFiniteDifferencesVariableGrid";
+        return B200SQP_ERR_INVALID;
+    }
+    s.dteq = (ocp.dt_eq_constraint && K > 1) ? 1 : 0;
 
     // ---- vertex indices ---------------------------------------------------------------------------------------------------
     s.x_idx.assign(N, -1);
@@ -300,6 +306,7 @@ int buildStructure(const b200sqp_ocp& ocp, Structure& s, std::string& err)
     s.control_cost_idx.assign(K, -1);
     s.dt_cost_idx.assign(2 * (size_t)K, -1);
     s.dynamics_idx.assign(K, -1);
+    s.dt_eq_idx.assign(K, -1);
     int lsq = 0, eq = 0;
     for (int k = 0; k < K; ++k)
     {
@@ -317,6 +324,7 @@ int buildStructure(const b200sqp_ocp& ocp, Structure& s, std::string& err)
         }
         s.dynamics_idx[k] = eq;
         eq += nx;
+        if (s.dteq && k > 0) s.dt_eq_idx[k] = eq++;  // TwoScalarEqualEdge(dt_{k-1}, dt_k), non_uniform_finite_differences_variable_grid.cpp:150-154
     }
     if (xf_free > 0 && ocp.final_cost == 1)
     {
@@ -376,6 +384,11 @@ int buildStructure(const b200sqp_ocp& ocp, Structure& s, std::string& err)
         block(row0, nx, s.u_idx[k], nu);
         block(row0, nx, s.x_idx[k + 1], k + 1 < K ? nx : xf_free);
         block(row0, nx, s.dt_idx[k], 1);
+        if (s.dt_eq_idx[k] >= 0)
+        {
+            block(eq_start + s.dt_eq_idx[k], 1, s.dt_idx[k - 1], 1);
+            block(eq_start + s.dt_eq_idx[k], 1, s.dt_idx[k], 1);
+        }
     }
     if (s.final_cost_idx >= 0) block(s.final_cost_idx, nx, s.x_idx[K], xf_free);
     if (s.final_eq_idx >= 0) block(eq_start + s.final_eq_idx, nx, s.x_idx[K], xf_free);
@@ -499,6 +512,12 @@ int buildStructure(const b200sqp_ocp& ocp, Structure& s, std::string& err)
         for (int c = 0; c < nu; ++c)
             for (int r = 0; r < nx; ++r) jp[L.j_Bu() + c * nx + r] = at(ucol[c], erow + r);
         for (int r = 0; r < nx; ++r) jp[L.j_Bt() + r] = at(tcol, erow + r);
+        if (s.dt_eq_idx[k] >= 0)
+        {
+            vr[L.v_dq()]     = eq_start + s.dt_eq_idx[k];
+            jp[L.j_dq()]     = at(s.dt_idx[k - 1], eq_start + s.dt_eq_idx[k]);
+            jp[L.j_dq() + 1] = at(tcol, eq_start + s.dt_eq_idx[k]);
+        }
         if (k == K - 1)
         {
             if (s.final_eq_idx >= 0)

@@ -51,6 +51,8 @@ struct Structure
     std::vector<int32_t> state_cost_idx, control_cost_idx;     // [K] lsq row offsets, -1 = absent
     std::vector<int32_t> dt_cost_idx;                          // [2K]
     std::vector<int32_t> dynamics_idx;                         // [K] equality row offsets
+    std::vector<int32_t> dt_eq_idx;                            // [K] equality row offset of TwoScalarEqualEdge(dt_{k-1}, dt_k), -1 if none
+    int dteq = 0;                                              // 1: consecutive dt vertices are coupled by equality edges
     int32_t final_cost_idx = -1;
     int32_t final_eq_idx = -1, final_ineq_idx = -1;            // final-stage constraint edge: row offset inside its category
     std::vector<int32_t> bound_row;                            // [n] row offset inside the bounds block or -1
@@ -99,7 +101,8 @@ struct EvalLayout
     int v_xb() const { return 3 * nx + 2 * nu + 3; }
     int v_teq() const { return 4 * nx + 2 * nu + 3; }  // final-stage equality rows (last interval only)
     int v_tin() const { return 5 * nx + 2 * nu + 3; }  // final-stage inequality row
-    int v_count() const { return 5 * nx + 2 * nu + 4; }
+    int v_dq() const { return 5 * nx + 2 * nu + 4; }   // TwoScalarEqualEdge(dt_{k-1}, dt_k) row
+    int v_count() const { return 5 * nx + 2 * nu + 5; }
     // Jacobian positions per interval: [uc diag nu | tc 2 | xs diag nx | A nx*nx (col-major) | Bu nx*nu | Bt nx | C nx*nx |
     //                                   bounds u nu | bound dt 1 | bounds x_{k+1} nx | final-stage equality nx*nx | final-stage inequality nx]
     int j_uc() const { return 0; }
@@ -118,7 +121,9 @@ struct EvalLayout
     // (col-major: [column c][row i]); the diagonal slots above stay unused then
     int j_ucd() const { return j_tin() + nx; }
     int j_xsd() const { return j_ucd() + nu * nu; }
-    int j_count() const { return j_xsd() + nx * nx; }
+    // TwoScalarEqualEdge(dt_{k-1}, dt_k), stored with interval k: d/d dt_{k-1}, d/d dt_k
+    int j_dq() const { return j_xsd() + nx * nx; }
+    int j_count() const { return j_dq() + 2; }
 };
 
 

@@ -17,7 +17,7 @@ def _fill(arr, values, default=0.0):
 
 def make_ocp(*, grid, dynamics, n_grid, dt, collocation=abi.COLL_CRANK_NICOLSON, integrator=abi.INT_RK4, stage_cost=abi.COST_QUADRATIC_LSQ,
              q=(), r=(), qf=None, x_lb=None, x_ub=None, u_lb=None, u_ub=None, xf_fixed=None, dt_lb=0.0, dt_ub=abi.CORBO_INF_DBL,
-             dyn_params=(), terminal_equality=None, terminal_ball=None, q_full=None, r_full=None, qf_full=None):
+             dyn_params=(), terminal_equality=None, terminal_ball=None, q_full=None, r_full=None, qf_full=None, dt_eq_constraint=False):
     nx, nu = abi.DYN_DIMS[dynamics]
     d = abi.Ocp()
     d.grid, d.dynamics, d.collocation, d.integrator = grid, dynamics, collocation, integrator
@@ -27,6 +27,7 @@ def make_ocp(*, grid, dynamics, n_grid, dt, collocation=abi.COLL_CRANK_NICOLSON,
     d.zero_x_ref, d.zero_u_ref = 0, 1
     _fill(d.xf_fixed, [int(b) for b in (xf_fixed or [])], 0)
     d.dt_ref, d.dt_lb, d.dt_ub = dt, dt_lb, dt_ub
+    d.dt_eq_constraint = 1 if dt_eq_constraint else 0
     _fill(d.dyn_params, list(dyn_params))
     _fill(d.q_diag, list(q))
     _fill(d.r_diag, list(r))
@@ -67,10 +68,10 @@ def van_der_pol_shooting(n_grid=20, dt=0.1, integrator=abi.INT_RK4, a=1.0, **kw)
                     q=(1.0, 1.0), r=(0.1,), qf=(1.0, 1.0), u_lb=(-1.0,), u_ub=(1.0,), dyn_params=(a,), **kw)
 
 
-def unicycle_time_optimal(n_grid=50, dt=0.1):
+def unicycle_time_optimal(n_grid=50, dt=0.1, **kw):
     """configs[2]: unicycle, NonUniformFiniteDifferencesVariableGrid, MinimumTime(lsq), xf fixed, |v|,|w|<=1, dt in [0,1]."""
     return make_ocp(grid=abi.GRID_FD_NONUNIFORM_VARDT, dynamics=abi.DYN_UNICYCLE, n_grid=n_grid, dt=dt,
-                    stage_cost=abi.COST_MINIMUM_TIME_LSQ, u_lb=(-1.0, -1.0), u_ub=(1.0, 1.0), xf_fixed=(1, 1, 1), dt_lb=0.0, dt_ub=1.0)
+                    stage_cost=abi.COST_MINIMUM_TIME_LSQ, u_lb=(-1.0, -1.0), u_ub=(1.0, 1.0), xf_fixed=(1, 1, 1), dt_lb=0.0, dt_ub=1.0, **kw)
 
 
 def cart_pole_shooting(n_grid=100, dt=0.02, **kw):

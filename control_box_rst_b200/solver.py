@@ -28,7 +28,7 @@ ABI_SYMBOLS = [
     "b200sqp_last_solve_ms", "b200sqp_launch_count", "b200sqp_device_pointers", "b200sqp_set_stream", "b200sqp_set_threads_per_instance",
     "b200sqp_set_phase_profile", "b200sqp_get_phase_cycles", "b200sqp_final_constraint_indices",
     "b200sqp_peer_export", "b200sqp_peer_attach", "b200sqp_peer_wait", "b200sqp_peer_gathered", "b200sqp_peer_detach", "b200sqp_peer_status", "b200sqp_linearize_dynamics", "b200sqp_warm_start_shift", "b200sqp_mpc_step",
-    "b200sqp_plant_step", "b200sqp_closed_loop", "b200sqp_dynamics_hessian", "b200sqp_set_feature_set", "b200sqp_measure_fp64_peak", "b200sqp_set_precision", "b200sqp_set_reference_trajectory",
+    "b200sqp_plant_step", "b200sqp_closed_loop", "b200sqp_dynamics_hessian", "b200sqp_set_feature_set", "b200sqp_measure_fp64_peak", "b200sqp_set_precision", "b200sqp_set_reference_trajectory", "b200sqp_dt_equality_indices",
 ]
 
 
@@ -94,6 +94,13 @@ def edge_indices(ocp):
     fc = C.c_int32(-2)
     _check(load_library().b200sqp_edge_indices(C.byref(ocp), _i(sc), _i(cc), _i(tc), _i(dy), C.byref(fc)))
     return dict(state_cost=sc, control_cost=cc, dt_cost=tc.reshape(K, 2), dynamics=dy, final_cost=fc.value)
+
+
+def dt_equality_indices(ocp):
+    """row offset (equality category) of the TwoScalarEqualEdge between dt_{k-1} and dt_k, [N-1], -1 where there is none"""
+    out = np.full(ocp.n_grid - 1, -2, np.int32)
+    _check(load_library().b200sqp_dt_equality_indices(C.byref(ocp), _i(out)))
+    return out
 
 
 def final_constraint_indices(ocp):

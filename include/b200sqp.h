@@ -129,6 +129,10 @@ typedef struct b200sqp_ocp {
     double q_full[B200SQP_MAX_NX * B200SQP_MAX_NX];
     double r_full[B200SQP_MAX_NU * B200SQP_MAX_NU];
     double qf_full[B200SQP_MAX_NX * B200SQP_MAX_NX];
+    /* NonUniformFiniteDifferencesVariableGrid::setDtEqConstraint (non_uniform_finite_differences_variable_grid.cpp:150-154): one
+     * TwoScalarEqualEdge (edges/misc_edges.h:40-67) per pair of consecutive intervals, value dt_k - dt_{k-1}, created right after the
+     * dynamics edge of interval k (k >= 1) in the equality category.  Couples consecutive dt vertices. */
+    int32_t dt_eq_constraint;
 } b200sqp_ocp;
 
 /* LevenbergMarquardtSparse parameters (levenberg_marquardt_sparse.h:85-90,112-124); defaults 10 / 2,2,2 / 1,1,1 / 500,500,500 */
@@ -175,6 +179,9 @@ int b200sqp_vertex_indices(const b200sqp_ocp* ocp, int32_t* x_idx /*[N]*/, int32
  * control-cost and dynamics edge of every interval; final-cost edge index in final_cost_idx (or -1). */
 int b200sqp_edge_indices(const b200sqp_ocp* ocp, int32_t* state_cost_idx /*[N-1]*/, int32_t* control_cost_idx /*[N-1]*/,
                          int32_t* dt_cost_idx /*[2*(N-1)]*/, int32_t* dynamics_idx /*[N-1]*/, int32_t* final_cost_idx /*[1]*/);
+/* row offset inside the equality category of the TwoScalarEqualEdge between dt_{k-1} and dt_k, k = 1..N-2 (entry 0 is -1); all -1
+ * without dt_eq_constraint */
+int b200sqp_dt_equality_indices(const b200sqp_ocp* ocp, int32_t* dt_eq_idx /*[N-1]*/);
 /* row offset of the final-stage constraint edge inside the equality (eq_idx) or inequality (ineq_idx) category, -1 if absent */
 int b200sqp_final_constraint_indices(const b200sqp_ocp* ocp, int32_t* eq_idx /*[1]*/, int32_t* ineq_idx /*[1]*/);
 /* CSC pattern of computeCombinedSparseJacobian (hyper_graph_optimization_problem_edge_based.cpp:1480-1753), rows lsq->eq->ineq->bounds */

@@ -244,7 +244,7 @@ bool buildOcp(const b200sqp_ocp& d, const b200sqp_lm_options& o, RefOcp& r)
         g->setDtRef(d.dt_ref);
         g->setDtBounds(d.dt_lb, d.dt_ub);
         g->disableGridAdaptation();
-        g->setDtEqConstraint(false);
+        g->setDtEqConstraint(d.dt_eq_constraint != 0);
         g->setFiniteDifferencesCollocationMethod(makeCollocation(d.collocation));
         g->setCostIntegrationRule(NonUniformFullDiscretizationGridBase::CostIntegrationRule::LeftSum);
         g->setXfFixed(xf_fixed);

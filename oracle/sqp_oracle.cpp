@@ -685,6 +685,18 @@ std::unique_ptr<Graph> buildGraph(const BuildInput& in)
         else
             e.values = [=](double* out) { collocation(coll, f, nx, xk->val.data(), uk->val.data(), xn->val.data(), dtk->val[0], out); };
         g.eq.push_back(e);
+        // TwoScalarEqualEdge(dt_{k-1}, dt_k): values = s2 - s1 (edges/misc_edges.h:57-63), created right after the dynamics edge of
+        // interval k >= 1 when setDtEqConstraint(true) (non_uniform_finite_differences_variable_grid.cpp:150-154)
+        if (var_dt && d.dt_eq_constraint && k > 0)
+        {
+            Vertex* s1 = g.dts[k - 1];
+            Vertex* s2 = g.dts[k];
+            Edge q;
+            q.dim    = 1;
+            q.v      = {s1, s2};
+            q.values = [s1, s2](double* out) { out[0] = s2->val[0] - s1->val[0]; };
+            g.eq.push_back(q);
+        }
     }
     if (!xf->isFixed()) addFinalCostEdge(g, d, xf, xref);
     if (!xf->isFixed()) addFinalConstraintEdge(g, d, xf, xref);

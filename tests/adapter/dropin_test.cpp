@@ -121,7 +121,7 @@ struct TebLoop
     SystemDynamicsInterface::Ptr dynamics;
 };
 
-static TebLoop makeTebUnicycle(NlpSolverInterface::Ptr solver, int n)
+static TebLoop makeTebUnicycle(NlpSolverInterface::Ptr solver, int n, bool dt_eq_constraint = false)
 {
     TebLoop l;
     l.dynamics = std::make_shared<Unicycle>();
@@ -130,7 +130,7 @@ static TebLoop makeTebUnicycle(NlpSolverInterface::Ptr solver, int n)
     grid->setDtRef(0.1);
     grid->setDtBounds(0.0, 1.0);
     grid->disableGridAdaptation();
-    grid->setDtEqConstraint(false);
+    grid->setDtEqConstraint(dt_eq_constraint);
     grid->setCostIntegrationRule(NonUniformFullDiscretizationGridBase::CostIntegrationRule::LeftSum);
     Eigen::Matrix<bool, -1, 1> xf_fixed = Eigen::Matrix<bool, -1, 1>::Constant(3, true);
     grid->setXfFixed(xf_fixed);
@@ -729,6 +729,36 @@ int main(int argc, char** argv)
         if (!ok_r || !ok_d || !(diff <= 1e-5))
         {
             std::printf("FAIL: full weight matrices through the plugin (ok_ref=%d ok_b200=%d, %s)\n", (int)ok_r, (int)ok_d, s_dev->lastError().c_str());
+            ++failures;
+        }
+    }
+    // ---- 11. the time-optimal unicycle with setDtEqConstraint(true): TwoScalarEqualEdges between consecutive dt vertices
+    {
+        ZeroReference xref3(3), uref2(2);
+        auto s_ref = std::make_shared<LevenbergMarquardtSparse>();
+        auto s_dev = std::make_shared<SolverB200Lm>();
+        s_ref->setIterations(6);
+        s_dev->setIterations(6);
+        TebLoop lr = makeTebUnicycle(s_ref, 16, true), lb = makeTebUnicycle(s_dev, 16, true);
+        lr.ocp->initialize();
+        lb.ocp->initialize();
+        Eigen::VectorXd x0(3);
+        x0 << 1.2, -0.9, 0.4;
+        double worst11 = 0;
+        bool ok11      = true;
+        for (int s = 0; s < 2; ++s)
+        {
+            ok11 = lr.ocp->compute(x0, xref3, uref2, nullptr, Time(0.1 * s), true) && ok11;
+            ok11 = lb.ocp->compute(x0, xref3, uref2, nullptr, Time(0.1 * s), true) && ok11;
+            worst11 = std::max(worst11, relDiff(paramsOf(*lr.problem), paramsOf(*lb.problem)));
+            x0[1] += 0.04;
+        }
+        std::printf("time-optimal unicycle with dt equality edges (eq dim %d): max relative trajectory difference vs reference = %.3e "
+                    "(objective %.9g vs %.9g)\n", lb.problem->getEqualityDimension(), worst11, lr.ocp->getCurrentObjectiveValue(),
+                    lb.ocp->getCurrentObjectiveValue());
+        if (!ok11 || !(worst11 <= 1e-4))
+        {
+            std::printf("FAIL: dt equality edges through the plugin (ok=%d, %s)\n", (int)ok11, s_dev->lastError().c_str());
             ++failures;
         }
     }

@@ -624,3 +624,57 @@ def test_full_weight_matrices_match_the_checkers(oracle):
     with pytest.raises(solver.B200SqpError) as info:
         solver.BatchedLevenbergMarquardt(problems.cart_pole_shooting(10, q_full=Q4), 4)
     assert info.value.code == abi.ERR_UNSUPPORTED
+
+
+def test_dt_equality_edges_match_the_checkers(oracle):
+    """NonUniformFiniteDifferencesVariableGrid::setDtEqConstraint(true) (TwoScalarEqualEdge, edges/misc_edges.h:40-67): consecutive dt
+    vertices are tied by equality edges, which couples the dt slots of neighbouring stage blocks on the device (sub-diagonal blocks one
+    column wider).  Values, Jacobian and drift bit-identical to the checker for the polynomial models (incl. the bound rows of the dt
+    vertices, finished one interval late), solves for T = 1 and the widest thread mapping (chunk boundaries cut through the dt
+    coupling), N = 3 (a single equality edge) included."""
+    import sys as _sys
+    _sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+    from test_oracle_vs_reference import DT_EQ_CASES
+    from oracle import bindings
+
+    chk = bindings.Reference() if bindings.Reference.available() else oracle
+    for name, make in DT_EQ_CASES.items():
+        ocp = make()
+        B = 40
+        x0, xref = problems.instance_data(ocp, B, seed=4)
+        rng = np.random.default_rng(2)
+        lm = solver.BatchedLevenbergMarquardt(ocp, B)
+        lm.set_problem_data(x0, xref)
+        lm.initialize_trajectories()
+        p = lm.get_params() + rng.uniform(-0.2, 0.2, (B, lm.dims.n_params))
+        dt_idx = solver.vertex_indices(ocp)[2]
+        p[:, dt_idx] = np.abs(p[:, dt_idx]) + 0.05
+        p[::3, dt_idx[0]] = 1.3  # some dt vertices beyond their upper bound: active bound rows
+        lm.set_params(p)
+        w = (2.0, 3.0, 4.0)
+        values, jac = lm.evaluate(w)
+        after = lm.get_params()
+        exact = ocp.dynamics != abi.DYN_UNICYCLE
+        for i in range(4):
+            v_c, J_c, _, a_c = chk.evaluate(ocp, x0[i], xref[i], p[i], w)
+            J = _csc_to_dense(ocp, jac[i])
+            if exact:
+                assert np.array_equal(values[i], v_c), (name, np.abs(values[i] - v_c).max())
+                assert np.array_equal(J, J_c), (name, np.abs(J - J_c).max())
+                assert np.array_equal(after[i], a_c), (name, np.abs(after[i] - a_c).max())
+            else:
+                np.testing.assert_allclose(values[i], v_c, rtol=1e-13, atol=1e-13)
+                np.testing.assert_allclose(J, J_c, rtol=0, atol=2e-6 * max(1.0, np.abs(J_c).max()))
+        opts = abi.LmOptions.defaults(iterations=6, weights=w)
+        p_c, c_c, _, _ = chk.solve_batch(ocp, opts, x0, xref, threads=4)
+        for T in (1, 8):
+            lm.setIterations(6)
+            lm.setPenaltyWeights(*w)
+            lm.set_threads_per_instance(T)
+            lm.initialize_trajectories()
+            _, chi2 = lm.solve(new_run=True)
+            err = _traj_err(lm.get_params(), p_c)
+            print(f"{name} T={T}: trajectory error max {err.max():.2e}, chi2 rel {np.abs(chi2 / c_c - 1).max():.2e}")
+            assert err.max() <= 1e-3 and np.percentile(err, 90) <= 1e-4, (name, T, err.max())
+            np.testing.assert_allclose(chi2, c_c, rtol=1e-4)
+        lm.clear()

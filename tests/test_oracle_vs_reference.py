@@ -214,3 +214,56 @@ def test_full_weight_matrices_oracle_matches_compiled_reference(oracle, referenc
     err = np.abs(po - pr).max(axis=1) / np.maximum(1.0, np.abs(pr).max(axis=1))
     assert err.max() <= (1e-5 if exact else 1e-3), err
     np.testing.assert_allclose(co, cr, rtol=1e-6)
+
+
+DT_EQ_CASES = {
+    "unicycle12_timeopt_dteq": lambda: problems.unicycle_time_optimal(12, dt_eq_constraint=True),
+    "vdp10_timeopt_dteq": lambda: problems.make_ocp(grid=abi.GRID_FD_NONUNIFORM_VARDT, dynamics=abi.DYN_VAN_DER_POL, n_grid=10, dt=0.1,
+                                                     stage_cost=abi.COST_MINIMUM_TIME_LSQ, u_lb=(-1.0,), u_ub=(1.0,), xf_fixed=(1, 1), dt_lb=0.0, dt_ub=1.0,
+                                                     dyn_params=(1.0,), dt_eq_constraint=True),
+    "rocket9_timeopt_dteq": lambda: _with_dt_eq(problems.free_space_rocket_time_optimal(9)),
+    "dint3_timeopt_dteq": lambda: problems.make_ocp(grid=abi.GRID_FD_NONUNIFORM_VARDT, dynamics=abi.DYN_DOUBLE_INTEGRATOR, n_grid=3, dt=0.2,
+                                                     stage_cost=abi.COST_MINIMUM_TIME_LSQ, u_lb=(-1.0,), u_ub=(1.0,), xf_fixed=(1, 1), dt_lb=0.01, dt_ub=1.0,
+                                                     dyn_params=(1.0,), dt_eq_constraint=True),
+}
+
+
+def _with_dt_eq(ocp):
+    ocp.dt_eq_constraint = 1
+    return ocp
+
+
+@pytest.mark.parametrize("name", list(DT_EQ_CASES))
+def test_dt_equality_edges_oracle_matches_compiled_reference(oracle, reference, name):
+    """NonUniformFiniteDifferencesVariableGrid::setDtEqConstraint(true): a TwoScalarEqualEdge (edges/misc_edges.h:40-67) after the dynamics
+    edge of every interval k >= 1 ties dt_k to dt_{k-1}.  Dimensions, edge tables (row offsets, vertex indices), values, the Jacobian and
+    the parameter drift equal the compiled reference's bit for bit (polynomial models); solves agree."""
+    ocp = DT_EQ_CASES[name]()
+    d_r, d_o = reference.dims(ocp), oracle.dims(ocp)
+    for f in ("n_params", "m_lsq", "m_eq", "m_ineq", "m_bounds", "nnz_jacobian", "nnz_hessian_upper", "algorithmic_bytes_per_iteration"):
+        assert getattr(d_r, f) == getattr(d_o, f), f
+    assert d_r.m_eq == (ocp.n_grid - 1) * ocp.nx + (ocp.n_grid - 2)
+    for cat in range(3):
+        assert np.array_equal(reference.edge_table(ocp, cat), oracle.edge_table(ocp, cat))
+    B = 6
+    x0, xref = problems.instance_data(ocp, B, seed=4)
+    rng = np.random.default_rng(2)
+    p_r = reference.initial_params(ocp, x0[0], xref[0])
+    p = p_r + rng.uniform(-0.2, 0.2, p_r.shape)
+    dt_idx = reference.vertex_indices(ocp)[2]
+    p[dt_idx] = np.abs(p[dt_idx]) + 0.05
+    w = (2.0, 3.0, 4.0)
+    v_r, J_r, P_r, a_r = reference.evaluate(ocp, x0[0], xref[0], p, w)
+    v_o, J_o, P_o, a_o = oracle.evaluate(ocp, x0[0], xref[0], p, w)
+    assert np.array_equal(P_r, P_o)
+    if ocp.dynamics != abi.DYN_UNICYCLE:
+        assert np.array_equal(v_r, v_o) and np.array_equal(J_r, J_o) and np.array_equal(a_r, a_o)
+    else:
+        np.testing.assert_allclose(v_o, v_r, rtol=1e-13, atol=1e-13)
+        np.testing.assert_allclose(J_o, J_r, rtol=0, atol=2e-6 * max(1.0, np.abs(J_r).max()))
+    opts = abi.LmOptions.defaults(iterations=5, weights=w)
+    pr, cr, sr, _ = reference.solve_batch(ocp, opts, x0, xref, threads=2)
+    po, co, so, _ = oracle.solve_batch(ocp, opts, x0, xref, threads=2)
+    err = np.abs(po - pr).max(axis=1) / np.maximum(1.0, np.abs(pr).max(axis=1))
+    assert err.max() <= 1e-4, err
+    np.testing.assert_allclose(co, cr, rtol=1e-5)

@@ -142,3 +142,38 @@ def test_full_weight_matrices_structure_and_refusals(oracle):
         solver.dims_of(problems.van_der_pol(12, q_full=np.array([[1.0, 2.0], [2.0, 1.0]])))
     assert info.value.code == abi.ERR_INVALID
     solver.dims_of(problems.van_der_pol(12, q_full=np.diag([2.0, 0.5])))  # full but diagonal: the diagonal branch, zero reference allowed
+
+
+def test_dt_equality_edges_structure(oracle):
+    """setDtEqConstraint(true) on the non-uniform grid: N-2 more equality rows, each right after the dynamics rows of its interval, two
+    more Jacobian entries per row; dimensions, indices and the CSC pattern equal the oracle's (which the CPU suite pins to the compiled
+    reference)."""
+    import sys as _sys
+    _sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+    from test_oracle_vs_reference import DT_EQ_CASES
+
+    for name, make in DT_EQ_CASES.items():
+        ocp = make()
+        d, d_o = solver.dims_of(ocp), oracle.dims(ocp)
+        for f in ("n_params", "m_lsq", "m_eq", "m_ineq", "m_bounds", "nnz_jacobian", "nnz_hessian_upper", "algorithmic_bytes_per_iteration"):
+            assert getattr(d, f) == getattr(d_o, f), (name, f)
+        K, nx = ocp.n_grid - 1, ocp.nx
+        idx = solver.dt_equality_indices(ocp)
+        dyn = solver.edge_indices(ocp)["dynamics"]
+        assert idx[0] == -1
+        for k in range(1, K):
+            assert idx[k] == dyn[k] + nx and (k + 1 == K or dyn[k + 1] == idx[k] + 1)
+        # pattern: the oracle's stored-entry mask at any point
+        x0, xref = problems.instance_data(ocp, 1, seed=1)
+        _, _, P_o, _ = oracle.evaluate(ocp, x0[0], xref[0], None, (2.0, 2.0, 2.0))
+        col_ptr, row_idx = solver.jacobian_pattern(ocp)
+        pat = np.zeros_like(P_o)
+        for c in range(d.n_params):
+            pat[row_idx[col_ptr[c]:col_ptr[c + 1]], c] = True
+        assert np.array_equal(pat, P_o), name
+    plain = problems.unicycle_time_optimal(12)
+    assert np.all(solver.dt_equality_indices(plain) == -1)
+    fixed = problems.van_der_pol(10)
+    fixed.dt_eq_constraint = 1
+    with pytest.raises(solver.B200SqpError):
+        solver.dims_of(fixed)
