@@ -415,12 +415,16 @@ def main_b200(args):
     def timed(fn, steps):
         total_ms, kernel_ms = 0.0, 0.0
         for _ in range(steps):
+            if world > 1:
+                # device-side rendezvous, outside the timed region: all ranks enter the step together, so a step's time is its own
+                # work + exchange and not another rank's late start (the per-step analogue of the bracket barrier).  The L2 flush and a
+                # short spin follow the rendezvous: equal device work on every rank, during which each rank's host thread enqueues the
+                # launches of the step -- otherwise the step would start whenever that rank's Python got there (measured: 40-90 us of
+                # skew between ranks at 8 GPUs, which the stop-test wait then turns into step time).
+                dist.all_reduce(rendezvous)
             flush.zero_()  # evict L2 between timed iterations (outside the timed region)
             if world > 1:
-                # device-side rendezvous, also outside the timed region: all ranks enter the step together, so a step's time is
-                # its own work + exchange and not the other rank's leftover flush (the per-step analogue of the bracket barrier)
-                dist.all_reduce(rendezvous)
-                rendezvous.add_(0.0)  # a trivial kernel of ours behind NCCL's (its shared-memory configuration is not the LM kernel's)
+                torch.cuda._sleep(400000)  # ~0.2 ms
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record(stream)
             fn()
