@@ -1,0 +1,227 @@
+// Grid adaptation of the time-optimal grids on the device: per-instance grid size N.
+//
+// Instances of one batch are bucketed by their grid size; bucket N is an ordinary solver handle of the structure with n_grid = N whose
+// first `count` slots are in use (api.cpp, b200sqp_adaptive_*).  The kernels here implement the grid side of one OCP iteration:
+//   decide   NonUniformFiniteDifferencesVariableGrid::adaptGridTimeBasedSingleStep (non_uniform_finite_differences_variable_grid.cpp:206-257):
+//            walk dt_0 .. dt_{N-2}; the first dt above dt_ref (1 + hyst) with N < n_max splits its interval, the first one below
+//            dt_ref (1 - hyst) with N > n_min is merged into its successor; one change per call
+//   migrate  apply the change while moving every instance to its slot in the bucket of its new size: insertion of the mid state
+//            0.5 (x_i + x_{i+1}) with the control of interval i and HALF its dt (the interval itself keeps dt_i, as the reference does),
+//            or removal of (x_i, u_i, dt_i) with dt_{i+1} += dt_i; removing node 0 makes the old x_1 the (fixed) start state until the next
+//            measurement overwrites it (:239-240 and non_uniform_full_discretization_grid_base.cpp:111)
+//   commit   swap the roles of the two parameter buffers of every written slot
+// Two cases the reference leaves undefined (it indexes one past the end of its vertex vectors) are defined here: a split of the LAST
+// interval uses the final state x_f as its right neighbour, a merge of the last interval drops its dt.
+//
+// Trajectory layout of a bucket (lm_device.cuh): K = N-1 blocks of nb = nu + 1 + nx slots (u_k, dt_k, x_{k+1}) per instance, tiled
+// instance-minor; x_0 lives in the bucket's x0 array, the last block holds x_f (fixed components pinned to the reference).
+#include "../../include/b200sqp.h"
+#include "launch.h"
+#include "lm_device_types.h"
+
+namespace b200sqp {
+
+namespace {
+
+__device__ __forceinline__ size_t tiled(int i, int slot, int nslots) { return ((size_t)(i >> 5) * nslots + slot) * 32 + (i & 31); }
+
+__global__ void adaptDecideKernel(const double* __restrict__ z0, const double* __restrict__ z1, const int* __restrict__ cur, int K, int nb, int nu,
+                                  int count, const int* __restrict__ inst_of_slot, double hi, double lo, int n_min, int n_max,
+                                  int* __restrict__ decision)
+{
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= count) return;
+    const double* src = cur[j] ? z1 : z0;
+    const int slots = K * nb, n = K + 1;
+    int dec = ADAPT_NONE;
+    for (int k = 0; k < K; ++k)
+    {
+        const double dt = src[tiled(j, k * nb + nu, slots)];
+        if (dt > hi && n < n_max)
+        {
+            dec = ADAPT_SPLIT | (k << 2);
+            break;
+        }
+        else if (dt < lo && n > n_min)
+        {
+            dec = ADAPT_MERGE | (k << 2);
+            break;
+        }
+    }
+    decision[inst_of_slot[j]] = dec;
+}
+
+struct Source
+{
+    const double* z;
+    const double* x0;  // master copy of the start state of this instance [nx]
+    int slot, K, nb, nu;
+    __device__ double x(int node, int j) const { return node == 0 ? x0[j] : z[tiled(slot, (node - 1) * nb + nu + 1 + j, K * nb)]; }
+    __device__ double u(int k, int j) const { return z[tiled(slot, k * nb + j, K * nb)]; }
+    __device__ double dt(int k) const { return z[tiled(slot, k * nb + nu, K * nb)]; }
+};
+
+// one thread per (instance, destination block)
+__global__ void adaptMigrateKernel(const AdaptBucketView* __restrict__ views, const int* __restrict__ plan /*[5][B]: src bucket, src slot, dst
+                                   bucket, dst slot, decision*/, double* __restrict__ x0_master, const double* __restrict__ xref_master, int nx,
+                                   int nu, int keep_start, int B)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    const int kd = blockIdx.y;
+    if (i >= B) return;
+    const AdaptBucketView sb = views[plan[i]], db = views[plan[2 * B + i]];
+    const int sslot = plan[B + i], dslot = plan[3 * B + i], dec = plan[4 * B + i];
+    const int type = dec & 3, p = dec >> 2;
+    const int Kd = db.K, nb = nu + 1 + nx;
+    if (kd >= Kd) return;
+    Source s{sb.cur[sslot] ? sb.z[1] : sb.z[0], x0_master + (size_t)i * nx, sslot, sb.K, nb, nu};
+    double* dst = db.z[db.cur[dslot] ? 0 : 1];  // the slot's idle buffer: its current one may still be read as somebody's source
+    const int dslots = Kd * nb;
+
+    // interval kd of the new grid
+    int ks = kd;  // source interval
+    double dtv;
+    if (type == ADAPT_SPLIT)
+    {
+        ks  = kd <= p ? kd : kd - 1;
+        dtv = (kd == p + 1) ? 0.5 * s.dt(p) : s.dt(ks);
+    }
+    else if (type == ADAPT_MERGE)
+    {
+        ks  = kd < p ? kd : kd + 1;
+        dtv = s.dt(ks);
+        if (kd == p) dtv += s.dt(p);  // _dt_seq[i + 1].value() += dt
+    }
+    else
+        dtv = s.dt(ks);
+    for (int j = 0; j < nu; ++j) dst[tiled(dslot, kd * nb + j, dslots)] = s.u(ks, j);
+    dst[tiled(dslot, kd * nb + nu, dslots)] = dtv;
+
+    // node kd + 1 of the new grid (the last one is x_f)
+    const int m = kd + 1;
+    for (int j = 0; j < nx; ++j)
+    {
+        double v;
+        if (type == ADAPT_SPLIT)
+            v = (m == p + 1) ? 0.5 * (s.x(p, j) + s.x(p + 1, j)) : s.x(m <= p ? m : m - 1, j);
+        else if (type == ADAPT_MERGE)
+            v = s.x(m < p ? m : m + 1, j);
+        else
+            v = s.x(m, j);
+        dst[tiled(dslot, kd * nb + nu + 1 + j, dslots)] = v;
+    }
+
+    if (kd == 0)
+    {
+        // start state and reference of the slot; a removed node 0 promotes the old x_1 (read before the master copy is overwritten: no
+        // other block of this instance reads node 0 in that case)
+        for (int j = 0; j < nx; ++j)
+        {
+            double v = x0_master[(size_t)i * nx + j];
+            if (type == ADAPT_MERGE && p == 0 && !keep_start)
+            {
+                v                              = s.x(1, j);
+                x0_master[(size_t)i * nx + j] = v;
+            }
+            db.x0[tiled(dslot, j, nx)]   = v;
+            db.xref[tiled(dslot, j, nx)] = xref_master[(size_t)i * nx + j];
+        }
+    }
+}
+
+__global__ void adaptCommitKernel(const AdaptBucketView* __restrict__ views, const int* __restrict__ plan, int B)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= B) return;
+    const AdaptBucketView db = views[plan[2 * B + i]];
+    const int dslot          = plan[3 * B + i];
+    db.cur[dslot]            = db.cur[dslot] ? 0 : 1;  // every (bucket, slot) is the destination of exactly one instance
+}
+
+// measured start states / references of a new run -> the buckets' tiled arrays (x_seq.front() = x0; the fixed goal components follow
+// through launchFillPinned)
+__global__ void adaptScatterStartKernel(const AdaptBucketView* __restrict__ views, const int* __restrict__ plan /*dst bucket, dst slot at rows 2, 3*/,
+                                        const double* __restrict__ x0_master, const double* __restrict__ xref_master, int nx, int B)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= B) return;
+    const AdaptBucketView db = views[plan[2 * B + i]];
+    const int dslot          = plan[3 * B + i];
+    for (int j = 0; j < nx; ++j)
+    {
+        db.x0[tiled(dslot, j, nx)]   = x0_master[(size_t)i * nx + j];
+        db.xref[tiled(dslot, j, nx)] = xref_master[(size_t)i * nx + j];
+    }
+}
+
+// per-instance results in batch order: first control, chi2, status
+__global__ void adaptGatherKernel(const AdaptBucketView* __restrict__ views, const int* __restrict__ plan, int nx, int nu, double* __restrict__ u0,
+                                  double* __restrict__ chi2, int* __restrict__ status, int B)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= B) return;
+    const AdaptBucketView b = views[plan[2 * B + i]];
+    const int slot          = plan[3 * B + i];
+    const double* src       = b.cur[slot] ? b.z[1] : b.z[0];
+    const int nb            = nu + 1 + nx;
+    for (int j = 0; j < nu; ++j) u0[(size_t)i * nu + j] = src[tiled(slot, j, b.K * nb)];
+    chi2[i]   = b.chi2[slot];
+    status[i] = b.status[slot];
+}
+
+// trajectories in batch order, padded to n_cap grid points: x [B][n_cap][nx], u [B][n_cap][nu], dt [B][n_cap], n [B]
+__global__ void adaptExportKernel(const AdaptBucketView* __restrict__ views, const int* __restrict__ plan, const double* __restrict__ x0_master,
+                                  int nx, int nu, int n_cap, double* __restrict__ x, double* __restrict__ u, double* __restrict__ dt,
+                                  int* __restrict__ n, int B)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    const int k = blockIdx.y;  // grid point
+    if (i >= B) return;
+    const AdaptBucketView b = views[plan[2 * B + i]];
+    const int slot          = plan[3 * B + i];
+    if (k == 0) n[i] = b.K + 1;
+    if (k > b.K || k >= n_cap) return;
+    Source s{b.cur[slot] ? b.z[1] : b.z[0], x0_master + (size_t)i * nx, slot, b.K, nu + 1 + nx, nu};
+    // node 0 comes from the bucket's own start-state array: the master copy is the last measurement, which differs after a removed node 0
+    for (int j = 0; j < nx; ++j) x[((size_t)i * n_cap + k) * nx + j] = k == 0 ? b.x0[tiled(slot, j, nx)] : s.x(k, j);
+    if (k < b.K)
+    {
+        for (int j = 0; j < nu; ++j) u[((size_t)i * n_cap + k) * nu + j] = s.u(k, j);
+        dt[(size_t)i * n_cap + k] = s.dt(k);
+    }
+}
+
+}  // namespace
+
+void launchAdaptDecide(const double* z0, const double* z1, const int* cur, int K, int nx, int nu, int count, const int* inst_of_slot, double hi,
+                       double lo, int n_min, int n_max, int* decision, cudaStream_t stream)
+{
+    if (count <= 0) return;
+    adaptDecideKernel<<<(count + 127) / 128, 128, 0, stream>>>(z0, z1, cur, K, nu + 1 + nx, nu, count, inst_of_slot, hi, lo, n_min, n_max, decision);
+}
+
+void launchAdaptMigrate(const AdaptBucketView* views, const int* plan, double* x0_master, const double* xref_master, int nx, int nu, int keep_start,
+                        int k_max, int B, cudaStream_t stream)
+{
+    adaptMigrateKernel<<<dim3((B + 127) / 128, k_max), 128, 0, stream>>>(views, plan, x0_master, xref_master, nx, nu, keep_start, B);
+    adaptCommitKernel<<<(B + 127) / 128, 128, 0, stream>>>(views, plan, B);
+}
+
+void launchAdaptScatterStart(const AdaptBucketView* views, const int* plan, const double* x0_master, const double* xref_master, int nx, int B,
+                             cudaStream_t stream)
+{
+    adaptScatterStartKernel<<<(B + 127) / 128, 128, 0, stream>>>(views, plan, x0_master, xref_master, nx, B);
+}
+
+void launchAdaptGather(const AdaptBucketView* views, const int* plan, int nx, int nu, double* u0, double* chi2, int* status, int B, cudaStream_t stream)
+{
+    adaptGatherKernel<<<(B + 127) / 128, 128, 0, stream>>>(views, plan, nx, nu, u0, chi2, status, B);
+}
+
+void launchAdaptExport(const AdaptBucketView* views, const int* plan, const double* x0_master, int nx, int nu, int n_cap, double* x, double* u,
+                       double* dt, int* n, int B, cudaStream_t stream)
+{
+    adaptExportKernel<<<dim3((B + 127) / 128, n_cap), 128, 0, stream>>>(views, plan, x0_master, nx, nu, n_cap, x, u, dt, n, B);
+}
+
+}  // namespace b200sqp

@@ -1317,4 +1317,373 @@ int b200sqp_set_stream(b200sqp_handle h, void* cuda_stream)
     return B200SQP_OK;
 }
 
+
+/* ---- grid adaptation front-end ---------------------------------------------------------------------------
+ * Per-instance grid size for the time-optimal grid.  The batch is bucketed by grid size N: bucket N is a solver handle of the same OCP with
+ * n_grid = N (created on first use, sized for the whole batch) whose first count[N] slots are occupied.  The grid side of an OCP
+ * iteration (decision, insertion / removal of a grid point, move to the bucket of the new size) runs in adapt_kernels.cu; the host only
+ * turns the per-instance decisions (4 bytes each) into slot assignments.  Buckets solve concurrently on their own streams. */
+struct b200sqp_adaptive
+{
+    b200sqp_ocp ocp{};
+    int B = 0, device = 0, n_min = 0, n_max = 0, n_lo = 0, n_hi = 0, nx = 0, nu = 0;
+    double hyst = 0.1;
+    int warm_start = 1;
+    std::vector<b200sqp_handle> bucket;
+    std::vector<int> count, offset;          // occupied slots per bucket; start of the bucket's slice in d_inst_sorted
+    std::vector<int> bucket_of, slot_of;     // per instance
+    std::vector<AdaptBucketView> views;
+    AdaptBucketView* d_views = nullptr;
+    int *d_plan = nullptr, *hp_plan = nullptr;          // [5][B] (device / pinned host)
+    int *d_decision = nullptr, *hp_decision = nullptr;  // [B]
+    int *d_inst_sorted = nullptr, *hp_inst_sorted = nullptr;  // [B] instance ids grouped by bucket, slot order
+    double *d_x0_master = nullptr, *d_xref_master = nullptr, *d_u0 = nullptr, *d_chi2 = nullptr;
+    int* d_status = nullptr;
+    double *d_tx = nullptr, *d_tu = nullptr, *d_tdt = nullptr;  // trajectory export staging
+    int* d_tn = nullptr;
+    int export_cap = 0;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev_ready = nullptr;
+    bool first_run = true, weights_initialised = false;
+    double w_eq = 2, w_ineq = 2, w_b = 2;
+    int64_t launches = 0, splits = 0, merges = 0;
+    std::vector<void*> allocations;
+};
+
+namespace {
+
+int adaptiveEnsureBucket(b200sqp_adaptive* a, int idx)
+{
+    if (a->bucket[idx]) return B200SQP_OK;
+    b200sqp_ocp o = a->ocp;
+    o.n_grid      = a->n_lo + idx;
+    b200sqp_handle h = nullptr;
+    int rc = b200sqp_create(&o, a->B, a->device, &h);
+    if (rc) return rc;
+    a->bucket[idx] = h;
+    AdaptBucketView& v = a->views[idx];
+    v.z[0] = h->st.z[0], v.z[1] = h->st.z[1], v.cur = h->st.cur, v.x0 = h->st.x0, v.xref = h->st.xref, v.chi2 = h->st.chi2, v.status = h->st.status;
+    v.K = h->s.K;
+    CUDA_TRY(cudaMemcpyAsync(a->d_views + idx, &v, sizeof(v), cudaMemcpyHostToDevice, a->stream));
+    CUDA_TRY(cudaStreamSynchronize(a->stream));
+    return B200SQP_OK;
+}
+
+// occupied buckets: offsets into the grouped instance list, and that list, from bucket_of / slot_of
+int adaptiveUploadGrouping(b200sqp_adaptive* a)
+{
+    int acc = 0;
+    for (size_t b = 0; b < a->count.size(); ++b)
+    {
+        a->offset[b] = acc;
+        acc += a->count[b];
+    }
+    for (int i = 0; i < a->B; ++i) a->hp_inst_sorted[a->offset[a->bucket_of[i]] + a->slot_of[i]] = i;
+    CUDA_TRY(cudaMemcpyAsync(a->d_inst_sorted, a->hp_inst_sorted, sizeof(int) * a->B, cudaMemcpyHostToDevice, a->stream));
+    return B200SQP_OK;
+}
+
+void adaptiveFillPinned(b200sqp_adaptive* a)
+{
+    unsigned mask = 0;
+    for (int i = 0; i < a->nx; ++i)
+        if (a->ocp.xf_fixed[i]) mask |= 1u << i;
+    if (!mask) return;
+    for (size_t b = 0; b < a->bucket.size(); ++b)
+        if (a->count[b] > 0)
+        {
+            b200sqp_handle h = a->bucket[b];
+            const int nb = h->s.nb, xo = h->s.nu + h->s.vt;
+            launchFillPinned(h->st.xref, h->st.z[0], h->st.z[1], (h->s.K - 1) * nb + xo, h->s.K * nb, h->s.nx, mask, a->count[b], a->stream);
+            a->launches += 1;
+        }
+}
+
+// NonUniformFiniteDifferencesVariableGrid::adaptGrid for every instance; *changed = any grid changed
+int adaptiveAdapt(b200sqp_adaptive* a, bool* changed)
+{
+    *changed        = false;
+    const double hi = a->ocp.dt_ref * (1.0 + a->hyst), lo = a->ocp.dt_ref * (1.0 - a->hyst);
+    for (size_t b = 0; b < a->bucket.size(); ++b)
+        if (a->count[b] > 0)
+        {
+            b200sqp_handle h = a->bucket[b];
+            launchAdaptDecide(h->st.z[0], h->st.z[1], h->st.cur, h->s.K, a->nx, a->nu, a->count[b], a->d_inst_sorted + a->offset[b], hi, lo, a->n_min,
+                              a->n_max, a->d_decision, a->stream);
+            a->launches += 1;
+        }
+    CUDA_TRY(cudaGetLastError());
+    CUDA_TRY(cudaMemcpyAsync(a->hp_decision, a->d_decision, sizeof(int) * a->B, cudaMemcpyDeviceToHost, a->stream));
+    CUDA_TRY(cudaStreamSynchronize(a->stream));
+    bool any = false;
+    for (int i = 0; i < a->B && !any; ++i) any = a->hp_decision[i] != 0;
+    if (!any) return B200SQP_OK;
+
+    const int B = a->B;
+    std::vector<int> new_count(a->count.size(), 0);
+    int k_max = 1;
+    for (int i = 0; i < B; ++i)
+    {
+        const int dec = a->hp_decision[i], type = dec & 3;
+        const int src = a->bucket_of[i];
+        const int dst = src + (type == ADAPT_SPLIT ? 1 : type == ADAPT_MERGE ? -1 : 0);
+        if (dst < 0 || dst >= (int)a->bucket.size()) return fail(B200SQP_ERR_INVALID, "grid adaptation left the bucket range");
+        a->splits += type == ADAPT_SPLIT;
+        a->merges += type == ADAPT_MERGE;
+        int rc = adaptiveEnsureBucket(a, dst);
+        if (rc) return rc;
+        a->hp_plan[i]         = src;
+        a->hp_plan[B + i]     = a->slot_of[i];
+        a->hp_plan[2 * B + i] = dst;
+        a->hp_plan[3 * B + i] = new_count[dst]++;
+        a->hp_plan[4 * B + i] = dec;
+        k_max                 = std::max(k_max, a->n_lo + dst - 1);
+    }
+    CUDA_TRY(cudaMemcpyAsync(a->d_plan, a->hp_plan, sizeof(int) * 5 * B, cudaMemcpyHostToDevice, a->stream));
+    launchAdaptMigrate(a->d_views, a->d_plan, a->d_x0_master, a->d_xref_master, a->nx, a->nu, a->warm_start ? 0 : 1, k_max, B, a->stream);
+    a->launches += 2;
+    CUDA_TRY(cudaGetLastError());
+    for (int i = 0; i < B; ++i)
+    {
+        a->bucket_of[i] = a->hp_plan[2 * B + i];
+        a->slot_of[i]   = a->hp_plan[3 * B + i];
+    }
+    a->count = new_count;
+    CUDA_TRY(cudaStreamSynchronize(a->stream));  // hp_plan / hp_inst_sorted are rewritten below and by the next call
+    int rc = adaptiveUploadGrouping(a);
+    if (rc) return rc;
+    adaptiveFillPinned(a);  // both parameter buffers of a slot carry the fixed goal components
+    CUDA_TRY(cudaGetLastError());
+    *changed = true;
+    return B200SQP_OK;
+}
+
+}  // namespace
+
+int b200sqp_adaptive_create(const b200sqp_ocp* ocp, int32_t batch, int32_t device, int32_t n_min, int32_t n_max, double dt_hyst_ratio,
+                            int32_t warm_start, b200sqp_adaptive_handle* out)
+{
+    if (!ocp || !out || batch < 1) return fail(B200SQP_ERR_INVALID, "null argument or batch < 1");
+    *out = nullptr;
+    if (ocp->grid != B200SQP_GRID_FD_NONUNIFORM_VARDT)
+        return fail(B200SQP_ERR_UNSUPPORTED, "grid adaptation is implemented for the non-uniform time-optimal grid (one dt vertex per interval)");
+    if (n_min < 3 || n_max < n_min || !(dt_hyst_ratio >= 0.0 && dt_hyst_ratio < 1.0))
+        return fail(B200SQP_ERR_INVALID, "need 3 <= n_min <= n_max and 0 <= dt_hyst_ratio < 1");
+    if (ocp->n_grid < 3) return fail(B200SQP_ERR_INVALID, "n_grid < 3");
+    b200sqp_adaptive* a = new b200sqp_adaptive;
+    a->ocp = *ocp, a->B = batch, a->device = device, a->n_min = n_min, a->n_max = n_max, a->hyst = dt_hyst_ratio, a->warm_start = warm_start ? 1 : 0;
+    a->nx = ocp->nx, a->nu = ocp->nu;
+    // a grid only shrinks while N > n_min and only grows while N < n_max, so its size stays inside the hull of [n_min, n_max] and n_grid
+    a->n_lo = std::min(n_min, ocp->n_grid), a->n_hi = std::max(n_max, ocp->n_grid);
+    const int nbuckets = a->n_hi - a->n_lo + 1;
+    a->bucket.assign(nbuckets, nullptr);
+    a->count.assign(nbuckets, 0);
+    a->offset.assign(nbuckets, 0);
+    a->views.assign(nbuckets, AdaptBucketView{});
+    a->bucket_of.assign(batch, ocp->n_grid - a->n_lo);
+    a->slot_of.resize(batch);
+    for (int i = 0; i < batch; ++i) a->slot_of[i] = i;
+    auto destroy_and_fail = [&](int code, const std::string& msg) {
+        b200sqp_adaptive_destroy(a);
+        return fail(code, msg);
+    };
+    int dev_count = 0;
+    if (cudaGetDeviceCount(&dev_count) != cudaSuccess || dev_count == 0)
+    {
+        cudaGetLastError();
+        return destroy_and_fail(B200SQP_ERR_NO_DEVICE, "no CUDA device visible: the LM hot path only exists as sm_100a kernels");
+    }
+    if (device < 0 || device >= dev_count) return destroy_and_fail(B200SQP_ERR_INVALID, "device index out of range");
+    cudaError_t e = cudaSetDevice(device);
+    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&a->stream, cudaStreamNonBlocking);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&a->ev_ready, cudaEventDisableTiming);
+    auto A = [&](auto** p, size_t cnt) {
+        if (e == cudaSuccess) e = cudaMalloc((void**)p, sizeof(**p) * cnt);
+        if (e == cudaSuccess) a->allocations.push_back(*p);
+        if (e == cudaSuccess) e = cudaMemsetAsync(*p, 0, sizeof(**p) * cnt, a->stream);
+    };
+    A(&a->d_views, (size_t)nbuckets);
+    A(&a->d_plan, (size_t)5 * batch);
+    A(&a->d_decision, (size_t)batch);
+    A(&a->d_inst_sorted, (size_t)batch);
+    A(&a->d_x0_master, (size_t)batch * a->nx);
+    A(&a->d_xref_master, (size_t)batch * a->nx);
+    A(&a->d_u0, (size_t)batch * a->nu);
+    A(&a->d_chi2, (size_t)batch);
+    A(&a->d_status, (size_t)batch);
+    if (e == cudaSuccess) e = cudaMallocHost((void**)&a->hp_plan, sizeof(int) * 5 * batch);
+    if (e == cudaSuccess) e = cudaMallocHost((void**)&a->hp_decision, sizeof(int) * batch);
+    if (e == cudaSuccess) e = cudaMallocHost((void**)&a->hp_inst_sorted, sizeof(int) * batch);
+    if (e != cudaSuccess) return destroy_and_fail(B200SQP_ERR_CUDA, std::string("device allocation failed: ") + cudaGetErrorString(e));
+    const int idx0 = ocp->n_grid - a->n_lo;
+    int rc         = adaptiveEnsureBucket(a, idx0);  // also the check that the structure is in the registry
+    if (rc)
+    {
+        const std::string msg = g_last_error;
+        return destroy_and_fail(rc, msg);
+    }
+    a->count[idx0] = batch;
+    for (int i = 0; i < batch; ++i)
+    {
+        a->hp_plan[i] = a->hp_plan[2 * batch + i] = idx0;
+        a->hp_plan[batch + i] = a->hp_plan[3 * batch + i] = i;
+        a->hp_plan[4 * batch + i]                          = 0;
+    }
+    e = cudaMemcpyAsync(a->d_plan, a->hp_plan, sizeof(int) * 5 * batch, cudaMemcpyHostToDevice, a->stream);
+    if (e == cudaSuccess) rc = adaptiveUploadGrouping(a);
+    if (e == cudaSuccess && !rc) e = cudaStreamSynchronize(a->stream);
+    if (e != cudaSuccess || rc) return destroy_and_fail(B200SQP_ERR_CUDA, "initial grouping upload failed");
+    *out = a;
+    return B200SQP_OK;
+}
+
+int b200sqp_adaptive_destroy(b200sqp_adaptive_handle a)
+{
+    if (!a) return B200SQP_OK;
+    cudaSetDevice(a->device);
+    if (a->stream) cudaStreamSynchronize(a->stream);
+    for (b200sqp_handle h : a->bucket) b200sqp_destroy(h);
+    for (void* p : a->allocations) cudaFree(p);
+    if (a->hp_plan) cudaFreeHost(a->hp_plan);
+    if (a->hp_decision) cudaFreeHost(a->hp_decision);
+    if (a->hp_inst_sorted) cudaFreeHost(a->hp_inst_sorted);
+    if (a->ev_ready) cudaEventDestroy(a->ev_ready);
+    if (a->stream) cudaStreamDestroy(a->stream);
+    delete a;
+    return B200SQP_OK;
+}
+
+int b200sqp_adaptive_step(b200sqp_adaptive_handle a, const b200sqp_lm_options* opts, int32_t num_ocp_iterations, const double* x0,
+                          const double* xref, double* u0_out, double* chi2_out, int32_t* status_out, int32_t* n_out)
+{
+    if (!a || !opts || !x0 || !xref || num_ocp_iterations < 1 || opts->iterations < 0) return fail(B200SQP_ERR_INVALID, "bad argument");
+    CUDA_TRY(cudaSetDevice(a->device));
+    const int B = a->B, nx = a->nx, nu = a->nu;
+    for (int it = 0; it < num_ocp_iterations; ++it)
+    {
+        const bool new_run = it == 0;
+        // FullDiscretizationGridBase / NonUniformFullDiscretizationGridBase::update: adaptGrid unless first run or new run
+        if (!a->first_run && !new_run)
+        {
+            bool changed = false;
+            int rc       = adaptiveAdapt(a, &changed);
+            if (rc) return rc;
+        }
+        if (new_run)
+        {
+            CUDA_TRY(cudaMemcpyAsync(a->d_x0_master, x0, sizeof(double) * (size_t)B * nx, cudaMemcpyHostToDevice, a->stream));
+            CUDA_TRY(cudaMemcpyAsync(a->d_xref_master, xref, sizeof(double) * (size_t)B * nx, cudaMemcpyHostToDevice, a->stream));
+            launchAdaptScatterStart(a->d_views, a->d_plan, a->d_x0_master, a->d_xref_master, nx, B, a->stream);
+            a->launches += 1;
+            adaptiveFillPinned(a);
+            CUDA_TRY(cudaGetLastError());
+        }
+        if (a->first_run || !a->warm_start)
+        {
+            // initializeSequences at the current grid size of every instance (n_init = _n_adapt, non_uniform_full_discretization_grid_base.cpp:161)
+            for (size_t b = 0; b < a->bucket.size(); ++b)
+                if (a->count[b] > 0)
+                {
+                    b200sqp_handle h = a->bucket[b];
+                    launchInitTrajectories(h->st.x0, h->st.xref, nullptr, h->st.z[0], h->st.cur, h->s.K, nx, nu, h->s.vt, a->ocp.dt_ref, a->count[b], h->S,
+                                           a->stream);
+                    a->launches += 1;
+                }
+            CUDA_TRY(cudaGetLastError());
+        }
+        CUDA_TRY(cudaEventRecord(a->ev_ready, a->stream));
+        // resetWeights / adaptWeights (levenberg_marquardt_sparse.cpp:83-86, 264-287): one solver object per instance, all in lockstep
+        if (new_run || !a->weights_initialised)
+            a->w_eq = opts->weight_eq, a->w_ineq = opts->weight_ineq, a->w_b = opts->weight_bounds;
+        else
+        {
+            a->w_eq   = std::min(a->w_eq * opts->adapt_factor_eq, opts->adapt_max_eq);
+            a->w_ineq = std::min(a->w_ineq * opts->adapt_factor_ineq, opts->adapt_max_ineq);
+            a->w_b    = std::min(a->w_b * opts->adapt_factor_bounds, opts->adapt_max_bounds);
+        }
+        a->weights_initialised = true;
+        for (size_t b = 0; b < a->bucket.size(); ++b)
+            if (a->count[b] > 0)
+            {
+                b200sqp_handle h = a->bucket[b];
+                int rc           = ensureTrace(h, opts->iterations);
+                if (rc) return rc;
+                h->st.w_eq = a->w_eq, h->st.w_ineq = a->w_ineq, h->st.w_b = a->w_b;
+                h->weights_initialised = true;
+                DeviceOcp P            = h->P;
+                P.B                    = a->count[b];  // the occupied slots of the bucket
+                CUDA_TRY(cudaStreamWaitEvent(h->stream, a->ev_ready, 0));
+                CUDA_TRY(cudaEventRecord(h->ev_begin, h->stream));
+                h->kernels->solve(P, h->st, opts->iterations, h->threads_per_instance, h->solve_flags, h->stream);
+                CUDA_TRY(cudaGetLastError());
+                CUDA_TRY(cudaEventRecord(h->ev_end, h->stream));
+                h->timed = true;
+                h->launches += 1;
+                a->launches += 1;
+                CUDA_TRY(cudaStreamWaitEvent(a->stream, h->ev_end, 0));
+            }
+        a->first_run = false;
+    }
+    launchAdaptGather(a->d_views, a->d_plan, nx, nu, a->d_u0, a->d_chi2, a->d_status, B, a->stream);
+    a->launches += 1;
+    CUDA_TRY(cudaGetLastError());
+    if (u0_out) CUDA_TRY(cudaMemcpyAsync(u0_out, a->d_u0, sizeof(double) * (size_t)B * nu, cudaMemcpyDeviceToHost, a->stream));
+    if (chi2_out) CUDA_TRY(cudaMemcpyAsync(chi2_out, a->d_chi2, sizeof(double) * B, cudaMemcpyDeviceToHost, a->stream));
+    if (status_out) CUDA_TRY(cudaMemcpyAsync(status_out, a->d_status, sizeof(int32_t) * B, cudaMemcpyDeviceToHost, a->stream));
+    CUDA_TRY(cudaStreamSynchronize(a->stream));
+    if (n_out)
+        for (int i = 0; i < B; ++i) n_out[i] = a->n_lo + a->bucket_of[i];
+    return B200SQP_OK;
+}
+
+int b200sqp_adaptive_get_trajectories(b200sqp_adaptive_handle a, int32_t n_cap, double* x, double* u, double* dt, int32_t* n)
+{
+    if (!a || n_cap < 2) return fail(B200SQP_ERR_INVALID, "bad argument");
+    CUDA_TRY(cudaSetDevice(a->device));
+    for (int i = 0; i < a->B; ++i)
+        if (a->n_lo + a->bucket_of[i] > n_cap) return fail(B200SQP_ERR_INVALID, "n_cap is smaller than the largest grid of the batch");
+    const size_t B = a->B;
+    if (a->export_cap < n_cap)
+    {
+        cudaError_t e = cudaSuccess;
+        auto A        = [&](auto** p, size_t cnt) {
+            if (e == cudaSuccess) e = cudaMalloc((void**)p, sizeof(**p) * cnt);
+            if (e == cudaSuccess) a->allocations.push_back(*p);
+        };
+        A(&a->d_tx, B * n_cap * a->nx);
+        A(&a->d_tu, B * n_cap * a->nu);
+        A(&a->d_tdt, B * n_cap);
+        if (!a->d_tn) A(&a->d_tn, B);
+        if (e != cudaSuccess) return fail(B200SQP_ERR_CUDA, std::string("device allocation failed: ") + cudaGetErrorString(e));
+        a->export_cap = n_cap;
+    }
+    CUDA_TRY(cudaMemsetAsync(a->d_tx, 0, sizeof(double) * B * n_cap * a->nx, a->stream));
+    CUDA_TRY(cudaMemsetAsync(a->d_tu, 0, sizeof(double) * B * n_cap * a->nu, a->stream));
+    CUDA_TRY(cudaMemsetAsync(a->d_tdt, 0, sizeof(double) * B * n_cap, a->stream));
+    launchAdaptExport(a->d_views, a->d_plan, a->d_x0_master, a->nx, a->nu, n_cap, a->d_tx, a->d_tu, a->d_tdt, a->d_tn, a->B, a->stream);
+    a->launches += 1;
+    CUDA_TRY(cudaGetLastError());
+    if (x) CUDA_TRY(cudaMemcpyAsync(x, a->d_tx, sizeof(double) * B * n_cap * a->nx, cudaMemcpyDeviceToHost, a->stream));
+    if (u) CUDA_TRY(cudaMemcpyAsync(u, a->d_tu, sizeof(double) * B * n_cap * a->nu, cudaMemcpyDeviceToHost, a->stream));
+    if (dt) CUDA_TRY(cudaMemcpyAsync(dt, a->d_tdt, sizeof(double) * B * n_cap, cudaMemcpyDeviceToHost, a->stream));
+    if (n) CUDA_TRY(cudaMemcpyAsync(n, a->d_tn, sizeof(int32_t) * B, cudaMemcpyDeviceToHost, a->stream));
+    CUDA_TRY(cudaStreamSynchronize(a->stream));
+    return B200SQP_OK;
+}
+
+int b200sqp_adaptive_statistics(b200sqp_adaptive_handle a, int32_t* occupied_buckets, int64_t* splits, int64_t* merges, int64_t* launches)
+{
+    if (!a) return fail(B200SQP_ERR_INVALID, "null handle");
+    if (occupied_buckets)
+    {
+        int c = 0;
+        for (int v : a->count) c += v > 0;
+        *occupied_buckets = c;
+    }
+    if (splits) *splits = a->splits;
+    if (merges) *merges = a->merges;
+    if (launches) *launches = a->launches;
+    return B200SQP_OK;
+}
+
 }  // extern "C"

@@ -96,6 +96,20 @@ void launchPeerPublish(const DeviceState& st, int B, cudaStream_t);
 void launchPeerWait(const unsigned long long* arrivals, int world, unsigned long long expected, unsigned long long timeout_ns, int* timed_out,
                     cudaStream_t);
 
+// grid adaptation of the time-optimal grids (adapt_kernels.cu; b200sqp_adaptive_*): decision per instance of one bucket, migration of every
+// instance to (bucket, slot) of its new grid size, start-state scatter, result gather and trajectory export in batch order.
+// plan [5][B] device: source bucket, source slot, destination bucket, destination slot, decision (ADAPT_* | interval << 2)
+struct AdaptBucketView;
+void launchAdaptDecide(const double* z0, const double* z1, const int* cur, int K, int nx, int nu, int count, const int* inst_of_slot, double hi,
+                       double lo, int n_min, int n_max, int* decision, cudaStream_t);
+void launchAdaptMigrate(const AdaptBucketView* views, const int* plan, double* x0_master, const double* xref_master, int nx, int nu, int keep_start,
+                        int k_max, int B, cudaStream_t);
+void launchAdaptScatterStart(const AdaptBucketView* views, const int* plan, const double* x0_master, const double* xref_master, int nx, int B,
+                             cudaStream_t);
+void launchAdaptGather(const AdaptBucketView* views, const int* plan, int nx, int nu, double* u0, double* chi2, int* status, int B, cudaStream_t);
+void launchAdaptExport(const AdaptBucketView* views, const int* plan, const double* x0_master, int nx, int nu, int n_cap, double* x, double* u,
+                       double* dt, int* n, int B, cudaStream_t);
+
 // measured fp64 FMA throughput of the device (TFLOP/s, 2 flops per FMA), all SMs, best of three timed launches; < 0 on failure
 double measureFp64PeakTflops(int sm_count, cudaStream_t);
 

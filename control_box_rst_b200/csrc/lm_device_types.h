@@ -129,6 +129,19 @@ inline int paddedTriangle(int nx, int bytes_per_value)
     return (n + per16 - 1) / per16 * per16;
 }
 
+// grid adaptation (adapt_kernels.cu): what the kernels see of one bucket (a solver handle whose grid has K + 1 points)
+struct AdaptBucketView
+{
+    double* z[2];
+    int* cur;
+    double* x0;
+    double* xref;
+    double* chi2;
+    int* status;
+    int K;
+};
+enum { ADAPT_NONE = 0, ADAPT_SPLIT = 1, ADAPT_MERGE = 2 };  // decision = type | interval << 2
+
 // structures the pipeline covers (lm_pipeline.cuh); everything else runs through the fused kernel
 inline bool pipelineEligible(const DeviceOcp& P, int nx)
 {

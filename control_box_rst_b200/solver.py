@@ -29,6 +29,8 @@ ABI_SYMBOLS = [
     "b200sqp_set_phase_profile", "b200sqp_get_phase_cycles", "b200sqp_final_constraint_indices",
     "b200sqp_peer_export", "b200sqp_peer_attach", "b200sqp_peer_wait", "b200sqp_peer_gathered", "b200sqp_peer_detach", "b200sqp_peer_status", "b200sqp_linearize_dynamics", "b200sqp_warm_start_shift", "b200sqp_mpc_step",
     "b200sqp_plant_step", "b200sqp_closed_loop", "b200sqp_dynamics_hessian", "b200sqp_set_feature_set", "b200sqp_measure_fp64_peak", "b200sqp_set_precision", "b200sqp_set_reference_trajectory", "b200sqp_dt_equality_indices",
+    "b200sqp_adaptive_create", "b200sqp_adaptive_destroy", "b200sqp_adaptive_step", "b200sqp_adaptive_get_trajectories",
+    "b200sqp_adaptive_statistics",
 ]
 
 
@@ -431,3 +433,66 @@ class BatchedLevenbergMarquardt:
     @property
     def options(self):
         return self._opts
+
+
+class AdaptiveGridBatch:
+    """`batch` time-optimal controllers whose grids adapt independently: the reference's NonUniformFiniteDifferencesVariableGrid with
+    setGridAdaptTimeBasedSingleStep(n_max, dt_hyst_ratio), setNmin(n_min), setWarmStart(warm_start)
+    (non_uniform_finite_differences_variable_grid.h:52-54) under PredictiveController::step's OCP iterations.  Instances are bucketed by
+    grid size on the device (include/b200sqp.h, b200sqp_adaptive_*).  Setter names follow the reference's solver class."""
+
+    def __init__(self, ocp, batch, n_min, n_max, dt_hyst_ratio=0.1, warm_start=True, device=0):
+        self._lib = load_library()
+        self.ocp = ocp
+        self.batch = int(batch)
+        self.n_min, self.n_max = int(n_min), int(n_max)
+        self._opts = abi.LmOptions.defaults()
+        self._h = C.c_void_p()
+        _check(self._lib.b200sqp_adaptive_create(C.byref(ocp), C.c_int32(self.batch), C.c_int32(device), C.c_int32(n_min), C.c_int32(n_max),
+                                                 C.c_double(dt_hyst_ratio), C.c_int32(1 if warm_start else 0), C.byref(self._h)))
+
+    setIterations = BatchedLevenbergMarquardt.setIterations
+    setPenaltyWeights = BatchedLevenbergMarquardt.setPenaltyWeights
+    setWeightAdapation = BatchedLevenbergMarquardt.setWeightAdapation
+
+    def step(self, x0, xref, num_ocp_iterations=1):
+        """one controller step of every instance -> (u0 [B, nu], chi2 [B], status [B], n [B])"""
+        x0 = np.ascontiguousarray(x0, np.float64)
+        xref = np.ascontiguousarray(xref, np.float64)
+        assert x0.shape == (self.batch, self.ocp.nx) and xref.shape == x0.shape
+        u0 = np.zeros((self.batch, self.ocp.nu))
+        chi2 = np.zeros(self.batch)
+        status = np.zeros(self.batch, np.int32)
+        n = np.zeros(self.batch, np.int32)
+        _check(self._lib.b200sqp_adaptive_step(self._h, C.byref(self._opts), C.c_int32(num_ocp_iterations), _d(x0), _d(xref), _d(u0), _d(chi2),
+                                               _i(status), _i(n)))
+        return u0, chi2, status, n
+
+    def trajectories(self):
+        """-> (x [B, n_cap, nx], u [B, n_cap, nu], dt [B, n_cap], n [B]); rows beyond an instance's grid are zero"""
+        cap = max(self.n_max, self.ocp.n_grid)
+        x = np.zeros((self.batch, cap, self.ocp.nx))
+        u = np.zeros((self.batch, cap, self.ocp.nu))
+        dt = np.zeros((self.batch, cap))
+        n = np.zeros(self.batch, np.int32)
+        _check(self._lib.b200sqp_adaptive_get_trajectories(self._h, C.c_int32(cap), _d(x), _d(u), _d(dt), _i(n)))
+        return x, u, dt, n
+
+    def statistics(self):
+        b = C.c_int32(0)
+        sp, me, la = C.c_int64(0), C.c_int64(0), C.c_int64(0)
+        _check(self._lib.b200sqp_adaptive_statistics(self._h, C.byref(b), C.byref(sp), C.byref(me), C.byref(la)))
+        return dict(occupied_buckets=b.value, splits=sp.value, merges=me.value, launches=la.value)
+
+    def clear(self):
+        if self._h:
+            self._lib.b200sqp_adaptive_destroy(self._h)
+            self._h = C.c_void_p()
+
+    close = clear
+
+    def __del__(self):
+        try:
+            self.clear()
+        except Exception:
+            pass

@@ -349,6 +349,32 @@ int b200sqp_measure_fp64_peak(int32_t device, double* tflops);
 /* make the handle launch on an external stream (e.g. torch's current stream); pass NULL to restore its own */
 int b200sqp_set_stream(b200sqp_handle h, void* cuda_stream);
 
+/* ---- time-optimal grids with grid adaptation: per-instance grid size ---------------------------------------
+ * Replaces, for `batch` independent controllers, NonUniformFiniteDifferencesVariableGrid with setGridAdaptTimeBasedSingleStep(n_max,
+ * dt_hyst_ratio) + setNmin(n_min) + setWarmStart(warm_start)
+ * (src/optimal_control/include/corbo-optimal-control/structured_ocp/discretization_grids/non_uniform_finite_differences_variable_grid.h:52-54,
+ * src/optimal_control/src/structured_ocp/discretization_grids/non_uniform_finite_differences_variable_grid.cpp:176-257) under the OCP loop of
+ * PredictiveController::step (src/controllers/src/predictive_controller.cpp:66).  Instances are bucketed by grid size on the device; a
+ * bucket is an ordinary solver of `ocp` with n_grid = N, created on first use and sized for the whole batch (180 GB of HBM make that the
+ * cheap choice).  ocp->grid must be B200SQP_GRID_FD_NONUNIFORM_VARDT; ocp->n_grid is the initial size of every instance;
+ * 3 <= n_min <= n_max (the reference's default n_min = 2 leaves a single interval between two fixed states). */
+typedef struct b200sqp_adaptive* b200sqp_adaptive_handle;
+int b200sqp_adaptive_create(const b200sqp_ocp* ocp, int32_t batch, int32_t device, int32_t n_min, int32_t n_max, double dt_hyst_ratio,
+                            int32_t warm_start, b200sqp_adaptive_handle* out);
+int b200sqp_adaptive_destroy(b200sqp_adaptive_handle a);
+/* One controller step of every instance = num_ocp_iterations x StructuredOptimalControlProblem::compute: the first with new_run = 1 (start
+ * state <- x0, fixed goal components <- xref, penalty weights reset, no adaptation), the others with new_run = 0 (adaptGridTimeBasedSingleStep
+ * on the previous solution -- one inserted or removed grid point per instance -- then the solve with adapted weights).  With warm_start = 0
+ * every solve starts from initializeSequences at the instance's current grid size, as the reference does.  The very first solve of a handle
+ * always initialises.  Host pointers: x0, xref [batch*nx]; u0_out [batch*nu], chi2_out / status_out / n_out [batch] (any may be NULL). */
+int b200sqp_adaptive_step(b200sqp_adaptive_handle a, const b200sqp_lm_options* opts, int32_t num_ocp_iterations, const double* x0,
+                          const double* xref, double* u0_out, double* chi2_out, int32_t* status_out, int32_t* n_out);
+/* getStateAndControlTimeSeries of every instance, padded to n_cap grid points: x [batch][n_cap][nx] (N rows used), u [batch][n_cap][nu] and
+ * dt [batch][n_cap] (N-1 rows used), n [batch]; unused rows are zero.  n_cap must cover the largest grid of the batch. */
+int b200sqp_adaptive_get_trajectories(b200sqp_adaptive_handle a, int32_t n_cap, double* x, double* u, double* dt, int32_t* n);
+/* bookkeeping: buckets in use, grid points inserted / removed so far, kernels launched */
+int b200sqp_adaptive_statistics(b200sqp_adaptive_handle a, int32_t* occupied_buckets, int64_t* splits, int64_t* merges, int64_t* launches);
+
 #ifdef __cplusplus
 }
 #endif

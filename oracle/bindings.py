@@ -299,6 +299,44 @@ class Reference(_Checker):
             raise RuntimeError(f"corbo_ref_warm_start_shift failed: {rc}")
         return out
 
+    def adapt_once(self, ocp, x, u, dt, n_min, n_max, dt_hyst_ratio=0.1):
+        """one isolated call of NonUniformFiniteDifferencesVariableGrid::adaptGrid (TimeBasedSingleStep) on a given trajectory
+        (x [N][nx], u [N-1][nu], dt [N-1], N = ocp.n_grid) -> (x, u, dt) of the adapted grid"""
+        N = ocp.n_grid
+        x = np.ascontiguousarray(x, np.float64).reshape(N, ocp.nx)
+        u = np.ascontiguousarray(u, np.float64).reshape(N - 1, ocp.nu)
+        dt = np.ascontiguousarray(dt, np.float64).reshape(N - 1)
+        xo, uo, dto = np.zeros((N + 1, ocp.nx)), np.zeros((N + 1, ocp.nu)), np.zeros(N + 1)
+        n = C.c_int32(0)
+        f = self.lib.corbo_ref_adapt_once
+        f.restype = C.c_int
+        rc = f(C.byref(ocp), C.c_int(n_min), C.c_int(n_max), C.c_double(dt_hyst_ratio), _d(x), _d(u), _d(dt), _d(xo), _d(uo), _d(dto), C.byref(n))
+        if rc != 0:
+            raise RuntimeError(f"corbo_ref_adapt_once failed: {rc}")
+        n = n.value
+        return xo[:n].copy(), uo[:n - 1].copy(), dto[:n - 1].copy()
+
+    def adaptive_steps(self, ocp, opts, x0_seq, xref, n_min, n_max, dt_hyst_ratio=0.1, warm_start=True, num_ocp_iterations=2):
+        """Time-optimal MPC with the reference's grid adaptation (NonUniformFiniteDifferencesVariableGrid::adaptGridTimeBasedSingleStep)
+        for one instance: x0_seq [steps][nx] -> (n_trace [steps][num_ocp_iterations], u0 [steps][nu], x [N][nx], u [N-1][nu], dt [N-1])"""
+        x0_seq = np.ascontiguousarray(x0_seq, np.float64).reshape(-1, ocp.nx)
+        steps = x0_seq.shape[0]
+        n_trace = np.zeros((steps, num_ocp_iterations), np.int32)
+        u0 = np.zeros((steps, ocp.nu))
+        cap = max(n_max, ocp.n_grid) + 2
+        x = np.zeros((cap, ocp.nx))
+        u = np.zeros((cap, ocp.nu))
+        dt = np.zeros(cap)
+        f = self.lib.corbo_ref_adaptive_steps
+        f.restype = C.c_int
+        rc = f(C.byref(ocp), C.byref(opts), C.c_int(n_min), C.c_int(n_max), C.c_double(dt_hyst_ratio), C.c_int(1 if warm_start else 0),
+               C.c_int(num_ocp_iterations), C.c_int(steps), _d(x0_seq), _d(np.ascontiguousarray(xref, np.float64)), _i(n_trace), _d(u0), _d(x), _d(u),
+               _d(dt))
+        if rc != 0:
+            raise RuntimeError(f"corbo_ref_adaptive_steps failed: {rc}")
+        n = int(n_trace[-1, -1])
+        return n_trace, u0, x[:n].copy(), u[:n - 1].copy(), dt[:n - 1].copy()
+
     def known_answer(self, case_id, stage=0):
         return _known_answer(self.lib, "corbo_ref_known_answer", case_id, stage)
 

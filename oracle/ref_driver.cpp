@@ -841,6 +841,89 @@ int corbo_ref_closed_loop_plant(const b200sqp_ocp* d, const b200sqp_lm_options* 
     return 0;
 }
 
+// One call of the reference's grid adaptation in isolation: initialise the grid (N = n_grid), overwrite its vertices with the given
+// trajectory (x_in [N][nx] incl. start and final state, u_in [N-1][nu], dt_in [N-1]), run the grid update of a continued run
+// (new_run = false, warm start on -> adaptGrid, no re-initialisation) and read the vertices back (capacity N + 1 rows); *n_out = new N.
+int corbo_ref_adapt_once(const b200sqp_ocp* d, int n_min, int n_max, double dt_hyst_ratio, const double* x_in, const double* u_in, const double* dt_in,
+                         double* x_out, double* u_out, double* dt_out, int32_t* n_out)
+{
+    if (d->grid != B200SQP_GRID_FD_NONUNIFORM_VARDT) return -9;
+    b200sqp_lm_options o = {0, 2, 2, 2, 1, 1, 1, 500, 500, 500};
+    RefOcp r;
+    if (!buildOcp(*d, o, r)) return -1;
+    auto* g = dynamic_cast<NuGridProbe*>(r.grid.get());
+    if (!g) return -9;
+    g->setGridAdaptTimeBasedSingleStep(n_max, dt_hyst_ratio);
+    g->setNmin(n_min);
+    g->setWarmStart(true);
+    const int N = d->n_grid;
+    if (!prepare(r, *d, x_in, x_in + (size_t)(N - 1) * d->nx, true, nullptr)) return -2;
+    for (int k = 0; k < N - 1; ++k)
+    {
+        g->xs()[k].values() = Eigen::Map<const Eigen::VectorXd>(x_in + (size_t)k * d->nx, d->nx);
+        g->us()[k].values() = Eigen::Map<const Eigen::VectorXd>(u_in + (size_t)k * d->nu, d->nu);
+        g->dts()[k].value() = dt_in[k];
+    }
+    g->xf().values() = Eigen::Map<const Eigen::VectorXd>(x_in + (size_t)(N - 1) * d->nx, d->nx);
+    if (!prepare(r, *d, x_in, x_in + (size_t)(N - 1) * d->nx, false, nullptr)) return -3;
+    const int n = g->getN();
+    *n_out      = n;
+    for (int k = 0; k < n - 1; ++k)
+    {
+        std::memcpy(x_out + (size_t)k * d->nx, g->xs()[k].values().data(), sizeof(double) * d->nx);
+        std::memcpy(u_out + (size_t)k * d->nu, g->us()[k].values().data(), sizeof(double) * d->nu);
+        dt_out[k] = g->dts()[k].value();
+    }
+    std::memcpy(x_out + (size_t)(n - 1) * d->nx, g->xf().values().data(), sizeof(double) * d->nx);
+    return 0;
+}
+
+// Time-optimal MPC with grid adaptation, the reference's own classes: a NonUniformFiniteDifferencesVariableGrid with
+// setGridAdaptTimeBasedSingleStep(n_max, dt_hyst_ratio) and setNmin(n_min) (non_uniform_finite_differences_variable_grid.cpp:45-50,206-257)
+// under the OCP loop of PredictiveController::step (predictive_controller.cpp:66): num_ocp_iterations computes per controller step, the
+// first with new_run = true (no adaptation, start state overwritten), the others with new_run = false (adaptGrid before the solve).
+// warm_start = 0: the grid re-initialises the trajectories at the adapted size before every solve (non_uniform_full_discretization_grid_base.cpp:90-101).
+// x0_seq [steps][nx]: the measured state of every controller step; xref [nx] static reference (goal).
+// n_trace [steps*num_ocp_iterations]: grid size N each solve ran on; u0_out [steps][nu]: first control after each step;
+// x_last [n_max][nx], u_last [n_max][nu], dt_last [n_max]: the final trajectories (N = last n_trace entry; x has N rows, u and dt N-1).
+int corbo_ref_adaptive_steps(const b200sqp_ocp* d, const b200sqp_lm_options* o, int n_min, int n_max, double dt_hyst_ratio, int warm_start,
+                             int num_ocp_iterations, int steps, const double* x0_seq, const double* xref, int32_t* n_trace, double* u0_out,
+                             double* x_last, double* u_last, double* dt_last)
+{
+    if (d->grid != B200SQP_GRID_FD_NONUNIFORM_VARDT) return -9;
+    RefOcp r;
+    if (!buildOcp(*d, *o, r)) return -1;
+    auto* g = dynamic_cast<NuGridProbe*>(r.grid.get());
+    if (!g) return -9;
+    g->setGridAdaptTimeBasedSingleStep(n_max, dt_hyst_ratio);
+    g->setNmin(n_min);
+    g->setWarmStart(warm_start != 0);
+    StaticReference xr(Eigen::VectorXd(Eigen::Map<const Eigen::VectorXd>(xref, d->nx)));
+    ZeroReference uref(d->nu);
+    for (int s = 0; s < steps; ++s)
+    {
+        Eigen::VectorXd x = Eigen::Map<const Eigen::VectorXd>(x0_seq + (size_t)s * d->nx, d->nx);
+        for (int i = 0; i < num_ocp_iterations; ++i)
+        {
+            r.ocp->compute(x, xr, uref, nullptr, Time(s * d->dt_ref), i == 0);  // the solver status is not part of this check
+            n_trace[(size_t)s * num_ocp_iterations + i] = g->getN();
+        }
+        Eigen::VectorXd u(d->nu);
+        if (!r.ocp->getFirstControlInput(u)) return -3;
+        std::memcpy(u0_out + (size_t)s * d->nu, u.data(), sizeof(double) * d->nu);
+    }
+    const int n = g->getN();
+    if (n > n_max + 1) return -10;
+    for (int k = 0; k < n - 1; ++k)
+    {
+        std::memcpy(x_last + (size_t)k * d->nx, g->xs()[k].values().data(), sizeof(double) * d->nx);
+        std::memcpy(u_last + (size_t)k * d->nu, g->us()[k].values().data(), sizeof(double) * d->nu);
+        dt_last[k] = g->dts()[k].value();
+    }
+    std::memcpy(x_last + (size_t)(n - 1) * d->nx, g->xf().values().data(), sizeof(double) * d->nx);
+    return 0;
+}
+
 // The reference's known-answer solver tests (optimization/test/test_levenberg_marquardt_sparse.cpp:72-296, excluded from its build)
 // run against the compiled reference: SimpleOptimizationProblemWithCallbacks + LevenbergMarquardtSparse, 100 iterations.
 // the reference's own getLinearA / getLinearB with its ForwardDifferences (method 0, the default) or CentralDifferences (method 1)

@@ -1,0 +1,101 @@
+"""Grid adaptation of the time-optimal grid, CPU side: the numpy restatement (oracle/grid_adaptation.py) against the
+compiled reference's NonUniformFiniteDifferencesVariableGrid::adaptGridTimeBasedSingleStep run in isolation, the reference's adaptive MPC
+loop as the GPU tests use it, and the argument checks of the C ABI that need no device."""
+import numpy as np
+import pytest
+
+from control_box_rst_b200 import _abi as abi
+from control_box_rst_b200 import problems, solver
+from oracle import bindings, grid_adaptation as ga
+
+
+@pytest.fixture(scope="module")
+def reference():
+    if not bindings.Reference.available():
+        pytest.skip("compiled reference not present (oracle/_ref)")
+    return bindings.Reference()
+
+
+def _trajectory(rng, N, nx, nu, dt_profile):
+    return rng.uniform(-1, 1, (N, nx)), rng.uniform(-1, 1, (N - 1, nu)), np.array(dt_profile, float)
+
+
+@pytest.mark.parametrize("case", ["split_first", "split_middle", "merge_first", "merge_middle", "none", "split_blocked_by_n_max",
+                                  "merge_blocked_by_n_min", "large_then_small", "small_then_large", "at_thresholds"])
+def test_restatement_matches_the_compiled_reference_bit_for_bit(reference, case):
+    N, dt_ref, hyst = 7, 0.1, 0.1
+    n_min, n_max = 3, 12
+    base = [0.1] * (N - 1)
+    prof = {
+        "split_first": [0.2] + base[1:],
+        "split_middle": base[:2] + [0.1101] + base[3:],
+        "merge_first": [0.05] + base[1:],
+        "merge_middle": base[:3] + [0.0899] + base[4:],
+        "none": [0.105, 0.095, 0.1, 0.109, 0.091, 0.1],
+        "split_blocked_by_n_max": base[:2] + [0.3] + base[3:],
+        "merge_blocked_by_n_min": base[:2] + [0.01] + base[3:],
+        "large_then_small": [0.1, 0.15, 0.02, 0.1, 0.1, 0.1],
+        "small_then_large": [0.1, 0.02, 0.15, 0.1, 0.1, 0.1],
+        # dt_ref (1 +- hyst) themselves change nothing (strict comparisons), one ulp beyond does
+        "at_thresholds": [0.1 * (1.0 + 0.1), 0.1 * (1.0 - 0.1), np.nextafter(0.1 * (1.0 - 0.1), 0.0), 0.1, 0.1, 0.1],
+    }[case]
+    if case == "split_blocked_by_n_max":
+        n_max = N
+    if case == "merge_blocked_by_n_min":
+        n_min = N
+    ocp = problems.unicycle_time_optimal(N, dt_ref)
+    rng = np.random.default_rng(3)
+    x, u, dt = _trajectory(rng, N, ocp.nx, ocp.nu, prof)
+    xr, ur, dtr = reference.adapt_once(ocp, x, u, dt, n_min, n_max, hyst)
+    xo, uo, dto, kind, i = ga.adapt_time_based_single_step(x, u, dt, n_min, n_max, dt_ref, hyst)
+    assert xr.shape == xo.shape and np.array_equal(xr, xo)
+    assert np.array_equal(ur, uo) and np.array_equal(dtr, dto)
+    expect = {"split_first": (ga.SPLIT, 0), "split_middle": (ga.SPLIT, 2), "merge_first": (ga.MERGE, 0), "merge_middle": (ga.MERGE, 3),
+              "none": (ga.NONE, -1), "split_blocked_by_n_max": (ga.NONE, -1), "merge_blocked_by_n_min": (ga.NONE, -1),
+              "large_then_small": (ga.SPLIT, 1), "small_then_large": (ga.MERGE, 1), "at_thresholds": (ga.MERGE, 2)}[case]
+    assert (kind, i) == expect
+
+
+def test_split_keeps_the_interval_dt_and_halves_only_the_new_one(reference):
+    """the quirk the device reproduces: after a split the total time GROWS by dt_i / 2"""
+    ocp = problems.unicycle_time_optimal(5, 0.1)
+    rng = np.random.default_rng(0)
+    x, u, dt = _trajectory(rng, 5, 3, 2, [0.1, 0.4, 0.1, 0.1])
+    xr, ur, dtr = reference.adapt_once(ocp, x, u, dt, 3, 10, 0.1)
+    assert np.array_equal(dtr, [0.1, 0.4, 0.2, 0.1, 0.1])
+    assert np.array_equal(xr[2], 0.5 * (x[1] + x[2])) and np.array_equal(ur[2], u[1])
+
+
+def test_reference_adaptive_loop_obeys_its_own_rules(reference):
+    ocp = problems.unicycle_time_optimal(16, 0.1)
+    opts = abi.LmOptions.defaults(iterations=6, weights=(2.0, 2.0, 2.0))
+    steps, m = 4, 3
+    for goal, direction in (([0.3, 0.1, 0.2], -1), ([4.0, 1.0, 0.3], +1)):
+        x0_seq = np.zeros((steps, 3))
+        for warm in (True, False):
+            n_trace, u0, x, u, dt = reference.adaptive_steps(ocp, opts, x0_seq, np.array(goal), 3, 26, 0.1, warm, m)
+            flat = np.concatenate([[16], n_trace.ravel()])
+            assert (np.abs(np.diff(flat)) <= 1).all()                      # one grid point per OCP iteration
+            assert (n_trace[1:, 0] == n_trace[:-1, -1]).all() and n_trace[0, 0] == 16   # a new run does not adapt
+            assert np.sign(n_trace[-1, -1] - 16) == direction
+            assert x.shape == (n_trace[-1, -1], 3) and dt.shape == (n_trace[-1, -1] - 1,)
+            assert np.array_equal(x[-1], goal)
+            # a removed grid point 0 (continued run) promotes the old x_1 to start state until the next measurement: only a growing
+            # warm-started grid is sure to still start at the measured state
+            if direction > 0 or not warm:
+                assert np.array_equal(x[0], x0_seq[-1])
+
+
+def test_adaptive_front_end_checks_arguments_and_needs_a_device():
+    ocp = problems.unicycle_time_optimal(16, 0.1)
+    with pytest.raises(solver.B200SqpError) as e:
+        solver.AdaptiveGridBatch(problems.van_der_pol(20), 4, 3, 30)
+    assert e.value.code == abi.ERR_UNSUPPORTED
+    for bad in (dict(n_min=2, n_max=30), dict(n_min=10, n_max=9), dict(n_min=3, n_max=30, dt_hyst_ratio=1.0)):
+        with pytest.raises(solver.B200SqpError) as e:
+            solver.AdaptiveGridBatch(ocp, 4, **bad)
+        assert e.value.code == abi.ERR_INVALID
+    if not solver.device_available():
+        with pytest.raises(solver.B200SqpError) as e:
+            solver.AdaptiveGridBatch(ocp, 4, 3, 30)
+        assert e.value.code == abi.ERR_NO_DEVICE  # no CPU fallback
