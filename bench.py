@@ -357,6 +357,67 @@ def other_configs(device, stream, hbm_peak, fp64_peak, with_cpu):
     return out
 
 
+def adaptive_config(device, with_cpu):
+    """SURVEY 8f row 2 on BASELINE configs[2]'s controller: 4096 time-optimal unicycle controllers whose grids adapt independently
+    (NonUniformFiniteDifferencesVariableGrid::adaptGridTimeBasedSingleStep, 3 OCP iterations per controller step), bucketed by grid size
+    on the device.  Timed end to end through b200sqp_adaptive_step with host buffers (host clock: the buckets solve on their own streams)."""
+    import torch
+
+    from control_box_rst_b200 import solver
+
+    try:
+        ocp, kw, B = problems.config(2)
+        iterations, m, steps = kw["iterations"], 3, 4
+        rng = np.random.default_rng(77)
+        r, ang = rng.uniform(0.5, 9.0, B), rng.uniform(-1.0, 1.0, B)
+        x0 = np.zeros((B, 3))
+        xf = np.stack([r * np.cos(ang), r * np.sin(ang), ang + rng.uniform(-0.5, 0.5, B)], axis=1)
+        ad = solver.AdaptiveGridBatch(ocp, B, 5, 100, 0.1, warm_start=True, device=device)
+        ad.setIterations(iterations)
+        ad.setPenaltyWeights(*kw["weights"])
+        ad.reserve()  # all buckets up front: a bucket allocates for the whole batch
+        flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=f"cuda:{device}")
+        total, n_hist = 0.0, []
+        for it in range(steps + 3):  # three warm-up steps: they also create the buckets the grids spread into
+            flush.zero_()
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            u0, chi2, status, n = ad.step(x0 + 0.01 * it * (xf - x0), xf, num_ocp_iterations=m)
+            dt = time.perf_counter() - t0
+            if it >= 3:
+                total += dt
+            n_hist.append([int(n.min()), float(n.mean()), int(n.max())])
+        stats = ad.statistics()
+        ad.close()
+        del flush
+        torch.cuda.empty_cache()
+        entry = {"workload": f"unicycle_time_optimal_adaptive_grid_n{ocp.n_grid}_b{B}_it{iterations}x{m}", "dtype": "f64",
+                 "value": B * iterations * m * steps / total, "unit": UNIT, "steps": steps, "ms_per_step": total / steps * 1e3,
+                 "ocp_iterations_per_step": m, "timing": "host clock around b200sqp_adaptive_step (H2D states, adaptation, solves, D2H controls)",
+                 "grid_size_min_mean_max": n_hist[-1], "occupied_buckets": stats["occupied_buckets"], "splits": stats["splits"],
+                 "merges": stats["merges"]}
+        if with_cpu:
+            from oracle import bindings  # the one other place bench.py may use oracle/: the reported CPU baseline
+
+        if with_cpu and bindings.Reference.available():
+            ref = bindings.Reference()
+            opts = abi.LmOptions.defaults(iterations=iterations, weights=kw["weights"])
+            sample = 8
+            t0 = time.perf_counter()
+            done = 0
+            for i in range(sample):
+                seq = np.stack([x0[i] + 0.01 * s * (xf[i] - x0[i]) for s in range(2)])
+                # forked: the reference's adaptation has inputs it does not survive (oracle/bindings.py isolated)
+                if bindings.isolated(lambda: ref.adaptive_steps(ocp, opts, seq, xf[i], 5, 100, 0.1, True, m)[0]) is not None:
+                    done += 1
+            dt = time.perf_counter() - t0
+            entry["cpu_baseline"] = {"value": done * iterations * m * 2 / dt, "unit": UNIT, "cores": 1, "kind": "reference",
+                                     "sample": f"{done} instances x 2 controller steps x {m} OCP iterations, one thread, wall clock incl. grid update"}
+        return entry
+    except Exception as exc:
+        return {"error": f"{type(exc).__name__}: {exc}"}
+
+
 def main_b200(args):
     import torch
     import torch.distributed as dist
@@ -595,6 +656,7 @@ def main_b200(args):
             del flush
             torch.cuda.empty_cache()
             line["configs"] = other_configs(local_rank, stream, peak, fp64_peak, not args.no_cpu_baseline)
+            line["configs"]["2_adaptive"] = adaptive_config(local_rank, not args.no_cpu_baseline)
             line["e2e_plugin"] = plugin_e2e(B, iterations)
         emit(line)
     if use_p2p:

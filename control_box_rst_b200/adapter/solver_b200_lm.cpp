@@ -644,6 +644,57 @@ bool SolverB200Lm::solveBatch(const std::vector<OptimizationProblemInterface*>& 
 {
     const int B = (int)problems.size();
     if (B == 0) return true;
+    // resetWeights / adaptWeights (levenberg_marquardt_sparse.cpp:83-86, 264-287) once per call: every object of the batch is in the
+    // same OCP iteration.  The device gets the resulting weights as the initial weights of a new run.
+    if (new_run || !_weights_initialised)
+    {
+        _w_eq = _opts.weight_eq, _w_ineq = _opts.weight_ineq, _w_bounds = _opts.weight_bounds;
+    }
+    else
+    {
+        _w_eq     = std::min(_w_eq * _opts.adapt_factor_eq, _opts.adapt_max_eq);
+        _w_ineq   = std::min(_w_ineq * _opts.adapt_factor_ineq, _opts.adapt_max_ineq);
+        _w_bounds = std::min(_w_bounds * _opts.adapt_factor_bounds, _opts.adapt_max_bounds);
+    }
+    _weights_initialised = true;
+    b200sqp_lm_options opts = _opts;
+    opts.weight_eq = _w_eq, opts.weight_ineq = _w_ineq, opts.weight_bounds = _w_bounds;
+
+    // bucket by grid size (same OCP kind: the parameter dimension identifies N)
+    std::map<int, std::vector<int>> groups;
+    for (int i = 0; i < B; ++i) groups[problems[i]->getParameterDimension()].push_back(i);
+    if (groups.size() == 1) return solveUniform(problems, opts, statuses, obj_values);
+    if (statuses) statuses->assign(B, SolverStatus::Error);
+    if (obj_values) obj_values->assign(B, -1.0);
+    for (auto& g : groups)
+    {
+        std::shared_ptr<SolverB200Lm>& child = _by_size[g.first];
+        if (!child) child = std::make_shared<SolverB200Lm>();
+        child->_dynamics = _dynamics, child->_dynamics_parameters = _dynamics_parameters, child->_collocation = _collocation;
+        child->_integrator = _integrator, child->_stage_cost = _stage_cost, child->_final_cost = _final_cost;
+        child->_final_constraint = _final_constraint, child->_xref = _xref, child->_device = _device;
+        std::vector<OptimizationProblemInterface*> sub;
+        for (int i : g.second) sub.push_back(problems[i]);
+        std::vector<SolverStatus> st;
+        std::vector<double> obj;
+        if (!child->solveUniform(sub, opts, &st, &obj))
+        {
+            fail("bucket of parameter dimension " + std::to_string(g.first) + ": " + child->lastError());
+            return false;
+        }
+        for (size_t j = 0; j < g.second.size(); ++j)
+        {
+            if (statuses) (*statuses)[g.second[j]] = st[j];
+            if (obj_values) (*obj_values)[g.second[j]] = obj[j];
+        }
+    }
+    return true;
+}
+
+bool SolverB200Lm::solveUniform(const std::vector<OptimizationProblemInterface*>& problems, const b200sqp_lm_options& opts,
+                                std::vector<SolverStatus>* statuses, std::vector<double>* obj_values)
+{
+    const int B = (int)problems.size();
     std::vector<double> x0_first, xref_first;
     if (!upload(*problems[0], B, &x0_first, &xref_first))
     {
@@ -694,7 +745,7 @@ bool SolverB200Lm::solveBatch(const std::vector<OptimizationProblemInterface*>& 
     }
     std::vector<int32_t> status(B);
     std::vector<double> chi2(B);
-    if (b200sqp_solve(_handle, &_opts, new_run ? 1 : 0, status.data(), chi2.data()) != 0 || b200sqp_get_params(_handle, params.data()) != 0)
+    if (b200sqp_solve(_handle, &opts, 1, status.data(), chi2.data()) != 0 || b200sqp_get_params(_handle, params.data()) != 0)
     {
         fail(std::string("solve failed: ") + b200sqp_last_error());
         return false;

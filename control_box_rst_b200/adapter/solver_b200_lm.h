@@ -23,6 +23,7 @@
 #include <corbo-optimization/solver/nlp_solver_interface.h>
 #include <corbo-systems/system_dynamics_interface.h>
 
+#include <map>
 #include <memory>
 #include <string>
 #include <vector>
@@ -67,8 +68,10 @@ class SolverB200Lm : public NlpSolverInterface
     void setStateReference(ReferenceTrajectoryInterface::Ptr xref) { _xref = xref; }
     void setDevice(int device) { _device = device; }
 
-    // ---- batch front-end: B OCP objects of identical structure, one device call (SURVEY.md section 7 "hard parts") ------------------
+    // ---- batch front-end: B OCP objects, one device call per structure (SURVEY.md section 7 "hard parts") ---------------------------
     // problems[i] hold the initial parameters before and the optimised ones after the call; statuses/obj_values may be null.
+    // The objects are OCPs of one kind; their grids may differ in size (time-optimal grids after the reference's own adaptGrid,
+    // SURVEY.md section 8f row 2): the batch is then bucketed by structure and every bucket keeps its own device handle.
     bool solveBatch(const std::vector<OptimizationProblemInterface*>& problems, bool new_run, std::vector<SolverStatus>* statuses,
                     std::vector<double>* obj_values);
 
@@ -83,6 +86,8 @@ class SolverB200Lm : public NlpSolverInterface
     double lastSolveMilliseconds() const;
 
  private:
+    bool solveUniform(const std::vector<OptimizationProblemInterface*>& problems, const b200sqp_lm_options& opts, std::vector<SolverStatus>* statuses,
+                      std::vector<double>* obj_values);
     bool describe(OptimizationProblemInterface& problem, b200sqp_ocp& ocp, std::vector<double>& x0, std::vector<double>& xref);
     bool upload(OptimizationProblemInterface& problem, int batch, std::vector<double>* x0_out = nullptr, std::vector<double>* xref_out = nullptr);
     bool instanceData(OptimizationProblemInterface& problem, double* x0, double* xref, std::string& error) const;
@@ -108,6 +113,11 @@ class SolverB200Lm : public NlpSolverInterface
     FinalStageConstraint::Ptr _final_constraint;
     ReferenceTrajectoryInterface::Ptr _xref;
     std::vector<int32_t> _col_ptr, _row_idx;  // CSC pattern of the combined Jacobian of the uploaded structure
+    // penalty weights live in the solver object like the reference's (_weight_eq, ...; levenberg_marquardt_sparse.cpp:83-86, 264-287):
+    // they survive a change of structure (a grid that was adapted between two solves of one run)
+    double _w_eq = 0, _w_ineq = 0, _w_bounds = 0;
+    bool _weights_initialised = false;
+    std::map<int, std::shared_ptr<SolverB200Lm>> _by_size;  // buckets of a batch with mixed grid sizes, keyed by parameter dimension
 };
 
 FACTORY_REGISTER_NLP_SOLVER(SolverB200Lm)

@@ -1347,6 +1347,7 @@ struct b200sqp_adaptive
     bool first_run = true, weights_initialised = false;
     double w_eq = 2, w_ineq = 2, w_b = 2;
     int64_t launches = 0, splits = 0, merges = 0;
+    std::vector<int> last_interval_changes;  // per instance: adaptations that changed the last interval (undefined in the reference)
     std::vector<void*> allocations;
 };
 
@@ -1430,6 +1431,7 @@ int adaptiveAdapt(b200sqp_adaptive* a, bool* changed)
         if (dst < 0 || dst >= (int)a->bucket.size()) return fail(B200SQP_ERR_INVALID, "grid adaptation left the bucket range");
         a->splits += type == ADAPT_SPLIT;
         a->merges += type == ADAPT_MERGE;
+        if (type != ADAPT_NONE && (dec >> 2) == a->n_lo + src - 2) a->last_interval_changes[i] += 1;  // interval K - 1 of a grid of K + 1 points
         int rc = adaptiveEnsureBucket(a, dst);
         if (rc) return rc;
         a->hp_plan[i]         = src;
@@ -1482,6 +1484,7 @@ int b200sqp_adaptive_create(const b200sqp_ocp* ocp, int32_t batch, int32_t devic
     a->views.assign(nbuckets, AdaptBucketView{});
     a->bucket_of.assign(batch, ocp->n_grid - a->n_lo);
     a->slot_of.resize(batch);
+    a->last_interval_changes.assign(batch, 0);
     for (int i = 0; i < batch; ++i) a->slot_of[i] = i;
     auto destroy_and_fail = [&](int code, const std::string& msg) {
         b200sqp_adaptive_destroy(a);
@@ -1633,6 +1636,25 @@ int b200sqp_adaptive_step(b200sqp_adaptive_handle a, const b200sqp_lm_options* o
     CUDA_TRY(cudaStreamSynchronize(a->stream));
     if (n_out)
         for (int i = 0; i < B; ++i) n_out[i] = a->n_lo + a->bucket_of[i];
+    return B200SQP_OK;
+}
+
+int b200sqp_adaptive_last_interval_changes(b200sqp_adaptive_handle a, int32_t* count)
+{
+    if (!a || !count) return fail(B200SQP_ERR_INVALID, "null argument");
+    for (int i = 0; i < a->B; ++i) count[i] = a->last_interval_changes[i];
+    return B200SQP_OK;
+}
+
+int b200sqp_adaptive_reserve(b200sqp_adaptive_handle a, int32_t n_from, int32_t n_to)
+{
+    if (!a || n_from > n_to) return fail(B200SQP_ERR_INVALID, "bad argument");
+    CUDA_TRY(cudaSetDevice(a->device));
+    for (int n = std::max(n_from, a->n_lo); n <= std::min(n_to, a->n_hi); ++n)
+    {
+        int rc = adaptiveEnsureBucket(a, n - a->n_lo);
+        if (rc) return rc;
+    }
     return B200SQP_OK;
 }
 

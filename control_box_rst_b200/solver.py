@@ -30,7 +30,7 @@ ABI_SYMBOLS = [
     "b200sqp_peer_export", "b200sqp_peer_attach", "b200sqp_peer_wait", "b200sqp_peer_gathered", "b200sqp_peer_detach", "b200sqp_peer_status", "b200sqp_linearize_dynamics", "b200sqp_warm_start_shift", "b200sqp_mpc_step",
     "b200sqp_plant_step", "b200sqp_closed_loop", "b200sqp_dynamics_hessian", "b200sqp_set_feature_set", "b200sqp_measure_fp64_peak", "b200sqp_set_precision", "b200sqp_set_reference_trajectory", "b200sqp_dt_equality_indices",
     "b200sqp_adaptive_create", "b200sqp_adaptive_destroy", "b200sqp_adaptive_step", "b200sqp_adaptive_get_trajectories",
-    "b200sqp_adaptive_statistics",
+    "b200sqp_adaptive_statistics", "b200sqp_adaptive_reserve", "b200sqp_adaptive_last_interval_changes",
 ]
 
 
@@ -467,6 +467,17 @@ class AdaptiveGridBatch:
         _check(self._lib.b200sqp_adaptive_step(self._h, C.byref(self._opts), C.c_int32(num_ocp_iterations), _d(x0), _d(xref), _d(u0), _d(chi2),
                                                _i(status), _i(n)))
         return u0, chi2, status, n
+
+    def reserve(self, n_from=None, n_to=None):
+        """create the buckets of these grid sizes now (default: the whole reachable range) instead of on first use"""
+        _check(self._lib.b200sqp_adaptive_reserve(self._h, C.c_int32(self.n_min if n_from is None else n_from),
+                                                  C.c_int32(self.n_max if n_to is None else n_to)))
+
+    def last_interval_changes(self):
+        """[B]: adaptations per instance that changed its last interval -- inputs the reference has no defined answer for"""
+        out = np.zeros(self.batch, np.int32)
+        _check(self._lib.b200sqp_adaptive_last_interval_changes(self._h, _i(out)))
+        return out
 
     def trajectories(self):
         """-> (x [B, n_cap, nx], u [B, n_cap, nu], dt [B, n_cap], n [B]); rows beyond an instance's grid are zero"""

@@ -369,6 +369,14 @@ int b200sqp_adaptive_destroy(b200sqp_adaptive_handle a);
  * always initialises.  Host pointers: x0, xref [batch*nx]; u0_out [batch*nu], chi2_out / status_out / n_out [batch] (any may be NULL). */
 int b200sqp_adaptive_step(b200sqp_adaptive_handle a, const b200sqp_lm_options* opts, int32_t num_ocp_iterations, const double* x0,
                           const double* xref, double* u0_out, double* chi2_out, int32_t* status_out, int32_t* n_out);
+/* count [batch]: how many adaptations of each instance so far changed its LAST interval.  The reference has no defined answer there (it
+ * indexes one past the end of its vertex vectors: non_uniform_finite_differences_variable_grid.cpp:225 `_x_seq[i + 1]`, :237
+ * `_dt_seq[i + 1]` with i = size - 1 -- stale memory at best, heap corruption at worst); the device uses x_f as the right neighbour of a
+ * split last interval and drops the dt of a removed one.  Parity with the reference is claimed for instances whose count is 0. */
+int b200sqp_adaptive_last_interval_changes(b200sqp_adaptive_handle a, int32_t* count);
+/* create the buckets of grid sizes n_from..n_to (clipped to the reachable range) now instead of on first use: a bucket allocates its
+ * device state for the whole batch, which a latency-sensitive control loop wants outside its first steps */
+int b200sqp_adaptive_reserve(b200sqp_adaptive_handle a, int32_t n_from, int32_t n_to);
 /* getStateAndControlTimeSeries of every instance, padded to n_cap grid points: x [batch][n_cap][nx] (N rows used), u [batch][n_cap][nu] and
  * dt [batch][n_cap] (N-1 rows used), n [batch]; unused rows are zero.  n_cap must cover the largest grid of the batch. */
 int b200sqp_adaptive_get_trajectories(b200sqp_adaptive_handle a, int32_t n_cap, double* x, double* u, double* dt, int32_t* n);

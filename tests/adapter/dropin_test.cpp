@@ -762,6 +762,118 @@ int main(int argc, char** argv)
             ++failures;
         }
     }
+    // ---- 12. grid adaptation: the reference's own NonUniformFiniteDifferencesVariableGrid adapts the grid
+    //      (setGridAdaptTimeBasedSingleStep) between the OCP iterations of a controller step; the plugin follows the changing structure
+    //      with the penalty weights carried over, and solveBatch buckets objects of different grid sizes
+    {
+        ZeroReference xref3(3), uref2(2);
+        auto adaptive = [](NlpSolverInterface::Ptr solver) {
+            TebLoop l = makeTebUnicycle(solver, 14);
+            auto* grid = dynamic_cast<NonUniformFiniteDifferencesVariableGrid*>(l.ocp->getDiscretizationGrid().get());
+            grid->setGridAdaptTimeBasedSingleStep(30, 0.1);
+            grid->setNmin(3);
+            grid->setWarmStart(true);
+            l.ocp->initialize();
+            return l;
+        };
+        // (a) one OCP with the plugin as its solver, 3 controller steps x 3 OCP iterations
+        auto s_ref = std::make_shared<LevenbergMarquardtSparse>();
+        auto s_dev = std::make_shared<SolverB200Lm>();
+        s_ref->setIterations(6);
+        s_dev->setIterations(6);
+        TebLoop lr = adaptive(s_ref), lb = adaptive(s_dev);
+        Eigen::VectorXd x0(3);
+        x0 << 3.1, -1.2, 0.5;
+        double worst12 = 0;
+        bool ok12      = true;
+        int n_first = 0, n_last = 0;
+        for (int s = 0; s < 3; ++s)
+        {
+            for (int it = 0; it < 3; ++it)
+            {
+                ok12 = lr.ocp->compute(x0, xref3, uref2, nullptr, Time(0.1 * s), it == 0) && ok12;
+                ok12 = lb.ocp->compute(x0, xref3, uref2, nullptr, Time(0.1 * s), it == 0) && ok12;
+                const int nr = lr.ocp->getDiscretizationGrid()->getN(), nb = lb.ocp->getDiscretizationGrid()->getN();
+                if (s == 0 && it == 0) n_first = nr;
+                n_last = nr;
+                if (nr != nb)
+                {
+                    std::printf("FAIL: grid sizes diverge (step %d, OCP iteration %d): %d vs %d\n", s, it, nr, nb);
+                    ok12 = false;
+                    break;
+                }
+                worst12 = std::max(worst12, relDiff(paramsOf(*lr.problem), paramsOf(*lb.problem)));
+            }
+            x0[0] -= 0.05;
+        }
+        std::printf("adaptive time-optimal unicycle through the plugin: grid %d -> %d points over 9 solves, max relative trajectory difference "
+                    "vs reference = %.3e\n", n_first, n_last, worst12);
+        if (!ok12 || n_first == n_last || !(worst12 <= 1e-4))
+        {
+            std::printf("FAIL: grid adaptation through the plugin (ok=%d, %s)\n", (int)ok12, s_dev->lastError().c_str());
+            ++failures;
+        }
+        // (b) six objects whose grids drift apart, one solveBatch per OCP iteration
+        const int Ba = 6;
+        const double start_x[Ba] = {0.4, 0.9, 1.5, 2.2, 3.0, 3.8};
+        std::vector<TebLoop> refs, devs;
+        std::vector<OptimizationProblemInterface*> probs;
+        std::vector<Eigen::VectorXd> starts;
+        for (int i = 0; i < Ba; ++i)
+        {
+            Eigen::VectorXd xs(3);
+            xs << start_x[i], 0.3 * (i % 3) - 0.3, 0.2 * i - 0.4;
+            starts.push_back(xs);
+            auto si = std::make_shared<LevenbergMarquardtSparse>();
+            si->setIterations(6);
+            refs.push_back(adaptive(si));
+            auto dummy = std::make_shared<LevenbergMarquardtSparse>();
+            dummy->setIterations(0);
+            devs.push_back(adaptive(dummy));
+            probs.push_back(devs.back().problem.get());
+        }
+        auto batch12 = std::make_shared<SolverB200Lm>();
+        batch12->setIterations(6);
+        batch12->setSystemDynamics(devs[0].dynamics);
+        batch12->setStageCost(std::make_shared<MinimumTime>(true));
+        double worst12b = 0;
+        bool ok12b      = true;
+        int n_min_seen = 1000, n_max_seen = 0;
+        for (int s = 0; s < 2 && ok12b; ++s)
+            for (int it = 0; it < 3 && ok12b; ++it)
+            {
+                for (int i = 0; i < Ba; ++i)
+                {
+                    ok12b = refs[i].ocp->compute(starts[i], xref3, uref2, nullptr, Time(0.1 * s), it == 0) && ok12b;
+                    ok12b = devs[i].ocp->compute(starts[i], xref3, uref2, nullptr, Time(0.1 * s), it == 0) && ok12b;  // grid update + adaptation only
+                }
+                if (!batch12->solveBatch(probs, it == 0, nullptr, nullptr))
+                {
+                    std::printf("FAIL: solveBatch over mixed grid sizes (step %d, OCP iteration %d): %s\n", s, it, batch12->lastError().c_str());
+                    ok12b = false;
+                    break;
+                }
+                for (int i = 0; i < Ba; ++i)
+                {
+                    const int nr = refs[i].ocp->getDiscretizationGrid()->getN(), nb = devs[i].ocp->getDiscretizationGrid()->getN();
+                    n_min_seen = std::min(n_min_seen, nb), n_max_seen = std::max(n_max_seen, nb);
+                    if (nr != nb)
+                    {
+                        std::printf("FAIL: object %d: grid sizes diverge (%d vs %d)\n", i, nr, nb);
+                        ok12b = false;
+                    }
+                    else
+                        worst12b = std::max(worst12b, relDiff(paramsOf(*refs[i].problem), paramsOf(*devs[i].problem)));
+                }
+            }
+        std::printf("adaptive time-optimal unicycle, %d objects x 6 solves through solveBatch, grid sizes %d..%d in one batch: max relative "
+                    "trajectory difference vs reference = %.3e\n", Ba, n_min_seen, n_max_seen, worst12b);
+        if (!ok12b || n_min_seen == n_max_seen || !(worst12b <= 1e-4))
+        {
+            std::printf("FAIL: batched grid adaptation through the plugin\n");
+            ++failures;
+        }
+    }
     std::printf(failures ? "DROP-IN TEST FAILED\n" : "DROP-IN TEST PASSED\n");
     return failures ? 1 : 0;
 }

