@@ -427,6 +427,7 @@ def main_b200(args):
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    solver.load_library()  # before the first CUDA call: the library asks for one hardware queue per concurrent bucket stream (api.cpp)
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device -- the hot path only exists as sm_100a kernels (no CPU fallback)")
     torch.cuda.set_device(local_rank)

@@ -57,6 +57,10 @@ def isolated(fn):
     if pid == 0:
         code = 1
         try:
+            import faulthandler
+
+            faulthandler.disable()  # a dying child is an expected outcome here, not a crash report
+            os.dup2(os.open(os.devnull, os.O_WRONLY), 2)
             os.close(r)
             with os.fdopen(w, "wb") as f:
                 pickle.dump(fn(), f)
