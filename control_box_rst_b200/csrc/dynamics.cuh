@@ -256,6 +256,8 @@ struct Quadrotor
     // The attitude angles x[3..5] enter only through their sines and cosines: callers that evaluate f at many points which share
     // most angles (the finite-difference columns of the pipeline, lm_pipeline.cuh) keep the six values and refresh one pair.
     static constexpr int NANG = 3, ANG0 = 3;
+    // f is affine in u (thrust and torques enter linearly): f(x, u) = (f(x, u + d e_j) + f(x, u - d e_j)) / 2 up to rounding
+    static constexpr bool CONTROL_AFFINE = true;
     // templated on the scalar type: double everywhere, float only in the reduced-precision pipeline (b200sqp_set_precision)
     template <class T>
     __device__ __forceinline__ static void trig(const T* x, T* sc /*[2*NANG]: sin, cos per angle*/)

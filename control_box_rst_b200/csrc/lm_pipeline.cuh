@@ -245,7 +245,72 @@ __global__ void __launch_bounds__(128, 4) pipeLinearizeKernel(const __grid_const
     }
     StepSizeT<Real> h(P.dt_ref);
     Real e2[NX], e1[NX];
-    if constexpr (DEFECT == DEFECT_CRANK_NICOLSON && PipeTrig<M>::value)
+#ifdef B200SQP_FP32_WHOLE_DEFECTS  // development switch: the fp32 variant with two whole defects per lane, as in fp64
+    constexpr bool PAIRS = false;
+#else
+    constexpr bool PAIRS = !F64;
+#endif
+    if constexpr (PAIRS)
+    {
+        // Reduced precision: no bit-parity to keep, so the unit of work is one distinct PAIR of dynamics evaluations per lane instead of
+        // two whole defects (four evaluations).  A column of x_k only moves f(x_k, u_k), a column of x_{k+1} only f(x_{k+1}, u_k); the
+        // NU control columns move both and are split over two lanes: lane NX + m differences f(x_k, .), lane NV + m differences
+        // f(x_{k+1}, .) and hands its part over by a shuffle.  With NV + NU = 32 every lane has exactly one pair.  The model is affine in u,
+        // so the unperturbed values the LM loop needs are the MEANS of a control column's pair: no extra evaluation for them.
+        static_assert(DEFECT == DEFECT_CRANK_NICOLSON && PipeTrig<M>::value && M::CONTROL_AFFINE && NV + NU <= 32,
+                      "the fp32 variant exists for the trig-cached Crank-Nicolson path of a control-affine model");
+        constexpr int NA = M::NANG, A0 = M::ANG0;
+        const bool second = lane >= NX + NU;                                 // this lane works on f(x_{k+1}, u_k)
+        const bool ucol   = (lane >= NX && lane < NX + NU) || lane >= NV;    // ... on a control column
+        const int comp    = ucol ? (lane < NV ? lane - NX : lane - NV) : (second ? lane - NX - NU : lane);
+        // lane-dependent choices are selects, not branches: the warp must not serialise over them
+        const int xsel = ucol ? -1 : comp, usel = ucol ? comp : -1;
+        Real xa[NX], ua[NU];
+#pragma unroll
+        for (int j = 0; j < NX; ++j) xa[j] = (second ? v[NX + NU + j] : v[j]) + (j == xsel ? delta : Real(0));
+#pragma unroll
+        for (int j = 0; j < NU; ++j) ua[j] = v[NX + j] + (j == usel ? delta : Real(0));
+        Real sc[2 * NA], fp[NX], fm[NX];
+        M::trig(xa, sc);
+        M::fTrig(P.dyn, xa, ua, sc, fp);
+        Real ang = 0;
+#pragma unroll
+        for (int q = 0; q < NX; ++q)
+        {
+            xa[q] += (q == xsel ? neg2delta : Real(0));
+            ang = (q == xsel) ? xa[q] : ang;
+        }
+#pragma unroll
+        for (int q = 0; q < NU; ++q) ua[q] += (q == usel ? neg2delta : Real(0));
+        Real sa, ca;
+        sincosT(ang, &sa, &ca);  // the one sine / cosine pair the perturbation may have touched
+#pragma unroll
+        for (int a = 0; a < NA; ++a)
+        {
+            sc[2 * a]     = (xsel == A0 + a) ? sa : sc[2 * a];
+            sc[2 * a + 1] = (xsel == A0 + a) ? ca : sc[2 * a + 1];
+        }
+        M::fTrig(P.dyn, xa, ua, sc, fm);
+        // the (x_{k+1} - x_k) / dt part of the defect moves only in row `comp` of a state column: own component +-delta against the
+        // same component of the other state (lane +- (NX + NU))
+        const Real other = __shfl_sync(0xffffffffu, mine, second ? lane - NX - NU : lane + NX + NU);
+        const Real a1 = mine + delta, b1 = a1 + neg2delta;
+        const Real dx_self = second ? h.div(a1 - other) - h.div(b1 - other) : h.div(other - a1) - h.div(other - b1);
+        const bool ufirst = lane >= NX && lane < NX + NU;
+#pragma unroll
+        for (int j = 0; j < NX; ++j)
+        {
+            Real d          = fp[j] - fm[j];
+            const Real mean = Real(0.5) * (fp[j] + fm[j]);
+            const Real d2   = __shfl_down_sync(0xffffffffu, d, NV - NX);  // lane NX + m <- lane NV + m: the f(x_{k+1}, .) half of a control column
+            const Real f2b  = __shfl_sync(0xffffffffu, mean, NV);         // f(x_{k+1}, u_k) from the first helper lane
+            d += ufirst ? d2 : Real(0);
+            if (lane == NX) sE0[wib][j] = (h.div(v[NX + NU + j] - v[j]) - Real(0.5) * (mean + f2b)) * w_eq;  // levenberg_marquardt_sparse.cpp:231-235
+            const Real dx = (j == xsel) ? dx_self : Real(0);
+            if (lane < NV) sG[wib][lane][j] = col_lane ? scalar * (dx - Real(0.5) * d) * w_eq : Real(0);
+        }
+    }
+    else if constexpr (DEFECT == DEFECT_CRANK_NICOLSON && PipeTrig<M>::value)
     {
         // The model's angles enter only through sin/cos and a column perturbs at most one of them: keep the sines and cosines of
         // both states from the +delta evaluation and refresh the one pair the perturbation touched for the -delta evaluation (one
@@ -300,15 +365,18 @@ __global__ void __launch_bounds__(128, 4) pipeLinearizeKernel(const __grid_const
             defect<M, DEFECT>(P.dyn, vec, vec + NX, vec + NX + NU, h, e1);
         }
     }
-    if (p < NV)
+    if constexpr (!PAIRS)
     {
+        if (p < NV)
+        {
 #pragma unroll
-        for (int j = 0; j < NX; ++j) sG[wib][p][j] = col_lane ? scalar * (e2[j] - e1[j]) * w_eq : Real(0);
-    }
-    else if (p == NV)
-    {
+            for (int j = 0; j < NX; ++j) sG[wib][p][j] = col_lane ? scalar * (e2[j] - e1[j]) * w_eq : Real(0);
+        }
+        else if (p == NV)
+        {
 #pragma unroll
-        for (int j = 0; j < NX; ++j) sE0[wib][j] = e2[j] * w_eq;  // levenberg_marquardt_sparse.cpp:231-235
+            for (int j = 0; j < NX; ++j) sE0[wib][j] = e2[j] * w_eq;  // levenberg_marquardt_sparse.cpp:231-235
+        }
     }
 
     // ---- lsq cost and bound rows of the block slots [u_k | x_{k+1}] (diagonal): lane s < NB handles slot s

@@ -1,5 +1,5 @@
 import sys, numpy as np
-sys.path.insert(0, "/root/repo")
+sys.path.insert(0, ".")
 from control_box_rst_b200 import problems, solver
 ocp, kw, _ = problems.config(4)
 B = 4096
