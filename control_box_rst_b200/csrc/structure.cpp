@@ -150,6 +150,23 @@ int buildStructure(const b200sqp_ocp& ocp, Structure& s, std::string& err)
         err = "nx/nu do not match the dynamics id";
         return B200SQP_ERR_INVALID;
     }
+    if (ocp.dynamics == B200SQP_DYN_CART_POLE)
+    {
+        // CartPoleSystem has no parameter setters (nonlinear_benchmark_systems.h:337-365: private constants): the device functor uses the
+        // same constants.  All-zero parameters mean "the class as it is"; anything else must be those constants.
+        const double fixed[4] = {1.0, 0.3, 0.5, 9.81};
+        bool zero = true, same = true;
+        for (int i = 0; i < 4; ++i)
+        {
+            zero = zero && ocp.dyn_params[i] == 0.0;
+            same = same && ocp.dyn_params[i] == fixed[i];
+        }
+        if (!zero && !same)
+        {
+            err = "the cart-pole of the reference has fixed parameters (mc, mp, l, g) = (1, 0.3, 0.5, 9.81); other values are not supported";
+            return B200SQP_ERR_UNSUPPORTED;
+        }
+    }
     if (ocp.n_grid < 2)
     {
         err = "n_grid must be >= 2";

@@ -43,7 +43,7 @@ typedef enum {
     B200SQP_DYN_VAN_DER_POL      = 0, /* nonlinear_benchmark_systems.h:52-60, params[0] = a */
     B200SQP_DYN_DUFFING          = 1, /* nonlinear_benchmark_systems.h DuffingOscillator */
     B200SQP_DYN_SIMPLE_PENDULUM  = 2, /* nonlinear_benchmark_systems.h SimplePendulum, params = m,l,g,rho */
-    B200SQP_DYN_CART_POLE        = 3, /* nonlinear_benchmark_systems.h:337-352, params = mc,mp,l,g */
+    B200SQP_DYN_CART_POLE        = 3, /* nonlinear_benchmark_systems.h:337-352; params = mc,mp,l,g are the class' private constants (1, 0.3, 0.5, 9.81): pass those or zeros, other values are refused */
     B200SQP_DYN_DOUBLE_INTEGRATOR = 4, /* linear_benchmark_systems.h DoubleIntegratorDiscreteTime's continuous twin: x'' = u */
     B200SQP_DYN_UNICYCLE         = 5, /* new: x' = v cos(th), y' = v sin(th), th' = w */
     B200SQP_DYN_QUADROTOR        = 6, /* new: 12-state rigid-body quadrotor, params = m,g,Ixx,Iyy,Izz */

@@ -177,3 +177,17 @@ def test_dt_equality_edges_structure(oracle):
     fixed.dt_eq_constraint = 1
     with pytest.raises(solver.B200SqpError):
         solver.dims_of(fixed)
+
+
+def test_cart_pole_parameters_are_the_reference_constants():
+    """CartPoleSystem has no parameter setters (nonlinear_benchmark_systems.h:337-365): the descriptor may carry its constants or zeros,
+    anything else is refused instead of silently running the default plant"""
+    ocp = problems.cart_pole_shooting(20)
+    assert solver.dims_of(ocp).n_params > 0
+    for i in range(4):
+        ocp.dyn_params[i] = 0.0
+    assert solver.dims_of(ocp).n_params > 0
+    ocp.dyn_params[1] = 0.4
+    with pytest.raises(solver.B200SqpError) as e:
+        solver.dims_of(ocp)
+    assert e.value.code == abi.ERR_UNSUPPORTED
