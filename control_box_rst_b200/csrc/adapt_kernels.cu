@@ -191,6 +191,150 @@ __global__ void adaptExportKernel(const AdaptBucketView* __restrict__ views, con
     }
 }
 
+// ---- second strategy: NonUniformFiniteDifferencesVariableGrid::adaptGridRedundantControls (non_uniform_finite_differences_variable_grid.cpp:
+//      259-352).  An interval whose control repeats in its successor (every component within epsilon) or whose dt is below 1e-6 is
+//      redundant (the last interval never counts).  More redundant intervals than `backup`: the surplus is removed from the back, a removed
+//      interval's dt going to its predecessor, down to n_min grid points; fewer: the missing ones are created by halving the interval with
+//      the largest dt (first maximum, last interval excluded), up to n_max.  Several grid points may change per call and an inserted mid
+//      state can be the neighbour of the next insertion, so the edits are a per-instance SCRIPT: the decision kernel derives it from
+//      (u, dt) alone -- states never influence it -- and reports the new grid size; the apply kernel replays it on the trajectory.
+//      One thread per instance for both: the scripts are sequential and a few dozen steps long.
+__global__ void adaptDecideRedundantKernel(const double* __restrict__ z0, const double* __restrict__ z1, const int* __restrict__ cur, int K, int nb,
+                                           int nu, int count, const int* __restrict__ inst_of_slot, double eps, int backup, int n_min, int n_max,
+                                           int* __restrict__ new_n, int* __restrict__ ops, int* __restrict__ nops)
+{
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= count) return;
+    const int inst    = inst_of_slot[j];
+    const double* src = cur[j] ? z1 : z0;
+    const int slots   = K * nb;
+    int* my_ops       = ops + (size_t)inst * ADAPT_KMAX;
+    int no = 0, n = K + 1;
+    if (n >= 3)
+    {
+        unsigned char list[ADAPT_KMAX];
+        int cnt = 0;
+        for (int idx = 0; idx + 1 < K; ++idx)  // never the last control
+        {
+            bool red = src[tiled(j, idx * nb + nu, slots)] < 1e-6;
+            if (!red)
+            {
+                red = true;
+                for (int c = 0; c < nu; ++c)
+                    if (!(fabs(src[tiled(j, (idx + 1) * nb + c, slots)] - src[tiled(j, idx * nb + c, slots)]) <= eps)) red = false;
+            }
+            if (red) list[cnt++] = (unsigned char)idx;
+        }
+        const int diff = cnt - backup;
+        if (diff < 0)
+        {
+            double dtl[ADAPT_KMAX];
+            int len = K;
+            for (int k = 0; k < K; ++k) dtl[k] = src[tiled(j, k * nb + nu, slots)];
+            for (int t = 0; t < -diff && n < n_max && len < ADAPT_KMAX; ++t)
+            {
+                int i = 0;
+                if (n > 2)
+                    for (int k = 1; k + 1 < len; ++k)  // std::max_element over [begin, end - 1): first maximum
+                        if (dtl[i] < dtl[k]) i = k;
+                const double new_dt = 0.5 * dtl[i];
+                dtl[i]              = new_dt;
+                for (int k = len; k > i + 1; --k) dtl[k] = dtl[k - 1];
+                dtl[i + 1] = new_dt;
+                ++len;
+                ++n;
+                my_ops[no++] = (i << 1) | 1;
+            }
+        }
+        else if (diff > 0)
+        {
+            int it = cnt - 1;
+            for (int t = 0; t < diff && n > n_min; ++t, --it)
+            {
+                int k = list[it];
+                if (k >= n - 2) --k;
+                my_ops[no++] = k << 1;
+                --n;
+            }
+        }
+    }
+    new_n[inst] = n;
+    nops[inst]  = no;
+}
+
+// replay of the script on the trajectory: plain per-instance scratch (nodes [K+1][nx], controls [K][nu], dt [K]), then the store into the
+// idle parameter buffer of the destination slot
+__global__ void adaptApplyOpsKernel(const AdaptBucketView* __restrict__ views, const int* __restrict__ plan, const int* __restrict__ ops,
+                                    const int* __restrict__ nops, double* __restrict__ scratch, const double* __restrict__ x0_master,
+                                    const double* __restrict__ xref_master, int nx, int nu, int B)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= B) return;
+    const AdaptBucketView sb = views[plan[i]], db = views[plan[2 * B + i]];
+    const int sslot = plan[B + i], dslot = plan[3 * B + i];
+    const int nb    = nu + 1 + nx;
+    Source s{sb.cur[sslot] ? sb.z[1] : sb.z[0], x0_master + (size_t)i * nx, sslot, sb.K, nb, nu};
+    double* X  = scratch + (size_t)i * ((size_t)(ADAPT_KMAX + 1) * nx + (size_t)ADAPT_KMAX * (nu + 1));
+    double* U  = X + (size_t)(ADAPT_KMAX + 1) * nx;
+    double* DT = U + (size_t)ADAPT_KMAX * nu;
+    int len    = sb.K;  // intervals; nodes = len + 1
+    for (int m = 0; m <= len; ++m)
+        for (int j = 0; j < nx; ++j) X[m * nx + j] = s.x(m, j);
+    for (int k = 0; k < len; ++k)
+    {
+        for (int j = 0; j < nu; ++j) U[k * nu + j] = s.u(k, j);
+        DT[k] = s.dt(k);
+    }
+    const int* my_ops = ops + (size_t)i * ADAPT_KMAX;
+    for (int t = 0; t < nops[i]; ++t)
+    {
+        const int op = my_ops[t], k = op >> 1;
+        if (op & 1)
+        {
+            // insert behind interval k: mid state, the interval's control, both halves get half the dt
+            const double new_dt = 0.5 * DT[k];
+            DT[k]               = new_dt;
+            for (int m = len; m > k; --m)
+                for (int j = 0; j < nx; ++j) X[(m + 1) * nx + j] = X[m * nx + j];
+            for (int j = 0; j < nx; ++j) X[(k + 1) * nx + j] = 0.5 * (X[k * nx + j] + X[(k + 2) * nx + j]);
+            for (int q = len; q > k + 1; --q)
+            {
+                for (int j = 0; j < nu; ++j) U[q * nu + j] = U[(q - 1) * nu + j];
+                DT[q] = DT[q - 1];
+            }
+            for (int j = 0; j < nu; ++j) U[(k + 1) * nu + j] = U[k * nu + j];
+            DT[k + 1] = new_dt;
+            ++len;
+        }
+        else
+        {
+            // remove grid point k + 1: its interval's dt goes to interval k
+            DT[k] += DT[k + 1];
+            for (int m = k + 1; m < len; ++m)
+                for (int j = 0; j < nx; ++j) X[m * nx + j] = X[(m + 1) * nx + j];
+            for (int q = k + 1; q + 1 < len; ++q)
+            {
+                for (int j = 0; j < nu; ++j) U[q * nu + j] = U[(q + 1) * nu + j];
+                DT[q] = DT[q + 1];
+            }
+            --len;
+        }
+    }
+    double* dst      = db.z[db.cur[dslot] ? 0 : 1];
+    const int dslots = db.K * nb;  // db.K == len by construction of the plan
+    for (int k = 0; k < len && k < db.K; ++k)
+    {
+        for (int j = 0; j < nu; ++j) dst[tiled(dslot, k * nb + j, dslots)] = U[k * nu + j];
+        dst[tiled(dslot, k * nb + nu, dslots)] = DT[k];
+        for (int j = 0; j < nx; ++j) dst[tiled(dslot, k * nb + nu + 1 + j, dslots)] = X[(k + 1) * nx + j];
+    }
+    for (int j = 0; j < nx; ++j)
+    {
+        db.x0[tiled(dslot, j, nx)]   = x0_master[(size_t)i * nx + j];
+        db.xref[tiled(dslot, j, nx)] = xref_master[(size_t)i * nx + j];
+    }
+}
+
 }  // namespace
 
 void launchAdaptDecide(const double* z0, const double* z1, const int* cur, int K, int nx, int nu, int count, const int* inst_of_slot, double hi,
@@ -222,6 +366,25 @@ void launchAdaptExport(const AdaptBucketView* views, const int* plan, const doub
                        double* dt, int* n, int B, cudaStream_t stream)
 {
     adaptExportKernel<<<dim3((B + 127) / 128, n_cap), 128, 0, stream>>>(views, plan, x0_master, nx, nu, n_cap, x, u, dt, n, B);
+}
+
+}  // namespace b200sqp
+
+namespace b200sqp {
+
+void launchAdaptDecideRedundant(const double* z0, const double* z1, const int* cur, int K, int nx, int nu, int count, const int* inst_of_slot,
+                                double eps, int backup, int n_min, int n_max, int* new_n, int* ops, int* nops, cudaStream_t stream)
+{
+    if (count <= 0) return;
+    adaptDecideRedundantKernel<<<(count + 63) / 64, 64, 0, stream>>>(z0, z1, cur, K, nu + 1 + nx, nu, count, inst_of_slot, eps, backup, n_min, n_max,
+                                                                      new_n, ops, nops);
+}
+
+void launchAdaptApplyOps(const AdaptBucketView* views, const int* plan, const int* ops, const int* nops, double* scratch, const double* x0_master,
+                         const double* xref_master, int nx, int nu, int B, cudaStream_t stream)
+{
+    adaptApplyOpsKernel<<<(B + 63) / 64, 64, 0, stream>>>(views, plan, ops, nops, scratch, x0_master, xref_master, nx, nu, B);
+    adaptCommitKernel<<<(B + 127) / 128, 128, 0, stream>>>(views, plan, B);
 }
 
 }  // namespace b200sqp

@@ -1355,6 +1355,11 @@ struct b200sqp_adaptive
     double w_eq = 2, w_ineq = 2, w_b = 2;
     int64_t launches = 0, splits = 0, merges = 0;
     std::vector<int> last_interval_changes;  // per instance: adaptations that changed the last interval (undefined in the reference)
+    int strategy = 0;  // 0 adaptGridTimeBasedSingleStep, 1 adaptGridRedundantControls
+    int redundant_backup = 1;
+    double redundant_epsilon = 1e-3;
+    int *d_ops = nullptr, *d_nops = nullptr;  // edit scripts of the redundant-controls strategy [B][ADAPT_KMAX], [B]
+    double* d_scratch = nullptr;
     std::vector<void*> allocations;
 };
 
@@ -1416,15 +1421,22 @@ int adaptiveAdapt(b200sqp_adaptive* a, bool* changed)
         if (a->count[b] > 0)
         {
             b200sqp_handle h = a->bucket[b];
-            launchAdaptDecide(h->st.z[0], h->st.z[1], h->st.cur, h->s.K, a->nx, a->nu, a->count[b], a->d_inst_sorted + a->offset[b], hi, lo, a->n_min,
-                              a->n_max, a->d_decision, a->stream);
+            if (a->strategy == 1)  // d_decision receives the new grid size, d_ops / d_nops the edit script
+                launchAdaptDecideRedundant(h->st.z[0], h->st.z[1], h->st.cur, h->s.K, a->nx, a->nu, a->count[b], a->d_inst_sorted + a->offset[b],
+                                           a->redundant_epsilon, a->redundant_backup, a->n_min, a->n_max, a->d_decision, a->d_ops, a->d_nops, a->stream);
+            else
+                launchAdaptDecide(h->st.z[0], h->st.z[1], h->st.cur, h->s.K, a->nx, a->nu, a->count[b], a->d_inst_sorted + a->offset[b], hi, lo, a->n_min,
+                                  a->n_max, a->d_decision, a->stream);
             a->launches += 1;
         }
     CUDA_TRY(cudaGetLastError());
     CUDA_TRY(cudaMemcpyAsync(a->hp_decision, a->d_decision, sizeof(int) * a->B, cudaMemcpyDeviceToHost, a->stream));
     CUDA_TRY(cudaStreamSynchronize(a->stream));
     bool any = false;
-    for (int i = 0; i < a->B && !any; ++i) any = a->hp_decision[i] != 0;
+    if (a->strategy == 1)
+        for (int i = 0; i < a->B && !any; ++i) any = a->hp_decision[i] != a->n_lo + a->bucket_of[i];
+    else
+        for (int i = 0; i < a->B && !any; ++i) any = a->hp_decision[i] != 0;
     if (!any) return B200SQP_OK;
 
     const int B = a->B;
@@ -1434,11 +1446,21 @@ int adaptiveAdapt(b200sqp_adaptive* a, bool* changed)
     {
         const int dec = a->hp_decision[i], type = dec & 3;
         const int src = a->bucket_of[i];
-        const int dst = src + (type == ADAPT_SPLIT ? 1 : type == ADAPT_MERGE ? -1 : 0);
+        int dst;
+        if (a->strategy == 1)
+        {
+            dst = dec - a->n_lo;  // the decision is the new grid size
+            if (dst > src) a->splits += dst - src;
+            if (dst < src) a->merges += src - dst;
+        }
+        else
+        {
+            dst = src + (type == ADAPT_SPLIT ? 1 : type == ADAPT_MERGE ? -1 : 0);
+            a->splits += type == ADAPT_SPLIT;
+            a->merges += type == ADAPT_MERGE;
+            if (type != ADAPT_NONE && (dec >> 2) == a->n_lo + src - 2) a->last_interval_changes[i] += 1;  // interval K - 1 of a grid of K + 1 points
+        }
         if (dst < 0 || dst >= (int)a->bucket.size()) return fail(B200SQP_ERR_INVALID, "grid adaptation left the bucket range");
-        a->splits += type == ADAPT_SPLIT;
-        a->merges += type == ADAPT_MERGE;
-        if (type != ADAPT_NONE && (dec >> 2) == a->n_lo + src - 2) a->last_interval_changes[i] += 1;  // interval K - 1 of a grid of K + 1 points
         int rc = adaptiveEnsureBucket(a, dst);
         if (rc) return rc;
         a->hp_plan[i]         = src;
@@ -1449,7 +1471,10 @@ int adaptiveAdapt(b200sqp_adaptive* a, bool* changed)
         k_max                 = std::max(k_max, a->n_lo + dst - 1);
     }
     CUDA_TRY(cudaMemcpyAsync(a->d_plan, a->hp_plan, sizeof(int) * 5 * B, cudaMemcpyHostToDevice, a->stream));
-    launchAdaptMigrate(a->d_views, a->d_plan, a->d_x0_master, a->d_xref_master, a->nx, a->nu, a->warm_start ? 0 : 1, k_max, B, a->stream);
+    if (a->strategy == 1)
+        launchAdaptApplyOps(a->d_views, a->d_plan, a->d_ops, a->d_nops, a->d_scratch, a->d_x0_master, a->d_xref_master, a->nx, a->nu, B, a->stream);
+    else
+        launchAdaptMigrate(a->d_views, a->d_plan, a->d_x0_master, a->d_xref_master, a->nx, a->nu, a->warm_start ? 0 : 1, k_max, B, a->stream);
     a->launches += 2;
     CUDA_TRY(cudaGetLastError());
     for (int i = 0; i < B; ++i)
@@ -1643,6 +1668,29 @@ int b200sqp_adaptive_step(b200sqp_adaptive_handle a, const b200sqp_lm_options* o
     CUDA_TRY(cudaStreamSynchronize(a->stream));
     if (n_out)
         for (int i = 0; i < B; ++i) n_out[i] = a->n_lo + a->bucket_of[i];
+    return B200SQP_OK;
+}
+
+int b200sqp_adaptive_set_redundant_controls(b200sqp_adaptive_handle a, int32_t num_backup_nodes, double epsilon)
+{
+    if (!a || num_backup_nodes < 0 || !(epsilon >= 0.0)) return fail(B200SQP_ERR_INVALID, "bad argument");
+    if (!a->first_run) return fail(B200SQP_ERR_INVALID, "the adaptation strategy must be chosen before the first step");
+    if (a->n_hi > ADAPT_KMAX + 1) return fail(B200SQP_ERR_UNSUPPORTED, "the redundant-controls strategy is sized for grids of at most 129 points");
+    CUDA_TRY(cudaSetDevice(a->device));
+    if (!a->d_ops)
+    {
+        cudaError_t e = cudaSuccess;
+        auto A        = [&](auto** p, size_t cnt) {
+            if (e == cudaSuccess) e = cudaMalloc((void**)p, sizeof(**p) * cnt);
+            if (e == cudaSuccess) a->allocations.push_back(*p);
+            if (e == cudaSuccess) e = cudaMemsetAsync(*p, 0, sizeof(**p) * cnt, a->stream);
+        };
+        A(&a->d_ops, (size_t)a->B * ADAPT_KMAX);
+        A(&a->d_nops, (size_t)a->B);
+        A(&a->d_scratch, (size_t)a->B * ((size_t)(ADAPT_KMAX + 1) * a->nx + (size_t)ADAPT_KMAX * (a->nu + 1)));
+        if (e != cudaSuccess) return fail(B200SQP_ERR_CUDA, std::string("device allocation failed: ") + cudaGetErrorString(e));
+    }
+    a->strategy = 1, a->redundant_backup = num_backup_nodes, a->redundant_epsilon = epsilon;
     return B200SQP_OK;
 }
 

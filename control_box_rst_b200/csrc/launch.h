@@ -104,6 +104,12 @@ void launchAdaptDecide(const double* z0, const double* z1, const int* cur, int K
                        double lo, int n_min, int n_max, int* decision, cudaStream_t);
 void launchAdaptMigrate(const AdaptBucketView* views, const int* plan, double* x0_master, const double* xref_master, int nx, int nu, int keep_start,
                         int k_max, int B, cudaStream_t);
+// strategy adaptGridRedundantControls: per-instance edit script from (u, dt) + new grid size; replay on the trajectory while moving
+// (ops [B][ADAPT_KMAX], nops [B], scratch [B][(ADAPT_KMAX + 1) nx + ADAPT_KMAX (nu + 1)])
+void launchAdaptDecideRedundant(const double* z0, const double* z1, const int* cur, int K, int nx, int nu, int count, const int* inst_of_slot,
+                                double eps, int backup, int n_min, int n_max, int* new_n, int* ops, int* nops, cudaStream_t);
+void launchAdaptApplyOps(const AdaptBucketView* views, const int* plan, const int* ops, const int* nops, double* scratch, const double* x0_master,
+                         const double* xref_master, int nx, int nu, int B, cudaStream_t);
 void launchAdaptScatterStart(const AdaptBucketView* views, const int* plan, const double* x0_master, const double* xref_master, int nx, int B,
                              cudaStream_t);
 void launchAdaptGather(const AdaptBucketView* views, const int* plan, int nx, int nu, double* u0, double* chi2, int* status, int B, cudaStream_t);

@@ -141,6 +141,7 @@ struct AdaptBucketView
     int K;
 };
 enum { ADAPT_NONE = 0, ADAPT_SPLIT = 1, ADAPT_MERGE = 2 };  // decision = type | interval << 2
+constexpr int ADAPT_KMAX = 128;  // intervals per instance the edit scripts of the redundant-controls strategy are sized for
 
 // structures the pipeline covers (lm_pipeline.cuh); everything else runs through the fused kernel
 inline bool pipelineEligible(const DeviceOcp& P, int nx)

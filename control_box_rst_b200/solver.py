@@ -30,7 +30,7 @@ ABI_SYMBOLS = [
     "b200sqp_peer_export", "b200sqp_peer_attach", "b200sqp_peer_wait", "b200sqp_peer_gathered", "b200sqp_peer_detach", "b200sqp_peer_status", "b200sqp_linearize_dynamics", "b200sqp_warm_start_shift", "b200sqp_mpc_step",
     "b200sqp_plant_step", "b200sqp_closed_loop", "b200sqp_dynamics_hessian", "b200sqp_set_feature_set", "b200sqp_measure_fp64_peak", "b200sqp_set_precision", "b200sqp_set_reference_trajectory", "b200sqp_dt_equality_indices",
     "b200sqp_adaptive_create", "b200sqp_adaptive_destroy", "b200sqp_adaptive_step", "b200sqp_adaptive_get_trajectories",
-    "b200sqp_adaptive_statistics", "b200sqp_adaptive_reserve", "b200sqp_adaptive_last_interval_changes",
+    "b200sqp_adaptive_statistics", "b200sqp_adaptive_reserve", "b200sqp_adaptive_last_interval_changes", "b200sqp_adaptive_set_redundant_controls",
 ]
 
 
@@ -467,6 +467,10 @@ class AdaptiveGridBatch:
         _check(self._lib.b200sqp_adaptive_step(self._h, C.byref(self._opts), C.c_int32(num_ocp_iterations), _d(x0), _d(xref), _d(u0), _d(chi2),
                                                _i(status), _i(n)))
         return u0, chi2, status, n
+
+    def setGridAdaptRedundantControls(self, num_backup_nodes=1, epsilon=1e-3):
+        """the reference's second strategy (NonUniformFiniteDifferencesVariableGrid::setGridAdaptRedundantControls); before the first step"""
+        _check(self._lib.b200sqp_adaptive_set_redundant_controls(self._h, C.c_int32(num_backup_nodes), C.c_double(epsilon)))
 
     def reserve(self, n_from=None, n_to=None):
         """create the buckets of these grid sizes now (default: the whole reachable range) instead of on first use"""

@@ -369,6 +369,12 @@ int b200sqp_adaptive_destroy(b200sqp_adaptive_handle a);
  * always initialises.  Host pointers: x0, xref [batch*nx]; u0_out [batch*nu], chi2_out / status_out / n_out [batch] (any may be NULL). */
 int b200sqp_adaptive_step(b200sqp_adaptive_handle a, const b200sqp_lm_options* opts, int32_t num_ocp_iterations, const double* x0,
                           const double* xref, double* u0_out, double* chi2_out, int32_t* status_out, int32_t* n_out);
+/* switch the handle to the reference's second strategy, setGridAdaptRedundantControls(n_max, num_backup_nodes, epsilon)
+ * (non_uniform_finite_differences_variable_grid.cpp:52-58, 259-352): intervals whose control repeats in the successor (within epsilon) or
+ * whose dt is below 1e-6 are redundant; a surplus over num_backup_nodes is removed from the back, a deficit is made up by halving the
+ * interval with the largest dt -- several grid points per call, replayed per instance as an edit script on the device.  Call before the
+ * first step; n_max <= 129.  (dt_hyst_ratio of b200sqp_adaptive_create is then unused.) */
+int b200sqp_adaptive_set_redundant_controls(b200sqp_adaptive_handle a, int32_t num_backup_nodes, double epsilon);
 /* count [batch]: how many adaptations of each instance so far changed its LAST interval.  The reference has no defined answer there (it
  * indexes one past the end of its vertex vectors: non_uniform_finite_differences_variable_grid.cpp:225 `_x_seq[i + 1]`, :237
  * `_dt_seq[i + 1]` with i = size - 1 -- stale memory at best, heap corruption at worst); the device uses x_f as the right neighbour of a

@@ -330,24 +330,32 @@ class Reference(_Checker):
             raise RuntimeError(f"corbo_ref_warm_start_shift failed: {rc}")
         return out
 
-    def adapt_once(self, ocp, x, u, dt, n_min, n_max, dt_hyst_ratio=0.1):
-        """one isolated call of NonUniformFiniteDifferencesVariableGrid::adaptGrid (TimeBasedSingleStep) on a given trajectory
-        (x [N][nx], u [N-1][nu], dt [N-1], N = ocp.n_grid) -> (x, u, dt) of the adapted grid"""
+    def adapt_once(self, ocp, x, u, dt, n_min, n_max, dt_hyst_ratio=0.1, redundant_controls=None):
+        """one isolated call of NonUniformFiniteDifferencesVariableGrid::adaptGrid on a given trajectory (x [N][nx], u [N-1][nu], dt [N-1],
+        N = ocp.n_grid) -> (x, u, dt) of the adapted grid.  Strategy TimeBasedSingleStep, or RedundantControls when
+        redundant_controls = (num_backup_nodes, epsilon) is given."""
         N = ocp.n_grid
         x = np.ascontiguousarray(x, np.float64).reshape(N, ocp.nx)
         u = np.ascontiguousarray(u, np.float64).reshape(N - 1, ocp.nu)
         dt = np.ascontiguousarray(dt, np.float64).reshape(N - 1)
-        xo, uo, dto = np.zeros((N + 1, ocp.nx)), np.zeros((N + 1, ocp.nu)), np.zeros(N + 1)
+        cap = max(N, n_max) + 2
+        xo, uo, dto = np.zeros((cap, ocp.nx)), np.zeros((cap, ocp.nu)), np.zeros(cap)
         n = C.c_int32(0)
-        f = self.lib.corbo_ref_adapt_once
-        f.restype = C.c_int
-        rc = f(C.byref(ocp), C.c_int(n_min), C.c_int(n_max), C.c_double(dt_hyst_ratio), _d(x), _d(u), _d(dt), _d(xo), _d(uo), _d(dto), C.byref(n))
+        if redundant_controls is None:
+            f = self.lib.corbo_ref_adapt_once
+            f.restype = C.c_int
+            rc = f(C.byref(ocp), C.c_int(n_min), C.c_int(n_max), C.c_double(dt_hyst_ratio), _d(x), _d(u), _d(dt), _d(xo), _d(uo), _d(dto), C.byref(n))
+        else:
+            f = self.lib.corbo_ref_adapt_once_redundant
+            f.restype = C.c_int
+            rc = f(C.byref(ocp), C.c_int(n_min), C.c_int(n_max), C.c_int(redundant_controls[0]), C.c_double(redundant_controls[1]), _d(x), _d(u), _d(dt),
+                   _d(xo), _d(uo), _d(dto), C.byref(n))
         if rc != 0:
             raise RuntimeError(f"corbo_ref_adapt_once failed: {rc}")
         n = n.value
         return xo[:n].copy(), uo[:n - 1].copy(), dto[:n - 1].copy()
 
-    def adaptive_steps(self, ocp, opts, x0_seq, xref, n_min, n_max, dt_hyst_ratio=0.1, warm_start=True, num_ocp_iterations=2):
+    def adaptive_steps(self, ocp, opts, x0_seq, xref, n_min, n_max, dt_hyst_ratio=0.1, warm_start=True, num_ocp_iterations=2, redundant_controls=None):
         """Time-optimal MPC with the reference's grid adaptation (NonUniformFiniteDifferencesVariableGrid::adaptGridTimeBasedSingleStep)
         for one instance: x0_seq [steps][nx] -> (n_trace [steps][num_ocp_iterations], u0 [steps][nu], x [N][nx], u [N-1][nu], dt [N-1])"""
         x0_seq = np.ascontiguousarray(x0_seq, np.float64).reshape(-1, ocp.nx)
@@ -358,11 +366,16 @@ class Reference(_Checker):
         x = np.zeros((cap, ocp.nx))
         u = np.zeros((cap, ocp.nu))
         dt = np.zeros(cap)
-        f = self.lib.corbo_ref_adaptive_steps
-        f.restype = C.c_int
-        rc = f(C.byref(ocp), C.byref(opts), C.c_int(n_min), C.c_int(n_max), C.c_double(dt_hyst_ratio), C.c_int(1 if warm_start else 0),
-               C.c_int(num_ocp_iterations), C.c_int(steps), _d(x0_seq), _d(np.ascontiguousarray(xref, np.float64)), _i(n_trace), _d(u0), _d(x), _d(u),
-               _d(dt))
+        tail = (C.c_int(1 if warm_start else 0), C.c_int(num_ocp_iterations), C.c_int(steps), _d(x0_seq), _d(np.ascontiguousarray(xref, np.float64)),
+                _i(n_trace), _d(u0), _d(x), _d(u), _d(dt))
+        if redundant_controls is None:
+            f = self.lib.corbo_ref_adaptive_steps
+            f.restype = C.c_int
+            rc = f(C.byref(ocp), C.byref(opts), C.c_int(n_min), C.c_int(n_max), C.c_double(dt_hyst_ratio), *tail)
+        else:  # (num_backup_nodes, epsilon): setGridAdaptRedundantControls
+            f = self.lib.corbo_ref_adaptive_steps_redundant
+            f.restype = C.c_int
+            rc = f(C.byref(ocp), C.byref(opts), C.c_int(n_min), C.c_int(n_max), C.c_int(redundant_controls[0]), C.c_double(redundant_controls[1]), *tail)
         if rc != 0:
             raise RuntimeError(f"corbo_ref_adaptive_steps failed: {rc}")
         n = int(n_trace[-1, -1])

@@ -44,3 +44,52 @@ def adapt_time_based_single_step(x, u, dt, n_min, n_max, dt_ref, hyst):
         u = np.delete(u, i, axis=0)
         dt = np.delete(dt, i)
     return x, u, dt, kind, i
+
+
+def adapt_redundant_controls(x, u, dt, n_min, n_max, epsilon, num_backup_nodes):
+    """NonUniformFiniteDifferencesVariableGrid::adaptGridRedundantControls (non_uniform_finite_differences_variable_grid.cpp:259-352):
+    an interval whose control repeats in its successor (all components within epsilon) or whose dt is below 1e-6 is redundant (the last
+    interval never counts).  More redundant intervals than `num_backup_nodes`: the surplus is removed from the back (a removed interval's dt
+    goes to its predecessor), down to n_min grid points.  Fewer: the missing ones are created by halving the interval with the largest dt
+    (first maximum, last interval excluded; both halves get half the dt), up to n_max grid points.
+    -> (x, u, dt, ops) with ops = [(+1, interval) for an insertion behind `interval` | (-1, k) for the removal of grid point k + 1]"""
+    x, u, dt = [np.array(r, float) for r in x], [np.array(r, float) for r in u], [float(v) for v in dt]
+    ops = []
+    n = len(x)
+    if n < 3:
+        return np.array(x), np.array(u), np.array(dt), ops
+    num_interv = len(u)
+    non_unique = []
+    for idx in range(num_interv - 1):
+        if dt[idx] < 1e-6:
+            non_unique.append(idx)
+            continue
+        if np.all(np.abs(u[idx + 1] - u[idx]) <= epsilon):
+            non_unique.append(idx)
+    diff = len(non_unique) - num_backup_nodes
+    if diff < 0:
+        for _ in range(-diff):
+            if len(x) >= n_max:
+                break
+            i = 0
+            if len(x) > 2:
+                i = int(np.argmax(np.array(dt[:-1])))  # first maximum
+            new_dt = 0.5 * dt[i]
+            dt[i] = new_dt
+            x.insert(i + 1, 0.5 * (x[i] + x[i + 1]))
+            u.insert(i + 1, u[i].copy())
+            dt.insert(i + 1, new_dt)
+            ops.append((+1, i))
+    elif diff > 0:
+        it = len(non_unique) - 1
+        for _ in range(diff):
+            if len(x) <= n_min:
+                break
+            k = non_unique[it]
+            if k >= len(x) - 2:
+                k -= 1
+            dt[k] += dt[k + 1]
+            del x[k + 1], u[k + 1], dt[k + 1]
+            ops.append((-1, k))
+            it -= 1
+    return np.array(x), np.array(u), np.array(dt), ops

@@ -844,8 +844,18 @@ int corbo_ref_closed_loop_plant(const b200sqp_ocp* d, const b200sqp_lm_options* 
 // One call of the reference's grid adaptation in isolation: initialise the grid (N = n_grid), overwrite its vertices with the given
 // trajectory (x_in [N][nx] incl. start and final state, u_in [N-1][nu], dt_in [N-1]), run the grid update of a continued run
 // (new_run = false, warm start on -> adaptGrid, no re-initialisation) and read the vertices back (capacity N + 1 rows); *n_out = new N.
-int corbo_ref_adapt_once(const b200sqp_ocp* d, int n_min, int n_max, double dt_hyst_ratio, const double* x_in, const double* u_in, const double* dt_in,
-                         double* x_out, double* u_out, double* dt_out, int32_t* n_out)
+// strategy 0: setGridAdaptTimeBasedSingleStep(n_max, p0 = dt_hyst_ratio); 1: setGridAdaptRedundantControls(n_max, p1 = num_backup_nodes, p0 = epsilon)
+static void selectGridAdaptation(NuGridProbe* g, int strategy, int n_min, int n_max, double p0, int p1)
+{
+    if (strategy == 1)
+        g->setGridAdaptRedundantControls(n_max, p1, p0);
+    else
+        g->setGridAdaptTimeBasedSingleStep(n_max, p0);
+    g->setNmin(n_min);
+}
+
+static int adaptOnce(const b200sqp_ocp* d, int strategy, int n_min, int n_max, double p0, int p1, const double* x_in, const double* u_in,
+                     const double* dt_in, double* x_out, double* u_out, double* dt_out, int32_t* n_out)
 {
     if (d->grid != B200SQP_GRID_FD_NONUNIFORM_VARDT) return -9;
     b200sqp_lm_options o = {0, 2, 2, 2, 1, 1, 1, 500, 500, 500};
@@ -853,8 +863,7 @@ int corbo_ref_adapt_once(const b200sqp_ocp* d, int n_min, int n_max, double dt_h
     if (!buildOcp(*d, o, r)) return -1;
     auto* g = dynamic_cast<NuGridProbe*>(r.grid.get());
     if (!g) return -9;
-    g->setGridAdaptTimeBasedSingleStep(n_max, dt_hyst_ratio);
-    g->setNmin(n_min);
+    selectGridAdaptation(g, strategy, n_min, n_max, p0, p1);
     g->setWarmStart(true);
     const int N = d->n_grid;
     if (!prepare(r, *d, x_in, x_in + (size_t)(N - 1) * d->nx, true, nullptr)) return -2;
@@ -878,6 +887,19 @@ int corbo_ref_adapt_once(const b200sqp_ocp* d, int n_min, int n_max, double dt_h
     return 0;
 }
 
+int corbo_ref_adapt_once(const b200sqp_ocp* d, int n_min, int n_max, double dt_hyst_ratio, const double* x_in, const double* u_in, const double* dt_in,
+                         double* x_out, double* u_out, double* dt_out, int32_t* n_out)
+{
+    return adaptOnce(d, 0, n_min, n_max, dt_hyst_ratio, 0, x_in, u_in, dt_in, x_out, u_out, dt_out, n_out);
+}
+
+// the same for adaptGridRedundantControls (non_uniform_finite_differences_variable_grid.cpp:259-352); output capacity n_max + 1 rows
+int corbo_ref_adapt_once_redundant(const b200sqp_ocp* d, int n_min, int n_max, int num_backup_nodes, double epsilon, const double* x_in,
+                                   const double* u_in, const double* dt_in, double* x_out, double* u_out, double* dt_out, int32_t* n_out)
+{
+    return adaptOnce(d, 1, n_min, n_max, epsilon, num_backup_nodes, x_in, u_in, dt_in, x_out, u_out, dt_out, n_out);
+}
+
 // Time-optimal MPC with grid adaptation, the reference's own classes: a NonUniformFiniteDifferencesVariableGrid with
 // setGridAdaptTimeBasedSingleStep(n_max, dt_hyst_ratio) and setNmin(n_min) (non_uniform_finite_differences_variable_grid.cpp:45-50,206-257)
 // under the OCP loop of PredictiveController::step (predictive_controller.cpp:66): num_ocp_iterations computes per controller step, the
@@ -886,17 +908,16 @@ int corbo_ref_adapt_once(const b200sqp_ocp* d, int n_min, int n_max, double dt_h
 // x0_seq [steps][nx]: the measured state of every controller step; xref [nx] static reference (goal).
 // n_trace [steps*num_ocp_iterations]: grid size N each solve ran on; u0_out [steps][nu]: first control after each step;
 // x_last [n_max][nx], u_last [n_max][nu], dt_last [n_max]: the final trajectories (N = last n_trace entry; x has N rows, u and dt N-1).
-int corbo_ref_adaptive_steps(const b200sqp_ocp* d, const b200sqp_lm_options* o, int n_min, int n_max, double dt_hyst_ratio, int warm_start,
-                             int num_ocp_iterations, int steps, const double* x0_seq, const double* xref, int32_t* n_trace, double* u0_out,
-                             double* x_last, double* u_last, double* dt_last)
+static int adaptiveSteps(const b200sqp_ocp* d, const b200sqp_lm_options* o, int strategy, int n_min, int n_max, double p0, int p1, int warm_start,
+                         int num_ocp_iterations, int steps, const double* x0_seq, const double* xref, int32_t* n_trace, double* u0_out,
+                         double* x_last, double* u_last, double* dt_last)
 {
     if (d->grid != B200SQP_GRID_FD_NONUNIFORM_VARDT) return -9;
     RefOcp r;
     if (!buildOcp(*d, *o, r)) return -1;
     auto* g = dynamic_cast<NuGridProbe*>(r.grid.get());
     if (!g) return -9;
-    g->setGridAdaptTimeBasedSingleStep(n_max, dt_hyst_ratio);
-    g->setNmin(n_min);
+    selectGridAdaptation(g, strategy, n_min, n_max, p0, p1);
     g->setWarmStart(warm_start != 0);
     StaticReference xr(Eigen::VectorXd(Eigen::Map<const Eigen::VectorXd>(xref, d->nx)));
     ZeroReference uref(d->nu);
@@ -922,6 +943,23 @@ int corbo_ref_adaptive_steps(const b200sqp_ocp* d, const b200sqp_lm_options* o, 
     }
     std::memcpy(x_last + (size_t)(n - 1) * d->nx, g->xf().values().data(), sizeof(double) * d->nx);
     return 0;
+}
+
+int corbo_ref_adaptive_steps(const b200sqp_ocp* d, const b200sqp_lm_options* o, int n_min, int n_max, double dt_hyst_ratio, int warm_start,
+                             int num_ocp_iterations, int steps, const double* x0_seq, const double* xref, int32_t* n_trace, double* u0_out,
+                             double* x_last, double* u_last, double* dt_last)
+{
+    return adaptiveSteps(d, o, 0, n_min, n_max, dt_hyst_ratio, 0, warm_start, num_ocp_iterations, steps, x0_seq, xref, n_trace, u0_out, x_last, u_last,
+                         dt_last);
+}
+
+// the same loop with setGridAdaptRedundantControls(n_max, num_backup_nodes, epsilon)
+int corbo_ref_adaptive_steps_redundant(const b200sqp_ocp* d, const b200sqp_lm_options* o, int n_min, int n_max, int num_backup_nodes, double epsilon,
+                                       int warm_start, int num_ocp_iterations, int steps, const double* x0_seq, const double* xref, int32_t* n_trace,
+                                       double* u0_out, double* x_last, double* u_last, double* dt_last)
+{
+    return adaptiveSteps(d, o, 1, n_min, n_max, epsilon, num_backup_nodes, warm_start, num_ocp_iterations, steps, x0_seq, xref, n_trace, u0_out, x_last,
+                         u_last, dt_last);
 }
 
 // The reference's known-answer solver tests (optimization/test/test_levenberg_marquardt_sparse.cpp:72-296, excluded from its build)

@@ -44,13 +44,25 @@ CASES = {
 }
 
 
-def _reference_run(ref, ocp, opts, x0_seq, xf, n_min, n_max, hyst, warm, m):
-    return [bindings.isolated(lambda: ref.adaptive_steps(ocp, opts, x0_seq[:, i], xf[i], n_min, n_max, hyst, warm, m)) for i in range(xf.shape[0])]
+def _reference_run(ref, ocp, opts, x0_seq, xf, n_min, n_max, hyst, warm, m, redundant=None):
+    return [bindings.isolated(lambda: ref.adaptive_steps(ocp, opts, x0_seq[:, i], xf[i], n_min, n_max, hyst, warm, m, redundant_controls=redundant))
+            for i in range(xf.shape[0])]
 
 
 @pytest.mark.parametrize("warm", [True, False], ids=["warm", "cold"])
 @pytest.mark.parametrize("name", list(CASES))
 def test_grid_sizes_and_trajectories_match_the_compiled_reference(name, warm):
+    _compare_with_reference(name, warm, None)
+
+
+@pytest.mark.parametrize("warm", [True, False], ids=["warm", "cold"])
+@pytest.mark.parametrize("name", ["dint12", "vdp10", "unicycle16"])
+def test_redundant_controls_strategy_matches_the_compiled_reference(name, warm):
+    """setGridAdaptRedundantControls(n_max, 2 backup nodes, epsilon 1e-2): several grid points inserted / removed per OCP iteration"""
+    _compare_with_reference(name, warm, (2, 1e-2))
+
+
+def _compare_with_reference(name, warm, redundant):
     if not bindings.Reference.available():
         pytest.skip("compiled reference not present (oracle/_ref)")
     ref = bindings.Reference()
@@ -62,9 +74,11 @@ def test_grid_sizes_and_trajectories_match_the_compiled_reference(name, warm):
     # the measured state creeps towards the goal from step to step
     x0_seq = np.stack([x0 + 0.04 * s * (xf - x0) for s in range(steps)])
     opts = abi.LmOptions.defaults(iterations=6, weights=(2.0, 2.0, 2.0))
-    expected = _reference_run(ref, ocp, opts, x0_seq, xf, n_min, n_max, hyst, warm, m)
+    expected = _reference_run(ref, ocp, opts, x0_seq, xf, n_min, n_max, hyst, warm, m, redundant)
 
     ad = solver.AdaptiveGridBatch(ocp, B, n_min, n_max, hyst, warm_start=warm)
+    if redundant is not None:
+        ad.setGridAdaptRedundantControls(*redundant)
     ad.setIterations(6)
     ad.setPenaltyWeights(2.0, 2.0, 2.0)
     n_dev = np.zeros((steps, B), np.int32)
@@ -88,8 +102,12 @@ def test_grid_sizes_and_trajectories_match_the_compiled_reference(name, warm):
     # polynomial models: every instance follows the reference's sequence of grid sizes; with trigonometric dynamics a dt within the
     # finite-difference noise of a threshold may decide differently (tests/test_gpu_noise_floor.py), which must stay the exception
     assert same[defined].mean() >= (0.9 if trig else 1.0), (n_dev.T[~same & defined], n_ref.T[~same & defined])
-    assert n_ref[:, defined].min() < ocp.n_grid < n_ref[:, defined].max(), "the case must exercise both directions"
-    assert stats["splits"] > 0 and stats["merges"] > 0 and stats["occupied_buckets"] > 1
+    if redundant is None:
+        assert n_ref[:, defined].min() < ocp.n_grid < n_ref[:, defined].max(), "the case must exercise both directions"
+        assert stats["splits"] > 0 and stats["merges"] > 0
+    else:
+        assert n_ref[:, defined].min() != n_ref[:, defined].max() and stats["splits"] + stats["merges"] > 0
+    assert stats["occupied_buckets"] > 1
     assert np.array_equal(n_last, n_dev[-1])
     # 12 chained solves (4 steps x 3 OCP iterations), each within the single-solve bar of tests/test_gpu_parity.py (1e-6; trigonometric
     # models: the finite-difference noise floor of tests/test_gpu_noise_floor.py)

@@ -99,3 +99,30 @@ def test_adaptive_front_end_checks_arguments_and_needs_a_device():
         with pytest.raises(solver.B200SqpError) as e:
             solver.AdaptiveGridBatch(ocp, 4, 3, 30)
         assert e.value.code == abi.ERR_NO_DEVICE  # no CPU fallback
+
+
+@pytest.mark.parametrize("seed", range(12))
+def test_redundant_controls_restatement_matches_the_compiled_reference_bit_for_bit(reference, seed):
+    """adaptGridRedundantControls on random trajectories with plateaus in the controls and a few vanishing dts: every combination of
+    surplus (removals from the back), deficit (halving the largest interval, repeatedly) and the n_min / n_max stops"""
+    rng = np.random.default_rng(100 + seed)
+    N = int(rng.integers(4, 14))
+    ocp = problems.unicycle_time_optimal(N, 0.1)
+    x = rng.uniform(-1, 1, (N, 3))
+    u = rng.uniform(-1, 1, (N - 1, 2))
+    for k in range(1, N - 1):  # plateaus: a control repeats its predecessor (exactly, or within / just outside the threshold)
+        r = rng.uniform()
+        if r < 0.35:
+            u[k] = u[k - 1]
+        elif r < 0.5:
+            u[k] = u[k - 1] + rng.choice([0.5e-3, 0.99e-3, 1.01e-3, 2e-3]) * rng.choice([-1, 1], 2)
+    dt = rng.uniform(0.02, 0.3, N - 1)
+    if seed % 3 == 0:
+        dt[rng.integers(0, N - 1)] = 1e-7
+    backup = int(rng.integers(0, 5))
+    n_min = int(rng.integers(3, max(4, N - 1)))
+    n_max = int(rng.integers(N, N + 4))
+    xr, ur, dtr = reference.adapt_once(ocp, x, u, dt, n_min, n_max, redundant_controls=(backup, 1e-3))
+    xo, uo, dto, ops = ga.adapt_redundant_controls(x, u, dt, n_min, n_max, 1e-3, backup)
+    assert xr.shape == xo.shape, (xr.shape, xo.shape, ops)
+    assert np.array_equal(xr, xo) and np.array_equal(ur, uo) and np.array_equal(dtr, dto)
