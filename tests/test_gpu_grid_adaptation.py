@@ -9,7 +9,7 @@ from control_box_rst_b200 import _abi as abi
 from control_box_rst_b200 import problems, solver
 from oracle import bindings
 
-pytestmark = pytest.mark.gpu
+pytestmark = [pytest.mark.gpu, pytest.mark.filterwarnings("ignore:This process.*fork:DeprecationWarning")]  # bindings.isolated forks on purpose
 
 
 def _time_optimal(dynamics, n_grid, nx, nu, dt=0.1, **kw):
@@ -56,10 +56,53 @@ def test_grid_sizes_and_trajectories_match_the_compiled_reference(name, warm):
 
 
 @pytest.mark.parametrize("warm", [True, False], ids=["warm", "cold"])
-@pytest.mark.parametrize("name", ["dint12", "vdp10", "unicycle16"])
+@pytest.mark.parametrize("name", ["vdp10", "unicycle16"])
 def test_redundant_controls_strategy_matches_the_compiled_reference(name, warm):
-    """setGridAdaptRedundantControls(n_max, 2 backup nodes, epsilon 1e-2): several grid points inserted / removed per OCP iteration"""
+    """setGridAdaptRedundantControls(n_max, 2 backup nodes, epsilon 1e-2): several grid points inserted / removed per OCP iteration.
+    (The double integrator is left to the replay test below: with this strategy and a warm start the REFERENCE's own sequence of grid
+    sizes changes in 2-5 of 8 runs when the goal moves by a few ulps, for half of the instances -- nothing to compare against.)"""
     _compare_with_reference(name, warm, (2, 1e-2))
+
+
+@pytest.mark.parametrize("strategy", ["time_based", "redundant_controls"])
+@pytest.mark.parametrize("name", ["dint12", "vdp10", "unicycle16"])
+def test_adaptation_of_a_solved_trajectory_equals_the_restatement(name, strategy):
+    """The grid side in isolation: solve once, then run an OCP iteration with zero LM iterations -- what comes back is the adapted
+    trajectory itself.  It equals oracle/grid_adaptation.py (pinned bit for bit against the compiled reference in
+    tests/test_grid_adaptation.py) on the solved trajectory, up to the round-trip drift of the finite differences of the empty solve."""
+    from oracle import grid_adaptation as ga
+
+    ocp = CASES[name]()
+    B = 24
+    rng = np.random.default_rng(11)
+    x0, xf = _goals(name, B, rng)
+    n_min, n_max, hyst, red = 3, 26, 0.1, (2, 1e-2)
+    ad = solver.AdaptiveGridBatch(ocp, B, n_min, n_max, hyst, warm_start=True)
+    if strategy == "redundant_controls":
+        ad.setGridAdaptRedundantControls(*red)
+    ad.setIterations(6)
+    ad.setPenaltyWeights(2.0, 2.0, 2.0)
+    ad.step(x0, xf, num_ocp_iterations=1)
+    xa, ua, dta, na = ad.trajectories()
+    ad.setIterations(0)
+    ad.step(x0, xf, num_ocp_iterations=2)
+    xb, ub, dtb, nb = ad.trajectories()
+    undefined = ad.last_interval_changes() > 0
+    ad.close()
+    changed = 0
+    for i in range(B):
+        n = int(na[i])
+        if strategy == "redundant_controls":
+            xo, uo, dto, _ = ga.adapt_redundant_controls(xa[i, :n], ua[i, :n - 1], dta[i, :n - 1], n_min, n_max, red[1], red[0])
+        else:
+            xo, uo, dto, _, _ = ga.adapt_time_based_single_step(xa[i, :n], ua[i, :n - 1], dta[i, :n - 1], n_min, n_max, ocp.dt_ref, hyst)
+        m = len(xo)
+        assert m == int(nb[i]), (i, n, m, int(nb[i]))
+        changed += m != n
+        for dev, exp in ((xb[i, :m], xo), (ub[i, :m - 1], uo), (dtb[i, :m - 1], dto)):
+            np.testing.assert_allclose(dev, exp, rtol=0, atol=1e-13 * max(1.0, np.abs(exp).max()))
+    assert changed >= B // 4
+    assert strategy == "time_based" or not undefined.any()
 
 
 def _compare_with_reference(name, warm, redundant):
