@@ -45,7 +45,7 @@ def build_reference(reference_root="/root/reference"):
     return True
 
 
-def isolated(fn):
+def isolated(fn, timeout=120.0):
     """fn() in a forked child -> its result, or None if the child died.  Needed around Reference.adaptive_steps: the reference indexes one
     past the end of its vertex vectors when the interval it splits or merges is the last one
     (non_uniform_finite_differences_variable_grid.cpp:225,237: _x_seq[i + 1], _dt_seq[i + 1] with i = size - 1), which ends in heap
@@ -68,9 +68,24 @@ def isolated(fn):
         finally:
             os._exit(code)
     os.close(w)
-    with os.fdopen(r, "rb") as f:
-        data = f.read()
+    import select
+    import signal
+    import time
+
+    chunks, deadline = [], time.monotonic() + timeout
+    while True:
+        left = deadline - time.monotonic()
+        ready = select.select([r], [], [], max(left, 0.0))[0] if left > 0 else []
+        if not ready:  # a child that neither finishes nor dies (a fork of a multi-threaded parent may inherit a held lock)
+            os.kill(pid, signal.SIGKILL)
+            break
+        chunk = os.read(r, 1 << 16)
+        if not chunk:
+            break
+        chunks.append(chunk)
+    os.close(r)
     _, status = os.waitpid(pid, 0)
+    data = b"".join(chunks)
     if status != 0 or not data:
         return None
     return pickle.loads(data)

@@ -170,11 +170,13 @@ def _compare_with_reference(name, warm, redundant):
         assert worst.max() <= tol, np.sort(worst)[-5:]
 
 
-def test_batch_equals_its_instances_solved_alone():
-    """bucketing is invisible: an instance yields the same grid sizes, controls and trajectory whether it shares the batch with 95 others
-    (several buckets, slots reassigned after every adaptation) or runs as a batch of one"""
+@pytest.mark.parametrize("B", [96, 4096])
+def test_batch_equals_its_instances_solved_alone(B):
+    """bucketing is invisible: an instance yields the same grid sizes, controls and trajectory whether it shares the batch with thousands of
+    others (dozens of buckets, slots reassigned after every adaptation) or runs as a batch of one -- the size-independent property that
+    carries the small-batch parity above to BASELINE's batch"""
     ocp = CASES["dint12"]()
-    B, steps, m = 96, 3, 3
+    steps, m = 3, 3
     rng = np.random.default_rng(5)
     x0, xf = _goals("dint", B, rng)
     perm = rng.permutation(B)
@@ -189,7 +191,7 @@ def test_batch_equals_its_instances_solved_alone():
         return out, traj
 
     full, traj = run(x0, xf)
-    for i in (0, 17, 41, 95):
+    for i in (0, 17, 41, B - 1):
         alone, traj1 = run(x0[i:i + 1], xf[i:i + 1])
         for s in range(steps):
             assert full[s][3][i] == alone[s][3][0]
