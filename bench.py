@@ -486,7 +486,7 @@ def main_b200(args):
                 dist.all_reduce(rendezvous)
             flush.zero_()  # evict L2 between timed iterations (outside the timed region)
             if world > 1:
-                torch.cuda._sleep(400000)  # ~0.2 ms
+                torch.cuda._sleep(2000000)  # ~1 ms: every rank's host thread has the step enqueued before the device gets to it
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record(stream)
             fn()
