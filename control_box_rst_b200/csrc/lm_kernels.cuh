@@ -460,6 +460,13 @@ void launchSolve(const DeviceOcp& P, const DeviceState& st, int iterations, int 
     for (int j = 0; j < M::NX; ++j) lean = lean && !P.x_bounded[j] && !P.xf_fixed[j];
     if (flags & SOLVE_FORCE_GENERAL_FEATURES) lean = false;
     if (st.xref_traj) lean = false;  // a time-varying state reference is a feature of the general set only  // b200sqp_set_feature_set: parity tests run both variants on one structure
+    if constexpr (VT >= 1)
+    {
+        // time-optimal feature set: minimum-time lsq cost, no state bounds, no final-stage constraint, static reference
+        bool topt = P.final_constraint == 0 && P.stage_cost == B200SQP_COST_MINIMUM_TIME_LSQ && !st.xref_traj && !(flags & SOLVE_FORCE_GENERAL_FEATURES);
+        for (int j = 0; j < M::NX; ++j) topt = topt && !P.x_bounded[j];
+        if (topt) return launchSolveT<M, DEFECT, VT, MAXT, FeatTimeOpt>(P, st, iterations, T, blocks, stream);
+    }
     if (lean)
         launchSolveT<M, DEFECT, VT, MAXT, FeatLean>(P, st, iterations, T, blocks, stream);
     else

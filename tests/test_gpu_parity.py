@@ -678,3 +678,31 @@ def test_dt_equality_edges_match_the_checkers(oracle):
             assert err.max() <= 1e-3 and np.percentile(err, 90) <= 1e-4, (name, T, err.max())
             np.testing.assert_allclose(chi2, c_c, rtol=1e-4)
         lm.clear()
+
+
+@pytest.mark.parametrize("name,make", [
+    ("unicycle_timeopt", lambda: problems.unicycle_time_optimal(24)),
+    ("unicycle_timeopt_dteq", lambda: problems.unicycle_time_optimal(16, dt_eq_constraint=True)),
+    ("dint_timeopt", lambda: problems.make_ocp(grid=abi.GRID_FD_NONUNIFORM_VARDT, dynamics=abi.DYN_DOUBLE_INTEGRATOR, n_grid=14, dt=0.1,
+                                               stage_cost=abi.COST_MINIMUM_TIME_LSQ, u_lb=(-1.0,), u_ub=(1.0,), xf_fixed=(1, 0), dt_lb=0.0, dt_ub=1.0,
+                                               dyn_params=(1.0,))),
+], ids=["unicycle", "unicycle_dteq", "dint_partial_goal"])
+@pytest.mark.parametrize("threads", [1, 8], ids=["T1", "T8"])
+def test_time_optimal_feature_set_is_bit_identical_to_the_general_one(name, make, threads):
+    """Time-optimal structures without state bounds / final-stage constraint run a compile-time feature set of their own (FeatTimeOpt,
+    lm_device.cuh): it only removes code of absent features, so parameters, chi2 and statuses equal the general set's bit for bit"""
+    ocp = make()
+    B = 96
+    x0, xref = problems.instance_data(ocp, B, seed=21)
+    out = []
+    for general in (True, False):
+        lm = solver.BatchedLevenbergMarquardt(ocp, B)
+        lm.setIterations(8)
+        lm.set_threads_per_instance(threads)
+        lm.set_feature_set(general)
+        lm.set_problem_data(x0, xref)
+        lm.initialize_trajectories()
+        status, chi2 = lm.solve(new_run=True)
+        out.append((lm.get_params(), chi2, status))
+        lm.clear()
+    assert np.array_equal(out[0][0], out[1][0]) and np.array_equal(out[0][1], out[1][1]) and np.array_equal(out[0][2], out[1][2])
