@@ -367,7 +367,7 @@ def adaptive_config(device, with_cpu):
 
     try:
         ocp, kw, B = problems.config(2)
-        iterations, m, steps = kw["iterations"], 3, 4
+        iterations, m, steps = kw["iterations"], 3, 6
         rng = np.random.default_rng(77)
         r, ang = rng.uniform(0.5, 9.0, B), rng.uniform(-1.0, 1.0, B)
         x0 = np.zeros((B, 3))
@@ -378,13 +378,13 @@ def adaptive_config(device, with_cpu):
         ad.reserve()  # all buckets up front: a bucket allocates for the whole batch
         flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=f"cuda:{device}")
         total, n_hist = 0.0, []
-        for it in range(steps + 3):  # three warm-up steps: they also create the buckets the grids spread into
+        for it in range(steps + 5):  # five warm-up steps: the grids spread over their sizes first
             flush.zero_()
             torch.cuda.synchronize()
             t0 = time.perf_counter()
             u0, chi2, status, n = ad.step(x0 + 0.01 * it * (xf - x0), xf, num_ocp_iterations=m)
             dt = time.perf_counter() - t0
-            if it >= 3:
+            if it >= 5:
                 total += dt
             n_hist.append([int(n.min()), float(n.mean()), int(n.max())])
         stats = ad.statistics()
