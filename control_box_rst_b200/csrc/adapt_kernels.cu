@@ -25,13 +25,15 @@ namespace {
 
 __device__ __forceinline__ size_t tiled(int i, int slot, int nslots) { return ((size_t)(i >> 5) * nslots + slot) * 32 + (i & 31); }
 
-__global__ void adaptDecideKernel(const double* __restrict__ z0, const double* __restrict__ z1, const int* __restrict__ cur, int K, int nb, int nu,
-                                  int count, const int* __restrict__ inst_of_slot, double hi, double lo, int n_min, int n_max,
-                                  int* __restrict__ decision)
+// one thread per instance of the batch; the instance's current (bucket, slot) are rows 2 and 3 of the plan
+__global__ void adaptDecideKernel(const AdaptBucketView* __restrict__ views, const int* __restrict__ plan, int nx, int nu, int B, double hi,
+                                  double lo, int n_min, int n_max, int* __restrict__ decision)
 {
-    const int j = blockIdx.x * blockDim.x + threadIdx.x;
-    if (j >= count) return;
-    const double* src = cur[j] ? z1 : z0;
+    const int inst = blockIdx.x * blockDim.x + threadIdx.x;
+    if (inst >= B) return;
+    const AdaptBucketView b = views[plan[2 * B + inst]];
+    const int j = plan[3 * B + inst], K = b.K, nb = nu + 1 + nx;
+    const double* src = b.cur[j] ? b.z[1] : b.z[0];
     const int slots = K * nb, n = K + 1;
     int dec = ADAPT_NONE;
     for (int k = 0; k < K; ++k)
@@ -48,7 +50,7 @@ __global__ void adaptDecideKernel(const double* __restrict__ z0, const double* _
             break;
         }
     }
-    decision[inst_of_slot[j]] = dec;
+    decision[inst] = dec;
 }
 
 struct Source
@@ -154,6 +156,23 @@ __global__ void adaptScatterStartKernel(const AdaptBucketView* __restrict__ view
     }
 }
 
+// fixed goal components <- reference, both parameter buffers of every instance's slot (launchFillPinned for the whole batch at once)
+__global__ void adaptFillPinnedKernel(const AdaptBucketView* __restrict__ views, const int* __restrict__ plan, const double* __restrict__ xref_master,
+                                      unsigned mask, int nx, int nu, int B)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= B) return;
+    const AdaptBucketView b = views[plan[2 * B + i]];
+    const int slot = plan[3 * B + i], nb = nu + 1 + nx, slots = b.K * nb, slot0 = (b.K - 1) * nb + nu + 1;
+    for (int j = 0; j < nx; ++j)
+        if (mask & (1u << j))
+        {
+            const double v                      = xref_master[(size_t)i * nx + j];
+            b.z[0][tiled(slot, slot0 + j, slots)] = v;
+            b.z[1][tiled(slot, slot0 + j, slots)] = v;
+        }
+}
+
 // per-instance results in batch order: first control, chi2, status
 __global__ void adaptGatherKernel(const AdaptBucketView* __restrict__ views, const int* __restrict__ plan, int nx, int nu, double* __restrict__ u0,
                                   double* __restrict__ chi2, int* __restrict__ status, int B)
@@ -199,14 +218,14 @@ __global__ void adaptExportKernel(const AdaptBucketView* __restrict__ views, con
 //      state can be the neighbour of the next insertion, so the edits are a per-instance SCRIPT: the decision kernel derives it from
 //      (u, dt) alone -- states never influence it -- and reports the new grid size; the apply kernel replays it on the trajectory.
 //      One thread per instance for both: the scripts are sequential and a few dozen steps long.
-__global__ void adaptDecideRedundantKernel(const double* __restrict__ z0, const double* __restrict__ z1, const int* __restrict__ cur, int K, int nb,
-                                           int nu, int count, const int* __restrict__ inst_of_slot, double eps, int backup, int n_min, int n_max,
-                                           int* __restrict__ new_n, int* __restrict__ ops, int* __restrict__ nops)
+__global__ void adaptDecideRedundantKernel(const AdaptBucketView* __restrict__ views, const int* __restrict__ plan, int nx, int nu, int B, double eps,
+                                           int backup, int n_min, int n_max, int* __restrict__ new_n, int* __restrict__ ops, int* __restrict__ nops)
 {
-    const int j = blockIdx.x * blockDim.x + threadIdx.x;
-    if (j >= count) return;
-    const int inst    = inst_of_slot[j];
-    const double* src = cur[j] ? z1 : z0;
+    const int inst = blockIdx.x * blockDim.x + threadIdx.x;
+    if (inst >= B) return;
+    const AdaptBucketView b = views[plan[2 * B + inst]];
+    const int j = plan[3 * B + inst], K = b.K, nb = nu + 1 + nx;
+    const double* src = b.cur[j] ? b.z[1] : b.z[0];
     const int slots   = K * nb;
     int* my_ops       = ops + (size_t)inst * ADAPT_KMAX;
     int no = 0, n = K + 1;
@@ -337,11 +356,16 @@ __global__ void adaptApplyOpsKernel(const AdaptBucketView* __restrict__ views, c
 
 }  // namespace
 
-void launchAdaptDecide(const double* z0, const double* z1, const int* cur, int K, int nx, int nu, int count, const int* inst_of_slot, double hi,
-                       double lo, int n_min, int n_max, int* decision, cudaStream_t stream)
+void launchAdaptDecide(const AdaptBucketView* views, const int* plan, int nx, int nu, int B, double hi, double lo, int n_min, int n_max, int* decision,
+                       cudaStream_t stream)
 {
-    if (count <= 0) return;
-    adaptDecideKernel<<<(count + 127) / 128, 128, 0, stream>>>(z0, z1, cur, K, nu + 1 + nx, nu, count, inst_of_slot, hi, lo, n_min, n_max, decision);
+    adaptDecideKernel<<<(B + 127) / 128, 128, 0, stream>>>(views, plan, nx, nu, B, hi, lo, n_min, n_max, decision);
+}
+
+void launchAdaptFillPinned(const AdaptBucketView* views, const int* plan, const double* xref_master, unsigned mask, int nx, int nu, int B,
+                           cudaStream_t stream)
+{
+    if (mask) adaptFillPinnedKernel<<<(B + 127) / 128, 128, 0, stream>>>(views, plan, xref_master, mask, nx, nu, B);
 }
 
 void launchAdaptMigrate(const AdaptBucketView* views, const int* plan, double* x0_master, const double* xref_master, int nx, int nu, int keep_start,
@@ -372,12 +396,10 @@ void launchAdaptExport(const AdaptBucketView* views, const int* plan, const doub
 
 namespace b200sqp {
 
-void launchAdaptDecideRedundant(const double* z0, const double* z1, const int* cur, int K, int nx, int nu, int count, const int* inst_of_slot,
-                                double eps, int backup, int n_min, int n_max, int* new_n, int* ops, int* nops, cudaStream_t stream)
+void launchAdaptDecideRedundant(const AdaptBucketView* views, const int* plan, int nx, int nu, int B, double eps, int backup, int n_min, int n_max,
+                                int* new_n, int* ops, int* nops, cudaStream_t stream)
 {
-    if (count <= 0) return;
-    adaptDecideRedundantKernel<<<(count + 63) / 64, 64, 0, stream>>>(z0, z1, cur, K, nu + 1 + nx, nu, count, inst_of_slot, eps, backup, n_min, n_max,
-                                                                      new_n, ops, nops);
+    adaptDecideRedundantKernel<<<(B + 63) / 64, 64, 0, stream>>>(views, plan, nx, nu, B, eps, backup, n_min, n_max, new_n, ops, nops);
 }
 
 void launchAdaptApplyOps(const AdaptBucketView* views, const int* plan, const int* ops, const int* nops, double* scratch, const double* x0_master,

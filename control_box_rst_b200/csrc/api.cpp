@@ -1337,13 +1337,12 @@ struct b200sqp_adaptive
     double hyst = 0.1;
     int warm_start = 1;
     std::vector<b200sqp_handle> bucket;
-    std::vector<int> count, offset;          // occupied slots per bucket; start of the bucket's slice in d_inst_sorted
+    std::vector<int> count;                  // occupied slots per bucket
     std::vector<int> bucket_of, slot_of;     // per instance
     std::vector<AdaptBucketView> views;
     AdaptBucketView* d_views = nullptr;
     int *d_plan = nullptr, *hp_plan = nullptr;          // [5][B] (device / pinned host)
     int *d_decision = nullptr, *hp_decision = nullptr;  // [B]
-    int *d_inst_sorted = nullptr, *hp_inst_sorted = nullptr;  // [B] instance ids grouped by bucket, slot order
     double *d_x0_master = nullptr, *d_xref_master = nullptr, *d_u0 = nullptr, *d_chi2 = nullptr;
     int* d_status = nullptr;
     double *d_tx = nullptr, *d_tu = nullptr, *d_tdt = nullptr;  // trajectory export staging
@@ -1382,34 +1381,14 @@ int adaptiveEnsureBucket(b200sqp_adaptive* a, int idx)
     return B200SQP_OK;
 }
 
-// occupied buckets: offsets into the grouped instance list, and that list, from bucket_of / slot_of
-int adaptiveUploadGrouping(b200sqp_adaptive* a)
-{
-    int acc = 0;
-    for (size_t b = 0; b < a->count.size(); ++b)
-    {
-        a->offset[b] = acc;
-        acc += a->count[b];
-    }
-    for (int i = 0; i < a->B; ++i) a->hp_inst_sorted[a->offset[a->bucket_of[i]] + a->slot_of[i]] = i;
-    CUDA_TRY(cudaMemcpyAsync(a->d_inst_sorted, a->hp_inst_sorted, sizeof(int) * a->B, cudaMemcpyHostToDevice, a->stream));
-    return B200SQP_OK;
-}
-
 void adaptiveFillPinned(b200sqp_adaptive* a)
 {
     unsigned mask = 0;
     for (int i = 0; i < a->nx; ++i)
         if (a->ocp.xf_fixed[i]) mask |= 1u << i;
     if (!mask) return;
-    for (size_t b = 0; b < a->bucket.size(); ++b)
-        if (a->count[b] > 0)
-        {
-            b200sqp_handle h = a->bucket[b];
-            const int nb = h->s.nb, xo = h->s.nu + h->s.vt;
-            launchFillPinned(h->st.xref, h->st.z[0], h->st.z[1], (h->s.K - 1) * nb + xo, h->s.K * nb, h->s.nx, mask, a->count[b], a->stream);
-            a->launches += 1;
-        }
+    launchAdaptFillPinned(a->d_views, a->d_plan, a->d_xref_master, mask, a->nx, a->nu, a->B, a->stream);  // one launch for all buckets
+    a->launches += 1;
 }
 
 // NonUniformFiniteDifferencesVariableGrid::adaptGrid for every instance; *changed = any grid changed
@@ -1417,18 +1396,13 @@ int adaptiveAdapt(b200sqp_adaptive* a, bool* changed)
 {
     *changed        = false;
     const double hi = a->ocp.dt_ref * (1.0 + a->hyst), lo = a->ocp.dt_ref * (1.0 - a->hyst);
-    for (size_t b = 0; b < a->bucket.size(); ++b)
-        if (a->count[b] > 0)
-        {
-            b200sqp_handle h = a->bucket[b];
-            if (a->strategy == 1)  // d_decision receives the new grid size, d_ops / d_nops the edit script
-                launchAdaptDecideRedundant(h->st.z[0], h->st.z[1], h->st.cur, h->s.K, a->nx, a->nu, a->count[b], a->d_inst_sorted + a->offset[b],
-                                           a->redundant_epsilon, a->redundant_backup, a->n_min, a->n_max, a->d_decision, a->d_ops, a->d_nops, a->stream);
-            else
-                launchAdaptDecide(h->st.z[0], h->st.z[1], h->st.cur, h->s.K, a->nx, a->nu, a->count[b], a->d_inst_sorted + a->offset[b], hi, lo, a->n_min,
-                                  a->n_max, a->d_decision, a->stream);
-            a->launches += 1;
-        }
+    // one launch over the whole batch: every instance finds its bucket and slot through the plan
+    if (a->strategy == 1)  // d_decision receives the new grid size, d_ops / d_nops the edit script
+        launchAdaptDecideRedundant(a->d_views, a->d_plan, a->nx, a->nu, a->B, a->redundant_epsilon, a->redundant_backup, a->n_min, a->n_max,
+                                   a->d_decision, a->d_ops, a->d_nops, a->stream);
+    else
+        launchAdaptDecide(a->d_views, a->d_plan, a->nx, a->nu, a->B, hi, lo, a->n_min, a->n_max, a->d_decision, a->stream);
+    a->launches += 1;
     CUDA_TRY(cudaGetLastError());
     CUDA_TRY(cudaMemcpyAsync(a->hp_decision, a->d_decision, sizeof(int) * a->B, cudaMemcpyDeviceToHost, a->stream));
     CUDA_TRY(cudaStreamSynchronize(a->stream));
@@ -1483,9 +1457,7 @@ int adaptiveAdapt(b200sqp_adaptive* a, bool* changed)
         a->slot_of[i]   = a->hp_plan[3 * B + i];
     }
     a->count = new_count;
-    CUDA_TRY(cudaStreamSynchronize(a->stream));  // hp_plan / hp_inst_sorted are rewritten below and by the next call
-    int rc = adaptiveUploadGrouping(a);
-    if (rc) return rc;
+    CUDA_TRY(cudaStreamSynchronize(a->stream));  // hp_plan is rewritten by the next call
     adaptiveFillPinned(a);  // both parameter buffers of a slot carry the fixed goal components
     CUDA_TRY(cudaGetLastError());
     *changed = true;
@@ -1512,7 +1484,6 @@ int b200sqp_adaptive_create(const b200sqp_ocp* ocp, int32_t batch, int32_t devic
     const int nbuckets = a->n_hi - a->n_lo + 1;
     a->bucket.assign(nbuckets, nullptr);
     a->count.assign(nbuckets, 0);
-    a->offset.assign(nbuckets, 0);
     a->views.assign(nbuckets, AdaptBucketView{});
     a->bucket_of.assign(batch, ocp->n_grid - a->n_lo);
     a->slot_of.resize(batch);
@@ -1540,7 +1511,6 @@ int b200sqp_adaptive_create(const b200sqp_ocp* ocp, int32_t batch, int32_t devic
     A(&a->d_views, (size_t)nbuckets);
     A(&a->d_plan, (size_t)5 * batch);
     A(&a->d_decision, (size_t)batch);
-    A(&a->d_inst_sorted, (size_t)batch);
     A(&a->d_x0_master, (size_t)batch * a->nx);
     A(&a->d_xref_master, (size_t)batch * a->nx);
     A(&a->d_u0, (size_t)batch * a->nu);
@@ -1548,7 +1518,6 @@ int b200sqp_adaptive_create(const b200sqp_ocp* ocp, int32_t batch, int32_t devic
     A(&a->d_status, (size_t)batch);
     if (e == cudaSuccess) e = cudaMallocHost((void**)&a->hp_plan, sizeof(int) * 5 * batch);
     if (e == cudaSuccess) e = cudaMallocHost((void**)&a->hp_decision, sizeof(int) * batch);
-    if (e == cudaSuccess) e = cudaMallocHost((void**)&a->hp_inst_sorted, sizeof(int) * batch);
     if (e != cudaSuccess) return destroy_and_fail(B200SQP_ERR_CUDA, std::string("device allocation failed: ") + cudaGetErrorString(e));
     const int idx0 = ocp->n_grid - a->n_lo;
     int rc         = adaptiveEnsureBucket(a, idx0);  // also the check that the structure is in the registry
@@ -1565,7 +1534,6 @@ int b200sqp_adaptive_create(const b200sqp_ocp* ocp, int32_t batch, int32_t devic
         a->hp_plan[4 * batch + i]                          = 0;
     }
     e = cudaMemcpyAsync(a->d_plan, a->hp_plan, sizeof(int) * 5 * batch, cudaMemcpyHostToDevice, a->stream);
-    if (e == cudaSuccess) rc = adaptiveUploadGrouping(a);
     if (e == cudaSuccess && !rc) e = cudaStreamSynchronize(a->stream);
     if (e != cudaSuccess || rc) return destroy_and_fail(B200SQP_ERR_CUDA, "initial grouping upload failed");
     *out = a;
@@ -1581,7 +1549,6 @@ int b200sqp_adaptive_destroy(b200sqp_adaptive_handle a)
     for (void* p : a->allocations) cudaFree(p);
     if (a->hp_plan) cudaFreeHost(a->hp_plan);
     if (a->hp_decision) cudaFreeHost(a->hp_decision);
-    if (a->hp_inst_sorted) cudaFreeHost(a->hp_inst_sorted);
     if (a->ev_ready) cudaEventDestroy(a->ev_ready);
     if (a->stream) cudaStreamDestroy(a->stream);
     delete a;

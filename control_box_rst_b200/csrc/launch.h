@@ -100,14 +100,16 @@ void launchPeerWait(const unsigned long long* arrivals, int world, unsigned long
 // instance to (bucket, slot) of its new grid size, start-state scatter, result gather and trajectory export in batch order.
 // plan [5][B] device: source bucket, source slot, destination bucket, destination slot, decision (ADAPT_* | interval << 2)
 struct AdaptBucketView;
-void launchAdaptDecide(const double* z0, const double* z1, const int* cur, int K, int nx, int nu, int count, const int* inst_of_slot, double hi,
-                       double lo, int n_min, int n_max, int* decision, cudaStream_t);
+void launchAdaptDecide(const AdaptBucketView* views, const int* plan, int nx, int nu, int B, double hi, double lo, int n_min, int n_max, int* decision,
+                       cudaStream_t);
+// fixed goal components <- reference for every instance's slot (mask: bit j = component j of the goal is fixed)
+void launchAdaptFillPinned(const AdaptBucketView* views, const int* plan, const double* xref_master, unsigned mask, int nx, int nu, int B, cudaStream_t);
 void launchAdaptMigrate(const AdaptBucketView* views, const int* plan, double* x0_master, const double* xref_master, int nx, int nu, int keep_start,
                         int k_max, int B, cudaStream_t);
 // strategy adaptGridRedundantControls: per-instance edit script from (u, dt) + new grid size; replay on the trajectory while moving
 // (ops [B][ADAPT_KMAX], nops [B], scratch [B][(ADAPT_KMAX + 1) nx + ADAPT_KMAX (nu + 1)])
-void launchAdaptDecideRedundant(const double* z0, const double* z1, const int* cur, int K, int nx, int nu, int count, const int* inst_of_slot,
-                                double eps, int backup, int n_min, int n_max, int* new_n, int* ops, int* nops, cudaStream_t);
+void launchAdaptDecideRedundant(const AdaptBucketView* views, const int* plan, int nx, int nu, int B, double eps, int backup, int n_min, int n_max,
+                                int* new_n, int* ops, int* nops, cudaStream_t);
 void launchAdaptApplyOps(const AdaptBucketView* views, const int* plan, const int* ops, const int* nops, double* scratch, const double* x0_master,
                          const double* xref_master, int nx, int nu, int B, cudaStream_t);
 void launchAdaptScatterStart(const AdaptBucketView* views, const int* plan, const double* x0_master, const double* xref_master, int nx, int B,
