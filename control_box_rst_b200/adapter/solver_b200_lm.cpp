@@ -702,7 +702,11 @@ bool SolverB200Lm::solveUniform(const std::vector<OptimizationProblemInterface*>
         return false;
     }
     const int n = _dims.n_params, nx = _ocp.nx;
-    std::vector<double> x0((size_t)B * nx), xref((size_t)B * nx), params((size_t)B * n);
+    // staging buffers live in the solver object: a fresh 10 MB of zeroed pages per call costs more than the device time of the batch
+    std::vector<double>&x0 = _x0_buf, &xref = _xref_buf, &params = _params_buf;
+    x0.resize((size_t)B * nx);
+    xref.resize((size_t)B * nx);
+    params.resize((size_t)B * n);
     std::copy(x0_first.begin(), x0_first.end(), x0.begin());
     std::copy(xref_first.begin(), xref_first.end(), xref.begin());
     std::atomic<int> first_bad(B);
@@ -743,8 +747,10 @@ bool SolverB200Lm::solveUniform(const std::vector<OptimizationProblemInterface*>
             return false;
         }
     }
-    std::vector<int32_t> status(B);
-    std::vector<double> chi2(B);
+    std::vector<int32_t>& status = _status_buf;
+    std::vector<double>& chi2 = _chi2_buf;
+    status.resize(B);
+    chi2.resize(B);
     if (b200sqp_solve(_handle, &opts, 1, status.data(), chi2.data()) != 0 || b200sqp_get_params(_handle, params.data()) != 0)
     {
         fail(std::string("solve failed: ") + b200sqp_last_error());

@@ -117,6 +117,8 @@ class SolverB200Lm : public NlpSolverInterface
     // they survive a change of structure (a grid that was adapted between two solves of one run)
     double _w_eq = 0, _w_ineq = 0, _w_bounds = 0;
     bool _weights_initialised = false;
+    std::vector<double> _x0_buf, _xref_buf, _params_buf, _chi2_buf;  // host staging of a batch, reused across calls
+    std::vector<int32_t> _status_buf;
     std::map<int, std::shared_ptr<SolverB200Lm>> _by_size;  // buckets of a batch with mixed grid sizes, keyed by parameter dimension
 };
 
