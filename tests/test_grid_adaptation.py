@@ -126,3 +126,24 @@ def test_redundant_controls_restatement_matches_the_compiled_reference_bit_for_b
     xo, uo, dto, ops = ga.adapt_redundant_controls(x, u, dt, n_min, n_max, 1e-3, backup)
     assert xr.shape == xo.shape, (xr.shape, xo.shape, ops)
     assert np.array_equal(xr, xo) and np.array_equal(ur, uo) and np.array_equal(dtr, dto)
+
+
+def test_golden_fixture_of_the_adaptive_loop_is_what_the_compiled_reference_answers(reference):
+    """tests/golden/grid_adaptation.npz (made by tests/golden/make_grid_adaptation.py) is what the GPU tests fall back to where the compiled
+    reference did not travel: spot-check it against the live reference"""
+    import os
+    import sys
+
+    sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+    import test_gpu_grid_adaptation as T
+
+    g = np.load(T.GOLDEN)
+    for name, warm, redundant in (("vdp10", True, None), ("unicycle16", False, T.REDUNDANT)):
+        ocp, opts, x0_seq, xf, n_min, n_max, hyst = T._inputs(name)
+        stored = T._unpack(T._key(name, warm, redundant), g)
+        for i in (0, 7, 23):
+            live = bindings.isolated(lambda: reference.adaptive_steps(ocp, opts, x0_seq[:, i], xf[i], n_min, n_max, hyst, warm, T.M, redundant_controls=redundant))
+            assert (live is None) == (stored[i] is None)
+            if live is not None:
+                assert np.array_equal(live[0][:, -1], stored[i][0][:, -1]) and np.array_equal(live[1], stored[i][1])
+                assert np.array_equal(live[2], stored[i][2]) and np.array_equal(live[4], stored[i][4])
