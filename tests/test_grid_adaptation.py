@@ -147,3 +147,80 @@ def test_golden_fixture_of_the_adaptive_loop_is_what_the_compiled_reference_answ
             if live is not None:
                 assert np.array_equal(live[0][:, -1], stored[i][0][:, -1]) and np.array_equal(live[1], stored[i][1])
                 assert np.array_equal(live[2], stored[i][2]) and np.array_equal(live[4], stored[i][4])
+
+
+def _pack_params(ocp, x, u, dt, idx):
+    """trajectory -> parameter vector of `ocp` (n_grid = len(x)); start and goal state fully fixed (not parameters)"""
+    x_idx, u_idx, dt_idx = idx
+    p = np.zeros(solver.dims_of(ocp).n_params)
+    for k in range(len(x)):
+        if x_idx[k] >= 0:
+            p[x_idx[k]:x_idx[k] + ocp.nx] = x[k]
+    for k in range(len(u)):
+        p[u_idx[k]:u_idx[k] + ocp.nu] = u[k]
+        p[dt_idx[k]] = dt[k]
+    return p
+
+
+def _unpack_params(ocp, p, x_start, x_goal, idx):
+    x_idx, u_idx, dt_idx = idx
+    N = ocp.n_grid
+    x = np.array([p[x_idx[k]:x_idx[k] + ocp.nx] if x_idx[k] >= 0 else (x_start if k == 0 else x_goal) for k in range(N)])
+    u = np.array([p[u_idx[k]:u_idx[k] + ocp.nu] for k in range(N - 1)])
+    dt = np.array([p[dt_idx[k]] for k in range(N - 1)])
+    return x, u, dt
+
+
+@pytest.mark.parametrize("name", ["vdp10", "unicycle16"])
+def test_cpu_restatement_of_the_whole_adaptive_loop_follows_the_reference(oracle, name):
+    """The adaptive controller step restated end to end on the CPU -- LM solves by the oracle (oracle/sqp_oracle.cpp) on the grid of the
+    moment, grid adaptation by oracle/grid_adaptation.py, the weights reset / adapted like LevenbergMarquardtSparse does -- reproduces the
+    compiled reference's grid sizes, first controls and final trajectories (golden fixture) for the warm-started time-based strategy."""
+    import os
+    import sys
+
+    sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+    import test_gpu_grid_adaptation as T
+
+    ocp0, opts, x0_seq, xf, n_min, n_max, hyst = T._inputs(name)
+    stored = T._unpack(T._key(name, True, None), np.load(T.GOLDEN))
+    checked = 0
+    for i in range(0, T.B, 3):
+        if stored[i] is None:
+            continue
+        x = u = dt = None
+        n_after, u0s, undefined = [], [], False
+        w = None
+        for s in range(T.STEPS):
+            for it in range(T.M):
+                new_run = it == 0
+                if x is not None and not new_run:
+                    kind, at = ga.decide(dt, n_min, n_max, ocp0.dt_ref, hyst)
+                    undefined = undefined or (kind != ga.NONE and at == len(dt) - 1)  # the reference indexes past its vectors there
+                    x, u, dt, _, _ = ga.adapt_time_based_single_step(x, u, dt, n_min, n_max, ocp0.dt_ref, hyst)
+                ocp = type(ocp0).from_buffer_copy(ocp0)
+                if x is not None:
+                    ocp.n_grid = len(x)
+                idx = solver.vertex_indices(ocp)
+                if x is None:  # first run: initializeSequences
+                    x, u, dt = _unpack_params(ocp, oracle.initial_params(ocp, x0_seq[s, i], xf[i]), x0_seq[s, i], xf[i], idx)
+                if new_run:
+                    x[0] = x0_seq[s, i]
+                    w = [opts.weight_eq, opts.weight_ineq, opts.weight_bounds]
+                else:
+                    w = [min(w[0] * opts.adapt_factor_eq, opts.adapt_max_eq), min(w[1] * opts.adapt_factor_ineq, opts.adapt_max_ineq),
+                         min(w[2] * opts.adapt_factor_bounds, opts.adapt_max_bounds)]
+                o = abi.LmOptions.defaults(iterations=opts.iterations, weights=tuple(w))
+                p, _, _, _ = oracle.solve_batch(ocp, o, x[0][None, :], xf[i][None, :], _pack_params(ocp, x, u, dt, idx)[None, :])
+                x, u, dt = _unpack_params(ocp, p[0], x[0], xf[i], idx)
+            n_after.append(len(x))
+            u0s.append(u[0].copy())
+        if undefined:
+            continue
+        n_ref, u0_ref, x_ref, u_ref, dt_ref = stored[i]
+        assert n_after == [int(v) for v in n_ref[:, -1]], (name, i, n_after, n_ref[:, -1])
+        tol = 2e-4 if name.startswith("unicycle") else 1e-6
+        assert np.abs(np.array(u0s) - u0_ref).max() <= tol and np.abs(x - x_ref).max() <= tol * max(1.0, np.abs(x_ref).max())
+        assert np.abs(dt - dt_ref).max() <= tol
+        checked += 1
+    assert checked >= 4
