@@ -224,3 +224,26 @@ def test_cpu_restatement_of_the_whole_adaptive_loop_follows_the_reference(oracle
         assert np.abs(dt - dt_ref).max() <= tol
         checked += 1
     assert checked >= 4
+
+
+@pytest.mark.parametrize("seed", range(40))
+def test_time_based_restatement_on_random_trajectories(reference, seed):
+    """adaptGridTimeBasedSingleStep on random dt profiles around the thresholds (values at, one ulp beside and far from
+    dt_ref (1 +- hyst)), random grid sizes and n_min / n_max stops -- bit for bit against the compiled reference.  Profiles whose decision
+    falls on the last interval are skipped: the reference indexes past the end of its vectors there."""
+    rng = np.random.default_rng(500 + seed)
+    N = int(rng.integers(3, 16))
+    dt_ref, hyst = 0.1, float(rng.choice([0.05, 0.1, 0.25]))
+    hi, lo = dt_ref * (1.0 + hyst), dt_ref * (1.0 - hyst)
+    pool = [dt_ref, hi, lo, np.nextafter(hi, 1.0), np.nextafter(lo, 0.0), np.nextafter(hi, 0.0), np.nextafter(lo, 1.0), 0.5 * dt_ref, 2.0 * dt_ref]
+    dt = np.array([rng.choice(pool) if rng.uniform() < 0.5 else dt_ref * rng.uniform(0.8, 1.2) for _ in range(N - 1)])
+    n_min = int(rng.integers(2, N + 1))
+    n_max = int(rng.integers(N, N + 3))
+    kind, at = ga.decide(dt, n_min, n_max, dt_ref, hyst)
+    if kind != ga.NONE and at == N - 2:
+        pytest.skip("decision on the last interval: undefined in the reference")
+    ocp = problems.unicycle_time_optimal(N, dt_ref)
+    x, u = rng.uniform(-1, 1, (N, 3)), rng.uniform(-1, 1, (N - 1, 2))
+    xr, ur, dtr = reference.adapt_once(ocp, x, u, dt, n_min, n_max, hyst)
+    xo, uo, dto, _, _ = ga.adapt_time_based_single_step(x, u, dt, n_min, n_max, dt_ref, hyst)
+    assert xr.shape == xo.shape and np.array_equal(xr, xo) and np.array_equal(ur, uo) and np.array_equal(dtr, dto)
