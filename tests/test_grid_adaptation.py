@@ -101,7 +101,7 @@ def test_adaptive_front_end_checks_arguments_and_needs_a_device():
         assert e.value.code == abi.ERR_NO_DEVICE  # no CPU fallback
 
 
-@pytest.mark.parametrize("seed", range(12))
+@pytest.mark.parametrize("seed", range(48))
 def test_redundant_controls_restatement_matches_the_compiled_reference_bit_for_bit(reference, seed):
     """adaptGridRedundantControls on random trajectories with plateaus in the controls and a few vanishing dts: every combination of
     surplus (removals from the back), deficit (halving the largest interval, repeatedly) and the n_min / n_max stops"""
